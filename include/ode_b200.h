@@ -1,0 +1,170 @@
+/*
+ * ode_b200.h -- C-ABI of the B200-native ODE step path (batch entry points).
+ *
+ * Boundary: plain C, pointers and sizes only, no torch / CUDA types.  One shared library per
+ * precision, like the reference (libode_b200_single.so: odeb_real == float,
+ * libode_b200_double.so: odeb_real == double; reference: include/ode/precision.h.in:9-15,
+ * include/ode/common.h:56-65).
+ *
+ * The reference steps ONE world through
+ *     dSpaceCollide(space, data, &nearCallback)      include/ode/collision_space.h:49-64
+ *     dWorldQuickStep(world, h)                      include/ode/objects.h:419-425
+ *     dJointGroupEmpty(contactgroup)                 include/ode/objects.h:1720 (ode.cpp:1325)
+ * with user code (the near-callback, ode/demo/demo_boxstack.cpp:131-176) in the middle.  These entry
+ * points step W independent worlds of identical topology with that whole sequence resident on the
+ * GPU; the near-callback is replaced by the declarative contact policy in OdebWorldParams (the same
+ * fields a callback fills into dSurfaceParameters, include/ode/contact.h:55-103).
+ *
+ * The classic per-object API (dWorldCreate/dBodyCreate/dJointCreateContact/dSpaceCollide/
+ * dWorldQuickStep ...) is declared in include/ode_b200_classic.h and layered on the same kernels.
+ *
+ * The structs below are also read by oracle/ (test infrastructure) so that reference, oracle and
+ * CUDA path are fed byte-identical scene descriptions.
+ */
+#ifndef ODE_B200_H
+#define ODE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(ODEB_DOUBLE)
+typedef double odeb_real;
+#else
+typedef float odeb_real;
+#endif
+
+/* geom classes: numbering of the reference (include/ode/collision.h:881-902) */
+enum { ODEB_SPHERE = 0, ODEB_BOX = 1, ODEB_CAPSULE = 2, ODEB_PLANE = 4 };
+/* joint types: numbering of the reference dJointType (include/ode/common.h:406-426) */
+enum { ODEB_JOINT_BALL = 1, ODEB_JOINT_HINGE = 2, ODEB_JOINT_CONTACT = 4, ODEB_JOINT_UNIVERSAL = 5 };
+/* broadphase flavours: which reference space's callback stream is reproduced (as a set) */
+enum { ODEB_SPACE_HASH = 0, ODEB_SPACE_SAP = 1 };
+
+/* contact surface mode bits: include/ode/contact.h:34-52 */
+enum {
+    ODEB_CONTACT_MU2 = 0x001, ODEB_CONTACT_FDIR1 = 0x002, ODEB_CONTACT_BOUNCE = 0x004,
+    ODEB_CONTACT_SOFT_ERP = 0x008, ODEB_CONTACT_SOFT_CFM = 0x010, ODEB_CONTACT_MOTION1 = 0x020,
+    ODEB_CONTACT_MOTION2 = 0x040, ODEB_CONTACT_MOTIONN = 0x080, ODEB_CONTACT_SLIP1 = 0x100,
+    ODEB_CONTACT_SLIP2 = 0x200, ODEB_CONTACT_APPROX1_1 = 0x1000, ODEB_CONTACT_APPROX1_2 = 0x2000,
+    ODEB_CONTACT_APPROX1 = 0x7000
+};
+
+/* body flag bits a scene may set (ode/src/objects.h:72-87 keeps these internal; meaning identical) */
+enum {
+    ODEB_BODY_NO_GRAVITY = 1, ODEB_BODY_NO_GYRO = 2, ODEB_BODY_DISABLED = 4,
+    ODEB_BODY_FINITE_ROTATION = 8
+};
+
+/* World-level parameters (dWorldSet*; defaults ode/src/objects.cpp:37-121) + the contact policy. */
+typedef struct OdebWorldParams {
+    double gravity[3];          /* dWorldSetGravity */
+    double erp;                 /* dWorldSetERP, default 0.2 */
+    double cfm;                 /* dWorldSetCFM; < 0 selects the precision default 1e-5 / 1e-10 */
+    int    num_iterations;      /* dWorldSetQuickStepNumIterations, default 20 */
+    double sor_w;               /* dWorldSetQuickStepW, default 1.3 */
+    double premature_exit_delta;/* dWorldSetQuickStepDynamicIterationParameters, default 1e-8 */
+    double max_extra_factor;    /*   "   default 1.0 */
+    double extra_iter_delta;    /*   "   default 1e-2 */
+    double contact_max_vel;     /* dWorldSetContactMaxCorrectingVel, default +inf */
+    double contact_surface_layer;/* dWorldSetContactSurfaceLayer, default 0 */
+    int    auto_disable;        /* dWorldSetAutoDisableFlag */
+    double adis_linear_thr;     /* dWorldSetAutoDisableLinearThreshold (speed, not squared), default 0.01 */
+    double adis_angular_thr;    /* dWorldSetAutoDisableAngularThreshold, default 0.01 */
+    int    adis_steps;          /* dWorldSetAutoDisableSteps, default 10 */
+    double adis_time;           /* dWorldSetAutoDisableTime, default 0 */
+    int    adis_samples;        /* dWorldSetAutoDisableAverageSamplesCount, default 1 */
+    double linear_damping;      /* dWorldSetLinearDamping, default 0 */
+    double angular_damping;     /* dWorldSetAngularDamping, default 0 */
+    double linear_damping_thr;  /* dWorldSetLinearDampingThreshold, default 0.01 */
+    double angular_damping_thr; /* dWorldSetAngularDampingThreshold, default 0.01 */
+    double max_angular_speed;   /* dWorldSetMaxAngularSpeed, default +inf */
+    /* --- contact policy: what the reference's near-callback does (demo_boxstack.cpp:131-176) */
+    int    space_type;          /* ODEB_SPACE_HASH | ODEB_SPACE_SAP */
+    int    max_contacts;        /* dCollide flags & NUMC_MASK, 1..8 */
+    int    skip_connected;      /* if both bodies: dAreConnectedExcluding(b1,b2,dJointTypeContact) -> skip */
+    int    surf_mode;           /* dSurfaceParameters.mode */
+    double mu, mu2, bounce, bounce_vel, soft_erp, soft_cfm;
+    double motion1, motion2, motionN, slip1, slip2;
+} OdebWorldParams;
+
+typedef struct OdebBodyDesc {
+    double mass;                /* dMass.mass */
+    double inertia[9];          /* dMass.I, 3x3 row-major about the centre of mass (c == 0) */
+    int    flags;               /* ODEB_BODY_* */
+} OdebBodyDesc;
+
+typedef struct OdebGeomDesc {
+    int    type;                /* ODEB_SPHERE: p[0]=radius; ODEB_BOX: p[0..2]=side lengths;
+                                   ODEB_CAPSULE: p[0]=radius, p[1]=length; ODEB_PLANE: p[0..3]=a,b,c,d */
+    int    body;                /* body index in the world, -1 = static (dGeomSetBody not called) */
+    double p[4];
+    uint32_t category_bits, collide_bits; /* dGeomSetCategoryBits / dGeomSetCollideBits */
+} OdebGeomDesc;
+
+typedef struct OdebJointDesc {
+    int    type;                /* ODEB_JOINT_BALL | ODEB_JOINT_HINGE | ODEB_JOINT_UNIVERSAL */
+    int    body1, body2;        /* dJointAttach(j, body1, body2); -1 = the static environment */
+    double anchor[3];           /* dJointSet*Anchor, world frame at the template pose */
+    double axis1[3], axis2[3];  /* dJointSetHingeAxis / dJointSetUniversalAxis1,2 */
+    double lo_stop[2], hi_stop[2]; /* dParamLoStop/HiStop (axis 1, axis 2); defaults -inf/+inf */
+    double vel[2], fmax[2];     /* dParamVel, dParamFMax; default 0 */
+    double fudge_factor[2], bounce[2], stop_erp[2], stop_cfm[2]; /* <0 = keep defaults */
+} OdebJointDesc;
+
+/* per-world counters of dWorldQuickStepIterationCount_DynamicAdjustmentStatistics
+ * (include/ode/objects.h:538-576): iteration_count, premature_exits, prolonged_execs, full_extra_execs */
+typedef struct OdebStats { uint32_t v[4]; } OdebStats;
+
+typedef struct OdebBatch OdebBatch;
+
+/* Create W worlds from one template. The template pose is body_pos/body_quat ([nbody][3], [nbody][4],
+ * doubles); joint anchors/axes are bound at that pose exactly as dJointSet*Anchor/Axis would.
+ * Returns NULL on failure (message via odeb_last_error). Fails loudly when no CUDA device is present. */
+OdebBatch *odeb_create(const OdebWorldParams *wp,
+                       int nbody, const OdebBodyDesc *bodies, const double *body_pos, const double *body_quat,
+                       int ngeom, const OdebGeomDesc *geoms,
+                       int njoint, const OdebJointDesc *joints,
+                       int nworlds, int device);
+void odeb_destroy(OdebBatch *);
+const char *odeb_last_error(void);
+
+/* bulk state, host buffers laid out [world][body][3|4] in odeb_real. NULL pointers are skipped.
+ * Setting a quaternion normalises it and rebuilds R like dBodySetQuaternion (ode.cpp:330-343). */
+int odeb_set_state(OdebBatch *, const odeb_real *pos, const odeb_real *quat, const odeb_real *lvel, const odeb_real *avel);
+int odeb_get_state(OdebBatch *, odeb_real *pos, odeb_real *quat, odeb_real *lvel, odeb_real *avel);
+/* dBodyAddForce / dBodyAddTorque for every body: added to the accumulators consumed by the next step */
+int odeb_add_force(OdebBatch *, const odeb_real *force, const odeb_real *torque);
+/* per-world dRandSetSeed / dRandGetSeed (ode/src/misc.cpp:52-61) */
+int odeb_set_seeds(OdebBatch *, const uint32_t *seeds);
+int odeb_get_seeds(OdebBatch *, uint32_t *seeds);
+int odeb_get_enabled(OdebBatch *, int *enabled /* [world][body] */);
+
+/* nsteps x { dSpaceCollide + contact policy ; dWorldQuickStep(h) ; dJointGroupEmpty }.
+ * Returns 1 on success, 0 on failure (like dWorldQuickStep), state untouched on allocation failure. */
+int odeb_step(OdebBatch *, double h, int nsteps);
+/* same, asynchronous on the batch's stream; pair with odeb_sync */
+int odeb_step_async(OdebBatch *, double h, int nsteps);
+int odeb_sync(OdebBatch *);
+/* number of kernel launches issued by this batch so far */
+uint64_t odeb_launch_count(const OdebBatch *);
+/* device-side duration (ms) of the solver kernel launches accumulated since the last call; resets */
+double odeb_solver_ms(OdebBatch *, int *launches);
+void   odeb_enable_timing(OdebBatch *, int on);
+
+/* observables of the most recent step, one world at a time (parity tests).
+ * pairs: (geomA, geomB) in callback order; contacts: [pos3, normal3, depth] + (g1, g2);
+ * islands: label per body (-1 = not stepped), labels numbered in processing order. */
+int odeb_get_pairs(OdebBatch *, int world, int *pairs, int cap);
+int odeb_get_contacts(OdebBatch *, int world, odeb_real *geom7, int *g12, int cap);
+int odeb_get_islands(OdebBatch *, int world, int *label_per_body);
+int odeb_get_stats(OdebBatch *, int world, OdebStats *out);
+/* totals over all worlds for the most recent step: [pairs, contacts, rows, islands, sweeps(sum over islands)] */
+int odeb_get_totals(OdebBatch *, uint64_t out[5]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

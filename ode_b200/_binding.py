@@ -1,0 +1,308 @@
+"""ctypes mirror of include/ode_b200.h.
+
+`SceneLib` binds one shared library exporting the scene-description C interface under a symbol
+prefix.  The product library uses the prefix ``odeb_`` (ode_b200/csrc, CUDA).  The same class is
+reused by tests/ and bench.py's cpu_baseline leg to drive the checkers under oracle/ (prefixes
+``ref_`` and ``orc_``) -- the package itself never opens anything under oracle/.
+"""
+import ctypes as C
+import numpy as np
+
+c_double3 = C.c_double * 3
+
+
+class OdebWorldParams(C.Structure):
+    _fields_ = [
+        ("gravity", C.c_double * 3), ("erp", C.c_double), ("cfm", C.c_double),
+        ("num_iterations", C.c_int), ("sor_w", C.c_double),
+        ("premature_exit_delta", C.c_double), ("max_extra_factor", C.c_double), ("extra_iter_delta", C.c_double),
+        ("contact_max_vel", C.c_double), ("contact_surface_layer", C.c_double),
+        ("auto_disable", C.c_int), ("adis_linear_thr", C.c_double), ("adis_angular_thr", C.c_double),
+        ("adis_steps", C.c_int), ("adis_time", C.c_double), ("adis_samples", C.c_int),
+        ("linear_damping", C.c_double), ("angular_damping", C.c_double),
+        ("linear_damping_thr", C.c_double), ("angular_damping_thr", C.c_double),
+        ("max_angular_speed", C.c_double),
+        ("space_type", C.c_int), ("max_contacts", C.c_int), ("skip_connected", C.c_int), ("surf_mode", C.c_int),
+        ("mu", C.c_double), ("mu2", C.c_double), ("bounce", C.c_double), ("bounce_vel", C.c_double),
+        ("soft_erp", C.c_double), ("soft_cfm", C.c_double),
+        ("motion1", C.c_double), ("motion2", C.c_double), ("motionN", C.c_double),
+        ("slip1", C.c_double), ("slip2", C.c_double),
+    ]
+
+
+class OdebBodyDesc(C.Structure):
+    _fields_ = [("mass", C.c_double), ("inertia", C.c_double * 9), ("flags", C.c_int)]
+
+
+class OdebGeomDesc(C.Structure):
+    _fields_ = [("type", C.c_int), ("body", C.c_int), ("p", C.c_double * 4),
+                ("category_bits", C.c_uint32), ("collide_bits", C.c_uint32)]
+
+
+class OdebJointDesc(C.Structure):
+    _fields_ = [("type", C.c_int), ("body1", C.c_int), ("body2", C.c_int),
+                ("anchor", C.c_double * 3), ("axis1", C.c_double * 3), ("axis2", C.c_double * 3),
+                ("lo_stop", C.c_double * 2), ("hi_stop", C.c_double * 2),
+                ("vel", C.c_double * 2), ("fmax", C.c_double * 2),
+                ("fudge_factor", C.c_double * 2), ("bounce", C.c_double * 2),
+                ("stop_erp", C.c_double * 2), ("stop_cfm", C.c_double * 2)]
+
+
+class OdebStats(C.Structure):
+    _fields_ = [("v", C.c_uint32 * 4)]
+
+
+SPHERE, BOX, CAPSULE, PLANE = 0, 1, 2, 4
+JOINT_BALL, JOINT_HINGE, JOINT_CONTACT, JOINT_UNIVERSAL = 1, 2, 4, 5
+SPACE_HASH, SPACE_SAP = 0, 1
+CONTACT_MU2, CONTACT_BOUNCE, CONTACT_SOFT_ERP, CONTACT_SOFT_CFM = 0x001, 0x004, 0x008, 0x010
+CONTACT_MOTION1, CONTACT_MOTION2, CONTACT_MOTIONN = 0x020, 0x040, 0x080
+CONTACT_SLIP1, CONTACT_SLIP2, CONTACT_APPROX1 = 0x100, 0x200, 0x7000
+BODY_NO_GRAVITY, BODY_NO_GYRO, BODY_DISABLED, BODY_FINITE_ROTATION = 1, 2, 4, 8
+INF = float("inf")
+
+
+def default_world_params(**kw):
+    """World defaults of the reference (ode/src/objects.cpp:37-121, include/ode/objects.h:451-475)."""
+    p = OdebWorldParams()
+    p.gravity[:] = (0.0, 0.0, 0.0)
+    p.erp, p.cfm = 0.2, -1.0
+    p.num_iterations, p.sor_w = 20, 1.3
+    p.premature_exit_delta, p.max_extra_factor, p.extra_iter_delta = 1e-8, 1.0, 1e-2
+    p.contact_max_vel, p.contact_surface_layer = INF, 0.0
+    p.auto_disable, p.adis_linear_thr, p.adis_angular_thr = 0, 0.01, 0.01
+    p.adis_steps, p.adis_time, p.adis_samples = 10, 0.0, 1
+    p.linear_damping = p.angular_damping = 0.0
+    p.linear_damping_thr = p.angular_damping_thr = 0.01
+    p.max_angular_speed = INF
+    p.space_type, p.max_contacts, p.skip_connected, p.surf_mode = SPACE_HASH, 4, 1, 0
+    p.mu, p.mu2 = INF, 0.0
+    for k, v in kw.items():
+        if k == "gravity":
+            p.gravity[:] = v
+        else:
+            if not hasattr(p, k):
+                raise AttributeError(k)
+            setattr(p, k, v)
+    return p
+
+
+class Scene:
+    """A template world + per-world initial state; consumed identically by every implementation."""
+
+    def __init__(self, wp, nworlds=1):
+        self.wp = wp
+        self.nworlds = nworlds
+        self.bodies, self.body_pos, self.body_quat = [], [], []
+        self.geoms, self.joints = [], []
+        self.state = None  # optional dict(pos, quat, lvel, avel) of [W][NB][k] float64
+        self.seeds = None
+
+    def add_body(self, mass, inertia, pos, quat=(1, 0, 0, 0), flags=0):
+        d = OdebBodyDesc()
+        d.mass = mass
+        d.inertia[:] = np.asarray(inertia, dtype=np.float64).reshape(9)
+        d.flags = flags
+        self.bodies.append(d)
+        self.body_pos.append(tuple(float(x) for x in pos))
+        self.body_quat.append(tuple(float(x) for x in quat))
+        return len(self.bodies) - 1
+
+    def add_geom(self, gtype, params, body=-1, category=0xFFFFFFFF, collide=0xFFFFFFFF):
+        g = OdebGeomDesc()
+        g.type, g.body = gtype, body
+        pp = list(params) + [0.0] * (4 - len(params))
+        g.p[:] = pp
+        g.category_bits, g.collide_bits = category, collide
+        self.geoms.append(g)
+        return len(self.geoms) - 1
+
+    def add_joint(self, jtype, body1, body2, anchor, axis1=(1, 0, 0), axis2=(0, 1, 0),
+                  lo_stop=(-INF, -INF), hi_stop=(INF, INF), vel=(0, 0), fmax=(0, 0),
+                  fudge_factor=(-1, -1), bounce=(-1, -1), stop_erp=(-1, -1), stop_cfm=(-1, -1)):
+        j = OdebJointDesc()
+        j.type, j.body1, j.body2 = jtype, body1, body2
+        j.anchor[:] = anchor
+        j.axis1[:] = axis1
+        j.axis2[:] = axis2
+        j.lo_stop[:] = lo_stop
+        j.hi_stop[:] = hi_stop
+        j.vel[:] = vel
+        j.fmax[:] = fmax
+        j.fudge_factor[:] = fudge_factor
+        j.bounce[:] = bounce
+        j.stop_erp[:] = stop_erp
+        j.stop_cfm[:] = stop_cfm
+        self.joints.append(j)
+        return len(self.joints) - 1
+
+    @property
+    def nbody(self):
+        return len(self.bodies)
+
+    @property
+    def ngeom(self):
+        return len(self.geoms)
+
+
+def box_mass(density, lx, ly, lz):
+    m = density * lx * ly * lz
+    return m, np.diag([m / 12.0 * (ly * ly + lz * lz), m / 12.0 * (lx * lx + lz * lz), m / 12.0 * (lx * lx + ly * ly)])
+
+
+def sphere_mass(density, r):
+    m = 4.0 / 3.0 * np.pi * r ** 3 * density
+    return m, np.eye(3) * (0.4 * m * r * r)
+
+
+def capsule_mass(density, r, length):
+    """dMassSetCapsule along z (ode/src/mass.cpp:138-166), direction = 3."""
+    M1 = np.pi * r * r * length * density
+    M2 = 4.0 / 3.0 * np.pi * r ** 3 * density
+    m = M1 + M2
+    Ia = M1 * (0.25 * r * r + length * length / 12.0) + M2 * (0.4 * r * r + 0.375 * r * length + 0.25 * length * length)
+    Ib = (M1 * 0.5 + M2 * 0.4) * r * r
+    return m, np.diag([Ia, Ia, Ib])
+
+
+class SceneLib:
+    """One loaded library + symbol prefix."""
+
+    def __init__(self, path, prefix, real):
+        self.lib = C.CDLL(path)
+        self.prefix = prefix
+        self.real = np.dtype(real)
+        self.path = path
+        f = self._fn("create")
+        f.restype = C.c_void_p
+        f.argtypes = [C.POINTER(OdebWorldParams), C.c_int, C.POINTER(OdebBodyDesc), C.POINTER(C.c_double),
+                      C.POINTER(C.c_double), C.c_int, C.POINTER(OdebGeomDesc), C.c_int, C.POINTER(OdebJointDesc),
+                      C.c_int, C.c_int]
+        self._fn("destroy").argtypes = [C.c_void_p]
+        self._fn("destroy").restype = None
+        for name in ("set_state", "get_state"):
+            self._fn(name).argtypes = [C.c_void_p] + [C.c_void_p] * 4
+        self._fn("add_force").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        for name in ("set_seeds", "get_seeds", "get_enabled"):
+            self._fn(name).argtypes = [C.c_void_p, C.c_void_p]
+        self._fn("step").argtypes = [C.c_void_p, C.c_double, C.c_int]
+        self._fn("get_pairs").argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        self._fn("get_contacts").argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        self._fn("get_islands").argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        self._fn("get_stats").argtypes = [C.c_void_p, C.c_int, C.POINTER(OdebStats)]
+
+    def _fn(self, name):
+        return getattr(self.lib, self.prefix + name)
+
+    def has(self, name):
+        return hasattr(self.lib, self.prefix + name)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Batch:
+    """W worlds built from a Scene on one implementation."""
+
+    def __init__(self, slib, scene, device=0):
+        self.slib, self.scene = slib, scene
+        nb, ng, nj = scene.nbody, scene.ngeom, len(scene.joints)
+        bodies = (OdebBodyDesc * max(nb, 1))(*scene.bodies)
+        geoms = (OdebGeomDesc * max(ng, 1))(*scene.geoms)
+        joints = (OdebJointDesc * max(nj, 1))(*scene.joints)
+        pos = np.ascontiguousarray(np.asarray(scene.body_pos, dtype=np.float64).reshape(-1))
+        quat = np.ascontiguousarray(np.asarray(scene.body_quat, dtype=np.float64).reshape(-1))
+        self._keep = (bodies, geoms, joints, pos, quat)
+        self.h = slib._fn("create")(C.byref(scene.wp), nb, bodies, pos.ctypes.data_as(C.POINTER(C.c_double)),
+                                    quat.ctypes.data_as(C.POINTER(C.c_double)), ng, geoms, nj, joints,
+                                    scene.nworlds, device)
+        if not self.h:
+            msg = ""
+            if slib.has("last_error"):
+                fn = slib._fn("last_error")
+                fn.restype = C.c_char_p
+                msg = (fn() or b"").decode()
+            raise RuntimeError("%screate failed: %s" % (slib.prefix, msg))
+        self.W, self.NB = scene.nworlds, nb
+        if scene.state is not None:
+            self.set_state(**scene.state)
+        if scene.seeds is not None:
+            self.set_seeds(scene.seeds)
+
+    def close(self):
+        if self.h:
+            self.slib._fn("destroy")(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _arr(self, a, k):
+        if a is None:
+            return None
+        a = np.ascontiguousarray(np.asarray(a, dtype=self.slib.real).reshape(self.W, self.NB, k))
+        return a
+
+    def set_state(self, pos=None, quat=None, lvel=None, avel=None):
+        arrs = [self._arr(pos, 3), self._arr(quat, 4), self._arr(lvel, 3), self._arr(avel, 3)]
+        self.slib._fn("set_state")(self.h, *[_ptr(a) for a in arrs])
+
+    def get_state(self):
+        r = self.slib.real
+        pos = np.empty((self.W, self.NB, 3), r)
+        quat = np.empty((self.W, self.NB, 4), r)
+        lvel = np.empty((self.W, self.NB, 3), r)
+        avel = np.empty((self.W, self.NB, 3), r)
+        self.slib._fn("get_state")(self.h, _ptr(pos), _ptr(quat), _ptr(lvel), _ptr(avel))
+        return dict(pos=pos, quat=quat, lvel=lvel, avel=avel)
+
+    def add_force(self, force=None, torque=None):
+        self.slib._fn("add_force")(self.h, _ptr(self._arr(force, 3)), _ptr(self._arr(torque, 3)))
+
+    def set_seeds(self, seeds):
+        s = np.ascontiguousarray(np.asarray(seeds, dtype=np.uint32).reshape(self.W))
+        self.slib._fn("set_seeds")(self.h, _ptr(s))
+
+    def get_seeds(self):
+        s = np.empty(self.W, np.uint32)
+        self.slib._fn("get_seeds")(self.h, _ptr(s))
+        return s
+
+    def get_enabled(self):
+        e = np.empty((self.W, self.NB), np.int32)
+        self.slib._fn("get_enabled")(self.h, _ptr(e))
+        return e
+
+    def step(self, h, nsteps=1):
+        ok = self.slib._fn("step")(self.h, float(h), int(nsteps))
+        if not ok:
+            raise RuntimeError("%sstep failed" % self.slib.prefix)
+
+    def get_pairs(self, world, cap=1 << 16):
+        buf = np.empty((cap, 2), np.int32)
+        n = self.slib._fn("get_pairs")(self.h, world, _ptr(buf), cap)
+        if n > cap:
+            return self.get_pairs(world, n)
+        return buf[:n].copy()
+
+    def get_contacts(self, world, cap=1 << 14):
+        g = np.empty((cap, 7), self.slib.real)
+        ids = np.empty((cap, 2), np.int32)
+        n = self.slib._fn("get_contacts")(self.h, world, _ptr(g), _ptr(ids), cap)
+        if n > cap:
+            return self.get_contacts(world, n)
+        return g[:n].copy(), ids[:n].copy()
+
+    def get_islands(self, world):
+        lab = np.empty(self.NB, np.int32)
+        n = self.slib._fn("get_islands")(self.h, world, _ptr(lab))
+        return n, lab
+
+    def get_stats(self, world):
+        s = OdebStats()
+        self.slib._fn("get_stats")(self.h, world, C.byref(s))
+        return np.array(list(s.v), dtype=np.uint32)

@@ -1,0 +1,120 @@
+"""Synthetic scenes of BASELINE.json's configs, as Scene descriptions.
+
+Scene recipes follow the reference's demos (ode/demo/demo_boxstack.cpp, demo_chain2.cpp,
+demo_crash.cpp); the ragdoll is authored here because the reference has none.
+"""
+import numpy as np
+from . import _binding as B
+
+
+def _rng(seed):
+    return np.random.RandomState(seed)
+
+
+def box_stack(nworlds=1, nboxes=16, seed0=1000, jitter=1e-3, demo_world_options=True):
+    """Config 2: nboxes boxes of side 0.5, density 5, stacked on the plane z=0.
+
+    Surface parameters of demo_boxstack.cpp:144-151 (Bounce|SoftCFM, mu=inf, bounce 0.1,
+    bounce_vel 0.1, soft_cfm 0.01), <= 8 contacts per pair, g = (0,0,-0.5), CFM 1e-5; world options of
+    demo_boxstack.cpp:582-597 (auto-disable, damping, max angular speed, correcting vel, surface layer).
+    """
+    kw = dict(gravity=(0, 0, -0.5), cfm=1e-5, max_contacts=8,
+              surf_mode=B.CONTACT_BOUNCE | B.CONTACT_SOFT_CFM, mu=B.INF, mu2=0.0,
+              bounce=0.1, bounce_vel=0.1, soft_cfm=0.01, space_type=B.SPACE_HASH)
+    if demo_world_options:
+        kw.update(auto_disable=1, adis_samples=10, linear_damping=1e-5, angular_damping=0.005,
+                  max_angular_speed=200.0, contact_max_vel=0.1, contact_surface_layer=0.001)
+    sc = B.Scene(B.default_world_params(**kw), nworlds)
+    sc.add_geom(B.PLANE, (0, 0, 1, 0))
+    side = 0.5
+    m, I = B.box_mass(5.0, side, side, side)
+    for i in range(nboxes):
+        pos = (0.01 * (i % 3), 0.005 * (i % 2), 0.25 + 0.5 * i + 0.001 * i)
+        b = sc.add_body(m, I, pos)
+        sc.add_geom(B.BOX, (side, side, side), body=b)
+    pos = np.tile(np.asarray(sc.body_pos)[None], (nworlds, 1, 1))
+    for w in range(nworlds):
+        r = _rng(seed0 + w)
+        pos[w, :, :2] += jitter * (r.rand(nboxes, 2) - 0.5)
+    quat = np.tile(np.array([1.0, 0, 0, 0])[None, None], (nworlds, nboxes, 1))
+    sc.state = dict(pos=pos, quat=quat, lvel=np.zeros_like(pos), avel=np.zeros_like(pos))
+    sc.seeds = (seed0 + np.arange(nworlds)).astype(np.uint32)
+    return sc
+
+
+def pile(nworlds=1, nbodies=1000, seed=12345, spacing=1.1, space_type=B.SPACE_HASH, max_contacts=4):
+    """Config 1: alternating unit boxes / r=0.5 spheres on a cubic lattice dropped on the plane z=0.
+
+    dContactApprox1, mu=0.5, <= 4 contacts per pair, g=(0,0,-9.81), defaults otherwise.
+    """
+    sc = B.Scene(B.default_world_params(gravity=(0, 0, -9.81), max_contacts=max_contacts,
+                                        surf_mode=B.CONTACT_APPROX1, mu=0.5, space_type=space_type), nworlds)
+    sc.add_geom(B.PLANE, (0, 0, 1, 0))
+    n = int(np.ceil(nbodies ** (1.0 / 3.0) - 1e-9))
+    r = _rng(seed)
+    mb, Ib = B.box_mass(1.0, 1, 1, 1)
+    ms, Is = B.sphere_mass(1.0, 0.5)
+    k = 0
+    for iz in range(n):
+        for iy in range(n):
+            for ix in range(n):
+                if k >= nbodies:
+                    break
+                jit = 0.01 * r.rand(2)
+                pos = (ix * spacing + jit[0], iy * spacing + jit[1], 0.6 + iz * spacing)
+                if k % 2 == 0:
+                    b = sc.add_body(mb, Ib, pos)
+                    sc.add_geom(B.BOX, (1, 1, 1), body=b)
+                else:
+                    b = sc.add_body(ms, Is, pos)
+                    sc.add_geom(B.SPHERE, (0.5,), body=b)
+                k += 1
+    sc.seeds = (seed + np.arange(nworlds)).astype(np.uint32)
+    return sc
+
+
+def chain(nworlds=1, nlinks=10, seed0=7):
+    """Config 3: demo_chain2.cpp:138-160 -- boxes of side 0.2, mass 1, ball joints between neighbours,
+    plane, g=(0,0,-0.5), CFM 1e-5, contacts: 1 per pair, mode 0, mu=inf (demo_chain2.cpp:65-82)."""
+    sc = B.Scene(B.default_world_params(gravity=(0, 0, -0.5), cfm=1e-5, max_contacts=1, surf_mode=0,
+                                        mu=B.INF, skip_connected=0), nworlds)
+    sc.add_geom(B.PLANE, (0, 0, 1, 0))
+    side = 0.2
+    _, I = B.box_mass(1.0, side, side, side)
+    I = I / (side ** 3)  # dMassAdjust(m, MASS=1)
+    for i in range(nlinks):
+        k = i * side
+        b = sc.add_body(1.0, I, (k, k, k + 0.4))
+        sc.add_geom(B.BOX, (side, side, side), body=b)
+    for i in range(nlinks - 1):
+        k = (i + 0.5) * side
+        sc.add_joint(B.JOINT_BALL, i, i + 1, (k, k, k + 0.4))
+    pos = np.tile(np.asarray(sc.body_pos)[None], (nworlds, 1, 1))
+    lvel = np.zeros_like(pos)
+    for w in range(nworlds):
+        r = _rng(seed0 + w)
+        lvel[w] = 0.05 * (r.rand(nlinks, 3) - 0.5)
+    quat = np.tile(np.array([1.0, 0, 0, 0])[None, None], (nworlds, nlinks, 1))
+    sc.state = dict(pos=pos, quat=quat, lvel=lvel, avel=np.zeros_like(pos))
+    sc.seeds = (seed0 + np.arange(nworlds)).astype(np.uint32)
+    return sc
+
+
+def free_boxes(nworlds=1, nboxes=64, seed0=5, grid=8, spacing=1.5):
+    """nboxes separate unit boxes resting/falling on the plane: many one-body islands per world
+    (the scattered 64-body world of SURVEY.md 7.2(4))."""
+    sc = B.Scene(B.default_world_params(gravity=(0, 0, -9.81), max_contacts=4, surf_mode=B.CONTACT_APPROX1,
+                                        mu=0.5), nworlds)
+    sc.add_geom(B.PLANE, (0, 0, 1, 0))
+    m, I = B.box_mass(1.0, 1, 1, 1)
+    for i in range(nboxes):
+        b = sc.add_body(m, I, ((i % grid) * spacing, (i // grid) * spacing, 0.5 + 0.02))
+        sc.add_geom(B.BOX, (1, 1, 1), body=b)
+    pos = np.tile(np.asarray(sc.body_pos)[None], (nworlds, 1, 1))
+    for w in range(nworlds):
+        r = _rng(seed0 + w)
+        pos[w, :, 2] += 0.05 * r.rand(nboxes)
+    quat = np.tile(np.array([1.0, 0, 0, 0])[None, None], (nworlds, nboxes, 1))
+    sc.state = dict(pos=pos, quat=quat, lvel=np.zeros_like(pos), avel=np.zeros_like(pos))
+    sc.seeds = (seed0 + np.arange(nworlds)).astype(np.uint32)
+    return sc

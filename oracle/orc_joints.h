@@ -1,0 +1,259 @@
+// orc_joints.h -- TEST INFRASTRUCTURE (oracle). Ball / hinge / universal joint row builders restated
+// from ode/src/joints/{joint,ball,hinge,universal}.cpp. Included inside orc_world.cpp's namespace
+// (uses World, Body, Joint, Limot and the row layout constants).
+#ifndef ORC_JOINTS_H
+#define ORC_JOINTS_H
+
+static inline void qmul3(Real *qa, const Real *qb, const Real *qc)
+{   // dQMultiply3 rotation.cpp:221-228
+    qa[0] = qb[0] * qc[0] - qb[1] * qc[1] - qb[2] * qc[2] - qb[3] * qc[3];
+    qa[1] = -qb[0] * qc[1] - qb[1] * qc[0] + qb[2] * qc[3] - qb[3] * qc[2];
+    qa[2] = -qb[0] * qc[2] - qb[2] * qc[0] + qb[3] * qc[1] - qb[1] * qc[3];
+    qa[3] = -qb[0] * qc[3] - qb[3] * qc[0] + qb[1] * qc[2] - qb[2] * qc[1];
+}
+
+// dRFrom2Axes rotation.cpp:94-133; returns false when the reference returns without writing R
+static inline bool r_from_2axes(Real *R, Real ax, Real ay, Real az, Real bx, Real by, Real bz)
+{
+    Real l = RSQRT(ax * ax + ay * ay + az * az), k;
+    if (l <= R_(0.0)) return false;
+    l = rrecip(l); ax *= l; ay *= l; az *= l;
+    k = ax * bx + ay * by + az * bz;
+    bx -= k * ax; by -= k * ay; bz -= k * az;
+    l = RSQRT(bx * bx + by * by + bz * bz);
+    if (l <= R_(0.0)) return false;
+    l = rrecip(l); bx *= l; by *= l; bz *= l;
+    R[0] = ax; R[4] = ay; R[8] = az;
+    R[1] = bx; R[5] = by; R[9] = bz;
+    R[2] = -by * az + ay * bz; R[6] = -bz * ax + az * bx; R[10] = -bx * ay + ax * by;
+    R[3] = R[7] = R[11] = R_(0.0);
+    return true;
+}
+
+enum { ROWLEN = 16, C_J1L = 0, C_J1A = 3, C_RHS = 6, C_CFM = 7, C_J2L = 8, C_J2A = 11, C_LO = 14, C_HI = 15 };
+
+// setBall joints/joint.cpp:111-157
+static void set_ball(World &W, Joint &j, Real fps, Real erp, Real *row, const Real *anchor1, const Real *anchor2)
+{
+    Real a1[3], a2[3];
+    Body &b0 = W.bodies[j.b0];
+    row[C_J1L + 0] = 1; row[ROWLEN + C_J1L + 1] = 1; row[2 * ROWLEN + C_J1L + 2] = 1;
+    mul0_331(a1, b0.R, anchor1);
+    // dSetCrossMatrixMinus(J1 + JA, a1, rowskip) odemath.h:286-296
+    row[C_J1A + 1] = +a1[2]; row[C_J1A + 2] = -a1[1];
+    row[ROWLEN + C_J1A + 0] = -a1[2]; row[ROWLEN + C_J1A + 2] = +a1[0];
+    row[2 * ROWLEN + C_J1A + 0] = +a1[1]; row[2 * ROWLEN + C_J1A + 1] = -a1[0];
+    if (j.b1 >= 0) {
+        Body &b1 = W.bodies[j.b1];
+        row[C_J2L + 0] = -1; row[ROWLEN + C_J2L + 1] = -1; row[2 * ROWLEN + C_J2L + 2] = -1;
+        mul0_331(a2, b1.R, anchor2);
+        // dSetCrossMatrixPlus odemath.h:274-284
+        row[C_J2A + 1] = -a2[2]; row[C_J2A + 2] = +a2[1];
+        row[ROWLEN + C_J2A + 0] = +a2[2]; row[ROWLEN + C_J2A + 2] = -a2[0];
+        row[2 * ROWLEN + C_J2A + 0] = -a2[1]; row[2 * ROWLEN + C_J2A + 1] = +a2[0];
+    }
+    Real k = fps * erp;
+    if (j.b1 >= 0) {
+        Body &b1 = W.bodies[j.b1];
+        for (int t = 0; t < 3; t++) row[t * ROWLEN + C_RHS] = k * (a2[t] + b1.pos[t] - a1[t] - b0.pos[t]);
+    } else {
+        for (int t = 0; t < 3; t++) row[t * ROWLEN + C_RHS] = k * (anchor2[t] - a1[t] - b0.pos[t]);
+    }
+}
+
+// getHingeAngleFromRelativeQuat joints/joint.cpp:421-458 (double compare with M_PI)
+static Real hinge_angle_from_relq(const Real *qrel, const Real *axis)
+{
+    Real cost2 = qrel[0];
+    Real sint2 = RSQRT(qrel[1] * qrel[1] + qrel[2] * qrel[2] + qrel[3] * qrel[3]);
+    Real theta = (dot3(qrel + 1, axis) >= 0) ? (2 * RATAN2(sint2, cost2)) : (2 * RATAN2(sint2, -cost2));
+    if (theta > M_PI) theta -= (Real)(2 * M_PI);
+    theta = -theta;
+    return theta;
+}
+
+// getHingeAngle joints/joint.cpp:470-490
+static Real hinge_angle(World &W, int body1, int body2, const Real *axis, const Real *q_initial)
+{
+    Real qrel[4];
+    if (body2 >= 0) { Real qq[4]; qmul1(qq, W.bodies[body1].q, W.bodies[body2].q); qmul2(qrel, qq, q_initial); }
+    else qmul3(qrel, W.bodies[body1].q, q_initial);
+    return hinge_angle_from_relq(qrel, axis);
+}
+
+// dxJointLimitMotor::testRotationalLimit joints/joint.cpp:574-593
+static bool limot_test(Limot &l, Real angle)
+{
+    if (angle <= l.lostop) { l.limit = 1; l.limit_err = angle - l.lostop; return true; }
+    if (angle >= l.histop) { l.limit = 2; l.limit_err = angle - l.histop; return true; }
+    l.limit = 0;
+    return false;
+}
+
+// dxJointLimitMotor::addLimot joints/joint.cpp:596-780, rotational form
+static bool add_limot(World &W, Joint &j, Limot &l, Real fps, Real *row, const Real *ax1)
+{
+    int powered = l.fmax > 0;
+    if (!(powered || l.limit)) return false;
+    row[C_J1A] = ax1[0]; row[C_J1A + 1] = ax1[1]; row[C_J1A + 2] = ax1[2];
+    if (j.b1 >= 0) { row[C_J2A] = -ax1[0]; row[C_J2A + 1] = -ax1[1]; row[C_J2A + 2] = -ax1[2]; }
+    if (l.limit && (l.lostop == l.histop)) powered = 0;
+    if (powered) {
+        row[C_CFM] = l.normal_cfm;
+        if (!l.limit) { row[C_RHS] = l.vel; row[C_LO] = -l.fmax; row[C_HI] = l.fmax; }
+        else {
+            Real fm = l.fmax;
+            if ((l.vel > 0) || (l.vel == 0 && l.limit == 2)) fm = -fm;
+            if ((l.limit == 1 && l.vel > 0) || (l.limit == 2 && l.vel < 0)) fm *= l.fudge_factor;
+            Real f0 = fm * ax1[0], f1 = fm * ax1[1], f2 = fm * ax1[2];
+            if (j.b1 >= 0) { Body &b1 = W.bodies[j.b1]; b1.tacc[0] += f0; b1.tacc[1] += f1; b1.tacc[2] += f2; }
+            Body &b0 = W.bodies[j.b0]; b0.tacc[0] += -f0; b0.tacc[1] += -f1; b0.tacc[2] += -f2;
+        }
+    }
+    if (l.limit) {
+        Real k = fps * l.stop_erp;
+        row[C_RHS] = -k * l.limit_err;
+        row[C_CFM] = l.stop_cfm;
+        if (l.lostop == l.histop) { row[C_LO] = -R_INF; row[C_HI] = R_INF; }
+        else {
+            if (l.limit == 1) { row[C_LO] = 0; row[C_HI] = R_INF; } else { row[C_LO] = -R_INF; row[C_HI] = 0; }
+            if (l.bounce > 0) {
+                Real vel = dot3(W.bodies[j.b0].avel, ax1);
+                if (j.b1 >= 0) vel -= dot3(W.bodies[j.b1].avel, ax1);
+                if (l.limit == 1) { if (vel < 0) { Real newc = -l.bounce * vel; if (newc > row[C_RHS]) row[C_RHS] = newc; } }
+                else { if (vel > 0) { Real newc = -l.bounce * vel; if (newc < row[C_RHS]) row[C_RHS] = newc; } }
+            }
+        }
+    }
+    return true;
+}
+
+// dxJointHinge::getInfo1 hinge.cpp:54-74
+static void hinge_info1(World &W, Joint &j)
+{
+    j.nub = 5;
+    j.m = (j.limot1.fmax > 0) ? 6 : 5;
+    if ((j.limot1.lostop >= -M_PI || j.limot1.histop <= M_PI) && j.limot1.lostop <= j.limot1.histop) {
+        Real angle = hinge_angle(W, j.b0, j.b1, j.axis1, j.qrel);
+        if (limot_test(j.limot1, angle)) j.m = 6;
+    }
+}
+
+// dxJointHinge::getInfo2 hinge.cpp:77-147
+static void hinge_info2(World &W, Joint &j, Real fps, Real worldERP, Real *row, int * /*findex*/)
+{
+    set_ball(W, j, fps, worldERP, row, j.anchor1, j.anchor2);
+    Real ax1[3], p[3], q[3];
+    mul0_331(ax1, W.bodies[j.b0].R, j.axis1);
+    plane_space(ax1, p, q);
+    Real *r3 = row + 3 * ROWLEN, *r4 = row + 4 * ROWLEN;
+    r3[C_J1A] = p[0]; r3[C_J1A + 1] = p[1]; r3[C_J1A + 2] = p[2];
+    if (j.b1 >= 0) { r3[C_J2A] = -p[0]; r3[C_J2A + 1] = -p[1]; r3[C_J2A + 2] = -p[2]; }
+    r4[C_J1A] = q[0]; r4[C_J1A + 1] = q[1]; r4[C_J1A + 2] = q[2];
+    if (j.b1 >= 0) { r4[C_J2A] = -q[0]; r4[C_J2A + 1] = -q[1]; r4[C_J2A + 2] = -q[2]; }
+    Real b[3];
+    if (j.b1 >= 0) { Real ax2[3]; mul0_331(ax2, W.bodies[j.b1].R, j.axis2); cross3(b, ax1, ax2); }
+    else cross3(b, ax1, j.axis2);
+    Real k = fps * worldERP;
+    r3[C_RHS] = k * dot3(b, p);
+    r4[C_RHS] = k * dot3(b, q);
+    add_limot(W, j, j.limot1, fps, row + 5 * ROWLEN, ax1);
+}
+
+// dxJointUniversal::getAxes universal.cpp:55-71
+static void universal_axes(World &W, Joint &j, Real *ax1, Real *ax2)
+{
+    mul0_331(ax1, W.bodies[j.b0].R, j.axis1);
+    if (j.b1 >= 0) mul0_331(ax2, W.bodies[j.b1].R, j.axis2);
+    else { ax2[0] = j.axis2[0]; ax2[1] = j.axis2[1]; ax2[2] = j.axis2[2]; }
+}
+
+// dxJointUniversal::getAngles universal.cpp:73-166
+static void universal_angles(World &W, Joint &j, Real *angle1, Real *angle2)
+{
+    Real ax1[3], ax2[3], R[12], qcross[4], qq[4], qrel[4];
+    universal_axes(W, j, ax1, ax2);
+    r_from_2axes(R, ax1[0], ax1[1], ax1[2], ax2[0], ax2[1], ax2[2]);
+    q_from_r(qcross, R);
+    qmul1(qq, W.bodies[j.b0].q, qcross);
+    qmul2(qrel, qq, j.qrel1);
+    *angle1 = hinge_angle_from_relq(qrel, j.axis1);
+    Real qcross2[4];
+    qrel[0] = 0; qrel[1] = ax1[0] + ax2[0]; qrel[2] = ax1[1] + ax2[1]; qrel[3] = ax1[2] + ax2[2];
+    Real l = rrecip(sqrt(qrel[1] * qrel[1] + qrel[2] * qrel[2] + qrel[3] * qrel[3]));
+    qrel[1] *= l; qrel[2] *= l; qrel[3] *= l;
+    qmul0(qcross2, qrel, qcross);
+    if (j.b1 >= 0) { qmul1(qq, W.bodies[j.b1].q, qcross2); qmul2(qrel, qq, j.qrel2); }
+    else qmul2(qrel, qcross2, j.qrel2);
+    *angle2 = -hinge_angle_from_relq(qrel, j.axis2);
+}
+
+// dxJointUniversal::getInfo1 universal.cpp:266-293
+static void universal_info1(World &W, Joint &j)
+{
+    j.nub = 4; j.m = 4;
+    bool lim1 = (j.limot1.lostop >= -M_PI || j.limot1.histop <= M_PI) && j.limot1.lostop <= j.limot1.histop;
+    bool lim2 = (j.limot2.lostop >= -M_PI || j.limot2.histop <= M_PI) && j.limot2.lostop <= j.limot2.histop;
+    j.limot1.limit = 0; j.limot2.limit = 0;
+    if (lim1 || lim2) {
+        Real a1, a2;
+        universal_angles(W, j, &a1, &a2);
+        if (lim1) limot_test(j.limot1, a1);
+        if (lim2) limot_test(j.limot2, a2);
+    }
+    if (j.limot1.limit || j.limot1.fmax > 0) j.m++;
+    if (j.limot2.limit || j.limot2.fmax > 0) j.m++;
+}
+
+// dxJointUniversal::getInfo2 universal.cpp:297-369
+static void universal_info2(World &W, Joint &j, Real fps, Real worldERP, Real *row, int * /*findex*/)
+{
+    set_ball(W, j, fps, worldERP, row, j.anchor1, j.anchor2);
+    Real ax1[3], ax2[3], p[3];
+    universal_axes(W, j, ax1, ax2);
+    Real k = dot3(ax1, ax2);
+    Real ax2t[3] = { ax2[0] + (-k) * ax1[0], ax2[1] + (-k) * ax1[1], ax2[2] + (-k) * ax1[2] };  // dAddVectorScaledVector3
+    cross3(p, ax1, ax2t);
+    normalize3(p);
+    Real *r3 = row + 3 * ROWLEN;
+    r3[C_J1A] = p[0]; r3[C_J1A + 1] = p[1]; r3[C_J1A + 2] = p[2];
+    if (j.b1 >= 0) { r3[C_J2A] = -p[0]; r3[C_J2A + 1] = -p[1]; r3[C_J2A + 2] = -p[2]; }
+    r3[C_RHS] = fps * worldERP * (-k);
+    int r = 4;
+    if (add_limot(W, j, j.limot1, fps, row + r * ROWLEN, ax1)) r++;
+    add_limot(W, j, j.limot2, fps, row + r * ROWLEN, ax2);
+}
+
+// dJointSet{Ball,Hinge,Universal}Anchor/Axis at the template pose
+static void joint_setup(const Batch &B, World &W, Joint &j, const OdebJointDesc &d)
+{
+    (void)B;
+    set_anchors(W, j, (Real)d.anchor[0], (Real)d.anchor[1], (Real)d.anchor[2]);
+    if (j.type == ODEB_JOINT_HINGE) {
+        j.axis1[0] = 1; j.axis2[0] = 1;   // constructor defaults hinge.cpp:36-43
+        set_axes(W, j, (Real)d.axis1[0], (Real)d.axis1[1], (Real)d.axis1[2], j.axis1, j.axis2);
+        // computeInitialRelativeRotation hinge.cpp:376-393
+        if (j.b1 >= 0) qmul1(j.qrel, W.bodies[j.b0].q, W.bodies[j.b1].q);
+        else { const Real *q = W.bodies[j.b0].q; j.qrel[0] = q[0]; j.qrel[1] = -q[1]; j.qrel[2] = -q[2]; j.qrel[3] = -q[3]; }
+        limot_set(j.limot1, d, 0);
+    } else if (j.type == ODEB_JOINT_UNIVERSAL) {
+        j.axis1[0] = 1; j.axis2[1] = 1;   // universal.cpp:40-52
+        if (j.reverse) set_axes(W, j, (Real)d.axis1[0], (Real)d.axis1[1], (Real)d.axis1[2], 0, j.axis2);
+        else set_axes(W, j, (Real)d.axis1[0], (Real)d.axis1[1], (Real)d.axis1[2], j.axis1, 0);
+        if (j.reverse) set_axes(W, j, (Real)d.axis2[0], (Real)d.axis2[1], (Real)d.axis2[2], j.axis1, 0);
+        else set_axes(W, j, (Real)d.axis2[0], (Real)d.axis2[1], (Real)d.axis2[2], 0, j.axis2);
+        // computeInitialRelativeRotations universal.cpp:372-401
+        Real ax1[3], ax2[3], R[12], qcross[4];
+        universal_axes(W, j, ax1, ax2);
+        r_from_2axes(R, ax1[0], ax1[1], ax1[2], ax2[0], ax2[1], ax2[2]);
+        q_from_r(qcross, R);
+        qmul1(j.qrel1, W.bodies[j.b0].q, qcross);
+        r_from_2axes(R, ax2[0], ax2[1], ax2[2], ax1[0], ax1[1], ax1[2]);
+        q_from_r(qcross, R);
+        if (j.b1 >= 0) qmul1(j.qrel2, W.bodies[j.b1].q, qcross);
+        else for (int i = 0; i < 4; i++) j.qrel2[i] = qcross[i];
+        limot_set(j.limot1, d, 0);
+        limot_set(j.limot2, d, 1);
+    }
+}
+#endif
