@@ -161,8 +161,9 @@ int odeb_get_pairs(OdebBatch *, int world, int *pairs, int cap);
 int odeb_get_contacts(OdebBatch *, int world, odeb_real *geom7, int *g12, int cap);
 int odeb_get_islands(OdebBatch *, int world, int *label_per_body);
 int odeb_get_stats(OdebBatch *, int world, OdebStats *out);
-/* totals over all worlds for the most recent step: [pairs, contacts, rows, islands, sweeps(sum over islands)] */
-int odeb_get_totals(OdebBatch *, uint64_t out[5]);
+/* totals over all worlds for the most recent step:
+ * [pairs, contacts, rows, islands, sweeps (sum over islands), row-sweeps (sum over islands of rows x sweeps)] */
+int odeb_get_totals(OdebBatch *, uint64_t out[6]);
 
 #ifdef __cplusplus
 }

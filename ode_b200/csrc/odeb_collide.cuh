@@ -1,0 +1,681 @@
+// odeb_collide.cuh -- device-side AABBs and primitive colliders (sphere / box / capsule / plane) of the
+// B200 step path: one thread evaluates one geom pair. Operation order follows the reference functions
+// cited at each routine (ode/src/box.cpp, sphere.cpp, capsule.cpp, plane.cpp, collision_util.cpp,
+// collision_kernel.cpp) so contacts are bit-identical under -fmad=false except where CUDA libm
+// (atan2 in the contact culling) differs from glibc in the last ulp.
+#ifndef ODEB_COLLIDE_CUH
+#define ODEB_COLLIDE_CUH
+#include "odeb_math.cuh"
+
+
+struct DGeom {
+    int type;        // ODEB_SPHERE / BOX / CAPSULE / PLANE
+    int body;        // -1 = none
+    Real p[4];       // radius | sides | radius,length | plane a,b,c,d (normalised)
+    Real pos[3];
+    Real R[12];
+};
+
+struct DContactGeom { Real pos[3], normal[3], depth; };
+
+#define ODEB_NUMC_MASK 0xffff
+#define ODEB_CONTACTS_UNIMPORTANT 0x80000000
+
+// dxSphere::computeAABB sphere.cpp:59-67; dxBox::computeAABB box.cpp:60-77;
+// dxCapsule::computeAABB capsule.cpp:60-74; dxPlane::computeAABB plane.cpp:80-107
+__device__ __forceinline__ void odeb_compute_aabb(const DGeom &g, Real *a)
+{
+    const Real *pos = g.pos, *R = g.R;
+    if (g.type == 0) {
+        Real r = g.p[0];
+        a[0] = pos[0] - r; a[1] = pos[0] + r; a[2] = pos[1] - r; a[3] = pos[1] + r; a[4] = pos[2] - r; a[5] = pos[2] + r;
+    } else if (g.type == 1) {
+        const Real *s = g.p;
+        Real xr = R_(0.5) * (RFABS(R[0] * s[0]) + RFABS(R[1] * s[1]) + RFABS(R[2] * s[2]));
+        Real yr = R_(0.5) * (RFABS(R[4] * s[0]) + RFABS(R[5] * s[1]) + RFABS(R[6] * s[2]));
+        Real zr = R_(0.5) * (RFABS(R[8] * s[0]) + RFABS(R[9] * s[1]) + RFABS(R[10] * s[2]));
+        a[0] = pos[0] - xr; a[1] = pos[0] + xr; a[2] = pos[1] - yr; a[3] = pos[1] + yr; a[4] = pos[2] - zr; a[5] = pos[2] + zr;
+    } else if (g.type == 2) {
+        Real radius = g.p[0], lz = g.p[1];
+        Real xr = RFABS(R[2] * lz) * R_(0.5) + radius;
+        Real yr = RFABS(R[6] * lz) * R_(0.5) + radius;
+        Real zr = RFABS(R[10] * lz) * R_(0.5) + radius;
+        a[0] = pos[0] - xr; a[1] = pos[0] + xr; a[2] = pos[1] - yr; a[3] = pos[1] + yr; a[4] = pos[2] - zr; a[5] = pos[2] + zr;
+    } else {
+        const Real *p = g.p;
+        a[0] = -R_INF; a[1] = R_INF; a[2] = -R_INF; a[3] = R_INF; a[4] = -R_INF; a[5] = R_INF;
+        if (p[1] == 0.0f && p[2] == 0.0f) { a[0] = (p[0] > 0) ? -R_INF : -p[3]; a[1] = (p[0] > 0) ? p[3] : R_INF; }
+        else if (p[0] == 0.0f && p[2] == 0.0f) { a[2] = (p[1] > 0) ? -R_INF : -p[3]; a[3] = (p[1] > 0) ? p[3] : R_INF; }
+        else if (p[0] == 0.0f && p[1] == 0.0f) { a[4] = (p[2] > 0) ? -R_INF : -p[3]; a[5] = (p[2] > 0) ? p[3] : R_INF; }
+    }
+}
+
+// dCollideSpheres collision_util.cpp:38-67
+__device__ int odeb_collide_spheres(const Real *p1, Real r1, const Real *p2, Real r2, DContactGeom *c)
+{
+    Real t[3] = { p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2] };
+    Real d = RSQRT(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
+    if (d > (r1 + r2)) return 0;
+    if (d <= 0) {
+        c->pos[0] = p1[0]; c->pos[1] = p1[1]; c->pos[2] = p1[2];
+        c->normal[0] = 1; c->normal[1] = 0; c->normal[2] = 0;
+        c->depth = r1 + r2;
+    } else {
+        Real d1 = rrecip(d);
+        c->normal[0] = (p1[0] - p2[0]) * d1; c->normal[1] = (p1[1] - p2[1]) * d1; c->normal[2] = (p1[2] - p2[2]) * d1;
+        Real k = R_(0.5) * (r2 - r1 - d);
+        c->pos[0] = p1[0] + c->normal[0] * k; c->pos[1] = p1[1] + c->normal[1] * k; c->pos[2] = p1[2] + c->normal[2] * k;
+        c->depth = r1 + r2 - d;
+    }
+    return 1;
+}
+
+// dCollideSphereBox sphere.cpp:133-218
+__device__ int odeb_sphere_box(const DGeom &o1, const DGeom &o2, DContactGeom *c)
+{
+    Real l[3], t[3], p[3], q[3], r[3];
+    int onborder = 0;
+    const Real *R = o2.R;
+    p[0] = o1.pos[0] - o2.pos[0]; p[1] = o1.pos[1] - o2.pos[1]; p[2] = o1.pos[2] - o2.pos[2];
+    for (int i = 0; i < 3; i++) {
+        l[i] = o2.p[i] * R_(0.5);
+        t[i] = dot3s(p, 1, R + i, 4);
+        if (t[i] < -l[i]) { t[i] = -l[i]; onborder = 1; }
+        if (t[i] > l[i]) { t[i] = l[i]; onborder = 1; }
+    }
+    if (!onborder) {
+        Real mind = l[0] - RFABS(t[0]);
+        int mini = 0;
+        for (int i = 1; i < 3; i++) { Real fd = l[i] - RFABS(t[i]); if (fd < mind) { mind = fd; mini = i; } }
+        c->pos[0] = o1.pos[0]; c->pos[1] = o1.pos[1]; c->pos[2] = o1.pos[2];
+        Real tmp[3] = { 0, 0, 0 };
+        tmp[mini] = (t[mini] > 0) ? R_(1.0) : R_(-1.0);
+        mul0_331(c->normal, R, tmp);
+        c->depth = mind + o1.p[0];
+        return 1;
+    }
+    mul0_331(q, R, t);
+    r[0] = p[0] - q[0]; r[1] = p[1] - q[1]; r[2] = p[2] - q[2];
+    Real depth = o1.p[0] - RSQRT(dot3(r, r));
+    if (depth < 0) return 0;
+    c->pos[0] = q[0] + o2.pos[0]; c->pos[1] = q[1] + o2.pos[1]; c->pos[2] = q[2] + o2.pos[2];
+    c->normal[0] = r[0]; c->normal[1] = r[1]; c->normal[2] = r[2];
+    normalize3(c->normal);
+    c->depth = depth;
+    return 1;
+}
+
+// dCollideSpherePlane sphere.cpp:221-251
+__device__ int odeb_sphere_plane(const DGeom &o1, const DGeom &o2, DContactGeom *c)
+{
+    const Real *pl = o2.p;
+    Real k = dot3(o1.pos, pl);
+    Real depth = pl[3] - k + o1.p[0];
+    if (depth >= 0) {
+        c->normal[0] = pl[0]; c->normal[1] = pl[1]; c->normal[2] = pl[2];
+        c->pos[0] = o1.pos[0] - pl[0] * o1.p[0]; c->pos[1] = o1.pos[1] - pl[1] * o1.p[0]; c->pos[2] = o1.pos[2] - pl[2] * o1.p[0];
+        c->depth = depth;
+        return 1;
+    }
+    return 0;
+}
+
+// dLineClosestApproach collision_util.cpp:70-92
+__device__ void odeb_line_closest_approach(const Real *pa, const Real *ua, const Real *pb, const Real *ub, Real *alpha, Real *beta)
+{
+    Real p[3] = { pb[0] - pa[0], pb[1] - pa[1], pb[2] - pa[2] };
+    Real uaub = dot3(ua, ub), q1 = dot3(ua, p), q2 = -dot3(ub, p);
+    Real d = 1 - uaub * uaub;
+    if (d <= R_(0.0001)) { *alpha = 0; *beta = 0; }
+    else { d = rrecip(d); *alpha = (q1 + uaub * q2) * d; *beta = (uaub * q1 + q2) * d; }
+}
+
+// intersectRectQuad box.cpp:212-263
+__device__ __noinline__ int odeb_intersect_rect_quad(const Real h[2], Real p[8], Real ret[16])
+{
+    int nq = 4, nr = 0;
+    Real buffer[16];
+    Real *q = p, *r = ret;
+    for (int dir = 0; dir <= 1; dir++) {
+        for (int sign = -1; sign <= 1; sign += 2) {
+            Real *pq = q, *pr = r;
+            nr = 0;
+            for (int i = nq; i > 0; i--) {
+                if (sign * pq[dir] < h[dir]) {
+                    pr[0] = pq[0]; pr[1] = pq[1]; pr += 2; nr++;
+                    if (nr & 8) { q = r; goto done; }
+                }
+                Real *nextq = (i > 1) ? pq + 2 : q;
+                if ((sign * pq[dir] < h[dir]) ^ (sign * nextq[dir] < h[dir])) {
+                    pr[1 - dir] = pq[1 - dir] + (nextq[1 - dir] - pq[1 - dir]) / (nextq[dir] - pq[dir]) * (sign * h[dir] - pq[dir]);
+                    pr[dir] = sign * h[dir];
+                    pr += 2; nr++;
+                    if (nr & 8) { q = r; goto done; }
+                }
+                pq += 2;
+            }
+            q = r;
+            r = (q == ret) ? buffer : ret;
+            nq = nr;
+        }
+    }
+done:
+    if (q != ret) for (int t = 0; t < nr * 2; t++) ret[t] = q[t];
+    return nr;
+}
+
+// cullPoints box.cpp:274-336 (note the double-precision M_PI expressions in the single build)
+__device__ __noinline__ void odeb_cull_points(int n, const Real p[], int m, int i0, int iret[])
+{
+    int i, j;
+    Real a, cx, cy, q;
+    if (n == 1) { cx = p[0]; cy = p[1]; }
+    else if (n == 2) { cx = R_(0.5) * (p[0] + p[2]); cy = R_(0.5) * (p[1] + p[3]); }
+    else {
+        a = 0; cx = 0; cy = 0;
+        for (i = 0; i < (n - 1); i++) {
+            q = p[i * 2] * p[i * 2 + 3] - p[i * 2 + 2] * p[i * 2 + 1];
+            a += q;
+            cx += q * (p[i * 2] + p[i * 2 + 2]);
+            cy += q * (p[i * 2 + 1] + p[i * 2 + 3]);
+        }
+        q = p[n * 2 - 2] * p[1] - p[0] * p[n * 2 - 1];
+        a = rrecip(R_(3.0) * (a + q));
+        cx = a * (cx + q * (p[n * 2 - 2] + p[0]));
+        cy = a * (cy + q * (p[n * 2 - 1] + p[1]));
+    }
+    Real A[8];
+    for (i = 0; i < n; i++) A[i] = RATAN2(p[i * 2 + 1] - cy, p[i * 2] - cx);
+    int avail[8];
+    for (i = 0; i < n; i++) avail[i] = 1;
+    avail[i0] = 0;
+    iret[0] = i0;
+    iret++;
+    for (j = 1; j < m; j++) {
+        a = (Real)((Real)j * (2 * M_PI / m) + A[i0]);
+        if (a > M_PI) a -= (Real)(2 * M_PI);
+        Real maxdiff = 1e9, diff;
+        *iret = i0;
+        for (i = 0; i < n; i++) {
+            if (avail[i]) {
+                diff = RFABS(A[i] - a);
+                if (diff > M_PI) diff = (Real)(2 * M_PI - diff);
+                if (diff < maxdiff) { maxdiff = diff; *iret = i; }
+            }
+        }
+        avail[*iret] = 0;
+        iret++;
+    }
+}
+
+// dBoxBox box.cpp:356-737. Returns contact count; normal/depth/code as the reference.
+__device__ __noinline__ int odeb_box_box(const Real *p1, const Real *R1, const Real *side1, const Real *p2, const Real *R2, const Real *side2,
+                              Real *normal, Real *depth, int *return_code, int flags, DContactGeom *contact)
+{
+    const Real fudge = R_(1.05);
+    Real p[3], pp[3], normalC[3] = { 0, 0, 0 };
+    const Real *normalR = 0;
+    Real A[3], B[3], Rm[3][3], Q[3][3], s, s2, l, e1;
+    int i, j, invert_normal, code;
+    p[0] = p2[0] - p1[0]; p[1] = p2[1] - p1[1]; p[2] = p2[2] - p1[2];
+    mul1_331(pp, R1, p);
+    for (i = 0; i < 3; i++) { A[i] = side1[i] * R_(0.5); B[i] = side2[i] * R_(0.5); }
+    for (i = 0; i < 3; i++) for (j = 0; j < 3; j++) { Rm[i][j] = dot3s(R1 + i, 4, R2 + j, 4); Q[i][j] = RFABS(Rm[i][j]); }
+    s = -R_INF; invert_normal = 0; code = 0;
+    const bool unimportant = (flags & ODEB_CONTACTS_UNIMPORTANT) != 0;
+    do {
+#define ODEB_TST1(expr1, expr2, norm, cc) \
+        e1 = (expr1); s2 = RFABS(e1) - (expr2); if (s2 > 0) return 0; \
+        if (s2 > s) { s = s2; normalR = norm; invert_normal = (e1 < 0); code = (cc); if (unimportant) break; }
+        ODEB_TST1(pp[0], (A[0] + B[0] * Q[0][0] + B[1] * Q[0][1] + B[2] * Q[0][2]), R1 + 0, 1);
+        ODEB_TST1(pp[1], (A[1] + B[0] * Q[1][0] + B[1] * Q[1][1] + B[2] * Q[1][2]), R1 + 1, 2);
+        ODEB_TST1(pp[2], (A[2] + B[0] * Q[2][0] + B[1] * Q[2][1] + B[2] * Q[2][2]), R1 + 2, 3);
+        ODEB_TST1(dot3s(R2 + 0, 4, p, 1), (A[0] * Q[0][0] + A[1] * Q[1][0] + A[2] * Q[2][0] + B[0]), R2 + 0, 4);
+        ODEB_TST1(dot3s(R2 + 1, 4, p, 1), (A[0] * Q[0][1] + A[1] * Q[1][1] + A[2] * Q[2][1] + B[1]), R2 + 1, 5);
+        ODEB_TST1(dot3s(R2 + 2, 4, p, 1), (A[0] * Q[0][2] + A[1] * Q[1][2] + A[2] * Q[2][2] + B[2]), R2 + 2, 6);
+#undef ODEB_TST1
+#define ODEB_TST2(expr1, expr2, n1, n2, n3, cc) \
+        e1 = (expr1); s2 = RFABS(e1) - (expr2); if (s2 > 0) return 0; \
+        l = RSQRT((n1) * (n1) + (n2) * (n2) + (n3) * (n3)); \
+        if (l > 0) { s2 /= l; if (s2 * fudge > s) { s = s2; normalR = 0; \
+            normalC[0] = (n1) / l; normalC[1] = (n2) / l; normalC[2] = (n3) / l; \
+            invert_normal = (e1 < 0); code = (cc); if (unimportant) break; } }
+        ODEB_TST2(pp[2] * Rm[1][0] - pp[1] * Rm[2][0], (A[1] * Q[2][0] + A[2] * Q[1][0] + B[1] * Q[0][2] + B[2] * Q[0][1]), 0, -Rm[2][0], Rm[1][0], 7);
+        ODEB_TST2(pp[2] * Rm[1][1] - pp[1] * Rm[2][1], (A[1] * Q[2][1] + A[2] * Q[1][1] + B[0] * Q[0][2] + B[2] * Q[0][0]), 0, -Rm[2][1], Rm[1][1], 8);
+        ODEB_TST2(pp[2] * Rm[1][2] - pp[1] * Rm[2][2], (A[1] * Q[2][2] + A[2] * Q[1][2] + B[0] * Q[0][1] + B[1] * Q[0][0]), 0, -Rm[2][2], Rm[1][2], 9);
+        ODEB_TST2(pp[0] * Rm[2][0] - pp[2] * Rm[0][0], (A[0] * Q[2][0] + A[2] * Q[0][0] + B[1] * Q[1][2] + B[2] * Q[1][1]), Rm[2][0], 0, -Rm[0][0], 10);
+        ODEB_TST2(pp[0] * Rm[2][1] - pp[2] * Rm[0][1], (A[0] * Q[2][1] + A[2] * Q[0][1] + B[0] * Q[1][2] + B[2] * Q[1][0]), Rm[2][1], 0, -Rm[0][1], 11);
+        ODEB_TST2(pp[0] * Rm[2][2] - pp[2] * Rm[0][2], (A[0] * Q[2][2] + A[2] * Q[0][2] + B[0] * Q[1][1] + B[1] * Q[1][0]), Rm[2][2], 0, -Rm[0][2], 12);
+        ODEB_TST2(pp[1] * Rm[0][0] - pp[0] * Rm[1][0], (A[0] * Q[1][0] + A[1] * Q[0][0] + B[1] * Q[2][2] + B[2] * Q[2][1]), -Rm[1][0], Rm[0][0], 0, 13);
+        ODEB_TST2(pp[1] * Rm[0][1] - pp[0] * Rm[1][1], (A[0] * Q[1][1] + A[1] * Q[0][1] + B[0] * Q[2][2] + B[2] * Q[2][0]), -Rm[1][1], Rm[0][1], 0, 14);
+        ODEB_TST2(pp[1] * Rm[0][2] - pp[0] * Rm[1][2], (A[0] * Q[1][2] + A[1] * Q[0][2] + B[0] * Q[2][1] + B[1] * Q[2][0]), -Rm[1][2], Rm[0][2], 0, 15);
+#undef ODEB_TST2
+    } while (0);
+    if (!code) return 0;
+    if (normalR) { normal[0] = normalR[0]; normal[1] = normalR[4]; normal[2] = normalR[8]; }
+    else mul0_331(normal, R1, normalC);
+    if (invert_normal) { normal[0] = -normal[0]; normal[1] = -normal[1]; normal[2] = -normal[2]; }
+    *depth = -s;
+
+    if (code > 6) {
+        Real pa[3], pb[3], sign;
+        for (i = 0; i < 3; i++) pa[i] = p1[i];
+        for (j = 0; j < 3; j++) {
+            sign = (dot3s(normal, 1, R1 + j, 4) > 0) ? R_(1.0) : R_(-1.0);
+            for (i = 0; i < 3; i++) pa[i] += sign * A[j] * R1[i * 4 + j];
+        }
+        for (i = 0; i < 3; i++) pb[i] = p2[i];
+        for (j = 0; j < 3; j++) {
+            sign = (dot3s(normal, 1, R2 + j, 4) > 0) ? R_(-1.0) : R_(1.0);
+            for (i = 0; i < 3; i++) pb[i] += sign * B[j] * R2[i * 4 + j];
+        }
+        Real alpha, beta, ua[3], ub[3];
+        for (i = 0; i < 3; i++) ua[i] = R1[(code - 7) / 3 + i * 4];
+        for (i = 0; i < 3; i++) ub[i] = R2[(code - 7) % 3 + i * 4];
+        odeb_line_closest_approach(pa, ua, pb, ub, &alpha, &beta);
+        for (i = 0; i < 3; i++) pa[i] += ua[i] * alpha;
+        for (i = 0; i < 3; i++) pb[i] += ub[i] * beta;
+        for (i = 0; i < 3; i++) contact[0].pos[i] = R_(0.5) * (pa[i] + pb[i]);
+        contact[0].depth = *depth;
+        *return_code = code;
+        return 1;
+    }
+
+    const Real *Ra, *Rb, *pa, *pb, *Sa, *Sb;
+    if (code <= 3) { Ra = R1; Rb = R2; pa = p1; pb = p2; Sa = A; Sb = B; }
+    else { Ra = R2; Rb = R1; pa = p2; pb = p1; Sa = B; Sb = A; }
+    Real normal2[3], nr[3], anr[3];
+    if (code <= 3) { normal2[0] = normal[0]; normal2[1] = normal[1]; normal2[2] = normal[2]; }
+    else { normal2[0] = -normal[0]; normal2[1] = -normal[1]; normal2[2] = -normal[2]; }
+    mul1_331(nr, Rb, normal2);
+    anr[0] = RFABS(nr[0]); anr[1] = RFABS(nr[1]); anr[2] = RFABS(nr[2]);
+    int lanr, a1, a2;
+    if (anr[1] > anr[0]) {
+        if (anr[1] > anr[2]) { a1 = 0; lanr = 1; a2 = 2; } else { a1 = 0; a2 = 1; lanr = 2; }
+    } else {
+        if (anr[0] > anr[2]) { lanr = 0; a1 = 1; a2 = 2; } else { a1 = 0; a2 = 1; lanr = 2; }
+    }
+    Real center[3];
+    if (nr[lanr] < 0) { for (i = 0; i < 3; i++) center[i] = pb[i] - pa[i] + Sb[lanr] * Rb[i * 4 + lanr]; }
+    else { for (i = 0; i < 3; i++) center[i] = pb[i] - pa[i] - Sb[lanr] * Rb[i * 4 + lanr]; }
+    int codeN, code1, code2;
+    codeN = (code <= 3) ? code - 1 : code - 4;
+    if (codeN == 0) { code1 = 1; code2 = 2; } else if (codeN == 1) { code1 = 0; code2 = 2; } else { code1 = 0; code2 = 1; }
+    Real quad[8], c1, c2, m11, m12, m21, m22;
+    c1 = dot3s(center, 1, Ra + code1, 4);
+    c2 = dot3s(center, 1, Ra + code2, 4);
+    m11 = dot3s(Ra + code1, 4, Rb + a1, 4); m12 = dot3s(Ra + code1, 4, Rb + a2, 4);
+    m21 = dot3s(Ra + code2, 4, Rb + a1, 4); m22 = dot3s(Ra + code2, 4, Rb + a2, 4);
+    {
+        Real k1 = m11 * Sb[a1], k2 = m21 * Sb[a1], k3 = m12 * Sb[a2], k4 = m22 * Sb[a2];
+        quad[0] = c1 - k1 - k3; quad[1] = c2 - k2 - k4; quad[2] = c1 - k1 + k3; quad[3] = c2 - k2 + k4;
+        quad[4] = c1 + k1 + k3; quad[5] = c2 + k2 + k4; quad[6] = c1 + k1 - k3; quad[7] = c2 + k2 - k4;
+    }
+    Real rect[2] = { Sa[code1], Sa[code2] };
+    Real ret[16];
+    int n = odeb_intersect_rect_quad(rect, quad, ret);
+    if (n < 1) return 0;
+    Real point[3 * 8], dep[8];
+    Real det1 = rrecip(m11 * m22 - m12 * m21);
+    m11 *= det1; m12 *= det1; m21 *= det1; m22 *= det1;
+    int cnum = 0;
+    for (j = 0; j < n; j++) {
+        Real k1 = m22 * (ret[j * 2] - c1) - m12 * (ret[j * 2 + 1] - c2);
+        Real k2 = -m21 * (ret[j * 2] - c1) + m11 * (ret[j * 2 + 1] - c2);
+        for (i = 0; i < 3; i++) point[cnum * 3 + i] = center[i] + k1 * Rb[i * 4 + a1] + k2 * Rb[i * 4 + a2];
+        dep[cnum] = Sa[codeN] - dot3(normal2, point + cnum * 3);
+        if (dep[cnum] >= 0) {
+            ret[cnum * 2] = ret[j * 2]; ret[cnum * 2 + 1] = ret[j * 2 + 1];
+            cnum++;
+            if ((unsigned)(cnum | ODEB_CONTACTS_UNIMPORTANT) == ((unsigned)flags & (ODEB_NUMC_MASK | ODEB_CONTACTS_UNIMPORTANT))) break;
+        }
+    }
+    if (cnum < 1) return 0;
+    int maxc = flags & ODEB_NUMC_MASK;
+    if (maxc > cnum) maxc = cnum;
+    if (maxc < 1) maxc = 1;
+    if (cnum <= maxc) {
+        for (j = 0; j < cnum; j++) {
+            for (i = 0; i < 3; i++) contact[j].pos[i] = point[j * 3 + i] + pa[i];
+            contact[j].depth = dep[j];
+        }
+    } else {
+        int i1 = 0;
+        Real maxdepth = dep[0];
+        for (i = 1; i < cnum; i++) if (dep[i] > maxdepth) { maxdepth = dep[i]; i1 = i; }
+        int iret[8];
+        odeb_cull_points(cnum, ret, maxc, i1, iret);
+        for (j = 0; j < maxc; j++) {
+            for (i = 0; i < 3; i++) contact[j].pos[i] = point[iret[j] * 3 + i] + pa[i];
+            contact[j].depth = dep[iret[j]];
+        }
+        cnum = maxc;
+    }
+    *return_code = code;
+    return cnum;
+}
+
+// dCollideBoxBox box.cpp:741-767
+__device__ int odeb_collide_box_box(const DGeom &o1, const DGeom &o2, int flags, DContactGeom *c)
+{
+    Real normal[3], depth; int code;
+    int num = odeb_box_box(o1.pos, o1.R, o1.p, o2.pos, o2.R, o2.p, normal, &depth, &code, flags, c);
+    for (int i = 0; i < num; i++) { c[i].normal[0] = -normal[0]; c[i].normal[1] = -normal[1]; c[i].normal[2] = -normal[2]; }
+    return num;
+}
+
+// dCollideBoxPlane box.cpp:770-903
+__device__ int odeb_box_plane(const DGeom &o1, const DGeom &o2, int flags, DContactGeom *c)
+{
+    const Real *R = o1.R, *n = o2.p, *side = o1.p;
+    int ret = 0;
+    Real Q1 = dot3s(n, 1, R + 0, 4), Q2 = dot3s(n, 1, R + 1, 4), Q3 = dot3s(n, 1, R + 2, 4);
+    Real Av[3] = { side[0] * Q1, side[1] * Q2, side[2] * Q3 };
+    Real Bv[3] = { RFABS(Av[0]), RFABS(Av[1]), RFABS(Av[2]) };
+    Real depth = n[3] + R_(0.5) * (Bv[0] + Bv[1] + Bv[2]) - dot3(n, o1.pos);
+    if (depth < 0) return 0;
+    int maxc = flags & ODEB_NUMC_MASK;
+    if (maxc > 4) maxc = 4;
+    Real p[3] = { o1.pos[0], o1.pos[1], o1.pos[2] };
+    for (int i = 0; i < 3; i++) {
+        if (Av[i] > 0) { p[0] -= R_(0.5) * side[i] * R[0 + i]; p[1] -= R_(0.5) * side[i] * R[4 + i]; p[2] -= R_(0.5) * side[i] * R[8 + i]; }
+        else { p[0] += R_(0.5) * side[i] * R[0 + i]; p[1] += R_(0.5) * side[i] * R[4 + i]; p[2] += R_(0.5) * side[i] * R[8 + i]; }
+    }
+    c[0].pos[0] = p[0]; c[0].pos[1] = p[1]; c[0].pos[2] = p[2]; c[0].depth = depth;
+    ret = 1;
+    if (maxc != 1) {
+        // choose the two sides with the smallest projected length, in the reference's order
+        int first, second;
+        if (Bv[0] < Bv[1]) {
+            if (Bv[2] < Bv[0]) { first = 2; second = (Bv[0] < Bv[1]) ? 0 : 1; }
+            else { first = 0; second = (Bv[1] < Bv[2]) ? 1 : 2; }
+        } else {
+            if (Bv[2] < Bv[1]) { first = 2; second = (Bv[0] < Bv[1]) ? 0 : 1; }
+            else { first = 1; second = (Bv[0] < Bv[2]) ? 0 : 2; }
+        }
+        const int order[2] = { first, second };
+        for (int k = 0; k < 2; k++) {
+            int sd = order[k], ci = k + 1;
+            if (depth - Bv[sd] < 0) break;
+            if (Av[sd] > 0) { c[ci].pos[0] = p[0] + side[sd] * R[0 + sd]; c[ci].pos[1] = p[1] + side[sd] * R[4 + sd]; c[ci].pos[2] = p[2] + side[sd] * R[8 + sd]; }
+            else { c[ci].pos[0] = p[0] - side[sd] * R[0 + sd]; c[ci].pos[1] = p[1] - side[sd] * R[4 + sd]; c[ci].pos[2] = p[2] - side[sd] * R[8 + sd]; }
+            c[ci].depth = depth - Bv[sd];
+            ret++;
+            if (k == 0 && maxc == 2) break;
+        }
+    }
+    if (maxc == 4 && ret == 3) {
+        Real d4 = c[1].depth + c[2].depth - depth;
+        if (d4 > 0) {
+            c[3].pos[0] = c[1].pos[0] + c[2].pos[0] - p[0];
+            c[3].pos[1] = c[1].pos[1] + c[2].pos[1] - p[1];
+            c[3].pos[2] = c[1].pos[2] + c[2].pos[2] - p[2];
+            c[3].depth = d4;
+            ret++;
+        }
+    }
+    for (int i = 0; i < ret; i++) { c[i].normal[0] = n[0]; c[i].normal[1] = n[1]; c[i].normal[2] = n[2]; }
+    return ret;
+}
+
+
+
+// dClosestLineSegmentPoints collision_util.cpp:109-223
+__device__ __noinline__ void odeb_closest_segment_points(const Real *a1, const Real *a2, const Real *b1, const Real *b2, Real *cp1, Real *cp2)
+{
+    Real a1a2[3], b1b2[3], a1b1[3], a1b2[3], a2b1[3], a2b2[3], n[3];
+    Real la, lb, k, da1, da2, da3, da4, db1, db2, db3, db4, det;
+    for (int i = 0; i < 3; i++) { a1a2[i] = a2[i] - a1[i]; b1b2[i] = b2[i] - b1[i]; a1b1[i] = b1[i] - a1[i]; }
+    da1 = dot3(a1a2, a1b1); db1 = dot3(b1b2, a1b1);
+    if (da1 <= 0 && db1 >= 0) { for (int i = 0; i < 3; i++) { cp1[i] = a1[i]; cp2[i] = b1[i]; } return; }
+    for (int i = 0; i < 3; i++) a1b2[i] = b2[i] - a1[i];
+    da2 = dot3(a1a2, a1b2); db2 = dot3(b1b2, a1b2);
+    if (da2 <= 0 && db2 <= 0) { for (int i = 0; i < 3; i++) { cp1[i] = a1[i]; cp2[i] = b2[i]; } return; }
+    for (int i = 0; i < 3; i++) a2b1[i] = b1[i] - a2[i];
+    da3 = dot3(a1a2, a2b1); db3 = dot3(b1b2, a2b1);
+    if (da3 >= 0 && db3 >= 0) { for (int i = 0; i < 3; i++) { cp1[i] = a2[i]; cp2[i] = b1[i]; } return; }
+    for (int i = 0; i < 3; i++) a2b2[i] = b2[i] - a2[i];
+    da4 = dot3(a1a2, a2b2); db4 = dot3(b1b2, a2b2);
+    if (da4 >= 0 && db4 <= 0) { for (int i = 0; i < 3; i++) { cp1[i] = a2[i]; cp2[i] = b2[i]; } return; }
+    la = dot3(a1a2, a1a2);
+    if (da1 >= 0 && da3 <= 0) {
+        k = da1 / la;
+        for (int i = 0; i < 3; i++) n[i] = a1b1[i] - k * a1a2[i];
+        if (dot3(b1b2, n) >= 0) { for (int i = 0; i < 3; i++) { cp1[i] = a1[i] + k * a1a2[i]; cp2[i] = b1[i]; } return; }
+    }
+    if (da2 >= 0 && da4 <= 0) {
+        k = da2 / la;
+        for (int i = 0; i < 3; i++) n[i] = a1b2[i] - k * a1a2[i];
+        if (dot3(b1b2, n) <= 0) { for (int i = 0; i < 3; i++) { cp1[i] = a1[i] + k * a1a2[i]; cp2[i] = b2[i]; } return; }
+    }
+    lb = dot3(b1b2, b1b2);
+    if (db1 <= 0 && db2 >= 0) {
+        k = -db1 / lb;
+        for (int i = 0; i < 3; i++) n[i] = -a1b1[i] - k * b1b2[i];
+        if (dot3(a1a2, n) >= 0) { for (int i = 0; i < 3; i++) { cp1[i] = a1[i]; cp2[i] = b1[i] + k * b1b2[i]; } return; }
+    }
+    if (db3 <= 0 && db4 >= 0) {
+        k = -db3 / lb;
+        for (int i = 0; i < 3; i++) n[i] = -a2b1[i] - k * b1b2[i];
+        if (dot3(a1a2, n) <= 0) { for (int i = 0; i < 3; i++) { cp1[i] = a2[i]; cp2[i] = b1[i] + k * b1b2[i]; } return; }
+    }
+    k = dot3(a1a2, b1b2);
+    det = la * lb - k * k;
+    if (det <= 0) { for (int i = 0; i < 3; i++) { cp1[i] = a1[i]; cp2[i] = b1[i]; } return; }
+    det = rrecip(det);
+    Real alpha = (lb * da1 - k * db1) * det;
+    Real beta = (k * da1 - la * db1) * det;
+    for (int i = 0; i < 3; i++) { cp1[i] = a1[i] + alpha * a1a2[i]; cp2[i] = b1[i] + beta * b1b2[i]; }
+}
+
+// dClosestLineBoxPoints collision_util.cpp:247-384
+__device__ __noinline__ void odeb_closest_line_box_points(const Real *p1, const Real *p2, const Real *c, const Real *R, const Real *side, Real *lret, Real *bret)
+{
+    int i;
+    Real tmp[3], s[3], v[3], sign[3], v2[3], h[3], tanchor[3];
+    int region[3];
+    tmp[0] = p1[0] - c[0]; tmp[1] = p1[1] - c[1]; tmp[2] = p1[2] - c[2];
+    mul1_331(s, R, tmp);
+    tmp[0] = p2[0] - p1[0]; tmp[1] = p2[1] - p1[1]; tmp[2] = p2[2] - p1[2];
+    mul1_331(v, R, tmp);
+    for (i = 0; i < 3; i++) { if (v[i] < 0) { s[i] = -s[i]; v[i] = -v[i]; sign[i] = -1; } else sign[i] = 1; }
+    for (i = 0; i < 3; i++) { v2[i] = v[i] * v[i]; h[i] = R_(0.5) * side[i]; }
+#if defined(ODEB_DOUBLE)
+    const Real eps = R_(1e-307);
+#else
+    const Real eps = R_(1e-19);
+#endif
+    for (i = 0; i < 3; i++) {
+        if (v[i] > eps) {
+            if (s[i] < -h[i]) { region[i] = -1; tanchor[i] = (-h[i] - s[i]) / v[i]; }
+            else { region[i] = (s[i] > h[i]); tanchor[i] = (h[i] - s[i]) / v[i]; }
+        } else { region[i] = 0; tanchor[i] = 2; }
+    }
+    Real t = 0, dd2dt = 0;
+    for (i = 0; i < 3; i++) dd2dt -= (region[i] ? v2[i] : 0) * tanchor[i];
+    if (!(dd2dt >= 0)) {
+        bool answered = false;
+        do {
+            Real next_t = 1;
+            for (i = 0; i < 3; i++) if (tanchor[i] > t && tanchor[i] < 1 && tanchor[i] < next_t) next_t = tanchor[i];
+            Real next_dd2dt = 0;
+            for (i = 0; i < 3; i++) next_dd2dt += (region[i] ? v2[i] : 0) * (next_t - tanchor[i]);
+            if (next_dd2dt >= 0) {
+                Real m = (next_dd2dt - dd2dt) / (next_t - t);
+                t -= dd2dt / m;
+                answered = true;
+                break;
+            }
+            for (i = 0; i < 3; i++) if (tanchor[i] == next_t) { tanchor[i] = (h[i] - s[i]) / v[i]; region[i]++; }
+            t = next_t;
+            dd2dt = next_dd2dt;
+        } while (t < 1);
+        if (!answered) t = 1;
+    }
+    for (i = 0; i < 3; i++) lret[i] = p1[i] + t * tmp[i];
+    for (i = 0; i < 3; i++) {
+        tmp[i] = sign[i] * (s[i] + t * v[i]);
+        if (tmp[i] < -h[i]) tmp[i] = -h[i]; else if (tmp[i] > h[i]) tmp[i] = h[i];
+    }
+    mul0_331(s, R, tmp);
+    for (i = 0; i < 3; i++) bret[i] = s[i] + c[i];
+}
+
+// dCollideCapsuleSphere capsule.cpp:130-163
+__device__ int odeb_capsule_sphere(const DGeom &o1, const DGeom &o2, DContactGeom *c)
+{
+    const Real *R = o1.R;
+    Real alpha = R[2] * (o2.pos[0] - o1.pos[0]) + R[6] * (o2.pos[1] - o1.pos[1]) + R[10] * (o2.pos[2] - o1.pos[2]);
+    Real lz2 = o1.p[1] * R_(0.5);
+    if (alpha > lz2) alpha = lz2;
+    if (alpha < -lz2) alpha = -lz2;
+    Real p[3] = { o1.pos[0] + alpha * R[2], o1.pos[1] + alpha * R[6], o1.pos[2] + alpha * R[10] };
+    return odeb_collide_spheres(p, o1.p[0], o2.pos, o2.p[0], c);
+}
+
+__device__ __noinline__ int odeb_box_box(const Real *p1, const Real *R1, const Real *side1, const Real *p2, const Real *R2, const Real *side2,
+                              Real *normal, Real *depth, int *return_code, int flags, DContactGeom *contact);
+
+// dCollideCapsuleBox capsule.cpp:166-237
+__device__ int odeb_capsule_box(const DGeom &o1, const DGeom &o2, int flags, DContactGeom *contact)
+{
+    const Real *R1 = o1.R;
+    Real p1[3], p2[3];
+    Real clen = o1.p[1] * R_(0.5);
+    p1[0] = o1.pos[0] + clen * R1[2]; p1[1] = o1.pos[1] + clen * R1[6]; p1[2] = o1.pos[2] + clen * R1[10];
+    p2[0] = o1.pos[0] - clen * R1[2]; p2[1] = o1.pos[1] - clen * R1[6]; p2[2] = o1.pos[2] - clen * R1[10];
+    Real radius = o1.p[0];
+    Real pl[3], pb[3];
+    odeb_closest_line_box_points(p1, p2, o2.pos, o2.R, o2.p, pl, pb);
+#if defined(ODEB_DOUBLE)
+    Real mindist = R_(1e-15);
+#else
+    Real mindist = R_(1e-6);
+#endif
+    Real d[3] = { pl[0] - pb[0], pl[1] - pb[1], pl[2] - pb[2] };
+    if (RSQRT(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]) < mindist) {
+        Real normal[3], depth; int code;
+        Real r2 = radius * R_(2.0);
+        const Real capboxside[3] = { r2, r2, o1.p[1] + r2 };
+        int num = odeb_box_box(o2.pos, o2.R, o2.p, o1.pos, o1.R, capboxside, normal, &depth, &code, flags, contact);
+        for (int i = 0; i < num; i++) { contact[i].normal[0] = normal[0]; contact[i].normal[1] = normal[1]; contact[i].normal[2] = normal[2]; }
+        return num;
+    }
+    return odeb_collide_spheres(pl, radius, pb, 0, contact);
+}
+
+// dCollideCapsuleCapsule capsule.cpp:240-353
+__device__ int odeb_capsule_capsule(const DGeom &o1, const DGeom &o2, int flags, DContactGeom *contact)
+{
+    int i;
+    const Real tolerance = R_(1e-5);
+    Real lz1 = o1.p[1] * R_(0.5), lz2 = o2.p[1] * R_(0.5);
+    const Real *pos1 = o1.pos, *pos2 = o2.pos;
+    Real axis1[3] = { o1.R[2], o1.R[6], o1.R[10] }, axis2[3] = { o2.R[2], o2.R[6], o2.R[10] };
+    Real sphere1[3], sphere2[3];
+    Real a1a2 = dot3(axis1, axis2);
+    Real det = R_(1.0) - a1a2 * a1a2;
+    if (det < tolerance) {
+        if (a1a2 < 0) { axis2[0] = -axis2[0]; axis2[1] = -axis2[1]; axis2[2] = -axis2[2]; }
+        Real q[3];
+        for (i = 0; i < 3; i++) q[i] = pos1[i] - pos2[i];
+        Real k = dot3(axis1, q);
+        Real a1lo = -lz1, a1hi = lz1, a2lo = -lz2 - k, a2hi = lz2 - k;
+        Real lo = (a1lo > a2lo) ? a1lo : a2lo;
+        Real hi = (a1hi < a2hi) ? a1hi : a2hi;
+        if (lo <= hi) {
+            int num_contacts = flags & ODEB_NUMC_MASK;
+            if (num_contacts >= 2 && lo < hi) {
+                for (i = 0; i < 3; i++) sphere1[i] = pos1[i] + lo * axis1[i];
+                for (i = 0; i < 3; i++) sphere2[i] = pos2[i] + (lo + k) * axis2[i];
+                int n1 = odeb_collide_spheres(sphere1, o1.p[0], sphere2, o2.p[0], contact);
+                if (n1) {
+                    for (i = 0; i < 3; i++) sphere1[i] = pos1[i] + hi * axis1[i];
+                    for (i = 0; i < 3; i++) sphere2[i] = pos2[i] + (hi + k) * axis2[i];
+                    int n2 = odeb_collide_spheres(sphere1, o1.p[0], sphere2, o2.p[0], contact + 1);
+                    if (n2) return 2;
+                }
+            }
+            Real alpha1 = (lo + hi) * R_(0.5);
+            Real alpha2 = alpha1 + k;
+            for (i = 0; i < 3; i++) sphere1[i] = pos1[i] + alpha1 * axis1[i];
+            for (i = 0; i < 3; i++) sphere2[i] = pos2[i] + alpha2 * axis2[i];
+            return odeb_collide_spheres(sphere1, o1.p[0], sphere2, o2.p[0], contact);
+        }
+    }
+    Real a1[3], a2[3], b1[3], b2[3];
+    for (i = 0; i < 3; i++) {
+        a1[i] = pos1[i] + axis1[i] * lz1; a2[i] = pos1[i] - axis1[i] * lz1;
+        b1[i] = pos2[i] + axis2[i] * lz2; b2[i] = pos2[i] - axis2[i] * lz2;
+    }
+    odeb_closest_segment_points(a1, a2, b1, b2, sphere1, sphere2);
+    return odeb_collide_spheres(sphere1, o1.p[0], sphere2, o2.p[0], contact);
+}
+
+// dCollideCapsulePlane capsule.cpp:356-415
+__device__ int odeb_capsule_plane(const DGeom &o1, const DGeom &o2, int flags, DContactGeom *contact)
+{
+    const Real *R = o1.R, *pl = o2.p;
+    Real radius = o1.p[0], lz = o1.p[1];
+    Real sign = (dot3s(pl, 1, R + 2, 4) > 0) ? R_(-1.0) : R_(1.0);
+    Real p[3];
+    p[0] = o1.pos[0] + R[2] * lz * R_(0.5) * sign;
+    p[1] = o1.pos[1] + R[6] * lz * R_(0.5) * sign;
+    p[2] = o1.pos[2] + R[10] * lz * R_(0.5) * sign;
+    Real k = dot3(p, pl);
+    Real depth = pl[3] - k + radius;
+    if (depth < 0) return 0;
+    contact[0].normal[0] = pl[0]; contact[0].normal[1] = pl[1]; contact[0].normal[2] = pl[2];
+    contact[0].pos[0] = p[0] - pl[0] * radius; contact[0].pos[1] = p[1] - pl[1] * radius; contact[0].pos[2] = p[2] - pl[2] * radius;
+    contact[0].depth = depth;
+    int ncontacts = 1;
+    if ((flags & ODEB_NUMC_MASK) >= 2) {
+        p[0] = o1.pos[0] - R[2] * lz * R_(0.5) * sign;
+        p[1] = o1.pos[1] - R[6] * lz * R_(0.5) * sign;
+        p[2] = o1.pos[2] - R[10] * lz * R_(0.5) * sign;
+        k = dot3(p, pl);
+        depth = pl[3] - k + radius;
+        if (depth >= 0) {
+            contact[1].normal[0] = pl[0]; contact[1].normal[1] = pl[1]; contact[1].normal[2] = pl[2];
+            contact[1].pos[0] = p[0] - pl[0] * radius; contact[1].pos[1] = p[1] - pl[1] * radius; contact[1].pos[2] = p[2] - pl[2] * radius;
+            contact[1].depth = depth;
+            ncontacts = 2;
+        }
+    }
+    return ncontacts;
+}
+
+
+// dCollide collision_kernel.cpp:292-338 with the collider table of dInitColliders (:166-268):
+// direct entries (sphere,sphere) (sphere,box) (sphere,plane) (box,box) (box,plane) (capsule,sphere)
+// (capsule,box) (capsule,capsule) (capsule,plane); the transposed pairs call the same function with
+// swapped arguments and negate the normals.
+__device__ int odeb_collide_direct(const DGeom &a, const DGeom &b, int flags, DContactGeom *c, int *handled)
+{
+    *handled = 1;
+    if (a.type == 0 && b.type == 0) return odeb_collide_spheres(a.pos, a.p[0], b.pos, b.p[0], c);
+    if (a.type == 0 && b.type == 1) return odeb_sphere_box(a, b, c);
+    if (a.type == 0 && b.type == 4) return odeb_sphere_plane(a, b, c);
+    if (a.type == 1 && b.type == 1) return odeb_collide_box_box(a, b, flags, c);
+    if (a.type == 1 && b.type == 4) return odeb_box_plane(a, b, flags, c);
+    if (a.type == 2 && b.type == 0) return odeb_capsule_sphere(a, b, c);
+    if (a.type == 2 && b.type == 1) return odeb_capsule_box(a, b, flags, c);
+    if (a.type == 2 && b.type == 2) return odeb_capsule_capsule(a, b, flags, c);
+    if (a.type == 2 && b.type == 4) return odeb_capsule_plane(a, b, flags, c);
+    *handled = 0;
+    return 0;
+}
+
+__device__ int odeb_collide(const DGeom &o1, const DGeom &o2, int flags, DContactGeom *c)
+{
+    if ((flags & ODEB_NUMC_MASK) == 0) return 0;
+    if (o1.body == o2.body && o1.body >= 0) return 0;
+    int handled;
+    int n = odeb_collide_direct(o1, o2, flags, c, &handled);
+    if (handled) return n;
+    n = odeb_collide_direct(o2, o1, flags, c, &handled);
+    if (!handled) return 0;
+    for (int i = 0; i < n; i++) { c[i].normal[0] = -c[i].normal[0]; c[i].normal[1] = -c[i].normal[1]; c[i].normal[2] = -c[i].normal[2]; }
+    return n;
+}
+#endif

@@ -1,0 +1,612 @@
+// odeb_host.inl -- host side of the C-ABI (include/ode_b200.h): mirrors world/body/geom/joint
+// descriptions into the SoA device buffers and launches the step kernels. No CPU fallback: every
+// entry point fails loudly when no CUDA device is usable.
+
+static thread_local std::string g_err;
+static void set_err(const char *fmt, ...)
+{
+    char buf[512]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    g_err = buf;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_err("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); return 0; } } while (0)
+
+struct OdebBatch {
+    DevParams P;
+    DevPtrs D;
+    int device;
+    cudaStream_t stream;
+    std::vector<void *> allocs;
+    size_t bytes;
+    uint64_t launches;
+    // optional per-kernel timing of k_solve
+    bool timing; cudaEvent_t ev0, ev1; double solver_ms; int solver_launches;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t> > pending;
+    // staging
+    Real4 *d_stage; size_t stage_elems;
+    Real4 *h_stage;
+    // cuda graph of one step
+    cudaGraphExec_t graph; double graph_h; bool use_graph;
+};
+
+template <class T> static bool dev_alloc(OdebBatch *B, T **p, size_t n)
+{
+    if (n == 0) n = 1;
+    void *q = 0;
+    cudaError_t e = cudaMalloc(&q, n * sizeof(T));
+    if (e != cudaSuccess) { set_err("cudaMalloc(%zu bytes) failed: %s", n * sizeof(T), cudaGetErrorString(e)); return false; }
+    cudaMemset(q, 0, n * sizeof(T));
+    B->allocs.push_back(q); B->bytes += n * sizeof(T);
+    *p = (T *)q;
+    return true;
+}
+template <class T> static bool upload(T *dst, const std::vector<T> &v)
+{
+    if (v.empty()) return true;
+    return cudaMemcpy(dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice) == cudaSuccess;
+}
+
+// dxFactorCholesky / dxSolveCholesky / dxInvertPDMatrix for n=3 (ode/src/matrix.cpp:107-253): dBodySetMass (ode.cpp:486-503)
+static int host_invert_pd3(const Real *A, Real *Ainv)
+{
+    Real L[12], recip[3];
+    memcpy(L, A, sizeof(L));
+    for (int i = 0; i < 3; i++) {
+        Real *aa = L + 4 * i;
+        for (int j = 0; j < i; j++) {
+            Real sum = aa[j];
+            const Real *bb = L + 4 * j;
+            for (int k = 0; k < j; k++) sum -= aa[k] * bb[k];
+            aa[j] = sum * recip[j];
+        }
+        Real sum = aa[i];
+        for (int k = 0; k < i; k++) sum -= aa[k] * aa[k];
+        if (sum <= R_(0.0)) return 0;
+        Real sq = RSQRT(sum);
+        aa[i] = sq;
+        recip[i] = rrecip(sq);
+    }
+    memset(Ainv, 0, 12 * sizeof(Real));
+    for (int col = 0; col < 3; col++) {
+        Real X[3] = { 0, 0, 0 }, y[3];
+        X[col] = R_(1.0);
+        for (int i = 0; i < 3; i++) {
+            Real sum = R_(0.0);
+            for (int k = 0; k < i; k++) sum += L[4 * i + k] * y[k];
+            y[i] = (X[i] - sum) / L[4 * i + i];
+        }
+        for (int i = 3; i > 0;) {
+            --i;
+            Real sum = R_(0.0);
+            for (int k = i + 1; k < 3; k++) sum += L[4 * k + i] * X[k];
+            X[i] = (y[i] - sum) / L[4 * i + i];
+        }
+        for (int i = 0; i < 3; i++) Ainv[4 * i + col] = X[i];
+    }
+    return 1;
+}
+
+struct HostBody { Real pos[3], q[4], R[12]; };
+
+// setAnchors joints/joint.cpp:289-320
+static void host_set_anchors(const std::vector<HostBody> &hb, DJointT &j, Real x, Real y, Real z)
+{
+    if (j.b0 >= 0) {
+        const HostBody &b0 = hb[j.b0];
+        Real q[3] = { x - b0.pos[0], y - b0.pos[1], z - b0.pos[2] };
+        mul1_331(j.anchor1, b0.R, q);
+        if (j.b1 >= 0) {
+            const HostBody &b1 = hb[j.b1];
+            Real q2[3] = { x - b1.pos[0], y - b1.pos[1], z - b1.pos[2] };
+            mul1_331(j.anchor2, b1.R, q2);
+        } else { j.anchor2[0] = x; j.anchor2[1] = y; j.anchor2[2] = z; }
+    }
+    j.anchor1[3] = 0; j.anchor2[3] = 0;
+}
+// setAxes joints/joint.cpp:325-369
+static void host_set_axes(const std::vector<HostBody> &hb, DJointT &j, Real x, Real y, Real z, Real *axis1, Real *axis2)
+{
+    if (j.b0 >= 0) {
+        Real q[3] = { x, y, z };
+        normalize3(q);
+        if (axis1) { mul1_331(axis1, hb[j.b0].R, q); axis1[3] = 0; }
+        if (axis2) {
+            if (j.b1 >= 0) mul1_331(axis2, hb[j.b1].R, q);
+            else { axis2[0] = x; axis2[1] = y; axis2[2] = z; }
+            axis2[3] = 0;
+        }
+    }
+}
+static void host_limot(DLimot &l, Real erp, Real cfm, const OdebJointDesc &d, int a)
+{   // dxJointLimitMotor::init + ::set joints/joint.cpp:494-540
+    l.vel = 0; l.fmax = 0; l.lostop = -R_INF; l.histop = R_INF; l.fudge_factor = 1;
+    l.normal_cfm = cfm; l.stop_erp = erp; l.stop_cfm = cfm; l.bounce = 0;
+    l.lostop = (Real)d.lo_stop[a]; l.histop = (Real)d.hi_stop[a];
+    l.vel = (Real)d.vel[a];
+    if ((Real)d.fmax[a] >= 0) l.fmax = (Real)d.fmax[a];
+    if (d.fudge_factor[a] >= 0 && (Real)d.fudge_factor[a] <= 1) l.fudge_factor = (Real)d.fudge_factor[a];
+    if (d.bounce[a] >= 0) l.bounce = (Real)d.bounce[a];
+    if (d.stop_erp[a] >= 0) l.stop_erp = (Real)d.stop_erp[a];
+    if (d.stop_cfm[a] >= 0) l.stop_cfm = (Real)d.stop_cfm[a];
+}
+
+static inline unsigned nblk(size_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
+
+extern "C" {
+
+const char *odeb_last_error(void) { return g_err.c_str(); }
+
+void odeb_destroy(OdebBatch *B)
+{
+    if (!B) return;
+    cudaSetDevice(B->device);
+    cudaDeviceSynchronize();
+    for (size_t i = 0; i < B->pending.size(); i++) { cudaEventDestroy(B->pending[i].first); cudaEventDestroy(B->pending[i].second); }
+    if (B->graph) cudaGraphExecDestroy(B->graph);
+    for (size_t i = 0; i < B->allocs.size(); i++) cudaFree(B->allocs[i]);
+    if (B->h_stage) cudaFreeHost(B->h_stage);
+    if (B->stream) cudaStreamDestroy(B->stream);
+    delete B;
+}
+
+OdebBatch *odeb_create(const OdebWorldParams *wp,
+                       int nbody, const OdebBodyDesc *bodies, const double *body_pos, const double *body_quat,
+                       int ngeom, const OdebGeomDesc *geoms,
+                       int njoint, const OdebJointDesc *joints,
+                       int nworlds, int device)
+{
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) { set_err("no CUDA device: %s (this library has no CPU path)", cudaGetErrorString(e)); return 0; }
+    if (device < 0 || device >= ndev) { set_err("bad device index %d (have %d)", device, ndev); return 0; }
+    if (cudaSetDevice(device) != cudaSuccess) { set_err("cudaSetDevice(%d) failed", device); return 0; }
+    if (nworlds <= 0 || nbody <= 0 || ngeom < 0 || njoint < 0) { set_err("bad sizes"); return 0; }
+    if (wp->surf_mode & (ODEB_CONTACT_FDIR1 | 0x400)) { set_err("contact modes FDir1 / Rolling are outside the supported policy"); return 0; }
+    if (wp->max_contacts < 1 || wp->max_contacts > 8) { set_err("max_contacts must be in 1..8"); return 0; }
+
+    OdebBatch *B = new OdebBatch();
+    B->device = device; B->bytes = 0; B->launches = 0; B->timing = false; B->solver_ms = 0; B->solver_launches = 0;
+    B->graph = 0; B->graph_h = -1; B->use_graph = getenv("ODEB_NO_GRAPH") == 0; B->h_stage = 0; B->d_stage = 0; B->stream = 0;
+    memset(&B->D, 0, sizeof(B->D));
+    DevParams &P = B->P;
+    memset(&P, 0, sizeof(P));
+    P.W = nworlds; P.NB = nbody; P.NG = ngeom; P.NJ = njoint;
+    P.maxc = wp->max_contacts; P.space_type = wp->space_type; P.skip_connected = wp->skip_connected;
+    {
+        long long all = (long long)ngeom * (ngeom - 1) / 2;
+        long long mp = all < 16LL * ngeom ? all : 16LL * ngeom;
+        if (const char *s = getenv("ODEB_MAX_PAIRS")) mp = atoll(s);
+        P.MP = (int)(mp < 1 ? 1 : mp);
+        long long mc = (long long)P.MP * P.maxc;
+        long long cap = 2LL * ngeom * P.maxc;
+        if (mc > cap) mc = cap;
+        if (const char *s = getenv("ODEB_MAX_CONTACTS")) mc = atoll(s);
+        P.MC = (int)(mc < 1 ? 1 : mc);
+    }
+    // contact policy: getInfo1 row count (contact.cpp:48-122) is uniform
+    DSurface &S = P.surf;
+    S.mode = wp->surf_mode;
+    S.mu = (Real)wp->mu < 0 ? 0 : (Real)wp->mu;
+    S.mu2 = (Real)wp->mu2 < 0 ? 0 : (Real)wp->mu2;
+    S.bounce = (Real)wp->bounce; S.bounce_vel = (Real)wp->bounce_vel; S.soft_erp = (Real)wp->soft_erp; S.soft_cfm = (Real)wp->soft_cfm;
+    S.motion1 = (Real)wp->motion1; S.motion2 = (Real)wp->motion2; S.motionN = (Real)wp->motionN; S.slip1 = (Real)wp->slip1; S.slip2 = (Real)wp->slip2;
+    {
+        int m = 1;
+        if (S.mode & ODEB_CONTACT_MU2) { if (S.mu > 0) m++; if (S.mu2 > 0) m++; }
+        else if (S.mu > 0) m += 2;
+        S.the_m = m; P.m_contact = m;
+    }
+    P.NJT = P.NJ + P.MC;
+    P.MR = P.MC * P.m_contact + P.NJ * 6;
+    for (int k = 0; k < 3; k++) P.gravity[k] = (Real)wp->gravity[k];
+    P.erp = (Real)wp->erp;
+#if defined(ODEB_DOUBLE)
+    P.cfm = wp->cfm >= 0 ? (Real)wp->cfm : R_(1e-10);
+#else
+    P.cfm = wp->cfm >= 0 ? (Real)wp->cfm : R_(1e-5);
+#endif
+    P.sor_w = (Real)wp->sor_w;
+    P.num_iter = wp->num_iterations > 1 ? wp->num_iterations : 1;
+    P.premature_delta = (Real)wp->premature_exit_delta; P.extra_delta = (Real)wp->extra_iter_delta;
+    { Real f = (Real)wp->max_extra_factor; Real ex = P.num_iter * f; P.max_extra = ex < (Real)UINT32_MAX ? (unsigned)ex : UINT32_MAX; }  // objects.h:177-184
+    P.dyn_enabled = (P.max_extra != 0 || P.premature_delta != 0) ? 1 : 0;
+    P.max_vel = (Real)wp->contact_max_vel; P.min_depth = (Real)wp->contact_surface_layer;
+    { Real t = (Real)wp->adis_linear_thr; P.adis_lin = t * t; t = (Real)wp->adis_angular_thr; P.adis_ang = t * t; }
+    P.adis_time = (Real)wp->adis_time; P.adis_steps = wp->adis_steps; P.adis_samples = wp->adis_samples;
+    P.damp_lin_scale = (Real)wp->linear_damping; P.damp_ang_scale = (Real)wp->angular_damping;
+    { Real t = (Real)wp->linear_damping_thr; P.damp_lin_thr = t * t; t = (Real)wp->angular_damping_thr; P.damp_ang_thr = t * t; }
+    P.max_ang_speed = (Real)wp->max_angular_speed;
+    P.solver_lanes = 8;
+    if (const char *s = getenv("ODEB_SOLVER_LANES")) { int v = atoi(s); if (v >= 1 && v <= 32) P.solver_lanes = v; }
+
+    // ---- template on the host
+    std::vector<Real> bmass(nbody), binvmass(nbody), bI(12 * nbody, 0), binvI(12 * nbody, 0);
+    std::vector<HostBody> hb(nbody);
+    std::vector<int> bflags0(nbody);
+    for (int i = 0; i < nbody; i++) {
+        bmass[i] = (Real)bodies[i].mass;
+        if (!(bmass[i] > 0)) { set_err("body %d: mass must be > 0", i); delete B; return 0; }
+        binvmass[i] = rrecip(bmass[i]);
+        const double *I = bodies[i].inertia;
+        Real *Ib = &bI[12 * i];
+        Ib[0] = (Real)I[0]; Ib[5] = (Real)I[4]; Ib[10] = (Real)I[8];          // dMassSetParameters mass.cpp:74-93
+        Ib[1] = (Real)I[1]; Ib[2] = (Real)I[2]; Ib[6] = (Real)I[5];
+        Ib[4] = (Real)I[1]; Ib[8] = (Real)I[2]; Ib[9] = (Real)I[5];
+        if (!host_invert_pd3(Ib, &binvI[12 * i])) { Real *v = &binvI[12 * i]; memset(v, 0, 12 * sizeof(Real)); v[0] = v[5] = v[10] = 1; }
+        HostBody &h = hb[i];
+        for (int k = 0; k < 3; k++) h.pos[k] = (Real)body_pos[3 * i + k];
+        for (int k = 0; k < 4; k++) h.q[k] = (Real)body_quat[4 * i + k];
+        normalize4(h.q); r_from_q(h.R, h.q);
+        int fl = BF_GYRO;
+        if (wp->auto_disable) fl |= BF_AUTO_DISABLE;
+        if (P.damp_lin_scale) fl |= BF_LIN_DAMP;
+        if (P.damp_ang_scale) fl |= BF_ANG_DAMP;
+        if (P.max_ang_speed < R_INF) fl |= BF_MAX_ANG_SPEED;
+        int sf = bodies[i].flags;
+        if (sf & ODEB_BODY_NO_GRAVITY) fl |= BF_NO_GRAVITY;
+        if (sf & ODEB_BODY_NO_GYRO) fl &= ~BF_GYRO;
+        if (sf & ODEB_BODY_FINITE_ROTATION) fl |= BF_FINITE_ROT;
+        if (sf & ODEB_BODY_DISABLED) fl |= BF_DISABLED;
+        bflags0[i] = fl;
+    }
+    std::vector<int> gtype(ngeom), gbody(ngeom); std::vector<Real> gparam(4 * ngeom); std::vector<unsigned> gcat(ngeom), gcol(ngeom);
+    for (int i = 0; i < ngeom; i++) {
+        gtype[i] = geoms[i].type; gbody[i] = geoms[i].body; gcat[i] = geoms[i].category_bits; gcol[i] = geoms[i].collide_bits;
+        if (gbody[i] >= nbody) { set_err("geom %d: bad body index", i); delete B; return 0; }
+        if (gtype[i] != ODEB_SPHERE && gtype[i] != ODEB_BOX && gtype[i] != ODEB_CAPSULE && gtype[i] != ODEB_PLANE) { set_err("geom %d: unsupported class %d", i, gtype[i]); delete B; return 0; }
+        Real *p = &gparam[4 * i];
+        for (int k = 0; k < 4; k++) p[k] = (Real)geoms[i].p[k];
+        if (gtype[i] == ODEB_PLANE) {   // make_sure_plane_normal_has_unit_length plane.cpp:48-63
+            Real l = p[0] * p[0] + p[1] * p[1] + p[2] * p[2];
+            if (l > 0) { l = rrecipsqrt(l); p[0] *= l; p[1] *= l; p[2] *= l; p[3] *= l; }
+            else { p[0] = 1; p[1] = 0; p[2] = 0; p[3] = 0; }
+        }
+    }
+    std::vector<DJointT> jt(njoint);
+    std::vector<std::vector<std::pair<int, int> > > adj(nbody);
+    std::vector<unsigned char> conn((size_t)nbody * nbody, 0);
+    for (int i = 0; i < njoint; i++) {
+        const OdebJointDesc &d = joints[i];
+        DJointT &j = jt[i];
+        memset(&j, 0, sizeof(j));
+        if (d.type != ODEB_JOINT_BALL && d.type != ODEB_JOINT_HINGE && d.type != ODEB_JOINT_UNIVERSAL) { set_err("joint %d: unsupported type %d", i, d.type); delete B; return 0; }
+        j.type = d.type; j.erp = P.erp; j.cfm = P.cfm;
+        int b1 = d.body1, b2 = d.body2;
+        if (b1 >= nbody || b2 >= nbody || (b1 < 0 && b2 < 0) || b1 == b2) { set_err("joint %d: bad bodies", i); delete B; return 0; }
+        if (b1 < 0) { b1 = b2; b2 = -1; j.reverse = 1; }         // dJointAttach ode.cpp:1404-1411
+        j.b0 = b1; j.b1 = b2;
+        adj[b1].push_back(std::make_pair(i, b2));
+        if (b2 >= 0) { adj[b2].push_back(std::make_pair(i, b1)); conn[(size_t)b1 * nbody + b2] = conn[(size_t)b2 * nbody + b1] = 1; }
+        host_set_anchors(hb, j, (Real)d.anchor[0], (Real)d.anchor[1], (Real)d.anchor[2]);
+        host_limot(j.limot1, P.erp, P.cfm, d, 0);
+        host_limot(j.limot2, P.erp, P.cfm, d, 1);
+        if (j.type == ODEB_JOINT_HINGE) {
+            j.axis1[0] = 1; j.axis2[0] = 1;
+            host_set_axes(hb, j, (Real)d.axis1[0], (Real)d.axis1[1], (Real)d.axis1[2], j.axis1, j.axis2);
+            if (j.b1 >= 0) qmul1(j.qrel, hb[j.b0].q, hb[j.b1].q);      // hinge.cpp:376-393
+            else { const Real *q = hb[j.b0].q; j.qrel[0] = q[0]; j.qrel[1] = -q[1]; j.qrel[2] = -q[2]; j.qrel[3] = -q[3]; }
+        } else if (j.type == ODEB_JOINT_UNIVERSAL) {
+            j.axis1[0] = 1; j.axis2[1] = 1;
+            if (j.reverse) host_set_axes(hb, j, (Real)d.axis1[0], (Real)d.axis1[1], (Real)d.axis1[2], 0, j.axis2);
+            else host_set_axes(hb, j, (Real)d.axis1[0], (Real)d.axis1[1], (Real)d.axis1[2], j.axis1, 0);
+            if (j.reverse) host_set_axes(hb, j, (Real)d.axis2[0], (Real)d.axis2[1], (Real)d.axis2[2], j.axis1, 0);
+            else host_set_axes(hb, j, (Real)d.axis2[0], (Real)d.axis2[1], (Real)d.axis2[2], 0, j.axis2);
+            Real ax1[3], ax2[3], R[12] = { 0 }, qcross[4];                 // universal.cpp:372-401
+            mul0_331(ax1, hb[j.b0].R, j.axis1);
+            if (j.b1 >= 0) mul0_331(ax2, hb[j.b1].R, j.axis2); else { ax2[0] = j.axis2[0]; ax2[1] = j.axis2[1]; ax2[2] = j.axis2[2]; }
+            odeb_r_from_2axes(R, ax1[0], ax1[1], ax1[2], ax2[0], ax2[1], ax2[2]);
+            q_from_r(qcross, R);
+            qmul1(j.qrel1, hb[j.b0].q, qcross);
+            odeb_r_from_2axes(R, ax2[0], ax2[1], ax2[2], ax1[0], ax1[1], ax1[2]);
+            q_from_r(qcross, R);
+            if (j.b1 >= 0) qmul1(j.qrel2, hb[j.b1].q, qcross); else for (int k = 0; k < 4; k++) j.qrel2[k] = qcross[k];
+        }
+    }
+    std::vector<int> sofs(nbody + 1, 0), sj, so;
+    for (int b = 0; b < nbody; b++) {
+        sofs[b] = (int)sj.size();
+        for (size_t k = 0; k < adj[b].size(); k++) { sj.push_back(adj[b][k].first); so.push_back(adj[b][k].second); }
+    }
+    sofs[nbody] = (int)sj.size();
+
+    // ---- device buffers
+    DevPtrs &D = B->D;
+    const size_t W = nworlds, WB = W * nbody, WG = W * ngeom, WJ = W * njoint;
+    const int NS = P.adis_samples > 0 ? P.adis_samples : 1;
+    bool ok = true;
+    ok = ok && dev_alloc(B, &D.pos, WB) && dev_alloc(B, &D.quat, WB) && dev_alloc(B, &D.lvel, WB) && dev_alloc(B, &D.avel, WB)
+            && dev_alloc(B, &D.facc, WB) && dev_alloc(B, &D.tacc, WB) && dev_alloc(B, &D.R, 3 * WB)
+            && dev_alloc(B, &D.bflags, WB) && dev_alloc(B, &D.adis_steps, WB) && dev_alloc(B, &D.adis_time, WB)
+            && dev_alloc(B, &D.avg_buf, WB * 6 * NS) && dev_alloc(B, &D.avg_counter, WB) && dev_alloc(B, &D.avg_ready, WB);
+    ok = ok && dev_alloc(B, &D.bmass, nbody) && dev_alloc(B, &D.binvmass, nbody) && dev_alloc(B, &D.bI, 12 * (size_t)nbody) && dev_alloc(B, &D.binvI, 12 * (size_t)nbody)
+            && dev_alloc(B, &D.gtype, ngeom) && dev_alloc(B, &D.gbody, ngeom) && dev_alloc(B, &D.gparam, 4 * (size_t)ngeom)
+            && dev_alloc(B, &D.gcat, ngeom) && dev_alloc(B, &D.gcol, ngeom) && dev_alloc(B, &D.joints, njoint)
+            && dev_alloc(B, &D.sadj_ofs, nbody + 1) && dev_alloc(B, &D.sadj_joint, sj.size()) && dev_alloc(B, &D.sadj_other, so.size())
+            && dev_alloc(B, &D.conn, (size_t)nbody * nbody);
+    ok = ok && dev_alloc(B, &D.aabb, WG * 6) && dev_alloc(B, &D.pair_cnt, WG) && dev_alloc(B, &D.pair_ofs, WG) && dev_alloc(B, &D.npairs, W)
+            && dev_alloc(B, &D.pairs, W * P.MP) && dev_alloc(B, &D.pc_count, W * P.MP) && dev_alloc(B, &D.cgeom, W * P.MP * P.maxc * 2)
+            && dev_alloc(B, &D.ncontacts, W) && dev_alloc(B, &D.cinfo, W * P.MC) && dev_alloc(B, &D.jm, WJ) && dev_alloc(B, &D.jlimit, WJ);
+    ok = ok && dev_alloc(B, &D.c_ofs, W * (nbody + 1)) && dev_alloc(B, &D.c_cur, WB) && dev_alloc(B, &D.c_adj_c, W * 2 * P.MC) && dev_alloc(B, &D.c_adj_o, W * 2 * P.MC)
+            && dev_alloc(B, &D.btag, WB) && dev_alloc(B, &D.jtag, W * P.NJT) && dev_alloc(B, &D.stack, WB)
+            && dev_alloc(B, &D.body_order, WB) && dev_alloc(B, &D.body_pos, WB) && dev_alloc(B, &D.body_island, WB)
+            && dev_alloc(B, &D.joint_order, W * P.NJT) && dev_alloc(B, &D.joint_row, W * P.NJT) && dev_alloc(B, &D.joint_island, W * P.NJT)
+            && dev_alloc(B, &D.island_info, WB) && dev_alloc(B, &D.nislands, W) && dev_alloc(B, &D.nordered, W) && dev_alloc(B, &D.njord, W) && dev_alloc(B, &D.mrows, W);
+    ok = ok && dev_alloc(B, &D.J, W * P.MR * 4) && dev_alloc(B, &D.iMJ, W * P.MR * 4) && dev_alloc(B, &D.findex, W * P.MR) && dev_alloc(B, &D.order, W * P.MR)
+            && dev_alloc(B, &D.lambda, W * P.MR) && dev_alloc(B, &D.cforce, WB * 2) && dev_alloc(B, &D.invIw, WB * 12)
+            && dev_alloc(B, &D.stats, W * 4) && dev_alloc(B, &D.seed, W) && dev_alloc(B, &D.sweeps, 2 * W) && dev_alloc(B, &D.overflow, 1);
+    B->stage_elems = WB;
+    ok = ok && dev_alloc(B, &B->d_stage, WB);
+    if (ok && cudaMallocHost((void **)&B->h_stage, WB * sizeof(Real4)) != cudaSuccess) { set_err("cudaMallocHost failed"); ok = false; }
+    if (ok && cudaStreamCreateWithFlags(&B->stream, cudaStreamNonBlocking) != cudaSuccess) { set_err("cudaStreamCreate failed"); ok = false; }
+    if (!ok) { odeb_destroy(B); return 0; }
+
+    ok = upload(D.bmass, bmass) && upload(D.binvmass, binvmass) && upload(D.bI, bI) && upload(D.binvI, binvI)
+      && upload(D.gtype, gtype) && upload(D.gbody, gbody) && upload(D.gparam, gparam) && upload(D.gcat, gcat) && upload(D.gcol, gcol)
+      && upload(D.joints, jt) && upload(D.sadj_ofs, sofs) && upload(D.sadj_joint, sj) && upload(D.sadj_other, so) && upload(D.conn, conn);
+    // initial per-world state = template pose
+    {
+        std::vector<Real4> pos(WB), quat(WB), R(3 * WB);
+        std::vector<int> fl(WB), st(WB); std::vector<Real> tl(WB);
+        for (size_t w = 0; w < W; w++) for (int i = 0; i < nbody; i++) {
+            size_t k = w * nbody + i;
+            const HostBody &h = hb[i];
+            Real4 p = { h.pos[0], h.pos[1], h.pos[2], 0 }, q = { h.q[0], h.q[1], h.q[2], h.q[3] };
+            pos[k] = p; quat[k] = q;
+            Real4 r0 = { h.R[0], h.R[1], h.R[2], 0 }, r1 = { h.R[4], h.R[5], h.R[6], 0 }, r2 = { h.R[8], h.R[9], h.R[10], 0 };
+            R[3 * k] = r0; R[3 * k + 1] = r1; R[3 * k + 2] = r2;
+            fl[k] = bflags0[i]; st[k] = P.adis_steps; tl[k] = P.adis_time;
+        }
+        ok = ok && upload(D.pos, pos) && upload(D.quat, quat) && upload(D.R, R) && upload(D.bflags, fl) && upload(D.adis_steps, st) && upload(D.adis_time, tl);
+    }
+    if (!ok || cudaDeviceSynchronize() != cudaSuccess) { set_err("template upload failed: %s", cudaGetErrorString(cudaGetLastError())); odeb_destroy(B); return 0; }
+    return B;
+}
+
+static int stage_up(OdebBatch *B, const Real *src, int k, Real4 *dst)
+{
+    const size_t n = (size_t)B->P.W * B->P.NB;
+    for (size_t i = 0; i < n; i++) {
+        Real4 v = { src[k * i], src[k * i + 1], src[k * i + 2], k == 4 ? src[k * i + 3] : R_(0.0) };
+        B->h_stage[i] = v;
+    }
+    CK(cudaMemcpyAsync(dst, B->h_stage, n * sizeof(Real4), cudaMemcpyHostToDevice, B->stream));
+    CK(cudaStreamSynchronize(B->stream));
+    return 1;
+}
+static int stage_down(OdebBatch *B, Real *dst, int k, const Real4 *src)
+{
+    const size_t n = (size_t)B->P.W * B->P.NB;
+    CK(cudaMemcpyAsync(B->h_stage, src, n * sizeof(Real4), cudaMemcpyDeviceToHost, B->stream));
+    CK(cudaStreamSynchronize(B->stream));
+    for (size_t i = 0; i < n; i++) {
+        Real4 v = B->h_stage[i];
+        dst[k * i] = v.x; dst[k * i + 1] = v.y; dst[k * i + 2] = v.z; if (k == 4) dst[k * i + 3] = v.w;
+    }
+    return 1;
+}
+
+int odeb_set_state(OdebBatch *B, const odeb_real *pos, const odeb_real *quat, const odeb_real *lvel, const odeb_real *avel)
+{
+    CK(cudaSetDevice(B->device));
+    const size_t n = (size_t)B->P.W * B->P.NB;
+    if (pos && !stage_up(B, pos, 3, B->D.pos)) return 0;
+    if (quat) {
+        if (!stage_up(B, quat, 4, B->D.quat)) return 0;
+        k_set_quat<<<nblk(n, 128), 128, 0, B->stream>>>((int)n, B->D.quat, B->D.R);
+        B->launches++;
+        CK(cudaStreamSynchronize(B->stream));
+    }
+    if (lvel && !stage_up(B, lvel, 3, B->D.lvel)) return 0;
+    if (avel && !stage_up(B, avel, 3, B->D.avel)) return 0;
+    return 1;
+}
+
+int odeb_get_state(OdebBatch *B, odeb_real *pos, odeb_real *quat, odeb_real *lvel, odeb_real *avel)
+{
+    CK(cudaSetDevice(B->device));
+    if (pos && !stage_down(B, pos, 3, B->D.pos)) return 0;
+    if (quat && !stage_down(B, quat, 4, B->D.quat)) return 0;
+    if (lvel && !stage_down(B, lvel, 3, B->D.lvel)) return 0;
+    if (avel && !stage_down(B, avel, 3, B->D.avel)) return 0;
+    return 1;
+}
+
+int odeb_add_force(OdebBatch *B, const odeb_real *force, const odeb_real *torque)
+{
+    CK(cudaSetDevice(B->device));
+    const size_t n = (size_t)B->P.W * B->P.NB;
+    if (force) { if (!stage_up(B, force, 3, B->d_stage)) return 0; k_add4<<<nblk(n, 256), 256, 0, B->stream>>>(n, B->D.facc, B->d_stage); B->launches++; CK(cudaStreamSynchronize(B->stream)); }
+    if (torque) { if (!stage_up(B, torque, 3, B->d_stage)) return 0; k_add4<<<nblk(n, 256), 256, 0, B->stream>>>(n, B->D.tacc, B->d_stage); B->launches++; CK(cudaStreamSynchronize(B->stream)); }
+    return 1;
+}
+
+int odeb_set_seeds(OdebBatch *B, const uint32_t *seeds)
+{
+    CK(cudaSetDevice(B->device));
+    CK(cudaMemcpy(B->D.seed, seeds, B->P.W * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    return 1;
+}
+int odeb_get_seeds(OdebBatch *B, uint32_t *seeds)
+{
+    CK(cudaSetDevice(B->device));
+    CK(cudaStreamSynchronize(B->stream));
+    CK(cudaMemcpy(seeds, B->D.seed, B->P.W * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return 1;
+}
+int odeb_get_enabled(OdebBatch *B, int *enabled)
+{
+    CK(cudaSetDevice(B->device));
+    CK(cudaStreamSynchronize(B->stream));
+    const size_t n = (size_t)B->P.W * B->P.NB;
+    CK(cudaMemcpy(enabled, B->D.bflags, n * sizeof(int), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; i++) enabled[i] = !(enabled[i] & BF_DISABLED);
+    return 1;
+}
+
+static int launch_step(OdebBatch *B, cudaStream_t s, bool timed)
+{
+    const DevParams &P = B->P; const DevPtrs &D = B->D;
+    const size_t W = P.W;
+    if (P.NG > 0) {
+        k_aabb<<<nblk(W * P.NG, 128), 128, 0, s>>>(P, D);
+        k_pair_pass<false><<<nblk(W * P.NG, 128), 128, 0, s>>>(P, D);
+        k_pair_scan<<<nblk(W, 64), 64, 0, s>>>(P, D);
+        k_pair_pass<true><<<nblk(W * P.NG, 128), 128, 0, s>>>(P, D);
+        k_narrow<<<nblk(W * P.MP, 64), 64, 0, s>>>(P, D);
+        B->launches += 5;
+    }
+    if (P.NJ > 0) { k_joint_info1<<<nblk(W * P.NJ, 128), 128, 0, s>>>(P, D); B->launches++; }
+    k_islands<<<nblk(W, 32), 32, 0, s>>>(P, D);
+    k_body_pre<<<nblk(W * P.NB, 128), 128, 0, s>>>(P, D);
+    k_rows<<<nblk(W * P.NJT, 64), 64, 0, s>>>(P, D);
+    k_rows_finish<<<nblk(W * P.MR, 128), 128, 0, s>>>(P, D);
+    cudaEvent_t e0 = 0, e1 = 0;
+    if (timed) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s); }
+    {
+        size_t warps = (W + P.solver_lanes - 1) / P.solver_lanes;
+        const int wpb = 4;
+        k_solve<<<nblk(warps, wpb), wpb * 32, 0, s>>>(P, D);
+    }
+    if (timed) { cudaEventRecord(e1, s); B->pending.push_back(std::make_pair(e0, e1)); }
+    k_integrate<<<nblk(W * P.NB, 128), 128, 0, s>>>(P, D);
+    B->launches += 6;
+    return 1;
+}
+
+int odeb_step_async(OdebBatch *B, double h, int nsteps)
+{
+    CK(cudaSetDevice(B->device));
+    if (!(h > 0)) { set_err("stepsize must be > 0"); return 0; }
+    B->P.h = (Real)h; B->P.hrecip = rrecip((Real)h);
+    const bool graph_ok = B->use_graph && !B->timing;
+    if (graph_ok && (B->graph == 0 || B->graph_h != h)) {
+        if (B->graph) { cudaGraphExecDestroy(B->graph); B->graph = 0; }
+        cudaGraph_t g = 0;
+        uint64_t l0 = B->launches;
+        CK(cudaStreamBeginCapture(B->stream, cudaStreamCaptureModeThreadLocal));
+        launch_step(B, B->stream, false);
+        CK(cudaStreamEndCapture(B->stream, &g));
+        B->launches = l0;
+        CK(cudaGraphInstantiate(&B->graph, g, 0));
+        cudaGraphDestroy(g);
+        B->graph_h = h;
+    }
+    for (int s = 0; s < nsteps; s++) {
+        if (graph_ok) {
+            CK(cudaGraphLaunch(B->graph, B->stream));
+            B->launches += (B->P.NG > 0 ? 5 : 0) + (B->P.NJ > 0 ? 1 : 0) + 6;
+        } else launch_step(B, B->stream, B->timing);
+    }
+    CK(cudaGetLastError());
+    return 1;
+}
+
+int odeb_sync(OdebBatch *B)
+{
+    CK(cudaSetDevice(B->device));
+    CK(cudaStreamSynchronize(B->stream));
+    for (size_t i = 0; i < B->pending.size(); i++) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, B->pending[i].first, B->pending[i].second);
+        B->solver_ms += ms; B->solver_launches++;
+        cudaEventDestroy(B->pending[i].first); cudaEventDestroy(B->pending[i].second);
+    }
+    B->pending.clear();
+    int ov = 0;
+    CK(cudaMemcpy(&ov, B->D.overflow, sizeof(int), cudaMemcpyDeviceToHost));
+    if (ov) {
+        set_err("capacity overflow (%s): raise ODEB_MAX_PAIRS / ODEB_MAX_CONTACTS", ov == 1 ? "pairs" : ov == 2 ? "contacts" : "rows");
+        cudaMemset(B->D.overflow, 0, sizeof(int));
+        return 0;
+    }
+    return 1;
+}
+
+int odeb_step(OdebBatch *B, double h, int nsteps)
+{
+    if (!odeb_step_async(B, h, nsteps)) return 0;
+    return odeb_sync(B);
+}
+
+uint64_t odeb_launch_count(const OdebBatch *B) { return B->launches; }
+void odeb_enable_timing(OdebBatch *B, int on) { B->timing = on != 0; }
+double odeb_solver_ms(OdebBatch *B, int *launches)
+{
+    double v = B->solver_ms;
+    if (launches) *launches = B->solver_launches;
+    B->solver_ms = 0; B->solver_launches = 0;
+    return v;
+}
+
+int odeb_get_pairs(OdebBatch *B, int world, int *pairs, int cap)
+{
+    CK(cudaSetDevice(B->device));
+    CK(cudaStreamSynchronize(B->stream));
+    int n = 0;
+    CK(cudaMemcpy(&n, B->D.npairs + world, sizeof(int), cudaMemcpyDeviceToHost));
+    int m = n < cap ? n : cap;
+    if (m > 0) CK(cudaMemcpy(pairs, B->D.pairs + (size_t)world * B->P.MP, (size_t)m * sizeof(int2), cudaMemcpyDeviceToHost));
+    return n;
+}
+
+int odeb_get_contacts(OdebBatch *B, int world, odeb_real *geom7, int *g12, int cap)
+{
+    CK(cudaSetDevice(B->device));
+    CK(cudaStreamSynchronize(B->stream));
+    const DevParams &P = B->P;
+    int n = 0;
+    CK(cudaMemcpy(&n, B->D.ncontacts + world, sizeof(int), cudaMemcpyDeviceToHost));
+    if (n == 0) return 0;
+    std::vector<int4> ci(n);
+    CK(cudaMemcpy(ci.data(), B->D.cinfo + (size_t)world * P.MC, n * sizeof(int4), cudaMemcpyDeviceToHost));
+    int np = 0;
+    CK(cudaMemcpy(&np, B->D.npairs + world, sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<int2> pr(np);
+    CK(cudaMemcpy(pr.data(), B->D.pairs + (size_t)world * P.MP, np * sizeof(int2), cudaMemcpyDeviceToHost));
+    std::vector<Real4> cg((size_t)np * P.maxc * 2);
+    CK(cudaMemcpy(cg.data(), B->D.cgeom + (size_t)world * P.MP * P.maxc * 2, cg.size() * sizeof(Real4), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n && i < cap; i++) {
+        int slot = ci[i].x;
+        Real4 a = cg[2 * slot], b = cg[2 * slot + 1];
+        geom7[7 * i] = a.x; geom7[7 * i + 1] = a.y; geom7[7 * i + 2] = a.z;
+        geom7[7 * i + 3] = b.x; geom7[7 * i + 4] = b.y; geom7[7 * i + 5] = b.z; geom7[7 * i + 6] = a.w;
+        int2 p = pr[slot / P.maxc];
+        g12[2 * i] = p.x; g12[2 * i + 1] = p.y;
+    }
+    return n;
+}
+
+int odeb_get_islands(OdebBatch *B, int world, int *label_per_body)
+{
+    CK(cudaSetDevice(B->device));
+    CK(cudaStreamSynchronize(B->stream));
+    int n = 0;
+    CK(cudaMemcpy(&n, B->D.nislands + world, sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(label_per_body, B->D.body_island + (size_t)world * B->P.NB, B->P.NB * sizeof(int), cudaMemcpyDeviceToHost));
+    return n;
+}
+
+int odeb_get_stats(OdebBatch *B, int world, OdebStats *out)
+{
+    CK(cudaSetDevice(B->device));
+    CK(cudaStreamSynchronize(B->stream));
+    CK(cudaMemcpy(out->v, B->D.stats + 4 * (size_t)world, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    return 1;
+}
+
+int odeb_get_totals(OdebBatch *B, uint64_t out[6])
+{
+    CK(cudaSetDevice(B->device));
+    CK(cudaStreamSynchronize(B->stream));
+    const int W = B->P.W;
+    std::vector<int> a(W), b(W), c(W), d(W); std::vector<unsigned long long> s(2 * (size_t)W);
+    CK(cudaMemcpy(a.data(), B->D.npairs, W * sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(b.data(), B->D.ncontacts, W * sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(c.data(), B->D.mrows, W * sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(d.data(), B->D.nislands, W * sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(s.data(), B->D.sweeps, 2 * (size_t)W * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 6; k++) out[k] = 0;
+    for (int w = 0; w < W; w++) { out[0] += a[w]; out[1] += b[w]; out[2] += c[w]; out[3] += d[w]; out[4] += s[2 * (size_t)w]; out[5] += s[2 * (size_t)w + 1]; }
+    return 1;
+}
+
+} // extern "C"

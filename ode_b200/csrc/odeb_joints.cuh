@@ -1,0 +1,323 @@
+// odeb_joints.cuh -- device-side constraint-row builders (the reference's getInfo1/getInfo2 contract)
+// for contact, ball, hinge and universal joints. One thread builds all rows of one joint in the
+// reference's 16-wide row layout [J1l(3) J1a(3) rhs cfm J2l(3) J2a(3) lo hi] (quickstep.cpp:267-322).
+// Operation order follows the cited reference functions.
+#ifndef ODEB_JOINTS_CUH
+#define ODEB_JOINTS_CUH
+#include "odeb_math.cuh"
+
+enum { ROWLEN = 16, C_J1L = 0, C_J1A = 3, C_RHS = 6, C_CFM = 7, C_J2L = 8, C_J2A = 11, C_LO = 14, C_HI = 15 };
+
+struct DBody { Real pos[3], q[4], lvel[3], avel[3], R[12]; };
+
+struct DLimot {     // dxJointLimitMotor, static part (joints/joint.h:291-320)
+    Real vel, fmax, lostop, histop, fudge_factor, normal_cfm, stop_erp, stop_cfm, bounce;
+};
+
+struct DJointT {    // template (per-batch) description of a permanent joint, after dJointAttach's swap
+    int type, b0, b1, reverse;
+    Real anchor1[4], anchor2[4], axis1[4], axis2[4], qrel[4], qrel1[4], qrel2[4];
+    Real erp, cfm;
+    DLimot limot1, limot2;
+};
+
+struct DLimitState { int limit1, limit2; Real err1, err2; };
+
+__host__ __device__ __forceinline__ void odeb_qmul3(Real *qa, const Real *qb, const Real *qc)
+{   // dQMultiply3 rotation.cpp:221-228
+    qa[0] = qb[0] * qc[0] - qb[1] * qc[1] - qb[2] * qc[2] - qb[3] * qc[3];
+    qa[1] = -qb[0] * qc[1] - qb[1] * qc[0] + qb[2] * qc[3] - qb[3] * qc[2];
+    qa[2] = -qb[0] * qc[2] - qb[2] * qc[0] + qb[3] * qc[1] - qb[1] * qc[3];
+    qa[3] = -qb[0] * qc[3] - qb[3] * qc[0] + qb[1] * qc[2] - qb[2] * qc[1];
+}
+
+// dRFrom2Axes rotation.cpp:94-133
+__host__ __device__ __forceinline__ bool odeb_r_from_2axes(Real *R, Real ax, Real ay, Real az, Real bx, Real by, Real bz)
+{
+    Real l = RSQRT(ax * ax + ay * ay + az * az), k;
+    if (l <= R_(0.0)) return false;
+    l = rrecip(l); ax *= l; ay *= l; az *= l;
+    k = ax * bx + ay * by + az * bz;
+    bx -= k * ax; by -= k * ay; bz -= k * az;
+    l = RSQRT(bx * bx + by * by + bz * bz);
+    if (l <= R_(0.0)) return false;
+    l = rrecip(l); bx *= l; by *= l; bz *= l;
+    R[0] = ax; R[4] = ay; R[8] = az;
+    R[1] = bx; R[5] = by; R[9] = bz;
+    R[2] = -by * az + ay * bz; R[6] = -bz * ax + az * bx; R[10] = -bx * ay + ax * by;
+    R[3] = R[7] = R[11] = R_(0.0);
+    return true;
+}
+
+// setBall joints/joint.cpp:111-157
+__device__ void odeb_set_ball(const DBody &b0, const DBody *b1, Real fps, Real erp, Real *row, const Real *anchor1, const Real *anchor2)
+{
+    Real a1[3], a2[3];
+    row[C_J1L + 0] = 1; row[ROWLEN + C_J1L + 1] = 1; row[2 * ROWLEN + C_J1L + 2] = 1;
+    mul0_331(a1, b0.R, anchor1);
+    row[C_J1A + 1] = +a1[2]; row[C_J1A + 2] = -a1[1];
+    row[ROWLEN + C_J1A + 0] = -a1[2]; row[ROWLEN + C_J1A + 2] = +a1[0];
+    row[2 * ROWLEN + C_J1A + 0] = +a1[1]; row[2 * ROWLEN + C_J1A + 1] = -a1[0];
+    if (b1) {
+        row[C_J2L + 0] = -1; row[ROWLEN + C_J2L + 1] = -1; row[2 * ROWLEN + C_J2L + 2] = -1;
+        mul0_331(a2, b1->R, anchor2);
+        row[C_J2A + 1] = -a2[2]; row[C_J2A + 2] = +a2[1];
+        row[ROWLEN + C_J2A + 0] = +a2[2]; row[ROWLEN + C_J2A + 2] = -a2[0];
+        row[2 * ROWLEN + C_J2A + 0] = -a2[1]; row[2 * ROWLEN + C_J2A + 1] = +a2[0];
+    }
+    Real k = fps * erp;
+    if (b1) { for (int t = 0; t < 3; t++) row[t * ROWLEN + C_RHS] = k * (a2[t] + b1->pos[t] - a1[t] - b0.pos[t]); }
+    else { for (int t = 0; t < 3; t++) row[t * ROWLEN + C_RHS] = k * (anchor2[t] - a1[t] - b0.pos[t]); }
+}
+
+// getHingeAngleFromRelativeQuat joints/joint.cpp:421-458
+__device__ Real odeb_hinge_angle_from_relq(const Real *qrel, const Real *axis)
+{
+    Real cost2 = qrel[0];
+    Real sint2 = RSQRT(qrel[1] * qrel[1] + qrel[2] * qrel[2] + qrel[3] * qrel[3]);
+    Real theta = (dot3(qrel + 1, axis) >= 0) ? (2 * RATAN2(sint2, cost2)) : (2 * RATAN2(sint2, -cost2));
+    if (theta > M_PI) theta -= (Real)(2 * M_PI);
+    theta = -theta;
+    return theta;
+}
+
+// getHingeAngle joints/joint.cpp:470-490
+__device__ Real odeb_hinge_angle(const DBody &b0, const DBody *b1, const Real *axis, const Real *q_initial)
+{
+    Real qrel[4];
+    if (b1) { Real qq[4]; qmul1(qq, b0.q, b1->q); qmul2(qrel, qq, q_initial); }
+    else odeb_qmul3(qrel, b0.q, q_initial);
+    return odeb_hinge_angle_from_relq(qrel, axis);
+}
+
+// dxJointLimitMotor::testRotationalLimit joints/joint.cpp:574-593
+__device__ __forceinline__ bool odeb_limot_test(const DLimot &l, Real angle, int *limit, Real *err)
+{
+    if (angle <= l.lostop) { *limit = 1; *err = angle - l.lostop; return true; }
+    if (angle >= l.histop) { *limit = 2; *err = angle - l.histop; return true; }
+    *limit = 0;
+    return false;
+}
+
+// dxJointLimitMotor::addLimot joints/joint.cpp:596-780 (rotational). Torque applied to the bodies when
+// powered at a limit is returned in tq (added to b1.tacc, subtracted from b0.tacc by the caller).
+__device__ bool odeb_add_limot(const DLimot &l, int limit, Real limit_err, const DBody &b0, const DBody *b1,
+                               Real fps, Real *row, const Real *ax1, Real *tq, bool *has_tq)
+{
+    int powered = l.fmax > 0;
+    if (!(powered || limit)) return false;
+    row[C_J1A] = ax1[0]; row[C_J1A + 1] = ax1[1]; row[C_J1A + 2] = ax1[2];
+    if (b1) { row[C_J2A] = -ax1[0]; row[C_J2A + 1] = -ax1[1]; row[C_J2A + 2] = -ax1[2]; }
+    if (limit && (l.lostop == l.histop)) powered = 0;
+    if (powered) {
+        row[C_CFM] = l.normal_cfm;
+        if (!limit) { row[C_RHS] = l.vel; row[C_LO] = -l.fmax; row[C_HI] = l.fmax; }
+        else {
+            Real fm = l.fmax;
+            if ((l.vel > 0) || (l.vel == 0 && limit == 2)) fm = -fm;
+            if ((limit == 1 && l.vel > 0) || (limit == 2 && l.vel < 0)) fm *= l.fudge_factor;
+            tq[0] = fm * ax1[0]; tq[1] = fm * ax1[1]; tq[2] = fm * ax1[2];
+            *has_tq = true;
+        }
+    }
+    if (limit) {
+        Real k = fps * l.stop_erp;
+        row[C_RHS] = -k * limit_err;
+        row[C_CFM] = l.stop_cfm;
+        if (l.lostop == l.histop) { row[C_LO] = -R_INF; row[C_HI] = R_INF; }
+        else {
+            if (limit == 1) { row[C_LO] = 0; row[C_HI] = R_INF; } else { row[C_LO] = -R_INF; row[C_HI] = 0; }
+            if (l.bounce > 0) {
+                Real vel = dot3(b0.avel, ax1);
+                if (b1) vel -= dot3(b1->avel, ax1);
+                if (limit == 1) { if (vel < 0) { Real newc = -l.bounce * vel; if (newc > row[C_RHS]) row[C_RHS] = newc; } }
+                else { if (vel > 0) { Real newc = -l.bounce * vel; if (newc < row[C_RHS]) row[C_RHS] = newc; } }
+            }
+        }
+    }
+    return true;
+}
+
+// dxJointUniversal::getAxes universal.cpp:55-71
+__device__ __forceinline__ void odeb_universal_axes(const DJointT &j, const DBody &b0, const DBody *b1, Real *ax1, Real *ax2)
+{
+    mul0_331(ax1, b0.R, j.axis1);
+    if (b1) mul0_331(ax2, b1->R, j.axis2);
+    else { ax2[0] = j.axis2[0]; ax2[1] = j.axis2[1]; ax2[2] = j.axis2[2]; }
+}
+
+// dxJointUniversal::getAngles universal.cpp:73-166
+__device__ void odeb_universal_angles(const DJointT &j, const DBody &b0, const DBody *b1, Real *angle1, Real *angle2)
+{
+    Real ax1[3], ax2[3], R[12], qcross[4], qq[4], qrel[4];
+    odeb_universal_axes(j, b0, b1, ax1, ax2);
+    odeb_r_from_2axes(R, ax1[0], ax1[1], ax1[2], ax2[0], ax2[1], ax2[2]);
+    q_from_r(qcross, R);
+    qmul1(qq, b0.q, qcross);
+    qmul2(qrel, qq, j.qrel1);
+    *angle1 = odeb_hinge_angle_from_relq(qrel, j.axis1);
+    Real qcross2[4];
+    qrel[0] = 0; qrel[1] = ax1[0] + ax2[0]; qrel[2] = ax1[1] + ax2[1]; qrel[3] = ax1[2] + ax2[2];
+    Real l = rrecip(RSQRT(qrel[1] * qrel[1] + qrel[2] * qrel[2] + qrel[3] * qrel[3]));
+    qrel[1] *= l; qrel[2] *= l; qrel[3] *= l;
+    qmul0(qcross2, qrel, qcross);
+    if (b1) { qmul1(qq, b1->q, qcross2); qmul2(qrel, qq, j.qrel2); }
+    else qmul2(qrel, qcross2, j.qrel2);
+    *angle2 = -odeb_hinge_angle_from_relq(qrel, j.axis2);
+}
+
+// getInfo1 of hinge (hinge.cpp:54-74) and universal (universal.cpp:266-293): row count + limit state
+__device__ void odeb_joint_info1(const DJointT &j, const DBody &b0, const DBody *b1, int *m, DLimitState *ls)
+{
+    ls->limit1 = ls->limit2 = 0; ls->err1 = ls->err2 = 0;
+    if (j.type == 1) { *m = 3; return; }
+    if (j.type == 2) {
+        int mm = (j.limot1.fmax > 0) ? 6 : 5;
+        if ((j.limot1.lostop >= -M_PI || j.limot1.histop <= M_PI) && j.limot1.lostop <= j.limot1.histop) {
+            Real angle = odeb_hinge_angle(b0, b1, j.axis1, j.qrel);
+            if (odeb_limot_test(j.limot1, angle, &ls->limit1, &ls->err1)) mm = 6;
+        }
+        *m = mm;
+        return;
+    }
+    int mm = 4;
+    bool lim1 = (j.limot1.lostop >= -M_PI || j.limot1.histop <= M_PI) && j.limot1.lostop <= j.limot1.histop;
+    bool lim2 = (j.limot2.lostop >= -M_PI || j.limot2.histop <= M_PI) && j.limot2.lostop <= j.limot2.histop;
+    if (lim1 || lim2) {
+        Real a1, a2;
+        odeb_universal_angles(j, b0, b1, &a1, &a2);
+        if (lim1) odeb_limot_test(j.limot1, a1, &ls->limit1, &ls->err1);
+        if (lim2) odeb_limot_test(j.limot2, a2, &ls->limit2, &ls->err2);
+    }
+    if (ls->limit1 || j.limot1.fmax > 0) mm++;
+    if (ls->limit2 || j.limot2.fmax > 0) mm++;
+    *m = mm;
+}
+
+// getInfo2 of ball (ball.cpp:57-67), hinge (hinge.cpp:77-147), universal (universal.cpp:297-369).
+// tq0 accumulates the torque the limit motors add to body0 (negated) / body1.
+__device__ void odeb_joint_info2(const DJointT &j, const DLimitState &ls, const DBody &b0, const DBody *b1,
+                                 Real fps, Real worldERP, Real *row, Real *tq, bool *has_tq)
+{
+    if (j.type == 1) {
+        row[C_CFM] = j.cfm; row[ROWLEN + C_CFM] = j.cfm; row[2 * ROWLEN + C_CFM] = j.cfm;
+        odeb_set_ball(b0, b1, fps, j.erp, row, j.anchor1, j.anchor2);
+        return;
+    }
+    odeb_set_ball(b0, b1, fps, worldERP, row, j.anchor1, j.anchor2);
+    if (j.type == 2) {
+        Real ax1[3], p[3], q[3];
+        mul0_331(ax1, b0.R, j.axis1);
+        plane_space(ax1, p, q);
+        Real *r3 = row + 3 * ROWLEN, *r4 = row + 4 * ROWLEN;
+        r3[C_J1A] = p[0]; r3[C_J1A + 1] = p[1]; r3[C_J1A + 2] = p[2];
+        if (b1) { r3[C_J2A] = -p[0]; r3[C_J2A + 1] = -p[1]; r3[C_J2A + 2] = -p[2]; }
+        r4[C_J1A] = q[0]; r4[C_J1A + 1] = q[1]; r4[C_J1A + 2] = q[2];
+        if (b1) { r4[C_J2A] = -q[0]; r4[C_J2A + 1] = -q[1]; r4[C_J2A + 2] = -q[2]; }
+        Real b[3];
+        if (b1) { Real ax2[3]; mul0_331(ax2, b1->R, j.axis2); cross3(b, ax1, ax2); }
+        else cross3(b, ax1, j.axis2);
+        Real k = fps * worldERP;
+        r3[C_RHS] = k * dot3(b, p);
+        r4[C_RHS] = k * dot3(b, q);
+        Real t[3];
+        bool ht = false;
+        odeb_add_limot(j.limot1, ls.limit1, ls.err1, b0, b1, fps, row + 5 * ROWLEN, ax1, t, &ht);
+        if (ht) { tq[0] += t[0]; tq[1] += t[1]; tq[2] += t[2]; *has_tq = true; }
+        return;
+    }
+    Real ax1[3], ax2[3], p[3];
+    odeb_universal_axes(j, b0, b1, ax1, ax2);
+    Real k = dot3(ax1, ax2);
+    Real ax2t[3] = { ax2[0] + (-k) * ax1[0], ax2[1] + (-k) * ax1[1], ax2[2] + (-k) * ax1[2] };
+    cross3(p, ax1, ax2t);
+    normalize3(p);
+    Real *r3 = row + 3 * ROWLEN;
+    r3[C_J1A] = p[0]; r3[C_J1A + 1] = p[1]; r3[C_J1A + 2] = p[2];
+    if (b1) { r3[C_J2A] = -p[0]; r3[C_J2A + 1] = -p[1]; r3[C_J2A + 2] = -p[2]; }
+    r3[C_RHS] = fps * worldERP * (-k);
+    int r = 4;
+    Real t[3];
+    bool ht = false;
+    if (odeb_add_limot(j.limot1, ls.limit1, ls.err1, b0, b1, fps, row + r * ROWLEN, ax1, t, &ht)) r++;
+    if (ht) { tq[0] += t[0]; tq[1] += t[1]; tq[2] += t[2]; *has_tq = true; }
+    ht = false;
+    odeb_add_limot(j.limot2, ls.limit2, ls.err2, b0, b1, fps, row + r * ROWLEN, ax2, t, &ht);
+    if (ht) { tq[0] += t[0]; tq[1] += t[1]; tq[2] += t[2]; *has_tq = true; }
+}
+
+// surface parameters of the contact policy (dSurfaceParameters, include/ode/contact.h:55-72)
+struct DSurface {
+    int mode, the_m;
+    Real mu, mu2, bounce, bounce_vel, soft_erp, soft_cfm, motion1, motion2, motionN, slip1, slip2;
+};
+
+// dxJointContact::getInfo2 joints/contact.cpp:125-347 (no rolling friction, no fdir1)
+__device__ void odeb_contact_info2(const DSurface &s, const Real *cpos, const Real *cnormal, Real cdepth, int reverse,
+                                   const DBody &b0, const DBody *b1, Real fps, Real worldERP, Real min_depth, Real maxvel,
+                                   Real *row, int *findex)
+{
+    const int mode = s.mode;
+    Real erp = (mode & 0x008) ? s.soft_erp : worldERP;
+    Real k = fps * erp;
+    Real depth = cdepth - min_depth;
+    if (depth < 0) depth = 0;
+    Real motionN = (mode & 0x080) ? s.motionN : R_(0.0);
+    const Real pushout = k * depth + motionN;
+    bool apply_bounce = (mode & 0x004) != 0 && s.bounce_vel >= 0;
+    Real outgoing = 0;
+    Real c = pushout > maxvel ? maxvel : pushout;
+    Real c1[3], c2[3] = { 0, 0, 0 }, normal[3];
+    if (reverse) { normal[0] = -cnormal[0]; normal[1] = -cnormal[1]; normal[2] = -cnormal[2]; }
+    else { normal[0] = cnormal[0]; normal[1] = cnormal[1]; normal[2] = cnormal[2]; }
+    Real *J1 = row, *J2 = row + C_J2L;
+    if (b1) {
+        for (int i = 0; i < 3; i++) c2[i] = cpos[i] - b1->pos[i];
+        J2[0] = -normal[0]; J2[1] = -normal[1]; J2[2] = -normal[2];
+        cross3(J2 + 3, normal, c2);
+        if (apply_bounce) outgoing = dot3(J2 + 3, b1->avel) - dot3(normal, b1->lvel);
+    }
+    for (int i = 0; i < 3; i++) c1[i] = cpos[i] - b0.pos[i];
+    J1[0] = normal[0]; J1[1] = normal[1]; J1[2] = normal[2];
+    cross3(J1 + 3, c1, normal);
+    if (apply_bounce) {
+        outgoing += dot3(J1 + 3, b0.avel) + dot3(normal, b0.lvel);
+        Real neg_out = motionN - outgoing;
+        if (neg_out > s.bounce_vel) {
+            const Real newc = s.bounce * neg_out + motionN;
+            if (newc > c) c = newc;
+        }
+    }
+    row[C_RHS] = c;
+    if (mode & 0x010) row[C_CFM] = s.soft_cfm;
+    row[C_LO] = 0; row[C_HI] = R_INF;
+    if (s.the_m > 1) {
+        Real t1[3], t2[3];
+        plane_space(normal, t1, t2);
+        int r = 1;
+        if (s.mu > 0) {
+            Real *q = row + r * ROWLEN;
+            q[C_J1L] = t1[0]; q[C_J1L + 1] = t1[1]; q[C_J1L + 2] = t1[2];
+            cross3(q + C_J1A, c1, t1);
+            if (b1) { q[C_J2L] = -t1[0]; q[C_J2L + 1] = -t1[1]; q[C_J2L + 2] = -t1[2]; cross3(q + C_J2A, t1, c2); }
+            if (mode & 0x020) q[C_RHS] = s.motion1;
+            if (mode & 0x100) q[C_CFM] = s.slip1;
+            q[C_LO] = -s.mu; q[C_HI] = s.mu;
+            if (mode & 0x1000) findex[r] = 0;
+            r++;
+        }
+        const Real mu2 = (mode & 0x001) ? s.mu2 : s.mu;
+        if (mu2 > 0) {
+            Real *q = row + r * ROWLEN;
+            q[C_J1L] = t2[0]; q[C_J1L + 1] = t2[1]; q[C_J1L + 2] = t2[2];
+            cross3(q + C_J1A, c1, t2);
+            if (b1) { q[C_J2L] = -t2[0]; q[C_J2L + 1] = -t2[1]; q[C_J2L + 2] = -t2[2]; cross3(q + C_J2A, t2, c2); }
+            if (mode & 0x040) q[C_RHS] = s.motion2;
+            if (mode & 0x200) q[C_CFM] = s.slip2;
+            q[C_LO] = -mu2; q[C_HI] = mu2;
+            if (mode & 0x2000) findex[r] = 0;
+            r++;
+        }
+    }
+}
+#endif

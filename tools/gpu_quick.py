@@ -1,0 +1,25 @@
+import sys, time, numpy as np
+sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+from parity_util import *
+from ode_b200 import scenes
+def run(name, sc, h, nsteps, prec):
+    orc = B.Batch(orc_lib(prec), sc); gpu = B.Batch(gpu_lib(prec), sc)
+    for s in range(nsteps):
+        orc.step(h); gpu.step(h)
+        bad = compare_step(orc, gpu, sc.nworlds)
+        if bad:
+            print(name, prec, "step", s, "MISMATCH:", bad[:6]); return False
+    print(name, prec, "bit-exact for", nsteps, "steps")
+    return True
+for prec in ("single", "double"):
+    run("stack", scenes.box_stack(nworlds=3), 0.02, 120, prec)
+    run("stack_noopt", scenes.box_stack(nworlds=2, demo_world_options=False), 0.02, 120, prec)
+    run("pile", scenes.pile(nbodies=64), 0.01, 120, prec)
+    run("chain", scenes.chain(2), 0.05, 120, prec)
+    run("free", scenes.free_boxes(2, 16, grid=4), 0.01, 80, prec)
+# quick timing
+sc = scenes.box_stack(nworlds=4096, demo_world_options=False)
+gpu = B.Batch(gpu_lib("single"), sc)
+gpu.step(0.02, 20)
+t = time.time(); gpu.step(0.02, 50); dt = time.time() - t
+print("4096 stacks: ms/step", dt / 50 * 1e3, "body-steps/s", 4096 * 16 * 50 / dt)
