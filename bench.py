@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""bench.py -- body-steps/s of the per-step world update (collide -> QuickStep) on batched worlds.
+
+Workload (BASELINE.json configs[1]): 4096 independent worlds per GPU of a 16-box stack on a plane
+(demo_boxstack-style surface, quickstep 20 iterations + the reference's default dynamic iteration
+adjustment, dt = 0.02, auto-disable OFF so the work per step does not vanish when the stack settles).
+A "step" = one pass of the whole hot path over all worlds of the rank.
+
+    python bench.py --gpus N --steps K --warmup W          (N>1: launched through torch.distributed.run)
+    python bench.py --impl reference ...                   (the reference's CPU path on the host cores)
+
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+from ode_b200 import _binding as B  # noqa: E402
+from ode_b200 import scenes  # noqa: E402
+
+WORLDS_PER_GPU = 4096
+NBOX = 16
+H = 0.02
+PREC = "single"
+METRIC = "body_steps_per_sec"
+FLUSH_BYTES = 256 << 20
+
+
+def make_scene(nworlds, seed0=1000):
+    return scenes.box_stack(nworlds=nworlds, nboxes=NBOX, seed0=seed0, demo_world_options=False)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            j = json.load(open(p))
+            v = j.get("hbm_gbs") or j.get("hbm_gb_s")
+            if v:
+                return float(v), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None, "reasons": reasons}
+
+
+# ---------------------------------------------------------------------------------------------- CPU arm
+
+def _cpu_worker(args):
+    path, prefix, nworlds, seed0, steps, warm = args
+    real = np.float32 if PREC == "single" else np.float64
+    lib = B.SceneLib(path, prefix, real)
+    b = B.Batch(lib, make_scene(nworlds, seed0))
+    if prefix == "ref_":
+        fn = lib.lib.ref_step_plain
+        fn.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int]
+        fn(b.h, H, warm, 0, nworlds)     # warm = settle + warm-up steps: same phase of the scene as the GPU arm
+        t = time.time()
+        fn(b.h, H, steps, 0, nworlds)
+        return time.time() - t
+    b.step(H, warm)
+    t = time.time()
+    b.step(H, steps)
+    return time.time() - t
+
+
+def cpu_reference(steps, warm, worlds_per_proc=16, procs=None):
+    """The reference's own CPU implementation of the path (oracle/_ref: unmodified ODE built from its sources,
+    plain dSpaceCollide / dWorldQuickStep / dJointGroupEmpty loop, self-threaded stepper), one independent
+    process per host core each stepping its own worlds (dRand's seed is process-global)."""
+    import multiprocessing as mp
+    ref = os.path.join(ROOT, "oracle", "_ref", "libode_ref_%s.so" % PREC)
+    if os.path.exists(ref):
+        path, prefix, kind = ref, "ref_", "reference"
+    else:
+        path, prefix, kind = os.path.join(ROOT, "oracle", "liborc_%s.so" % PREC), "orc_", "port"
+    procs = procs or os.cpu_count() or 1
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(procs) as pool:
+        t0 = time.time()
+        times = pool.map(_cpu_worker, [(path, prefix, worlds_per_proc, 1000 + 97 * i, steps, warm) for i in range(procs)])
+        wall = time.time() - t0
+    slowest = max(times)
+    value = procs * worlds_per_proc * NBOX * steps / slowest
+    sample = "%d processes x %d worlds x %d steps of the %d-box stack after %d settle steps (max process time %.2f s, pool wall %.2f s)" % (
+        procs, worlds_per_proc, steps, NBOX, warm, slowest, wall)
+    return {"value": value, "unit": "body-steps/s", "cores": procs, "kind": kind, "sample": sample}
+
+
+# ---------------------------------------------------------------------------------------------- GPU arm
+
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ngpu = world
+    from ode_b200 import load
+    slib = load(PREC)                      # raises if the CUDA extension is missing: no fallback
+    L = slib.lib
+    L.odeb_timed_steps.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_size_t, C.POINTER(C.c_double)]
+    L.odeb_launch_count.restype = C.c_uint64
+    L.odeb_launch_count.argtypes = [C.c_void_p]
+    L.odeb_get_totals.argtypes = [C.c_void_p, C.c_void_p]
+    L.odeb_enable_timing.argtypes = [C.c_void_p, C.c_int]
+    L.odeb_solver_ms.restype = C.c_double
+    L.odeb_solver_ms.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+
+    W = WORLDS_PER_GPU
+    sc = make_scene(W, seed0=1000 + rank * W)
+    batch = B.Batch(slib, sc, device=local_rank)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # the stack needs ~150 steps to come to rest on its contacts; settle before measuring steady state
+    batch.step(H, args.settle)
+    batch.step(H, args.warmup)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    l0 = L.odeb_launch_count(batch.h)
+    ms = C.c_double(0)
+    ok = L.odeb_timed_steps(batch.h, H, args.steps, FLUSH_BYTES, C.byref(ms))
+    if not ok:
+        raise RuntimeError("timed steps failed")
+    launches = int(L.odeb_launch_count(batch.h) - l0)
+    barrier()
+    sampler.stop_flag = True
+    t = torch.tensor([ms.value], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = ngpu * W * NBOX * args.steps / (total_ms * 1e-3)
+
+    # ---- end-to-end through the C-ABI with host buffers: per step H2D of per-body forces (the "actions"),
+    #      the step, D2H of the full body state (the "observations")
+    real = slib.real
+    force = np.zeros((W, NBOX, 3), real)
+    force[:, -1, 0] = 0.01
+    barrier()
+    e2e_steps = max(3, min(args.steps, 20))
+    t0 = time.time()
+    for s in range(e2e_steps):
+        batch.add_force(force=force)
+        batch.step(H)
+        st = batch.get_state()
+    torch.cuda.synchronize()
+    e2e_t = time.time() - t0
+    tt = torch.tensor([e2e_t], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    e2e_value = ngpu * W * NBOX * e2e_steps / float(tt.item())
+    h2d = int(force.nbytes)
+    d2h = int(sum(v.nbytes for v in st.values()))
+
+    # ---- roofline of the dominant kernel (k_solve): algorithmic bytes / measured launch duration
+    out = None
+    if rank == 0:
+        s = 4 if PREC == "single" else 8
+        L.odeb_enable_timing(batch.h, 1)
+        batch.step(H, 5)
+        n = C.c_int(0)
+        sol_ms = L.odeb_solver_ms(batch.h, C.byref(n))
+        L.odeb_enable_timing(batch.h, 0)
+        tot = (C.c_uint64 * 6)()
+        L.odeb_get_totals(batch.h, tot)
+        pairs, contacts, rows, islands, sweeps, rowsweeps = [int(x) for x in tot]
+        # per row per sweep B_row = 30 s + 16; per row once (write J,iMJ; read for Ad; rewrite) 46 s + 16;
+        # per body (invI 12, cforce 6, rhs_tmp 6, fa 2) 26 s
+        alg_bytes = rowsweeps * (30 * s + 16) + rows * (46 * s + 16) + W * NBOX * 26 * s
+        sol_avg_ms = sol_ms / max(1, n.value)
+        achieved = alg_bytes / (sol_avg_ms * 1e-3) / 1e9
+        peak, which = peaks()
+        traffic = None
+        pj = os.path.join(ROOT, "profiles", "solver_traffic.json")
+        if os.path.exists(pj):
+            try:
+                traffic = json.load(open(pj)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        roofline = {"bound": "hbm", "kernel": "k_solve", "achieved": round(achieved, 1), "peak": peak, "peak_source": which,
+                    "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
+                    "algorithmic_bytes_per_launch": int(alg_bytes), "launch_ms": round(sol_avg_ms, 4),
+                    "share_of_step": round(sol_avg_ms / (total_ms / args.steps), 3),
+                    "note": "rows are served from L2/shared memory, so algorithmic GB/s is not DRAM traffic; the kernel is bound by the serial row-update latency per world"}
+        cpu = None
+        if ngpu == 1 and not args.no_cpu:
+            cpu = cpu_reference(args.cpu_steps, args.settle + args.warmup)
+        out = {
+            "metric": METRIC, "value": value, "unit": "body-steps/s", "n_gpus": ngpu, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if PREC == "single" else "f64", "data": "synthetic",
+            "config": {"workload": "%d worlds/GPU x %d-box stack on a plane (BASELINE configs[1]), dt=%g, 20 iters + default dynamic adjustment, auto-disable off" % (W, NBOX, H),
+                       "worlds_per_gpu": W, "bodies_per_world": NBOX, "precision": PREC, "settle_steps": args.settle,
+                       "l2": "flushed before every timed step (256 MiB memset outside the event pairs)",
+                       "per_step": {"pairs": pairs / W, "contacts": contacts / W, "rows": rows / W, "islands": islands / W,
+                                    "sweeps_per_island": sweeps / max(1, islands)}},
+            "e2e": {"value": e2e_value, "unit": "body-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "api": "odeb_add_force + odeb_step + odeb_get_state (host buffers)"},
+            "gpu_launches": launches,
+            "clocks": sampler.summary(),
+            "roofline": roofline,
+        }
+        if cpu is not None:
+            out["cpu_baseline"] = cpu
+    batch.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if out is not None:
+        print(json.dumps(out))
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    cpu = cpu_reference(min(4000, max(500, steps * 20)), args.settle + max(3, args.warmup))
+    out = {
+        "impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": "body-steps/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if PREC == "single" else "f64", "data": "synthetic",
+        "config": {"workload": "%d-box stack worlds (BASELINE configs[1]) on the host CPU, %s" % (NBOX, cpu["sample"])},
+        "cpu_baseline": cpu,
+        "e2e": {"value": cpu["value"], "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--settle", type=int, default=150)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=1500)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -148,6 +148,9 @@ int odeb_step(OdebBatch *, double h, int nsteps);
 /* same, asynchronous on the batch's stream; pair with odeb_sync */
 int odeb_step_async(OdebBatch *, double h, int nsteps);
 int odeb_sync(OdebBatch *);
+/* nsteps steps, each timed by its own CUDA event pair on the batch's stream; when flush_bytes > 0 the L2 is
+ * flushed by a memset of that size before every step, outside the timed intervals. *total_ms = summed time. */
+int odeb_timed_steps(OdebBatch *, double h, int nsteps, size_t flush_bytes, double *total_ms);
 /* number of kernel launches issued by this batch so far */
 uint64_t odeb_launch_count(const OdebBatch *);
 /* device-side duration (ms) of the solver kernel launches accumulated since the last call; resets */

@@ -26,6 +26,8 @@ struct OdebBatch {
     Real4 *h_stage;
     // cuda graph of one step
     cudaGraphExec_t graph; double graph_h; bool use_graph;
+    size_t solve_smem;
+    void *flush_buf; size_t flush_bytes;
 };
 
 template <class T> static bool dev_alloc(OdebBatch *B, T **p, size_t n)
@@ -144,6 +146,7 @@ void odeb_destroy(OdebBatch *B)
     if (B->graph) cudaGraphExecDestroy(B->graph);
     for (size_t i = 0; i < B->allocs.size(); i++) cudaFree(B->allocs[i]);
     if (B->h_stage) cudaFreeHost(B->h_stage);
+    if (B->flush_buf) cudaFree(B->flush_buf);
     if (B->stream) cudaStreamDestroy(B->stream);
     delete B;
 }
@@ -165,7 +168,7 @@ OdebBatch *odeb_create(const OdebWorldParams *wp,
 
     OdebBatch *B = new OdebBatch();
     B->device = device; B->bytes = 0; B->launches = 0; B->timing = false; B->solver_ms = 0; B->solver_launches = 0;
-    B->graph = 0; B->graph_h = -1; B->use_graph = getenv("ODEB_NO_GRAPH") == 0; B->h_stage = 0; B->d_stage = 0; B->stream = 0;
+    B->graph = 0; B->graph_h = -1; B->use_graph = getenv("ODEB_NO_GRAPH") == 0; B->h_stage = 0; B->d_stage = 0; B->stream = 0; B->flush_buf = 0; B->flush_bytes = 0;
     memset(&B->D, 0, sizeof(B->D));
     DevParams &P = B->P;
     memset(&P, 0, sizeof(P));
@@ -217,6 +220,21 @@ OdebBatch *odeb_create(const OdebWorldParams *wp,
     P.max_ang_speed = (Real)wp->max_angular_speed;
     P.solver_lanes = 8;
     if (const char *s = getenv("ODEB_SOLVER_LANES")) { int v = atoi(s); if (v >= 1 && v <= 32) P.solver_lanes = v; }
+    {   // shared-memory budget of k_solve: ring + per-body accumulators + lambda/order for SR rows, per lane
+        int sr = P.MR < 512 ? P.MR : 512;
+        if (const char *s = getenv("ODEB_SOLVER_ROWS")) sr = atoi(s);
+        if (sr > 65534) sr = 65534;
+        for (;;) {
+            size_t per_lane = (size_t)ODEB_RING * 32 * sizeof(Real) + 2 * (size_t)P.NB * sizeof(Real4) + (size_t)sr * (sizeof(Real) + 2);
+            B->solve_smem = ((per_lane * P.solver_lanes + 31) / 32) * 32;
+            if (B->solve_smem <= 200 * 1024 || sr == 0) break;
+            sr /= 2;
+        }
+        if (sr & 1) sr--;
+        P.SR = sr;
+        if (2 * (size_t)P.NB * sizeof(Real4) * P.solver_lanes > 150 * 1024) P.SR = 0;   // bodies alone overflow: global path only
+        if (P.SR == 0) B->solve_smem = 0;
+    }
 
     // ---- template on the host
     std::vector<Real> bmass(nbody), binvmass(nbody), bI(12 * nbody, 0), binvI(12 * nbody, 0);
@@ -330,13 +348,14 @@ OdebBatch *odeb_create(const OdebWorldParams *wp,
             && dev_alloc(B, &D.body_order, WB) && dev_alloc(B, &D.body_pos, WB) && dev_alloc(B, &D.body_island, WB)
             && dev_alloc(B, &D.joint_order, W * P.NJT) && dev_alloc(B, &D.joint_row, W * P.NJT) && dev_alloc(B, &D.joint_island, W * P.NJT)
             && dev_alloc(B, &D.island_info, WB) && dev_alloc(B, &D.nislands, W) && dev_alloc(B, &D.nordered, W) && dev_alloc(B, &D.njord, W) && dev_alloc(B, &D.mrows, W);
-    ok = ok && dev_alloc(B, &D.J, W * P.MR * 4) && dev_alloc(B, &D.iMJ, W * P.MR * 4) && dev_alloc(B, &D.findex, W * P.MR) && dev_alloc(B, &D.order, W * P.MR)
+    ok = ok && dev_alloc(B, &D.rows, W * P.MR * 8) && dev_alloc(B, &D.findex, W * P.MR) && dev_alloc(B, &D.order, W * P.MR)
             && dev_alloc(B, &D.lambda, W * P.MR) && dev_alloc(B, &D.cforce, WB * 2) && dev_alloc(B, &D.invIw, WB * 12)
             && dev_alloc(B, &D.stats, W * 4) && dev_alloc(B, &D.seed, W) && dev_alloc(B, &D.sweeps, 2 * W) && dev_alloc(B, &D.overflow, 1);
     B->stage_elems = WB;
     ok = ok && dev_alloc(B, &B->d_stage, WB);
     if (ok && cudaMallocHost((void **)&B->h_stage, WB * sizeof(Real4)) != cudaSuccess) { set_err("cudaMallocHost failed"); ok = false; }
     if (ok && cudaStreamCreateWithFlags(&B->stream, cudaStreamNonBlocking) != cudaSuccess) { set_err("cudaStreamCreate failed"); ok = false; }
+    if (ok && B->solve_smem > 48 * 1024 && cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->solve_smem) != cudaSuccess) { set_err("cudaFuncSetAttribute(smem=%zu) failed", B->solve_smem); ok = false; }
     if (!ok) { odeb_destroy(B); return 0; }
 
     ok = upload(D.bmass, bmass) && upload(D.binvmass, binvmass) && upload(D.bI, bI) && upload(D.binvI, binvI)
@@ -463,8 +482,7 @@ static int launch_step(OdebBatch *B, cudaStream_t s, bool timed)
     if (timed) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s); }
     {
         size_t warps = (W + P.solver_lanes - 1) / P.solver_lanes;
-        const int wpb = 4;
-        k_solve<<<nblk(warps, wpb), wpb * 32, 0, s>>>(P, D);
+        k_solve<<<(unsigned)warps, 32, B->solve_smem, s>>>(P, D);
     }
     if (timed) { cudaEventRecord(e1, s); B->pending.push_back(std::make_pair(e0, e1)); }
     k_integrate<<<nblk(W * P.NB, 128), 128, 0, s>>>(P, D);
@@ -525,6 +543,33 @@ int odeb_step(OdebBatch *B, double h, int nsteps)
 {
     if (!odeb_step_async(B, h, nsteps)) return 0;
     return odeb_sync(B);
+}
+
+/* K steps, each bracketed by its own CUDA event pair on the batch's stream; optionally the L2 is flushed
+ * (memset of flush_bytes, outside the event pairs) before every step. Returns the summed device time. */
+int odeb_timed_steps(OdebBatch *B, double h, int nsteps, size_t flush_bytes, double *total_ms)
+{
+    CK(cudaSetDevice(B->device));
+    if (flush_bytes > B->flush_bytes) {
+        if (B->flush_buf) cudaFree(B->flush_buf);
+        B->flush_buf = 0; B->flush_bytes = 0;
+        CK(cudaMalloc(&B->flush_buf, flush_bytes));
+        B->flush_bytes = flush_bytes;
+    }
+    std::vector<cudaEvent_t> ev(2 * (size_t)nsteps);
+    for (size_t i = 0; i < ev.size(); i++) CK(cudaEventCreate(&ev[i]));
+    for (int s = 0; s < nsteps; s++) {
+        if (flush_bytes) CK(cudaMemsetAsync(B->flush_buf, s & 0xff, flush_bytes, B->stream));
+        CK(cudaEventRecord(ev[2 * s], B->stream));
+        if (!odeb_step_async(B, h, 1)) return 0;
+        CK(cudaEventRecord(ev[2 * s + 1], B->stream));
+    }
+    if (!odeb_sync(B)) return 0;
+    double tot = 0;
+    for (int s = 0; s < nsteps; s++) { float ms = 0; CK(cudaEventElapsedTime(&ms, ev[2 * s], ev[2 * s + 1])); tot += ms; }
+    for (size_t i = 0; i < ev.size(); i++) cudaEventDestroy(ev[i]);
+    *total_ms = tot;
+    return 1;
 }
 
 uint64_t odeb_launch_count(const OdebBatch *B) { return B->launches; }

@@ -38,6 +38,7 @@
 // device data model
 
 struct alignas(sizeof(Real) * 4) Real4 { Real x, y, z, w; };
+#define FINDEX_FLAG 0x40000000
 
 // body flag values (meaning of ode/src/objects.h:49-57)
 enum { BF_FINITE_ROT = 1, BF_DISABLED = 4, BF_NO_GRAVITY = 8, BF_AUTO_DISABLE = 16, BF_LIN_DAMP = 32,
@@ -55,6 +56,7 @@ struct DevParams {
     Real damp_lin_scale, damp_ang_scale, damp_lin_thr, damp_ang_thr, max_ang_speed;
     Real h, hrecip;
     int solver_lanes;                     // active lanes per warp in k_solve
+    int SR;                               // rows per island that fit the shared-memory solve path
 };
 
 struct DevPtrs {
@@ -84,7 +86,9 @@ struct DevPtrs {
     int4 *island_info;                           // [W*NB] = (bodyStart, nb, rowStart, m)
     int *nislands, *nordered, *njord, *mrows;    // [W]
     // rows
-    Real4 *J, *iMJ;                              // [W*MR*4] each
+    Real4 *rows;                                 // [W*MR*8]: one 32-real record per row = J row (4 Real4) + iMJ row (4 Real4);
+                                                 //   record slot 30 = order position of body 1 (| FINDEX_FLAG), slot 31 = body 2 or -1;
+                                                 //   rows with a friction index carry it in the (unused) LO slot as integer bits
     int *findex, *order; Real *lambda;           // [W*MR]
     Real4 *cforce;                               // [W*NB*2]  (fc 6, fa 2)
     Real *invIw;                                 // [W*NB*12], indexed by order position
@@ -479,18 +483,16 @@ __global__ void k_rows(const __grid_constant__ DevParams P, const __grid_constan
         odeb_joint_info2(jt, D.jlimit[(size_t)w * P.NJ + jid], b0, b1i >= 0 ? &b1 : 0, P.hrecip, P.erp, row, tq, &has_tq);
     }
     int p0 = D.body_pos[(size_t)w * P.NB + b0i], p1 = b1i >= 0 ? D.body_pos[(size_t)w * P.NB + b1i] : -1;
-    Real4 *Jw = D.J + ((size_t)w * P.MR + row0) * 4;
-    Real4 *Mw = D.iMJ + ((size_t)w * P.MR + row0) * 4;
+    Real4 *rec = D.rows + ((size_t)w * P.MR + row0) * 8;
     int *fi = D.findex + (size_t)w * P.MR + row0;
     for (int r = 0; r < m; r++) {
         Real *q = row + r * ROWLEN;
         q[C_RHS] *= P.hrecip; q[C_CFM] *= P.hrecip;
         Real4 v0 = { q[0], q[1], q[2], q[3] }, v1 = { q[4], q[5], q[6], q[7] }, v2 = { q[8], q[9], q[10], q[11] }, v3 = { q[12], q[13], q[14], q[15] };
-        Jw[4 * r] = v0; Jw[4 * r + 1] = v1; Jw[4 * r + 2] = v2; Jw[4 * r + 3] = v3;
+        rec[8 * r] = v0; rec[8 * r + 1] = v1; rec[8 * r + 2] = v2; rec[8 * r + 3] = v3;
         fi[r] = findex[r] == -1 ? -1 : findex[r] + row0;
-        // body order positions travel in the last two slots of the iMJ row
-        int *mb = (int *)&Mw[4 * r + 3].z;
-        mb[0] = p0; *(int *)&Mw[4 * r + 3].w = p1;
+        // body order positions travel in the last two slots of the record
+        *(int *)&rec[8 * r + 7].z = p0; *(int *)&rec[8 * r + 7].w = p1;
     }
     if (has_tq) {   // dBodyAddTorque from a powered limit motor at its stop (joints/joint.cpp:677-705)
         Real *t0 = (Real *)&D.tacc[(size_t)w * P.NB + b0i];
@@ -533,7 +535,7 @@ __global__ void k_rows_finish(const __grid_constant__ DevParams P, const __grid_
     if (t >= (size_t)P.W * P.MR) return;
     int w = (int)(t / P.MR), i = (int)(t % P.MR);
     if (i >= D.mrows[w]) return;
-    Real4 *Jp = D.J + t * 4, *Mp = D.iMJ + t * 4;
+    Real4 *Jp = D.rows + t * 8, *Mp = Jp + 4;
     Real q[16];
     { Real4 v0 = Jp[0], v1 = Jp[1], v2 = Jp[2], v3 = Jp[3];
       q[0] = v0.x; q[1] = v0.y; q[2] = v0.z; q[3] = v0.w; q[4] = v1.x; q[5] = v1.y; q[6] = v1.z; q[7] = v1.w;
@@ -569,134 +571,16 @@ __global__ void k_rows_finish(const __grid_constant__ DevParams P, const __grid_
     for (int k = 0; k < 6; k++) q[C_J1L + k] *= Ad;
     if (p1 != -1) for (int k = 0; k < 6; k++) q[C_J2L + k] *= Ad;
     Real4 v0 = { q[0], q[1], q[2], q[3] }, v1 = { q[4], q[5], q[6], q[7] }, v2 = { q[8], q[9], q[10], q[11] }, v3 = { q[12], q[13], q[14], q[15] };
+    int fi = D.findex[t];
+    if (fi != -1) { v3.z = 0; *(int *)&v3.z = fi; p0 |= FINDEX_FLAG; }   // LO is unused for friction-index rows (quickstep.cpp:2971-2978)
     Jp[0] = v0; Jp[1] = v1; Jp[2] = v2; Jp[3] = v3;
     Real4 m0 = { imj[0], imj[1], imj[2], imj[3] }, m1 = { imj[4], imj[5], imj[6], imj[7] }, m2 = { imj[8], imj[9], imj[10], imj[11] };
-    Mp[0] = m0; Mp[1] = m1; Mp[2] = m2; Mp[3].x = imj[12]; Mp[3].y = imj[13];
+    Real4 m3 = { imj[12], imj[13], 0, 0 };
+    *(int *)&m3.z = p0; *(int *)&m3.w = p1;
+    Mp[0] = m0; Mp[1] = m1; Mp[2] = m2; Mp[3] = m3;
 }
 
-// ------------------------------------------------------------------------------------------------
-// SOR-LCP solve: one thread walks one world's islands in the reference's order
-
-struct RowRegs { Real4 j0, j1, j2, j3, m0, m1, m2, m3; int fi; };
-
-__device__ __forceinline__ void load_row(const Real4 *J, const Real4 *M, const int *findex, int idx, RowRegs &r)
-{
-    const Real4 *jp = J + 4 * (size_t)idx, *mp = M + 4 * (size_t)idx;
-    r.j0 = jp[0]; r.j1 = jp[1]; r.j2 = jp[2]; r.j3 = jp[3];
-    r.m0 = mp[0]; r.m1 = mp[1]; r.m2 = mp[2]; r.m3 = mp[3];
-    r.fi = findex[idx];
-}
-
-__global__ void __launch_bounds__(128) k_solve(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D)
-{
-    int lane = threadIdx.x & 31;
-    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (lane >= P.solver_lanes) return;
-    int w = warp * P.solver_lanes + lane;
-    if (w >= P.W) return;
-    unsigned seed = D.seed[w];
-    unsigned st0 = 0, st1 = 0, st2 = 0, st3 = 0;
-    unsigned long long sweeps = 0, rowsweeps = 0;
-    const Real4 *J = D.J + (size_t)w * P.MR * 4, *M = D.iMJ + (size_t)w * P.MR * 4;
-    const int *findex = D.findex + (size_t)w * P.MR;
-    int *order = D.order + (size_t)w * P.MR;
-    Real *lambda = D.lambda + (size_t)w * P.MR;
-    Real4 *cf = D.cforce + (size_t)w * P.NB * 2;
-    const int4 *iinfo = D.island_info + (size_t)w * P.NB;
-    int nis = D.nislands[w];
-    for (int is = 0; is < nis; is++) {
-        int4 info = iinfo[is];
-        const int bstart = info.x, nb = info.y, rstart = info.z, m = info.w;
-        if (m > 0) {
-            Real4 z4 = { 0, 0, 0, 0 };
-            for (int k = 0; k < 2 * nb; k++) cf[2 * bstart + k] = z4;
-            // ReorderPrep quickstep.cpp:2329-2355
-            int nvalid = 0;
-            for (int i = 0; i < m; i++) { lambda[rstart + i] = 0; if (findex[rstart + i] != -1) nvalid++; }
-            {
-                int head = 0, tail = m - nvalid;
-                for (int i = 0; i < m; i++) { if (findex[rstart + i] == -1) order[rstart + head++] = rstart + i; else order[rstart + tail++] = rstart + i; }
-            }
-            Real exit_delta = P.premature_delta;
-            const unsigned num_iterations = P.num_iter;
-            for (unsigned iteration = 0, extra = 0;;) {
-                if (iteration >= 8 && (iteration & 7) == 0) {
-                    // ConstraintsShuffling quickstep.cpp:2578-2611 with dRandInt misc.cpp:78-139
-                    for (int idx = 1; idx < m; idx++) {
-                        int sw = odeb_rand_int(&seed, idx + 1);
-                        int a = order[rstart + idx], b = order[rstart + sw];
-                        order[rstart + idx] = b; order[rstart + sw] = a;
-                    }
-                }
-                // one sweep (IterationStep quickstep.cpp:2917-3033); next row is loaded while the current one is solved
-                RowRegs cur, nxt;
-                int index = order[rstart];
-                load_row(J, M, findex, index, cur);
-                for (int i = 0; i < m; i++) {
-                    int nindex = (i + 1 < m) ? order[rstart + i + 1] : index;
-                    load_row(J, M, findex, nindex, nxt);
-                    Real old_lambda = lambda[index];
-                    int b1 = *(int *)&cur.m3.z, b2 = *(int *)&cur.m3.w;
-                    Real delta = cur.j1.z - old_lambda * cur.j1.w;
-                    Real4 f1a = cf[2 * b1], f1b = cf[2 * b1 + 1];
-                    delta -= f1a.x * cur.j0.x + f1a.y * cur.j0.y + f1a.z * cur.j0.z + f1a.w * cur.j0.w + f1b.x * cur.j1.x + f1b.y * cur.j1.y;
-                    Real4 f2a, f2b;
-                    if (b2 != -1) {
-                        f2a = cf[2 * b2]; f2b = cf[2 * b2 + 1];
-                        delta -= f2a.x * cur.j2.x + f2a.y * cur.j2.y + f2a.z * cur.j2.z + f2a.w * cur.j2.w + f2b.x * cur.j3.x + f2b.y * cur.j3.y;
-                    }
-                    Real hi_act, lo_act;
-                    if (cur.fi != -1) { hi_act = RFABS(cur.j3.w * lambda[cur.fi]); lo_act = -hi_act; }
-                    else { hi_act = cur.j3.w; lo_act = cur.j3.z; }
-                    Real new_lambda = old_lambda + delta;
-                    if (new_lambda < lo_act) { delta = lo_act - old_lambda; lambda[index] = lo_act; }
-                    else if (new_lambda > hi_act) { delta = hi_act - old_lambda; lambda[index] = hi_act; }
-                    else lambda[index] = new_lambda;
-                    if (delta != 0) {
-                        f1a.x += delta * cur.m0.x; f1a.y += delta * cur.m0.y; f1a.z += delta * cur.m0.z; f1a.w += delta * cur.m0.w;
-                        f1b.x += delta * cur.m1.x; f1b.y += delta * cur.m1.y;
-                        if (delta > 0) f1b.w += delta * cur.m1.z; else f1b.z += delta * cur.m1.z;
-                        cf[2 * b1] = f1a; cf[2 * b1 + 1] = f1b;
-                        if (b2 != -1) {
-                            if (delta > 0) f2b.w += delta * cur.m3.y; else f2b.z += delta * cur.m3.y;
-                            f2a.x += delta * cur.m1.w; f2a.y += delta * cur.m2.x; f2a.z += delta * cur.m2.y; f2a.w += delta * cur.m2.z;
-                            f2b.x += delta * cur.m2.w; f2b.y += delta * cur.m3.x;
-                            cf[2 * b2] = f2a; cf[2 * b2 + 1] = f2b;
-                        }
-                    }
-                    cur = nxt; index = nindex;
-                }
-                ++iteration; ++sweeps; rowsweeps += m;
-                if (iteration - extra == num_iterations) {
-                    if (extra != 0 || P.max_extra == 0) { if (extra != 0) st3++; break; }
-                    extra = P.max_extra;
-                    exit_delta = P.extra_delta;
-                }
-                if (P.dyn_enabled) {
-                    // CheckForMaximumToBeLessThanLimitAndResetMaxAdjustments quickstep.cpp:3253-3285
-                    bool hit = false;
-                    if (exit_delta == 0) hit = true;
-                    for (int k = 0; k < nb; k++) {
-                        Real4 v = cf[2 * (bstart + k) + 1];
-                        if (!hit && (!(v.w < exit_delta) || !(-v.z < exit_delta))) hit = true;
-                        v.z = 0; v.w = 0;
-                        cf[2 * (bstart + k) + 1] = v;
-                    }
-                    if (!hit) {
-                        if (iteration < num_iterations) st1++;
-                        else if (iteration > num_iterations) st2++;
-                        break;
-                    }
-                }
-            }
-        }
-        st0++;
-    }
-    D.seed[w] = seed;
-    unsigned *st = D.stats + 4 * (size_t)w;
-    st[0] += st0; st[1] += st1; st[2] += st2; st[3] += st3;
-    D.sweeps[2 * (size_t)w] = sweeps; D.sweeps[2 * (size_t)w + 1] = rowsweeps;
-}
+#include "odeb_solve.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // Stage 4b + 6a + 6b (dxStepBody)

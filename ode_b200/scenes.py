@@ -118,3 +118,67 @@ def free_boxes(nworlds=1, nboxes=64, seed0=5, grid=8, spacing=1.5):
     sc.state = dict(pos=pos, quat=quat, lvel=np.zeros_like(pos), avel=np.zeros_like(pos))
     sc.seeds = (seed0 + np.arange(nworlds)).astype(np.uint32)
     return sc
+
+
+def ragdoll(nworlds=1, seed0=11, drop=0.25, max_contacts=3):
+    """Config 4: a 15-capsule humanoid (authored here; the reference ships no ragdoll), z up.
+
+    14 joints: ball (neck, shoulders, hips), universal with stops on both axes (spine x2, wrists, ankles),
+    hinge with stops (elbows, knees). Contacts: <= 3 per pair, dContactApprox1, mu = 1, bodies joined by a
+    joint do not collide (dAreConnectedExcluding). g = -9.81, ERP 0.2, default CFM, 20 iterations.
+    Per world: small random initial linear / angular velocities from seed0 + w.
+    """
+    sc = B.Scene(B.default_world_params(gravity=(0, 0, -9.81), max_contacts=max_contacts, surf_mode=B.CONTACT_APPROX1,
+                                        mu=1.0, skip_connected=1), nworlds)
+    sc.add_geom(B.PLANE, (0, 0, 1, 0))
+    s = np.sqrt(0.5)
+    QX = (s, 0.0, s, 0.0)      # capsule axis (local z) -> world x
+    QY = (s, -s, 0.0, 0.0)     # local z -> world y
+    QZ = (1.0, 0.0, 0.0, 0.0)
+    idx = {}
+
+    def cap(name, pos, r, length, q):
+        m, I = B.capsule_mass(1000.0, r, length)
+        b = sc.add_body(m, I, (pos[0], pos[1], pos[2] + drop), q)
+        sc.add_geom(B.CAPSULE, (r, length), body=b)
+        idx[name] = b
+
+    cap("pelvis", (0, 0, 1.00), 0.11, 0.14, QX)
+    cap("belly", (0, 0, 1.16), 0.10, 0.10, QX)
+    cap("chest", (0, 0, 1.34), 0.12, 0.16, QX)
+    cap("head", (0, 0, 1.64), 0.10, 0.05, QZ)
+    for sgn, sd in ((1, "L"), (-1, "R")):
+        cap("uarm" + sd, (sgn * 0.34, 0, 1.42), 0.05, 0.20, QX)
+        cap("larm" + sd, (sgn * 0.63, 0, 1.42), 0.045, 0.20, QX)
+        cap("hand" + sd, (sgn * 0.85, 0, 1.42), 0.04, 0.04, QX)
+        cap("uleg" + sd, (sgn * 0.10, 0, 0.70), 0.07, 0.28, QZ)
+        cap("lleg" + sd, (sgn * 0.10, 0, 0.29), 0.06, 0.28, QZ)
+        cap("foot" + sd, (sgn * 0.10, 0.06, 0.055), 0.05, 0.12, QY)
+
+    def J(jt, a, b, anchor, **kw):
+        sc.add_joint(jt, idx[a], idx[b], (anchor[0], anchor[1], anchor[2] + drop), **kw)
+
+    J(B.JOINT_UNIVERSAL, "pelvis", "belly", (0, 0, 1.08), axis1=(1, 0, 0), axis2=(0, 1, 0), lo_stop=(-0.4, -0.4), hi_stop=(0.4, 0.4))
+    J(B.JOINT_UNIVERSAL, "belly", "chest", (0, 0, 1.24), axis1=(1, 0, 0), axis2=(0, 1, 0), lo_stop=(-0.4, -0.4), hi_stop=(0.4, 0.4))
+    J(B.JOINT_BALL, "chest", "head", (0, 0, 1.52))
+    for sgn, sd in ((1, "L"), (-1, "R")):
+        J(B.JOINT_BALL, "chest", "uarm" + sd, (sgn * 0.19, 0, 1.42))
+        J(B.JOINT_HINGE, "uarm" + sd, "larm" + sd, (sgn * 0.485, 0, 1.42), axis1=(0, 0, 1), lo_stop=(-2.0, 0), hi_stop=(0.05, 0))
+        J(B.JOINT_UNIVERSAL, "larm" + sd, "hand" + sd, (sgn * 0.78, 0, 1.42), axis1=(0, 1, 0), axis2=(0, 0, 1),
+          lo_stop=(-0.6, -0.6), hi_stop=(0.6, 0.6))
+        J(B.JOINT_BALL, "pelvis", "uleg" + sd, (sgn * 0.10, 0, 0.92))
+        J(B.JOINT_HINGE, "uleg" + sd, "lleg" + sd, (sgn * 0.10, 0, 0.495), axis1=(1, 0, 0), lo_stop=(-0.05, 0), hi_stop=(2.2, 0))
+        J(B.JOINT_UNIVERSAL, "lleg" + sd, "foot" + sd, (sgn * 0.10, 0, 0.09), axis1=(1, 0, 0), axis2=(0, 1, 0),
+          lo_stop=(-0.5, -0.3), hi_stop=(0.5, 0.3))
+    nb = sc.nbody
+    pos = np.tile(np.asarray(sc.body_pos)[None], (nworlds, 1, 1))
+    quat = np.tile(np.asarray(sc.body_quat)[None], (nworlds, 1, 1))
+    lvel = np.zeros((nworlds, nb, 3))
+    avel = np.zeros((nworlds, nb, 3))
+    for w in range(nworlds):
+        r = _rng(seed0 + w)
+        lvel[w] = 0.3 * (r.rand(nb, 3) - 0.5)
+        avel[w] = 0.5 * (r.rand(nb, 3) - 0.5)
+    sc.state = dict(pos=pos, quat=quat, lvel=lvel, avel=avel)
+    sc.seeds = (seed0 + np.arange(nworlds)).astype(np.uint32)
+    return sc

@@ -35,6 +35,36 @@ void orc_geom_aabb(int type, const Real *p, const Real *pos, const Real *R, Real
     for (int k = 0; k < 6; k++) aabb6[k] = g.aabb[k];
 }
 
+/* dxJointContact::getInfo1 + getInfo2 on an explicit contact between two free bodies at pos1/pos2 (identity
+ * rotation, zero velocity), 16-wide row layout -- the call pattern of the reference's tests/friction.cpp:69-173. */
+int orc_contact_rows(int mode, Real mu, Real mu2, const Real *cpos, const Real *cnormal, Real depth, const Real *fdir1,
+                     const Real *pos1, const Real *pos2, Real fps, Real erp, Real *rows48, int *findex3)
+{
+    Batch B;
+    memset(&B.wp, 0, sizeof(B.wp));
+    B.wp.surf_mode = mode & ~ODEB_CONTACT_FDIR1; B.wp.mu = mu; B.wp.mu2 = mu2;
+    B.max_vel = R_INF; B.min_depth = 0; B.cfm = 0;
+    World W;
+    W.bodies.resize(2);
+    for (int i = 0; i < 2; i++) {
+        Body &b = W.bodies[i];
+        memset(b.pos, 0, sizeof(Real) * (4 + 12 + 4 + 4 + 4 + 4 + 4));
+        const Real *p = i ? pos2 : pos1;
+        b.pos[0] = p[0]; b.pos[1] = p[1]; b.pos[2] = p[2];
+        b.R[0] = b.R[5] = b.R[10] = 1; b.q[0] = 1;
+    }
+    Joint j;
+    memset(&j, 0, sizeof(j));
+    j.type = ODEB_JOINT_CONTACT; j.b0 = 0; j.b1 = 1;
+    for (int k = 0; k < 3; k++) { j.cg.pos[k] = cpos[k]; j.cg.normal[k] = cnormal[k]; }
+    j.cg.depth = depth;
+    contact_info1(B, j);
+    for (int k = 0; k < 48; k++) rows48[k] = 0;
+    for (int k = 0; k < 3; k++) findex3[k] = -1;
+    contact_info2(B, W, j, fps, erp, rows48, findex3, (mode & ODEB_CONTACT_FDIR1) ? fdir1 : 0);
+    return j.m;
+}
+
 unsigned long orc_rand_next(uint32_t *seed) { return orc_rand(seed); }
 int orc_rand_int_(uint32_t *seed, int n) { return orc_rand_int(seed, n); }
 int orc_sizeof_real(void) { return (int)sizeof(Real); }

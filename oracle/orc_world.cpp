@@ -454,7 +454,7 @@ void contact_info1(const Batch &B, Joint &j)
 // row layout of quickstep.cpp:267-322: [J1l(3) J1a(3) rhs cfm J2l(3) J2a(3) lo hi]
 enum { J1L = 0, J1A = 3, RHS = 6, CFM = 7, J2L = 8, J2A = 11, LO = 14, HI = 15, ROW = 16 };
 
-void contact_info2(const Batch &B, World &W, Joint &j, Real fps, Real worldERP, Real *row, int *findex)
+void contact_info2(const Batch &B, World &W, Joint &j, Real fps, Real worldERP, Real *row, int *findex, const Real *fdir1 = 0)
 {
     const OdebWorldParams &p = B.wp;
     const int mode = p.surf_mode;
@@ -497,7 +497,8 @@ void contact_info2(const Batch &B, World &W, Joint &j, Real fps, Real worldERP, 
     row[LO] = 0; row[HI] = R_INF;
     if (j.the_m > 1) {
         Real t1[3], t2[3];
-        plane_space(normal, t1, t2);
+        if (fdir1) { t1[0] = fdir1[0]; t1[1] = fdir1[1]; t1[2] = fdir1[2]; cross3(t2, normal, t1); }   // dContactFDir1 contact.cpp:203-206
+        else plane_space(normal, t1, t2);
         int r = 1;
         if (mu > 0) {
             Real *q = row + r * ROW;

@@ -450,6 +450,34 @@ void ref_geom_aabb(int type, const dReal *p, const dReal *pos, const dReal *R, d
     dGeomDestroy(g);
 }
 
+/* the reference's own contact row builder, called the way tests/friction.cpp:69-173 calls it */
+int ref_contact_rows(int mode, dReal mu, dReal mu2, const dReal *cpos, const dReal *cnormal, dReal depth, const dReal *fdir1,
+                     const dReal *pos1, const dReal *pos2, dReal fps, dReal erp, dReal *rows48, int *findex3)
+{
+    if (!g_init) { dInitODE2(0); dAllocateODEDataForThread(dAllocateMaskAll); g_init = 1; }
+    dWorldID world = dWorldCreate();
+    dWorldSetCFM(world, 0);
+    dBodyID b1 = dBodyCreate(world), b2 = dBodyCreate(world);
+    dBodySetPosition(b1, pos1[0], pos1[1], pos1[2]);
+    dBodySetPosition(b2, pos2[0], pos2[1], pos2[2]);
+    dContact c;
+    memset(&c, 0, sizeof(c));
+    c.surface.mode = mode; c.surface.mu = mu; c.surface.mu2 = mu2;
+    for (int k = 0; k < 3; k++) { c.geom.pos[k] = cpos[k]; c.geom.normal[k] = cnormal[k]; c.fdir1[k] = fdir1[k]; }
+    c.geom.depth = depth;
+    dJointID j = dJointCreateContact(world, 0, &c);
+    dJointAttach(j, b1, b2);
+    dxJoint::Info1 info1;
+    j->getInfo1(&info1);
+    for (int k = 0; k < 48; k++) rows48[k] = 0;
+    for (int k = 0; k < 3; k++) findex3[k] = -1;
+    j->getInfo2(fps, erp, 16, rows48, rows48 + 8, 16, rows48 + 6, rows48 + 14, findex3);
+    int m = info1.m;
+    dJointDestroy(j);
+    dWorldDestroy(world);
+    return m;
+}
+
 unsigned long ref_rand_next(uint32_t *seed) { dRandSetSeed(*seed); unsigned long r = dRand(); *seed = (uint32_t)dRandGetSeed(); return r; }
 int ref_rand_int(uint32_t *seed, int n) { dRandSetSeed(*seed); int r = dRandInt(n); *seed = (uint32_t)dRandGetSeed(); return r; }
 int ref_test_rand(void) { return dTestRand(); }

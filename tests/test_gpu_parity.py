@@ -1,0 +1,141 @@
+"""GPU parity tests (pytest -m gpu): the CUDA path through the C-ABI against the oracle on the same seeded
+inputs and against the committed golden fixtures recorded from the reference.
+
+Bar: integer observables (broadphase pair set, per-pair contact counts, island labels, the four dynamic
+iteration counters, dRand seed) identical; floating observables bit-identical wherever the path uses only
++,-,*,/,sqrt (the build uses -fmad=false); where CUDA libm differs from glibc (atan2 in cullPoints and the
+hinge angle, sin/cos in finite rotation) the stated tolerance is 2e-5 (single) / 1e-12 (double) absolute on
+body state per teacher-forced step, and 5e-4 / 1e-10 over the free-running golden trajectories (<= 160 steps;
+an ulp of difference in a joint-limit error or a culled contact is amplified by the contact dynamics).
+"""
+import os
+import numpy as np
+import pytest
+from parity_util import B, ROOT, REAL, gpu_lib, orc_lib, compare_step
+import golden_cases as G
+from ode_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(ROOT, "tests", "golden")
+PRECS = ("single", "double")
+TOL = {"single": dict(contact=2e-5, state=2e-5), "double": dict(contact=1e-12, state=1e-12)}
+TOL_FREE = {"single": dict(contact=5e-4, state=5e-4), "double": dict(contact=1e-10, state=1e-10)}
+# scenes whose path contains no libm transcendental call: bit-exact; the others: tolerance above
+EXACT = {"stack": True, "stack_plain": True, "chain": True, "free": True, "pile": False, "pile_sap": False, "ragdoll": False}
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("name", sorted(G.TRAJ_SCENES))
+def test_golden_trajectories(prec, name):
+    mk, h, nsteps, every = G.TRAJ_SCENES[name]
+    gold = np.load(os.path.join(GOLD, "traj_%s_%s.npz" % (name, prec)))
+    bad = G.compare_traj(B.Batch(gpu_lib(prec), mk()), gold, h, exact=EXACT[name], tol=TOL_FREE[prec])
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_free_running_vs_oracle_bit_exact(prec):
+    """Box stacks (both world-option sets), chains and free boxes: every observable identical, every step."""
+    for mk, h, n in ((lambda: scenes.box_stack(nworlds=5), 0.02, 150),
+                     (lambda: scenes.box_stack(nworlds=3, demo_world_options=False), 0.02, 150),
+                     (lambda: scenes.chain(4), 0.05, 150),
+                     (lambda: scenes.free_boxes(3, 16, grid=4), 0.01, 100)):
+        sc = mk()
+        a, b = B.Batch(orc_lib(prec), sc), B.Batch(gpu_lib(prec), sc)
+        for s in range(n):
+            a.step(h)
+            b.step(h)
+            bad = compare_step(a, b, sc.nworlds)
+            assert not bad, (s, bad)
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_teacher_forced_single_step(prec):
+    """SURVEY 8(d) protocol (i): upload the oracle's state at steps {0,10,100,300}, step once on both,
+    compare. Scenes with transcendental calls (pile: cullPoints/atan2, ragdoll: hinge angles) included."""
+    for mk, h in ((lambda: scenes.pile(nbodies=125), 0.01), (lambda: scenes.ragdoll(3), 0.01), (lambda: scenes.box_stack(nworlds=2), 0.02)):
+        sc = mk()
+        a = B.Batch(orc_lib(prec), sc)
+        b = B.Batch(gpu_lib(prec), sc)
+        done = 0
+        for target in (0, 10, 100, 300):
+            a.step(h, target - done)
+            done = target
+            st = a.get_state()
+            b.set_state(**st)
+            b.set_seeds(a.get_seeds())
+            a.set_state(**st)        # same normalise + R rebuild on both sides
+            a.step(h)
+            b.step(h)
+            done += 1
+            bad = compare_step(a, b, sc.nworlds, exact_float=False, tol=TOL[prec], what=("pairs", "contacts", "islands", "seeds", "state"))
+            assert not bad, (target, bad)
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_full_size_properties(prec):
+    """BASELINE config sizes, size-independent properties: replicated worlds stay replicated (4096 stacks built
+    from 8 distinct seeds -> only 8 distinct trajectories), results do not depend on batch position or batch
+    size, state stays finite, the stack neither sinks nor explodes."""
+    W = 4096
+    sc = scenes.box_stack(nworlds=W, demo_world_options=False)
+    for k in sc.state:
+        sc.state[k] = np.ascontiguousarray(np.tile(sc.state[k][:8], (W // 8, 1, 1)))
+    sc.seeds = np.tile(sc.seeds[:8], W // 8)
+    b = B.Batch(gpu_lib(prec), sc)
+    b.step(0.02, 60)
+    st = b.get_state()
+    for k in st:
+        assert np.isfinite(st[k]).all()
+        v = st[k].reshape(W // 8, 8, -1)
+        assert np.array_equal(v, np.broadcast_to(v[:1], v.shape)), "%s differs between replicas" % k
+    seeds = b.get_seeds().reshape(W // 8, 8)
+    assert np.array_equal(seeds, np.broadcast_to(seeds[:1], seeds.shape))
+    # the same 8 worlds alone give the same answer (no dependence on batch size / placement)
+    sc8 = scenes.box_stack(nworlds=8, demo_world_options=False)
+    b8 = B.Batch(gpu_lib(prec), sc8)
+    b8.step(0.02, 60)
+    st8 = b8.get_state()
+    for k in st:
+        assert np.array_equal(st[k][:8], st8[k])
+    z = st["pos"][:8, :, 2]
+    assert (z > 0.2).all() and (z < 9.0).all()
+    # and the oracle agrees on those 8 worlds bit for bit
+    o = B.Batch(orc_lib(prec), sc8)
+    o.step(0.02, 60)
+    so = o.get_state()
+    for k in st8:
+        assert np.array_equal(so[k], st8[k])
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_large_island_global_path(prec):
+    """A pile big enough that its island exceeds the shared-memory solve budget takes the global-memory
+    solve path; islands, pair sets and contact counts stay identical to the oracle, state within tolerance."""
+    sc = scenes.pile(nbodies=343)
+    a, b = B.Batch(orc_lib(prec), sc), B.Batch(gpu_lib(prec), sc)
+    for s in range(70):
+        a.step(0.01)
+        b.step(0.01)
+        if s % 10 == 9:
+            st = a.get_state()
+            b.set_state(**st)
+            a.set_state(**st)
+            b.set_seeds(a.get_seeds())
+    a.step(0.01)
+    b.step(0.01)
+    bad = compare_step(a, b, 1, exact_float=False, tol=TOL[prec], what=("pairs", "contacts", "islands", "seeds", "state"))
+    assert not bad, bad
+    n, lab = b.get_islands(0)
+    assert n >= 1
+
+
+def test_capacity_overflow_is_reported():
+    """Too small a contact capacity must make the step fail loudly, never drop contacts silently."""
+    os.environ["ODEB_MAX_CONTACTS"] = "4"
+    try:
+        b = B.Batch(gpu_lib("single"), scenes.box_stack(nworlds=2, nboxes=6))
+    finally:
+        del os.environ["ODEB_MAX_CONTACTS"]
+    with pytest.raises(RuntimeError):
+        b.step(0.02, 40)

@@ -1,0 +1,122 @@
+"""CPU tests (no GPU): the oracle restatement against the reference's golden vectors and, when the compiled
+reference is present (oracle/_ref), against the reference itself, observable by observable and bit for bit."""
+import ctypes as C
+import os
+import numpy as np
+import pytest
+from parity_util import B, ROOT, REAL, ref_lib, orc_lib, compare_step
+import golden_cases as G
+from ode_b200 import scenes
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+PRECS = ("single", "double")
+
+
+def test_rand_known_answers():
+    """dTestRand's known answers (ode/src/misc.cpp:64-74) and recorded dRand/dRandInt streams."""
+    lib = orc_lib("single")
+    g = np.load(os.path.join(GOLD, "rand.npz"))
+    fn = lib.lib.orc_rand_next
+    fn.restype = C.c_ulong
+    seed = C.c_uint32(0)
+    stream = [fn(C.byref(seed)) for _ in range(64)]
+    assert stream[:5] == [0x3c6ef35f, 0x47502932, 0xd1ccf6e9, 0xaaf95334, 0x6252e503]
+    assert np.array_equal(np.array(stream, np.uint64), g["stream"])
+    seed = C.c_uint32(12345)
+    out = []
+    for rep in range(8):
+        for n in g["ns"]:
+            out.append(lib.lib.orc_rand_int_(C.byref(seed), int(n)))
+    assert np.array_equal(np.array(out, np.int64), g["randint"])
+    assert seed.value == int(g["final_seed"])
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_colliders_golden(prec):
+    """dCollide for all 15 ordered pairs of {sphere, box, capsule, plane} + computeAABB: contact count exact,
+    position / normal / depth bit-exact against the recorded reference outputs."""
+    lib = orc_lib(prec)
+    g = np.load(os.path.join(GOLD, "collide_%s.npz" % prec))
+    n, g7, aabb = G.run_collide(lib, "orc_", G.collide_cases(REAL[prec]))
+    assert np.array_equal(n, g["n"])
+    assert (n > 0).sum() > 100 and (n > 1).sum() > 30    # the fixture really exercises multi-contact paths
+    assert np.array_equal(aabb, g["aabb"])
+    for i in range(len(n)):
+        assert np.array_equal(g7[i][:n[i]], g["geom7"][i][:n[i]]), "case %d" % i
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_contact_rows_golden(prec):
+    """dxJointContact::getInfo1/getInfo2 (16-wide row layout), incl. the reference's own test vectors."""
+    lib = orc_lib(prec)
+    cases = G.contact_row_cases(REAL[prec])
+    m, rows, fi = G.run_contact_rows(lib, "orc_", cases)
+    # tests/friction.cpp:119-136 and :150-170 (expected J rows written out in the reference's test)
+    assert m[0] == 2 and m[1] == 2
+    np.testing.assert_allclose(rows[0][1][[0, 1, 2, 3, 4, 5, 8, 9, 10, 11, 12, 13]], [0, 0, -1, 0, 1, 0, 0, 0, 1, 0, 1, 0], atol=1e-6)
+    np.testing.assert_allclose(rows[1][1][[0, 1, 2, 3, 4, 5, 8, 9, 10, 11, 12, 13]], [0, 1, 0, 0, 0, 1, 0, -1, 0, 0, 0, 1], atol=1e-6)
+    assert fi[0][1] == 0 and fi[1][1] == 0
+    g = np.load(os.path.join(GOLD, "contact_rows_%s.npz" % prec))
+    assert np.array_equal(m, g["m"]) and np.array_equal(fi, g["findex"])
+    assert np.array_equal(rows, g["rows"])
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("name", sorted(G.TRAJ_SCENES))
+def test_trajectories_golden(prec, name):
+    """Whole-step observables on small scenes (pair set, contacts, island labels, iteration statistics,
+    dRand seed, body state) against the recorded reference run -- all bit-exact."""
+    mk, h, nsteps, every = G.TRAJ_SCENES[name]
+    gold = np.load(os.path.join(GOLD, "traj_%s_%s.npz" % (name, prec)))
+    bad = G.compare_traj(B.Batch(orc_lib(prec), mk()), gold, h)
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_oracle_vs_compiled_reference(prec):
+    """Direct run against oracle/_ref (skipped where the reference build is absent)."""
+    ref = ref_lib(prec)
+    if ref is None:
+        pytest.skip("oracle/_ref not built here")
+    for mk, h, n in ((lambda: scenes.box_stack(nworlds=2, nboxes=10), 0.02, 60), (lambda: scenes.pile(nbodies=40), 0.01, 60),
+                     (lambda: scenes.ragdoll(1, seed0=3), 0.01, 120), (lambda: scenes.chain(1), 0.05, 60)):
+        sc = mk()
+        a, b = B.Batch(ref, sc), B.Batch(orc_lib(prec), sc)
+        for s in range(n):
+            a.step(h)
+            b.step(h)
+            bad = compare_step(a, b, sc.nworlds)
+            assert not bad, (s, bad)
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_edge_cases(prec):
+    """Empty contact set (bodies in free fall), a world with a single body, geoms without bodies only,
+    category bits that filter everything, zero gravity."""
+    lib = orc_lib(prec)
+    ref = ref_lib(prec)
+    cases = []
+    sc = scenes.free_boxes(1, 1, grid=1)
+    cases.append(sc)
+    sc = scenes.free_boxes(1, 4, grid=2)
+    sc.state["pos"][..., 2] += 5.0          # far above the plane: no pairs at all
+    cases.append(sc)
+    sc = scenes.free_boxes(1, 4, grid=2)
+    for g in sc.geoms:
+        g.collide_bits = 0
+        g.category_bits = 0
+    cases.append(sc)
+    sc = scenes.box_stack(nworlds=1, nboxes=3)
+    sc.wp.gravity[2] = 0.0
+    cases.append(sc)
+    for sc in cases:
+        b = B.Batch(lib, sc)
+        a = B.Batch(ref, sc) if ref is not None else None
+        for s in range(20):
+            b.step(0.01)
+            st = b.get_state()
+            assert all(np.isfinite(st[k]).all() for k in st)
+            if a is not None:
+                a.step(0.01)
+                bad = compare_step(a, b, sc.nworlds)
+                assert not bad, bad
