@@ -90,7 +90,7 @@ struct DevPtrs {
                                                  //   record slot 30 = order position of body 1 (| FINDEX_FLAG), slot 31 = body 2 or -1;
                                                  //   rows with a friction index carry it in the (unused) LO slot as integer bits
     int *findex, *order; Real *lambda;           // [W*MR]
-    Real4 *cforce;                               // [W*NB*2]  (fc 6, fa 2)
+    Real4 *cforce;                               // [W*(NB+1)*2]  (fc 6, fa 2) per order position + one dummy slot per world
     Real *invIw;                                 // [W*NB*12], indexed by order position
     unsigned *stats, *seed;                      // [W*4], [W]
     unsigned long long *sweeps;                  // [W*2] = (sweeps, row-sweeps) of the last step
@@ -576,7 +576,7 @@ __global__ void k_rows_finish(const __grid_constant__ DevParams P, const __grid_
     Jp[0] = v0; Jp[1] = v1; Jp[2] = v2; Jp[3] = v3;
     Real4 m0 = { imj[0], imj[1], imj[2], imj[3] }, m1 = { imj[4], imj[5], imj[6], imj[7] }, m2 = { imj[8], imj[9], imj[10], imj[11] };
     Real4 m3 = { imj[12], imj[13], 0, 0 };
-    *(int *)&m3.z = p0; *(int *)&m3.w = p1;
+    *(int *)&m3.z = p0; *(int *)&m3.w = (p1 == -1) ? P.NB : p1;     // one-body rows address the dummy accumulator slot NB
     Mp[0] = m0; Mp[1] = m1; Mp[2] = m2; Mp[3] = m3;
 }
 
@@ -603,7 +603,8 @@ __global__ void k_integrate(const __grid_constant__ DevParams P, const __grid_co
     Real4 lv = D.lvel[gb], av = D.avel[gb], fa = D.facc[gb], ta = D.tacc[gb];
     int4 info = D.island_info[(size_t)w * P.NB + D.body_island[gb]];
     if (info.w > 0) {   // Stage4b quickstep.cpp:3082-3108
-        Real4 c0 = D.cforce[2 * t], c1 = D.cforce[2 * t + 1];
+        const Real4 *cfp = D.cforce + ((size_t)w * (P.NB + 1) + k) * 2;
+        Real4 c0 = cfp[0], c1 = cfp[1];
         lv.x += h * c0.x; av.x += h * c0.w;
         lv.y += h * c0.y; av.y += h * c1.x;
         lv.z += h * c0.z; av.z += h * c1.y;

@@ -159,8 +159,11 @@ def record_traj(batch, h, nsteps, every):
     return out
 
 
-def compare_traj(batch, gold, h, exact=True, tol=None):
-    """Replays the recorded scene on `batch` and compares every checkpoint. Returns list of mismatches."""
+def compare_traj(batch, gold, h, exact=True, tol=None, resync=False):
+    """Replays the recorded scene on `batch` and compares every checkpoint. Returns list of mismatches.
+    resync=True re-uploads the recorded reference state (and dRand seeds) after each checkpoint, so that every
+    segment between checkpoints starts from the reference's state (teacher forcing) and last-ulp libm
+    differences are not amplified over the whole run."""
     bad = []
     W = batch.W
     steps = list(gold["steps"])
@@ -208,4 +211,7 @@ def compare_traj(batch, gold, h, exact=True, tol=None):
                     bad.append("step %d: %s differs by %.3g > %.3g" % (s, k, d, tol["state"]))
         if bad:
             break
+        if resync:
+            batch.set_state(pos=gold["pos"][ci], quat=gold["quat"][ci], lvel=gold["lvel"][ci], avel=gold["avel"][ci])
+            batch.set_seeds(gold["seeds"][ci])
     return bad
