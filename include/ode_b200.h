@@ -25,6 +25,7 @@
 #define ODE_B200_H
 
 #include <stdint.h>
+#include <stddef.h>
 
 #ifdef __cplusplus
 extern "C" {
