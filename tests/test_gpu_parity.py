@@ -5,7 +5,7 @@ Bar: integer observables (broadphase pair set, per-pair contact counts, island l
 iteration counters, dRand seed) identical; floating observables bit-identical wherever the path uses only
 +,-,*,/,sqrt (the build uses -fmad=false); where CUDA libm differs from glibc (atan2 in cullPoints and the
 hinge angle, sin/cos in finite rotation) the stated tolerance is 2e-5 (single) / 1e-12 (double) absolute on
-body state per teacher-forced step, and 5e-4 / 1e-10 over each segment (<= 16 steps between checkpoints, re-
+body state per teacher-forced step, and 2e-3 / 1e-9 over each segment (<= 16 steps between checkpoints, re-
 synchronised to the recorded reference state at every checkpoint) of the golden trajectories of those scenes;
 an ulp of difference in a joint-limit error or a culled contact is amplified by the contact dynamics.
 """
@@ -20,7 +20,7 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(ROOT, "tests", "golden")
 PRECS = ("single", "double")
 TOL = {"single": dict(contact=2e-5, state=2e-5), "double": dict(contact=1e-12, state=1e-12)}
-TOL_FREE = {"single": dict(contact=5e-4, state=5e-4), "double": dict(contact=1e-10, state=1e-10)}
+TOL_FREE = {"single": dict(contact=2e-3, state=2e-3), "double": dict(contact=1e-9, state=1e-9)}
 # scenes whose path contains no libm transcendental call: bit-exact; the others: tolerance above
 EXACT = {"stack": True, "stack_plain": True, "chain": True, "free": True, "pile": False, "pile_sap": False, "ragdoll": False}
 
@@ -54,7 +54,8 @@ def test_free_running_vs_oracle_bit_exact(prec):
 def test_teacher_forced_single_step(prec):
     """SURVEY 8(d) protocol (i): upload the oracle's state at steps {0,10,100,300}, step once on both,
     compare. Scenes with transcendental calls (pile: cullPoints/atan2, ragdoll: hinge angles) included."""
-    for mk, h in ((lambda: scenes.pile(nbodies=125), 0.01), (lambda: scenes.ragdoll(3), 0.01), (lambda: scenes.box_stack(nworlds=2), 0.02)):
+    for mk, h in ((lambda: scenes.pile(nbodies=125), 0.01), (lambda: scenes.ragdoll(3), 0.01),
+                  (lambda: scenes.box_stack(nworlds=2, demo_world_options=False), 0.02)):   # no auto-disable: its history is not part of the uploaded state
         sc = mk()
         a = B.Batch(orc_lib(prec), sc)
         b = B.Batch(gpu_lib(prec), sc)
