@@ -218,21 +218,21 @@ OdebBatch *odeb_create(const OdebWorldParams *wp,
     P.damp_lin_scale = (Real)wp->linear_damping; P.damp_ang_scale = (Real)wp->angular_damping;
     { Real t = (Real)wp->linear_damping_thr; P.damp_lin_thr = t * t; t = (Real)wp->angular_damping_thr; P.damp_ang_thr = t * t; }
     P.max_ang_speed = (Real)wp->max_angular_speed;
-    P.solver_lanes = 16;
-    if (const char *s = getenv("ODEB_SOLVER_LANES")) { int v = atoi(s); if (v == 4 || v == 8 || v == 16 || v == 32) P.solver_lanes = v; }
-    {   // shared-memory budget of k_solve: ring + per-body accumulators + lambda/order for SR rows, per lane
+    {   // shared-memory budget of k_solve (16 worlds per warp): ring + per-body accumulators + lambda/metadata for SR rows
         int sr = P.MR < 512 ? P.MR : 512;
         if (const char *s = getenv("ODEB_SOLVER_ROWS")) sr = atoi(s);
-        if (sr > 65534) sr = 65534;
-        for (;;) {
-            size_t per_lane = (size_t)ODEB_RING * 32 * sizeof(Real) + 2 * (size_t)(P.NB + 1) * sizeof(Real4) + (size_t)(sr + 1) * (sizeof(Real) + 2);
-            B->solve_smem = ((per_lane * P.solver_lanes + 31) / 32) * 32;
-            if (B->solve_smem <= 200 * 1024 || sr == 0) break;
-            sr /= 2;
+        if (sr > 1023) sr = 1023;                      // metadata word: 10-bit friction-index row
+        if (P.NB + 1 > 2047) sr = 0;                   // metadata word: 11-bit body slots -> global path only
+        {
+            const size_t budget = 112 * 1024;          // two resident warps' worth per SM (227 KB / 2)
+            const size_t fixed = (size_t)ODEB_RING * ODEB_HALF_CHUNKS * 32 * 16 + 2 * (size_t)(P.NB + 1) * ODEB_WPW * sizeof(Real4)
+                               + ODEB_WPW * sizeof(Real) + (size_t)ODEB_META_PAD * 32 * sizeof(unsigned);
+            const size_t per_row = ODEB_WPW * sizeof(Real) + 32 * sizeof(unsigned);
+            if (fixed + per_row > budget) sr = 0;
+            else if (fixed + (size_t)sr * per_row > budget) sr = (int)((budget - fixed) / per_row);
+            B->solve_smem = ((fixed + (size_t)sr * per_row + 31) / 32) * 32;
         }
-        if (sr & 1) sr--;
         P.SR = sr;
-        if (2 * (size_t)P.NB * sizeof(Real4) * P.solver_lanes > 150 * 1024) P.SR = 0;   // bodies alone overflow: global path only
         if (P.SR == 0) B->solve_smem = 0;
     }
 
@@ -348,7 +348,7 @@ OdebBatch *odeb_create(const OdebWorldParams *wp,
             && dev_alloc(B, &D.body_order, WB) && dev_alloc(B, &D.body_pos, WB) && dev_alloc(B, &D.body_island, WB)
             && dev_alloc(B, &D.joint_order, W * P.NJT) && dev_alloc(B, &D.joint_row, W * P.NJT) && dev_alloc(B, &D.joint_island, W * P.NJT)
             && dev_alloc(B, &D.island_info, WB) && dev_alloc(B, &D.nislands, W) && dev_alloc(B, &D.nordered, W) && dev_alloc(B, &D.njord, W) && dev_alloc(B, &D.mrows, W);
-    ok = ok && dev_alloc(B, &D.rows, W * P.MR * 8) && dev_alloc(B, &D.findex, W * P.MR) && dev_alloc(B, &D.order, W * P.MR)
+    ok = ok && dev_alloc(B, &D.rows, W * P.MR * 8) && dev_alloc(B, &D.rbody, W * P.MR) && dev_alloc(B, &D.findex, W * P.MR) && dev_alloc(B, &D.order, W * P.MR)
             && dev_alloc(B, &D.lambda, W * P.MR) && dev_alloc(B, &D.cforce, W * (nbody + 1) * 2) && dev_alloc(B, &D.invIw, WB * 12)
             && dev_alloc(B, &D.stats, W * 4) && dev_alloc(B, &D.seed, W) && dev_alloc(B, &D.sweeps, 2 * W) && dev_alloc(B, &D.overflow, 1);
     B->stage_elems = WB;
@@ -356,14 +356,7 @@ OdebBatch *odeb_create(const OdebWorldParams *wp,
     if (ok && cudaMallocHost((void **)&B->h_stage, WB * sizeof(Real4)) != cudaSuccess) { set_err("cudaMallocHost failed"); ok = false; }
     if (ok && cudaStreamCreateWithFlags(&B->stream, cudaStreamNonBlocking) != cudaSuccess) { set_err("cudaStreamCreate failed"); ok = false; }
     if (ok && B->solve_smem > 48 * 1024) {
-        cudaError_t ea = cudaSuccess;
-        switch (P.solver_lanes) {
-        case 4: ea = cudaFuncSetAttribute(k_solve<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->solve_smem); break;
-        case 8: ea = cudaFuncSetAttribute(k_solve<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->solve_smem); break;
-        case 32: ea = cudaFuncSetAttribute(k_solve<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->solve_smem); break;
-        default: ea = cudaFuncSetAttribute(k_solve<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->solve_smem); break;
-        }
-        if (ea != cudaSuccess) { set_err("cudaFuncSetAttribute(smem=%zu) failed", B->solve_smem); ok = false; }
+        if (cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->solve_smem) != cudaSuccess) { set_err("cudaFuncSetAttribute(smem=%zu) failed", B->solve_smem); ok = false; }
     }
     if (!ok) { odeb_destroy(B); return 0; }
 
@@ -489,15 +482,7 @@ static int launch_step(OdebBatch *B, cudaStream_t s, bool timed)
     k_rows_finish<<<nblk(W * P.MR, 128), 128, 0, s>>>(P, D);
     cudaEvent_t e0 = 0, e1 = 0;
     if (timed) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s); }
-    {
-        size_t warps = (W + P.solver_lanes - 1) / P.solver_lanes;
-        switch (P.solver_lanes) {
-        case 4: k_solve<4><<<(unsigned)warps, 32, B->solve_smem, s>>>(P, D); break;
-        case 8: k_solve<8><<<(unsigned)warps, 32, B->solve_smem, s>>>(P, D); break;
-        case 32: k_solve<32><<<(unsigned)warps, 32, B->solve_smem, s>>>(P, D); break;
-        default: k_solve<16><<<(unsigned)warps, 32, B->solve_smem, s>>>(P, D); break;
-        }
-    }
+    k_solve<<<nblk(W, ODEB_WPW), 32, B->solve_smem, s>>>(P, D);
     if (timed) { cudaEventRecord(e1, s); B->pending.push_back(std::make_pair(e0, e1)); }
     k_integrate<<<nblk(W * P.NB, 128), 128, 0, s>>>(P, D);
     B->launches += 6;

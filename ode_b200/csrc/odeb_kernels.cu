@@ -55,7 +55,6 @@ struct DevParams {
     Real adis_lin, adis_ang, adis_time; int adis_steps, adis_samples;
     Real damp_lin_scale, damp_ang_scale, damp_lin_thr, damp_ang_thr, max_ang_speed;
     Real h, hrecip;
-    int solver_lanes;                     // active lanes per warp in k_solve
     int SR;                               // rows per island that fit the shared-memory solve path
 };
 
@@ -86,9 +85,9 @@ struct DevPtrs {
     int4 *island_info;                           // [W*NB] = (bodyStart, nb, rowStart, m)
     int *nislands, *nordered, *njord, *mrows;    // [W]
     // rows
-    Real4 *rows;                                 // [W*MR*8]: one 32-real record per row = J row (4 Real4) + iMJ row (4 Real4);
-                                                 //   record slot 30 = order position of body 1 (| FINDEX_FLAG), slot 31 = body 2 or -1;
-                                                 //   rows with a friction index carry it in the (unused) LO slot as integer bits
+    Real4 *rows;                                 // [W*MR*8]: one 32-real record per row, split into a body-1 half and a body-2 half
+                                                 //   (layout in odeb_solve.cuh)
+    int2 *rbody;                                 // [W*MR] accumulator slots (order positions) of the row's two bodies; one-body rows: (p0, NB)
     int *findex, *order; Real *lambda;           // [W*MR]
     Real4 *cforce;                               // [W*(NB+1)*2]  (fc 6, fa 2) per order position + one dummy slot per world
     Real *invIw;                                 // [W*NB*12], indexed by order position
@@ -570,14 +569,13 @@ __global__ void k_rows_finish(const __grid_constant__ DevParams P, const __grid_
     q[C_RHS] *= Ad;
     for (int k = 0; k < 6; k++) q[C_J1L + k] *= Ad;
     if (p1 != -1) for (int k = 0; k < 6; k++) q[C_J2L + k] *= Ad;
-    Real4 v0 = { q[0], q[1], q[2], q[3] }, v1 = { q[4], q[5], q[6], q[7] }, v2 = { q[8], q[9], q[10], q[11] }, v3 = { q[12], q[13], q[14], q[15] };
-    int fi = D.findex[t];
-    if (fi != -1) { v3.z = 0; *(int *)&v3.z = fi; p0 |= FINDEX_FLAG; }   // LO is unused for friction-index rows (quickstep.cpp:2971-2978)
-    Jp[0] = v0; Jp[1] = v1; Jp[2] = v2; Jp[3] = v3;
-    Real4 m0 = { imj[0], imj[1], imj[2], imj[3] }, m1 = { imj[4], imj[5], imj[6], imj[7] }, m2 = { imj[8], imj[9], imj[10], imj[11] };
-    Real4 m3 = { imj[12], imj[13], 0, 0 };
-    *(int *)&m3.z = p0; *(int *)&m3.w = (p1 == -1) ? P.NB : p1;     // one-body rows address the dummy accumulator slot NB
-    Mp[0] = m0; Mp[1] = m1; Mp[2] = m2; Mp[3] = m3;
+    // record = body-1 half | body-2 half (odeb_solve.cuh)
+    Real4 a0 = { q[0], q[1], q[2], q[3] }, a1 = { q[4], q[5], q[6], q[7] };
+    Real4 a2 = { imj[0], imj[1], imj[2], imj[3] }, a3 = { imj[4], imj[5], imj[6], q[C_HI] };
+    Real4 b0 = { q[8], q[9], q[10], q[11] }, b1 = { q[12], q[13], q[C_LO], q[C_HI] };
+    Real4 b2 = { imj[7], imj[8], imj[9], imj[10] }, b3 = { imj[11], imj[12], imj[13], 0 };
+    Jp[0] = a0; Jp[1] = a1; Jp[2] = a2; Jp[3] = a3; Jp[4] = b0; Jp[5] = b1; Jp[6] = b2; Jp[7] = b3;
+    D.rbody[t] = make_int2(p0, (p1 == -1) ? P.NB : p1);     // one-body rows address the dummy accumulator slot NB
 }
 
 #include "odeb_solve.cuh"

@@ -1,24 +1,34 @@
 // odeb_solve.cuh -- k_solve: the SOR-LCP sweeps of dxQuickStepIsland (quickstep.cpp:1823-1856 loop,
 // :2329-2355 ReorderPrep, :2578-2611 random reorder via dRandInt, :2917-3033 IterationStep,
-// :3253-3285 dynamic iteration control), one thread per world, islands in the reference's order.
+// :3253-3285 dynamic iteration control), islands of a world in the reference's order.
 //
 // The row update is a strict dependency chain (each row reads the constraint-force accumulators the
 // previous row wrote), so the kernel is latency-bound per world and throughput comes from worlds in
-// flight.  Data placement on B200:
-//   * lambda, the solve order and the per-body accumulators (cforce + max-adjustment pair) live in shared
-//     memory, interleaved [element][lane] so that every lane always hits its own bank;
-//   * the 32-real row records (J row + iMJ row, 128 B single / 256 B double) stream from L2/HBM through a
-//     per-lane ring of cp.async (LDGSTS) stages, issued RING-1 rows ahead in solve order, bypassing L1;
-//   * `solver_lanes` (template LS) lanes of each warp carry a world each: fewer lanes = more warps for the
-//     four schedulers, more lanes = fewer shared-memory instructions per world (measured optimum: 16).
-// Islands too large for the shared-memory budget take the global-memory path (same arithmetic).
+// flight and from the length of the per-row instruction stream.  Mapping on B200:
+//   * TWO lanes per world (16 worlds per warp): lane A owns the body-1 half of every row (J1, rhs, cfm,
+//     iMJ1), lane B the body-2 half (J2, lo, hi, iMJ2).  Each lane forms its own 6-term dot product in the
+//     reference's left-to-right order, the two partial results meet through one warp shuffle
+//     (delta = ((rhs - lambda*cfm) - s1) - s2, exactly the reference's association), both lanes clamp
+//     redundantly and each updates its own body's accumulators.  Per-lane instruction and shared-memory
+//     traffic are half of a one-lane-per-world sweep.
+//   * lambda, the per-position metadata (row index, friction index, the two body slots) and the per-body
+//     accumulators (cforce + max-adjustment pair) live in shared memory, interleaved [element][world];
+//   * the row half-records (16 reals: 64 B single / 128 B double) stream from L2/HBM through a per-lane ring
+//     of cp.async (LDGSTS, L1-bypass) stages issued RING-1 rows ahead in solve order;
+//   * the row update is branch-free; one-body rows address a dummy accumulator slot with zero J2/iMJ2.
+// Islands too large for the shared-memory budget take the global-memory path (same arithmetic, lane A).
 #ifndef ODEB_SOLVE_CUH
 #define ODEB_SOLVE_CUH
 
-#define ODEB_RING 8
-#define ODEB_REC_CHUNKS ((int)(sizeof(Real) * 32 / 16))   // 16-byte chunks per row record
+#define ODEB_RING 8                                        // must stay 8: the row loop is unrolled by the ring depth
+#define ODEB_HALF_CHUNKS ((int)(sizeof(Real) * 16 / 16))   // 16-byte chunks per half record
+#define ODEB_WPW 16                                        // worlds per warp
 
-struct RowRegs { Real4 j0, j1, j2, j3, m0, m1, m2, m3; };
+struct HalfRegs { Real4 q0, q1, q2, q3; };
+// record of one row in HBM (8 Real4):
+//   A half: q0 = {J1l.x, J1l.y, J1l.z, J1a.x}  q1 = {J1a.y, J1a.z, rhs, cfm}  q2 = {iMJ1l.xyz, iMJ1a.x}  q3 = {iMJ1a.y, iMJ1a.z, max|iMJ1|, hi}
+//   B half: q0 = {J2l.x, J2l.y, J2l.z, J2a.x}  q1 = {J2a.y, J2a.z, lo, hi}    q2 = {iMJ2l.xyz, iMJ2a.x}  q3 = {iMJ2a.y, iMJ2a.z, max|iMJ2|, 0}
+// (J row quickstep.cpp:267-322, iMJ row :374-431)
 
 __device__ __forceinline__ void cp_async16(unsigned dst, const void *src)
 {
@@ -27,43 +37,8 @@ __device__ __forceinline__ void cp_async16(unsigned dst, const void *src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-// one SOR row update on registers + accumulators reached through LD/ST functors (shared or global)
-template <class CF, class LAM>
-__device__ __forceinline__ void row_update(const RowRegs &cur, int index, int rbase, CF &cf, LAM &lam)
-{
-    Real old_lambda = lam.get(index);
-    int b1raw = *(const int *)&cur.m3.z, b2 = *(const int *)&cur.m3.w;
-    int b1 = b1raw & ~FINDEX_FLAG;
-    Real delta = cur.j1.z - old_lambda * cur.j1.w;
-    Real4 f1a = cf.get(2 * b1), f1b = cf.get(2 * b1 + 1);
-    delta -= f1a.x * cur.j0.x + f1a.y * cur.j0.y + f1a.z * cur.j0.z + f1a.w * cur.j0.w + f1b.x * cur.j1.x + f1b.y * cur.j1.y;
-    Real4 f2a = cf.get(2 * b2), f2b = cf.get(2 * b2 + 1);      // one-body rows: b2 = dummy slot NB, J2 = iMJ2 = 0
-    delta -= f2a.x * cur.j2.x + f2a.y * cur.j2.y + f2a.z * cur.j2.z + f2a.w * cur.j2.w + f2b.x * cur.j3.x + f2b.y * cur.j3.y;
-    Real hi_act, lo_act;
-    if (b1raw & FINDEX_FLAG) { int fi = *(const int *)&cur.j3.z; hi_act = RFABS(cur.j3.w * lam.get(fi - rbase)); lo_act = -hi_act; }
-    else { hi_act = cur.j3.w; lo_act = cur.j3.z; }
-    Real new_lambda = old_lambda + delta;
-    if (new_lambda < lo_act) { delta = lo_act - old_lambda; lam.set(index, lo_act); }
-    else if (new_lambda > hi_act) { delta = hi_act - old_lambda; lam.set(index, hi_act); }
-    else lam.set(index, new_lambda);
-    if (delta != 0) {
-        f1a.x += delta * cur.m0.x; f1a.y += delta * cur.m0.y; f1a.z += delta * cur.m0.z; f1a.w += delta * cur.m0.w;
-        f1b.x += delta * cur.m1.x; f1b.y += delta * cur.m1.y;
-        if (delta > 0) f1b.w += delta * cur.m1.z; else f1b.z += delta * cur.m1.z;
-        cf.set(2 * b1, f1a); cf.set(2 * b1 + 1, f1b);
-        if (delta > 0) f2b.w += delta * cur.m3.y; else f2b.z += delta * cur.m3.y;
-        f2a.x += delta * cur.m1.w; f2a.y += delta * cur.m2.x; f2a.z += delta * cur.m2.y; f2a.w += delta * cur.m2.z;
-        f2b.x += delta * cur.m2.w; f2b.y += delta * cur.m3.x;
-        cf.set(2 * b2, f2a); cf.set(2 * b2 + 1, f2b);
-    }
-}
-
-struct CfGlobal { Real4 *p; __device__ Real4 get(int i) const { return p[i]; } __device__ void set(int i, const Real4 &v) { p[i] = v; } };
-struct LamGlobal { Real *p; __device__ Real get(int i) const { return p[i]; } __device__ void set(int i, Real v) { p[i] = v; } };
-struct CfShared { Real4 *p; int ls; __device__ Real4 get(int i) const { return p[i * ls]; } __device__ void set(int i, const Real4 &v) { p[i * ls] = v; } };
-struct LamShared { Real *p; int ls; __device__ Real get(int i) const { return p[i * ls]; } __device__ void set(int i, Real v) { p[i * ls] = v; } };
-
-// iteration control shared by both paths; returns true when the island is finished
+// iteration control (quickstep.cpp:1832-1855, :3253-3285); returns true when the island is finished.
+// fa (max adjustments) live in the .z/.w of each body's second accumulator vector.
 template <class CF>
 __device__ __forceinline__ bool sweep_control(const DevParams &P, CF &cf, int bstart, int nb, unsigned &iteration, unsigned &extra,
                                               Real &exit_delta, unsigned &st1, unsigned &st2, unsigned &st3)
@@ -91,178 +66,250 @@ __device__ __forceinline__ bool sweep_control(const DevParams &P, CF &cf, int bs
     return false;
 }
 
-// Shared-memory island solve, software-pipelined for a single in-order warp:
-//   per row i:  (1) loads that depend on row i-1's stores (lambda, the two bodies' accumulators),
-//               (2) bookkeeping for later rows that fills their latency (cp.async issue for row i+RING-1,
-//                   wait + register load of row i+1's record and solve-order entry),
-//               (3) the branch-free arithmetic chain, (4) stores.
-// One-body rows address a dummy accumulator slot (index NB) with zero J2/iMJ2 instead of branching.
-template <int LS>
-__device__ __forceinline__ void solve_island_shared(const DevParams &P, unsigned char *smem, int lane,
-                                                    const Real4 *rows, const int *findex, Real4 *cf_out,
-                                                    int bstart, int nb, int rstart, int m, unsigned &seed,
-                                                    unsigned &st1, unsigned &st2, unsigned &st3,
-                                                    unsigned long long &sweeps, unsigned long long &rowsweeps)
+struct CfGlobal { Real4 *p; __device__ Real4 get(int i) const { return p[i]; } __device__ void set(int i, const Real4 &v) { p[i] = v; } };
+struct CfShared { Real4 *p; __device__ Real4 get(int i) const { return p[i * ODEB_WPW]; } __device__ void set(int i, const Real4 &v) { p[i * ODEB_WPW] = v; } };
+
+__device__ __forceinline__ Real shfl_xor1(unsigned mask, Real v)
 {
-    constexpr int CH = ODEB_REC_CHUNKS;
-    uint4 *ring = (uint4 *)smem + lane;                                            // chunk (slot,c) at ring[(slot*CH+c)*LS]
-    Real4 *cf = (Real4 *)((uint4 *)smem + ODEB_RING * CH * LS) + lane;             // cf[k*LS], k < 2*(NB+1)
-    Real *lam = (Real *)((Real4 *)((uint4 *)smem + ODEB_RING * CH * LS) + 2 * (P.NB + 1) * LS) + lane;   // lam[i*LS]
-    unsigned short *ord = (unsigned short *)((Real *)((Real4 *)((uint4 *)smem + ODEB_RING * CH * LS) + 2 * (P.NB + 1) * LS) + (P.SR + 1) * LS) + lane;
+    return __shfl_xor_sync(mask, v, 1);
+}
+
+__device__ __forceinline__ void load_half(HalfRegs &h, const uint4 *slot)
+{   // slot: chunk c at slot[c * 32]
+#if defined(ODEB_DOUBLE)
+    uint4 t[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) t[c] = slot[c * 32];
+    const Real4 *r4 = (const Real4 *)t;
+    h.q0 = r4[0]; h.q1 = r4[1]; h.q2 = r4[2]; h.q3 = r4[3];
+#else
+    const Real4 *s4 = (const Real4 *)slot;
+    h.q0 = s4[0]; h.q1 = s4[32]; h.q2 = s4[64]; h.q3 = s4[96];
+#endif
+}
+
+// per-position, per-lane metadata word: row index (bits 0..10) | friction-index row (bits 11..20) | this lane's
+// accumulator slot (bits 21..31).  Rows without a friction index carry their own index in the second field.
+#define META_IDX(mt) ((int)((mt) & 0x7ffu))
+#define META_FI(mt) ((int)(((mt) >> 11) & 0x3ffu))
+#define META_SLOT(mt) ((int)((mt) >> 21))
+#define ODEB_META_PAD (2 * ODEB_RING)
+#define ODEB_FULL 0xffffffffu
+
+// One row of the sweep for one lane of the pair.  CUR/NXT are the two register sets of the software pipeline,
+// K is the position of the row inside the unrolled group of ODEB_RING rows (ring stages become constants).
+//   (1) loads that depend on row i-1's stores (lambda, this lane's body accumulators),
+//   (2) bookkeeping that fills their latency (cp.async issue for row i+RING-1, register load of row i+1's
+//       half record and metadata), (3) the arithmetic chain with one shuffle, (4) stores + warp sync.
+// The whole warp runs the row loop in lockstep (trip count = longest island of its 16 worlds); positions past a
+// world's own row count read the zero metadata word and have their stores predicated off.
+#define ODEB_ROW(CUR, NXT, MT, MTN, K)                                                                                   \
+    {                                                                                                                    \
+        const int index = META_IDX(MT), fi = META_FI(MT);                                                                \
+        Real4 *cfp = cf + (size_t)META_SLOT(MT) * (2 * ODEB_WPW);                                                       \
+        const Real old_lambda = lam[index * ODEB_WPW];                                                                   \
+        const Real lam_fi = lam[fi * ODEB_WPW];                                                                          \
+        Real4 fa = cfp[0], fb = cfp[ODEB_WPW];                                                                           \
+        {                                                                                                                \
+            if (i + (K) + ODEB_RING - 1 < m) {                                                                           \
+                const char *src = rec_base + (size_t)META_IDX(ma) * (sizeof(Real) * 32);                                 \
+                const unsigned dst = ring_addr + (unsigned)((((K) + ODEB_RING - 1) & (ODEB_RING - 1)) * CH * 32 * 16);   \
+                _Pragma("unroll") for (int c = 0; c < CH; c++) cp_async16(dst + c * 32 * 16, src + c * 16);             \
+            }                                                                                                            \
+            cp_async_commit();                                                                                           \
+            cp_async_wait<ODEB_RING - 2>();                                                                              \
+        }                                                                                                                \
+        load_half(NXT, ring + (size_t)(((K) + 1) & (ODEB_RING - 1)) * CH * 32);                                         \
+        MTN = (i + (K) + 1 < m) ? mp[((K) + 1) * 32] : 0u;                                                               \
+        ma = mp[((K) + ODEB_RING) * 32];                                /* metadata of the row prefetched next */        \
+        const Real s = fa.x * CUR.q0.x + fa.y * CUR.q0.y + fa.z * CUR.q0.z + fa.w * CUR.q0.w + fb.x * CUR.q1.x + fb.y * CUR.q1.y; \
+        const Real ta = (CUR.q1.z - old_lambda * CUR.q1.w) - s;         /* lane A: (rhs - lambda*cfm) - s1 */           \
+        const Real mine = side ? s : ta;                                                                                 \
+        const Real other = shfl_xor1(ODEB_FULL, mine);                                                                   \
+        const Real lo_b = shfl_xor1(ODEB_FULL, CUR.q1.z);               /* lane A receives lo from lane B */             \
+        Real delta = side ? (other - mine) : (mine - other);            /* ((rhs - lambda*cfm) - s1) - s2 */             \
+        const Real hi = side ? CUR.q1.w : CUR.q3.w;                                                                      \
+        const Real lo = side ? CUR.q1.z : lo_b;                                                                          \
+        const bool hasfi = fi != index;                                                                                  \
+        const Real hi_f = RFABS(hi * lam_fi);                                                                            \
+        const Real hi_act = hasfi ? hi_f : hi;                                                                           \
+        const Real lo_act = hasfi ? -hi_f : lo;                                                                          \
+        Real new_lambda = old_lambda + delta;                                                                            \
+        const bool c_lo = new_lambda < lo_act;                                                                           \
+        const bool c_hi = !c_lo && (new_lambda > hi_act);                                                                \
+        const Real lim = c_lo ? lo_act : hi_act;                                                                         \
+        if (c_lo || c_hi) { delta = lim - old_lambda; new_lambda = lim; }                                                \
+        const bool pos = delta > 0;                                                                                      \
+        fa.x += delta * CUR.q2.x; fa.y += delta * CUR.q2.y; fa.z += delta * CUR.q2.z; fa.w += delta * CUR.q2.w;          \
+        fb.x += delta * CUR.q3.x; fb.y += delta * CUR.q3.y;                                                              \
+        {                                                                                                                \
+            const Real t1 = delta * CUR.q3.z;                                                                            \
+            const Real pv = fb.w + t1, nv = fb.z + t1;                                                                   \
+            fb.w = pos ? pv : fb.w; fb.z = pos ? fb.z : nv;                                                              \
+        }                                                                                                                \
+        if (i + (K) < m) {                                                                                               \
+            if (side == 0) lam[index * ODEB_WPW] = new_lambda;                                                           \
+            cfp[0] = fa; cfp[ODEB_WPW] = fb;                                                                             \
+        }                                                                                                                \
+        __syncwarp();                                                                                                    \
+    }
+
+// Shared-memory solve of one island per world by the whole warp (lane pairs in lockstep). `m_own` is the island's
+// row count for this lane's world, 0 when the world has no island for this round (the pair then idles through
+// the row loop with stores predicated off).
+__device__ __forceinline__ void solve_islands_warp(const DevParams &P, unsigned char *smem, int lane,
+                                                   const Real4 *rows, const int *findex, const int2 *rbody, Real4 *cf_out,
+                                                   int bstart, int nb, int rstart, int m_own, unsigned &seed,
+                                                   unsigned &st1, unsigned &st2, unsigned &st3,
+                                                   unsigned long long &sweeps, unsigned long long &rowsweeps)
+{
+    constexpr int CH = ODEB_HALF_CHUNKS;
+    const int wl = lane >> 1, side = lane & 1;
+    uint4 *ring = (uint4 *)smem + lane;                                          // chunk (stage,c) at ring[(stage*CH+c)*32]
+    unsigned char *p = smem + (size_t)ODEB_RING * CH * 32 * 16;
+    Real4 *cf = (Real4 *)p + wl;  p += (size_t)2 * (P.NB + 1) * ODEB_WPW * sizeof(Real4);          // cf[k*16], k < 2*(NB+1)
+    Real *lam = (Real *)p + wl;   p += (size_t)(P.SR + 1) * ODEB_WPW * sizeof(Real);               // lam[i*16]
+    unsigned *meta = (unsigned *)p + lane;                                                            // meta[pos*32], one column per lane
     const unsigned ring_addr = (unsigned)__cvta_generic_to_shared(ring);
     const Real4 z4 = { 0, 0, 0, 0 };
-    for (int k = 0; k < 2 * nb; k++) cf[(2 * bstart + k) * LS] = z4;
-    cf[(2 * P.NB) * LS] = z4; cf[(2 * P.NB + 1) * LS] = z4;
-    int nvalid = 0;
-    for (int i = 0; i < m; i++) { lam[i * LS] = 0; if (findex[rstart + i] != -1) nvalid++; }
-    {   // ReorderPrep quickstep.cpp:2329-2355
-        int head = 0, tail = m - nvalid;
-        for (int i = 0; i < m; i++) { if (findex[rstart + i] == -1) ord[(head++) * LS] = (unsigned short)i; else ord[(tail++) * LS] = (unsigned short)i; }
+    if (m_own > 0) {
+        for (int k = side; k < 2 * nb; k += 2) cf[(2 * bstart + k) * ODEB_WPW] = z4;
+        cf[(2 * P.NB + side) * ODEB_WPW] = z4;
+        for (int i = side; i <= m_own; i += 2) lam[i * ODEB_WPW] = 0;
+        // ReorderPrep quickstep.cpp:2329-2355: rows without a friction index first, then the others
+        int nvalid = 0;
+        for (int i = 0; i < m_own; i++) if (findex[rstart + i] != -1) nvalid++;
+        int head = 0, tail = m_own - nvalid;
+        for (int i = 0; i < m_own; i++) {
+            const int fi = findex[rstart + i];
+            const int2 rb = rbody[rstart + i];
+            const unsigned slot = (unsigned)(side ? rb.y : rb.x);
+            const unsigned mt = (unsigned)i | ((unsigned)(fi == -1 ? i : fi - rstart) << 11) | (slot << 21);
+            if (fi == -1) meta[(head++) * 32] = mt; else meta[(tail++) * 32] = mt;
+        }
+    } else {
+        lam[0] = 0;     // idle pairs address row 0 / slot 0 only
     }
-    ord[m * LS] = 0;
-    const char *rec_base = (const char *)(rows + (size_t)rstart * 8);
+    __syncwarp();
+    const char *rec_base = (const char *)(rows + (size_t)rstart * 8) + side * (sizeof(Real) * 16);
     Real exit_delta = P.premature_delta;
-    CfShared cfs = { cf, LS };
-    for (unsigned iteration = 0, extra = 0;;) {
-        if (iteration >= 8 && (iteration & 7) == 0) {
-            // ConstraintsShuffling quickstep.cpp:2578-2611 with dRandInt misc.cpp:78-139
-            for (int idx = 1; idx < m; idx++) {
+    CfShared cfs = { cf };
+    int done = m_own > 0 ? 0 : 1;
+    unsigned iteration = 0, extra = 0;
+    for (;;) {
+        if (!done && iteration >= 8 && (iteration & 7) == 0) {
+            // ConstraintsShuffling quickstep.cpp:2578-2611 with dRandInt misc.cpp:78-139; each lane permutes its own column
+            for (int idx = 1; idx < m_own; idx++) {
                 int sw = odeb_rand_int(&seed, idx + 1);
-                unsigned short a = ord[idx * LS], b = ord[sw * LS];
-                ord[idx * LS] = b; ord[sw * LS] = a;
+                unsigned a = meta[idx * 32], b = meta[sw * 32];
+                meta[idx * 32] = b; meta[sw * 32] = a;
             }
         }
+        __syncwarp();
+        const int m = done ? 0 : m_own;
+        const int m_max = __reduce_max_sync(ODEB_FULL, m);
 #pragma unroll
         for (int k = 0; k < ODEB_RING - 1; k++) {
             if (k < m) {
-                const char *src = rec_base + (size_t)ord[k * LS] * (sizeof(Real) * 32);
-                unsigned dst = ring_addr + (unsigned)(k * CH * LS * 16);
+                const char *src = rec_base + (size_t)META_IDX(meta[k * 32]) * (sizeof(Real) * 32);
+                unsigned dst = ring_addr + (unsigned)(k * CH * 32 * 16);
 #pragma unroll
-                for (int c = 0; c < CH; c++) cp_async16(dst + c * LS * 16, src + c * 16);
+                for (int c = 0; c < CH; c++) cp_async16(dst + c * 32 * 16, src + c * 16);
             }
             cp_async_commit();
         }
         cp_async_wait<ODEB_RING - 2>();
-        RowRegs cur;
-        {
-            const uint4 *slot = ring;
-#if defined(ODEB_DOUBLE)
-            uint4 t[16];
-#pragma unroll
-            for (int c = 0; c < 16; c++) t[c] = slot[c * LS];
-            const Real4 *r4 = (const Real4 *)t;
-            cur.j0 = r4[0]; cur.j1 = r4[1]; cur.j2 = r4[2]; cur.j3 = r4[3]; cur.m0 = r4[4]; cur.m1 = r4[5]; cur.m2 = r4[6]; cur.m3 = r4[7];
-#else
-            const Real4 *s4 = (const Real4 *)slot;
-            cur.j0 = s4[0]; cur.j1 = s4[LS]; cur.j2 = s4[2 * LS]; cur.j3 = s4[3 * LS];
-            cur.m0 = s4[4 * LS]; cur.m1 = s4[5 * LS]; cur.m2 = s4[6 * LS]; cur.m3 = s4[7 * LS];
-#endif
-        }
-        int index = ord[0];
-        for (int i = 0; i < m; i++) {
-            // (1) loads depending on the previous row's stores
-            const int b1raw = *(const int *)&cur.m3.z, b2 = *(const int *)&cur.m3.w;
-            const int b1 = b1raw & ~FINDEX_FLAG;
-            const bool hasfi = (b1raw & FINDEX_FLAG) != 0;
-            const int fi = hasfi ? (*(const int *)&cur.j3.z - rstart) : index;
-            const Real old_lambda = lam[index * LS];
-            const Real lam_fi = lam[fi * LS];
-            Real4 f1a = cf[(2 * b1) * LS], f1b = cf[(2 * b1 + 1) * LS];
-            Real4 f2a = cf[(2 * b2) * LS], f2b = cf[(2 * b2 + 1) * LS];
-            // (2) bookkeeping for later rows
-            {
-                const int ahead = i + ODEB_RING - 1;
-                if (ahead < m) {
-                    const char *src = rec_base + (size_t)ord[ahead * LS] * (sizeof(Real) * 32);
-                    unsigned dst = ring_addr + (unsigned)((ahead & (ODEB_RING - 1)) * CH * LS * 16);
-#pragma unroll
-                    for (int c = 0; c < CH; c++) cp_async16(dst + c * LS * 16, src + c * 16);
-                }
-                cp_async_commit();
-                cp_async_wait<ODEB_RING - 2>();
-            }
-            RowRegs nxt;
-            {
-                const uint4 *slot = ring + (size_t)((i + 1) & (ODEB_RING - 1)) * CH * LS;
-#if defined(ODEB_DOUBLE)
-                uint4 t[16];
-#pragma unroll
-                for (int c = 0; c < 16; c++) t[c] = slot[c * LS];
-                const Real4 *r4 = (const Real4 *)t;
-                nxt.j0 = r4[0]; nxt.j1 = r4[1]; nxt.j2 = r4[2]; nxt.j3 = r4[3]; nxt.m0 = r4[4]; nxt.m1 = r4[5]; nxt.m2 = r4[6]; nxt.m3 = r4[7];
-#else
-                const Real4 *s4 = (const Real4 *)slot;
-                nxt.j0 = s4[0]; nxt.j1 = s4[LS]; nxt.j2 = s4[2 * LS]; nxt.j3 = s4[3 * LS];
-                nxt.m0 = s4[4 * LS]; nxt.m1 = s4[5 * LS]; nxt.m2 = s4[6 * LS]; nxt.m3 = s4[7 * LS];
-#endif
-            }
-            const int nindex = ord[(i + 1) * LS];
-            // (3) IterationStep quickstep.cpp:2917-3033, branch-free
-            Real delta = cur.j1.z - old_lambda * cur.j1.w;
-            delta -= f1a.x * cur.j0.x + f1a.y * cur.j0.y + f1a.z * cur.j0.z + f1a.w * cur.j0.w + f1b.x * cur.j1.x + f1b.y * cur.j1.y;
-            delta -= f2a.x * cur.j2.x + f2a.y * cur.j2.y + f2a.z * cur.j2.z + f2a.w * cur.j2.w + f2b.x * cur.j3.x + f2b.y * cur.j3.y;
-            const Real hi_f = RFABS(cur.j3.w * lam_fi);
-            const Real hi_act = hasfi ? hi_f : cur.j3.w;
-            const Real lo_act = hasfi ? -hi_f : cur.j3.z;
-            Real new_lambda = old_lambda + delta;
-            const bool c_lo = new_lambda < lo_act;
-            const bool c_hi = !c_lo && (new_lambda > hi_act);
-            const Real lim = c_lo ? lo_act : hi_act;
-            if (c_lo || c_hi) { delta = lim - old_lambda; new_lambda = lim; }
-            const bool pos = delta > 0;
-            f1a.x += delta * cur.m0.x; f1a.y += delta * cur.m0.y; f1a.z += delta * cur.m0.z; f1a.w += delta * cur.m0.w;
-            f1b.x += delta * cur.m1.x; f1b.y += delta * cur.m1.y;
-            {
-                const Real t1 = delta * cur.m1.z, t2 = delta * cur.m3.y;
-                const Real p1v = f1b.w + t1, n1v = f1b.z + t1, p2v = f2b.w + t2, n2v = f2b.z + t2;
-                f1b.w = pos ? p1v : f1b.w; f1b.z = pos ? f1b.z : n1v;
-                f2b.w = pos ? p2v : f2b.w; f2b.z = pos ? f2b.z : n2v;
-            }
-            f2a.x += delta * cur.m1.w; f2a.y += delta * cur.m2.x; f2a.z += delta * cur.m2.y; f2a.w += delta * cur.m2.z;
-            f2b.x += delta * cur.m2.w; f2b.y += delta * cur.m3.x;
-            // (4) stores
-            lam[index * LS] = new_lambda;
-            cf[(2 * b1) * LS] = f1a; cf[(2 * b1 + 1) * LS] = f1b;
-            cf[(2 * b2) * LS] = f2a; cf[(2 * b2 + 1) * LS] = f2b;
-            cur = nxt; index = nindex;
+        HalfRegs r0, r1;
+        load_half(r0, ring);
+        unsigned mt0 = m > 0 ? meta[0] : 0u, mt1;
+        unsigned ma = meta[(ODEB_RING - 1) * 32];
+        const unsigned *mp = meta;
+        for (int i = 0; i < m_max; i += ODEB_RING, mp += ODEB_RING * 32) {
+            ODEB_ROW(r0, r1, mt0, mt1, 0)
+            ODEB_ROW(r1, r0, mt1, mt0, 1)
+            ODEB_ROW(r0, r1, mt0, mt1, 2)
+            ODEB_ROW(r1, r0, mt1, mt0, 3)
+            ODEB_ROW(r0, r1, mt0, mt1, 4)
+            ODEB_ROW(r1, r0, mt1, mt0, 5)
+            ODEB_ROW(r0, r1, mt0, mt1, 6)
+            ODEB_ROW(r1, r0, mt1, mt0, 7)
         }
         cp_async_wait<0>();
-        ++iteration; ++sweeps; rowsweeps += m;
-        if (sweep_control(P, cfs, bstart, nb, iteration, extra, exit_delta, st1, st2, st3)) break;
+        int d = 0;
+        if (!done) {
+            ++iteration; ++sweeps; rowsweeps += m_own;
+            if (side == 0) d = sweep_control(P, cfs, bstart, nb, iteration, extra, exit_delta, st1, st2, st3) ? 1 : 0;
+        }
+        __syncwarp();
+        d = __shfl_sync(ODEB_FULL, d, lane & ~1);
+        done |= d;
+        if (__all_sync(ODEB_FULL, done)) break;
     }
-    for (int k = 0; k < 2 * nb; k++) cf_out[2 * bstart + k] = cf[(2 * bstart + k) * LS];
+    if (m_own > 0) for (int k = side; k < 2 * nb; k += 2) cf_out[2 * bstart + k] = cf[(2 * bstart + k) * ODEB_WPW];
+    __syncwarp();
 }
 
-template <int LS>
+// one SOR row update straight from HBM (islands beyond the shared-memory budget)
+__device__ __forceinline__ void row_update_global(const Real4 *r, int index, int fi, int b1, int b2, Real4 *cf, Real *lam)
+{
+    const Real4 a0 = r[0], a1 = r[1], a2 = r[2], a3 = r[3], b0 = r[4], b1q = r[5], b2q = r[6], b3 = r[7];
+    const Real old_lambda = lam[index];
+    Real delta = a1.z - old_lambda * a1.w;
+    Real4 f1a = cf[2 * b1], f1b = cf[2 * b1 + 1];
+    delta -= f1a.x * a0.x + f1a.y * a0.y + f1a.z * a0.z + f1a.w * a0.w + f1b.x * a1.x + f1b.y * a1.y;
+    Real4 f2a = cf[2 * b2], f2b = cf[2 * b2 + 1];      // one-body rows: b2 = dummy slot NB, J2 = iMJ2 = 0
+    delta -= f2a.x * b0.x + f2a.y * b0.y + f2a.z * b0.z + f2a.w * b0.w + f2b.x * b1q.x + f2b.y * b1q.y;
+    Real hi_act, lo_act;
+    if (fi != -1) { hi_act = RFABS(b1q.w * lam[fi]); lo_act = -hi_act; }
+    else { hi_act = b1q.w; lo_act = b1q.z; }
+    Real new_lambda = old_lambda + delta;
+    if (new_lambda < lo_act) { delta = lo_act - old_lambda; lam[index] = lo_act; }
+    else if (new_lambda > hi_act) { delta = hi_act - old_lambda; lam[index] = hi_act; }
+    else lam[index] = new_lambda;
+    if (delta != 0) {
+        f1a.x += delta * a2.x; f1a.y += delta * a2.y; f1a.z += delta * a2.z; f1a.w += delta * a2.w;
+        f1b.x += delta * a3.x; f1b.y += delta * a3.y;
+        if (delta > 0) f1b.w += delta * a3.z; else f1b.z += delta * a3.z;
+        cf[2 * b1] = f1a; cf[2 * b1 + 1] = f1b;
+        if (delta > 0) f2b.w += delta * b3.z; else f2b.z += delta * b3.z;
+        f2a.x += delta * b2q.x; f2a.y += delta * b2q.y; f2a.z += delta * b2q.z; f2a.w += delta * b2q.w;
+        f2b.x += delta * b3.x; f2b.y += delta * b3.y;
+        cf[2 * b2] = f2a; cf[2 * b2 + 1] = f2b;
+    }
+}
+
 __global__ void __launch_bounds__(32) k_solve(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D)
 {
     extern __shared__ __align__(32) unsigned char smem[];
     const int lane = threadIdx.x;
-    const int w = blockIdx.x * LS + lane;
-    if (lane >= LS || w >= P.W) return;
+    const int side = lane & 1;
+    const int wraw = blockIdx.x * ODEB_WPW + (lane >> 1);
+    const bool valid = wraw < P.W;
+    const int w = valid ? wraw : P.W - 1;          // lanes past the last world idle through the warp-wide loops
     unsigned seed = D.seed[w];
     unsigned st0 = 0, st1 = 0, st2 = 0, st3 = 0;
     unsigned long long sweeps = 0, rowsweeps = 0;
     const Real4 *rows = D.rows + (size_t)w * P.MR * 8;
     const int *findex = D.findex + (size_t)w * P.MR;
+    const int2 *rbody = D.rbody + (size_t)w * P.MR;
     Real4 *cf_out = D.cforce + (size_t)w * (P.NB + 1) * 2;
     const int4 *iinfo = D.island_info + (size_t)w * P.NB;
-    const int nis = D.nislands[w];
-    for (int is = 0; is < nis; is++) {
-        const int4 info = iinfo[is];
+    const int nis = valid ? D.nislands[w] : 0;
+    const int nis_max = __reduce_max_sync(ODEB_FULL, nis);
+    for (int is = 0; is < nis_max; is++) {
+        int4 info = make_int4(0, 0, 0, 0);
+        if (is < nis) info = iinfo[is];
         const int bstart = info.x, nb = info.y, rstart = info.z, m = info.w;
-        if (m > 0 && m <= P.SR) {
-            solve_island_shared<LS>(P, smem, lane, rows, findex, cf_out, bstart, nb, rstart, m, seed, st1, st2, st3, sweeps, rowsweeps);
-        } else if (m > 0) {
-            // ---------------- global-memory path (islands beyond the shared-memory budget)
+        if (m > P.SR && side == 0) {
+            // ---------------- global-memory path (islands beyond the shared-memory budget), lane A only
             CfGlobal cfg = { cf_out };
-            LamGlobal lamg = { D.lambda + (size_t)w * P.MR + rstart };
+            Real *lamg = D.lambda + (size_t)w * P.MR + rstart;
             int *order = D.order + (size_t)w * P.MR + rstart;
             const Real4 z4 = { 0, 0, 0, 0 };
             for (int k = 0; k < 2 * nb; k++) cfg.set(2 * bstart + k, z4);
             cfg.set(2 * P.NB, z4); cfg.set(2 * P.NB + 1, z4);
             int nvalid = 0;
-            for (int i = 0; i < m; i++) { lamg.set(i, 0); if (findex[rstart + i] != -1) nvalid++; }
+            for (int i = 0; i < m; i++) { lamg[i] = 0; if (findex[rstart + i] != -1) nvalid++; }
             {
                 int head = 0, tail = m - nvalid;
                 for (int i = 0; i < m; i++) { if (findex[rstart + i] == -1) order[head++] = i; else order[tail++] = i; }
@@ -279,20 +326,26 @@ __global__ void __launch_bounds__(32) k_solve(const __grid_constant__ DevParams 
                 }
                 for (int i = 0; i < m; i++) {
                     const int index = order[i];
-                    const Real4 *r4 = rec + (size_t)index * 8;
-                    RowRegs cur;
-                    cur.j0 = r4[0]; cur.j1 = r4[1]; cur.j2 = r4[2]; cur.j3 = r4[3]; cur.m0 = r4[4]; cur.m1 = r4[5]; cur.m2 = r4[6]; cur.m3 = r4[7];
-                    row_update(cur, index, rstart, cfg, lamg);
+                    const int fi = findex[rstart + index];
+                    const int2 rb = rbody[rstart + index];
+                    row_update_global(rec + (size_t)index * 8, index, fi == -1 ? -1 : fi - rstart, rb.x, rb.y, cf_out, lamg);
                 }
                 ++iteration; ++sweeps; rowsweeps += m;
                 if (sweep_control(P, cfg, bstart, nb, iteration, extra, exit_delta, st1, st2, st3)) break;
             }
         }
-        st0++;
+        __syncwarp();
+        seed = __shfl_sync(ODEB_FULL, seed, lane & ~1);     // lane B replays the same dRand stream in the shared-memory path
+        const int m_smem = (m > 0 && m <= P.SR) ? m : 0;
+        if (__any_sync(ODEB_FULL, m_smem > 0))
+            solve_islands_warp(P, smem, lane, rows, findex, rbody, cf_out, bstart, nb, rstart, m_smem, seed, st1, st2, st3, sweeps, rowsweeps);
+        if (is < nis) st0++;
     }
-    D.seed[w] = seed;
-    unsigned *st = D.stats + 4 * (size_t)w;
-    st[0] += st0; st[1] += st1; st[2] += st2; st[3] += st3;
-    D.sweeps[2 * (size_t)w] = sweeps; D.sweeps[2 * (size_t)w + 1] = rowsweeps;
+    if (side == 0 && valid) {
+        D.seed[w] = seed;
+        unsigned *st = D.stats + 4 * (size_t)w;
+        st[0] += st0; st[1] += st1; st[2] += st2; st[3] += st3;
+        D.sweeps[2 * (size_t)w] = sweeps; D.sweeps[2 * (size_t)w + 1] = rowsweeps;
+    }
 }
 #endif

@@ -18,12 +18,10 @@ for prec in ("single", "double"):
     run("chain", scenes.chain(2), 0.05, 120, prec)
     run("free", scenes.free_boxes(2, 16, grid=4), 0.01, 80, prec)
 # quick timing
-import os
-for lanes in (4, 8, 16, 32):
-    os.environ["ODEB_SOLVER_LANES"] = str(lanes)
+for prec in ("single", "double"):
     sc = scenes.box_stack(nworlds=4096, demo_world_options=False)
-    gpu = B.Batch(gpu_lib("single"), sc)
-    gpu.step(0.02, 30)
+    gpu = B.Batch(gpu_lib(prec), sc)
+    gpu.step(0.02, 160)
     t = time.time(); gpu.step(0.02, 50); dt = time.time() - t
-    print("lanes", lanes, "4096 stacks: ms/step %.3f" % (dt / 50 * 1e3), "body-steps/s %.3e" % (4096 * 16 * 50 / dt))
+    print(prec, "4096 stacks: ms/step %.3f" % (dt / 50 * 1e3), "body-steps/s %.3e" % (4096 * 16 * 50 / dt))
     gpu.close()
