@@ -131,6 +131,72 @@ static void host_limot(DLimot &l, Real erp, Real cfm, const OdebJointDesc &d, in
     if (d.stop_cfm[a] >= 0) l.stop_cfm = (Real)d.stop_cfm[a];
 }
 
+
+// hinge.cpp:376-393 computeInitialRelativeRotation
+static void host_hinge_initial_rotation(const std::vector<HostBody> &hb, DJointT &j)
+{
+    if (j.b0 < 0) return;
+    if (j.b1 >= 0) qmul1(j.qrel, hb[j.b0].q, hb[j.b1].q);
+    else { const Real *q = hb[j.b0].q; j.qrel[0] = q[0]; j.qrel[1] = -q[1]; j.qrel[2] = -q[2]; j.qrel[3] = -q[3]; }
+}
+// universal.cpp:372-401 computeInitialRelativeRotations
+static void host_universal_initial_rotations(const std::vector<HostBody> &hb, DJointT &j)
+{
+    if (j.b0 < 0) return;
+    Real ax1[3], ax2[3], R[12] = { 0 }, qcross[4];
+    mul0_331(ax1, hb[j.b0].R, j.axis1);
+    if (j.b1 >= 0) mul0_331(ax2, hb[j.b1].R, j.axis2); else { ax2[0] = j.axis2[0]; ax2[1] = j.axis2[1]; ax2[2] = j.axis2[2]; }
+    odeb_r_from_2axes(R, ax1[0], ax1[1], ax1[2], ax2[0], ax2[1], ax2[2]);
+    q_from_r(qcross, R);
+    qmul1(j.qrel1, hb[j.b0].q, qcross);
+    odeb_r_from_2axes(R, ax2[0], ax2[1], ax2[2], ax1[0], ax1[1], ax1[2]);
+    q_from_r(qcross, R);
+    if (j.b1 >= 0) qmul1(j.qrel2, hb[j.b1].q, qcross); else for (int k = 0; k < 4; k++) j.qrel2[k] = qcross[k];
+}
+// make_sure_plane_normal_has_unit_length plane.cpp:48-63
+static void host_normalize_plane(Real *p)
+{
+    Real l = p[0] * p[0] + p[1] * p[1] + p[2] * p[2];
+    if (l > 0) { l = rrecipsqrt(l); p[0] *= l; p[1] *= l; p[2] *= l; p[3] *= l; }
+    else { p[0] = 1; p[1] = 0; p[2] = 0; p[3] = 0; }
+}
+
+// world-level parameters -> DevParams (dWorldSet*; defaults ode/src/objects.cpp:37-121). Also used by the classic layer
+// before every launch, because the classic setters may change them between steps.
+static void apply_world_params(DevParams &P, const OdebWorldParams *wp, bool classic)
+{
+    DSurface &S = P.surf;
+    S.mode = wp->surf_mode;
+    S.mu = (Real)wp->mu < 0 ? 0 : (Real)wp->mu;
+    S.mu2 = (Real)wp->mu2 < 0 ? 0 : (Real)wp->mu2;
+    S.bounce = (Real)wp->bounce; S.bounce_vel = (Real)wp->bounce_vel; S.soft_erp = (Real)wp->soft_erp; S.soft_cfm = (Real)wp->soft_cfm;
+    S.motion1 = (Real)wp->motion1; S.motion2 = (Real)wp->motion2; S.motionN = (Real)wp->motionN; S.slip1 = (Real)wp->slip1; S.slip2 = (Real)wp->slip2;
+    {   // getInfo1 row count of a contact joint (contact.cpp:48-122); uniform under one policy, per contact in classic mode
+        int m = 1;
+        if (S.mode & ODEB_CONTACT_MU2) { if (S.mu > 0) m++; if (S.mu2 > 0) m++; }
+        else if (S.mu > 0) m += 2;
+        S.the_m = m; P.m_contact = classic ? 3 : m;
+    }
+    for (int k = 0; k < 3; k++) P.gravity[k] = (Real)wp->gravity[k];
+    P.erp = (Real)wp->erp;
+#if defined(ODEB_DOUBLE)
+    P.cfm = wp->cfm >= 0 ? (Real)wp->cfm : R_(1e-10);
+#else
+    P.cfm = wp->cfm >= 0 ? (Real)wp->cfm : R_(1e-5);
+#endif
+    P.sor_w = (Real)wp->sor_w;
+    P.num_iter = wp->num_iterations > 1 ? wp->num_iterations : 1;
+    P.premature_delta = (Real)wp->premature_exit_delta; P.extra_delta = (Real)wp->extra_iter_delta;
+    { Real f = (Real)wp->max_extra_factor; Real ex = P.num_iter * f; P.max_extra = ex < (Real)UINT32_MAX ? (unsigned)ex : UINT32_MAX; }  // objects.h:177-184
+    P.dyn_enabled = (P.max_extra != 0 || P.premature_delta != 0) ? 1 : 0;
+    P.max_vel = (Real)wp->contact_max_vel; P.min_depth = (Real)wp->contact_surface_layer;
+    { Real t = (Real)wp->adis_linear_thr; P.adis_lin = t * t; t = (Real)wp->adis_angular_thr; P.adis_ang = t * t; }
+    P.adis_time = (Real)wp->adis_time; P.adis_steps = wp->adis_steps; P.adis_samples = wp->adis_samples;
+    P.damp_lin_scale = (Real)wp->linear_damping; P.damp_ang_scale = (Real)wp->angular_damping;
+    { Real t = (Real)wp->linear_damping_thr; P.damp_lin_thr = t * t; t = (Real)wp->angular_damping_thr; P.damp_ang_thr = t * t; }
+    P.max_ang_speed = (Real)wp->max_angular_speed;
+}
+
 static inline unsigned nblk(size_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
 
 extern "C" {
@@ -151,73 +217,59 @@ void odeb_destroy(OdebBatch *B)
     delete B;
 }
 
-OdebBatch *odeb_create(const OdebWorldParams *wp,
-                       int nbody, const OdebBodyDesc *bodies, const double *body_pos, const double *body_quat,
-                       int ngeom, const OdebGeomDesc *geoms,
-                       int njoint, const OdebJointDesc *joints,
-                       int nworlds, int device)
+
+// Host-side template of one world: what odeb_create derives from the scene description and what the classic
+// per-object layer (odeb_classic.inl) maintains incrementally.
+struct HostTemplate {
+    std::vector<Real> bmass, binvmass, bI, binvI;            // [NB], [NB*12]
+    std::vector<HostBody> hb;                                // pose of every body
+    std::vector<int> bflags0;                                // BF_* per body
+    std::vector<int> gtype, gbody; std::vector<Real> gparam; std::vector<unsigned> gcat, gcol;
+    std::vector<Real4> gspose;                               // [NG*4]: position + 3 rotation rows of geoms without a body
+    std::vector<DJointT> jt;
+    std::vector<int> sofs, sj, so;                           // per-body joint adjacency in attach order (CSR)
+    std::vector<unsigned char> conn;                         // [NB*NB] joined by a non-contact joint
+};
+
+struct BatchCaps { int classic, max_pairs, max_contacts; };  // classic: contacts / surfaces / adjacency come from the host every step
+
+static OdebBatch *batch_build(const OdebWorldParams *wp, const HostTemplate &T, int nworlds, int device, const BatchCaps *caps)
 {
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) { set_err("no CUDA device: %s (this library has no CPU path)", cudaGetErrorString(e)); return 0; }
     if (device < 0 || device >= ndev) { set_err("bad device index %d (have %d)", device, ndev); return 0; }
     if (cudaSetDevice(device) != cudaSuccess) { set_err("cudaSetDevice(%d) failed", device); return 0; }
-    if (nworlds <= 0 || nbody <= 0 || ngeom < 0 || njoint < 0) { set_err("bad sizes"); return 0; }
-    if (wp->surf_mode & (ODEB_CONTACT_FDIR1 | 0x400)) { set_err("contact modes FDir1 / Rolling are outside the supported policy"); return 0; }
+    const int nbody = (int)T.bmass.size(), ngeom = (int)T.gtype.size(), njoint = (int)T.jt.size();
+    const bool classic = caps && caps->classic;
+    if (nworlds <= 0 || nbody <= 0) { set_err("bad sizes"); return 0; }
+    if (!classic && (wp->surf_mode & (ODEB_CONTACT_FDIR1 | 0x400))) { set_err("contact modes FDir1 / Rolling are outside the supported policy"); return 0; }
     if (wp->max_contacts < 1 || wp->max_contacts > 8) { set_err("max_contacts must be in 1..8"); return 0; }
 
     OdebBatch *B = new OdebBatch();
     B->device = device; B->bytes = 0; B->launches = 0; B->timing = false; B->solver_ms = 0; B->solver_launches = 0;
-    B->graph = 0; B->graph_h = -1; B->use_graph = getenv("ODEB_NO_GRAPH") == 0; B->h_stage = 0; B->d_stage = 0; B->stream = 0; B->flush_buf = 0; B->flush_bytes = 0;
+    B->graph = 0; B->graph_h = -1; B->use_graph = getenv("ODEB_NO_GRAPH") == 0 && !classic; B->h_stage = 0; B->d_stage = 0; B->stream = 0; B->flush_buf = 0; B->flush_bytes = 0;
     memset(&B->D, 0, sizeof(B->D));
     DevParams &P = B->P;
     memset(&P, 0, sizeof(P));
-    P.W = nworlds; P.NB = nbody; P.NG = ngeom; P.NJ = njoint;
+    P.W = nworlds; P.NB = nbody; P.NG = ngeom; P.NJ = njoint; P.classic = classic ? 1 : 0;
     P.maxc = wp->max_contacts; P.space_type = wp->space_type; P.skip_connected = wp->skip_connected;
     {
         long long all = (long long)ngeom * (ngeom - 1) / 2;
         long long mp = all < 16LL * ngeom ? all : 16LL * ngeom;
         if (const char *s = getenv("ODEB_MAX_PAIRS")) mp = atoll(s);
+        if (caps && caps->max_pairs > 0) mp = caps->max_pairs;
         P.MP = (int)(mp < 1 ? 1 : mp);
         long long mc = (long long)P.MP * P.maxc;
         long long cap = 2LL * ngeom * P.maxc;
         if (mc > cap) mc = cap;
         if (const char *s = getenv("ODEB_MAX_CONTACTS")) mc = atoll(s);
+        if (caps && caps->max_contacts > 0) mc = caps->max_contacts;
         P.MC = (int)(mc < 1 ? 1 : mc);
     }
-    // contact policy: getInfo1 row count (contact.cpp:48-122) is uniform
-    DSurface &S = P.surf;
-    S.mode = wp->surf_mode;
-    S.mu = (Real)wp->mu < 0 ? 0 : (Real)wp->mu;
-    S.mu2 = (Real)wp->mu2 < 0 ? 0 : (Real)wp->mu2;
-    S.bounce = (Real)wp->bounce; S.bounce_vel = (Real)wp->bounce_vel; S.soft_erp = (Real)wp->soft_erp; S.soft_cfm = (Real)wp->soft_cfm;
-    S.motion1 = (Real)wp->motion1; S.motion2 = (Real)wp->motion2; S.motionN = (Real)wp->motionN; S.slip1 = (Real)wp->slip1; S.slip2 = (Real)wp->slip2;
-    {
-        int m = 1;
-        if (S.mode & ODEB_CONTACT_MU2) { if (S.mu > 0) m++; if (S.mu2 > 0) m++; }
-        else if (S.mu > 0) m += 2;
-        S.the_m = m; P.m_contact = m;
-    }
+    apply_world_params(P, wp, classic);
     P.NJT = P.NJ + P.MC;
     P.MR = P.MC * P.m_contact + P.NJ * 6;
-    for (int k = 0; k < 3; k++) P.gravity[k] = (Real)wp->gravity[k];
-    P.erp = (Real)wp->erp;
-#if defined(ODEB_DOUBLE)
-    P.cfm = wp->cfm >= 0 ? (Real)wp->cfm : R_(1e-10);
-#else
-    P.cfm = wp->cfm >= 0 ? (Real)wp->cfm : R_(1e-5);
-#endif
-    P.sor_w = (Real)wp->sor_w;
-    P.num_iter = wp->num_iterations > 1 ? wp->num_iterations : 1;
-    P.premature_delta = (Real)wp->premature_exit_delta; P.extra_delta = (Real)wp->extra_iter_delta;
-    { Real f = (Real)wp->max_extra_factor; Real ex = P.num_iter * f; P.max_extra = ex < (Real)UINT32_MAX ? (unsigned)ex : UINT32_MAX; }  // objects.h:177-184
-    P.dyn_enabled = (P.max_extra != 0 || P.premature_delta != 0) ? 1 : 0;
-    P.max_vel = (Real)wp->contact_max_vel; P.min_depth = (Real)wp->contact_surface_layer;
-    { Real t = (Real)wp->adis_linear_thr; P.adis_lin = t * t; t = (Real)wp->adis_angular_thr; P.adis_ang = t * t; }
-    P.adis_time = (Real)wp->adis_time; P.adis_steps = wp->adis_steps; P.adis_samples = wp->adis_samples;
-    P.damp_lin_scale = (Real)wp->linear_damping; P.damp_ang_scale = (Real)wp->angular_damping;
-    { Real t = (Real)wp->linear_damping_thr; P.damp_lin_thr = t * t; t = (Real)wp->angular_damping_thr; P.damp_ang_thr = t * t; }
-    P.max_ang_speed = (Real)wp->max_angular_speed;
     {   // shared-memory budget of k_solve (16 worlds per warp): ring + per-body accumulators + lambda/metadata for SR rows
         int sr = P.MR < 512 ? P.MR : 512;
         if (const char *s = getenv("ODEB_SOLVER_ROWS")) sr = atoi(s);
@@ -236,100 +288,11 @@ OdebBatch *odeb_create(const OdebWorldParams *wp,
         if (P.SR == 0) B->solve_smem = 0;
     }
 
-    // ---- template on the host
-    std::vector<Real> bmass(nbody), binvmass(nbody), bI(12 * nbody, 0), binvI(12 * nbody, 0);
-    std::vector<HostBody> hb(nbody);
-    std::vector<int> bflags0(nbody);
-    for (int i = 0; i < nbody; i++) {
-        bmass[i] = (Real)bodies[i].mass;
-        if (!(bmass[i] > 0)) { set_err("body %d: mass must be > 0", i); delete B; return 0; }
-        binvmass[i] = rrecip(bmass[i]);
-        const double *I = bodies[i].inertia;
-        Real *Ib = &bI[12 * i];
-        Ib[0] = (Real)I[0]; Ib[5] = (Real)I[4]; Ib[10] = (Real)I[8];          // dMassSetParameters mass.cpp:74-93
-        Ib[1] = (Real)I[1]; Ib[2] = (Real)I[2]; Ib[6] = (Real)I[5];
-        Ib[4] = (Real)I[1]; Ib[8] = (Real)I[2]; Ib[9] = (Real)I[5];
-        if (!host_invert_pd3(Ib, &binvI[12 * i])) { Real *v = &binvI[12 * i]; memset(v, 0, 12 * sizeof(Real)); v[0] = v[5] = v[10] = 1; }
-        HostBody &h = hb[i];
-        for (int k = 0; k < 3; k++) h.pos[k] = (Real)body_pos[3 * i + k];
-        for (int k = 0; k < 4; k++) h.q[k] = (Real)body_quat[4 * i + k];
-        normalize4(h.q); r_from_q(h.R, h.q);
-        int fl = BF_GYRO;
-        if (wp->auto_disable) fl |= BF_AUTO_DISABLE;
-        if (P.damp_lin_scale) fl |= BF_LIN_DAMP;
-        if (P.damp_ang_scale) fl |= BF_ANG_DAMP;
-        if (P.max_ang_speed < R_INF) fl |= BF_MAX_ANG_SPEED;
-        int sf = bodies[i].flags;
-        if (sf & ODEB_BODY_NO_GRAVITY) fl |= BF_NO_GRAVITY;
-        if (sf & ODEB_BODY_NO_GYRO) fl &= ~BF_GYRO;
-        if (sf & ODEB_BODY_FINITE_ROTATION) fl |= BF_FINITE_ROT;
-        if (sf & ODEB_BODY_DISABLED) fl |= BF_DISABLED;
-        bflags0[i] = fl;
-    }
-    std::vector<int> gtype(ngeom), gbody(ngeom); std::vector<Real> gparam(4 * ngeom); std::vector<unsigned> gcat(ngeom), gcol(ngeom);
-    for (int i = 0; i < ngeom; i++) {
-        gtype[i] = geoms[i].type; gbody[i] = geoms[i].body; gcat[i] = geoms[i].category_bits; gcol[i] = geoms[i].collide_bits;
-        if (gbody[i] >= nbody) { set_err("geom %d: bad body index", i); delete B; return 0; }
-        if (gtype[i] != ODEB_SPHERE && gtype[i] != ODEB_BOX && gtype[i] != ODEB_CAPSULE && gtype[i] != ODEB_PLANE) { set_err("geom %d: unsupported class %d", i, gtype[i]); delete B; return 0; }
-        Real *p = &gparam[4 * i];
-        for (int k = 0; k < 4; k++) p[k] = (Real)geoms[i].p[k];
-        if (gtype[i] == ODEB_PLANE) {   // make_sure_plane_normal_has_unit_length plane.cpp:48-63
-            Real l = p[0] * p[0] + p[1] * p[1] + p[2] * p[2];
-            if (l > 0) { l = rrecipsqrt(l); p[0] *= l; p[1] *= l; p[2] *= l; p[3] *= l; }
-            else { p[0] = 1; p[1] = 0; p[2] = 0; p[3] = 0; }
-        }
-    }
-    std::vector<DJointT> jt(njoint);
-    std::vector<std::vector<std::pair<int, int> > > adj(nbody);
-    std::vector<unsigned char> conn((size_t)nbody * nbody, 0);
-    for (int i = 0; i < njoint; i++) {
-        const OdebJointDesc &d = joints[i];
-        DJointT &j = jt[i];
-        memset(&j, 0, sizeof(j));
-        if (d.type != ODEB_JOINT_BALL && d.type != ODEB_JOINT_HINGE && d.type != ODEB_JOINT_UNIVERSAL) { set_err("joint %d: unsupported type %d", i, d.type); delete B; return 0; }
-        j.type = d.type; j.erp = P.erp; j.cfm = P.cfm;
-        int b1 = d.body1, b2 = d.body2;
-        if (b1 >= nbody || b2 >= nbody || (b1 < 0 && b2 < 0) || b1 == b2) { set_err("joint %d: bad bodies", i); delete B; return 0; }
-        if (b1 < 0) { b1 = b2; b2 = -1; j.reverse = 1; }         // dJointAttach ode.cpp:1404-1411
-        j.b0 = b1; j.b1 = b2;
-        adj[b1].push_back(std::make_pair(i, b2));
-        if (b2 >= 0) { adj[b2].push_back(std::make_pair(i, b1)); conn[(size_t)b1 * nbody + b2] = conn[(size_t)b2 * nbody + b1] = 1; }
-        host_set_anchors(hb, j, (Real)d.anchor[0], (Real)d.anchor[1], (Real)d.anchor[2]);
-        host_limot(j.limot1, P.erp, P.cfm, d, 0);
-        host_limot(j.limot2, P.erp, P.cfm, d, 1);
-        if (j.type == ODEB_JOINT_HINGE) {
-            j.axis1[0] = 1; j.axis2[0] = 1;
-            host_set_axes(hb, j, (Real)d.axis1[0], (Real)d.axis1[1], (Real)d.axis1[2], j.axis1, j.axis2);
-            if (j.b1 >= 0) qmul1(j.qrel, hb[j.b0].q, hb[j.b1].q);      // hinge.cpp:376-393
-            else { const Real *q = hb[j.b0].q; j.qrel[0] = q[0]; j.qrel[1] = -q[1]; j.qrel[2] = -q[2]; j.qrel[3] = -q[3]; }
-        } else if (j.type == ODEB_JOINT_UNIVERSAL) {
-            j.axis1[0] = 1; j.axis2[1] = 1;
-            if (j.reverse) host_set_axes(hb, j, (Real)d.axis1[0], (Real)d.axis1[1], (Real)d.axis1[2], 0, j.axis2);
-            else host_set_axes(hb, j, (Real)d.axis1[0], (Real)d.axis1[1], (Real)d.axis1[2], j.axis1, 0);
-            if (j.reverse) host_set_axes(hb, j, (Real)d.axis2[0], (Real)d.axis2[1], (Real)d.axis2[2], j.axis1, 0);
-            else host_set_axes(hb, j, (Real)d.axis2[0], (Real)d.axis2[1], (Real)d.axis2[2], 0, j.axis2);
-            Real ax1[3], ax2[3], R[12] = { 0 }, qcross[4];                 // universal.cpp:372-401
-            mul0_331(ax1, hb[j.b0].R, j.axis1);
-            if (j.b1 >= 0) mul0_331(ax2, hb[j.b1].R, j.axis2); else { ax2[0] = j.axis2[0]; ax2[1] = j.axis2[1]; ax2[2] = j.axis2[2]; }
-            odeb_r_from_2axes(R, ax1[0], ax1[1], ax1[2], ax2[0], ax2[1], ax2[2]);
-            q_from_r(qcross, R);
-            qmul1(j.qrel1, hb[j.b0].q, qcross);
-            odeb_r_from_2axes(R, ax2[0], ax2[1], ax2[2], ax1[0], ax1[1], ax1[2]);
-            q_from_r(qcross, R);
-            if (j.b1 >= 0) qmul1(j.qrel2, hb[j.b1].q, qcross); else for (int k = 0; k < 4; k++) j.qrel2[k] = qcross[k];
-        }
-    }
-    std::vector<int> sofs(nbody + 1, 0), sj, so;
-    for (int b = 0; b < nbody; b++) {
-        sofs[b] = (int)sj.size();
-        for (size_t k = 0; k < adj[b].size(); k++) { sj.push_back(adj[b][k].first); so.push_back(adj[b][k].second); }
-    }
-    sofs[nbody] = (int)sj.size();
-
     // ---- device buffers
     DevPtrs &D = B->D;
     const size_t W = nworlds, WB = W * nbody, WG = W * ngeom, WJ = W * njoint;
     const int NS = P.adis_samples > 0 ? P.adis_samples : 1;
+    const size_t nadj = classic ? 2 * (size_t)(njoint + P.MC) : T.sj.size();
     bool ok = true;
     ok = ok && dev_alloc(B, &D.pos, WB) && dev_alloc(B, &D.quat, WB) && dev_alloc(B, &D.lvel, WB) && dev_alloc(B, &D.avel, WB)
             && dev_alloc(B, &D.facc, WB) && dev_alloc(B, &D.tacc, WB) && dev_alloc(B, &D.R, 3 * WB)
@@ -337,12 +300,13 @@ OdebBatch *odeb_create(const OdebWorldParams *wp,
             && dev_alloc(B, &D.avg_buf, WB * 6 * NS) && dev_alloc(B, &D.avg_counter, WB) && dev_alloc(B, &D.avg_ready, WB);
     ok = ok && dev_alloc(B, &D.bmass, nbody) && dev_alloc(B, &D.binvmass, nbody) && dev_alloc(B, &D.bI, 12 * (size_t)nbody) && dev_alloc(B, &D.binvI, 12 * (size_t)nbody)
             && dev_alloc(B, &D.gtype, ngeom) && dev_alloc(B, &D.gbody, ngeom) && dev_alloc(B, &D.gparam, 4 * (size_t)ngeom)
-            && dev_alloc(B, &D.gcat, ngeom) && dev_alloc(B, &D.gcol, ngeom) && dev_alloc(B, &D.joints, njoint)
-            && dev_alloc(B, &D.sadj_ofs, nbody + 1) && dev_alloc(B, &D.sadj_joint, sj.size()) && dev_alloc(B, &D.sadj_other, so.size())
+            && dev_alloc(B, &D.gcat, ngeom) && dev_alloc(B, &D.gcol, ngeom) && dev_alloc(B, &D.gspose, 4 * (size_t)ngeom) && dev_alloc(B, &D.joints, njoint)
+            && dev_alloc(B, &D.sadj_ofs, nbody + 1) && dev_alloc(B, &D.sadj_joint, nadj) && dev_alloc(B, &D.sadj_other, nadj)
             && dev_alloc(B, &D.conn, (size_t)nbody * nbody);
     ok = ok && dev_alloc(B, &D.aabb, WG * 6) && dev_alloc(B, &D.pair_cnt, WG) && dev_alloc(B, &D.pair_ofs, WG) && dev_alloc(B, &D.npairs, W)
-            && dev_alloc(B, &D.pairs, W * P.MP) && dev_alloc(B, &D.pc_count, W * P.MP) && dev_alloc(B, &D.cgeom, W * P.MP * P.maxc * 2)
+            && dev_alloc(B, &D.pairs, W * P.MP) && dev_alloc(B, &D.pc_count, W * P.MP) && dev_alloc(B, &D.cgeom, W * (classic ? (size_t)P.MC : (size_t)P.MP * P.maxc) * 2)
             && dev_alloc(B, &D.ncontacts, W) && dev_alloc(B, &D.cinfo, W * P.MC) && dev_alloc(B, &D.jm, WJ) && dev_alloc(B, &D.jlimit, WJ);
+    if (classic) ok = ok && dev_alloc(B, &D.csurf, (size_t)P.MC);
     ok = ok && dev_alloc(B, &D.c_ofs, W * (nbody + 1)) && dev_alloc(B, &D.c_cur, WB) && dev_alloc(B, &D.c_adj_c, W * 2 * P.MC) && dev_alloc(B, &D.c_adj_o, W * 2 * P.MC)
             && dev_alloc(B, &D.btag, WB) && dev_alloc(B, &D.jtag, W * P.NJT) && dev_alloc(B, &D.stack, WB)
             && dev_alloc(B, &D.body_order, WB) && dev_alloc(B, &D.body_pos, WB) && dev_alloc(B, &D.body_island, WB)
@@ -360,26 +324,123 @@ OdebBatch *odeb_create(const OdebWorldParams *wp,
     }
     if (!ok) { odeb_destroy(B); return 0; }
 
-    ok = upload(D.bmass, bmass) && upload(D.binvmass, binvmass) && upload(D.bI, bI) && upload(D.binvI, binvI)
-      && upload(D.gtype, gtype) && upload(D.gbody, gbody) && upload(D.gparam, gparam) && upload(D.gcat, gcat) && upload(D.gcol, gcol)
-      && upload(D.joints, jt) && upload(D.sadj_ofs, sofs) && upload(D.sadj_joint, sj) && upload(D.sadj_other, so) && upload(D.conn, conn);
+    ok = upload(D.bmass, T.bmass) && upload(D.binvmass, T.binvmass) && upload(D.bI, T.bI) && upload(D.binvI, T.binvI)
+      && upload(D.gtype, T.gtype) && upload(D.gbody, T.gbody) && upload(D.gparam, T.gparam) && upload(D.gcat, T.gcat) && upload(D.gcol, T.gcol)
+      && upload(D.gspose, T.gspose)
+      && upload(D.joints, T.jt) && upload(D.sadj_ofs, T.sofs) && upload(D.sadj_joint, T.sj) && upload(D.sadj_other, T.so) && upload(D.conn, T.conn);
     // initial per-world state = template pose
     {
         std::vector<Real4> pos(WB), quat(WB), R(3 * WB);
         std::vector<int> fl(WB), st(WB); std::vector<Real> tl(WB);
         for (size_t w = 0; w < W; w++) for (int i = 0; i < nbody; i++) {
             size_t k = w * nbody + i;
-            const HostBody &h = hb[i];
+            const HostBody &h = T.hb[i];
             Real4 p = { h.pos[0], h.pos[1], h.pos[2], 0 }, q = { h.q[0], h.q[1], h.q[2], h.q[3] };
             pos[k] = p; quat[k] = q;
             Real4 r0 = { h.R[0], h.R[1], h.R[2], 0 }, r1 = { h.R[4], h.R[5], h.R[6], 0 }, r2 = { h.R[8], h.R[9], h.R[10], 0 };
             R[3 * k] = r0; R[3 * k + 1] = r1; R[3 * k + 2] = r2;
-            fl[k] = bflags0[i]; st[k] = P.adis_steps; tl[k] = P.adis_time;
+            fl[k] = T.bflags0[i]; st[k] = P.adis_steps; tl[k] = P.adis_time;
         }
         ok = ok && upload(D.pos, pos) && upload(D.quat, quat) && upload(D.R, R) && upload(D.bflags, fl) && upload(D.adis_steps, st) && upload(D.adis_time, tl);
     }
     if (!ok || cudaDeviceSynchronize() != cudaSuccess) { set_err("template upload failed: %s", cudaGetErrorString(cudaGetLastError())); odeb_destroy(B); return 0; }
     return B;
+}
+
+OdebBatch *odeb_create(const OdebWorldParams *wp,
+                       int nbody, const OdebBodyDesc *bodies, const double *body_pos, const double *body_quat,
+                       int ngeom, const OdebGeomDesc *geoms,
+                       int njoint, const OdebJointDesc *joints,
+                       int nworlds, int device)
+{
+    if (nworlds <= 0 || nbody <= 0 || ngeom < 0 || njoint < 0) { set_err("bad sizes"); return 0; }
+    HostTemplate T;
+    Real erp = (Real)wp->erp;
+#if defined(ODEB_DOUBLE)
+    Real cfm = wp->cfm >= 0 ? (Real)wp->cfm : R_(1e-10);
+#else
+    Real cfm = wp->cfm >= 0 ? (Real)wp->cfm : R_(1e-5);
+#endif
+    // ---- template on the host
+    T.bmass.resize(nbody); T.binvmass.resize(nbody); T.bI.assign(12 * (size_t)nbody, 0); T.binvI.assign(12 * (size_t)nbody, 0);
+    T.hb.resize(nbody); T.bflags0.resize(nbody);
+    std::vector<HostBody> &hb = T.hb;
+    for (int i = 0; i < nbody; i++) {
+        T.bmass[i] = (Real)bodies[i].mass;
+        if (!(T.bmass[i] > 0)) { set_err("body %d: mass must be > 0", i); return 0; }
+        T.binvmass[i] = rrecip(T.bmass[i]);
+        const double *I = bodies[i].inertia;
+        Real *Ib = &T.bI[12 * i];
+        Ib[0] = (Real)I[0]; Ib[5] = (Real)I[4]; Ib[10] = (Real)I[8];          // dMassSetParameters mass.cpp:74-93
+        Ib[1] = (Real)I[1]; Ib[2] = (Real)I[2]; Ib[6] = (Real)I[5];
+        Ib[4] = (Real)I[1]; Ib[8] = (Real)I[2]; Ib[9] = (Real)I[5];
+        if (!host_invert_pd3(Ib, &T.binvI[12 * i])) { Real *v = &T.binvI[12 * i]; memset(v, 0, 12 * sizeof(Real)); v[0] = v[5] = v[10] = 1; }
+        HostBody &h = hb[i];
+        for (int k = 0; k < 3; k++) h.pos[k] = (Real)body_pos[3 * i + k];
+        for (int k = 0; k < 4; k++) h.q[k] = (Real)body_quat[4 * i + k];
+        normalize4(h.q); r_from_q(h.R, h.q);
+        int fl = BF_GYRO;
+        if (wp->auto_disable) fl |= BF_AUTO_DISABLE;
+        if ((Real)wp->linear_damping) fl |= BF_LIN_DAMP;
+        if ((Real)wp->angular_damping) fl |= BF_ANG_DAMP;
+        if ((Real)wp->max_angular_speed < R_INF) fl |= BF_MAX_ANG_SPEED;
+        int sf = bodies[i].flags;
+        if (sf & ODEB_BODY_NO_GRAVITY) fl |= BF_NO_GRAVITY;
+        if (sf & ODEB_BODY_NO_GYRO) fl &= ~BF_GYRO;
+        if (sf & ODEB_BODY_FINITE_ROTATION) fl |= BF_FINITE_ROT;
+        if (sf & ODEB_BODY_DISABLED) fl |= BF_DISABLED;
+        T.bflags0[i] = fl;
+    }
+    T.gtype.resize(ngeom); T.gbody.resize(ngeom); T.gparam.resize(4 * (size_t)ngeom); T.gcat.resize(ngeom); T.gcol.resize(ngeom);
+    T.gspose.resize(4 * (size_t)ngeom);
+    for (int i = 0; i < ngeom; i++) {
+        T.gtype[i] = geoms[i].type; T.gbody[i] = geoms[i].body; T.gcat[i] = geoms[i].category_bits; T.gcol[i] = geoms[i].collide_bits;
+        if (T.gbody[i] >= nbody) { set_err("geom %d: bad body index", i); return 0; }
+        if (T.gtype[i] != ODEB_SPHERE && T.gtype[i] != ODEB_BOX && T.gtype[i] != ODEB_CAPSULE && T.gtype[i] != ODEB_PLANE) { set_err("geom %d: unsupported class %d", i, T.gtype[i]); return 0; }
+        Real *p = &T.gparam[4 * i];
+        for (int k = 0; k < 4; k++) p[k] = (Real)geoms[i].p[k];
+        if (T.gtype[i] == ODEB_PLANE) host_normalize_plane(p);
+        Real4 z = { 0, 0, 0, 0 }, r0 = { 1, 0, 0, 0 }, r1 = { 0, 1, 0, 0 }, r2 = { 0, 0, 1, 0 };
+        T.gspose[4 * i] = z; T.gspose[4 * i + 1] = r0; T.gspose[4 * i + 2] = r1; T.gspose[4 * i + 3] = r2;
+    }
+    T.jt.resize(njoint);
+    std::vector<std::vector<std::pair<int, int> > > adj(nbody);
+    T.conn.assign((size_t)nbody * nbody, 0);
+    for (int i = 0; i < njoint; i++) {
+        const OdebJointDesc &d = joints[i];
+        DJointT &j = T.jt[i];
+        memset(&j, 0, sizeof(j));
+        if (d.type != ODEB_JOINT_BALL && d.type != ODEB_JOINT_HINGE && d.type != ODEB_JOINT_UNIVERSAL) { set_err("joint %d: unsupported type %d", i, d.type); return 0; }
+        j.type = d.type; j.erp = erp; j.cfm = cfm;
+        int b1 = d.body1, b2 = d.body2;
+        if (b1 >= nbody || b2 >= nbody || (b1 < 0 && b2 < 0) || b1 == b2) { set_err("joint %d: bad bodies", i); return 0; }
+        if (b1 < 0) { b1 = b2; b2 = -1; j.reverse = 1; }         // dJointAttach ode.cpp:1404-1411
+        j.b0 = b1; j.b1 = b2;
+        adj[b1].push_back(std::make_pair(i, b2));
+        if (b2 >= 0) { adj[b2].push_back(std::make_pair(i, b1)); T.conn[(size_t)b1 * nbody + b2] = T.conn[(size_t)b2 * nbody + b1] = 1; }
+        host_set_anchors(hb, j, (Real)d.anchor[0], (Real)d.anchor[1], (Real)d.anchor[2]);
+        host_limot(j.limot1, erp, cfm, d, 0);
+        host_limot(j.limot2, erp, cfm, d, 1);
+        if (j.type == ODEB_JOINT_HINGE) {
+            j.axis1[0] = 1; j.axis2[0] = 1;
+            host_set_axes(hb, j, (Real)d.axis1[0], (Real)d.axis1[1], (Real)d.axis1[2], j.axis1, j.axis2);
+            host_hinge_initial_rotation(hb, j);
+        } else if (j.type == ODEB_JOINT_UNIVERSAL) {
+            j.axis1[0] = 1; j.axis2[1] = 1;
+            if (j.reverse) host_set_axes(hb, j, (Real)d.axis1[0], (Real)d.axis1[1], (Real)d.axis1[2], 0, j.axis2);
+            else host_set_axes(hb, j, (Real)d.axis1[0], (Real)d.axis1[1], (Real)d.axis1[2], j.axis1, 0);
+            if (j.reverse) host_set_axes(hb, j, (Real)d.axis2[0], (Real)d.axis2[1], (Real)d.axis2[2], j.axis1, 0);
+            else host_set_axes(hb, j, (Real)d.axis2[0], (Real)d.axis2[1], (Real)d.axis2[2], 0, j.axis2);
+            host_universal_initial_rotations(hb, j);
+        }
+    }
+    T.sofs.assign(nbody + 1, 0);
+    for (int b = 0; b < nbody; b++) {
+        T.sofs[b] = (int)T.sj.size();
+        for (size_t k = 0; k < adj[b].size(); k++) { T.sj.push_back(adj[b][k].first); T.so.push_back(adj[b][k].second); }
+    }
+    T.sofs[nbody] = (int)T.sj.size();
+    return batch_build(wp, T, nworlds, device, 0);
 }
 
 static int stage_up(OdebBatch *B, const Real *src, int k, Real4 *dst)
@@ -463,18 +524,23 @@ int odeb_get_enabled(OdebBatch *B, int *enabled)
     return 1;
 }
 
-static int launch_step(OdebBatch *B, cudaStream_t s, bool timed)
+static void launch_collide(OdebBatch *B, cudaStream_t s, bool narrow)
 {
     const DevParams &P = B->P; const DevPtrs &D = B->D;
     const size_t W = P.W;
-    if (P.NG > 0) {
-        k_aabb<<<nblk(W * P.NG, 128), 128, 0, s>>>(P, D);
-        k_pair_pass<false><<<nblk(W * P.NG, 128), 128, 0, s>>>(P, D);
-        k_pair_scan<<<nblk(W, 64), 64, 0, s>>>(P, D);
-        k_pair_pass<true><<<nblk(W * P.NG, 128), 128, 0, s>>>(P, D);
-        k_narrow<<<nblk(W * P.MP, 64), 64, 0, s>>>(P, D);
-        B->launches += 5;
-    }
+    if (P.NG <= 0) return;
+    k_aabb<<<nblk(W * P.NG, 128), 128, 0, s>>>(P, D);
+    k_pair_pass<false><<<nblk(W * P.NG, 128), 128, 0, s>>>(P, D);
+    k_pair_scan<<<nblk(W, 64), 64, 0, s>>>(P, D);
+    k_pair_pass<true><<<nblk(W * P.NG, 128), 128, 0, s>>>(P, D);
+    B->launches += 4;
+    if (narrow) { k_narrow<<<nblk(W * P.MP, 64), 64, 0, s>>>(P, D); B->launches++; }
+}
+
+static void launch_dynamics(OdebBatch *B, cudaStream_t s, bool timed)
+{
+    const DevParams &P = B->P; const DevPtrs &D = B->D;
+    const size_t W = P.W;
     if (P.NJ > 0) { k_joint_info1<<<nblk(W * P.NJ, 128), 128, 0, s>>>(P, D); B->launches++; }
     k_islands<<<nblk(W, 32), 32, 0, s>>>(P, D);
     k_body_pre<<<nblk(W * P.NB, 128), 128, 0, s>>>(P, D);
@@ -486,6 +552,12 @@ static int launch_step(OdebBatch *B, cudaStream_t s, bool timed)
     if (timed) { cudaEventRecord(e1, s); B->pending.push_back(std::make_pair(e0, e1)); }
     k_integrate<<<nblk(W * P.NB, 128), 128, 0, s>>>(P, D);
     B->launches += 6;
+}
+
+static int launch_step(OdebBatch *B, cudaStream_t s, bool timed)
+{
+    launch_collide(B, s, true);
+    launch_dynamics(B, s, timed);
     return 1;
 }
 

@@ -250,9 +250,10 @@ __device__ void odeb_joint_info2(const DJointT &j, const DLimitState &ls, const 
 struct DSurface {
     int mode, the_m;
     Real mu, mu2, bounce, bounce_vel, soft_erp, soft_cfm, motion1, motion2, motionN, slip1, slip2;
+    Real fdir1[3];          // dContact.fdir1, used when mode has dContactFDir1 (classic per-object API only)
 };
 
-// dxJointContact::getInfo2 joints/contact.cpp:125-347 (no rolling friction, no fdir1)
+// dxJointContact::getInfo2 joints/contact.cpp:125-347 (no rolling friction)
 __device__ void odeb_contact_info2(const DSurface &s, const Real *cpos, const Real *cnormal, Real cdepth, int reverse,
                                    const DBody &b0, const DBody *b1, Real fps, Real worldERP, Real min_depth, Real maxvel,
                                    Real *row, int *findex)
@@ -293,7 +294,8 @@ __device__ void odeb_contact_info2(const DSurface &s, const Real *cpos, const Re
     row[C_LO] = 0; row[C_HI] = R_INF;
     if (s.the_m > 1) {
         Real t1[3], t2[3];
-        plane_space(normal, t1, t2);
+        if (mode & 0x002) { t1[0] = s.fdir1[0]; t1[1] = s.fdir1[1]; t1[2] = s.fdir1[2]; cross3(t2, normal, t1); }   // contact.cpp:221-224
+        else plane_space(normal, t1, t2);
         int r = 1;
         if (s.mu > 0) {
             Real *q = row + r * ROWLEN;

@@ -47,6 +47,7 @@ enum { BF_FINITE_ROT = 1, BF_DISABLED = 4, BF_NO_GRAVITY = 8, BF_AUTO_DISABLE = 
 struct DevParams {
     int W, NB, NG, NJ, MP, MC, MR, NJT;   // worlds, bodies, geoms, permanent joints, pair / contact / row capacity, NJ+MC
     int maxc, space_type, skip_connected;
+    int classic;                          // 1: contacts, their surfaces and the joint adjacency are supplied by the host every step (odeb_classic.inl)
     int m_contact;                        // rows per contact joint (contact.cpp:48-122, uniform under one policy)
     DSurface surf;
     Real gravity[3], erp, cfm, sor_w, premature_delta, extra_delta;
@@ -65,6 +66,7 @@ struct DevPtrs {
     // template (per batch)
     Real *bmass, *binvmass; Real *bI, *binvI;    // [NB], [NB*12]
     int *gtype, *gbody; Real *gparam; unsigned *gcat, *gcol;   // [NG], gparam [NG*4]
+    Real4 *gspose;                               // [NG*4] position + rotation rows of geoms that have no body
     DJointT *joints;                             // [NJ]
     int *sadj_ofs, *sadj_joint, *sadj_other;     // static adjacency in attach order
     unsigned char *conn;                         // [NB*NB] connected by a non-contact joint
@@ -74,6 +76,7 @@ struct DevPtrs {
     int2 *pairs;                                 // [W*MP]
     int *pc_count; Real4 *cgeom;                 // [W*MP], [W*MP*maxc*2] (pos,depth | normal,0)
     int *ncontacts; int4 *cinfo;                 // [W], [W*MC] = (slot, b0, b1, reverse)
+    DSurface *csurf;                             // [MC] per-contact surface parameters (classic mode)
     // joints dynamic
     int *jm; DLimitState *jlimit;                // [W*NJ]
     // islands
@@ -125,9 +128,12 @@ __device__ __forceinline__ void load_geom(const DevParams &P, const DevPtrs &D, 
         G.R[4] = r1.x; G.R[5] = r1.y; G.R[6] = r1.z; G.R[7] = 0;
         G.R[8] = r2.x; G.R[9] = r2.y; G.R[10] = r2.z; G.R[11] = 0;
     } else {
-        G.pos[0] = G.pos[1] = G.pos[2] = 0;
-        for (int k = 0; k < 12; k++) G.R[k] = 0;
-        G.R[0] = G.R[5] = G.R[10] = 1;
+        const Real4 *sp = D.gspose + 4 * (size_t)g;
+        Real4 p = sp[0], r0 = sp[1], r1 = sp[2], r2 = sp[3];
+        G.pos[0] = p.x; G.pos[1] = p.y; G.pos[2] = p.z;
+        G.R[0] = r0.x; G.R[1] = r0.y; G.R[2] = r0.z; G.R[3] = 0;
+        G.R[4] = r1.x; G.R[5] = r1.y; G.R[6] = r1.z; G.R[7] = 0;
+        G.R[8] = r2.x; G.R[9] = r2.y; G.R[10] = r2.z; G.R[11] = 0;
     }
 }
 
@@ -256,7 +262,8 @@ __global__ void k_islands(const __grid_constant__ DevParams P, const __grid_cons
     const int NB = P.NB, NJ = P.NJ, MC = P.MC;
     // 1. number the contact joints in creation order (pair order, then dCollide's contact order)
     int nc = 0;
-    {
+    if (P.classic) nc = D.ncontacts[w];     // contact joints were created through dJointCreateContact: numbered by the host
+    else {
         int np = D.npairs[w];
         const int2 *pairs = D.pairs + (size_t)w * P.MP;
         const int *pcc = D.pc_count + (size_t)w * P.MP;
@@ -280,12 +287,14 @@ __global__ void k_islands(const __grid_constant__ DevParams P, const __grid_cons
     int *adj_c = D.c_adj_c + (size_t)w * 2 * MC, *adj_o = D.c_adj_o + (size_t)w * 2 * MC;
     const int4 *ci = D.cinfo + (size_t)w * MC;
     for (int b = 0; b <= NB; b++) cofs[b] = 0;
-    for (int c = 0; c < nc; c++) { int4 v = ci[c]; cofs[v.y + 1]++; if (v.z >= 0) cofs[v.z + 1]++; }
-    for (int b = 0; b < NB; b++) { cofs[b + 1] += cofs[b]; ccur[b] = cofs[b]; }
-    for (int c = 0; c < nc; c++) {
-        int4 v = ci[c];
-        int k = ccur[v.y]++; adj_c[k] = c; adj_o[k] = v.z;
-        if (v.z >= 0) { k = ccur[v.z]++; adj_c[k] = c; adj_o[k] = v.y; }
+    if (!P.classic) {       // classic mode: the host-built adjacency (sadj_*) already holds every joint in dJointAttach order
+        for (int c = 0; c < nc; c++) { int4 v = ci[c]; cofs[v.y + 1]++; if (v.z >= 0) cofs[v.z + 1]++; }
+        for (int b = 0; b < NB; b++) { cofs[b + 1] += cofs[b]; ccur[b] = cofs[b]; }
+        for (int c = 0; c < nc; c++) {
+            int4 v = ci[c];
+            int k = ccur[v.y]++; adj_c[k] = c; adj_o[k] = v.z;
+            if (v.z >= 0) { k = ccur[v.z]++; adj_c[k] = c; adj_o[k] = v.y; }
+        }
     }
     // 3. dInternalHandleAutoDisabling util.cpp:427-561 (world->firstbody order = reverse creation)
     int *bflags = D.bflags + (size_t)w * NB;
@@ -360,7 +369,7 @@ __global__ void k_islands(const __grid_constant__ DevParams P, const __grid_cons
                 int jid = D.sadj_joint[k];
                 if (!jtag[jid]) {
                     jtag[jid] = 1;
-                    int m = jm[jid];
+                    int m = jid < NJ ? jm[jid] : D.csurf[jid - NJ].the_m;
                     if (m != 0) { jorder[njo] = jid; jrow[njo] = mi; jisl[njo] = nis; njo++; mi += m; }
                     int nb2 = D.sadj_other[k];
                     if (nb2 >= 0 && btag[nb2] <= 0) { btag[nb2] = 1; bflags[nb2] &= ~BF_DISABLED; stack[sp++] = nb2; }
@@ -455,7 +464,8 @@ __global__ void k_rows(const __grid_constant__ DevParams P, const __grid_constan
     bool has_tq = false;
     if (jid >= P.NJ) {
         int4 ci = D.cinfo[(size_t)w * P.MC + (jid - P.NJ)];
-        m = P.m_contact; b0i = ci.y; b1i = ci.z;
+        const DSurface &surf = P.classic ? D.csurf[jid - P.NJ] : P.surf;
+        m = surf.the_m; b0i = ci.y; b1i = ci.z;
         for (int r = 0; r < m; r++) {
             Real *q = row + r * ROWLEN;
             for (int c = 0; c < ROWLEN; c++) q[c] = 0;
@@ -464,10 +474,10 @@ __global__ void k_rows(const __grid_constant__ DevParams P, const __grid_constan
         }
         load_body(D, w * P.NB + b0i, b0);
         if (b1i >= 0) load_body(D, w * P.NB + b1i, b1);
-        const Real4 *cg = D.cgeom + ((size_t)w * P.MP * P.maxc + ci.x) * 2;
+        const Real4 *cg = D.cgeom + ((size_t)w * (P.classic ? (size_t)P.MC : (size_t)P.MP * P.maxc) + ci.x) * 2;
         Real4 a = cg[0], n4 = cg[1];
         Real cpos[3] = { a.x, a.y, a.z }, cn[3] = { n4.x, n4.y, n4.z };
-        odeb_contact_info2(P.surf, cpos, cn, a.w, ci.w, b0, b1i >= 0 ? &b1 : 0, P.hrecip, P.erp, P.min_depth, P.max_vel, row, findex);
+        odeb_contact_info2(surf, cpos, cn, a.w, ci.w, b0, b1i >= 0 ? &b1 : 0, P.hrecip, P.erp, P.min_depth, P.max_vel, row, findex);
     } else {
         const DJointT &jt = D.joints[jid];
         m = D.jm[(size_t)w * P.NJ + jid]; b0i = jt.b0; b1i = jt.b1;
@@ -687,3 +697,4 @@ __global__ void k_add4(size_t n, Real4 *dst, const Real4 *src)
 }
 
 #include "odeb_host.inl"
+#include "odeb_classic.inl"

@@ -1,0 +1,225 @@
+"""The classic per-object API (include/ode_b200_classic.h): one ctypes 'application' (tests/classic_app.py) runs on the
+unmodified reference library and on the B200 library; observables must agree.
+
+CPU part: symbols, struct layouts, host-side functions (mass, rotations, dRand known answers, object bookkeeping) and the
+loud failure without a CUDA device.  GPU part (-m gpu): pair sets, contacts, trajectories, statistics, dRand seed."""
+import ctypes as C
+import os
+import re
+import subprocess
+import tempfile
+import numpy as np
+import pytest
+from parity_util import ROOT
+import classic_app as A
+
+REALS = {"single": C.c_float, "double": C.c_double}
+
+
+def b200_path(prec):
+    return os.path.join(ROOT, "ode_b200", "libode_b200_%s.so" % prec)
+
+
+def ref_path(prec):
+    p = os.path.join(ROOT, "oracle", "_ref", "libode_ref_%s.so" % prec)
+    return p if os.path.exists(p) else None
+
+
+def _declared():
+    txt = open(os.path.join(ROOT, "include", "ode_b200_classic.h")).read()
+    txt = txt[txt.index("/* ---- init"):]
+    return sorted(set(re.findall(r"\b(d[A-Z][A-Za-z0-9_]+)\s*\(", txt)))
+
+
+@pytest.mark.parametrize("prec", ("single", "double"))
+def test_exports_every_declared_classic_symbol(prec):
+    lib = C.CDLL(b200_path(prec))
+    names = _declared()
+    assert len(names) >= 150
+    for n in names:
+        assert hasattr(lib, n), "%s missing from libode_b200_%s.so" % (n, prec)
+    ref = ref_path(prec)
+    if ref:     # every one of them is a real symbol of the reference with the same name
+        rl = C.CDLL(ref)
+        for n in names:
+            assert hasattr(rl, n), "%s is not a symbol of the reference" % n
+
+
+@pytest.mark.parametrize("prec", ("single", "double"))
+def test_struct_layouts(prec):
+    """sizes the C compiler gives the header's structs == the ctypes mirrors the application uses"""
+    src = ('#include "ode_b200_classic.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu\\n", sizeof(dSurfaceParameters),'
+           ' sizeof(dContactGeom), sizeof(dContact), sizeof(dMass), sizeof(dWorldQuickStepIterationCount_DynamicAdjustmentStatistics));return 0;}\n')
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        flags = ["-DODEB_DOUBLE"] if prec == "double" else []
+        subprocess.check_call(["gcc"] + flags + ["-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")])
+        out = [int(x) for x in subprocess.check_output([os.path.join(d, "t")]).decode().split()]
+    t = A.make_types(REALS[prec])
+    assert out == [C.sizeof(x) for x in t]
+
+
+@pytest.mark.parametrize("prec", ("single", "double"))
+def test_host_side_functions_match_reference(prec):
+    """mass, rotation and RNG helpers are plain host arithmetic: bit-identical to the reference, and the reference's own
+    known answers hold (dTestRand, misc.cpp:64-74)."""
+    real = REALS[prec]
+    ours = A.Ode(b200_path(prec), real)
+    ours.dRandSetSeed(0)
+    lib = ours.lib
+    lib.dRand.restype = C.c_ulong
+    assert [lib.dRand() for _ in range(5)] == [0x3c6ef35f, 0x47502932, 0xd1ccf6e9, 0xaaf95334, 0x6252e503]
+    ref = ref_path(prec)
+    if not ref:
+        pytest.skip("reference build not present")
+    theirs = A.Ode(ref, real)
+    for o in (ours, theirs):
+        o.lib.dRandInt.restype = C.c_int
+        o.lib.dRandInt.argtypes = [C.c_int]
+        o.lib.dRandReal.restype = real
+    for n in (2, 3, 4, 7, 16, 17, 200, 256, 1000, 65536, 100000):
+        ours.dRandSetSeed(1234 + n)
+        theirs.dRandSetSeed(1234 + n)
+        assert [ours.lib.dRandInt(n) for _ in range(50)] == [theirs.lib.dRandInt(n) for _ in range(50)]
+        assert ours.lib.dRandReal() == theirs.lib.dRandReal()
+
+    def mass_bytes(o, fn, *args):
+        m = o.dMass()
+        getattr(o, fn)(C.byref(m), *args)
+        return bytes(m)
+    for fn, args in (("dMassSetBox", (2.5, 0.3, 0.7, 1.1)), ("dMassSetSphere", (1.7, 0.45)), ("dMassSetCapsule", (0.9, 3, 0.2, 0.6)),
+                     ("dMassSetCapsule", (1.3, 1, 0.11, 0.9)), ("dMassSetBoxTotal", (3.0, 0.5, 0.5, 0.25))):
+        assert mass_bytes(ours, fn, *args) == mass_bytes(theirs, fn, *args), fn
+    for ax in ((1, 0, 0, 0.3), (0.2, -0.5, 0.8, 1.9), (0, 0, 0, 1.0), (3, 4, 12, -2.2)):
+        qa, qb = (real * 4)(), (real * 4)()
+        ours.dQFromAxisAndAngle(qa, *ax)
+        theirs.dQFromAxisAndAngle(qb, *ax)
+        if prec == "double":    # sin/cos of the host libm on both sides
+            assert bytes(qa) == bytes(qb)
+        else:
+            assert np.allclose(list(qa), list(qb), rtol=0, atol=2e-7)
+
+
+@pytest.mark.parametrize("prec", ("single", "double"))
+def test_object_bookkeeping(prec):
+    """handles, setters/getters, dJointAttach swap rule, connectivity queries: same answers as the reference"""
+    real = REALS[prec]
+    libs = [A.Ode(b200_path(prec), real)]
+    if ref_path(prec):
+        libs.append(A.Ode(ref_path(prec), real))
+    answers = []
+    for o in libs:
+        o.dInitODE2(0)
+        w = o.dWorldCreate()
+        b = [o.dBodyCreate(w) for _ in range(3)]
+        o.dBodySetPosition(b[0], 1, 2, 3)
+        q = (real * 4)(2.0, 0.0, 0.0, 2.0)
+        o.dBodySetQuaternion(b[1], q)
+        j1 = o.dJointCreateBall(w, None)
+        o.dJointAttach(j1, b[0], b[1])
+        j2 = o.dJointCreateHinge(w, None)
+        o.dJointAttach(j2, None, b[2])
+        o.lib.dJointGetBody.restype = C.c_void_p
+        o.lib.dJointGetBody.argtypes = [C.c_void_p, C.c_int]
+        o.lib.dBodyGetNumJoints.argtypes = [C.c_void_p]
+        p = o.dBodyGetPosition(b[0])
+        qq = o.dBodyGetQuaternion(b[1])
+        R = o.dBodyGetRotation(b[1])
+        answers.append(([p[0], p[1], p[2]], [qq[k] for k in range(4)], [R[k] for k in range(12)],
+                        o.dAreConnected(b[0], b[1]), o.dAreConnected(b[0], b[2]), o.dAreConnectedExcluding(b[0], b[1], 1),
+                        o.lib.dJointGetBody(j2, 0) is None, o.lib.dJointGetBody(j2, 1) == b[2],
+                        o.lib.dBodyGetNumJoints(b[0]), o.lib.dBodyGetNumJoints(b[2]), o.dBodyIsEnabled(b[0])))
+        o.dWorldDestroy(w)
+        o.dCloseODE()
+    assert answers[0][0] == [1, 2, 3]
+    if len(answers) == 2:
+        assert answers[0] == answers[1]
+
+
+def _have_cuda():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_classic_step_fails_loudly_without_gpu():
+    if _have_cuda():
+        pytest.skip("a CUDA device is present")
+    o = A.Ode(b200_path("single"), C.c_float)
+    app = A.App(o)
+    A.scene_stack(app, 2)
+    assert app.step(0.01, seed=1) == 0          # dWorldQuickStep reports failure, the state is untouched
+    assert np.array_equal(app.state()[:, 2], np.array([0.25, 0.751], np.float32))
+    o.lib.odeb_last_error.restype = C.c_char_p
+    assert b"CUDA" in o.lib.odeb_last_error()
+
+
+# ------------------------------------------------------------------------------------------------ GPU parity
+
+def _run_both(prec, build, nsteps, h, **kw):
+    real = REALS[prec]
+    ref = ref_path(prec)
+    if not ref:
+        pytest.skip("reference build (oracle/_ref) not present")
+    apps = []
+    for path in (ref, b200_path(prec)):
+        app = A.App(A.Ode(path, real), **kw)
+        build(app)
+        apps.append(app)
+    return apps
+
+
+def _compare(apps, nsteps, h, exact=True, tol=0.0, seed0=100):
+    ra, ga = apps
+    worst = 0.0
+    for s in range(nsteps):
+        assert ra.step(h, seed=seed0 + s) == 1
+        assert ga.step(h, seed=seed0 + s) == 1, "B200 dWorldQuickStep failed at step %d" % s
+        assert ra.pair_set() == ga.pair_set(), "pair set differs at step %d" % s
+        assert len(ra.contact_log) == len(ga.contact_log), "contact count differs at step %d" % s
+        assert [c[:2] for c in ra.contact_log] == [c[:2] for c in ga.contact_log]
+        assert ra.o.dRandGetSeed() == ga.o.dRandGetSeed(), "dRand seed differs at step %d" % s
+        sa, sg = ra.state(), ga.state()
+        if exact:
+            ca = np.array([c[2] + c[3] + (c[4],) for c in ra.contact_log])
+            cg = np.array([c[2] + c[3] + (c[4],) for c in ga.contact_log])
+            assert np.array_equal(ca, cg), "contact geometry differs at step %d" % s
+            assert np.array_equal(sa, sg), "state differs at step %d: max %.3g" % (s, np.abs(sa - sg).max())
+        else:
+            worst = max(worst, float(np.abs(sa.astype(np.float64) - sg).max()))
+            assert worst <= tol, "state differs by %.3g at step %d" % (worst, s)
+    for k in ("iteration_count", "premature_exits", "prolonged_execs", "full_extra_execs"):
+        if exact:
+            assert getattr(ra.stats, k) == getattr(ga.stats, k), k
+    assert ra.ncontacts == ga.ncontacts and ra.ncontacts > 0
+    for a in apps:
+        a.close()
+    return worst
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec", ("single", "double"))
+def test_classic_boxstack_bit_exact(prec):
+    """demo_boxstack-style stack through dSpaceCollide/dCollide/dJointCreateContact/dWorldQuickStep: every observable identical"""
+    apps = _run_both(prec, lambda a: A.scene_stack(a, 8), 60, 0.02, space="hash", gravity=(0, 0, -0.5), max_contacts=8, surface="boxstack", cfm=1e-5)
+    _compare(apps, 60, 0.02, exact=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec,space", (("single", "sap"), ("double", "hash"), ("single", "simple")))
+def test_classic_mixed_pile(prec, space):
+    """boxes, spheres and capsules with friction (Approx1): all primitive pair types, per-contact surfaces.
+    Contact culling uses atan2 (box.cpp:305) -> CUDA libm vs glibc: stated tolerance on the state."""
+    apps = _run_both(prec, lambda a: A.scene_mixed_pile(a, 12), 80, 0.01, space=space, max_contacts=4, surface="approx1")
+    _compare(apps, 80, 0.01, exact=False, tol=2e-4 if prec == "single" else 1e-9)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec", ("single", "double"))
+def test_classic_linkage_joints(prec):
+    """ball / hinge / universal joints with stops created through the classic setters + ground contacts (hinge angles use
+    atan2 -> tolerance as in tests/test_gpu_parity.py)"""
+    apps = _run_both(prec, A.scene_linkage, 100, 0.01, space="hash", max_contacts=4, surface="chain")
+    _compare(apps, 100, 0.01, exact=False, tol=5e-4 if prec == "single" else 1e-9)
