@@ -117,16 +117,17 @@ __device__ __forceinline__ void load_half(HalfRegs &h, const uint4 *slot)
                 _Pragma("unroll") for (int c = 0; c < CH; c++) cp_async16(dst + c * 32 * 16, src + c * 16);             \
             }                                                                                                            \
             cp_async_commit();                                                                                           \
-            cp_async_wait<ODEB_RING - 2>();                                                                              \
         }                                                                                                                \
-        load_half(NXT, ring + (size_t)(((K) + 1) & (ODEB_RING - 1)) * CH * 32);                                         \
-        MTN = (i + (K) + 1 < m) ? mp[((K) + 1) * 32] : 0u;                                                               \
-        ma = mp[((K) + ODEB_RING) * 32];                                /* metadata of the row prefetched next */        \
+        const Real lo_b = shfl_xor1(ODEB_FULL, CUR.q1.z);               /* lane A receives lo from lane B */             \
         const Real s = fa.x * CUR.q0.x + fa.y * CUR.q0.y + fa.z * CUR.q0.z + fa.w * CUR.q0.w + fb.x * CUR.q1.x + fb.y * CUR.q1.y; \
         const Real ta = (CUR.q1.z - old_lambda * CUR.q1.w) - s;         /* lane A: (rhs - lambda*cfm) - s1 */           \
         const Real mine = side ? s : ta;                                                                                 \
         const Real other = shfl_xor1(ODEB_FULL, mine);                                                                   \
-        const Real lo_b = shfl_xor1(ODEB_FULL, CUR.q1.z);               /* lane A receives lo from lane B */             \
+        /* the next row's operands load while the shuffle is in flight */                                                \
+        cp_async_wait<ODEB_RING - 2>();                                                                                  \
+        load_half(NXT, ring + (size_t)(((K) + 1) & (ODEB_RING - 1)) * CH * 32);                                         \
+        MTN = (i + (K) + 1 < m) ? mp[((K) + 1) * 32] : 0u;                                                               \
+        ma = mp[((K) + ODEB_RING) * 32];                                /* metadata of the row prefetched next */        \
         Real delta = side ? (other - mine) : (mine - other);            /* ((rhs - lambda*cfm) - s1) - s2 */             \
         const Real hi = side ? CUR.q1.w : CUR.q3.w;                                                                      \
         const Real lo = side ? CUR.q1.z : lo_b;                                                                          \
