@@ -143,6 +143,39 @@ int odeb_set_seeds(OdebBatch *, const uint32_t *seeds);
 int odeb_get_seeds(OdebBatch *, uint32_t *seeds);
 int odeb_get_enabled(OdebBatch *, int *enabled /* [world][body] */);
 
+/* Solver order mode.
+ *   ODEB_MODE_REPLAY (default): constraint order, dRand-driven reorders and island sequencing of the reference are replayed
+ *     exactly (list mechanics of dJointAttach / dxProcessIslands); results are bit-comparable with the reference.  One world
+ *     is inherently serial in this mode, so it is meant for batches of small worlds.
+ *   ODEB_MODE_CANONICAL: the large-world path (single worlds of 10^3..10^5 bodies).  Pair set, contacts, island membership
+ *     and island numbering are those of the reference; inside an island bodies are ordered by descending creation index and
+ *     joints by ascending id (permanent joints, then contacts in creation order).  The row order of sweeps 0..7 keeps
+ *     ReorderPrep's two classes (rows without a friction index first) but sorts each class by odeb_canon_key(seed, island, 0,
+ *     row); the reorder at sweep 8k sorts all rows by odeb_canon_key(seed, island, k, row) instead of replaying Fisher-Yates,
+ *     and the world's dRand seed is advanced by the draws the reference would have consumed.  Hashed orders keep the
+ *     dependency graph of a sweep shallow; the sweeps themselves keep the sequential semantics of that order (a row runs
+ *     after exactly the rows that precede it on its two bodies), so the result is bit-identical to the oracle run in the same
+ *     mode (oracle: orc_set_solver_mode) and is one of the orders the reference's own random reordering could produce.
+ *     Requires nworlds == 1. */
+enum { ODEB_MODE_REPLAY = 0, ODEB_MODE_CANONICAL = 1 };
+int odeb_set_solver_mode(OdebBatch *, int mode);
+
+#if defined(__CUDACC__)
+#define ODEB_HD __host__ __device__
+#else
+#define ODEB_HD
+#endif
+/* key of row `row` of island `island` for the reorder at sweep 8*phase in ODEB_MODE_CANONICAL (murmur3 finaliser);
+ * `seed` = the world's dRand seed at the start of the step. Exported as odeb_canon_key; the inline body is shared with
+ * the kernels and with oracle/. */
+uint32_t odeb_canon_key(uint32_t seed, uint32_t island, uint32_t phase, uint32_t row);
+static inline ODEB_HD uint32_t odebi_canon_key(uint32_t seed, uint32_t island, uint32_t phase, uint32_t row)
+{
+    uint32_t x = seed ^ (island * 0x9E3779B9u) ^ (phase * 0x85EBCA6Bu) ^ (row * 0xC2B2AE35u);
+    x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+    return x;
+}
+
 /* nsteps x { dSpaceCollide + contact policy ; dWorldQuickStep(h) ; dJointGroupEmpty }.
  * Returns 1 on success, 0 on failure (like dWorldQuickStep), state untouched on allocation failure. */
 int odeb_step(OdebBatch *, double h, int nsteps);

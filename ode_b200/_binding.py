@@ -263,6 +263,13 @@ class Batch:
     def add_force(self, force=None, torque=None):
         self.slib._fn("add_force")(self.h, _ptr(self._arr(force, 3)), _ptr(self._arr(torque, 3)))
 
+    def set_solver_mode(self, mode):
+        """0 = replay of the reference's order (default), 1 = canonical order (large-world path, include/ode_b200.h)"""
+        f = self.slib._fn("set_solver_mode")
+        f.argtypes = [C.c_void_p, C.c_int]
+        if not f(self.h, int(mode)):
+            raise RuntimeError("%sset_solver_mode failed" % self.slib.prefix)
+
     def set_seeds(self, seeds):
         s = np.ascontiguousarray(np.asarray(seeds, dtype=np.uint32).reshape(self.W))
         self.slib._fn("set_seeds")(self.h, _ptr(s))
@@ -281,6 +288,15 @@ class Batch:
         ok = self.slib._fn("step")(self.h, float(h), int(nsteps))
         if not ok:
             raise RuntimeError("%sstep failed" % self.slib.prefix)
+
+    def get_totals(self):
+        """[pairs, contacts, rows, islands, sweeps, row-sweeps] of the most recent step, summed over worlds"""
+        out = (C.c_uint64 * 6)()
+        f = self.slib._fn("get_totals")
+        f.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        if not f(self.h, out):
+            raise RuntimeError("%sget_totals failed" % self.slib.prefix)
+        return [int(v) for v in out]
 
     def get_pairs(self, world, cap=1 << 16):
         buf = np.empty((cap, 2), np.int32)

@@ -184,7 +184,6 @@ static ClassicCtx *ctx_get(dxWorld *w, dxSpace *s, int need_contacts)
     }
     c->nj = (int)c->perm.size();
     T.jt.resize(c->nj);
-    T.conn.assign((size_t)nb * nb, 0);
     T.sofs.assign(nb + 1, 0);
     // capacities: pairs grow on overflow, contacts to what the caller is about to submit
     long long all = (long long)ng * (ng - 1) / 2;

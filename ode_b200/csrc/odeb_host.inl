@@ -28,7 +28,10 @@ struct OdebBatch {
     cudaGraphExec_t graph; double graph_h; bool use_graph;
     size_t solve_smem;
     void *flush_buf; size_t flush_bytes;
+    // large-world path (ODEB_MODE_CANONICAL, odeb_large_host.inl)
+    int mode; LargePtrs L; bool large_ready;
 };
+static int large_step(OdebBatch *B);
 
 template <class T> static bool dev_alloc(OdebBatch *B, T **p, size_t n)
 {
@@ -228,7 +231,6 @@ struct HostTemplate {
     std::vector<Real4> gspose;                               // [NG*4]: position + 3 rotation rows of geoms without a body
     std::vector<DJointT> jt;
     std::vector<int> sofs, sj, so;                           // per-body joint adjacency in attach order (CSR)
-    std::vector<unsigned char> conn;                         // [NB*NB] joined by a non-contact joint
 };
 
 struct BatchCaps { int classic, max_pairs, max_contacts; };  // classic: contacts / surfaces / adjacency come from the host every step
@@ -248,6 +250,7 @@ static OdebBatch *batch_build(const OdebWorldParams *wp, const HostTemplate &T, 
 
     OdebBatch *B = new OdebBatch();
     B->device = device; B->bytes = 0; B->launches = 0; B->timing = false; B->solver_ms = 0; B->solver_launches = 0;
+    B->mode = ODEB_MODE_REPLAY; B->large_ready = false; memset(&B->L, 0, sizeof(B->L));
     B->graph = 0; B->graph_h = -1; B->use_graph = getenv("ODEB_NO_GRAPH") == 0 && !classic; B->h_stage = 0; B->d_stage = 0; B->stream = 0; B->flush_buf = 0; B->flush_bytes = 0;
     memset(&B->D, 0, sizeof(B->D));
     DevParams &P = B->P;
@@ -261,7 +264,7 @@ static OdebBatch *batch_build(const OdebWorldParams *wp, const HostTemplate &T, 
         if (caps && caps->max_pairs > 0) mp = caps->max_pairs;
         P.MP = (int)(mp < 1 ? 1 : mp);
         long long mc = (long long)P.MP * P.maxc;
-        long long cap = 2LL * ngeom * P.maxc;
+        long long cap = (nworlds == 1 ? 4LL : 2LL) * ngeom * P.maxc;   // a single (large) world may be a dense wall / pile
         if (mc > cap) mc = cap;
         if (const char *s = getenv("ODEB_MAX_CONTACTS")) mc = atoll(s);
         if (caps && caps->max_contacts > 0) mc = caps->max_contacts;
@@ -301,8 +304,7 @@ static OdebBatch *batch_build(const OdebWorldParams *wp, const HostTemplate &T, 
     ok = ok && dev_alloc(B, &D.bmass, nbody) && dev_alloc(B, &D.binvmass, nbody) && dev_alloc(B, &D.bI, 12 * (size_t)nbody) && dev_alloc(B, &D.binvI, 12 * (size_t)nbody)
             && dev_alloc(B, &D.gtype, ngeom) && dev_alloc(B, &D.gbody, ngeom) && dev_alloc(B, &D.gparam, 4 * (size_t)ngeom)
             && dev_alloc(B, &D.gcat, ngeom) && dev_alloc(B, &D.gcol, ngeom) && dev_alloc(B, &D.gspose, 4 * (size_t)ngeom) && dev_alloc(B, &D.joints, njoint)
-            && dev_alloc(B, &D.sadj_ofs, nbody + 1) && dev_alloc(B, &D.sadj_joint, nadj) && dev_alloc(B, &D.sadj_other, nadj)
-            && dev_alloc(B, &D.conn, (size_t)nbody * nbody);
+            && dev_alloc(B, &D.sadj_ofs, nbody + 1) && dev_alloc(B, &D.sadj_joint, nadj) && dev_alloc(B, &D.sadj_other, nadj);
     ok = ok && dev_alloc(B, &D.aabb, WG * 6) && dev_alloc(B, &D.pair_cnt, WG) && dev_alloc(B, &D.pair_ofs, WG) && dev_alloc(B, &D.npairs, W)
             && dev_alloc(B, &D.pairs, W * P.MP) && dev_alloc(B, &D.pc_count, W * P.MP) && dev_alloc(B, &D.cgeom, W * (classic ? (size_t)P.MC : (size_t)P.MP * P.maxc) * 2)
             && dev_alloc(B, &D.ncontacts, W) && dev_alloc(B, &D.cinfo, W * P.MC) && dev_alloc(B, &D.jm, WJ) && dev_alloc(B, &D.jlimit, WJ);
@@ -327,7 +329,7 @@ static OdebBatch *batch_build(const OdebWorldParams *wp, const HostTemplate &T, 
     ok = upload(D.bmass, T.bmass) && upload(D.binvmass, T.binvmass) && upload(D.bI, T.bI) && upload(D.binvI, T.binvI)
       && upload(D.gtype, T.gtype) && upload(D.gbody, T.gbody) && upload(D.gparam, T.gparam) && upload(D.gcat, T.gcat) && upload(D.gcol, T.gcol)
       && upload(D.gspose, T.gspose)
-      && upload(D.joints, T.jt) && upload(D.sadj_ofs, T.sofs) && upload(D.sadj_joint, T.sj) && upload(D.sadj_other, T.so) && upload(D.conn, T.conn);
+      && upload(D.joints, T.jt) && upload(D.sadj_ofs, T.sofs) && upload(D.sadj_joint, T.sj) && upload(D.sadj_other, T.so);
     // initial per-world state = template pose
     {
         std::vector<Real4> pos(WB), quat(WB), R(3 * WB);
@@ -405,7 +407,6 @@ OdebBatch *odeb_create(const OdebWorldParams *wp,
     }
     T.jt.resize(njoint);
     std::vector<std::vector<std::pair<int, int> > > adj(nbody);
-    T.conn.assign((size_t)nbody * nbody, 0);
     for (int i = 0; i < njoint; i++) {
         const OdebJointDesc &d = joints[i];
         DJointT &j = T.jt[i];
@@ -417,7 +418,7 @@ OdebBatch *odeb_create(const OdebWorldParams *wp,
         if (b1 < 0) { b1 = b2; b2 = -1; j.reverse = 1; }         // dJointAttach ode.cpp:1404-1411
         j.b0 = b1; j.b1 = b2;
         adj[b1].push_back(std::make_pair(i, b2));
-        if (b2 >= 0) { adj[b2].push_back(std::make_pair(i, b1)); T.conn[(size_t)b1 * nbody + b2] = T.conn[(size_t)b2 * nbody + b1] = 1; }
+        if (b2 >= 0) adj[b2].push_back(std::make_pair(i, b1));
         host_set_anchors(hb, j, (Real)d.anchor[0], (Real)d.anchor[1], (Real)d.anchor[2]);
         host_limot(j.limot1, erp, cfm, d, 0);
         host_limot(j.limot2, erp, cfm, d, 1);
@@ -566,6 +567,10 @@ int odeb_step_async(OdebBatch *B, double h, int nsteps)
     CK(cudaSetDevice(B->device));
     if (!(h > 0)) { set_err("stepsize must be > 0"); return 0; }
     B->P.h = (Real)h; B->P.hrecip = rrecip((Real)h);
+    if (B->mode == ODEB_MODE_CANONICAL) {
+        for (int s = 0; s < nsteps; s++) if (!large_step(B)) return 0;
+        return 1;
+    }
     const bool graph_ok = B->use_graph && !B->timing;
     if (graph_ok && (B->graph == 0 || B->graph_h != h)) {
         if (B->graph) { cudaGraphExecDestroy(B->graph); B->graph = 0; }

@@ -69,7 +69,6 @@ struct DevPtrs {
     Real4 *gspose;                               // [NG*4] position + rotation rows of geoms that have no body
     DJointT *joints;                             // [NJ]
     int *sadj_ofs, *sadj_joint, *sadj_other;     // static adjacency in attach order
-    unsigned char *conn;                         // [NB*NB] connected by a non-contact joint
     // collision scratch
     Real *aabb;                                  // [W*NG*6]
     int *pair_cnt, *pair_ofs, *npairs;           // [W*NG], [W*NG], [W]
@@ -92,6 +91,7 @@ struct DevPtrs {
                                                  //   (layout in odeb_solve.cuh)
     int2 *rbody;                                 // [W*MR] accumulator slots (order positions) of the row's two bodies; one-body rows: (p0, NB)
     int *findex, *order; Real *lambda;           // [W*MR]
+    int *row_island, *row_group;                 // [MR] island of every row, first row of the row's group (large-world path only, else null)
     Real4 *cforce;                               // [W*(NB+1)*2]  (fc 6, fa 2) per order position + one dummy slot per world
     Real *invIw;                                 // [W*NB*12], indexed by order position
     unsigned *stats, *seed;                      // [W*4], [W]
@@ -215,7 +215,9 @@ __global__ void k_narrow(const __grid_constant__ DevParams P, const __grid_const
     int2 pr = D.pairs[t];
     int b1 = D.gbody[pr.x], b2 = D.gbody[pr.y];
     int n = 0;
-    bool skip = (b1 < 0 && b2 < 0) || (P.skip_connected && b1 >= 0 && b2 >= 0 && D.conn[b1 * P.NB + b2]);
+    bool skip = (b1 < 0 && b2 < 0);
+    if (!skip && P.skip_connected && P.NJ > 0 && b1 >= 0 && b2 >= 0)      // dAreConnectedExcluding(b1, b2, dJointTypeContact) ode.cpp:1569-1577
+        for (int k = D.sadj_ofs[b1]; k < D.sadj_ofs[b1 + 1]; k++) if (D.sadj_other[k] == b2) { skip = true; break; }
     if (!skip) {
         DGeom g1, g2;
         load_geom(P, D, w, pr.x, g1);
@@ -500,6 +502,10 @@ __global__ void k_rows(const __grid_constant__ DevParams P, const __grid_constan
         Real4 v0 = { q[0], q[1], q[2], q[3] }, v1 = { q[4], q[5], q[6], q[7] }, v2 = { q[8], q[9], q[10], q[11] }, v3 = { q[12], q[13], q[14], q[15] };
         rec[8 * r] = v0; rec[8 * r + 1] = v1; rec[8 * r + 2] = v2; rec[8 * r + 3] = v3;
         fi[r] = findex[r] == -1 ? -1 : findex[r] + row0;
+        if (D.row_island) {     // large-world path: the contacts of one geom pair (ids consecutive, same island) form one row group
+            D.row_island[row0 + r] = D.joint_island[t];
+            D.row_group[row0 + r] = (jid >= P.NJ) ? row0 - (D.cinfo[(size_t)w * P.MC + (jid - P.NJ)].x % P.maxc) * m : row0;
+        }
         // body order positions travel in the last two slots of the record
         *(int *)&rec[8 * r + 7].z = p0; *(int *)&rec[8 * r + 7].w = p1;
     }
@@ -589,6 +595,7 @@ __global__ void k_rows_finish(const __grid_constant__ DevParams P, const __grid_
 }
 
 #include "odeb_solve.cuh"
+#include "odeb_large.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // Stage 4b + 6a + 6b (dxStepBody)
@@ -697,4 +704,5 @@ __global__ void k_add4(size_t n, Real4 *dst, const Real4 *src)
 }
 
 #include "odeb_host.inl"
+#include "odeb_large_host.inl"
 #include "odeb_classic.inl"

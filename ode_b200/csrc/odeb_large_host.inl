@@ -1,0 +1,193 @@
+// odeb_large_host.inl -- host side of the large-world path (kernels in odeb_large.cuh): buffer set-up and the launch
+// sequence of one step.  The sequence has a few small device->host reads (pair / contact / row counts, number of
+// unfinished islands at each phase boundary) because the radix sorts need their sizes; a step of a 10^5-body world
+// is milliseconds of GPU work, so these cost nothing measurable.  No CPU fallback, no host-side physics.
+
+#define LCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_err("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); return 0; } } while (0)
+
+static size_t large_cub_bytes(const DevParams &P)
+{
+    size_t best = 0, b = 0;
+    cub::DeviceRadixSort::SortPairs(0, b, (unsigned *)0, (unsigned *)0, (int *)0, (int *)0, P.NG); best = b > best ? b : best;
+    cub::DeviceRadixSort::SortKeys(0, b, (u64 *)0, (u64 *)0, P.MP); best = b > best ? b : best;
+    cub::DeviceRadixSort::SortPairs(0, b, (u64 *)0, (u64 *)0, (int *)0, (int *)0, P.NB); best = b > best ? b : best;
+    cub::DeviceRadixSort::SortPairs(0, b, (u64 *)0, (u64 *)0, (int *)0, (int *)0, P.NJT); best = b > best ? b : best;
+    cub::DeviceRadixSort::SortPairs(0, b, (u64 *)0, (u64 *)0, (int *)0, (int *)0, P.MR); best = b > best ? b : best;
+    cub::DeviceScan::ExclusiveSum(0, b, (int *)0, (int *)0, P.MP); best = b > best ? b : best;
+    cub::DeviceScan::ExclusiveSum(0, b, (int *)0, (int *)0, P.NJT); best = b > best ? b : best;
+    cub::DeviceScan::InclusiveSum(0, b, (int *)0, (int *)0, P.NB + 2); best = b > best ? b : best;
+    return best + 256;
+}
+
+static int large_prepare(OdebBatch *B)
+{
+    if (B->large_ready) return 1;
+    const DevParams &P = B->P;
+    LargePtrs &L = B->L;
+    const size_t NB = P.NB, NG = P.NG > 0 ? P.NG : 1, MP = P.MP, MR = P.MR, NJT = P.NJT;
+    bool ok = dev_alloc(B, &L.counters, LWC_COUNT) && dev_alloc(B, &L.draws, 4)
+           && dev_alloc(B, &L.bp_key, NG) && dev_alloc(B, &L.bp_key_s, NG) && dev_alloc(B, &L.bp_idx, NG) && dev_alloc(B, &L.bp_idx_s, NG) && dev_alloc(B, &L.bp_big, NG)
+           && dev_alloc(B, &L.pair_key, MP) && dev_alloc(B, &L.pair_key_s, MP) && dev_alloc(B, &L.pc_base, MP)
+           && dev_alloc(B, &L.parent, NB) && dev_alloc(B, &L.maxen, NB) && dev_alloc(B, &L.head_scan, NB) && dev_alloc(B, &L.deg, NB)
+           && dev_alloc(B, &L.bkey, NB) && dev_alloc(B, &L.bkey_s, NB) && dev_alloc(B, &L.bval, NB)
+           && dev_alloc(B, &L.isl_nb, NB + 2) && dev_alloc(B, &L.isl_m, NB + 2) && dev_alloc(B, &L.isl_bstart, NB + 2) && dev_alloc(B, &L.isl_rstart, NB + 2)
+           && dev_alloc(B, &L.isl_done, NB + 2) && dev_alloc(B, &L.isl_viol, NB + 2)
+           && dev_alloc(B, &L.jkey, NJT) && dev_alloc(B, &L.jkey_s, NJT) && dev_alloc(B, &L.jmv, NJT) && dev_alloc(B, &L.jmv_s, NJT) && dev_alloc(B, &L.jrow, NJT)
+           && dev_alloc(B, &L.row_island, MR) && dev_alloc(B, &L.okey, MR) && dev_alloc(B, &L.okey_s, MR) && dev_alloc(B, &L.oval, MR) && dev_alloc(B, &L.ord, MR)
+           && dev_alloc(B, &L.rpos, MR) && dev_alloc(B, &L.inc_ofs, NB + 2) && dev_alloc(B, &L.inc_cur, NB + 2) && dev_alloc(B, &L.inc, 2 * MR)
+           && dev_alloc(B, &L.inc_pos, 2 * MR) && dev_alloc(B, &L.ticket, MR) && dev_alloc(B, &L.row_group, MR) && dev_alloc(B, &L.head_pos, MR + 1) && dev_alloc(B, &L.cnt, NB + 2);
+    if (!ok) return 0;
+    L.tmp_bytes = large_cub_bytes(P);
+    { unsigned char *t = 0; if (!dev_alloc(B, &t, L.tmp_bytes)) return 0; L.tmp = t; }
+    B->D.row_island = L.row_island; B->D.row_group = L.row_group;
+    B->large_ready = true;
+    return 1;
+}
+
+extern "C" int odeb_set_solver_mode(OdebBatch *B, int mode)
+{
+    if (mode != ODEB_MODE_REPLAY && mode != ODEB_MODE_CANONICAL) { set_err("unknown solver mode %d", mode); return 0; }
+    if (mode == ODEB_MODE_CANONICAL) {
+        if (B->P.W != 1 || B->P.classic) { set_err("ODEB_MODE_CANONICAL is the single-world path: needs nworlds == 1 and the batch API"); return 0; }
+        CK(cudaSetDevice(B->device));
+        if (!large_prepare(B)) return 0;
+    }
+    B->mode = mode;
+    return 1;
+}
+
+extern "C" uint32_t odeb_canon_key(uint32_t seed, uint32_t island, uint32_t phase, uint32_t row) { return odebi_canon_key(seed, island, phase, row); }
+
+static int bits_for(unsigned v) { int b = 1; while ((v >> b) != 0 && b < 32) b++; return b; }
+
+static int large_step(OdebBatch *B)
+{
+    const DevParams &P = B->P; const DevPtrs &D = B->D; LargePtrs &L = B->L;
+    cudaStream_t s = B->stream;
+    const int NB = P.NB, NG = P.NG;
+    int hc[LWC_COUNT];
+    LCK(cudaMemsetAsync(L.counters, 0, LWC_COUNT * sizeof(int), s));
+    LCK(cudaMemsetAsync(L.draws, 0, 4 * sizeof(u64), s));
+    // ---------------- collision
+    int np = 0;
+    if (NG > 0) {
+        k_aabb<<<nblk(NG, 128), 128, 0, s>>>(P, D);
+        k_bp_keys<<<nblk(NG, 128), 128, 0, s>>>(P, D, L);
+        LCK(cub::DeviceRadixSort::SortPairs(L.tmp, L.tmp_bytes, L.bp_key, L.bp_key_s, L.bp_idx, L.bp_idx_s, NG, 0, 32, s));
+        k_bp_sweep<<<nblk(NG, 64), 64, 0, s>>>(P, D, L);
+        k_bp_big<<<nblk(NG, 128), 128, 0, s>>>(P, D, L);
+        B->launches += 5;
+        LCK(cudaMemcpyAsync(hc, L.counters, sizeof(hc), cudaMemcpyDeviceToHost, s));
+        LCK(cudaStreamSynchronize(s));
+        np = hc[LWC_NPAIRS];
+        if (np > P.MP) { set_err("capacity overflow (pairs: %d > %d): raise ODEB_MAX_PAIRS", np, P.MP); return 0; }
+        if (np > 0) {
+            LCK(cub::DeviceRadixSort::SortKeys(L.tmp, L.tmp_bytes, L.pair_key, L.pair_key_s, np, 0, 32 + bits_for((unsigned)NG), s));
+            B->launches++;
+        }
+        k_bp_unpack<<<nblk(np > 0 ? np : 1, 256), 256, 0, s>>>(np, L.pair_key_s, D.pairs, D.npairs);
+        B->launches++;
+        if (np > 0) {
+            k_narrow<<<nblk(np, 64), 64, 0, s>>>(P, D);
+            LCK(cub::DeviceScan::ExclusiveSum(L.tmp, L.tmp_bytes, D.pc_count, L.pc_base, np, s));
+            k_lw_contact_fill<<<nblk(np, 128), 128, 0, s>>>(P, D, L, np);
+            B->launches += 3;
+        } else LCK(cudaMemsetAsync(D.ncontacts, 0, sizeof(int), s));
+    } else {
+        LCK(cudaMemsetAsync(D.npairs, 0, sizeof(int), s));
+        LCK(cudaMemsetAsync(D.ncontacts, 0, sizeof(int), s));
+    }
+    // ---------------- joints, auto-disable, islands
+    if (P.NJ > 0) { k_joint_info1<<<nblk(P.NJ, 128), 128, 0, s>>>(P, D); B->launches++; }
+    LCK(cudaMemcpyAsync(hc, L.counters, sizeof(hc), cudaMemcpyDeviceToHost, s));
+    LCK(cudaStreamSynchronize(s));
+    const int nc = hc[LWC_NCONTACTS];
+    const int nj = P.NJ + nc;
+    LCK(cudaMemsetAsync(L.deg, 0, NB * sizeof(int), s));
+    k_lw_init_bodies<<<nblk(NB + 1, 256), 256, 0, s>>>(P, D, L);
+    B->launches++;
+    if (P.adis_samples > 0) {
+        if (nc > 0) { k_lw_degree<<<nblk(nc, 256), 256, 0, s>>>(P, D, L); B->launches++; }
+        k_lw_autodisable<<<nblk(NB, 128), 128, 0, s>>>(P, D, L);
+        B->launches++;
+    }
+    if (nj > 0) { k_lw_union<<<nblk(nj, 256), 256, 0, s>>>(P, D, L); B->launches++; }
+    k_lw_roots<<<nblk(NB, 256), 256, 0, s>>>(P, D, L);
+    k_lw_heads<<<nblk(NB, 256), 256, 0, s>>>(P, L);
+    LCK(cub::DeviceScan::InclusiveSum(L.tmp, L.tmp_bytes, L.deg, L.head_scan, NB, s));
+    k_lw_label<<<nblk(NB, 256), 256, 0, s>>>(P, D, L);
+    k_lw_iota<<<nblk(NB, 256), 256, 0, s>>>(NB, L.bval);
+    LCK(cub::DeviceRadixSort::SortPairs(L.tmp, L.tmp_bytes, L.bkey, L.bkey_s, L.bval, D.body_order, NB, 0, 64, s));
+    k_lw_body_pos<<<nblk(NB, 256), 256, 0, s>>>(P, D, L);
+    k_lw_joint_keys<<<nblk(P.NJT, 256), 256, 0, s>>>(P, D, L);
+    B->launches += 8;
+    LCK(cudaMemcpyAsync(hc, L.counters, sizeof(hc), cudaMemcpyDeviceToHost, s));
+    LCK(cudaStreamSynchronize(s));
+    const int T = hc[LWC_NISLANDS], mrows = hc[LWC_MROWS], nordered = hc[LWC_NORDERED];
+    if (mrows > P.MR) { set_err("capacity overflow (rows: %d > %d): raise ODEB_MAX_CONTACTS", mrows, P.MR); return 0; }
+    LCK(cub::DeviceScan::ExclusiveSum(L.tmp, L.tmp_bytes, L.isl_nb, L.isl_bstart, NB + 1, s));
+    LCK(cub::DeviceScan::ExclusiveSum(L.tmp, L.tmp_bytes, L.isl_m, L.isl_rstart, NB + 1, s));
+    B->launches += 2;
+    if (nj > 0) {
+        LCK(cub::DeviceRadixSort::SortPairs(L.tmp, L.tmp_bytes, L.jkey, L.jkey_s, L.jmv, L.jmv_s, nj, 0, 64, s));
+        LCK(cub::DeviceScan::ExclusiveSum(L.tmp, L.tmp_bytes, L.jmv_s, L.jrow, nj, s));
+        B->launches += 2;
+    }
+    k_lw_joint_final<<<nblk(nj > 0 ? nj : 1, 256), 256, 0, s>>>(P, D, L, nj);
+    k_lw_island_info<<<nblk(T > 0 ? T : 1, 256), 256, 0, s>>>(P, D, L);
+    B->launches += 2;
+    // ---------------- QuickStep stages 0..3 (the batched path's kernels, W == 1)
+    k_body_pre<<<nblk(NB, 128), 128, 0, s>>>(P, D);
+    B->launches++;
+    if (hc[LWC_NJORD] > 0) { k_rows<<<nblk(hc[LWC_NJORD], 64), 64, 0, s>>>(P, D); B->launches++; }
+    LCK(cudaMemsetAsync(D.cforce, 0, (size_t)(NB + 1) * 2 * sizeof(Real4), s));
+    if (mrows > 0) {
+        k_rows_finish<<<nblk(mrows, 128), 128, 0, s>>>(P, D);
+        // body -> incident rows (CSR), built once per step; re-ranked by position for every phase
+        k_lw_inc_count<<<nblk(mrows, 256), 256, 0, s>>>(P, D, L, mrows);
+        LCK(cub::DeviceScan::ExclusiveSum(L.tmp, L.tmp_bytes, L.inc_cur, L.inc_ofs, NB + 1, s));
+        k_lw_zero_cur<<<nblk(NB + 1, 256), 256, 0, s>>>(NB + 1, L.inc_cur);
+        k_lw_inc_fill<<<nblk(mrows, 256), 256, 0, s>>>(P, D, L, mrows);
+        B->launches += 5;
+        // ---------------- SOR sweeps
+        cudaEvent_t e0 = 0, e1 = 0;
+        if (B->timing) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s); }
+        const int key_bits = 33 + bits_for((unsigned)(T > 0 ? T : 1));
+        int sweep_blocks = (mrows + 255) / 256;
+        { int cap = 148 * 8; if (sweep_blocks > cap) sweep_blocks = cap; }
+        Real exit_delta = P.premature_delta;
+        unsigned iteration = 0, extra = 0;
+        for (;;) {
+            if ((iteration & 7) == 0) {
+                if (iteration > 0) {
+                    LCK(cudaMemcpyAsync(hc, L.counters, sizeof(hc), cudaMemcpyDeviceToHost, s));
+                    LCK(cudaStreamSynchronize(s));
+                    if (hc[LWC_NACTIVE] == 0) break;
+                }
+                const int phase = (int)(iteration >> 3);
+                k_lw_order_keys<<<nblk(mrows, 256), 256, 0, s>>>(P, D, L, mrows, phase);
+                LCK(cub::DeviceRadixSort::SortPairs(L.tmp, L.tmp_bytes, L.okey, L.okey_s, L.oval, L.ord, mrows, 0, key_bits, s));
+                k_lw_runs<<<nblk(mrows, 256), 256, 0, s>>>(P, D, L, mrows, phase);
+                k_lw_tickets<<<nblk(nordered, 64), 64, 0, s>>>(P, D, L);
+                B->launches += 4;
+            }
+            k_lw_sweep<<<sweep_blocks, 256, 0, s>>>(P, D, L, mrows);
+            ++iteration;
+            int terminate_all = 0, in_extra = 0;
+            if (iteration - extra == P.num_iter) {          // quickstep.cpp:1832-1845
+                if (extra != 0 || P.max_extra == 0) { terminate_all = 1; in_extra = extra != 0; }
+                else { extra = P.max_extra; exit_delta = P.extra_delta; }
+            }
+            k_lw_body_check<<<nblk(nordered, 256), 256, 0, s>>>(P, D, L, exit_delta, (P.dyn_enabled && !terminate_all) ? 1 : 0);
+            k_lw_island_ctl<<<nblk(T, 256), 256, 0, s>>>(P, D, L, iteration, terminate_all, in_extra, exit_delta);
+            B->launches += 3;
+            if (terminate_all) break;
+        }
+        if (B->timing) { cudaEventRecord(e1, s); B->pending.push_back(std::make_pair(e0, e1)); }
+    }
+    k_lw_finish<<<1, 1, 0, s>>>(P, D, L);
+    k_integrate<<<nblk(NB, 128), 128, 0, s>>>(P, D);
+    B->launches += 2;
+    LCK(cudaGetLastError());
+    return 1;
+}

@@ -23,6 +23,20 @@
 #define ODEB_RING 8                                        // must stay 8: the row loop is unrolled by the ring depth
 #define ODEB_HALF_CHUNKS ((int)(sizeof(Real) * 16 / 16))   // 16-byte chunks per half record
 #define ODEB_WPW 16                                        // worlds per warp
+// lane -> (world in warp, side). Side = upper half-warp: the 8 lanes of one LDS.128 / STS.128 phase then belong to 8
+// different worlds (8 x 4 distinct banks), whereas interleaved sides (lane & 1) put both lanes of a world on the same
+// 4 banks with different accumulator slots -> 2-way conflict on every accumulator access.
+#if defined(ODEB_LANES_INTERLEAVED)
+#define LANE_WL(lane) ((lane) >> 1)
+#define LANE_SIDE(lane) ((lane) & 1)
+#define LANE_A(lane) ((lane) & ~1)
+#define ODEB_PARTNER 1
+#else
+#define LANE_WL(lane) ((lane) & 15)
+#define LANE_SIDE(lane) ((lane) >> 4)
+#define LANE_A(lane) ((lane) & 15)
+#define ODEB_PARTNER 16
+#endif
 
 struct HalfRegs { Real4 q0, q1, q2, q3; };
 // record of one row in HBM (8 Real4):
@@ -71,7 +85,7 @@ struct CfShared { Real4 *p; __device__ Real4 get(int i) const { return p[i * ODE
 
 __device__ __forceinline__ Real shfl_xor1(unsigned mask, Real v)
 {
-    return __shfl_xor_sync(mask, v, 1);
+    return __shfl_xor_sync(mask, v, ODEB_PARTNER);
 }
 
 __device__ __forceinline__ void load_half(HalfRegs &h, const uint4 *slot)
@@ -165,7 +179,7 @@ __device__ __forceinline__ void solve_islands_warp(const DevParams &P, unsigned 
                                                    unsigned long long &sweeps, unsigned long long &rowsweeps)
 {
     constexpr int CH = ODEB_HALF_CHUNKS;
-    const int wl = lane >> 1, side = lane & 1;
+    const int wl = LANE_WL(lane), side = LANE_SIDE(lane);
     uint4 *ring = (uint4 *)smem + lane;                                          // chunk (stage,c) at ring[(stage*CH+c)*32]
     unsigned char *p = smem + (size_t)ODEB_RING * CH * 32 * 16;
     Real4 *cf = (Real4 *)p + wl;  p += (size_t)2 * (P.NB + 1) * ODEB_WPW * sizeof(Real4);          // cf[k*16], k < 2*(NB+1)
@@ -242,7 +256,7 @@ __device__ __forceinline__ void solve_islands_warp(const DevParams &P, unsigned 
             if (side == 0) d = sweep_control(P, cfs, bstart, nb, iteration, extra, exit_delta, st1, st2, st3) ? 1 : 0;
         }
         __syncwarp();
-        d = __shfl_sync(ODEB_FULL, d, lane & ~1);
+        d = __shfl_sync(ODEB_FULL, d, LANE_A(lane));
         done |= d;
         if (__all_sync(ODEB_FULL, done)) break;
     }
@@ -283,8 +297,8 @@ __global__ void __launch_bounds__(32) k_solve(const __grid_constant__ DevParams 
 {
     extern __shared__ __align__(32) unsigned char smem[];
     const int lane = threadIdx.x;
-    const int side = lane & 1;
-    const int wraw = blockIdx.x * ODEB_WPW + (lane >> 1);
+    const int side = LANE_SIDE(lane);
+    const int wraw = blockIdx.x * ODEB_WPW + LANE_WL(lane);
     const bool valid = wraw < P.W;
     const int w = valid ? wraw : P.W - 1;          // lanes past the last world idle through the warp-wide loops
     unsigned seed = D.seed[w];
@@ -336,7 +350,7 @@ __global__ void __launch_bounds__(32) k_solve(const __grid_constant__ DevParams 
             }
         }
         __syncwarp();
-        seed = __shfl_sync(ODEB_FULL, seed, lane & ~1);     // lane B replays the same dRand stream in the shared-memory path
+        seed = __shfl_sync(ODEB_FULL, seed, LANE_A(lane));     // lane B replays the same dRand stream in the shared-memory path
         const int m_smem = (m > 0 && m <= P.SR) ? m : 0;
         if (__any_sync(ODEB_FULL, m_smem > 0))
             solve_islands_warp(P, smem, lane, rows, findex, rbody, cf_out, bstart, nb, rstart, m_smem, seed, st1, st2, st3, sweeps, rowsweeps);

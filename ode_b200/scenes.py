@@ -182,3 +182,38 @@ def ragdoll(nworlds=1, seed0=11, drop=0.25, max_contacts=3):
     sc.state = dict(pos=pos, quat=quat, lvel=lvel, avel=avel)
     sc.seeds = (seed0 + np.arange(nworlds)).astype(np.uint32)
     return sc
+
+
+def wall(width=500, height=200, max_contacts=4, ball=True, seed=21, space_type=B.SPACE_SAP, mu=0.5, jitter=0.0):
+    """Config 5: demo_crash.cpp:295-312-style brick wall scaled up, ONE world.
+
+    width x height unit boxes (WBOXSIZE 1, mass 1), every other course shifted by half a brick, laid along x (the
+    axis dSAP_AXES_XYZ sorts on) plus a cannon ball (sphere r=0.5, m=10, demo_crash.cpp:66-69) flying at the wall;
+    dSweepAndPruneSpace, g=(0,0,-1.5), CFM 1e-5, ERP 0.8, contact parameters of demo_crash.cpp:133-141
+    (Slip1|Slip2|SoftERP|SoftCFM|Approx1, mu=0.5, soft_erp 0.8, soft_cfm 0.01), <= 4 contacts per pair.
+    """
+    mode = B.CONTACT_SLIP1 | B.CONTACT_SLIP2 | B.CONTACT_SOFT_ERP | B.CONTACT_SOFT_CFM | B.CONTACT_APPROX1
+    sc = B.Scene(B.default_world_params(gravity=(0, 0, -1.5), cfm=1e-5, erp=0.8, max_contacts=max_contacts, surf_mode=mode,
+                                        mu=mu, slip1=0.0, slip2=0.0, soft_erp=0.8, soft_cfm=0.01, space_type=space_type), 1)
+    sc.add_geom(B.PLANE, (0, 0, 1, 0))
+    m, I = B.box_mass(1.0, 1, 1, 1)
+    r = _rng(seed)
+    for iz in range(height):
+        for ix in range(width):
+            j = jitter * (r.rand(2) - 0.5) if jitter else (0.0, 0.0)
+            b = sc.add_body(m, I, (ix + 0.5 * (iz % 2) + j[0], j[1], 0.5 + iz))
+            sc.add_geom(B.BOX, (1, 1, 1), body=b)
+    nb = sc.nbody
+    lvel = np.zeros((1, nb + (1 if ball else 0), 3))
+    if ball:
+        ms, Is = B.sphere_mass(1.0, 0.5)
+        ms, Is = 10.0, Is * (10.0 / ms)          # dMassAdjust(&m, CANNON_BALL_MASS)
+        b = sc.add_body(ms, Is, (0.5 * width, -6.0, 0.5 * min(height, 6) + 0.5))
+        sc.add_geom(B.SPHERE, (0.5,), body=b)
+        lvel[0, b] = (0.0, 30.0, 0.0)
+        nb += 1
+    pos = np.asarray(sc.body_pos)[None].copy()
+    quat = np.tile(np.array([1.0, 0, 0, 0])[None, None], (1, nb, 1))
+    sc.state = dict(pos=pos, quat=quat, lvel=lvel, avel=np.zeros_like(pos))
+    sc.seeds = np.asarray([seed], dtype=np.uint32)
+    return sc

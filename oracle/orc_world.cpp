@@ -69,6 +69,7 @@ struct World {
     std::vector<OrcContactGeom> last_cg;  // contact geoms of the last step (kept after dJointGroupEmpty)
     std::vector<int> island_label; int island_count;
     unsigned long long sweeps;
+    unsigned step_seed; int cur_island; unsigned long long draws;   // canonical mode bookkeeping
 };
 
 struct Batch {
@@ -80,6 +81,7 @@ struct Batch {
     Real adis_lin, adis_ang, adis_time; int adis_steps; unsigned adis_samples;
     Real damp_lin_scale, damp_ang_scale, damp_lin_thr, damp_ang_thr, max_ang_speed;
     int nbody, ngeom, njoint;
+    int canonical;                       // 1: canonical-order mode of the large-world path (see orc_set_solver_mode)
     std::vector<World> worlds;
 };
 
@@ -606,7 +608,7 @@ void quickstep_island(const Batch &B, World &W, const int *bodies, int nb, const
     int nj = (int)jl.size();
     const Real hrecip = rrecip(h);
     std::vector<Real> J, iMJ, lambda, cforce(6 * nb, 0), fa(2 * nb, 0), rhs_tmp(6 * nb);
-    std::vector<int> findex, jb, order, mindex(nj + 1);
+    std::vector<int> findex, jb, order, mindex(nj + 1), grp;
     if (m > 0) {
         // Stage1 :1364-1472
         mindex[0] = 0;
@@ -681,6 +683,27 @@ void quickstep_island(const Batch &B, World &W, const int *bodies, int nb, const
         {
             unsigned head = 0, tail = m - valid_findices;
             for (unsigned i = 0; i < m; i++) { if (findex[i] == -1) order[head++] = i; else order[tail++] = i; }
+            if (B.canonical) {
+                // canonical mode (include/ode_b200.h): row groups = the rows of the contacts of one geom pair / of one permanent
+                // joint; inside each of the two classes the rows are ordered by the phase-0 key of their group (ties by row index)
+                grp.resize(m);
+                const int npj = (int)W.pjoints.size();
+                for (int k = 0; k < nj; k++) {
+                    int first = mindex[k];
+                    if (k > 0 && jl[k] >= npj && jl[k - 1] >= npj) {
+                        int c = jl[k] - npj, cp = jl[k - 1] - npj;
+                        if (W.contact_g[2 * c] == W.contact_g[2 * cp] && W.contact_g[2 * c + 1] == W.contact_g[2 * cp + 1]) first = grp[mindex[k - 1]];
+                    }
+                    for (int r = mindex[k]; r < mindex[k + 1]; r++) grp[r] = first;
+                }
+                const unsigned nfree = m - valid_findices;
+                auto by_key = [&](int a, int b) {
+                    unsigned ka = odebi_canon_key(W.step_seed, (unsigned)W.cur_island, 0, (unsigned)grp[a]), kb = odebi_canon_key(W.step_seed, (unsigned)W.cur_island, 0, (unsigned)grp[b]);
+                    return ka != kb ? ka < kb : a < b;
+                };
+                std::sort(order.begin(), order.begin() + nfree, by_key);
+                std::sort(order.begin() + nfree, order.end(), by_key);
+            }
         }
         // iteration loop :1823-1856
         Real exit_delta = B.premature_delta;
@@ -688,6 +711,15 @@ void quickstep_island(const Batch &B, World &W, const int *bodies, int nb, const
         for (unsigned iteration = 0, extra = 0;;) {
             // IsSORConstraintsReorderRequiredForIteration :1080-1109 + ConstraintsShuffling :2578-2611
             if (iteration >= 8 && (iteration % 8) == 0) {
+                if (B.canonical) {
+                    // canonical mode: the permutation of phase k = rows sorted by the keyed hash of their group (ties by row index); the dRand
+                    // stream is advanced by the m-1 draws the reference's Fisher-Yates pass would have consumed (world_step)
+                    std::vector<std::pair<unsigned, unsigned> > kv(m);
+                    for (unsigned i = 0; i < m; i++) kv[i] = std::make_pair(odebi_canon_key(W.step_seed, (unsigned)W.cur_island, iteration / 8, (unsigned)grp[i]), i);
+                    std::stable_sort(kv.begin(), kv.end(), [](const std::pair<unsigned, unsigned> &a, const std::pair<unsigned, unsigned> &b) { return a.first < b.first; });
+                    for (unsigned i = 0; i < m; i++) order[i] = kv[i].second;
+                    W.draws += m - 1;
+                } else
                 for (unsigned idx = 1; idx < m; idx++) {
                     int sw = orc_rand_int(&W.seed, idx + 1);
                     int t = order[idx]; order[idx] = order[sw]; order[sw] = t;
@@ -785,11 +817,25 @@ void world_step(const Batch &B, World &W, Real h)
         for (int is = 0; is < W.island_count; is++) { for (int k = 0; k < isl.sizes[2 * is]; k++) W.island_label[isl.body[bo + k]] = is; bo += isl.sizes[2 * is]; }
     }
     size_t bo = 0, jo = 0;
+    if (B.canonical) {
+        // canonical order of the large-world path: island membership and numbering as the reference finds them, but inside an
+        // island bodies in descending creation index and joints in ascending id (permanent joints, then contacts in creation order)
+        for (int is = 0; is < W.island_count; is++) {
+            int nb = isl.sizes[2 * is], nj = isl.sizes[2 * is + 1];
+            std::sort(isl.body.begin() + bo, isl.body.begin() + bo + nb, [](int a, int b) { return a > b; });
+            std::sort(isl.joint.begin() + jo, isl.joint.begin() + jo + nj);
+            bo += nb; jo += nj;
+        }
+        bo = 0; jo = 0;
+        W.step_seed = W.seed; W.draws = 0;
+    }
     for (int is = 0; is < W.island_count; is++) {
         int nb = isl.sizes[2 * is], nj = isl.sizes[2 * is + 1];
+        W.cur_island = is;
         quickstep_island(B, W, &isl.body[bo], nb, nj ? &isl.joint[jo] : 0, nj, h);
         bo += nb; jo += nj;
     }
+    if (B.canonical) for (unsigned long long d = 0; d < W.draws; d++) orc_rand(&W.seed);
     W.last_cg.resize(W.contacts.size());
     for (size_t i = 0; i < W.contacts.size(); i++) W.last_cg[i] = W.contacts[i].cg;
     remove_contacts(W);
@@ -804,7 +850,7 @@ void *orc_create(const OdebWorldParams *wp, int nbody, const OdebBodyDesc *bodie
 {
     if (wp->surf_mode & (ODEB_CONTACT_FDIR1 | 0x400)) return 0;
     Batch *B = new Batch;
-    B->wp = *wp; B->nbody = nbody; B->ngeom = ngeom; B->njoint = njoint;
+    B->wp = *wp; B->nbody = nbody; B->ngeom = ngeom; B->njoint = njoint; B->canonical = 0;
     for (int k = 0; k < 3; k++) B->gravity[k] = (Real)wp->gravity[k];
     B->erp = (Real)wp->erp;
 #if defined(ODEB_DOUBLE)
@@ -931,6 +977,7 @@ int orc_add_force(void *h, const Real *force, const Real *torque)
     return 1;
 }
 
+int orc_set_solver_mode(void *h, int mode) { ((Batch *)h)->canonical = mode == ODEB_MODE_CANONICAL; return 1; }
 int orc_set_seeds(void *h, const uint32_t *s) { Batch *B = (Batch *)h; for (size_t w = 0; w < B->worlds.size(); w++) B->worlds[w].seed = s[w]; return 1; }
 int orc_get_seeds(void *h, uint32_t *s) { Batch *B = (Batch *)h; for (size_t w = 0; w < B->worlds.size(); w++) s[w] = B->worlds[w].seed; return 1; }
 int orc_get_enabled(void *h, int *en)

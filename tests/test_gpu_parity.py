@@ -141,3 +141,60 @@ def test_capacity_overflow_is_reported():
         del os.environ["ODEB_MAX_CONTACTS"]
     with pytest.raises(RuntimeError):
         b.step(0.02, 40)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# large-world path (ODEB_MODE_CANONICAL): sort/scan/union-find pipeline + ticketed sweeps against the oracle run in the
+# same mode. Integer observables identical; floats bit-identical for scenes without libm calls.
+def _canon_pair(prec, sc):
+    a, b = B.Batch(orc_lib(prec), sc), B.Batch(gpu_lib(prec), sc)
+    a.set_solver_mode(1)
+    b.set_solver_mode(1)
+    return a, b
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_canonical_mode_bit_exact(prec):
+    cases = ((lambda: scenes.wall(12, 8, max_contacts=8), 0.05, 40),                     # one island, SAP space, cannon ball hits at ~step 8
+             (lambda: scenes.wall(9, 5, max_contacts=8, space_type=B.SPACE_HASH, ball=False), 0.05, 25),
+             (lambda: scenes.free_boxes(1, 100, grid=10), 0.01, 40),                      # 100 one-body islands
+             (lambda: scenes.box_stack(nworlds=1, nboxes=16), 0.02, 120),                 # auto-disable + re-enable path
+             (lambda: scenes.chain(1), 0.05, 60))                                         # permanent joints
+    for mk, h, n in cases:
+        sc = mk()
+        a, b = _canon_pair(prec, sc)
+        for s in range(n):
+            a.step(h)
+            b.step(h)
+            bad = compare_step(a, b, 1)
+            assert not bad, (s, bad)
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_canonical_mode_teacher_forced(prec):
+    """Scenes with cullPoints/atan2 (<= 4 contacts per box pair) and hinge angles: teacher-forced single steps."""
+    for mk, h, targets in ((lambda: scenes.pile(nbodies=1000), 0.01, (0, 40, 80)),
+                           (lambda: scenes.pile(nbodies=512, space_type=B.SPACE_SAP), 0.01, (0, 60)),
+                           (lambda: scenes.wall(30, 20), 0.05, (0, 12)),
+                           (lambda: scenes.ragdoll(1), 0.01, (0, 50))):
+        sc = mk()
+        a, b = _canon_pair(prec, sc)
+        done = 0
+        for target in targets:
+            a.step(h, target - done)
+            done = target
+            st = a.get_state()
+            b.set_state(**st)
+            b.set_seeds(a.get_seeds())
+            a.set_state(**st)
+            a.step(h)
+            b.step(h)
+            done += 1
+            bad = compare_step(a, b, 1, exact_float=False, tol=TOL[prec], what=("pairs", "contacts", "islands", "seeds", "state"))
+            assert not bad, (target, bad)
+
+
+def test_canonical_mode_needs_single_world():
+    b = B.Batch(gpu_lib("single"), scenes.box_stack(nworlds=2, nboxes=4))
+    with pytest.raises(RuntimeError):
+        b.set_solver_mode(1)
