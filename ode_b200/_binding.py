@@ -287,7 +287,12 @@ class Batch:
     def step(self, h, nsteps=1):
         ok = self.slib._fn("step")(self.h, float(h), int(nsteps))
         if not ok:
-            raise RuntimeError("%sstep failed" % self.slib.prefix)
+            msg = ""
+            if self.slib.has("last_error"):
+                fn = self.slib._fn("last_error")
+                fn.restype = C.c_char_p
+                msg = ": " + (fn() or b"").decode()
+            raise RuntimeError("%sstep failed%s" % (self.slib.prefix, msg))
 
     def get_totals(self):
         """[pairs, contacts, rows, islands, sweeps, row-sweeps] of the most recent step, summed over worlds"""

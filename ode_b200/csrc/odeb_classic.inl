@@ -1187,7 +1187,7 @@ int dWorldQuickStep(dWorldID w, Real stepsize)
     unsigned seed = (unsigned)g_seed, st0[4] = { 0, 0, 0, 0 }, st1[4];
     CK(cudaMemcpy(D.seed, &seed, sizeof(unsigned), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(D.stats, st0, sizeof(st0), cudaMemcpyHostToDevice));
-    launch_dynamics(B, B->stream, false);
+    launch_dynamics(B, B->stream, false, choose_solver(B));
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(B->stream));
     {

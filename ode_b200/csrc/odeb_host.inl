@@ -25,8 +25,12 @@ struct OdebBatch {
     Real4 *d_stage; size_t stage_elems;
     Real4 *h_stage;
     // cuda graph of one step
-    cudaGraphExec_t graph; double graph_h; bool use_graph;
+    cudaGraphExec_t graph; double graph_h; bool use_graph; int graph_cfg;
+    // solver selection: 0 = k_solve (one row at a time per world), 1..3 = k_solve5<2/4/8> (static P-processor schedule),
+    // 4 = k_solve_bl (one lane per body). hint_m = largest island (rows) seen since the last sync, read back in odeb_sync.
+    int s5_sr[4]; size_t s5_smem[4]; int hint_m; int solver_force;
     size_t solve_smem;
+    int bl_G, bl_SR; size_t bl_smem;          // body-lane solver (odeb_solve_bl.cuh): lanes per world (0 = not used), row budget, bytes per warp
     void *flush_buf; size_t flush_bytes;
     // large-world path (ODEB_MODE_CANONICAL, odeb_large_host.inl)
     int mode; LargePtrs L; bool large_ready;
@@ -251,7 +255,7 @@ static OdebBatch *batch_build(const OdebWorldParams *wp, const HostTemplate &T, 
     OdebBatch *B = new OdebBatch();
     B->device = device; B->bytes = 0; B->launches = 0; B->timing = false; B->solver_ms = 0; B->solver_launches = 0;
     B->mode = ODEB_MODE_REPLAY; B->large_ready = false; memset(&B->L, 0, sizeof(B->L));
-    B->graph = 0; B->graph_h = -1; B->use_graph = getenv("ODEB_NO_GRAPH") == 0 && !classic; B->h_stage = 0; B->d_stage = 0; B->stream = 0; B->flush_buf = 0; B->flush_bytes = 0;
+    B->graph = 0; B->graph_h = -1; B->graph_cfg = -1; B->hint_m = 0; B->solver_force = -1; B->use_graph = getenv("ODEB_NO_GRAPH") == 0 && !classic; B->h_stage = 0; B->d_stage = 0; B->stream = 0; B->flush_buf = 0; B->flush_bytes = 0;
     memset(&B->D, 0, sizeof(B->D));
     DevParams &P = B->P;
     memset(&P, 0, sizeof(P));
@@ -290,6 +294,43 @@ static OdebBatch *batch_build(const OdebWorldParams *wp, const HostTemplate &T, 
         P.SR = sr;
         if (P.SR == 0) B->solve_smem = 0;
     }
+    {   // body-lane solver: one lane per body, G lanes per world. Row budget sized so that at least `want` warps are resident per SM.
+        B->bl_G = 0; B->bl_SR = 0; B->bl_smem = 0;
+        const char *sel = getenv("ODEB_SOLVER");
+        if (sel && strcmp(sel, "bl") == 0 && P.NB <= 32) {
+            const int G = P.NB <= 8 ? 8 : P.NB <= 16 ? 16 : 32;
+            int sr = P.MR < ODEB_BL_MAXROWS ? P.MR : ODEB_BL_MAXROWS;
+            const size_t budget = (size_t)(227 * 1024) / (sizeof(Real) == 4 ? 14 : 7) - 1024;   // 14 (single) / 7 (double) resident warps per SM; 1 KB per block is reserved by the system
+            while (sr > 64 && odeb_bl_smem(G, sr) > budget) sr -= 8;
+            if (const char *s = getenv("ODEB_BL_ROWS")) { sr = atoi(s); if (sr > ODEB_BL_MAXROWS) sr = ODEB_BL_MAXROWS; if (sr < 1) sr = 1; }
+            B->bl_G = G; B->bl_SR = sr; B->bl_smem = odeb_bl_smem(G, sr);
+        }
+    }
+
+    {   // k_solve5<P>: row capacity that fits when every warp of the batch is resident at once
+        cudaDeviceProp prop; int nsm = 148;
+        if (cudaGetDeviceProperties(&prop, device) == cudaSuccess && prop.multiProcessorCount > 0) nsm = prop.multiProcessorCount;
+        for (int k = 1; k <= 3; k++) {
+            const int Pk = 1 << k;
+            B->s5_sr[k] = 0; B->s5_smem[k] = 0;
+            if (P.NB > ODEB5_MAXBODIES) continue;
+            const long long warps = ((long long)nworlds + (16 / Pk) - 1) / (16 / Pk);
+            long long per_sm = (warps + nsm - 1) / nsm;
+            if (per_sm > 32) per_sm = 32;
+            const size_t budget = (size_t)(227 * 1024) / (size_t)per_sm - 1024;
+            int sr = P.MR < 1023 ? P.MR : 1023;
+            while (sr >= 16 && odeb5_smem(Pk, P.NB, sr) > budget) sr -= 4;
+            if (sr < 16) continue;
+            B->s5_sr[k] = sr; B->s5_smem[k] = odeb5_smem(Pk, P.NB, sr);
+        }
+        if (const char *sel = getenv("ODEB_SOLVER")) {
+            if (!strcmp(sel, "v4")) B->solver_force = 0;
+            else if (!strcmp(sel, "p2")) B->solver_force = 1;
+            else if (!strcmp(sel, "p4")) B->solver_force = 2;
+            else if (!strcmp(sel, "p8")) B->solver_force = 3;
+            else if (!strcmp(sel, "bl")) B->solver_force = 4;
+        }
+    }
 
     // ---- device buffers
     DevPtrs &D = B->D;
@@ -316,13 +357,35 @@ static OdebBatch *batch_build(const OdebWorldParams *wp, const HostTemplate &T, 
             && dev_alloc(B, &D.island_info, WB) && dev_alloc(B, &D.nislands, W) && dev_alloc(B, &D.nordered, W) && dev_alloc(B, &D.njord, W) && dev_alloc(B, &D.mrows, W);
     ok = ok && dev_alloc(B, &D.rows, W * P.MR * 8) && dev_alloc(B, &D.rbody, W * P.MR) && dev_alloc(B, &D.findex, W * P.MR) && dev_alloc(B, &D.order, W * P.MR)
             && dev_alloc(B, &D.lambda, W * P.MR) && dev_alloc(B, &D.cforce, W * (nbody + 1) * 2) && dev_alloc(B, &D.invIw, WB * 12)
-            && dev_alloc(B, &D.stats, W * 4) && dev_alloc(B, &D.seed, W) && dev_alloc(B, &D.sweeps, 2 * W) && dev_alloc(B, &D.overflow, 1);
+            && dev_alloc(B, &D.stats, W * 4) && dev_alloc(B, &D.seed, W) && dev_alloc(B, &D.sweeps, 2 * W) && dev_alloc(B, &D.overflow, 2);
     B->stage_elems = WB;
     ok = ok && dev_alloc(B, &B->d_stage, WB);
     if (ok && cudaMallocHost((void **)&B->h_stage, WB * sizeof(Real4)) != cudaSuccess) { set_err("cudaMallocHost failed"); ok = false; }
     if (ok && cudaStreamCreateWithFlags(&B->stream, cudaStreamNonBlocking) != cudaSuccess) { set_err("cudaStreamCreate failed"); ok = false; }
-    if (ok && B->solve_smem > 48 * 1024) {
-        if (cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B->solve_smem) != cudaSuccess) { set_err("cudaFuncSetAttribute(smem=%zu) failed", B->solve_smem); ok = false; }
+    if (ok) {   // opt every solver kernel into the full 227 KB of shared memory once (the attribute is per function, not per batch)
+        const int mx = 227 * 1024;
+        cudaError_t ce = cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_solve5<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_solve5<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_solve5<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_solve_bl<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_solve_bl<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_solve_bl<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        if (ce != cudaSuccess) { set_err("cudaFuncSetAttribute(max dynamic shared memory) failed: %s", cudaGetErrorString(ce)); ok = false; }
+        // the solvers live on shared memory and never reuse a global line through L1: ask for the largest carveout
+        cudaFuncSetAttribute(k_solve, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_solve5<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_solve5<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_solve5<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_solve_bl<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_solve_bl<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_solve_bl<32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (getenv("ODEB_DEBUG")) {
+            int nb0 = 0, nb4 = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb0, k_solve, 32, B->solve_smem);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb4, k_solve5<4>, 32, B->s5_smem[2]);
+            fprintf(stderr, "[odeb] k_solve: SR=%d smem=%zu blocks/SM=%d | k_solve5<4>: SR=%d smem=%zu blocks/SM=%d\n", P.SR, B->solve_smem, nb0, B->s5_sr[2], B->s5_smem[2], nb4);
+        }
     }
     if (!ok) { odeb_destroy(B); return 0; }
 
@@ -538,7 +601,28 @@ static void launch_collide(OdebBatch *B, cudaStream_t s, bool narrow)
     if (narrow) { k_narrow<<<nblk(W * P.MP, 64), 64, 0, s>>>(P, D); B->launches++; }
 }
 
-static void launch_dynamics(OdebBatch *B, cudaStream_t s, bool timed)
+// Which solver kernel the next step uses. k_solve5<P> needs every island to fit its shared-memory row budget; the largest
+// island of the previous call (hint_m) decides, so the first call after creation runs k_solve.
+static int choose_solver(const OdebBatch *B)
+{
+    const int f = B->solver_force;
+    if (f == 0) return 0;
+    if (f == 4) return B->bl_G ? 4 : 0;
+    if (f >= 1 && f <= 3) return B->s5_sr[f] > 0 ? f : 0;
+    if (B->hint_m <= 0) return 0;
+    // Measured on B200 (4096 x 16-box stacks, single; solver ms for W = 1024 / 2048 / 4096 worlds): k_solve 1.19 / 1.19 / 1.26,
+    // k_solve5<4> 0.73 / 0.90 / 1.30, k_solve5<8> 0.78 / - / -, k_solve5<2> - / - / 1.40.  With more than ~3.5 warps per SM the
+    // extra warps of the P-processor schedule contend for the SM's shared-memory pipe and the gain is gone, so P = 4 is used
+    // while the batch needs at most that many warps and every island fits its row budget.
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, B->device);
+    const long long warps4 = ((long long)B->P.W + 3) / 4;
+    const int need = B->hint_m + B->hint_m / 8 + 8;
+    if (warps4 * 2 <= 7LL * nsm && B->s5_sr[2] >= need) return 2;
+    return 0;
+}
+
+static void launch_dynamics(OdebBatch *B, cudaStream_t s, bool timed, int cfg)
 {
     const DevParams &P = B->P; const DevPtrs &D = B->D;
     const size_t W = P.W;
@@ -549,16 +633,26 @@ static void launch_dynamics(OdebBatch *B, cudaStream_t s, bool timed)
     k_rows_finish<<<nblk(W * P.MR, 128), 128, 0, s>>>(P, D);
     cudaEvent_t e0 = 0, e1 = 0;
     if (timed) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s); }
-    k_solve<<<nblk(W, ODEB_WPW), 32, B->solve_smem, s>>>(P, D);
+    switch (cfg) {
+    case 1: k_solve5<2><<<nblk(W, 8), 32, B->s5_smem[1], s>>>(P, D, B->s5_sr[1]); break;
+    case 2: k_solve5<4><<<nblk(W, 4), 32, B->s5_smem[2], s>>>(P, D, B->s5_sr[2]); break;
+    case 3: k_solve5<8><<<nblk(W, 2), 32, B->s5_smem[3], s>>>(P, D, B->s5_sr[3]); break;
+    case 4:
+        if (B->bl_G == 8) k_solve_bl<8><<<nblk(W, 4), 32, B->bl_smem, s>>>(P, D, B->bl_SR);
+        else if (B->bl_G == 16) k_solve_bl<16><<<nblk(W, 2), 32, B->bl_smem, s>>>(P, D, B->bl_SR);
+        else k_solve_bl<32><<<nblk(W, 1), 32, B->bl_smem, s>>>(P, D, B->bl_SR);
+        break;
+    default: k_solve<<<nblk(W, ODEB_WPW), 32, B->solve_smem, s>>>(P, D);
+    }
     if (timed) { cudaEventRecord(e1, s); B->pending.push_back(std::make_pair(e0, e1)); }
     k_integrate<<<nblk(W * P.NB, 128), 128, 0, s>>>(P, D);
     B->launches += 6;
 }
 
-static int launch_step(OdebBatch *B, cudaStream_t s, bool timed)
+static int launch_step(OdebBatch *B, cudaStream_t s, bool timed, int cfg)
 {
     launch_collide(B, s, true);
-    launch_dynamics(B, s, timed);
+    launch_dynamics(B, s, timed, cfg);
     return 1;
 }
 
@@ -572,23 +666,24 @@ int odeb_step_async(OdebBatch *B, double h, int nsteps)
         return 1;
     }
     const bool graph_ok = B->use_graph && !B->timing;
-    if (graph_ok && (B->graph == 0 || B->graph_h != h)) {
+    const int cfg = choose_solver(B);
+    if (graph_ok && (B->graph == 0 || B->graph_h != h || B->graph_cfg != cfg)) {
         if (B->graph) { cudaGraphExecDestroy(B->graph); B->graph = 0; }
         cudaGraph_t g = 0;
         uint64_t l0 = B->launches;
         CK(cudaStreamBeginCapture(B->stream, cudaStreamCaptureModeThreadLocal));
-        launch_step(B, B->stream, false);
+        launch_step(B, B->stream, false, cfg);
         CK(cudaStreamEndCapture(B->stream, &g));
         B->launches = l0;
         CK(cudaGraphInstantiate(&B->graph, g, 0));
         cudaGraphDestroy(g);
-        B->graph_h = h;
+        B->graph_h = h; B->graph_cfg = cfg;
     }
     for (int s = 0; s < nsteps; s++) {
         if (graph_ok) {
             CK(cudaGraphLaunch(B->graph, B->stream));
             B->launches += (B->P.NG > 0 ? 5 : 0) + (B->P.NJ > 0 ? 1 : 0) + 6;
-        } else launch_step(B, B->stream, B->timing);
+        } else launch_step(B, B->stream, B->timing, cfg);
     }
     CK(cudaGetLastError());
     return 1;
@@ -605,8 +700,10 @@ int odeb_sync(OdebBatch *B)
         cudaEventDestroy(B->pending[i].first); cudaEventDestroy(B->pending[i].second);
     }
     B->pending.clear();
-    int ov = 0;
-    CK(cudaMemcpy(&ov, B->D.overflow, sizeof(int), cudaMemcpyDeviceToHost));
+    int ovh[2] = { 0, 0 };
+    CK(cudaMemcpy(ovh, B->D.overflow, sizeof(ovh), cudaMemcpyDeviceToHost));
+    if (ovh[1] > 0) { B->hint_m = ovh[1]; CK(cudaMemset(B->D.overflow + 1, 0, sizeof(int))); }
+    const int ov = ovh[0];
     if (ov) {
         set_err("capacity overflow (%s): raise ODEB_MAX_PAIRS / ODEB_MAX_CONTACTS", ov == 1 ? "pairs" : ov == 2 ? "contacts" : "rows");
         cudaMemset(B->D.overflow, 0, sizeof(int));

@@ -96,7 +96,7 @@ struct DevPtrs {
     Real *invIw;                                 // [W*NB*12], indexed by order position
     unsigned *stats, *seed;                      // [W*4], [W]
     unsigned long long *sweeps;                  // [W*2] = (sweeps, row-sweeps) of the last step
-    int *overflow;                               // [1] capacity overflow flag
+    int *overflow;                               // [2] capacity overflow flag, largest island (rows) since the host last looked
 };
 
 __device__ __forceinline__ Real4 ld4(const Real4 *p) { return *p; }
@@ -383,6 +383,7 @@ __global__ void k_islands(const __grid_constant__ DevParams P, const __grid_cons
         }
         if (rstart + mi > P.MR) { atomicExch(D.overflow, 3); mi = 0; }
         iinfo[nis] = make_int4(bstart, nbo - bstart, rstart, mi);
+        if (mi > 0) atomicMax(D.overflow + 1, mi);          // largest island of the call: the host picks the solver kernel from it
         rows += mi;
         nis++;
     }
@@ -595,6 +596,8 @@ __global__ void k_rows_finish(const __grid_constant__ DevParams P, const __grid_
 }
 
 #include "odeb_solve.cuh"
+#include "odeb_solve_bl.cuh"
+#include "odeb_solve5.cuh"
 #include "odeb_large.cuh"
 
 // ------------------------------------------------------------------------------------------------

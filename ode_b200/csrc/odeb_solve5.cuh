@@ -1,0 +1,326 @@
+// odeb_solve5.cuh -- k_solve5<P>: the SOR-LCP sweeps of dxQuickStepIsland with P row processors per world
+// (quickstep.cpp:1823-1856 loop, :2329-2355 ReorderPrep, :2578-2611 random reorder via dRandInt,
+//  :2917-3033 IterationStep, :3253-3285 dynamic iteration control).
+//
+// k_solve (odeb_solve.cuh) runs one row at a time per world: with a few thousand worlds the GPU holds every world
+// at once and the step time is the length of the per-world dependency chain (m rows x N sweeps x ~420 cycles).
+// The reference's sequential sweep only orders rows that share a body (a row reads and writes the accumulators
+// of its two bodies and lambda of its own contact), so rows on disjoint bodies may run side by side with
+// bit-identical results.  This kernel gives every world P lane pairs ("processors") and a STATIC schedule:
+//   * after ReorderPrep and after every dRand reorder, the world's leader lane list-schedules the solve order
+//     onto P in-order processors: slot(row) = first slot after the latest earlier row on either of its bodies in
+//     which a processor is free.  The schedule is reused for the 8 sweeps until the next reorder;
+//   * a sweep then is `nslots` lockstep slots (16-box stack: 136 for the initial order, ~52 after a shuffle for
+//     P = 4, instead of 192), each slot the row update of k_solve: two lanes per row (body-1 / body-2 halves,
+//     one shuffle), accumulators + lambda in shared memory, half records through a per-lane cp.async ring that runs
+//     along the lane's own schedule column.  The ring is only 4 stages deep (shared memory is what limits the number of
+//     resident warps), which covers an L2 hit but not a DRAM miss, and with 64 sectors per slot and warp some sector
+//     misses in nearly every slot; so every lane also issues prefetch.global.L2 for the record it will need ODEB5_FAR
+//     slots later.  Idle slots carry the dummy body and have their copies and stores predicated off.
+// Lane layout: side = lane >> 4, column = lane & 15 = proc * WPW + world (WPW = 16 / P worlds per warp).
+// One order / meta entry: row (bits 0..9) | friction row (10..19) | body-1 slot (20..25) | body-2 slot (26..31).
+#ifndef ODEB_SOLVE5_CUH
+#define ODEB_SOLVE5_CUH
+
+#define ODEB5_RING 4                                       // must stay 4: the slot loop is unrolled by the ring depth
+#ifndef ODEB5_FAR
+#define ODEB5_FAR 12                                       // L2 prefetch distance in slots
+#endif
+#define ODEB5_PAD (ODEB5_RING + ODEB5_FAR + 4)
+#ifndef ODEB5_EXP_CH
+#define ODEB5_EXP_CH CH                                     // timing experiments only: copy fewer chunks per record
+#endif
+#define ODEB5_MAXBODIES 62
+#define E5_ROW(e) ((int)((e) & 0x3ffu))
+#define E5_FI(e) ((int)(((e) >> 10) & 0x3ffu))
+#define E5_B1(e) ((int)(((e) >> 20) & 63u))
+#define E5_B2(e) ((int)((e) >> 26))
+
+// shared memory per warp for a capacity of sr rows (= schedule slots) per island
+__host__ __device__ inline size_t odeb5_smem(int P, int NB, int sr)
+{
+    const int wpw = 16 / P;
+    size_t b = (size_t)ODEB5_RING * ODEB_HALF_CHUNKS * 32 * 16;              // ring
+    b += (size_t)2 * (NB + 1) * wpw * sizeof(Real4);                          // accumulators
+    b += (size_t)(sr + 1) * wpw * sizeof(Real);                               // lambda
+    b = (b + 15) / 16 * 16;
+    b += (size_t)(sr + ODEB5_PAD) * 16 * sizeof(unsigned);                    // schedule columns
+    b += (size_t)sr * wpw * sizeof(unsigned);                                 // solve order
+    b += (size_t)(NB + 1) * wpw * sizeof(unsigned short);                     // scheduler: last slot per body
+    return (b + 31) / 32 * 32;
+}
+
+// accumulator vector j (0/1) of body slot b for world wl: the 16-byte unit inside the body's 8 (WPW = 4) units is rotated
+// by a bit of the body index, so that two processors of one world meet in the same bank group half as often
+#define CF5(b, j) cf[(size_t)(b) * (2 * WPW) + ((((j) * WPW) + (((b) & 1) * WPW)) & (2 * WPW - 1))]
+
+template <int WPW> struct CfShared5 {     // element i = vector (i & 1) of body slot (i >> 1), see CF5
+    Real4 *cf;
+    __device__ Real4 get(int i) const { return CF5(i >> 1, i & 1); }
+    __device__ void set(int i, const Real4 &v) { CF5(i >> 1, i & 1) = v; }
+};
+
+#if defined(ODEB5_NOFAR)
+__device__ __forceinline__ void prefetch_l2(const void *) {}
+#else
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
+#endif
+
+// One schedule slot.  CUR/NXT: register sets of the software pipeline; MT: this slot's entry; MTN: next slot's (loaded here);
+// ma: entry RING-1 slots ahead (its cp.async is issued here), mf: entry FAR slots ahead (L2 prefetch).
+#define ODEB5_ROW(CUR, NXT, MT, MTN, K)                                                                                  \
+    {                                                                                                                    \
+        const int index = E5_ROW(MT), fi = E5_FI(MT), b1 = E5_B1(MT);                                                    \
+        const bool live = b1 != NBd;                                                                                     \
+        const int bs = side ? E5_B2(MT) : b1;                                                                            \
+        const Real old_lambda = lam[index * WPW];                                                                        \
+        const Real lam_fi = lam[fi * WPW];                                                                               \
+        Real4 fa = CF5(bs, 0), fb = CF5(bs, 1);                                                                          \
+        MTN = mp[((K) + 1) * 16];                                                                                        \
+        {                                                                                                                \
+            if (E5_B1(ma) != NBd) {                                                                                      \
+                const char *src = rec_base + (size_t)E5_ROW(ma) * (sizeof(Real) * 32);                                   \
+                const unsigned dst = ring_addr + (unsigned)((((K) + ODEB5_RING - 1) & (ODEB5_RING - 1)) * CH * 32 * 16); \
+                _Pragma("unroll") for (int c = 0; c < ODEB5_EXP_CH; c++) cp_async16(dst + c * 32 * 16, src + c * 16);   \
+            }                                                                                                            \
+            cp_async_commit();                                                                                           \
+            if (E5_B1(mf) != NBd) prefetch_l2(rec_base + (size_t)E5_ROW(mf) * (sizeof(Real) * 32));                      \
+        }                                                                                                                \
+        ma = mp[((K) + ODEB5_RING) * 16];                               /* schedule entries for the next slot's copies */ \
+        mf = mp[((K) + 1 + ODEB5_FAR) * 16];                                                                             \
+        const Real lo_b = shfl_xor1(ODEB_FULL, CUR.q1.z);               /* lane A receives lo from lane B */             \
+        const Real s = fa.x * CUR.q0.x + fa.y * CUR.q0.y + fa.z * CUR.q0.z + fa.w * CUR.q0.w + fb.x * CUR.q1.x + fb.y * CUR.q1.y; \
+        const Real ta = (CUR.q1.z - old_lambda * CUR.q1.w) - s;         /* lane A: (rhs - lambda*cfm) - s1 */           \
+        const Real mine = side ? s : ta;                                                                                 \
+        const Real other = shfl_xor1(ODEB_FULL, mine);                                                                   \
+        cp_async_wait<ODEB5_RING - 2>();                                                                                 \
+        load_half(NXT, ring + (size_t)(((K) + 1) & (ODEB5_RING - 1)) * CH * 32);                                        \
+        Real delta = side ? (other - mine) : (mine - other);            /* ((rhs - lambda*cfm) - s1) - s2 */             \
+        const Real hi = side ? CUR.q1.w : CUR.q3.w;                                                                      \
+        const Real lo = side ? CUR.q1.z : lo_b;                                                                          \
+        const bool hasfi = fi != index;                                                                                  \
+        const Real hi_f = RFABS(hi * lam_fi);                                                                            \
+        const Real hi_act = hasfi ? hi_f : hi;                                                                           \
+        const Real lo_act = hasfi ? -hi_f : lo;                                                                          \
+        Real new_lambda = old_lambda + delta;                                                                            \
+        const bool c_lo = new_lambda < lo_act;                                                                           \
+        const bool c_hi = !c_lo && (new_lambda > hi_act);                                                                \
+        const Real lim = c_lo ? lo_act : hi_act;                                                                         \
+        if (c_lo || c_hi) { delta = lim - old_lambda; new_lambda = lim; }                                                \
+        const bool pos = delta > 0;                                                                                      \
+        fa.x += delta * CUR.q2.x; fa.y += delta * CUR.q2.y; fa.z += delta * CUR.q2.z; fa.w += delta * CUR.q2.w;          \
+        fb.x += delta * CUR.q3.x; fb.y += delta * CUR.q3.y;                                                              \
+        {                                                                                                                \
+            const Real t1 = delta * CUR.q3.z;                                                                            \
+            const Real pv = fb.w + t1, nv = fb.z + t1;                                                                   \
+            fb.w = pos ? pv : fb.w; fb.z = pos ? fb.z : nv;                                                              \
+        }                                                                                                                \
+        if (live) {                                                                                                      \
+            if (side == 0) lam[index * WPW] = new_lambda;                                                                \
+            CF5(bs, 0) = fa; CF5(bs, 1) = fb;                                                                            \
+        }                                                                                                                \
+        __syncwarp();                                                                                                    \
+    }
+
+template <int P>
+__global__ void __launch_bounds__(32) k_solve5(const __grid_constant__ DevParams Pm, const __grid_constant__ DevPtrs D, const int SR5)
+{
+    extern __shared__ __align__(32) unsigned char smem[];
+    constexpr int WPW = 16 / P;
+    constexpr int CH = ODEB_HALF_CHUNKS;
+    const int lane = threadIdx.x;
+    const int side = lane >> 4, col = lane & 15;
+    const int wl = col & (WPW - 1), proc = col / WPW;
+    const int wid = lane / WPW;                                   // index of the lane among its world's 2P lanes
+    const unsigned wmask = ((WPW == 1) ? 0xffffffffu : (WPW == 2) ? 0x55555555u : (WPW == 4) ? 0x11111111u : 0x01010101u) << wl;
+    const unsigned below = (1u << lane) - 1u;
+    const bool leader = (proc == 0) && (side == 0);               // lane index == wl
+    const int NBd = Pm.NB;                                        // dummy accumulator slot
+    const int wraw = blockIdx.x * WPW + wl;
+    const bool valid = wraw < Pm.W;
+    const int w = valid ? wraw : Pm.W - 1;
+
+    // ---- shared memory
+    uint4 *ring = (uint4 *)smem + lane;                           // chunk (stage, c) at ring[(stage * CH + c) * 32]
+    const unsigned ring_addr = (unsigned)__cvta_generic_to_shared(ring);
+    unsigned char *p = smem + (size_t)ODEB5_RING * CH * 32 * 16;
+    Real4 *cf = (Real4 *)p + wl;    p += (size_t)2 * (Pm.NB + 1) * WPW * sizeof(Real4);        // cf[k * WPW]
+    Real *lam = (Real *)p + wl;     p += (size_t)(SR5 + 1) * WPW * sizeof(Real);                // lam[i * WPW]
+    p = smem + ((size_t)(p - smem) + 15) / 16 * 16;
+    unsigned *meta = (unsigned *)p; p += (size_t)(SR5 + ODEB5_PAD) * 16 * sizeof(unsigned);     // meta[slot * 16 + col]
+    unsigned *order = (unsigned *)p + wl; p += (size_t)SR5 * WPW * sizeof(unsigned);            // order[i * WPW]
+    unsigned short *last = (unsigned short *)p + wl;                                            // last[body * WPW]
+    const unsigned IDLE = ((unsigned)NBd << 20) | ((unsigned)NBd << 26);
+
+    unsigned seed = D.seed[w];
+    unsigned st0 = 0, st1 = 0, st2 = 0, st3 = 0;
+    unsigned long long sweeps = 0, rowsweeps = 0;
+    const Real4 *rows = D.rows + (size_t)w * Pm.MR * 8;
+    const int *findex = D.findex + (size_t)w * Pm.MR;
+    const int2 *rbody = D.rbody + (size_t)w * Pm.MR;
+    Real4 *cf_out = D.cforce + (size_t)w * (Pm.NB + 1) * 2;
+    const int4 *iinfo = D.island_info + (size_t)w * Pm.NB;
+    const int nis = valid ? D.nislands[w] : 0;
+    const int nis_max = __reduce_max_sync(ODEB_FULL, nis);
+    // every schedule column starts idle (shared memory is not cleared between kernels; lanes of worlds that never solve an
+    // island still walk their column)
+    if (side == 0) for (int s = 0; s < SR5 + ODEB5_PAD; s++) meta[s * 16 + col] = IDLE;
+    __syncwarp();
+    int fill = 0;                                                 // slots of this world's columns that may hold entries
+
+    for (int is = 0; is < nis_max; is++) {
+        int4 info = make_int4(0, 0, 0, 0);
+        if (is < nis) { info = iinfo[is]; if (leader) st0++; }
+        const int bstart = info.x, nb = info.y, rstart = info.z, m = info.w;
+        const bool big = m > SR5;
+        if (big && leader) solve_island_serial(Pm, D, w, bstart, nb, rstart, m, seed, st1, st2, st3, sweeps, rowsweeps);
+        __syncwarp();
+        const int m_own = (m > 0 && !big) ? m : 0;
+        const int m_max = __reduce_max_sync(ODEB_FULL, m_own);
+        if (m_max == 0) continue;
+
+        // ---- island set-up by the world's 2P lanes: accumulators and lambda = 0, ReorderPrep (stable partition:
+        //      rows without a friction index first, quickstep.cpp:2329-2355)
+        const Real4 z4 = { 0, 0, 0, 0 };
+        if (m_own > 0) {
+            for (int k = wid; k < 2 * nb; k += 2 * P) CF5(bstart + (k >> 1), k & 1) = z4;
+            if (wid < 2) CF5(Pm.NB, wid) = z4;
+            for (int i = wid; i <= m_own; i += 2 * P) lam[i * WPW] = 0;
+        }
+        int nfree = 0;
+        for (int i0 = 0; i0 < m_max; i0 += 2 * P) {
+            const int i = i0 + wid;
+            const bool fr = (i < m_own) && findex[rstart + i] == -1;
+            nfree += __popc(__ballot_sync(ODEB_FULL, fr) & wmask);
+        }
+        {
+            int head = 0, tail = nfree;
+            for (int i0 = 0; i0 < m_max; i0 += 2 * P) {
+                const int i = i0 + wid;
+                const bool in = i < m_own;
+                int fi = 0; int2 rb = make_int2(0, 0);
+                if (in) { fi = findex[rstart + i]; rb = rbody[rstart + i]; }
+                const bool fr = in && fi == -1;
+                const unsigned bf = __ballot_sync(ODEB_FULL, fr) & wmask, bo = __ballot_sync(ODEB_FULL, in && !fr) & wmask;
+                const unsigned e = (unsigned)i | ((unsigned)(fi == -1 ? i : fi - rstart) << 10) | ((unsigned)rb.x << 20) | ((unsigned)rb.y << 26);
+                if (fr) order[(head + __popc(bf & below)) * WPW] = e;
+                else if (in) order[(tail + __popc(bo & below)) * WPW] = e;
+                head += __popc(bf); tail += __popc(bo);
+            }
+        }
+        __syncwarp();
+
+        const char *rec_base = (const char *)(rows + (size_t)rstart * 8) + side * (sizeof(Real) * 16);
+        Real exit_delta = Pm.premature_delta;
+        CfShared5<WPW> cfs = { cf };
+        int done = m_own > 0 ? 0 : 1;
+        unsigned iteration = 0, extra = 0;
+        int nslots = 0;
+        bool resched = !done;
+        for (;;) {
+            if (__any_sync(ODEB_FULL, resched)) {
+                // ---- (re)build the schedule: clear the columns, then the leader list-schedules the order onto P processors
+                const int clr = __reduce_max_sync(ODEB_FULL, resched ? fill : 0);
+                if (side == 0) for (int s = 0; s < clr; s++) if (resched) meta[s * 16 + col] = IDLE;
+                __syncwarp();
+                int ns = 0;
+                if (resched && leader) {
+                    for (int k = 0; k < nb; k++) last[(bstart + k) * WPW] = 0;
+                    last[NBd * WPW] = 0;
+                    int pf[P];
+#pragma unroll
+                    for (int q = 0; q < P; q++) pf[q] = 0;
+                    unsigned *mcol = meta + wl;
+                    for (int i = 0; i < m_own; i++) {
+                        const unsigned e = order[i * WPW];
+                        const int b1 = E5_B1(e), b2 = E5_B2(e);
+                        const int l1 = last[b1 * WPW], l2 = last[b2 * WPW];
+                        const int r = l1 > l2 ? l1 : l2;
+                        int best = -1, bestpf = -1, mn = 0, mnpf = pf[0];
+#pragma unroll
+                        for (int q = 0; q < P; q++) {
+                            if (pf[q] <= r && pf[q] > bestpf) { best = q; bestpf = pf[q]; }
+                            if (pf[q] < mnpf) { mn = q; mnpf = pf[q]; }
+                        }
+                        const int pq = best >= 0 ? best : mn;
+                        const int slot = best >= 0 ? r : mnpf;
+#pragma unroll
+                        for (int q = 0; q < P; q++) if (q == pq) pf[q] = slot + 1;
+                        mcol[slot * 16 + pq * WPW] = e;
+                        last[b1 * WPW] = (unsigned short)(slot + 1);
+                        if (b2 != NBd) last[b2 * WPW] = (unsigned short)(slot + 1);
+                        ns = ns > slot + 1 ? ns : slot + 1;
+                    }
+                }
+                ns = __shfl_sync(ODEB_FULL, ns, wl);
+                if (resched) { nslots = ns; fill = ns; }
+                resched = false;
+                __syncwarp();
+            }
+            const int ns_own = done ? 0 : nslots;
+            const int ns_max = __reduce_max_sync(ODEB_FULL, ns_own);
+            // a finished world must not execute its (still valid) schedule again: its lanes read the idle entry
+            const unsigned *mp = done ? (meta + (size_t)SR5 * 16 + col) : (meta + col);   // [SR5, SR5 + PAD) stays idle for good
+            // ---- prime the ring along the lane's schedule column
+#pragma unroll
+            for (int k = 0; k < ODEB5_RING - 1; k++) {
+                const unsigned mk = mp[k * 16];
+                if (E5_B1(mk) != NBd) {
+                    const char *src = rec_base + (size_t)E5_ROW(mk) * (sizeof(Real) * 32);
+                    const unsigned dst = ring_addr + (unsigned)(k * CH * 32 * 16);
+#pragma unroll
+                    for (int c = 0; c < CH; c++) cp_async16(dst + c * 32 * 16, src + c * 16);
+                }
+                cp_async_commit();
+            }
+            for (int k = ODEB5_RING - 1; k < ODEB5_FAR; k++) {
+                const unsigned mk = mp[k * 16];
+                if (E5_B1(mk) != NBd) prefetch_l2(rec_base + (size_t)E5_ROW(mk) * (sizeof(Real) * 32));
+            }
+            cp_async_wait<ODEB5_RING - 2>();
+            HalfRegs r0, r1;
+            load_half(r0, ring);
+            unsigned mt0 = mp[0], mt1;
+            unsigned ma = mp[(ODEB5_RING - 1) * 16], mf = mp[ODEB5_FAR * 16];
+            for (int i = 0; i < ns_max; i += ODEB5_RING, mp = done ? mp : mp + ODEB5_RING * 16) {
+                ODEB5_ROW(r0, r1, mt0, mt1, 0)
+                ODEB5_ROW(r1, r0, mt1, mt0, 1)
+                ODEB5_ROW(r0, r1, mt0, mt1, 2)
+                ODEB5_ROW(r1, r0, mt1, mt0, 3)
+            }
+            cp_async_wait<0>();
+            int d = 0;
+            bool shuffle = false;
+            if (!done) {
+                ++iteration;
+                if (leader) {
+                    ++sweeps; rowsweeps += m_own;
+                    d = sweep_control(Pm, cfs, bstart, nb, iteration, extra, exit_delta, st1, st2, st3) ? 1 : 0;
+                    shuffle = !d && iteration >= 8 && (iteration & 7) == 0;
+                    if (shuffle) {
+                        // ConstraintsShuffling quickstep.cpp:2578-2611 with dRandInt misc.cpp:78-139
+                        for (int idx = 1; idx < m_own; idx++) {
+                            const int sw = odeb_rand_int(&seed, idx + 1);
+                            const unsigned a = order[idx * WPW], b = order[sw * WPW];
+                            order[idx * WPW] = b; order[sw * WPW] = a;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            d = __shfl_sync(ODEB_FULL, d, wl);
+            resched = __shfl_sync(ODEB_FULL, shuffle ? 1 : 0, wl) != 0;
+            done |= d;
+            if (__all_sync(ODEB_FULL, done)) break;
+        }
+        if (m_own > 0) for (int k = wid; k < 2 * nb; k += 2 * P) cf_out[2 * bstart + k] = CF5(bstart + (k >> 1), k & 1);
+        __syncwarp();
+    }
+    if (leader && valid) {
+        D.seed[w] = seed;
+        unsigned *st = D.stats + 4 * (size_t)w;
+        st[0] += st0; st[1] += st1; st[2] += st2; st[3] += st3;
+        D.sweeps[2 * (size_t)w] = sweeps; D.sweeps[2 * (size_t)w + 1] = rowsweeps;
+    }
+}
+#endif

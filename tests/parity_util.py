@@ -22,7 +22,7 @@ def orc_lib(prec):
 
 
 def gpu_lib(prec):
-    p = os.path.join(ROOT, "ode_b200", "libode_b200_%s.so" % prec)
+    p = os.path.join(os.environ.get("ODEB_LIB_DIR", os.path.join(ROOT, "ode_b200")), "libode_b200_%s.so" % prec)   # ODEB_LIB_DIR: kernel-variant experiments (tools/)
     if not os.path.exists(p):
         raise RuntimeError("CUDA extension %s is missing: run `python -c 'import __graft_entry__ as g; g.build()'`" % p)
     return B.SceneLib(p, "odeb_", REAL[prec])
