@@ -121,6 +121,57 @@ def cpu_reference(steps, warm, worlds_per_proc=16, procs=None):
     return {"value": value, "unit": "body-steps/s", "cores": procs, "kind": kind, "sample": sample}
 
 
+# ---------------------------------------------------------------------------------------------- other BASELINE configs
+
+def other_configs(slib, device):
+    """Device-timed throughput of BASELINE configs[2..4] on this GPU (bounded: a few seconds each). Not the headline
+    line: reported beside it so the other scene families carry a measured number too."""
+    L = slib.lib
+    out = {}
+
+    def timed(batch, h, steps, nbodies_total):
+        ms = C.c_double(0)
+        if not L.odeb_timed_steps(batch.h, h, steps, FLUSH_BYTES, C.byref(ms)):
+            raise RuntimeError("timed steps failed")
+        tot = (C.c_uint64 * 6)()
+        L.odeb_get_totals(batch.h, tot)
+        return {"ms_per_step": ms.value / steps, "body_steps_per_sec": nbodies_total * steps / (ms.value * 1e-3),
+                "rows_last_step": int(tot[2]), "steps": steps}
+
+    try:   # configs[2]: 65536 worlds of a 10-link ball-joint chain plus contacts (demo_chain2-style)
+        nw = 65536
+        b = B.Batch(slib, scenes.chain(nw), device=device)
+        b.step(0.05, 40)
+        r = timed(b, 0.05, 20, nw * 10)
+        r["workload"] = "%d worlds x 10-link chain, dt=0.05 (BASELINE configs[2], all on this GPU)" % nw
+        out["chain"] = r
+        b.close()
+    except Exception as e:  # noqa: BLE001
+        out["chain"] = {"error": str(e)[:200]}
+    try:   # configs[3]: capsule ragdolls; 16384 worlds are quoted on 8 GPUs -> 2048 per GPU
+        nw = 2048
+        b = B.Batch(slib, scenes.ragdoll(nw), device=device)
+        b.step(0.01, 60)
+        r = timed(b, 0.01, 20, nw * 15)
+        r["workload"] = "%d worlds x 15-capsule ragdoll (ball/hinge/universal joints with stops, friction contacts), dt=0.01 (BASELINE configs[3]: 16384 worlds / 8 GPUs)" % nw
+        out["ragdoll"] = r
+        b.close()
+    except Exception as e:  # noqa: BLE001
+        out["ragdoll"] = {"error": str(e)[:200]}
+    try:   # configs[4]: one 100k-box wall, sweep-and-prune space, large-island path (ODEB_MODE_CANONICAL)
+        sc = scenes.wall(500, 200)
+        b = B.Batch(slib, sc, device=device)
+        b.set_solver_mode(1)
+        b.step(0.05, 6)
+        r = timed(b, 0.05, 6, sc.nbody)
+        r["workload"] = "1 world x %d bodies (500 x 200 brick wall + cannon ball), dSweepAndPruneSpace semantics, dt=0.05 (BASELINE configs[4])" % sc.nbody
+        out["wall_100k"] = r
+        b.close()
+    except Exception as e:  # noqa: BLE001
+        out["wall_100k"] = {"error": str(e)[:200]}
+    return out
+
+
 # ---------------------------------------------------------------------------------------------- GPU arm
 
 def gpu_arm(args):
@@ -221,11 +272,17 @@ def gpu_arm(args):
                 traffic = json.load(open(pj)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        roofline = {"bound": "hbm", "kernel": "k_solve", "achieved": round(achieved, 1), "peak": peak, "peak_source": which,
+        L.odeb_solver_kernel.restype = C.c_char_p
+        L.odeb_solver_kernel.argtypes = [C.c_void_p]
+        roofline = {"bound": "hbm", "kernel": (L.odeb_solver_kernel(batch.h) or b"k_solve").decode(), "achieved": round(achieved, 1), "peak": peak, "peak_source": which,
                     "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
                     "algorithmic_bytes_per_launch": int(alg_bytes), "launch_ms": round(sol_avg_ms, 4),
                     "share_of_step": round(sol_avg_ms / (total_ms / args.steps), 3),
                     "note": "rows are served from L2/shared memory, so algorithmic GB/s is not DRAM traffic; the kernel is bound by the serial row-update latency per world"}
+        extras = None
+        if ngpu == 1 and not args.no_extras:
+            batch.close()
+            extras = other_configs(slib, local_rank)
         cpu = None
         if ngpu == 1 and not args.no_cpu:
             cpu = cpu_reference(args.cpu_steps, args.settle + args.warmup)
@@ -246,6 +303,8 @@ def gpu_arm(args):
         }
         if cpu is not None:
             out["cpu_baseline"] = cpu
+        if extras is not None:
+            out["other_configs"] = extras
     batch.close()
     if world > 1:
         dist.barrier()
@@ -279,6 +338,7 @@ def main():
     ap.add_argument("--settle", type=int, default=150)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the bounded runs of BASELINE configs[2..4]")
     ap.add_argument("--cpu-steps", type=int, default=1500)
     args = ap.parse_args()
     if args.warmup < 3:

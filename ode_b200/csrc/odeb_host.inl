@@ -358,9 +358,9 @@ static OdebBatch *batch_build(const OdebWorldParams *wp, const HostTemplate &T, 
     ok = ok && dev_alloc(B, &D.rows, W * P.MR * 8) && dev_alloc(B, &D.rbody, W * P.MR) && dev_alloc(B, &D.findex, W * P.MR) && dev_alloc(B, &D.order, W * P.MR)
             && dev_alloc(B, &D.lambda, W * P.MR) && dev_alloc(B, &D.cforce, W * (nbody + 1) * 2) && dev_alloc(B, &D.invIw, WB * 12)
             && dev_alloc(B, &D.stats, W * 4) && dev_alloc(B, &D.seed, W) && dev_alloc(B, &D.sweeps, 2 * W) && dev_alloc(B, &D.overflow, 2);
-    B->stage_elems = WB;
-    ok = ok && dev_alloc(B, &B->d_stage, WB);
-    if (ok && cudaMallocHost((void **)&B->h_stage, WB * sizeof(Real4)) != cudaSuccess) { set_err("cudaMallocHost failed"); ok = false; }
+    B->stage_elems = 4 * WB;                     // room for the tightly packed state of every body (13 reals) in one transfer
+    ok = ok && dev_alloc(B, &B->d_stage, 4 * WB);
+    if (ok && cudaMallocHost((void **)&B->h_stage, 4 * WB * sizeof(Real4)) != cudaSuccess) { set_err("cudaMallocHost failed"); ok = false; }
     if (ok && cudaStreamCreateWithFlags(&B->stream, cudaStreamNonBlocking) != cudaSuccess) { set_err("cudaStreamCreate failed"); ok = false; }
     if (ok) {   // opt every solver kernel into the full 227 KB of shared memory once (the attribute is per function, not per batch)
         const int mx = 227 * 1024;
@@ -518,18 +518,6 @@ static int stage_up(OdebBatch *B, const Real *src, int k, Real4 *dst)
     CK(cudaStreamSynchronize(B->stream));
     return 1;
 }
-static int stage_down(OdebBatch *B, Real *dst, int k, const Real4 *src)
-{
-    const size_t n = (size_t)B->P.W * B->P.NB;
-    CK(cudaMemcpyAsync(B->h_stage, src, n * sizeof(Real4), cudaMemcpyDeviceToHost, B->stream));
-    CK(cudaStreamSynchronize(B->stream));
-    for (size_t i = 0; i < n; i++) {
-        Real4 v = B->h_stage[i];
-        dst[k * i] = v.x; dst[k * i + 1] = v.y; dst[k * i + 2] = v.z; if (k == 4) dst[k * i + 3] = v.w;
-    }
-    return 1;
-}
-
 int odeb_set_state(OdebBatch *B, const odeb_real *pos, const odeb_real *quat, const odeb_real *lvel, const odeb_real *avel)
 {
     CK(cudaSetDevice(B->device));
@@ -548,20 +536,44 @@ int odeb_set_state(OdebBatch *B, const odeb_real *pos, const odeb_real *quat, co
 
 int odeb_get_state(OdebBatch *B, odeb_real *pos, odeb_real *quat, odeb_real *lvel, odeb_real *avel)
 {
+    // one pack kernel (Real4 SoA -> the caller's tight [body][3|4] layouts), one device->host transfer into pinned memory,
+    // plain memcpy into the caller's buffers
     CK(cudaSetDevice(B->device));
-    if (pos && !stage_down(B, pos, 3, B->D.pos)) return 0;
-    if (quat && !stage_down(B, quat, 4, B->D.quat)) return 0;
-    if (lvel && !stage_down(B, lvel, 3, B->D.lvel)) return 0;
-    if (avel && !stage_down(B, avel, 3, B->D.avel)) return 0;
+    const size_t n = (size_t)B->P.W * B->P.NB;
+    Real *d = (Real *)B->d_stage, *h = (Real *)B->h_stage;
+    k_pack_state<<<nblk(n, 256), 256, 0, B->stream>>>(n, B->D.pos, B->D.quat, B->D.lvel, B->D.avel, d);
+    B->launches++;
+    if (pos && quat && lvel && avel) CK(cudaMemcpyAsync(h, d, 13 * n * sizeof(Real), cudaMemcpyDeviceToHost, B->stream));
+    else {
+        if (pos) CK(cudaMemcpyAsync(h, d, 3 * n * sizeof(Real), cudaMemcpyDeviceToHost, B->stream));
+        if (quat) CK(cudaMemcpyAsync(h + 3 * n, d + 3 * n, 4 * n * sizeof(Real), cudaMemcpyDeviceToHost, B->stream));
+        if (lvel) CK(cudaMemcpyAsync(h + 7 * n, d + 7 * n, 3 * n * sizeof(Real), cudaMemcpyDeviceToHost, B->stream));
+        if (avel) CK(cudaMemcpyAsync(h + 10 * n, d + 10 * n, 3 * n * sizeof(Real), cudaMemcpyDeviceToHost, B->stream));
+    }
+    CK(cudaStreamSynchronize(B->stream));
+    if (pos) memcpy(pos, h, 3 * n * sizeof(Real));
+    if (quat) memcpy(quat, h + 3 * n, 4 * n * sizeof(Real));
+    if (lvel) memcpy(lvel, h + 7 * n, 3 * n * sizeof(Real));
+    if (avel) memcpy(avel, h + 10 * n, 3 * n * sizeof(Real));
     return 1;
 }
 
 int odeb_add_force(OdebBatch *B, const odeb_real *force, const odeb_real *torque)
 {
+    // tight [body][3] arrays go up through pinned memory in one transfer; the add runs stream-ordered before the next step
     CK(cudaSetDevice(B->device));
     const size_t n = (size_t)B->P.W * B->P.NB;
-    if (force) { if (!stage_up(B, force, 3, B->d_stage)) return 0; k_add4<<<nblk(n, 256), 256, 0, B->stream>>>(n, B->D.facc, B->d_stage); B->launches++; CK(cudaStreamSynchronize(B->stream)); }
-    if (torque) { if (!stage_up(B, torque, 3, B->d_stage)) return 0; k_add4<<<nblk(n, 256), 256, 0, B->stream>>>(n, B->D.tacc, B->d_stage); B->launches++; CK(cudaStreamSynchronize(B->stream)); }
+    if (!force && !torque) return 1;
+    Real *d = (Real *)B->d_stage, *h = (Real *)B->h_stage;
+    CK(cudaStreamSynchronize(B->stream));            // the staging buffers may still feed an earlier transfer
+    if (force) memcpy(h, force, 3 * n * sizeof(Real));
+    if (torque) memcpy(h + 3 * n, torque, 3 * n * sizeof(Real));
+    if (force && torque) CK(cudaMemcpyAsync(d, h, 6 * n * sizeof(Real), cudaMemcpyHostToDevice, B->stream));
+    else if (force) CK(cudaMemcpyAsync(d, h, 3 * n * sizeof(Real), cudaMemcpyHostToDevice, B->stream));
+    else CK(cudaMemcpyAsync(d + 3 * n, h + 3 * n, 3 * n * sizeof(Real), cudaMemcpyHostToDevice, B->stream));
+    k_add_ft<<<nblk(n, 256), 256, 0, B->stream>>>(n, force ? B->D.facc : 0, torque ? B->D.tacc : 0, d);
+    B->launches++;
+    CK(cudaStreamSynchronize(B->stream));            // the caller may reuse its arrays and ours right away
     return 1;
 }
 
@@ -746,6 +758,12 @@ int odeb_timed_steps(OdebBatch *B, double h, int nsteps, size_t flush_bytes, dou
 }
 
 uint64_t odeb_launch_count(const OdebBatch *B) { return B->launches; }
+const char *odeb_solver_kernel(const OdebBatch *B)
+{
+    static const char *names[5] = { "k_solve", "k_solve5<2>", "k_solve5<4>", "k_solve5<8>", "k_solve_bl" };
+    if (B->mode == ODEB_MODE_CANONICAL) return "k_lw_sweep";
+    return names[choose_solver(B)];
+}
 void odeb_enable_timing(OdebBatch *B, int on) { B->timing = on != 0; }
 double odeb_solver_ms(OdebBatch *B, int *launches)
 {

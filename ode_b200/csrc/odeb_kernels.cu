@@ -697,13 +697,25 @@ __global__ void k_set_quat(int n, Real4 *quat, Real4 *Rout)
     Rout[3 * t] = r0; Rout[3 * t + 1] = r1; Rout[3 * t + 2] = r2;
 }
 
-__global__ void k_add4(size_t n, Real4 *dst, const Real4 *src)
+// body state (Real4 SoA) -> tight arrays [pos 3n | quat 4n | lvel 3n | avel 3n] for one device->host transfer
+__global__ void k_pack_state(size_t n, const Real4 *pos, const Real4 *quat, const Real4 *lvel, const Real4 *avel, Real *out)
 {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
-    Real4 a = dst[t], b = src[t];
-    a.x += b.x; a.y += b.y; a.z += b.z;
-    dst[t] = a;
+    const Real4 p = pos[t], q = quat[t], l = lvel[t], a = avel[t];
+    Real *o = out + 3 * t;            o[0] = p.x; o[1] = p.y; o[2] = p.z;
+    o = out + 3 * n + 4 * t;          o[0] = q.x; o[1] = q.y; o[2] = q.z; o[3] = q.w;
+    o = out + 7 * n + 3 * t;          o[0] = l.x; o[1] = l.y; o[2] = l.z;
+    o = out + 10 * n + 3 * t;         o[0] = a.x; o[1] = a.y; o[2] = a.z;
+}
+
+// dBodyAddForce / dBodyAddTorque for every body from tight [force 3n | torque 3n] arrays
+__global__ void k_add_ft(size_t n, Real4 *facc, Real4 *tacc, const Real *src)
+{
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    if (facc) { Real4 a = facc[t]; const Real *f = src + 3 * t; a.x += f[0]; a.y += f[1]; a.z += f[2]; facc[t] = a; }
+    if (tacc) { Real4 a = tacc[t]; const Real *f = src + 3 * n + 3 * t; a.x += f[0]; a.y += f[1]; a.z += f[2]; tacc[t] = a; }
 }
 
 #include "odeb_host.inl"
