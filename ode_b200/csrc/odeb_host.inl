@@ -623,7 +623,7 @@ static int choose_solver(const OdebBatch *B)
     if (f >= 1 && f <= 3) return B->s5_sr[f] > 0 ? f : 0;
     if (B->hint_m <= 0) return 0;
     // Measured on B200 (4096 x 16-box stacks, single; solver ms for W = 1024 / 2048 / 4096 worlds): k_solve 1.19 / 1.19 / 1.26,
-    // k_solve5<4> 0.73 / 0.90 / 1.30, k_solve5<8> 0.78 / - / -, k_solve5<2> - / - / 1.40.  With more than ~3.5 warps per SM the
+    // k_solve5<4> 0.67 / 0.83 / 1.25, k_solve5<8> 0.78 / - / -, k_solve5<2> - / - / 1.39.  With more than ~3.5 warps per SM the
     // extra warps of the P-processor schedule contend for the SM's shared-memory pipe and the gain is gone, so P = 4 is used
     // while the batch needs at most that many warps and every island fits its row budget.
     int nsm = 148;

@@ -46,6 +46,7 @@ struct HalfRegs { Real4 q0, q1, q2, q3; };
 
 __device__ __forceinline__ void cp_async16(unsigned dst, const void *src)
 {
+    // .cg (L2 only): the L1-allocating .ca form measured 19 % slower here (profiles/r1_solver_variants.txt)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }

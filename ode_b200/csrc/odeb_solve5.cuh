@@ -13,16 +13,17 @@
 //   * a sweep then is `nslots` lockstep slots (16-box stack: 136 for the initial order, ~52 after a shuffle for
 //     P = 4, instead of 192), each slot the row update of k_solve: two lanes per row (body-1 / body-2 halves,
 //     one shuffle), accumulators + lambda in shared memory, half records through a per-lane cp.async ring that runs
-//     along the lane's own schedule column.  The ring is only 4 stages deep (shared memory is what limits the number of
-//     resident warps), which covers an L2 hit but not a DRAM miss, and with 64 sectors per slot and warp some sector
-//     misses in nearly every slot; so every lane also issues prefetch.global.L2 for the record it will need ODEB5_FAR
-//     slots later.  Idle slots carry the dummy body and have their copies and stores predicated off.
+//     along the lane's own schedule column (4 stages: shared memory is what limits the number of resident warps; 8
+//     stages and an additional prefetch.global.L2 ODEB5_FAR slots ahead were measured and bring nothing for P = 4,
+//     profiles/r1_solver_variants.txt).  Idle slots carry the dummy body and have their copies and stores predicated off.
 // Lane layout: side = lane >> 4, column = lane & 15 = proc * WPW + world (WPW = 16 / P worlds per warp).
 // One order / meta entry: row (bits 0..9) | friction row (10..19) | body-1 slot (20..25) | body-2 slot (26..31).
 #ifndef ODEB_SOLVE5_CUH
 #define ODEB_SOLVE5_CUH
 
-#define ODEB5_RING 4                                       // must stay 4: the slot loop is unrolled by the ring depth
+#ifndef ODEB5_RING
+#define ODEB5_RING 4                                       // 4 or 8: the slot loop is unrolled by the ring depth
+#endif
 #ifndef ODEB5_FAR
 #define ODEB5_FAR 12                                       // L2 prefetch distance in slots
 #endif
@@ -60,7 +61,7 @@ template <int WPW> struct CfShared5 {     // element i = vector (i & 1) of body 
     __device__ void set(int i, const Real4 &v) { CF5(i >> 1, i & 1) = v; }
 };
 
-#if defined(ODEB5_NOFAR)
+#if !defined(ODEB5_FAR_PREFETCH)     // measured: no gain (profiles/r1_solver_variants.txt), off by default
 __device__ __forceinline__ void prefetch_l2(const void *) {}
 #else
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
@@ -287,6 +288,12 @@ __global__ void __launch_bounds__(32) k_solve5(const __grid_constant__ DevParams
                 ODEB5_ROW(r1, r0, mt1, mt0, 1)
                 ODEB5_ROW(r0, r1, mt0, mt1, 2)
                 ODEB5_ROW(r1, r0, mt1, mt0, 3)
+#if ODEB5_RING == 8
+                ODEB5_ROW(r0, r1, mt0, mt1, 4)
+                ODEB5_ROW(r1, r0, mt1, mt0, 5)
+                ODEB5_ROW(r0, r1, mt0, mt1, 6)
+                ODEB5_ROW(r1, r0, mt1, mt0, 7)
+#endif
             }
             cp_async_wait<0>();
             int d = 0;
