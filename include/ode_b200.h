@@ -160,6 +160,14 @@ int odeb_get_enabled(OdebBatch *, int *enabled /* [world][body] */);
 enum { ODEB_MODE_REPLAY = 0, ODEB_MODE_CANONICAL = 1 };
 int odeb_set_solver_mode(OdebBatch *, int mode);
 
+/* Joint feedback (dJointSetFeedback / dJointFeedback, include/ode/common.h:439-447; quickstep.cpp:3108-3182): when enabled,
+ * every joint of every world behaves as if a dJointFeedback were attached. odeb_get_feedback returns, for one world, the
+ * joints in id order (the njoint permanent joints of the template, then the contact joints of the last step in creation
+ * order): out12 = f1[3] t1[3] f2[3] t2[3], state = 0 (joint not stepped: its island was disabled), 1 (body 1 only: f2/t2
+ * are not written by the reference either), 2 (both bodies). Returns the number of joints (may exceed cap), -1 on error. */
+int odeb_enable_feedback(OdebBatch *, int on);
+int odeb_get_feedback(OdebBatch *, int world, odeb_real *out12, int *state, int cap);
+
 #if defined(__CUDACC__)
 #define ODEB_HD __host__ __device__
 #else

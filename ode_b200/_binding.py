@@ -270,6 +270,26 @@ class Batch:
         if not f(self.h, int(mode)):
             raise RuntimeError("%sset_solver_mode failed" % self.slib.prefix)
 
+    def enable_feedback(self, on=True):
+        f = self.slib._fn("enable_feedback")
+        f.argtypes = [C.c_void_p, C.c_int]
+        if not f(self.h, int(bool(on))):
+            raise RuntimeError("%senable_feedback failed" % self.slib.prefix)
+
+    def get_feedback(self, world, cap=4096):
+        """(feedback [n,12] = f1 t1 f2 t2, state [n]) of the last step for one world; joints in id order
+        (permanent joints, then the step's contact joints in creation order)"""
+        f = self.slib._fn("get_feedback")
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        out = np.zeros((cap, 12), self.slib.real)
+        st = np.zeros(cap, np.int32)
+        n = f(self.h, int(world), out.ctypes.data, st.ctypes.data, cap)
+        if n < 0:
+            raise RuntimeError("%sget_feedback failed" % self.slib.prefix)
+        n = min(n, cap)
+        return out[:n].copy(), st[:n].copy()
+
     def set_seeds(self, seeds):
         s = np.ascontiguousarray(np.asarray(seeds, dtype=np.uint32).reshape(self.W))
         self.slib._fn("set_seeds")(self.h, _ptr(s))

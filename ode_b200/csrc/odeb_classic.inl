@@ -1184,6 +1184,10 @@ int dWorldQuickStep(dWorldID w, Real stepsize)
             CK(cudaMemcpy(D.sadj_other, so.data(), so.size() * sizeof(int), cudaMemcpyHostToDevice));
         }
     }
+    // dJointSetFeedback: any joint with a dJointFeedback attached turns the device-side feedback pass on for this context
+    bool want_fb = false;
+    for (std::map<dxJoint *, int>::const_iterator it = jid.begin(); it != jid.end(); ++it) if (it->first->feedback) { want_fb = true; break; }
+    if (want_fb != (B->D.jcopy != 0) && !odeb_enable_feedback(B, want_fb ? 1 : 0)) return 0;
     unsigned seed = (unsigned)g_seed, st0[4] = { 0, 0, 0, 0 }, st1[4];
     CK(cudaMemcpy(D.seed, &seed, sizeof(unsigned), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(D.stats, st0, sizeof(st0), cudaMemcpyHostToDevice));
@@ -1201,6 +1205,19 @@ int dWorldQuickStep(dWorldID w, Real stepsize)
     if (w->stats_sink) {
         w->stats_sink->iteration_count += st1[0]; w->stats_sink->premature_exits += st1[1];
         w->stats_sink->prolonged_execs += st1[2]; w->stats_sink->full_extra_execs += st1[3];
+    }
+    if (want_fb) {   // quickstep.cpp:3108-3182: f1/t1 always, f2/t2 only when the joint has a second body; untouched when not stepped
+        const int n = NJ + nc;
+        std::vector<Real4> v(4 * (size_t)n);
+        if (n) CK(cudaMemcpy(v.data(), B->D.jfb, v.size() * sizeof(Real4), cudaMemcpyDeviceToHost));
+        for (std::map<dxJoint *, int>::const_iterator it = jid.begin(); it != jid.end(); ++it) {
+            dJointFeedback *fb = it->first->feedback;
+            if (!fb || it->second >= n) continue;
+            const Real4 *q = &v[4 * (size_t)it->second];
+            const int state = (int)q[0].w;
+            if (state >= 1) { fb->f1[0] = q[0].x; fb->f1[1] = q[0].y; fb->f1[2] = q[0].z; fb->t1[0] = q[1].x; fb->t1[1] = q[1].y; fb->t1[2] = q[1].z; }
+            if (state >= 2) { fb->f2[0] = q[2].x; fb->f2[1] = q[2].y; fb->f2[2] = q[2].z; fb->t2[0] = q[3].x; fb->t2[1] = q[3].y; fb->t2[2] = q[3].z; }
+        }
     }
     if (!ctx_download_state(w, c)) return 0;
     return 1;

@@ -638,6 +638,7 @@ static void launch_dynamics(OdebBatch *B, cudaStream_t s, bool timed, int cfg)
 {
     const DevParams &P = B->P; const DevPtrs &D = B->D;
     const size_t W = P.W;
+    if (D.jfb) cudaMemsetAsync(D.jfb, 0, W * P.NJT * 4 * sizeof(Real4), s);      // state 0 = joint not stepped
     if (P.NJ > 0) { k_joint_info1<<<nblk(W * P.NJ, 128), 128, 0, s>>>(P, D); B->launches++; }
     k_islands<<<nblk(W, 32), 32, 0, s>>>(P, D);
     k_body_pre<<<nblk(W * P.NB, 128), 128, 0, s>>>(P, D);
@@ -657,6 +658,7 @@ static void launch_dynamics(OdebBatch *B, cudaStream_t s, bool timed, int cfg)
     default: k_solve<<<nblk(W, ODEB_WPW), 32, B->solve_smem, s>>>(P, D);
     }
     if (timed) { cudaEventRecord(e1, s); B->pending.push_back(std::make_pair(e0, e1)); }
+    if (D.jcopy) { k_feedback<<<nblk(W * P.NJT, 128), 128, 0, s>>>(P, D); B->launches++; }
     k_integrate<<<nblk(W * P.NB, 128), 128, 0, s>>>(P, D);
     B->launches += 6;
 }
@@ -694,7 +696,7 @@ int odeb_step_async(OdebBatch *B, double h, int nsteps)
     for (int s = 0; s < nsteps; s++) {
         if (graph_ok) {
             CK(cudaGraphLaunch(B->graph, B->stream));
-            B->launches += (B->P.NG > 0 ? 5 : 0) + (B->P.NJ > 0 ? 1 : 0) + 6;
+            B->launches += (B->P.NG > 0 ? 5 : 0) + (B->P.NJ > 0 ? 1 : 0) + 6 + (B->D.jcopy ? 1 : 0);
         } else launch_step(B, B->stream, B->timing, cfg);
     }
     CK(cudaGetLastError());
@@ -755,6 +757,40 @@ int odeb_timed_steps(OdebBatch *B, double h, int nsteps, size_t flush_bytes, dou
     for (size_t i = 0; i < ev.size(); i++) cudaEventDestroy(ev[i]);
     *total_ms = tot;
     return 1;
+}
+
+int odeb_enable_feedback(OdebBatch *B, int on)
+{
+    CK(cudaSetDevice(B->device));
+    CK(cudaStreamSynchronize(B->stream));
+    if (B->mode == ODEB_MODE_CANONICAL) { set_err("joint feedback is not available in ODEB_MODE_CANONICAL"); return 0; }
+    if (on && !B->D.jcopy) {
+        const size_t W = B->P.W;
+        if (!dev_alloc(B, &B->D.jcopy, W * B->P.MR * 3) || !dev_alloc(B, &B->D.jfb, W * B->P.NJT * 4)) return 0;
+    } else if (!on) { B->D.jcopy = 0; B->D.jfb = 0; }      // the buffers stay in the batch's allocation list until odeb_destroy
+    if (B->graph) { cudaGraphExecDestroy(B->graph); B->graph = 0; }
+    return 1;
+}
+int odeb_get_feedback(OdebBatch *B, int world, odeb_real *out12, int *state, int cap)
+{
+    CK(cudaSetDevice(B->device));
+    CK(cudaStreamSynchronize(B->stream));
+    if (!B->D.jfb) { set_err("joint feedback is not enabled"); return -1; }
+    if (world < 0 || world >= B->P.W) { set_err("bad world index"); return -1; }
+    int nc = 0;
+    CK(cudaMemcpy(&nc, B->D.ncontacts + world, sizeof(int), cudaMemcpyDeviceToHost));
+    if (nc > B->P.MC) nc = B->P.MC;
+    const int n = B->P.NJ + nc;
+    std::vector<Real4> v(4 * (size_t)n);
+    if (n) CK(cudaMemcpy(v.data(), B->D.jfb + (size_t)world * B->P.NJT * 4, v.size() * sizeof(Real4), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n && i < cap; i++) {
+        const Real4 *q = &v[4 * (size_t)i];
+        odeb_real *o = out12 + 12 * (size_t)i;
+        o[0] = q[0].x; o[1] = q[0].y; o[2] = q[0].z; o[3] = q[1].x; o[4] = q[1].y; o[5] = q[1].z;
+        o[6] = q[2].x; o[7] = q[2].y; o[8] = q[2].z; o[9] = q[3].x; o[10] = q[3].y; o[11] = q[3].z;
+        state[i] = (int)q[0].w;
+    }
+    return n;
 }
 
 uint64_t odeb_launch_count(const OdebBatch *B) { return B->launches; }

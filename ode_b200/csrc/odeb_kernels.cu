@@ -91,6 +91,8 @@ struct DevPtrs {
                                                  //   (layout in odeb_solve.cuh)
     int2 *rbody;                                 // [W*MR] accumulator slots (order positions) of the row's two bodies; one-body rows: (p0, NB)
     int *findex, *order; Real *lambda;           // [W*MR]
+    Real4 *jcopy;                                // [W*MR*3] J1l J1a J2l J2a of every row before any scaling (joint feedback on), else null
+    Real4 *jfb;                                  // [W*NJT*4] per joint id: {f1, state} {t1, 0} {f2, 0} {t2, 0} (quickstep.cpp:3108-3182)
     int *row_island, *row_group;                 // [MR] island of every row, first row of the row's group (large-world path only, else null)
     Real4 *cforce;                               // [W*(NB+1)*2]  (fc 6, fa 2) per order position + one dummy slot per world
     Real *invIw;                                 // [W*NB*12], indexed by order position
@@ -502,6 +504,12 @@ __global__ void k_rows(const __grid_constant__ DevParams P, const __grid_constan
         q[C_RHS] *= P.hrecip; q[C_CFM] *= P.hrecip;
         Real4 v0 = { q[0], q[1], q[2], q[3] }, v1 = { q[4], q[5], q[6], q[7] }, v2 = { q[8], q[9], q[10], q[11] }, v3 = { q[12], q[13], q[14], q[15] };
         rec[8 * r] = v0; rec[8 * r + 1] = v1; rec[8 * r + 2] = v2; rec[8 * r + 3] = v3;
+        if (D.jcopy) {   // Jcopy quickstep.cpp:1562-1583
+            Real4 *jc = D.jcopy + ((size_t)w * P.MR + row0 + r) * 3;
+            Real4 c0 = { q[C_J1L], q[C_J1L + 1], q[C_J1L + 2], q[C_J1A] }, c1 = { q[C_J1A + 1], q[C_J1A + 2], q[C_J2L], q[C_J2L + 1] },
+                  c2 = { q[C_J2L + 2], q[C_J2A], q[C_J2A + 1], q[C_J2A + 2] };
+            jc[0] = c0; jc[1] = c1; jc[2] = c2;
+        }
         fi[r] = findex[r] == -1 ? -1 : findex[r] + row0;
         if (D.row_island) {     // large-world path: the contacts of one geom pair (ids consecutive, same island) form one row group
             D.row_island[row0 + r] = D.joint_island[t];
@@ -593,6 +601,37 @@ __global__ void k_rows_finish(const __grid_constant__ DevParams P, const __grid_
     Real4 b2 = { imj[7], imj[8], imj[9], imj[10] }, b3 = { imj[11], imj[12], imj[13], 0 };
     Jp[0] = a0; Jp[1] = a1; Jp[2] = a2; Jp[3] = a3; Jp[4] = b0; Jp[5] = b1; Jp[6] = b2; Jp[7] = b3;
     D.rbody[t] = make_int2(p0, (p1 == -1) ? P.NB : p1);     // one-body rows address the dummy accumulator slot NB
+}
+
+// Stage4b joint feedback (quickstep.cpp:3108-3182, Multiply1_12q1 :153-184): f = sum over the joint's rows of Jcopy^T * lambda,
+// one running sum per component in row order. Thread per ordered joint.
+__global__ void k_feedback(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D)
+{
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)P.W * P.NJT) return;
+    int w = (int)(t / P.NJT), k = (int)(t % P.NJT);
+    if (k >= D.njord[w]) return;
+    int jid = D.joint_order[t];
+    int4 isl = D.island_info[(size_t)w * P.NB + D.joint_island[t]];
+    if (isl.w == 0) return;
+    const int row0 = isl.z + D.joint_row[t];
+    int m; bool two;
+    if (jid >= P.NJ) {
+        int4 ci = D.cinfo[(size_t)w * P.MC + (jid - P.NJ)];
+        m = (P.classic ? D.csurf[jid - P.NJ] : P.surf).the_m; two = ci.z >= 0;
+    } else { m = D.jm[(size_t)w * P.NJ + jid]; two = D.joints[jid].b1 >= 0; }
+    const Real4 *jc = D.jcopy + ((size_t)w * P.MR + row0) * 3;
+    const Real *lam = D.lambda + (size_t)w * P.MR + row0;
+    Real a[6] = { 0, 0, 0, 0, 0, 0 }, b[6] = { 0, 0, 0, 0, 0, 0 };
+    for (int r = 0; r < m; r++) {
+        const Real4 c0 = jc[3 * r], c1 = jc[3 * r + 1], c2 = jc[3 * r + 2];
+        const Real s = lam[r];
+        a[0] += c0.x * s; a[1] += c0.y * s; a[2] += c0.z * s; a[3] += c0.w * s; a[4] += c1.x * s; a[5] += c1.y * s;
+        if (two) { b[0] += c1.z * s; b[1] += c1.w * s; b[2] += c2.x * s; b[3] += c2.y * s; b[4] += c2.z * s; b[5] += c2.w * s; }
+    }
+    Real4 *o = D.jfb + ((size_t)w * P.NJT + jid) * 4;
+    Real4 o0 = { a[0], a[1], a[2], two ? R_(2.0) : R_(1.0) }, o1 = { a[3], a[4], a[5], 0 }, o2 = { b[0], b[1], b[2], 0 }, o3 = { b[3], b[4], b[5], 0 };
+    o[0] = o0; o[1] = o1; o[2] = o2; o[3] = o3;
 }
 
 #include "odeb_solve.cuh"

@@ -174,7 +174,7 @@ __device__ __forceinline__ void load_half(HalfRegs &h, const uint4 *slot)
 // row count for this lane's world, 0 when the world has no island for this round (the pair then idles through
 // the row loop with stores predicated off).
 __device__ __forceinline__ void solve_islands_warp(const DevParams &P, unsigned char *smem, int lane,
-                                                   const Real4 *rows, const int *findex, const int2 *rbody, Real4 *cf_out,
+                                                   const Real4 *rows, const int *findex, const int2 *rbody, Real4 *cf_out, Real *lam_out,
                                                    int bstart, int nb, int rstart, int m_own, unsigned &seed,
                                                    unsigned &st1, unsigned &st2, unsigned &st3,
                                                    unsigned long long &sweeps, unsigned long long &rowsweeps)
@@ -262,6 +262,7 @@ __device__ __forceinline__ void solve_islands_warp(const DevParams &P, unsigned 
         if (__all_sync(ODEB_FULL, done)) break;
     }
     if (m_own > 0) for (int k = side; k < 2 * nb; k += 2) cf_out[2 * bstart + k] = cf[(2 * bstart + k) * ODEB_WPW];
+    if (lam_out && m_own > 0) for (int i = side; i < m_own; i += 2) lam_out[rstart + i] = lam[i * ODEB_WPW];   // joint feedback needs the final lambda
     __syncwarp();
 }
 
@@ -354,7 +355,7 @@ __global__ void __launch_bounds__(32) k_solve(const __grid_constant__ DevParams 
         seed = __shfl_sync(ODEB_FULL, seed, LANE_A(lane));     // lane B replays the same dRand stream in the shared-memory path
         const int m_smem = (m > 0 && m <= P.SR) ? m : 0;
         if (__any_sync(ODEB_FULL, m_smem > 0))
-            solve_islands_warp(P, smem, lane, rows, findex, rbody, cf_out, bstart, nb, rstart, m_smem, seed, st1, st2, st3, sweeps, rowsweeps);
+            solve_islands_warp(P, smem, lane, rows, findex, rbody, cf_out, D.jcopy ? D.lambda + (size_t)w * P.MR : 0, bstart, nb, rstart, m_smem, seed, st1, st2, st3, sweeps, rowsweeps);
         if (is < nis) st0++;
     }
     if (side == 0 && valid) {

@@ -321,6 +321,7 @@ __global__ void __launch_bounds__(32) k_solve5(const __grid_constant__ DevParams
             if (__all_sync(ODEB_FULL, done)) break;
         }
         if (m_own > 0) for (int k = wid; k < 2 * nb; k += 2 * P) cf_out[2 * bstart + k] = CF5(bstart + (k >> 1), k & 1);
+        if (D.jcopy && m_own > 0) for (int i = wid; i < m_own; i += 2 * P) D.lambda[(size_t)w * Pm.MR + rstart + i] = lam[i * WPW];   // joint feedback
         __syncwarp();
     }
     if (leader && valid) {

@@ -344,6 +344,7 @@ __global__ void __launch_bounds__(32) k_solve_bl(const __grid_constant__ DevPara
             const Real4 a = { f0, f1, f2, f3 }, b = { f4, f5, fneg, fpos };
             cf_out[2 * (bstart + gl)] = a; cf_out[2 * (bstart + gl) + 1] = b;
         }
+        if (D.jcopy && m_own > 0) for (int i = gl; i < m_own; i += G) D.lambda[(size_t)w * P.MR + rstart + i] = lam[i];   // joint feedback
         __syncwarp();
     }
     if (gl == 0 && valid) {

@@ -70,6 +70,9 @@ struct World {
     std::vector<int> island_label; int island_count;
     unsigned long long sweeps;
     unsigned step_seed; int cur_island; unsigned long long draws;   // canonical mode bookkeeping
+    // joint feedback of the last step (dJointSetFeedback, quickstep.cpp:3108-3182): per joint id 12 reals f1 t1 f2 t2 and a
+    // state (0 = joint not stepped, 1 = body 1 only, 2 = both bodies)
+    std::vector<Real> fb; std::vector<int> fb_state;
 };
 
 struct Batch {
@@ -82,6 +85,7 @@ struct Batch {
     Real damp_lin_scale, damp_ang_scale, damp_lin_thr, damp_ang_thr, max_ang_speed;
     int nbody, ngeom, njoint;
     int canonical;                       // 1: canonical-order mode of the large-world path (see orc_set_solver_mode)
+    int feedback;                        // 1: every joint has a dJointFeedback attached
     std::vector<World> worlds;
 };
 
@@ -631,6 +635,9 @@ void quickstep_island(const Batch &B, World &W, const int *bodies, int nb, const
             int t0 = W.bodies[j.b0].tag, t1 = j.b1 >= 0 ? W.bodies[j.b1].tag : -1;
             for (int r = 0; r < infom; r++) { jb[2 * (ofs + r)] = t0; jb[2 * (ofs + r) + 1] = t1; }
         }
+        // Jcopy :1590-1606: the J blocks of joints with feedback, before any scaling
+        std::vector<Real> Jcopy;
+        if (B.feedback) Jcopy = J;
         // Stage2b :1644-1690
         for (int i = 0; i < nb; i++) {
             Body &b = W.bodies[bodies[i]];
@@ -786,6 +793,22 @@ void quickstep_island(const Batch &B, World &W, const int *bodies, int nb, const
             Body &b = W.bodies[bodies[i]];
             for (int k = 0; k < 3; k++) { b.lvel[k] += h * cforce[6 * i + k]; b.avel[k] += h * cforce[6 * i + 3 + k]; }
         }
+        // joint feedback :3108-3182 (Multiply1_12q1 :153-184: one running sum per component over the joint's rows)
+        if (B.feedback) for (int k = 0; k < nj; k++) {
+            const Joint &j = joint_ref(W, jl[k]);
+            Real *out = &W.fb[12 * (size_t)jl[k]];
+            for (int side = 0; side < 2; side++) {
+                if (side == 1 && j.b1 < 0) break;
+                Real acc[6] = { 0, 0, 0, 0, 0, 0 };
+                for (int r = 0; r < j.m; r++) {
+                    const Real *q = &Jcopy[(size_t)(mindex[k] + r) * ROW] + (side ? J2L : J1L);
+                    const Real sl = lambda[mindex[k] + r];
+                    for (int t = 0; t < 6; t++) acc[t] += q[t] * sl;
+                }
+                for (int t = 0; t < 6; t++) out[6 * side + t] = acc[t];
+            }
+            W.fb_state[jl[k]] = j.b1 < 0 ? 1 : 2;
+        }
     }
     W.stats[0]++;     // Stage5 :3201-3203
     // Stage6a :3299-3337
@@ -808,6 +831,10 @@ void quickstep_island(const Batch &B, World &W, const int *bodies, int nb, const
 void world_step(const Batch &B, World &W, Real h)
 {
     collide_world(B, W);
+    if (B.feedback) {
+        const size_t n = W.pjoints.size() + W.contacts.size();
+        W.fb.assign(12 * n, 0); W.fb_state.assign(n, 0);
+    }
     Islands isl;
     build_islands(B, W, h, isl);
     W.island_count = (int)isl.sizes.size() / 2;
@@ -850,7 +877,7 @@ void *orc_create(const OdebWorldParams *wp, int nbody, const OdebBodyDesc *bodie
 {
     if (wp->surf_mode & (ODEB_CONTACT_FDIR1 | 0x400)) return 0;
     Batch *B = new Batch;
-    B->wp = *wp; B->nbody = nbody; B->ngeom = ngeom; B->njoint = njoint; B->canonical = 0;
+    B->wp = *wp; B->nbody = nbody; B->ngeom = ngeom; B->njoint = njoint; B->canonical = 0; B->feedback = 0;
     for (int k = 0; k < 3; k++) B->gravity[k] = (Real)wp->gravity[k];
     B->erp = (Real)wp->erp;
 #if defined(ODEB_DOUBLE)
@@ -978,6 +1005,18 @@ int orc_add_force(void *h, const Real *force, const Real *torque)
 }
 
 int orc_set_solver_mode(void *h, int mode) { ((Batch *)h)->canonical = mode == ODEB_MODE_CANONICAL; return 1; }
+int orc_enable_feedback(void *h, int on) { ((Batch *)h)->feedback = on != 0; return 1; }
+int orc_get_feedback(void *h, int world, odeb_real *out12, int *state, int cap)
+{
+    Batch *B = (Batch *)h;
+    const World &W = B->worlds[world];
+    const int n = (int)W.fb_state.size();
+    for (int i = 0; i < n && i < cap; i++) {
+        for (int k = 0; k < 12; k++) out12[12 * i + k] = W.fb[12 * (size_t)i + k];
+        state[i] = W.fb_state[i];
+    }
+    return n;
+}
 int orc_set_seeds(void *h, const uint32_t *s) { Batch *B = (Batch *)h; for (size_t w = 0; w < B->worlds.size(); w++) B->worlds[w].seed = s[w]; return 1; }
 int orc_get_seeds(void *h, uint32_t *s) { Batch *B = (Batch *)h; for (size_t w = 0; w < B->worlds.size(); w++) s[w] = B->worlds[w].seed; return 1; }
 int orc_get_enabled(void *h, int *en)

@@ -47,11 +47,16 @@ struct RefWorld {
     std::vector<int> contact_g;          // 2 per contact
     std::vector<int> island_label;       // per body
     int island_count;
+    // joint feedback (dJointSetFeedback): storage for the permanent joints and for this step's contact joints
+    std::vector<dJointFeedback> fb_perm, fb_contact;
+    std::vector<dJointID> cjoints;
+    std::vector<dReal> fb; std::vector<int> fb_state;   // last step: 12 reals per joint id + 0/1/2 (not stepped / body 1 / both)
 };
 
 struct RefBatch {
     OdebWorldParams wp;
     int nbody, ngeom, njoint, nworlds;
+    int feedback;
     std::vector<RefWorld> worlds;
 };
 
@@ -121,7 +126,7 @@ void *ref_create(const OdebWorldParams *wp,
 {
     if (!g_init) { dInitODE2(0); dAllocateODEDataForThread(dAllocateMaskAll); g_init = 1; }
     RefBatch *B = new RefBatch;
-    B->wp = *wp; B->nbody = nbody; B->ngeom = ngeom; B->njoint = njoint; B->nworlds = nworlds;
+    B->wp = *wp; B->nbody = nbody; B->ngeom = ngeom; B->njoint = njoint; B->nworlds = nworlds; B->feedback = 0;
     B->worlds.resize(nworlds);
     for (int wi = 0; wi < nworlds; wi++) {
         RefWorld &W = B->worlds[wi];
@@ -244,6 +249,19 @@ int ref_add_force(void *h, const dReal *force, const dReal *torque)
     return 1;
 }
 
+int ref_enable_feedback(void *h, int on)
+{
+    RefBatch *B = (RefBatch *)h; B->feedback = on != 0;
+    if (!on) for (int w = 0; w < B->nworlds; w++) for (size_t k = 0; k < B->worlds[w].joints.size(); k++) dJointSetFeedback(B->worlds[w].joints[k], 0);
+    return 1;
+}
+int ref_get_feedback(void *h, int world, dReal *out12, int *state, int cap)
+{
+    RefBatch *B = (RefBatch *)h; const RefWorld &W = B->worlds[world];
+    const int n = (int)W.fb_state.size();
+    for (int i = 0; i < n && i < cap; i++) { for (int k = 0; k < 12; k++) out12[12 * i + k] = W.fb[12 * (size_t)i + k]; state[i] = W.fb_state[i]; }
+    return n;
+}
 int ref_set_seeds(void *h, const uint32_t *s) { RefBatch *B = (RefBatch *)h; for (int w = 0; w < B->nworlds; w++) B->worlds[w].seed = s[w]; return 1; }
 int ref_get_seeds(void *h, uint32_t *s) { RefBatch *B = (RefBatch *)h; for (int w = 0; w < B->nworlds; w++) s[w] = B->worlds[w].seed; return 1; }
 int ref_get_enabled(void *h, int *en)
@@ -259,7 +277,7 @@ static void ref_collide_world(RefBatch *B, RefWorld &W)
     CbCtx ctx; ctx.w = &W;
     dSpaceCollide(W.space, &ctx, &near_cb);
     std::sort(ctx.buf.begin(), ctx.buf.end());
-    W.pairs.clear(); W.contacts.clear(); W.contact_g.clear();
+    W.pairs.clear(); W.contacts.clear(); W.contact_g.clear(); W.cjoints.clear();
     dContact contact[8];
     for (size_t k = 0; k < ctx.buf.size(); k++) {
         int i1 = ctx.buf[k].first, i2 = ctx.buf[k].second;
@@ -279,6 +297,7 @@ static void ref_collide_world(RefBatch *B, RefWorld &W)
             s.slip1 = (dReal)p.slip1; s.slip2 = (dReal)p.slip2;
             dJointID c = dJointCreateContact(W.world, W.group, &contact[i]);
             dJointAttach(c, b1, b2);
+            W.cjoints.push_back(c);
             W.contacts.push_back(contact[i].geom);
             W.contact_g.push_back(i1); W.contact_g.push_back(i2);
         }
@@ -314,7 +333,29 @@ int ref_step(void *h, double hstep, int nsteps)
             RefWorld &W = B->worlds[w];
             dRandSetSeed(W.seed);
             ref_collide_world(B, W);
+            const dReal NOTSET = (dReal)-12345.678;
+            if (B->feedback) {   // a dJointFeedback on every joint, pre-filled with a marker the step overwrites
+                dJointFeedback mark;
+                for (int k = 0; k < 4; k++) { mark.f1[k] = mark.t1[k] = mark.f2[k] = mark.t2[k] = NOTSET; }
+                W.fb_perm.assign(W.joints.size(), mark); W.fb_contact.assign(W.cjoints.size(), mark);
+                for (size_t k = 0; k < W.joints.size(); k++) dJointSetFeedback(W.joints[k], &W.fb_perm[k]);
+                for (size_t k = 0; k < W.cjoints.size(); k++) dJointSetFeedback(W.cjoints[k], &W.fb_contact[k]);
+            }
             if (!ref_quickstep_world(B, W, (dReal)hstep)) return 0;
+            if (B->feedback) {
+                const size_t np = W.joints.size(), n = np + W.cjoints.size();
+                W.fb.assign(12 * n, 0); W.fb_state.assign(n, 0);
+                for (size_t i = 0; i < n; i++) {
+                    const dJointFeedback &f = i < np ? W.fb_perm[i] : W.fb_contact[i - np];
+                    if (f.f1[0] == NOTSET) continue;
+                    const bool two = f.f2[0] != NOTSET;
+                    W.fb_state[i] = two ? 2 : 1;
+                    for (int k = 0; k < 3; k++) {
+                        W.fb[12 * i + k] = f.f1[k]; W.fb[12 * i + 3 + k] = f.t1[k];
+                        if (two) { W.fb[12 * i + 6 + k] = f.f2[k]; W.fb[12 * i + 9 + k] = f.t2[k]; }
+                    }
+                }
+            }
             dJointGroupEmpty(W.group);
             W.seed = (uint32_t)dRandGetSeed();
         }

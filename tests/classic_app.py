@@ -32,10 +32,13 @@ def make_types(real):
     class dMass(C.Structure):
         _fields_ = [("mass", real), ("c", real * 4), ("I", real * 12)]
 
+    class dJointFeedback(C.Structure):
+        _fields_ = [("f1", real * 4), ("t1", real * 4), ("f2", real * 4), ("t2", real * 4)]
+
     class Stats(C.Structure):
         _fields_ = [("struct_size", C.c_uint), ("iteration_count", C.c_uint32), ("premature_exits", C.c_uint32),
                     ("prolonged_execs", C.c_uint32), ("full_extra_execs", C.c_uint32)]
-    return dSurfaceParameters, dContactGeom, dContact, dMass, Stats
+    return dSurfaceParameters, dContactGeom, dContact, dMass, Stats, dJointFeedback
 
 
 class Ode:
@@ -45,7 +48,7 @@ class Ode:
         self.lib = L = C.CDLL(path)
         self.real = real
         self.np_real = np.float32 if real is C.c_float else np.float64
-        self.dSurfaceParameters, self.dContactGeom, self.dContact, self.dMass, self.Stats = make_types(real)
+        self.dSurfaceParameters, self.dContactGeom, self.dContact, self.dMass, self.Stats, self.dJointFeedback = make_types(real)
         vp, r, i = C.c_void_p, real, C.c_int
         self.NearCallback = C.CFUNCTYPE(None, vp, vp, vp)
         sig = {
@@ -76,7 +79,7 @@ class Ode:
             "dJointSetBallAnchor": (None, [vp, r, r, r]), "dJointSetHingeAnchor": (None, [vp, r, r, r]), "dJointSetHingeAxis": (None, [vp, r, r, r]),
             "dJointSetHingeParam": (None, [vp, i, r]), "dJointSetUniversalAnchor": (None, [vp, r, r, r]),
             "dJointSetUniversalAxis1": (None, [vp, r, r, r]), "dJointSetUniversalAxis2": (None, [vp, r, r, r]),
-            "dJointSetUniversalParam": (None, [vp, i, r]), "dAreConnectedExcluding": (i, [vp, vp, i]), "dAreConnected": (i, [vp, vp]),
+            "dJointSetUniversalParam": (None, [vp, i, r]), "dJointSetFeedback": (None, [vp, vp]), "dJointGetFeedback": (vp, [vp]), "dAreConnectedExcluding": (i, [vp, vp, i]), "dAreConnected": (i, [vp, vp]),
         }
         for name, (res, args) in sig.items():
             f = getattr(L, name)
@@ -108,6 +111,11 @@ class App:
         self.ncontacts = 0
         self.contact_log = []
         self._cb = o.NearCallback(self._near)
+        # dJointSetFeedback: structs for permanent joints (attach_feedback) and, when contact_feedback is set, for every
+        # contact joint of the step; filled with a marker so that "not written by the step" is observable
+        self.feedback = []
+        self.contact_feedback = False
+        self.contact_fb = []
 
     # ---- scene building
     def _add_geom(self, g, body):
@@ -180,9 +188,31 @@ class App:
                     s.mode, s.mu = 0, float("inf")
                 j = o.dJointCreateContact(self.world, self.group, C.byref(arr[k]))
                 o.dJointAttach(j, b1, b2)
+                if self.contact_feedback:
+                    self.contact_fb.append(self._new_feedback(j))
                 g = arr[k].geom
                 self.contact_log.append((i1, i2, tuple(g.pos)[:3], tuple(g.normal)[:3], g.depth))
                 self.ncontacts += 1
+
+    MARK = -4321.5
+
+    def _new_feedback(self, joint):
+        fb = self.o.dJointFeedback()
+        for v in (fb.f1, fb.t1, fb.f2, fb.t2):
+            for k in range(4):
+                v[k] = self.MARK
+        self.o.dJointSetFeedback(joint, C.byref(fb))
+        return fb
+
+    def attach_feedback(self, joint):
+        self.feedback.append(self._new_feedback(joint))
+
+    def feedback_values(self):
+        """[n, 12] f1 t1 f2 t2 of the permanent joints with feedback, then of the step's contact joints"""
+        out = []
+        for fb in self.feedback + self.contact_fb:
+            out.append([fb.f1[0], fb.f1[1], fb.f1[2], fb.t1[0], fb.t1[1], fb.t1[2], fb.f2[0], fb.f2[1], fb.f2[2], fb.t2[0], fb.t2[1], fb.t2[2]])
+        return np.array(out, self.o.np_real).reshape(-1, 12)
 
     def step(self, h, seed=None):
         o = self.o
@@ -190,6 +220,7 @@ class App:
             o.dRandSetSeed(seed)
         self.pairs = []
         self.contact_log = []
+        self.contact_fb = []
         o.dSpaceCollide(self.space, None, self._cb)
         self._make_contacts()
         ok = o.dWorldQuickStep(self.world, h)
@@ -268,4 +299,5 @@ def scene_linkage(app):
             j = o.dJointCreateBall(app.world, None)
             o.dJointAttach(j, a, b)
             o.dJointSetBallAnchor(j, x, 0.0, 1.0)
+        app.perm_joints = getattr(app, "perm_joints", []) + [j]
     return bs

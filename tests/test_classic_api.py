@@ -48,8 +48,8 @@ def test_exports_every_declared_classic_symbol(prec):
 @pytest.mark.parametrize("prec", ("single", "double"))
 def test_struct_layouts(prec):
     """sizes the C compiler gives the header's structs == the ctypes mirrors the application uses"""
-    src = ('#include "ode_b200_classic.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu\\n", sizeof(dSurfaceParameters),'
-           ' sizeof(dContactGeom), sizeof(dContact), sizeof(dMass), sizeof(dWorldQuickStepIterationCount_DynamicAdjustmentStatistics));return 0;}\n')
+    src = ('#include "ode_b200_classic.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(dSurfaceParameters),'
+           ' sizeof(dContactGeom), sizeof(dContact), sizeof(dMass), sizeof(dWorldQuickStepIterationCount_DynamicAdjustmentStatistics), sizeof(dJointFeedback));return 0;}\n')
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "t.c"), "w").write(src)
         flags = ["-DODEB_DOUBLE"] if prec == "double" else []
@@ -223,3 +223,33 @@ def test_classic_linkage_joints(prec):
     atan2 -> tolerance as in tests/test_gpu_parity.py)"""
     apps = _run_both(prec, A.scene_linkage, 100, 0.01, space="hash", max_contacts=4, surface="chain")
     _compare(apps, 100, 0.01, exact=False, tol=5e-4 if prec == "single" else 1e-9)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec", ("single", "double"))
+def test_classic_joint_feedback(prec):
+    """dJointSetFeedback on permanent joints (hinge / universal / ball, two-body) and on every contact joint of the step
+    (one-body plane contacts and two-body contacts): the reference and the B200 library write the same components and leave
+    the same ones untouched (marker)."""
+    def build(a):
+        A.scene_linkage(a)
+        for j in a.perm_joints:
+            a.attach_feedback(j)
+        a.contact_feedback = True
+    apps = _run_both(prec, build, 60, 0.01, space="hash", max_contacts=4, surface="approx1")
+    ra, ga = apps
+    tol = 5e-3 if prec == "single" else 1e-8        # hinge / universal angles go through atan2 (CUDA libm vs glibc)
+    wrote = 0
+    for s in range(60):
+        assert ra.step(0.01, seed=100 + s) == 1 and ga.step(0.01, seed=100 + s) == 1
+        fr, fg = ra.feedback_values(), ga.feedback_values()
+        assert fr.shape == fg.shape
+        mr, mg = fr == A.App.MARK, fg == A.App.MARK
+        assert np.array_equal(mr, mg), "step %d: different components written" % s
+        wrote += int((~mr).sum())
+        d = np.abs(fr.astype(np.float64) - fg)[~mr]
+        scale = max(1.0, float(np.abs(fr[~mr]).max())) if d.size else 1.0
+        assert d.size == 0 or d.max() <= tol * scale, "step %d: feedback differs by %.3g" % (s, d.max())
+    assert wrote > 0
+    ra.close()
+    ga.close()

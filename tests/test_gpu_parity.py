@@ -242,3 +242,28 @@ def test_solver_kernels_agree_at_bench_size(monkeypatch):
             for k in ("pos", "quat", "lvel", "avel"):
                 assert np.array_equal(ref[0][k], st[k]), (solver, k)
             assert np.array_equal(ref[1], seeds), solver
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("solver", ("v4", "p4", "bl"))
+def test_joint_feedback_bit_exact(prec, solver, monkeypatch):
+    """Joint feedback (dJointSetFeedback, quickstep.cpp:3108-3182) through the batch C-ABI: f1/t1/f2/t2 and the written /
+    not-written state of every joint, CUDA path against the oracle, with every solver kernel (each writes lambda out)."""
+    from test_oracle import compare_feedback
+    monkeypatch.setenv("ODEB_SOLVER", solver)
+    for name, mk, h, n, exact in (("stack", lambda: scenes.box_stack(nworlds=5, nboxes=6), 0.02, 50, True),
+                                  ("chain", lambda: scenes.chain(3), 0.05, 50, True),
+                                  ("ragdoll", lambda: scenes.ragdoll(2), 0.01, 30, False)):
+        sc = mk()
+        a, b = B.Batch(orc_lib(prec), sc), B.Batch(gpu_lib(prec), sc)
+        a.enable_feedback()
+        b.enable_feedback()
+        for s in range(n):
+            a.step(h)
+            b.step(h)
+            if exact:
+                bad = compare_step(a, b, sc.nworlds)
+                assert not bad, (name, s, bad)
+            bad = compare_feedback(a, b, sc.nworlds, exact, 2e-2 if prec == "single" else 1e-8)
+            assert not bad, (name, solver, s, bad[:4])
+        b.close()

@@ -120,3 +120,47 @@ def test_edge_cases(prec):
                 a.step(0.01)
                 bad = compare_step(a, b, sc.nworlds)
                 assert not bad, bad
+
+
+def _feedback_scenes():
+    return (("stack", lambda: scenes.box_stack(nworlds=2, nboxes=6), 0.02, 60, True),
+            ("chain", lambda: scenes.chain(2), 0.05, 60, True),
+            ("ragdoll", lambda: scenes.ragdoll(2), 0.01, 40, False))
+
+
+def compare_feedback(a, b, nworlds, exact, tol):
+    bad = []
+    for w in range(nworlds):
+        (fa, sa), (fb, sb) = a.get_feedback(w), b.get_feedback(w)
+        if fa.shape != fb.shape or not np.array_equal(sa, sb):
+            bad.append("world %d: feedback joint count / state differ (%d vs %d)" % (w, len(sa), len(sb)))
+            continue
+        for i in range(len(sa)):
+            k = 0 if sa[i] == 0 else 6 if sa[i] == 1 else 12
+            if exact and not np.array_equal(fa[i, :k], fb[i, :k]):
+                bad.append("world %d joint %d: feedback differs by %.3g" % (w, i, np.abs(fa[i, :k] - fb[i, :k]).max()))
+            elif not exact and k and np.abs(fa[i, :k].astype(np.float64) - fb[i, :k]).max() > tol:
+                bad.append("world %d joint %d: feedback differs by %.3g > %.3g" % (w, i, np.abs(fa[i, :k].astype(np.float64) - fb[i, :k]).max(), tol))
+    return bad
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_joint_feedback_vs_reference(prec):
+    """dJointSetFeedback on every joint (permanent joints and the step's contact joints): f1/t1/f2/t2 and which of them the
+    step wrote, restatement against the compiled reference. Bit-exact where the path has no libm call."""
+    ref = ref_lib(prec)
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    for name, mk, h, n, exact in _feedback_scenes():
+        sc = mk()
+        a, b = B.Batch(ref, sc), B.Batch(orc_lib(prec), sc)
+        a.enable_feedback()
+        b.enable_feedback()
+        seen = 0
+        for s in range(n):
+            a.step(h)
+            b.step(h)
+            bad = compare_feedback(a, b, sc.nworlds, exact, 1e-3 if prec == "single" else 1e-9)
+            assert not bad, (name, s, bad[:4])
+            seen += int((a.get_feedback(0)[1] > 0).sum())
+        assert seen > 0, name
