@@ -40,7 +40,7 @@ typedef float odeb_real;
 /* geom classes: numbering of the reference (include/ode/collision.h:881-902) */
 enum { ODEB_SPHERE = 0, ODEB_BOX = 1, ODEB_CAPSULE = 2, ODEB_PLANE = 4 };
 /* joint types: numbering of the reference dJointType (include/ode/common.h:406-426) */
-enum { ODEB_JOINT_BALL = 1, ODEB_JOINT_HINGE = 2, ODEB_JOINT_CONTACT = 4, ODEB_JOINT_UNIVERSAL = 5 };
+enum { ODEB_JOINT_BALL = 1, ODEB_JOINT_HINGE = 2, ODEB_JOINT_CONTACT = 4, ODEB_JOINT_UNIVERSAL = 5, ODEB_JOINT_FIXED = 7 };
 /* broadphase flavours: which reference space's callback stream is reproduced (as a set) */
 enum { ODEB_SPACE_HASH = 0, ODEB_SPACE_SAP = 1 };
 
@@ -106,7 +106,7 @@ typedef struct OdebGeomDesc {
 } OdebGeomDesc;
 
 typedef struct OdebJointDesc {
-    int    type;                /* ODEB_JOINT_BALL | ODEB_JOINT_HINGE | ODEB_JOINT_UNIVERSAL */
+    int    type;                /* ODEB_JOINT_BALL | ODEB_JOINT_HINGE | ODEB_JOINT_UNIVERSAL | ODEB_JOINT_FIXED (dJointSetFixed at the template pose) */
     int    body1, body2;        /* dJointAttach(j, body1, body2); -1 = the static environment */
     double anchor[3];           /* dJointSet*Anchor, world frame at the template pose */
     double axis1[3], axis2[3];  /* dJointSetHingeAxis / dJointSetUniversalAxis1,2 */
@@ -167,6 +167,14 @@ int odeb_set_solver_mode(OdebBatch *, int mode);
  * are not written by the reference either), 2 (both bodies). Returns the number of joints (may exceed cap), -1 on error. */
 int odeb_enable_feedback(OdebBatch *, int on);
 int odeb_get_feedback(OdebBatch *, int world, odeb_real *out12, int *state, int cap);
+
+/* Checkpoint / resume: everything a step reads from earlier steps (body state, rotation matrices, force accumulators, enable
+ * flags, auto-disable history, per-world dRand seeds, iteration statistics) as one host blob. Restoring into a batch created
+ * from the same template continues bit-identically. (The reference offers only the text dump dWorldExportDIF,
+ * include/ode/export-dif.h:33.) */
+size_t odeb_snapshot_size(OdebBatch *);
+int odeb_snapshot(OdebBatch *, void *buf, size_t cap);
+int odeb_restore(OdebBatch *, const void *buf, size_t bytes);
 
 #if defined(__CUDACC__)
 #define ODEB_HD __host__ __device__

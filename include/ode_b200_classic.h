@@ -17,7 +17,7 @@
  * getters return pointers into library storage (ode.cpp:413-484).  There is no CPU implementation of any of these
  * stages: without a CUDA device dWorldQuickStep returns 0 and dSpaceCollide reports through the error handler.
  *
- * Outside the subset (calls are not exported): dWorldStep, joints other than contact/ball/hinge/universal, geoms other
+ * Outside the subset (calls are not exported): dWorldStep, joints other than contact/ball/hinge/universal/fixed, geoms other
  * than sphere/box/capsule/plane, geom offsets, nested spaces, rolling friction, per-body
  * auto-disable thresholds (the world's are used), SAP axis orders other than dSAP_AXES_XYZ.
  */
@@ -244,6 +244,10 @@ void dJointGroupEmpty(dJointGroupID);
 dJointID dJointCreateContact(dWorldID, dJointGroupID, const dContact *);
 dJointID dJointCreateBall(dWorldID, dJointGroupID);
 dJointID dJointCreateHinge(dWorldID, dJointGroupID);
+dJointID dJointCreateFixed(dWorldID, dJointGroupID);            /* joints/fixed.cpp */
+void dJointSetFixed(dJointID);
+void dJointSetFixedParam(dJointID, int parameter, dReal value);
+dReal dJointGetFixedParam(dJointID, int parameter);
 dJointID dJointCreateUniversal(dWorldID, dJointGroupID);
 void dJointDestroy(dJointID);
 void dJointAttach(dJointID, dBodyID body1, dBodyID body2);

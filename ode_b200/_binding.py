@@ -53,7 +53,7 @@ class OdebStats(C.Structure):
 
 
 SPHERE, BOX, CAPSULE, PLANE = 0, 1, 2, 4
-JOINT_BALL, JOINT_HINGE, JOINT_CONTACT, JOINT_UNIVERSAL = 1, 2, 4, 5
+JOINT_BALL, JOINT_HINGE, JOINT_CONTACT, JOINT_UNIVERSAL, JOINT_FIXED = 1, 2, 4, 5, 7
 SPACE_HASH, SPACE_SAP = 0, 1
 CONTACT_MU2, CONTACT_BOUNCE, CONTACT_SOFT_ERP, CONTACT_SOFT_CFM = 0x001, 0x004, 0x008, 0x010
 CONTACT_MOTION1, CONTACT_MOTION2, CONTACT_MOTIONN = 0x020, 0x040, 0x080
@@ -289,6 +289,25 @@ class Batch:
             raise RuntimeError("%sget_feedback failed" % self.slib.prefix)
         n = min(n, cap)
         return out[:n].copy(), st[:n].copy()
+
+    def snapshot(self):
+        f = self.slib._fn("snapshot_size")
+        f.restype = C.c_size_t
+        f.argtypes = [C.c_void_p]
+        n = f(self.h)
+        buf = np.empty(n, np.uint8)
+        g = self.slib._fn("snapshot")
+        g.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        if not g(self.h, buf.ctypes.data, n):
+            raise RuntimeError("%ssnapshot failed" % self.slib.prefix)
+        return buf
+
+    def restore(self, buf):
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        g = self.slib._fn("restore")
+        g.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        if not g(self.h, buf.ctypes.data, buf.size):
+            raise RuntimeError("%srestore failed" % self.slib.prefix)
 
     def set_seeds(self, seeds):
         s = np.ascontiguousarray(np.asarray(seeds, dtype=np.uint32).reshape(self.W))

@@ -378,7 +378,7 @@ static void limot_set(DLimot &l, int num, Real value)
 static void joint_set_relative_values(dxJoint *j)
 {   // dxJoint*::setRelativeValues (ball.cpp:179-185, hinge.cpp:359-369, universal.cpp:785-808): called by dJointAttach
     DJointT &t = j->t;
-    if (j->type == dJointTypeContact) return;
+    if (j->type == dJointTypeContact || j->type == dJointTypeFixed) return;     // dxJointFixed keeps offset / qrel until dJointSetFixed
     Real anchor[3] = { 0, 0, 0 };
     if (j->reverse) joint_get_anchor2(j, t.anchor2, anchor); else joint_get_anchor(j, t.anchor1, anchor);     // dJointGet{Ball,Hinge,Universal}Anchor
     std::vector<HostBody> hb = joint_bodies(j, t);
@@ -741,6 +741,20 @@ dJointID dJointCreateContact(dWorldID w, dJointGroupID g, const dContact *c)
 dJointID dJointCreateBall(dWorldID w, dJointGroupID g) { return new_joint(w, g, dJointTypeBall); }
 dJointID dJointCreateHinge(dWorldID w, dJointGroupID g) { return new_joint(w, g, dJointTypeHinge); }
 dJointID dJointCreateUniversal(dWorldID w, dJointGroupID g) { return new_joint(w, g, dJointTypeUniversal); }
+dJointID dJointCreateFixed(dWorldID w, dJointGroupID g) { return new_joint(w, g, dJointTypeFixed); }
+void dJointSetFixed(dJointID j)
+{   // fixed.cpp:113-136
+    std::vector<HostBody> hb = joint_bodies(j, j->t);
+    host_set_fixed(hb, j->t);
+}
+void dJointSetFixedParam(dJointID j, int parameter, Real value)
+{   // fixed.cpp:138-149
+    if (parameter == dParamCFM) j->t.cfm = value; else if (parameter == dParamERP) j->t.erp = value;
+}
+Real dJointGetFixedParam(dJointID j, int parameter)
+{
+    return parameter == dParamCFM ? j->t.cfm : parameter == dParamERP ? j->t.erp : 0;
+}
 void dJointDestroy(dJointID j)
 {   // ode.cpp:1301-1321: grouped joints are only destroyed through their group
     if (j->group) return;

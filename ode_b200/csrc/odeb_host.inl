@@ -146,6 +146,18 @@ static void host_hinge_initial_rotation(const std::vector<HostBody> &hb, DJointT
     if (j.b1 >= 0) qmul1(j.qrel, hb[j.b0].q, hb[j.b1].q);
     else { const Real *q = hb[j.b0].q; j.qrel[0] = q[0]; j.qrel[1] = -q[1]; j.qrel[2] = -q[2]; j.qrel[3] = -q[3]; }
 }
+// dJointSetFixed fixed.cpp:113-142: offset between the bodies in body 1's frame (anchor1) + computeInitialRelativeRotation
+static void host_set_fixed(const std::vector<HostBody> &hb, DJointT &j)
+{
+    if (j.b0 < 0) return;
+    const HostBody &b0 = hb[j.b0];
+    if (j.b1 >= 0) {
+        Real ofs[3] = { b0.pos[0] - hb[j.b1].pos[0], b0.pos[1] - hb[j.b1].pos[1], b0.pos[2] - hb[j.b1].pos[2] };
+        mul1_331(j.anchor1, b0.R, ofs);
+    } else { j.anchor1[0] = b0.pos[0]; j.anchor1[1] = b0.pos[1]; j.anchor1[2] = b0.pos[2]; }
+    j.anchor1[3] = 0;
+    host_hinge_initial_rotation(hb, j);          // fixed.cpp:172-192 is the same formula as hinge.cpp:376-393
+}
 // universal.cpp:372-401 computeInitialRelativeRotations
 static void host_universal_initial_rotations(const std::vector<HostBody> &hb, DJointT &j)
 {
@@ -474,7 +486,7 @@ OdebBatch *odeb_create(const OdebWorldParams *wp,
         const OdebJointDesc &d = joints[i];
         DJointT &j = T.jt[i];
         memset(&j, 0, sizeof(j));
-        if (d.type != ODEB_JOINT_BALL && d.type != ODEB_JOINT_HINGE && d.type != ODEB_JOINT_UNIVERSAL) { set_err("joint %d: unsupported type %d", i, d.type); return 0; }
+        if (d.type != ODEB_JOINT_BALL && d.type != ODEB_JOINT_HINGE && d.type != ODEB_JOINT_UNIVERSAL && d.type != ODEB_JOINT_FIXED) { set_err("joint %d: unsupported type %d", i, d.type); return 0; }
         j.type = d.type; j.erp = erp; j.cfm = cfm;
         int b1 = d.body1, b2 = d.body2;
         if (b1 >= nbody || b2 >= nbody || (b1 < 0 && b2 < 0) || b1 == b2) { set_err("joint %d: bad bodies", i); return 0; }
@@ -485,7 +497,8 @@ OdebBatch *odeb_create(const OdebWorldParams *wp,
         host_set_anchors(hb, j, (Real)d.anchor[0], (Real)d.anchor[1], (Real)d.anchor[2]);
         host_limot(j.limot1, erp, cfm, d, 0);
         host_limot(j.limot2, erp, cfm, d, 1);
-        if (j.type == ODEB_JOINT_HINGE) {
+        if (j.type == ODEB_JOINT_FIXED) host_set_fixed(hb, j);
+        else if (j.type == ODEB_JOINT_HINGE) {
             j.axis1[0] = 1; j.axis2[0] = 1;
             host_set_axes(hb, j, (Real)d.axis1[0], (Real)d.axis1[1], (Real)d.axis1[2], j.axis1, j.axis2);
             host_hinge_initial_rotation(hb, j);
@@ -791,6 +804,55 @@ int odeb_get_feedback(OdebBatch *B, int world, odeb_real *out12, int *state, int
         state[i] = (int)q[0].w;
     }
     return n;
+}
+
+// ---- snapshot / restore of everything a step reads from earlier steps (checkpoint / resume; the reference only has the
+//      text dump of dWorldExportDIF, ode/src/export-dif.cpp). Layout: header {magic, sizeof(real), W, NB, samples}, then the arrays.
+struct SnapItem { void *p; size_t bytes; };
+static std::vector<SnapItem> snapshot_items(OdebBatch *B)
+{
+    const DevPtrs &D = B->D; const size_t WB = (size_t)B->P.W * B->P.NB, W = B->P.W;
+    const size_t NS = B->P.adis_samples > 0 ? B->P.adis_samples : 1;
+    std::vector<SnapItem> v;
+    SnapItem it[] = { { D.pos, WB * sizeof(Real4) }, { D.quat, WB * sizeof(Real4) }, { D.lvel, WB * sizeof(Real4) }, { D.avel, WB * sizeof(Real4) },
+                      { D.facc, WB * sizeof(Real4) }, { D.tacc, WB * sizeof(Real4) }, { D.R, 3 * WB * sizeof(Real4) },
+                      { D.bflags, WB * sizeof(int) }, { D.adis_steps, WB * sizeof(int) }, { D.adis_time, WB * sizeof(Real) },
+                      { D.avg_buf, WB * 6 * NS * sizeof(Real) }, { D.avg_counter, WB * sizeof(int) }, { D.avg_ready, WB * sizeof(int) },
+                      { D.seed, W * sizeof(unsigned) }, { D.stats, 4 * W * sizeof(unsigned) } };
+    for (size_t i = 0; i < sizeof(it) / sizeof(it[0]); i++) v.push_back(it[i]);
+    return v;
+}
+size_t odeb_snapshot_size(OdebBatch *B)
+{
+    size_t n = 5 * sizeof(uint64_t);
+    std::vector<SnapItem> v = snapshot_items(B);
+    for (size_t i = 0; i < v.size(); i++) n += v[i].bytes;
+    return n;
+}
+int odeb_snapshot(OdebBatch *B, void *buf, size_t cap)
+{
+    CK(cudaSetDevice(B->device));
+    CK(cudaStreamSynchronize(B->stream));
+    if (cap < odeb_snapshot_size(B)) { set_err("snapshot buffer too small"); return 0; }
+    uint64_t hdr[5] = { 0x4f44454232303053ull, sizeof(Real), (uint64_t)B->P.W, (uint64_t)B->P.NB, (uint64_t)(B->P.adis_samples > 0 ? B->P.adis_samples : 1) };
+    char *o = (char *)buf; memcpy(o, hdr, sizeof(hdr)); o += sizeof(hdr);
+    std::vector<SnapItem> v = snapshot_items(B);
+    for (size_t i = 0; i < v.size(); i++) { CK(cudaMemcpy(o, v[i].p, v[i].bytes, cudaMemcpyDeviceToHost)); o += v[i].bytes; }
+    return 1;
+}
+int odeb_restore(OdebBatch *B, const void *buf, size_t bytes)
+{
+    CK(cudaSetDevice(B->device));
+    CK(cudaStreamSynchronize(B->stream));
+    uint64_t hdr[5];
+    if (bytes < sizeof(hdr) || bytes != odeb_snapshot_size(B)) { set_err("snapshot does not match this batch (size)"); return 0; }
+    memcpy(hdr, buf, sizeof(hdr));
+    if (hdr[0] != 0x4f44454232303053ull || hdr[1] != sizeof(Real) || hdr[2] != (uint64_t)B->P.W || hdr[3] != (uint64_t)B->P.NB
+        || hdr[4] != (uint64_t)(B->P.adis_samples > 0 ? B->P.adis_samples : 1)) { set_err("snapshot does not match this batch (header)"); return 0; }
+    const char *o = (const char *)buf + sizeof(hdr);
+    std::vector<SnapItem> v = snapshot_items(B);
+    for (size_t i = 0; i < v.size(); i++) { CK(cudaMemcpy(v[i].p, o, v[i].bytes, cudaMemcpyHostToDevice)); o += v[i].bytes; }
+    return 1;
 }
 
 uint64_t odeb_launch_count(const OdebBatch *B) { return B->launches; }

@@ -171,6 +171,7 @@ __device__ void odeb_joint_info1(const DJointT &j, const DBody &b0, const DBody 
 {
     ls->limit1 = ls->limit2 = 0; ls->err1 = ls->err2 = 0;
     if (j.type == 1) { *m = 3; return; }
+    if (j.type == 7) { *m = 6; return; }           // fixed.cpp:52-57
     if (j.type == 2) {
         int mm = (j.limot1.fmax > 0) ? 6 : 5;
         if ((j.limot1.lostop >= -M_PI || j.limot1.histop <= M_PI) && j.limot1.lostop <= j.limot1.histop) {
@@ -194,7 +195,21 @@ __device__ void odeb_joint_info1(const DJointT &j, const DBody &b0, const DBody 
     *m = mm;
 }
 
-// getInfo2 of ball (ball.cpp:57-67), hinge (hinge.cpp:77-147), universal (universal.cpp:297-369).
+// setFixedOrientation joints/joint.cpp:228-284: three rows that keep the relative rotation at qrel
+__device__ void odeb_set_fixed_orientation(const DBody &b0, const DBody *b1, Real fps, Real erp, Real *row, const Real *qrel)
+{
+    row[C_J1A] = 1; row[ROWLEN + C_J1A + 1] = 1; row[2 * ROWLEN + C_J1A + 2] = 1;
+    if (b1) { row[C_J2A] = -1; row[ROWLEN + C_J2A + 1] = -1; row[2 * ROWLEN + C_J2A + 2] = -1; }
+    Real qerr[4], e[3];
+    if (b1) { Real qq[4]; qmul1(qq, b0.q, b1->q); qmul2(qerr, qq, qrel); }
+    else odeb_qmul3(qerr, b0.q, qrel);
+    if (qerr[0] < 0) { qerr[1] = -qerr[1]; qerr[2] = -qerr[2]; qerr[3] = -qerr[3]; }
+    mul0_331(e, b0.R, qerr + 1);
+    const Real k2 = fps * erp * R_(2.0);
+    row[C_RHS] = k2 * e[0]; row[ROWLEN + C_RHS] = k2 * e[1]; row[2 * ROWLEN + C_RHS] = k2 * e[2];
+}
+
+// getInfo2 of ball (ball.cpp:57-67), hinge (hinge.cpp:77-147), universal (universal.cpp:297-369), fixed (fixed.cpp:60-110).
 // tq0 accumulates the torque the limit motors add to body0 (negated) / body1.
 __device__ void odeb_joint_info2(const DJointT &j, const DLimitState &ls, const DBody &b0, const DBody *b1,
                                  Real fps, Real worldERP, Real *row, Real *tq, bool *has_tq)
@@ -202,6 +217,24 @@ __device__ void odeb_joint_info2(const DJointT &j, const DLimitState &ls, const 
     if (j.type == 1) {
         row[C_CFM] = j.cfm; row[ROWLEN + C_CFM] = j.cfm; row[2 * ROWLEN + C_CFM] = j.cfm;
         odeb_set_ball(b0, b1, fps, j.erp, row, j.anchor1, j.anchor2);
+        return;
+    }
+    if (j.type == 7) {   // fixed.cpp:60-110; the body-1 relative offset of dJointSetFixed travels in anchor1
+        odeb_set_fixed_orientation(b0, b1, fps, worldERP, row + 3 * ROWLEN, j.qrel);
+        row[C_J1L] = 1; row[ROWLEN + C_J1L + 1] = 1; row[2 * ROWLEN + C_J1L + 2] = 1;
+        const Real k = fps * j.erp;
+        Real ofs[3];
+        mul0_331(ofs, b0.R, j.anchor1);
+        if (b1) {
+            row[C_J1A + 1] = -ofs[2]; row[C_J1A + 2] = +ofs[1];                                  // dSetCrossMatrixPlus odemath.h:277-286
+            row[ROWLEN + C_J1A + 0] = +ofs[2]; row[ROWLEN + C_J1A + 2] = -ofs[0];
+            row[2 * ROWLEN + C_J1A + 0] = -ofs[1]; row[2 * ROWLEN + C_J1A + 1] = +ofs[0];
+            row[C_J2L] = -1; row[ROWLEN + C_J2L + 1] = -1; row[2 * ROWLEN + C_J2L + 2] = -1;
+            for (int t = 0; t < 3; t++) row[t * ROWLEN + C_RHS] = k * (b1->pos[t] - b0.pos[t] + ofs[t]);
+        } else {
+            for (int t = 0; t < 3; t++) row[t * ROWLEN + C_RHS] = k * (j.anchor1[t] - b0.pos[t]);
+        }
+        row[C_CFM] = j.cfm; row[ROWLEN + C_CFM] = j.cfm; row[2 * ROWLEN + C_CFM] = j.cfm;
         return;
     }
     odeb_set_ball(b0, b1, fps, worldERP, row, j.anchor1, j.anchor2);

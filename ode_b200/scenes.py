@@ -100,6 +100,35 @@ def chain(nworlds=1, nlinks=10, seed0=7):
     return sc
 
 
+def compound(nworlds=1, seed0=31):
+    """Fixed joints (dJointCreateFixed + dJointSetFixed): per world two L-shaped compounds of three boxes welded together
+    and one box welded to the environment, dropped on / resting over a plane, plus a ball joint between the compounds.
+    Contacts: <= 4 per pair, mode 0, mu = inf (no libm on the path: bit-exact scenes)."""
+    sc = B.Scene(B.default_world_params(gravity=(0, 0, -2.0), cfm=1e-5, max_contacts=4, surf_mode=0, mu=B.INF, skip_connected=1), nworlds)
+    sc.add_geom(B.PLANE, (0, 0, 1, 0))
+    m, I = B.box_mass(2.0, 0.3, 0.2, 0.2)
+    centres = [(0.0, 0.0, 0.6), (0.3, 0.0, 0.6), (0.3, 0.0, 0.8), (1.2, 0.1, 0.5), (1.2, 0.4, 0.5), (1.5, 0.4, 0.5), (0.7, -0.8, 1.4)]
+    for c in centres:
+        b = sc.add_body(m, I, c)
+        sc.add_geom(B.BOX, (0.3, 0.2, 0.2), body=b)
+    for a, b in ((0, 1), (1, 2), (3, 4), (4, 5)):
+        sc.add_joint(B.JOINT_FIXED, a, b, (0, 0, 0))
+    sc.add_joint(B.JOINT_FIXED, -1, 6, (0, 0, 0))          # welded to the environment, attached with the bodies reversed
+    sc.add_joint(B.JOINT_BALL, 2, 3, (0.75, 0.05, 0.65))
+    nb = sc.nbody
+    pos = np.tile(np.asarray(sc.body_pos)[None], (nworlds, 1, 1))
+    quat = np.tile(np.array([1.0, 0, 0, 0])[None, None], (nworlds, nb, 1))
+    lvel = np.zeros((nworlds, nb, 3))
+    avel = np.zeros((nworlds, nb, 3))
+    for w in range(nworlds):
+        r = _rng(seed0 + w)
+        lvel[w] = 0.2 * (r.rand(nb, 3) - 0.5)
+        avel[w] = 0.3 * (r.rand(nb, 3) - 0.5)
+    sc.state = dict(pos=pos, quat=quat, lvel=lvel, avel=avel)
+    sc.seeds = (seed0 + np.arange(nworlds)).astype(np.uint32)
+    return sc
+
+
 def free_boxes(nworlds=1, nboxes=64, seed0=5, grid=8, spacing=1.5):
     """nboxes separate unit boxes resting/falling on the plane: many one-body islands per world
     (the scattered 64-body world of SURVEY.md 7.2(4))."""

@@ -224,12 +224,58 @@ static void universal_info2(World &W, Joint &j, Real fps, Real worldERP, Real *r
     add_limot(W, j, j.limot2, fps, row + r * ROWLEN, ax2);
 }
 
+// setFixedOrientation joints/joint.cpp:228-284
+static void set_fixed_orientation(World &W, Joint &j, Real fps, Real erp, Real *row, const Real *qrel)
+{
+    const Body &b0 = W.bodies[j.b0];
+    row[C_J1A] = 1; row[ROWLEN + C_J1A + 1] = 1; row[2 * ROWLEN + C_J1A + 2] = 1;
+    if (j.b1 >= 0) { row[C_J2A] = -1; row[ROWLEN + C_J2A + 1] = -1; row[2 * ROWLEN + C_J2A + 2] = -1; }
+    Real qerr[4], e[3];
+    if (j.b1 >= 0) { Real qq[4]; qmul1(qq, b0.q, W.bodies[j.b1].q); qmul2(qerr, qq, qrel); }
+    else qmul3(qerr, b0.q, qrel);
+    if (qerr[0] < 0) { qerr[1] = -qerr[1]; qerr[2] = -qerr[2]; qerr[3] = -qerr[3]; }
+    mul0_331(e, b0.R, qerr + 1);
+    Real k2 = fps * erp * R_(2.0);
+    row[C_RHS] = k2 * e[0]; row[ROWLEN + C_RHS] = k2 * e[1]; row[2 * ROWLEN + C_RHS] = k2 * e[2];
+}
+
+// dxJointFixed::getInfo2 fixed.cpp:60-110 (offset kept in anchor1)
+static void fixed_info2(World &W, Joint &j, Real fps, Real worldERP, Real *row)
+{
+    set_fixed_orientation(W, j, fps, worldERP, row + 3 * ROWLEN, j.qrel);
+    row[C_J1L] = 1; row[ROWLEN + C_J1L + 1] = 1; row[2 * ROWLEN + C_J1L + 2] = 1;
+    Real k = fps * j.erp;
+    const Body &b0 = W.bodies[j.b0];
+    Real ofs[3];
+    mul0_331(ofs, b0.R, j.anchor1);
+    if (j.b1 >= 0) {
+        const Body &b1 = W.bodies[j.b1];
+        row[C_J1A + 1] = -ofs[2]; row[C_J1A + 2] = +ofs[1];
+        row[ROWLEN + C_J1A + 0] = +ofs[2]; row[ROWLEN + C_J1A + 2] = -ofs[0];
+        row[2 * ROWLEN + C_J1A + 0] = -ofs[1]; row[2 * ROWLEN + C_J1A + 1] = +ofs[0];
+        row[C_J2L] = -1; row[ROWLEN + C_J2L + 1] = -1; row[2 * ROWLEN + C_J2L + 2] = -1;
+        for (int t = 0; t < 3; t++) row[t * ROWLEN + C_RHS] = k * (b1.pos[t] - b0.pos[t] + ofs[t]);
+    } else {
+        for (int t = 0; t < 3; t++) row[t * ROWLEN + C_RHS] = k * (j.anchor1[t] - b0.pos[t]);
+    }
+    row[C_CFM] = j.cfm; row[ROWLEN + C_CFM] = j.cfm; row[2 * ROWLEN + C_CFM] = j.cfm;
+}
+
 // dJointSet{Ball,Hinge,Universal}Anchor/Axis at the template pose
 static void joint_setup(const Batch &B, World &W, Joint &j, const OdebJointDesc &d)
 {
     (void)B;
     set_anchors(W, j, (Real)d.anchor[0], (Real)d.anchor[1], (Real)d.anchor[2]);
-    if (j.type == ODEB_JOINT_HINGE) {
+    if (j.type == ODEB_JOINT_FIXED) {
+        // dJointSetFixed fixed.cpp:113-142
+        const Body &b0 = W.bodies[j.b0];
+        if (j.b1 >= 0) {
+            Real ofs[3] = { b0.pos[0] - W.bodies[j.b1].pos[0], b0.pos[1] - W.bodies[j.b1].pos[1], b0.pos[2] - W.bodies[j.b1].pos[2] };
+            mul1_331(j.anchor1, b0.R, ofs);
+        } else { j.anchor1[0] = b0.pos[0]; j.anchor1[1] = b0.pos[1]; j.anchor1[2] = b0.pos[2]; }
+        if (j.b1 >= 0) qmul1(j.qrel, b0.q, W.bodies[j.b1].q);
+        else { const Real *q = b0.q; j.qrel[0] = q[0]; j.qrel[1] = -q[1]; j.qrel[2] = -q[2]; j.qrel[3] = -q[3]; }
+    } else if (j.type == ODEB_JOINT_HINGE) {
         j.axis1[0] = 1; j.axis2[0] = 1;   // constructor defaults hinge.cpp:36-43
         set_axes(W, j, (Real)d.axis1[0], (Real)d.axis1[1], (Real)d.axis1[2], j.axis1, j.axis2);
         // computeInitialRelativeRotation hinge.cpp:376-393

@@ -178,6 +178,9 @@ void *ref_create(const OdebWorldParams *wp,
             if (d.type == ODEB_JOINT_BALL) {
                 j = dJointCreateBall(W.world, 0); dJointAttach(j, b1, b2);
                 dJointSetBallAnchor(j, (dReal)d.anchor[0], (dReal)d.anchor[1], (dReal)d.anchor[2]);
+            } else if (d.type == ODEB_JOINT_FIXED) {
+                j = dJointCreateFixed(W.world, 0); dJointAttach(j, b1, b2);
+                dJointSetFixed(j);
             } else if (d.type == ODEB_JOINT_HINGE) {
                 j = dJointCreateHinge(W.world, 0); dJointAttach(j, b1, b2);
                 dJointSetHingeAnchor(j, (dReal)d.anchor[0], (dReal)d.anchor[1], (dReal)d.anchor[2]);

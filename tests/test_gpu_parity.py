@@ -267,3 +267,46 @@ def test_joint_feedback_bit_exact(prec, solver, monkeypatch):
             bad = compare_feedback(a, b, sc.nworlds, exact, 2e-2 if prec == "single" else 1e-8)
             assert not bad, (name, solver, s, bad[:4])
         b.close()
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_snapshot_restore_continues_bit_identically(prec):
+    """odeb_snapshot / odeb_restore: the continuation from a restored checkpoint equals the uninterrupted run, in the same
+    batch and in a freshly created one (auto-disable history, dRand seeds and statistics included)."""
+    mk = lambda: scenes.box_stack(nworlds=6)            # demo world options: auto-disable + damping on
+    a = B.Batch(gpu_lib(prec), mk())
+    a.step(0.02, 70)
+    snap = a.snapshot()
+    a.step(0.02, 90)
+    want, seeds, en = a.get_state(), a.get_seeds(), a.get_enabled()
+    stats = [a.get_stats(w).copy() for w in range(6)]
+    for target in (a, B.Batch(gpu_lib(prec), mk())):
+        target.restore(snap)
+        target.step(0.02, 90)
+        got = target.get_state()
+        for k in want:
+            assert np.array_equal(want[k], got[k]), k
+        assert np.array_equal(seeds, target.get_seeds()) and np.array_equal(en, target.get_enabled())
+        assert all(np.array_equal(stats[w], target.get_stats(w)) for w in range(6))
+    bad = B.Batch(gpu_lib(prec), scenes.box_stack(nworlds=5))
+    with pytest.raises(RuntimeError):
+        bad.restore(snap)
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("solver", ("v4", "p4"))
+def test_fixed_joints_bit_exact(prec, solver, monkeypatch):
+    """Fixed joints (fixed.cpp:60-110, setFixedOrientation joint.cpp:228-284) on the GPU: every observable and the joint
+    feedback identical to the oracle, every step."""
+    from test_oracle import compare_feedback
+    monkeypatch.setenv("ODEB_SOLVER", solver)
+    sc = scenes.compound(5)
+    a, b = B.Batch(orc_lib(prec), sc), B.Batch(gpu_lib(prec), sc)
+    a.enable_feedback()
+    b.enable_feedback()
+    for s in range(120):
+        a.step(0.02)
+        b.step(0.02)
+        bad = compare_step(a, b, sc.nworlds) + compare_feedback(a, b, sc.nworlds, True, 0)
+        assert not bad, (solver, s, bad[:4])
+    b.close()

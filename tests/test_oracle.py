@@ -164,3 +164,21 @@ def test_joint_feedback_vs_reference(prec):
             assert not bad, (name, s, bad[:4])
             seen += int((a.get_feedback(0)[1] > 0).sum())
         assert seen > 0, name
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_fixed_joints_vs_reference(prec):
+    """dJointCreateFixed / dJointSetFixed (joints/fixed.cpp) between bodies and to the environment: restatement against the
+    compiled reference, every observable of every step bit-identical (no libm on this path), feedback included."""
+    ref = ref_lib(prec)
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    sc = scenes.compound(3)
+    a, b = B.Batch(ref, sc), B.Batch(orc_lib(prec), sc)
+    a.enable_feedback()
+    b.enable_feedback()
+    for s in range(120):
+        a.step(0.02)
+        b.step(0.02)
+        bad = compare_step(a, b, sc.nworlds) + compare_feedback(a, b, sc.nworlds, True, 0)
+        assert not bad, (s, bad[:4])
