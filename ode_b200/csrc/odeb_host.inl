@@ -29,6 +29,7 @@ struct OdebBatch {
     // solver selection: 0 = k_solve (one row at a time per world), 1..3 = k_solve5<2/4/8> (static P-processor schedule),
     // 4 = k_solve_bl (one lane per body). hint_m = largest island (rows) seen since the last sync, read back in odeb_sync.
     int s5_sr[4]; size_t s5_smem[4]; int hint_m; int solver_force;
+    size_t isl_smem;                         // shared memory of k_islands_t<true> per block, 0 = scratch in global memory
     size_t solve_smem;
     int bl_G, bl_SR; size_t bl_smem;          // body-lane solver (odeb_solve_bl.cuh): lanes per world (0 = not used), row budget, bytes per warp
     void *flush_buf; size_t flush_bytes;
@@ -374,6 +375,11 @@ static OdebBatch *batch_build(const OdebWorldParams *wp, const HostTemplate &T, 
     ok = ok && dev_alloc(B, &B->d_stage, 4 * WB);
     if (ok && cudaMallocHost((void **)&B->h_stage, 4 * WB * sizeof(Real4)) != cudaSuccess) { set_err("cudaMallocHost failed"); ok = false; }
     if (ok && cudaStreamCreateWithFlags(&B->stream, cudaStreamNonBlocking) != cudaSuccess) { set_err("cudaStreamCreate failed"); ok = false; }
+    {   // island replay scratch in shared memory when 32 worlds fit (and the 16-bit indices hold)
+        const size_t need = odeb_islands_smem(P.NB, P.MC, P.NJT);
+        B->isl_smem = (need <= 200 * 1024 && 2 * (size_t)P.MC < 65535 && (size_t)P.NB < 65535 && !getenv("ODEB_ISLANDS_GLOBAL")) ? need : 0;
+        if (ok && cudaFuncSetAttribute(k_islands_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) { set_err("cudaFuncSetAttribute(k_islands) failed"); ok = false; }
+    }
     if (ok) {   // opt every solver kernel into the full 227 KB of shared memory once (the attribute is per function, not per batch)
         const int mx = 227 * 1024;
         cudaError_t ce = cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
@@ -653,7 +659,8 @@ static void launch_dynamics(OdebBatch *B, cudaStream_t s, bool timed, int cfg)
     const size_t W = P.W;
     if (D.jfb) cudaMemsetAsync(D.jfb, 0, W * P.NJT * 4 * sizeof(Real4), s);      // state 0 = joint not stepped
     if (P.NJ > 0) { k_joint_info1<<<nblk(W * P.NJ, 128), 128, 0, s>>>(P, D); B->launches++; }
-    k_islands<<<nblk(W, 32), 32, 0, s>>>(P, D);
+    if (B->isl_smem) k_islands_t<true><<<nblk(W, 32), 32, B->isl_smem, s>>>(P, D);
+    else k_islands_t<false><<<nblk(W, 32), 32, 0, s>>>(P, D);
     k_body_pre<<<nblk(W * P.NB, 128), 128, 0, s>>>(P, D);
     k_rows<<<nblk(W * P.NJT, 64), 64, 0, s>>>(P, D);
     k_rows_finish<<<nblk(W * P.MR, 128), 128, 0, s>>>(P, D);

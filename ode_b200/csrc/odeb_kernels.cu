@@ -259,11 +259,27 @@ __global__ void k_joint_info1(const __grid_constant__ DevParams P, const __grid_
 // ------------------------------------------------------------------------------------------------
 // contacts -> joint lists -> auto-disable -> islands (one thread replays one world's list mechanics)
 
-__global__ void k_islands(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D)
+template <bool SM> struct IslIdx { typedef int type; };
+template <> struct IslIdx<true> { typedef unsigned short type; };
+// shared memory of k_islands_t<true> per block of 32 worlds
+__host__ __device__ inline size_t odeb_islands_smem(int NB, int MC, int NJT)
 {
+    return (size_t)32 * (sizeof(unsigned short) * ((size_t)(NB + 1) + NB + 4 * (size_t)MC + NB) + (size_t)NB + NJT);
+}
+
+// SM = true: the scratch of the list replay (contact adjacency CSR, tags, DFS stack) lives in shared memory, interleaved
+// [element][thread] as 16-bit / 8-bit entries, instead of per-world global arrays: every step of the replay is a dependent
+// read-modify-write, and a world is one thread, so the kernel is bound by the latency of those accesses.
+template <bool SM>
+__global__ void __launch_bounds__(32) k_islands_t(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D)
+{
+    extern __shared__ __align__(16) unsigned char isl_smem[];
     int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= P.W) return;
     const int NB = P.NB, NJ = P.NJ, MC = P.MC;
+    constexpr int S = SM ? 32 : 1;                       // element stride of the scratch arrays
+    typedef typename IslIdx<SM>::type idx_t;             // unsigned short in shared memory, int in global memory
+    const int NONE = SM ? 0xffff : -1;                   // "no second body" in adj_o
     // 1. number the contact joints in creation order (pair order, then dCollide's contact order)
     int nc = 0;
     if (P.classic) nc = D.ncontacts[w];     // contact joints were created through dJointCreateContact: numbered by the host
@@ -287,17 +303,28 @@ __global__ void k_islands(const __grid_constant__ DevParams P, const __grid_cons
         D.ncontacts[w] = nc;
     }
     // 2. per-body contact adjacency (CSR, ascending contact index; walked descending = newest first)
-    int *cofs = D.c_ofs + (size_t)w * (NB + 1), *ccur = D.c_cur + (size_t)w * NB;
-    int *adj_c = D.c_adj_c + (size_t)w * 2 * MC, *adj_o = D.c_adj_o + (size_t)w * 2 * MC;
+    idx_t *cofs, *ccur, *adj_c, *adj_o, *stack;
+    signed char *btag, *jtag;
+    if (SM) {
+        idx_t *q = (idx_t *)isl_smem + threadIdx.x;
+        cofs = q; q += (size_t)(NB + 1) * 32; ccur = q; q += (size_t)NB * 32; adj_c = q; q += (size_t)2 * MC * 32;
+        adj_o = q; q += (size_t)2 * MC * 32; stack = q; q += (size_t)NB * 32;
+        btag = (signed char *)q + threadIdx.x; jtag = btag + (size_t)NB * 32;
+    } else {
+        cofs = (idx_t *)(D.c_ofs + (size_t)w * (NB + 1)); ccur = (idx_t *)(D.c_cur + (size_t)w * NB);
+        adj_c = (idx_t *)(D.c_adj_c + (size_t)w * 2 * MC); adj_o = (idx_t *)(D.c_adj_o + (size_t)w * 2 * MC);
+        stack = (idx_t *)(D.stack + (size_t)w * NB);
+        btag = D.btag + (size_t)w * NB; jtag = D.jtag + (size_t)w * P.NJT;
+    }
     const int4 *ci = D.cinfo + (size_t)w * MC;
-    for (int b = 0; b <= NB; b++) cofs[b] = 0;
+    for (int b = 0; b <= NB; b++) cofs[b * S] = 0;
     if (!P.classic) {       // classic mode: the host-built adjacency (sadj_*) already holds every joint in dJointAttach order
-        for (int c = 0; c < nc; c++) { int4 v = ci[c]; cofs[v.y + 1]++; if (v.z >= 0) cofs[v.z + 1]++; }
-        for (int b = 0; b < NB; b++) { cofs[b + 1] += cofs[b]; ccur[b] = cofs[b]; }
+        for (int c = 0; c < nc; c++) { int4 v = ci[c]; cofs[(v.y + 1) * S]++; if (v.z >= 0) cofs[(v.z + 1) * S]++; }
+        for (int b = 0; b < NB; b++) { cofs[(b + 1) * S] += cofs[b * S]; ccur[b * S] = cofs[b * S]; }
         for (int c = 0; c < nc; c++) {
             int4 v = ci[c];
-            int k = ccur[v.y]++; adj_c[k] = c; adj_o[k] = v.z;
-            if (v.z >= 0) { k = ccur[v.z]++; adj_c[k] = c; adj_o[k] = v.y; }
+            int k = ccur[v.y * S]++; adj_c[k * S] = (idx_t)c; adj_o[k * S] = (idx_t)(v.z >= 0 ? v.z : NONE);
+            if (v.z >= 0) { k = ccur[v.z * S]++; adj_c[k * S] = (idx_t)c; adj_o[k * S] = (idx_t)v.y; }
         }
     }
     // 3. dInternalHandleAutoDisabling util.cpp:427-561 (world->firstbody order = reverse creation)
@@ -306,7 +333,7 @@ __global__ void k_islands(const __grid_constant__ DevParams P, const __grid_cons
         for (int b = NB - 1; b >= 0; b--) {
             int fl = bflags[b];
             if ((fl & (BF_AUTO_DISABLE | BF_DISABLED)) != BF_AUTO_DISABLE) continue;
-            if (cofs[b + 1] == cofs[b] && D.sadj_ofs[b + 1] == D.sadj_ofs[b]) continue;
+            if (cofs[(b + 1) * S] == cofs[b * S] && D.sadj_ofs[b + 1] == D.sadj_ofs[b]) continue;
             size_t gb = (size_t)w * NB + b;
             Real4 lv = D.lvel[gb], av = D.avel[gb];
             Real *buf = D.avg_buf + gb * 6 * P.adis_samples;
@@ -342,45 +369,43 @@ __global__ void k_islands(const __grid_constant__ DevParams P, const __grid_cons
     }
     // 4. BuildIslands util.cpp:724-860: DFS from each untagged enabled body, LIFO body stack,
     //    each body's joints walked newest attachment first (contacts of this step, then permanent joints)
-    signed char *btag = D.btag + (size_t)w * NB, *jtag = D.jtag + (size_t)w * P.NJT;
-    int *stack = D.stack + (size_t)w * NB;
     int *border = D.body_order + (size_t)w * NB, *bpos = D.body_pos + (size_t)w * NB, *bisl = D.body_island + (size_t)w * NB;
     int *jorder = D.joint_order + (size_t)w * P.NJT, *jrow = D.joint_row + (size_t)w * P.NJT, *jisl = D.joint_island + (size_t)w * P.NJT;
     int4 *iinfo = D.island_info + (size_t)w * NB;
     const int *jm = D.jm + (size_t)w * NJ;
-    for (int b = 0; b < NB; b++) { btag[b] = 0; bisl[b] = -1; bpos[b] = -1; }
-    for (int j = 0; j < NJ + nc; j++) jtag[j] = 0;
+    for (int b = 0; b < NB; b++) { btag[b * S] = 0; bisl[b] = -1; bpos[b] = -1; }
+    for (int j = 0; j < NJ + nc; j++) jtag[j * S] = 0;
     int nbo = 0, njo = 0, nis = 0, rows = 0;
     for (int bb = NB - 1; bb >= 0; bb--) {
-        if (btag[bb]) continue;
-        if (bflags[bb] & BF_DISABLED) { btag[bb] = -1; continue; }
-        btag[bb] = 1;
+        if (btag[bb * S]) continue;
+        if (bflags[bb] & BF_DISABLED) { btag[bb * S] = -1; continue; }
+        btag[bb * S] = 1;
         int bstart = nbo, rstart = rows, mi = 0;
         border[nbo] = bb; bpos[bb] = nbo; bisl[bb] = nis; nbo++;
         int sp = 0, b = bb;
         while (true) {
-            for (int k = cofs[b + 1] - 1; k >= cofs[b]; k--) {
-                int jid = NJ + adj_c[k];
-                if (!jtag[jid]) {
-                    jtag[jid] = 1;
+            for (int k = (int)cofs[(b + 1) * S] - 1, k0 = (int)cofs[b * S]; k >= k0; k--) {
+                int jid = NJ + adj_c[k * S];
+                if (!jtag[jid * S]) {
+                    jtag[jid * S] = 1;
                     jorder[njo] = jid; jrow[njo] = mi; jisl[njo] = nis; njo++;
                     mi += P.m_contact;
-                    int nb2 = adj_o[k];
-                    if (nb2 >= 0 && btag[nb2] <= 0) { btag[nb2] = 1; bflags[nb2] &= ~BF_DISABLED; stack[sp++] = nb2; }
+                    int nb2 = adj_o[k * S];
+                    if (nb2 != NONE && btag[nb2 * S] <= 0) { btag[nb2 * S] = 1; bflags[nb2] &= ~BF_DISABLED; stack[(sp++) * S] = (idx_t)nb2; }
                 }
             }
             for (int k = D.sadj_ofs[b + 1] - 1; k >= D.sadj_ofs[b]; k--) {
                 int jid = D.sadj_joint[k];
-                if (!jtag[jid]) {
-                    jtag[jid] = 1;
+                if (!jtag[jid * S]) {
+                    jtag[jid * S] = 1;
                     int m = jid < NJ ? jm[jid] : D.csurf[jid - NJ].the_m;
                     if (m != 0) { jorder[njo] = jid; jrow[njo] = mi; jisl[njo] = nis; njo++; mi += m; }
                     int nb2 = D.sadj_other[k];
-                    if (nb2 >= 0 && btag[nb2] <= 0) { btag[nb2] = 1; bflags[nb2] &= ~BF_DISABLED; stack[sp++] = nb2; }
+                    if (nb2 >= 0 && btag[nb2 * S] <= 0) { btag[nb2 * S] = 1; bflags[nb2] &= ~BF_DISABLED; stack[(sp++) * S] = (idx_t)nb2; }
                 }
             }
             if (sp == 0) break;
-            b = stack[--sp];
+            b = stack[(--sp) * S];
             border[nbo] = b; bpos[b] = nbo; bisl[b] = nis; nbo++;
         }
         if (rstart + mi > P.MR) { atomicExch(D.overflow, 3); mi = 0; }
