@@ -399,9 +399,19 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p)
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v)
 {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_u32(unsigned *p, unsigned v)
+{
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ Real4 ldcg4(const Real4 *p)
 {
@@ -431,6 +441,9 @@ __device__ __forceinline__ Real4 shfl_up4(const Real4 &v)
     return r;
 }
 
+#ifndef ODEB_LW_BLOCKS
+#define ODEB_LW_BLOCKS 3             // resident blocks per SM (80 registers): 27.6 ms per step on the 100k-box wall, 2 -> 30.6, 4 (spills) -> 43.2
+#endif
 // One sweep over all rows of all unfinished islands, in the phase's order. Warps claim consecutive chunks of 32 positions
 // through one cursor, so every claimed position only ever waits for positions that are already claimed by a running warp
 // (or finished): the walk cannot deadlock whatever the grid size. Inside a chunk a lane owns one row (its record is in
@@ -438,22 +451,30 @@ __device__ __forceinline__ Real4 shfl_up4(const Real4 &v)
 // the run's tickets it loads the bodies' accumulators, and the run then executes in lockstep, one row per step, the
 // accumulators travelling from lane to lane by shuffle; the tail lane writes them back and bumps the counters.
 // Arithmetic = Stage4LCP_IterationStep quickstep.cpp:2917-3033.
-__global__ void __launch_bounds__(256) k_lw_sweep(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L, int mrows)
+__global__ void __launch_bounds__(256, ODEB_LW_BLOCKS) k_lw_sweep(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L, int mrows)
 {
     if (L.counters[LWC_NACTIVE] == 0) return;
     const int lane = threadIdx.x & 31;
     const int nchunks = (mrows + 31) >> 5;
     Real4 *cf = D.cforce;
     Real *lam = D.lambda;
-    for (;;) {
-        int chunk = 0;
-        if (lane == 0) chunk = atomicAdd(&L.counters[LWC_CURSOR], 1);
-        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+#ifndef ODEB_LW_CLAIM
+#define ODEB_LW_CLAIM 1             // chunks claimed per cursor atomic. Must stay 1: a warp that holds chunks it is not yet working on makes
+                                   // every later position wait for it (measured: 4 -> 9.8 s per step instead of 38 ms)
+#endif
+    for (int sub = ODEB_LW_CLAIM, base = 0;; sub++) {
+        if (sub == ODEB_LW_CLAIM) {
+            if (lane == 0) base = atomicAdd(&L.counters[LWC_CURSOR], ODEB_LW_CLAIM);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            sub = 0;
+        }
+        const int chunk = base + sub;
         if (chunk >= nchunks) break;
         const int p = chunk * 32 + lane;
         bool pending = p < mrows;
         int r = 0, fi = -1; int2 rb = make_int2(0, 0), tk = make_int2(0, 0);
         bool head = false, tail = false;
+        int hl = lane;                           // lane of the head of this lane's run
         Real old_lambda = 0;
         Real4 a0, a1, a2, a3, b0, b1q, b2q, b3;
         if (pending) {
@@ -464,7 +485,8 @@ __global__ void __launch_bounds__(256) k_lw_sweep(const __grid_constant__ DevPar
             const Real4 *rec = D.rows + (size_t)r * 8;
             a0 = rec[0]; a1 = rec[1]; a2 = rec[2]; a3 = rec[3]; b0 = rec[4]; b1q = rec[5]; b2q = rec[6]; b3 = rec[7];
             rb = D.rbody[r]; fi = D.findex[r];
-            head = L.head_pos[p] == p;
+            hl = L.head_pos[p] - chunk * 32;                       // runs never cross a chunk (k_lw_runs)
+            head = hl == lane;
             tail = (p + 1 >= mrows) || (L.head_pos[p + 1] == p + 1);
             if (head) tk = L.ticket[p];
             old_lambda = lam[r];            // each row is updated once per sweep: its own lambda cannot change under it
@@ -472,6 +494,17 @@ __global__ void __launch_bounds__(256) k_lw_sweep(const __grid_constant__ DevPar
         const bool two = rb.y != P.NB;
         Real4 f1a = { 0, 0, 0, 0 }, f1b = f1a, f2a = f1a, f2b = f1a;
         unsigned backoff = 0;
+        // lambda of the friction-index row (the contact's normal row). When that row sits earlier in the same run its new value
+        // is forwarded from the lane that computes it (fwd_src) instead of going through L2 once per friction row; otherwise
+        // the row ran in an earlier run on the same two bodies (or runs later in the sweep), so its value is final for this
+        // lane as soon as the run's tickets are up and is fetched together with the accumulators.
+        int fwd_src = lane; bool fwd = false;
+        {
+            const int src = lane - (r - fi);
+            const int r_src = __shfl_sync(0xffffffffu, r, (src >= 0 && src < 32) ? src : lane);
+            if (pending && fi != -1 && src >= hl && src < lane && r_src == fi) { fwd = true; fwd_src = src; }
+        }
+        Real lam_fi_val = 0, my_lambda = 0;
         while (__any_sync(0xffffffffu, pending)) {
             bool have = false;
             if (pending && head) {
@@ -483,21 +516,33 @@ __global__ void __launch_bounds__(256) k_lw_sweep(const __grid_constant__ DevPar
                     have = true;
                 }
             }
-            if (!__any_sync(0xffffffffu, have)) { backoff = backoff < 128 ? backoff + 16 : 128; __nanosleep(backoff); continue; }
+#ifndef ODEB_LW_BACKOFF_MAX
+#define ODEB_LW_BACKOFF_MAX 128
+#endif
+            {
+                const unsigned started = __ballot_sync(0xffffffffu, have);
+                if (pending && fi != -1 && !fwd && ((started >> hl) & 1u)) lam_fi_val = __ldcg(&lam[fi]);
+            }
+            if (!__any_sync(0xffffffffu, have)) {
+                if (ODEB_LW_BACKOFF_MAX > 0) { backoff = backoff < ODEB_LW_BACKOFF_MAX ? backoff + 16 : ODEB_LW_BACKOFF_MAX; __nanosleep(backoff); }
+                continue;
+            }
             backoff = 0;
             for (;;) {
                 const bool exec = have;
+                const Real lam_fw = __shfl_sync(0xffffffffu, my_lambda, fwd_src);
                 if (exec) {
                     Real delta = a1.z - old_lambda * a1.w;
                     delta -= f1a.x * a0.x + f1a.y * a0.y + f1a.z * a0.z + f1a.w * a0.w + f1b.x * a1.x + f1b.y * a1.y;
                     if (two) delta -= f2a.x * b0.x + f2a.y * b0.y + f2a.z * b0.z + f2a.w * b0.w + f2b.x * b1q.x + f2b.y * b1q.y;
                     Real hi_act, lo_act;
-                    if (fi != -1) { hi_act = RFABS(b1q.w * __ldcg(&lam[fi])); lo_act = -hi_act; }
+                    if (fi != -1) { hi_act = RFABS(b1q.w * (fwd ? lam_fw : lam_fi_val)); lo_act = -hi_act; }
                     else { hi_act = b1q.w; lo_act = b1q.z; }
                     Real new_lambda = old_lambda + delta;
                     if (new_lambda < lo_act) { delta = lo_act - old_lambda; new_lambda = lo_act; }
                     else if (new_lambda > hi_act) { delta = hi_act - old_lambda; new_lambda = hi_act; }
                     __stcg(&lam[r], new_lambda);
+                    my_lambda = new_lambda;
                     if (delta != 0) {
                         f1a.x += delta * a2.x; f1a.y += delta * a2.y; f1a.z += delta * a2.z; f1a.w += delta * a2.w;
                         f1b.x += delta * a3.x; f1b.y += delta * a3.y;
@@ -519,9 +564,10 @@ __global__ void __launch_bounds__(256) k_lw_sweep(const __grid_constant__ DevPar
                 // the run's tickets travel with the accumulators: the tail needs them for the release
                 const Real4 n1a = shfl_up4(f1a), n1b = shfl_up4(f1b), n2a = shfl_up4(f2a), n2b = shfl_up4(f2b);
                 const int ntx = __shfl_up_sync(0xffffffffu, tk.x, 1), nty = __shfl_up_sync(0xffffffffu, tk.y, 1);
-                if (exec && tail) {
-                    st_release_u32(&L.cnt[rb.x], (unsigned)tk.x + 1u);
-                    if (two) st_release_u32(&L.cnt[rb.y], (unsigned)tk.y + 1u);
+                if (exec && tail) {             // one fence for the run's stores, then both counters
+                    asm volatile("fence.acq_rel.gpu;" ::: "memory");        // (not __threadfence(): that is the sequentially consistent fence)
+                    st_relaxed_u32(&L.cnt[rb.x], (unsigned)tk.x + 1u);
+                    if (two) st_relaxed_u32(&L.cnt[rb.y], (unsigned)tk.y + 1u);
                 }
                 have = lane > 0 && ((pass >> (lane - 1)) & 1u);
                 if (have) { f1a = n1a; f1b = n1b; f2a = n2a; f2b = n2b; tk.x = ntx; tk.y = nty; }
