@@ -310,3 +310,42 @@ def test_fixed_joints_bit_exact(prec, solver, monkeypatch):
         bad = compare_step(a, b, sc.nworlds) + compare_feedback(a, b, sc.nworlds, True, 0)
         assert not bad, (solver, s, bad[:4])
     b.close()
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_edge_cases_gpu(prec):
+    """Edge cases of tests/test_oracle.py::test_edge_cases on the CUDA path: a single body, no pairs at all (free fall),
+    category bits that filter everything, zero gravity; plus ragged and maximum sizes: world counts that do not fill a warp
+    group (1, 3, 17, 33), dCollide contact limits 1..8, and body counts at the limits of the solver kernels' packed
+    indices (62 bodies: last size k_solve5 takes; 63 / 70: k_solve only)."""
+    cases = []
+    cases.append((scenes.free_boxes(1, 1, grid=1), 0.01, 20))
+    sc = scenes.free_boxes(1, 4, grid=2)
+    sc.state["pos"][..., 2] += 5.0
+    cases.append((sc, 0.01, 20))
+    sc = scenes.free_boxes(2, 4, grid=2)
+    for g in sc.geoms:
+        g.collide_bits = 0
+        g.category_bits = 0
+    cases.append((sc, 0.01, 20))
+    sc = scenes.box_stack(nworlds=1, nboxes=3)
+    sc.wp.gravity[2] = 0.0
+    cases.append((sc, 0.01, 20))
+    for nw in (1, 3, 17, 33):
+        cases.append((scenes.box_stack(nworlds=nw, nboxes=5), 0.02, 30))
+    for mc in (1, 2, 3, 5, 8):
+        sc = scenes.box_stack(nworlds=2, nboxes=4, demo_world_options=False)
+        sc.wp.max_contacts = mc
+        cases.append((sc, 0.02, 30))
+    for nb in (62, 63, 70):
+        cases.append((scenes.free_boxes(2, nb, grid=9), 0.01, 12))
+    for sc, h, n in cases:
+        a, b = B.Batch(orc_lib(prec), sc), B.Batch(gpu_lib(prec), sc)
+        for s in range(n):
+            a.step(h)
+            b.step(h)
+            bad = compare_step(a, b, sc.nworlds)
+            assert not bad, (sc.nworlds, sc.nbody, s, bad[:4])
+            st = b.get_state()
+            assert all(np.isfinite(st[k]).all() for k in st)
+        b.close()
