@@ -40,7 +40,7 @@ typedef float odeb_real;
 /* geom classes: numbering of the reference (include/ode/collision.h:881-902) */
 enum { ODEB_SPHERE = 0, ODEB_BOX = 1, ODEB_CAPSULE = 2, ODEB_PLANE = 4 };
 /* joint types: numbering of the reference dJointType (include/ode/common.h:406-426) */
-enum { ODEB_JOINT_BALL = 1, ODEB_JOINT_HINGE = 2, ODEB_JOINT_CONTACT = 4, ODEB_JOINT_UNIVERSAL = 5, ODEB_JOINT_FIXED = 7 };
+enum { ODEB_JOINT_BALL = 1, ODEB_JOINT_HINGE = 2, ODEB_JOINT_SLIDER = 3, ODEB_JOINT_CONTACT = 4, ODEB_JOINT_UNIVERSAL = 5, ODEB_JOINT_FIXED = 7 };
 /* broadphase flavours: which reference space's callback stream is reproduced (as a set) */
 enum { ODEB_SPACE_HASH = 0, ODEB_SPACE_SAP = 1 };
 
@@ -106,7 +106,8 @@ typedef struct OdebGeomDesc {
 } OdebGeomDesc;
 
 typedef struct OdebJointDesc {
-    int    type;                /* ODEB_JOINT_BALL | ODEB_JOINT_HINGE | ODEB_JOINT_UNIVERSAL | ODEB_JOINT_FIXED (dJointSetFixed at the template pose) */
+    int    type;                /* ODEB_JOINT_BALL | ODEB_JOINT_HINGE | ODEB_JOINT_UNIVERSAL | ODEB_JOINT_FIXED (dJointSetFixed at the template pose)
+                                   | ODEB_JOINT_SLIDER (dJointSetSliderAxis(axis1) at the template pose; stops / motor = axis-1 entries, lengths) */
     int    body1, body2;        /* dJointAttach(j, body1, body2); -1 = the static environment */
     double anchor[3];           /* dJointSet*Anchor, world frame at the template pose */
     double axis1[3], axis2[3];  /* dJointSetHingeAxis / dJointSetUniversalAxis1,2 */

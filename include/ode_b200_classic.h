@@ -17,7 +17,7 @@
  * getters return pointers into library storage (ode.cpp:413-484).  There is no CPU implementation of any of these
  * stages: without a CUDA device dWorldQuickStep returns 0 and dSpaceCollide reports through the error handler.
  *
- * Outside the subset (calls are not exported): dWorldStep, joints other than contact/ball/hinge/universal/fixed, geoms other
+ * Outside the subset (calls are not exported): dWorldStep, joints other than contact/ball/hinge/slider/universal/fixed, geoms other
  * than sphere/box/capsule/plane, geom offsets, nested spaces, rolling friction, per-body
  * auto-disable thresholds (the world's are used), SAP axis orders other than dSAP_AXES_XYZ.
  */
@@ -244,6 +244,11 @@ void dJointGroupEmpty(dJointGroupID);
 dJointID dJointCreateContact(dWorldID, dJointGroupID, const dContact *);
 dJointID dJointCreateBall(dWorldID, dJointGroupID);
 dJointID dJointCreateHinge(dWorldID, dJointGroupID);
+dJointID dJointCreateSlider(dWorldID, dJointGroupID);           /* joints/slider.cpp */
+void dJointSetSliderAxis(dJointID, dReal x, dReal y, dReal z);
+void dJointGetSliderAxis(dJointID, dVector3 result);
+void dJointSetSliderParam(dJointID, int parameter, dReal value);
+dReal dJointGetSliderPosition(dJointID);
 dJointID dJointCreateFixed(dWorldID, dJointGroupID);            /* joints/fixed.cpp */
 void dJointSetFixed(dJointID);
 void dJointSetFixedParam(dJointID, int parameter, dReal value);

@@ -53,7 +53,7 @@ class OdebStats(C.Structure):
 
 
 SPHERE, BOX, CAPSULE, PLANE = 0, 1, 2, 4
-JOINT_BALL, JOINT_HINGE, JOINT_CONTACT, JOINT_UNIVERSAL, JOINT_FIXED = 1, 2, 4, 5, 7
+JOINT_BALL, JOINT_HINGE, JOINT_SLIDER, JOINT_CONTACT, JOINT_UNIVERSAL, JOINT_FIXED = 1, 2, 3, 4, 5, 7
 SPACE_HASH, SPACE_SAP = 0, 1
 CONTACT_MU2, CONTACT_BOUNCE, CONTACT_SOFT_ERP, CONTACT_SOFT_CFM = 0x001, 0x004, 0x008, 0x010
 CONTACT_MOTION1, CONTACT_MOTION2, CONTACT_MOTIONN = 0x020, 0x040, 0x080

@@ -379,6 +379,15 @@ static void joint_set_relative_values(dxJoint *j)
 {   // dxJoint*::setRelativeValues (ball.cpp:179-185, hinge.cpp:359-369, universal.cpp:785-808): called by dJointAttach
     DJointT &t = j->t;
     if (j->type == dJointTypeContact || j->type == dJointTypeFixed) return;     // dxJointFixed keeps offset / qrel until dJointSetFixed
+    if (j->type == dJointTypeSlider) {                                          // slider.cpp:371-376: computeOffset + computeInitialRelativeRotation
+        std::vector<HostBody> hb = joint_bodies(j, t);
+        if (t.b0 >= 0) {
+            if (t.b1 >= 0) { Real c[3] = { hb[0].pos[0] - hb[1].pos[0], hb[0].pos[1] - hb[1].pos[1], hb[0].pos[2] - hb[1].pos[2] }; mul1_331(t.anchor1, hb[1].R, c); }
+            else { t.anchor1[0] = hb[0].pos[0]; t.anchor1[1] = hb[0].pos[1]; t.anchor1[2] = hb[0].pos[2]; }
+            host_hinge_initial_rotation(hb, t);
+        }
+        return;
+    }
     Real anchor[3] = { 0, 0, 0 };
     if (j->reverse) joint_get_anchor2(j, t.anchor2, anchor); else joint_get_anchor(j, t.anchor1, anchor);     // dJointGet{Ball,Hinge,Universal}Anchor
     std::vector<HostBody> hb = joint_bodies(j, t);
@@ -432,6 +441,7 @@ static dxJoint *new_joint(dxWorld *w, dxJointGroup *g, int type)
 #endif
     limot_init(j->t.limot1, w); limot_init(j->t.limot2, w);
     if (type == dJointTypeHinge) { j->t.axis1[0] = 1; j->t.axis2[0] = 1; }
+    if (type == dJointTypeSlider) j->t.axis1[0] = 1;
     if (type == dJointTypeUniversal) { j->t.axis1[0] = 1; j->t.axis2[1] = 1; }
     w->joints.push_back(j);
     if (g) g->joints.push_back(j);
@@ -742,6 +752,30 @@ dJointID dJointCreateBall(dWorldID w, dJointGroupID g) { return new_joint(w, g, 
 dJointID dJointCreateHinge(dWorldID w, dJointGroupID g) { return new_joint(w, g, dJointTypeHinge); }
 dJointID dJointCreateUniversal(dWorldID w, dJointGroupID g) { return new_joint(w, g, dJointTypeUniversal); }
 dJointID dJointCreateFixed(dWorldID w, dJointGroupID g) { return new_joint(w, g, dJointTypeFixed); }
+dJointID dJointCreateSlider(dWorldID w, dJointGroupID g) { return new_joint(w, g, dJointTypeSlider); }
+void dJointSetSliderAxis(dJointID j, Real x, Real y, Real z)
+{   // slider.cpp:249-260
+    std::vector<HostBody> hb = joint_bodies(j, j->t);
+    host_set_slider_axis(hb, j->t, x, y, z);
+}
+void dJointGetSliderAxis(dJointID j, Real *result) { joint_get_axis(j, j->t.axis1, result); }
+void dJointSetSliderParam(dJointID j, int parameter, Real value) { limot_set(j->t.limot1, parameter, value); }
+Real dJointGetSliderPosition(dJointID j)
+{   // slider.cpp:46-82 on the host mirror of the body state
+    const DJointT &t = j->t;
+    const dxBody *b0 = j->body[0], *b1 = j->body[1];
+    if (!b0) return 0;
+    Real ax1[3], q[3];
+    mul0_331(ax1, b0->R, t.axis1);
+    if (b1) {
+        mul0_331(q, b1->R, t.anchor1);
+        for (int i = 0; i < 3; i++) q[i] = b0->pos[i] - q[i] - b1->pos[i];
+    } else {
+        q[0] = b0->pos[0] - t.anchor1[0]; q[1] = b0->pos[1] - t.anchor1[1]; q[2] = b0->pos[2] - t.anchor1[2];
+        if (j->reverse) { ax1[0] = -ax1[0]; ax1[1] = -ax1[1]; ax1[2] = -ax1[2]; }
+    }
+    return dot3(ax1, q);
+}
 void dJointSetFixed(dJointID j)
 {   // fixed.cpp:113-136
     std::vector<HostBody> hb = joint_bodies(j, j->t);

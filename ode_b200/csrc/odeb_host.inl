@@ -159,6 +159,20 @@ static void host_set_fixed(const std::vector<HostBody> &hb, DJointT &j)
     j.anchor1[3] = 0;
     host_hinge_initial_rotation(hb, j);          // fixed.cpp:172-192 is the same formula as hinge.cpp:376-393
 }
+// dJointSetSliderAxis slider.cpp:249-260: setAxes(axis1) + computeOffset (:406-425, centre of body 1 in body 2's frame, kept in
+// anchor1) + computeInitialRelativeRotation (:382-401)
+static void host_set_slider_axis(const std::vector<HostBody> &hb, DJointT &j, Real x, Real y, Real z)
+{
+    host_set_axes(hb, j, x, y, z, j.axis1, 0);
+    if (j.b0 < 0) return;
+    const HostBody &b0 = hb[j.b0];
+    if (j.b1 >= 0) {
+        Real c[3] = { b0.pos[0] - hb[j.b1].pos[0], b0.pos[1] - hb[j.b1].pos[1], b0.pos[2] - hb[j.b1].pos[2] };
+        mul1_331(j.anchor1, hb[j.b1].R, c);
+    } else { j.anchor1[0] = b0.pos[0]; j.anchor1[1] = b0.pos[1]; j.anchor1[2] = b0.pos[2]; }
+    j.anchor1[3] = 0;
+    host_hinge_initial_rotation(hb, j);
+}
 // universal.cpp:372-401 computeInitialRelativeRotations
 static void host_universal_initial_rotations(const std::vector<HostBody> &hb, DJointT &j)
 {
@@ -492,7 +506,7 @@ OdebBatch *odeb_create(const OdebWorldParams *wp,
         const OdebJointDesc &d = joints[i];
         DJointT &j = T.jt[i];
         memset(&j, 0, sizeof(j));
-        if (d.type != ODEB_JOINT_BALL && d.type != ODEB_JOINT_HINGE && d.type != ODEB_JOINT_UNIVERSAL && d.type != ODEB_JOINT_FIXED) { set_err("joint %d: unsupported type %d", i, d.type); return 0; }
+        if (d.type != ODEB_JOINT_BALL && d.type != ODEB_JOINT_HINGE && d.type != ODEB_JOINT_UNIVERSAL && d.type != ODEB_JOINT_FIXED && d.type != ODEB_JOINT_SLIDER) { set_err("joint %d: unsupported type %d", i, d.type); return 0; }
         j.type = d.type; j.erp = erp; j.cfm = cfm;
         int b1 = d.body1, b2 = d.body2;
         if (b1 >= nbody || b2 >= nbody || (b1 < 0 && b2 < 0) || b1 == b2) { set_err("joint %d: bad bodies", i); return 0; }
@@ -504,6 +518,7 @@ OdebBatch *odeb_create(const OdebWorldParams *wp,
         host_limot(j.limot1, erp, cfm, d, 0);
         host_limot(j.limot2, erp, cfm, d, 1);
         if (j.type == ODEB_JOINT_FIXED) host_set_fixed(hb, j);
+        else if (j.type == ODEB_JOINT_SLIDER) { j.axis1[0] = 1; host_set_slider_axis(hb, j, (Real)d.axis1[0], (Real)d.axis1[1], (Real)d.axis1[2]); }
         else if (j.type == ODEB_JOINT_HINGE) {
             j.axis1[0] = 1; j.axis2[0] = 1;
             host_set_axes(hb, j, (Real)d.axis1[0], (Real)d.axis1[1], (Real)d.axis1[2], j.axis1, j.axis2);

@@ -138,6 +138,69 @@ __device__ bool odeb_add_limot(const DLimot &l, int limit, Real limit_err, const
     return true;
 }
 
+// addLimot, linear form (rotational = 0: the slider's stop / motor row), incl. the linear torque decoupling of joint.cpp:617-640.
+// Forces of a motor working against a stop (joint.cpp:655-704): fq is added to body 1 and subtracted from body 0, tboth is
+// added to both bodies' torques.
+__device__ bool odeb_add_limot_linear(const DLimot &l, int limit, Real limit_err, const DBody &b0, const DBody *b1,
+                                      Real fps, Real *row, const Real *ax1, Real *fq, Real *tboth, bool *has_f)
+{
+    int powered = l.fmax > 0;
+    if (!(powered || limit)) return false;
+    row[C_J1L] = ax1[0]; row[C_J1L + 1] = ax1[1]; row[C_J1L + 2] = ax1[2];
+    Real ltd[3] = { 0, 0, 0 };
+    if (b1) {
+        row[C_J2L] = -ax1[0]; row[C_J2L + 1] = -ax1[1]; row[C_J2L + 2] = -ax1[2];
+        Real c[3] = { R_(0.5) * (b1->pos[0] - b0.pos[0]), R_(0.5) * (b1->pos[1] - b0.pos[1]), R_(0.5) * (b1->pos[2] - b0.pos[2]) };
+        cross3(ltd, c, ax1);
+        row[C_J1A] = ltd[0]; row[C_J1A + 1] = ltd[1]; row[C_J1A + 2] = ltd[2];
+        row[C_J2A] = ltd[0]; row[C_J2A + 1] = ltd[1]; row[C_J2A + 2] = ltd[2];
+    }
+    if (limit && (l.lostop == l.histop)) powered = 0;
+    if (powered) {
+        row[C_CFM] = l.normal_cfm;
+        if (!limit) { row[C_RHS] = l.vel; row[C_LO] = -l.fmax; row[C_HI] = l.fmax; }
+        else {
+            Real fm = l.fmax;
+            if ((l.vel > 0) || (l.vel == 0 && limit == 2)) fm = -fm;
+            if ((limit == 1 && l.vel > 0) || (limit == 2 && l.vel < 0)) fm *= l.fudge_factor;
+            fq[0] = fm * ax1[0]; fq[1] = fm * ax1[1]; fq[2] = fm * ax1[2];
+            tboth[0] = -fm * ltd[0]; tboth[1] = -fm * ltd[1]; tboth[2] = -fm * ltd[2];
+            *has_f = true;
+        }
+    }
+    if (limit) {
+        Real k = fps * l.stop_erp;
+        row[C_RHS] = -k * limit_err;
+        row[C_CFM] = l.stop_cfm;
+        if (l.lostop == l.histop) { row[C_LO] = -R_INF; row[C_HI] = R_INF; }
+        else {
+            if (limit == 1) { row[C_LO] = 0; row[C_HI] = R_INF; } else { row[C_LO] = -R_INF; row[C_HI] = 0; }
+            if (l.bounce > 0) {
+                Real vel = dot3(b0.lvel, ax1);
+                if (b1) vel -= dot3(b1->lvel, ax1);
+                if (limit == 1) { if (vel < 0) { Real newc = -l.bounce * vel; if (newc > row[C_RHS]) row[C_RHS] = newc; } }
+                else { if (vel > 0) { Real newc = -l.bounce * vel; if (newc < row[C_RHS]) row[C_RHS] = newc; } }
+            }
+        }
+    }
+    return true;
+}
+
+// dJointGetSliderPosition slider.cpp:46-82 (offset of dxJointSlider::computeOffset travels in anchor1)
+__device__ Real odeb_slider_position(const DJointT &j, const DBody &b0, const DBody *b1)
+{
+    Real ax1[3], q[3];
+    mul0_331(ax1, b0.R, j.axis1);
+    if (b1) {
+        mul0_331(q, b1->R, j.anchor1);
+        for (int i = 0; i < 3; i++) q[i] = b0.pos[i] - q[i] - b1->pos[i];
+    } else {
+        q[0] = b0.pos[0] - j.anchor1[0]; q[1] = b0.pos[1] - j.anchor1[1]; q[2] = b0.pos[2] - j.anchor1[2];
+        if (j.reverse) { ax1[0] = -ax1[0]; ax1[1] = -ax1[1]; ax1[2] = -ax1[2]; }
+    }
+    return dot3(ax1, q);
+}
+
 // dxJointUniversal::getAxes universal.cpp:55-71
 __device__ __forceinline__ void odeb_universal_axes(const DJointT &j, const DBody &b0, const DBody *b1, Real *ax1, Real *ax2)
 {
@@ -172,6 +235,15 @@ __device__ void odeb_joint_info1(const DJointT &j, const DBody &b0, const DBody 
     ls->limit1 = ls->limit2 = 0; ls->err1 = ls->err2 = 0;
     if (j.type == 1) { *m = 3; return; }
     if (j.type == 7) { *m = 6; return; }           // fixed.cpp:52-57
+    if (j.type == 3) {                             // slider.cpp:115-145
+        int mm = (j.limot1.fmax > 0) ? 6 : 5;
+        if ((j.limot1.lostop > -R_INF || j.limot1.histop < R_INF) && j.limot1.lostop <= j.limot1.histop) {
+            Real pos = odeb_slider_position(j, b0, b1);
+            if (odeb_limot_test(j.limot1, pos, &ls->limit1, &ls->err1)) mm = 6;
+        }
+        *m = mm;
+        return;
+    }
     if (j.type == 2) {
         int mm = (j.limot1.fmax > 0) ? 6 : 5;
         if ((j.limot1.lostop >= -M_PI || j.limot1.histop <= M_PI) && j.limot1.lostop <= j.limot1.histop) {
@@ -212,8 +284,42 @@ __device__ void odeb_set_fixed_orientation(const DBody &b0, const DBody *b1, Rea
 // getInfo2 of ball (ball.cpp:57-67), hinge (hinge.cpp:77-147), universal (universal.cpp:297-369), fixed (fixed.cpp:60-110).
 // tq0 accumulates the torque the limit motors add to body0 (negated) / body1.
 __device__ void odeb_joint_info2(const DJointT &j, const DLimitState &ls, const DBody &b0, const DBody *b1,
-                                 Real fps, Real worldERP, Real *row, Real *tq, bool *has_tq)
+                                 Real fps, Real worldERP, Real *row, Real *tq, bool *has_tq, Real *fq, Real *tboth, bool *has_f)
 {
+    if (j.type == 3) {   // slider.cpp:148-246
+        odeb_set_fixed_orientation(b0, b1, fps, worldERP, row, j.qrel);
+        Real ax1[3], p[3], q[3], c[3] = { 0, 0, 0 };
+        mul0_331(ax1, b0.R, j.axis1);
+        plane_space(ax1, p, q);
+        if (b1) { c[0] = b1->pos[0] - b0.pos[0]; c[1] = b1->pos[1] - b0.pos[1]; c[2] = b1->pos[2] - b0.pos[2]; }
+        Real *r3 = row + 3 * ROWLEN, *r4 = row + 4 * ROWLEN;
+        r3[C_J1L] = p[0]; r3[C_J1L + 1] = p[1]; r3[C_J1L + 2] = p[2];
+        r4[C_J1L] = q[0]; r4[C_J1L + 1] = q[1]; r4[C_J1L + 2] = q[2];
+        if (b1) {
+            Real tmp[3];
+            r3[C_J2L] = -p[0]; r3[C_J2L + 1] = -p[1]; r3[C_J2L + 2] = -p[2];
+            cross3(tmp, c, p);
+            for (int t = 0; t < 3; t++) { r3[C_J1A + t] = tmp[t] * R_(0.5); r3[C_J2A + t] = r3[C_J1A + t]; }
+            r4[C_J2L] = -q[0]; r4[C_J2L + 1] = -q[1]; r4[C_J2L + 2] = -q[2];
+            cross3(tmp, c, q);
+            for (int t = 0; t < 3; t++) { r4[C_J1A + t] = tmp[t] * R_(0.5); r4[C_J2A + t] = r4[C_J1A + t]; }
+        }
+        const Real k = fps * worldERP;
+        if (b1) {
+            Real ofs[3];
+            mul0_331(ofs, b1->R, j.anchor1);
+            c[0] = c[0] + ofs[0]; c[1] = c[1] + ofs[1]; c[2] = c[2] + ofs[2];
+            r3[C_RHS] = k * dot3(p, c);
+            r4[C_RHS] = k * dot3(q, c);
+        } else {
+            Real ofs[3] = { j.anchor1[0] - b0.pos[0], j.anchor1[1] - b0.pos[1], j.anchor1[2] - b0.pos[2] };
+            r3[C_RHS] = k * dot3(p, ofs);
+            r4[C_RHS] = k * dot3(q, ofs);
+            if (j.reverse) { ax1[0] = -ax1[0]; ax1[1] = -ax1[1]; ax1[2] = -ax1[2]; }
+        }
+        odeb_add_limot_linear(j.limot1, ls.limit1, ls.err1, b0, b1, fps, row + 5 * ROWLEN, ax1, fq, tboth, has_f);
+        return;
+    }
     if (j.type == 1) {
         row[C_CFM] = j.cfm; row[ROWLEN + C_CFM] = j.cfm; row[2 * ROWLEN + C_CFM] = j.cfm;
         odeb_set_ball(b0, b1, fps, j.erp, row, j.anchor1, j.anchor2);

@@ -490,8 +490,8 @@ __global__ void k_rows(const __grid_constant__ DevParams P, const __grid_constan
     int findex[6];
     int m, b0i, b1i;
     DBody b0, b1;
-    Real tq[3] = { 0, 0, 0 };
-    bool has_tq = false;
+    Real tq[3] = { 0, 0, 0 }, fq[3] = { 0, 0, 0 }, tboth[3] = { 0, 0, 0 };
+    bool has_tq = false, has_f = false;
     if (jid >= P.NJ) {
         int4 ci = D.cinfo[(size_t)w * P.MC + (jid - P.NJ)];
         const DSurface &surf = P.classic ? D.csurf[jid - P.NJ] : P.surf;
@@ -519,7 +519,7 @@ __global__ void k_rows(const __grid_constant__ DevParams P, const __grid_constan
         }
         load_body(D, w * P.NB + b0i, b0);
         if (b1i >= 0) load_body(D, w * P.NB + b1i, b1);
-        odeb_joint_info2(jt, D.jlimit[(size_t)w * P.NJ + jid], b0, b1i >= 0 ? &b1 : 0, P.hrecip, P.erp, row, tq, &has_tq);
+        odeb_joint_info2(jt, D.jlimit[(size_t)w * P.NJ + jid], b0, b1i >= 0 ? &b1 : 0, P.hrecip, P.erp, row, tq, &has_tq, fq, tboth, &has_f);
     }
     int p0 = D.body_pos[(size_t)w * P.NB + b0i], p1 = b1i >= 0 ? D.body_pos[(size_t)w * P.NB + b1i] : -1;
     Real4 *rec = D.rows + ((size_t)w * P.MR + row0) * 8;
@@ -542,6 +542,16 @@ __global__ void k_rows(const __grid_constant__ DevParams P, const __grid_constan
         }
         // body order positions travel in the last two slots of the record
         *(int *)&rec[8 * r + 7].z = p0; *(int *)&rec[8 * r + 7].w = p1;
+    }
+    if (has_f) {    // dBodyAddForce / dBodyAddTorque from a powered linear limit motor at its stop (joints/joint.cpp:688-704)
+        Real *f0 = (Real *)&D.facc[(size_t)w * P.NB + b0i];
+        atomic_add_real(f0, -fq[0]); atomic_add_real(f0 + 1, -fq[1]); atomic_add_real(f0 + 2, -fq[2]);
+        if (b1i >= 0) {
+            Real *f1 = (Real *)&D.facc[(size_t)w * P.NB + b1i], *t0 = (Real *)&D.tacc[(size_t)w * P.NB + b0i], *t1 = (Real *)&D.tacc[(size_t)w * P.NB + b1i];
+            atomic_add_real(t0, tboth[0]); atomic_add_real(t0 + 1, tboth[1]); atomic_add_real(t0 + 2, tboth[2]);
+            atomic_add_real(t1, tboth[0]); atomic_add_real(t1 + 1, tboth[1]); atomic_add_real(t1 + 2, tboth[2]);
+            atomic_add_real(f1, fq[0]); atomic_add_real(f1 + 1, fq[1]); atomic_add_real(f1 + 2, fq[2]);
+        }
     }
     if (has_tq) {   // dBodyAddTorque from a powered limit motor at its stop (joints/joint.cpp:677-705)
         Real *t0 = (Real *)&D.tacc[(size_t)w * P.NB + b0i];

@@ -4,6 +4,7 @@ Scene recipes follow the reference's demos (ode/demo/demo_boxstack.cpp, demo_cha
 demo_crash.cpp); the ragdoll is authored here because the reference has none.
 """
 import numpy as np
+INF_ = float("inf")
 from . import _binding as B
 
 
@@ -124,6 +125,35 @@ def compound(nworlds=1, seed0=31):
         r = _rng(seed0 + w)
         lvel[w] = 0.2 * (r.rand(nb, 3) - 0.5)
         avel[w] = 0.3 * (r.rand(nb, 3) - 0.5)
+    sc.state = dict(pos=pos, quat=quat, lvel=lvel, avel=avel)
+    sc.seeds = (seed0 + np.arange(nworlds)).astype(np.uint32)
+    return sc
+
+
+def sliders(nworlds=1, seed0=41):
+    """Slider joints (joints/slider.cpp): a vertical piston between two boxes with stops and bounce, a horizontal slider to the
+    environment (bodies reversed) driven by a motor into its stop, and a free slider between two boxes lying on the plane.
+    Contacts <= 4 per pair, mode 0, mu = inf; nothing on the path calls libm."""
+    sc = B.Scene(B.default_world_params(gravity=(0, 0, -3.0), cfm=1e-5, max_contacts=4, surf_mode=0, mu=B.INF, skip_connected=1), nworlds)
+    sc.add_geom(B.PLANE, (0, 0, 1, 0))
+    m, I = B.box_mass(2.0, 0.3, 0.3, 0.2)
+    centres = [(0.0, 0.0, 0.1), (0.0, 0.0, 0.6), (1.5, 0.0, 0.8), (3.0, 0.0, 0.1), (3.6, 0.1, 0.1)]
+    for c in centres:
+        b = sc.add_body(m, I, c)
+        sc.add_geom(B.BOX, (0.3, 0.3, 0.2), body=b)
+    sc.add_joint(B.JOINT_SLIDER, 1, 0, (0, 0, 0), axis1=(0, 0, 1), lo_stop=(-0.15, -INF_), hi_stop=(0.25, INF_), bounce=(0.3, -1))
+    sc.add_joint(B.JOINT_SLIDER, -1, 2, (0, 0, 0), axis1=(1, 0, 0), lo_stop=(-0.2, -INF_), hi_stop=(0.3, INF_), vel=(0.8, 0), fmax=(6.0, 0),
+                 fudge_factor=(0.5, -1))
+    sc.add_joint(B.JOINT_SLIDER, 3, 4, (0, 0, 0), axis1=(1, 0.2, 0))
+    nb = sc.nbody
+    pos = np.tile(np.asarray(sc.body_pos)[None], (nworlds, 1, 1))
+    quat = np.tile(np.array([1.0, 0, 0, 0])[None, None], (nworlds, nb, 1))
+    lvel = np.zeros((nworlds, nb, 3))
+    avel = np.zeros((nworlds, nb, 3))
+    for w in range(nworlds):
+        r = _rng(seed0 + w)
+        lvel[w] = 0.6 * (r.rand(nb, 3) - 0.5)
+        avel[w] = 0.2 * (r.rand(nb, 3) - 0.5)
     sc.state = dict(pos=pos, quat=quat, lvel=lvel, avel=avel)
     sc.seeds = (seed0 + np.arange(nworlds)).astype(np.uint32)
     return sc

@@ -128,6 +128,88 @@ static bool add_limot(World &W, Joint &j, Limot &l, Real fps, Real *row, const R
     return true;
 }
 
+// addLimot joints/joint.cpp:596-780, linear form (rotational = 0) incl. the linear torque decoupling step :617-640
+static bool add_limot_linear(World &W, Joint &j, Limot &l, Real fps, Real *row, const Real *ax1)
+{
+    int powered = l.fmax > 0;
+    if (!(powered || l.limit)) return false;
+    Body &b0 = W.bodies[j.b0];
+    row[C_J1L] = ax1[0]; row[C_J1L + 1] = ax1[1]; row[C_J1L + 2] = ax1[2];
+    Real ltd[3] = { 0, 0, 0 };
+    if (j.b1 >= 0) {
+        const Body &b1 = W.bodies[j.b1];
+        row[C_J2L] = -ax1[0]; row[C_J2L + 1] = -ax1[1]; row[C_J2L + 2] = -ax1[2];
+        Real c[3] = { R_(0.5) * (b1.pos[0] - b0.pos[0]), R_(0.5) * (b1.pos[1] - b0.pos[1]), R_(0.5) * (b1.pos[2] - b0.pos[2]) };
+        cross3(ltd, c, ax1);
+        row[C_J1A] = ltd[0]; row[C_J1A + 1] = ltd[1]; row[C_J1A + 2] = ltd[2];
+        row[C_J2A] = ltd[0]; row[C_J2A + 1] = ltd[1]; row[C_J2A + 2] = ltd[2];
+    }
+    if (l.limit && (l.lostop == l.histop)) powered = 0;
+    if (powered) {
+        row[C_CFM] = l.normal_cfm;
+        if (!l.limit) { row[C_RHS] = l.vel; row[C_LO] = -l.fmax; row[C_HI] = l.fmax; }
+        else {
+            Real fm = l.fmax;
+            if ((l.vel > 0) || (l.vel == 0 && l.limit == 2)) fm = -fm;
+            if ((l.limit == 1 && l.vel > 0) || (l.limit == 2 && l.vel < 0)) fm *= l.fudge_factor;
+            Real f0 = fm * ax1[0], f1 = fm * ax1[1], f2 = fm * ax1[2];
+            if (j.b1 >= 0) {
+                Body &b1 = W.bodies[j.b1];
+                Real t0 = -fm * ltd[0], t1 = -fm * ltd[1], t2 = -fm * ltd[2];
+                b0.tacc[0] += t0; b0.tacc[1] += t1; b0.tacc[2] += t2;
+                b1.tacc[0] += t0; b1.tacc[1] += t1; b1.tacc[2] += t2;
+                b1.facc[0] += f0; b1.facc[1] += f1; b1.facc[2] += f2;
+            }
+            b0.facc[0] += -f0; b0.facc[1] += -f1; b0.facc[2] += -f2;
+        }
+    }
+    if (l.limit) {
+        Real k = fps * l.stop_erp;
+        row[C_RHS] = -k * l.limit_err;
+        row[C_CFM] = l.stop_cfm;
+        if (l.lostop == l.histop) { row[C_LO] = -R_INF; row[C_HI] = R_INF; }
+        else {
+            if (l.limit == 1) { row[C_LO] = 0; row[C_HI] = R_INF; } else { row[C_LO] = -R_INF; row[C_HI] = 0; }
+            if (l.bounce > 0) {
+                Real vel = dot3(b0.lvel, ax1);
+                if (j.b1 >= 0) vel -= dot3(W.bodies[j.b1].lvel, ax1);
+                if (l.limit == 1) { if (vel < 0) { Real newc = -l.bounce * vel; if (newc > row[C_RHS]) row[C_RHS] = newc; } }
+                else { if (vel > 0) { Real newc = -l.bounce * vel; if (newc < row[C_RHS]) row[C_RHS] = newc; } }
+            }
+        }
+    }
+    return true;
+}
+
+// dJointGetSliderPosition slider.cpp:46-82 (offset kept in anchor1)
+static Real slider_position(World &W, Joint &j)
+{
+    const Body &b0 = W.bodies[j.b0];
+    Real ax1[3], q[3];
+    mul0_331(ax1, b0.R, j.axis1);
+    if (j.b1 >= 0) {
+        const Body &b1 = W.bodies[j.b1];
+        mul0_331(q, b1.R, j.anchor1);
+        for (int i = 0; i < 3; i++) q[i] = b0.pos[i] - q[i] - b1.pos[i];
+    } else {
+        q[0] = b0.pos[0] - j.anchor1[0]; q[1] = b0.pos[1] - j.anchor1[1]; q[2] = b0.pos[2] - j.anchor1[2];
+        if (j.reverse) { ax1[0] = -ax1[0]; ax1[1] = -ax1[1]; ax1[2] = -ax1[2]; }
+    }
+    return dot3(ax1, q);
+}
+
+// dxJointSlider::getInfo1 slider.cpp:115-145
+static void slider_info1(World &W, Joint &j)
+{
+    j.nub = 5;
+    j.m = (j.limot1.fmax > 0) ? 6 : 5;
+    j.limot1.limit = 0;
+    if ((j.limot1.lostop > -R_INF || j.limot1.histop < R_INF) && j.limot1.lostop <= j.limot1.histop) {
+        Real pos = slider_position(W, j);
+        if (limot_test(j.limot1, pos)) j.m = 6;
+    }
+}
+
 // dxJointHinge::getInfo1 hinge.cpp:54-74
 static void hinge_info1(World &W, Joint &j)
 {
@@ -261,6 +343,43 @@ static void fixed_info2(World &W, Joint &j, Real fps, Real worldERP, Real *row)
     row[C_CFM] = j.cfm; row[ROWLEN + C_CFM] = j.cfm; row[2 * ROWLEN + C_CFM] = j.cfm;
 }
 
+// dxJointSlider::getInfo2 slider.cpp:148-246
+static void slider_info2(World &W, Joint &j, Real fps, Real worldERP, Real *row)
+{
+    set_fixed_orientation(W, j, fps, worldERP, row, j.qrel);
+    const Body &b0 = W.bodies[j.b0];
+    Real ax1[3], p[3], q[3], c[3] = { 0, 0, 0 };
+    mul0_331(ax1, b0.R, j.axis1);
+    plane_space(ax1, p, q);
+    if (j.b1 >= 0) { const Body &b1 = W.bodies[j.b1]; c[0] = b1.pos[0] - b0.pos[0]; c[1] = b1.pos[1] - b0.pos[1]; c[2] = b1.pos[2] - b0.pos[2]; }
+    Real *r3 = row + 3 * ROWLEN, *r4 = row + 4 * ROWLEN;
+    r3[C_J1L] = p[0]; r3[C_J1L + 1] = p[1]; r3[C_J1L + 2] = p[2];
+    r4[C_J1L] = q[0]; r4[C_J1L + 1] = q[1]; r4[C_J1L + 2] = q[2];
+    if (j.b1 >= 0) {
+        Real tmp[3];
+        r3[C_J2L] = -p[0]; r3[C_J2L + 1] = -p[1]; r3[C_J2L + 2] = -p[2];
+        cross3(tmp, c, p);
+        for (int t = 0; t < 3; t++) { r3[C_J1A + t] = tmp[t] * R_(0.5); r3[C_J2A + t] = r3[C_J1A + t]; }
+        r4[C_J2L] = -q[0]; r4[C_J2L + 1] = -q[1]; r4[C_J2L + 2] = -q[2];
+        cross3(tmp, c, q);
+        for (int t = 0; t < 3; t++) { r4[C_J1A + t] = tmp[t] * R_(0.5); r4[C_J2A + t] = r4[C_J1A + t]; }
+    }
+    Real k = fps * worldERP;
+    if (j.b1 >= 0) {
+        Real ofs[3];
+        mul0_331(ofs, W.bodies[j.b1].R, j.anchor1);
+        c[0] = c[0] + ofs[0]; c[1] = c[1] + ofs[1]; c[2] = c[2] + ofs[2];
+        r3[C_RHS] = k * dot3(p, c);
+        r4[C_RHS] = k * dot3(q, c);
+    } else {
+        Real ofs[3] = { j.anchor1[0] - b0.pos[0], j.anchor1[1] - b0.pos[1], j.anchor1[2] - b0.pos[2] };
+        r3[C_RHS] = k * dot3(p, ofs);
+        r4[C_RHS] = k * dot3(q, ofs);
+        if (j.reverse) { ax1[0] = -ax1[0]; ax1[1] = -ax1[1]; ax1[2] = -ax1[2]; }
+    }
+    add_limot_linear(W, j, j.limot1, fps, row + 5 * ROWLEN, ax1);
+}
+
 // dJointSet{Ball,Hinge,Universal}Anchor/Axis at the template pose
 static void joint_setup(const Batch &B, World &W, Joint &j, const OdebJointDesc &d)
 {
@@ -275,6 +394,18 @@ static void joint_setup(const Batch &B, World &W, Joint &j, const OdebJointDesc 
         } else { j.anchor1[0] = b0.pos[0]; j.anchor1[1] = b0.pos[1]; j.anchor1[2] = b0.pos[2]; }
         if (j.b1 >= 0) qmul1(j.qrel, b0.q, W.bodies[j.b1].q);
         else { const Real *q = b0.q; j.qrel[0] = q[0]; j.qrel[1] = -q[1]; j.qrel[2] = -q[2]; j.qrel[3] = -q[3]; }
+    } else if (j.type == ODEB_JOINT_SLIDER) {
+        // dJointSetSliderAxis slider.cpp:249-260: setAxes(axis1), computeOffset :406-425, computeInitialRelativeRotation :382-401
+        j.axis1[0] = 1;
+        set_axes(W, j, (Real)d.axis1[0], (Real)d.axis1[1], (Real)d.axis1[2], j.axis1, 0);
+        const Body &b0 = W.bodies[j.b0];
+        if (j.b1 >= 0) {
+            Real c[3] = { b0.pos[0] - W.bodies[j.b1].pos[0], b0.pos[1] - W.bodies[j.b1].pos[1], b0.pos[2] - W.bodies[j.b1].pos[2] };
+            mul1_331(j.anchor1, W.bodies[j.b1].R, c);
+        } else { j.anchor1[0] = b0.pos[0]; j.anchor1[1] = b0.pos[1]; j.anchor1[2] = b0.pos[2]; }
+        if (j.b1 >= 0) qmul1(j.qrel, b0.q, W.bodies[j.b1].q);
+        else { const Real *q = b0.q; j.qrel[0] = q[0]; j.qrel[1] = -q[1]; j.qrel[2] = -q[2]; j.qrel[3] = -q[3]; }
+        limot_set(j.limot1, d, 0);
     } else if (j.type == ODEB_JOINT_HINGE) {
         j.axis1[0] = 1; j.axis2[0] = 1;   // constructor defaults hinge.cpp:36-43
         set_axes(W, j, (Real)d.axis1[0], (Real)d.axis1[1], (Real)d.axis1[2], j.axis1, j.axis2);

@@ -538,6 +538,7 @@ void joint_info1(const Batch &B, World &W, Joint &j)
     case ODEB_JOINT_CONTACT: contact_info1(B, j); break;
     case ODEB_JOINT_BALL: j.m = 3; j.nub = 3; break;       // ball.cpp:49-54
     case ODEB_JOINT_FIXED: j.m = 6; j.nub = 6; break;      // fixed.cpp:52-57
+    case ODEB_JOINT_SLIDER: slider_info1(W, j); break;
     case ODEB_JOINT_HINGE: hinge_info1(W, j); break;
     case ODEB_JOINT_UNIVERSAL: universal_info1(W, j); break;
     }
@@ -552,6 +553,7 @@ void joint_info2(const Batch &B, World &W, Joint &j, Real fps, Real worldERP, Re
         set_ball(W, j, fps, j.erp, row, j.anchor1, j.anchor2);
         break;
     case ODEB_JOINT_FIXED: fixed_info2(W, j, fps, worldERP, row); break;
+    case ODEB_JOINT_SLIDER: slider_info2(W, j, fps, worldERP, row); break;
     case ODEB_JOINT_HINGE: hinge_info2(W, j, fps, worldERP, row, findex); break;
     case ODEB_JOINT_UNIVERSAL: universal_info2(W, j, fps, worldERP, row, findex); break;
     }

@@ -100,7 +100,7 @@ void set_limot(dJointID j, int type, const OdebJointDesc &d)
 {
     for (int a = 0; a < (type == ODEB_JOINT_UNIVERSAL ? 2 : 1); a++) {
         int grp = a * dParamGroup;
-        void (*setp)(dJointID, int, dReal) = (type == ODEB_JOINT_HINGE) ? dJointSetHingeParam : dJointSetUniversalParam;
+        void (*setp)(dJointID, int, dReal) = (type == ODEB_JOINT_HINGE) ? dJointSetHingeParam : (type == ODEB_JOINT_SLIDER) ? dJointSetSliderParam : dJointSetUniversalParam;
         // the reference documents setting lo, hi, lo again when lo > hi may be transiently true
         setp(j, dParamLoStop + grp, (dReal)d.lo_stop[a]);
         setp(j, dParamHiStop + grp, (dReal)d.hi_stop[a]);
@@ -178,6 +178,10 @@ void *ref_create(const OdebWorldParams *wp,
             if (d.type == ODEB_JOINT_BALL) {
                 j = dJointCreateBall(W.world, 0); dJointAttach(j, b1, b2);
                 dJointSetBallAnchor(j, (dReal)d.anchor[0], (dReal)d.anchor[1], (dReal)d.anchor[2]);
+            } else if (d.type == ODEB_JOINT_SLIDER) {
+                j = dJointCreateSlider(W.world, 0); dJointAttach(j, b1, b2);
+                dJointSetSliderAxis(j, (dReal)d.axis1[0], (dReal)d.axis1[1], (dReal)d.axis1[2]);
+                set_limot(j, d.type, d);
             } else if (d.type == ODEB_JOINT_FIXED) {
                 j = dJointCreateFixed(W.world, 0); dJointAttach(j, b1, b2);
                 dJointSetFixed(j);

@@ -349,3 +349,22 @@ def test_edge_cases_gpu(prec):
             st = b.get_state()
             assert all(np.isfinite(st[k]).all() for k in st)
         b.close()
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("solver", ("v4", "p4"))
+def test_slider_joints_bit_exact(prec, solver, monkeypatch):
+    """Slider joints (slider.cpp:115-246, linear addLimot joint.cpp:596-780 with stops, bounce and a motor at its stop) on the
+    GPU: every observable and the joint feedback identical to the oracle, every step."""
+    from test_oracle import compare_feedback
+    monkeypatch.setenv("ODEB_SOLVER", solver)
+    sc = scenes.sliders(5)
+    a, b = B.Batch(orc_lib(prec), sc), B.Batch(gpu_lib(prec), sc)
+    a.enable_feedback()
+    b.enable_feedback()
+    for s in range(150):
+        a.step(0.02)
+        b.step(0.02)
+        bad = compare_step(a, b, sc.nworlds) + compare_feedback(a, b, sc.nworlds, True, 0)
+        assert not bad, (solver, s, bad[:4])
+    b.close()

@@ -182,3 +182,25 @@ def test_fixed_joints_vs_reference(prec):
         b.step(0.02)
         bad = compare_step(a, b, sc.nworlds) + compare_feedback(a, b, sc.nworlds, True, 0)
         assert not bad, (s, bad[:4])
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_slider_joints_vs_reference(prec):
+    """dJointCreateSlider / dJointSetSliderAxis / dJointSetSliderParam (joints/slider.cpp) with stops, bounce, a motor driven
+    into its stop (dBodyAddForce path of the linear addLimot, joint.cpp:655-704) and a reversed attachment to the environment:
+    restatement against the compiled reference, bit-identical."""
+    ref = ref_lib(prec)
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    sc = scenes.sliders(3)
+    a, b = B.Batch(ref, sc), B.Batch(orc_lib(prec), sc)
+    a.enable_feedback()
+    b.enable_feedback()
+    six = 0
+    for s in range(150):
+        a.step(0.02)
+        b.step(0.02)
+        bad = compare_step(a, b, sc.nworlds) + compare_feedback(a, b, sc.nworlds, True, 0)
+        assert not bad, (s, bad[:4])
+    pos = b.get_state()["pos"]
+    assert np.isfinite(pos).all()
