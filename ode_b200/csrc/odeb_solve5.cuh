@@ -28,9 +28,6 @@
 #define ODEB5_FAR 12                                       // L2 prefetch distance in slots
 #endif
 #define ODEB5_PAD (ODEB5_RING + ODEB5_FAR + 4)
-#ifndef ODEB5_EXP_CH
-#define ODEB5_EXP_CH CH                                     // timing experiments only: copy fewer chunks per record
-#endif
 #define ODEB5_MAXBODIES 62
 #define E5_ROW(e) ((int)((e) & 0x3ffu))
 #define E5_FI(e) ((int)(((e) >> 10) & 0x3ffu))
@@ -82,7 +79,7 @@ __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefe
             if (E5_B1(ma) != NBd) {                                                                                      \
                 const char *src = rec_base + (size_t)E5_ROW(ma) * (sizeof(Real) * 32);                                   \
                 const unsigned dst = ring_addr + (unsigned)((((K) + ODEB5_RING - 1) & (ODEB5_RING - 1)) * CH * 32 * 16); \
-                _Pragma("unroll") for (int c = 0; c < ODEB5_EXP_CH; c++) cp_async16(dst + c * 32 * 16, src + c * 16);   \
+                _Pragma("unroll") for (int c = 0; c < CH; c++) cp_async16(dst + c * 32 * 16, src + c * 16);             \
             }                                                                                                            \
             cp_async_commit();                                                                                           \
             if (E5_B1(mf) != NBd) prefetch_l2(rec_base + (size_t)E5_ROW(mf) * (sizeof(Real) * 32));                      \
