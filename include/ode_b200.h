@@ -40,7 +40,7 @@ typedef float odeb_real;
 /* geom classes: numbering of the reference (include/ode/collision.h:881-902) */
 enum { ODEB_SPHERE = 0, ODEB_BOX = 1, ODEB_CAPSULE = 2, ODEB_PLANE = 4 };
 /* joint types: numbering of the reference dJointType (include/ode/common.h:406-426) */
-enum { ODEB_JOINT_BALL = 1, ODEB_JOINT_HINGE = 2, ODEB_JOINT_SLIDER = 3, ODEB_JOINT_CONTACT = 4, ODEB_JOINT_UNIVERSAL = 5, ODEB_JOINT_FIXED = 7 };
+enum { ODEB_JOINT_BALL = 1, ODEB_JOINT_HINGE = 2, ODEB_JOINT_SLIDER = 3, ODEB_JOINT_CONTACT = 4, ODEB_JOINT_UNIVERSAL = 5, ODEB_JOINT_HINGE2 = 6, ODEB_JOINT_FIXED = 7 };
 /* broadphase flavours: which reference space's callback stream is reproduced (as a set) */
 enum { ODEB_SPACE_HASH = 0, ODEB_SPACE_SAP = 1 };
 
@@ -114,6 +114,9 @@ typedef struct OdebJointDesc {
     double lo_stop[2], hi_stop[2]; /* dParamLoStop/HiStop (axis 1, axis 2); defaults -inf/+inf */
     double vel[2], fmax[2];     /* dParamVel, dParamFMax; default 0 */
     double fudge_factor[2], bounce[2], stop_erp[2], stop_cfm[2]; /* <0 = keep defaults */
+    double susp_erp, susp_cfm;  /* ODEB_JOINT_HINGE2: dParamSuspensionERP / dParamSuspensionCFM, <0 = the world's ERP / CFM.
+                                   Hinge2 = dJointSetHinge2Anchor(anchor) + dJointSetHinge2Axes(axis1, axis2), needs both bodies;
+                                   stops / motor of axis 1 and the motor of axis 2 are the [0] / [1] entries above */
 } OdebJointDesc;
 
 /* per-world counters of dWorldQuickStepIterationCount_DynamicAdjustmentStatistics

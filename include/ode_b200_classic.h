@@ -17,7 +17,7 @@
  * getters return pointers into library storage (ode.cpp:413-484).  There is no CPU implementation of any of these
  * stages: without a CUDA device dWorldQuickStep returns 0 and dSpaceCollide reports through the error handler.
  *
- * Outside the subset (calls are not exported): dWorldStep, joints other than contact/ball/hinge/slider/universal/fixed, geoms other
+ * Outside the subset (calls are not exported): dWorldStep, joints other than contact/ball/hinge/slider/universal/hinge2/fixed, geoms other
  * than sphere/box/capsule/plane, geom offsets, nested spaces, rolling friction, per-body
  * auto-disable thresholds (the world's are used), SAP axis orders other than dSAP_AXES_XYZ.
  */
@@ -244,6 +244,12 @@ void dJointGroupEmpty(dJointGroupID);
 dJointID dJointCreateContact(dWorldID, dJointGroupID, const dContact *);
 dJointID dJointCreateBall(dWorldID, dJointGroupID);
 dJointID dJointCreateHinge(dWorldID, dJointGroupID);
+dJointID dJointCreateHinge2(dWorldID, dJointGroupID);           /* joints/hinge2.cpp; needs two bodies */
+void dJointSetHinge2Anchor(dJointID, dReal x, dReal y, dReal z);
+void dJointSetHinge2Axes(dJointID, const dReal *axis1, const dReal *axis2);
+void dJointSetHinge2Axis1(dJointID, dReal x, dReal y, dReal z);
+void dJointSetHinge2Axis2(dJointID, dReal x, dReal y, dReal z);
+void dJointSetHinge2Param(dJointID, int parameter, dReal value);
 dJointID dJointCreateSlider(dWorldID, dJointGroupID);           /* joints/slider.cpp */
 void dJointSetSliderAxis(dJointID, dReal x, dReal y, dReal z);
 void dJointGetSliderAxis(dJointID, dVector3 result);

@@ -45,7 +45,8 @@ class OdebJointDesc(C.Structure):
                 ("lo_stop", C.c_double * 2), ("hi_stop", C.c_double * 2),
                 ("vel", C.c_double * 2), ("fmax", C.c_double * 2),
                 ("fudge_factor", C.c_double * 2), ("bounce", C.c_double * 2),
-                ("stop_erp", C.c_double * 2), ("stop_cfm", C.c_double * 2)]
+                ("stop_erp", C.c_double * 2), ("stop_cfm", C.c_double * 2),
+                ("susp_erp", C.c_double), ("susp_cfm", C.c_double)]
 
 
 class OdebStats(C.Structure):
@@ -53,7 +54,7 @@ class OdebStats(C.Structure):
 
 
 SPHERE, BOX, CAPSULE, PLANE = 0, 1, 2, 4
-JOINT_BALL, JOINT_HINGE, JOINT_SLIDER, JOINT_CONTACT, JOINT_UNIVERSAL, JOINT_FIXED = 1, 2, 3, 4, 5, 7
+JOINT_BALL, JOINT_HINGE, JOINT_SLIDER, JOINT_CONTACT, JOINT_UNIVERSAL, JOINT_HINGE2, JOINT_FIXED = 1, 2, 3, 4, 5, 6, 7
 SPACE_HASH, SPACE_SAP = 0, 1
 CONTACT_MU2, CONTACT_BOUNCE, CONTACT_SOFT_ERP, CONTACT_SOFT_CFM = 0x001, 0x004, 0x008, 0x010
 CONTACT_MOTION1, CONTACT_MOTION2, CONTACT_MOTIONN = 0x020, 0x040, 0x080
@@ -119,7 +120,7 @@ class Scene:
 
     def add_joint(self, jtype, body1, body2, anchor, axis1=(1, 0, 0), axis2=(0, 1, 0),
                   lo_stop=(-INF, -INF), hi_stop=(INF, INF), vel=(0, 0), fmax=(0, 0),
-                  fudge_factor=(-1, -1), bounce=(-1, -1), stop_erp=(-1, -1), stop_cfm=(-1, -1)):
+                  fudge_factor=(-1, -1), bounce=(-1, -1), stop_erp=(-1, -1), stop_cfm=(-1, -1), susp_erp=-1.0, susp_cfm=-1.0):
         j = OdebJointDesc()
         j.type, j.body1, j.body2 = jtype, body1, body2
         j.anchor[:] = anchor
@@ -133,6 +134,7 @@ class Scene:
         j.bounce[:] = bounce
         j.stop_erp[:] = stop_erp
         j.stop_cfm[:] = stop_cfm
+        j.susp_erp, j.susp_cfm = susp_erp, susp_cfm
         self.joints.append(j)
         return len(self.joints) - 1
 

@@ -379,6 +379,19 @@ static void joint_set_relative_values(dxJoint *j)
 {   // dxJoint*::setRelativeValues (ball.cpp:179-185, hinge.cpp:359-369, universal.cpp:785-808): called by dJointAttach
     DJointT &t = j->t;
     if (j->type == dJointTypeContact || j->type == dJointTypeFixed) return;     // dxJointFixed keeps offset / qrel until dJointSetFixed
+    if (j->type == dJointTypeHinge2) {                                          // hinge2.cpp:517-536: anchor, both axes, v1/v2 from the new bodies
+        Real anchor[3] = { 0, 0, 0 }, a1[3] = { 0, 0, 0 }, a2[3] = { 0, 0, 0 };
+        if (!j->body[0] || !j->body[1]) return;
+        joint_get_anchor(j, t.anchor1, anchor);
+        mul0_331(a1, j->body[0]->R, t.axis1);
+        mul0_331(a2, j->body[1]->R, t.axis2);
+        std::vector<HostBody> hb = joint_bodies(j, t);
+        host_set_anchors(hb, t, anchor[0], anchor[1], anchor[2]);
+        host_set_axes(hb, t, a1[0], a1[1], a1[2], t.axis1, 0);
+        host_set_axes(hb, t, a2[0], a2[1], a2[2], 0, t.axis2);
+        host_hinge2_finish(hb, t);
+        return;
+    }
     if (j->type == dJointTypeSlider) {                                          // slider.cpp:371-376: computeOffset + computeInitialRelativeRotation
         std::vector<HostBody> hb = joint_bodies(j, t);
         if (t.b0 >= 0) {
@@ -442,6 +455,7 @@ static dxJoint *new_joint(dxWorld *w, dxJointGroup *g, int type)
     limot_init(j->t.limot1, w); limot_init(j->t.limot2, w);
     if (type == dJointTypeHinge) { j->t.axis1[0] = 1; j->t.axis2[0] = 1; }
     if (type == dJointTypeSlider) j->t.axis1[0] = 1;
+    if (type == dJointTypeHinge2) { j->t.axis1[0] = 1; j->t.axis2[1] = 1; j->t.qrel1[0] = 1; j->t.qrel2[1] = 1; j->t.qrel[2] = j->t.erp; j->t.qrel[3] = j->t.cfm; }   // hinge2.cpp:76-100
     if (type == dJointTypeUniversal) { j->t.axis1[0] = 1; j->t.axis2[1] = 1; }
     w->joints.push_back(j);
     if (g) g->joints.push_back(j);
@@ -752,6 +766,29 @@ dJointID dJointCreateBall(dWorldID w, dJointGroupID g) { return new_joint(w, g, 
 dJointID dJointCreateHinge(dWorldID w, dJointGroupID g) { return new_joint(w, g, dJointTypeHinge); }
 dJointID dJointCreateUniversal(dWorldID w, dJointGroupID g) { return new_joint(w, g, dJointTypeUniversal); }
 dJointID dJointCreateFixed(dWorldID w, dJointGroupID g) { return new_joint(w, g, dJointTypeFixed); }
+dJointID dJointCreateHinge2(dWorldID w, dJointGroupID g) { return new_joint(w, g, dJointTypeHinge2); }
+void dJointSetHinge2Anchor(dJointID j, Real x, Real y, Real z)
+{   // hinge2.cpp:268-279
+    std::vector<HostBody> hb = joint_bodies(j, j->t);
+    host_set_anchors(hb, j->t, x, y, z);
+    host_hinge2_finish(hb, j->t);
+}
+void dJointSetHinge2Axes(dJointID j, const Real *axis1, const Real *axis2)
+{   // hinge2.cpp:283-312
+    std::vector<HostBody> hb = joint_bodies(j, j->t);
+    if (axis1) host_set_axes(hb, j->t, axis1[0], axis1[1], axis1[2], j->t.axis1, 0);
+    if (axis2) host_set_axes(hb, j->t, axis2[0], axis2[1], axis2[2], 0, j->t.axis2);
+    host_hinge2_finish(hb, j->t);
+}
+void dJointSetHinge2Axis1(dJointID j, Real x, Real y, Real z) { Real a[4] = { x, y, z, 0 }; dJointSetHinge2Axes(j, a, 0); }
+void dJointSetHinge2Axis2(dJointID j, Real x, Real y, Real z) { Real a[4] = { x, y, z, 0 }; dJointSetHinge2Axes(j, 0, a); }
+void dJointSetHinge2Param(dJointID j, int parameter, Real value)
+{   // hinge2.cpp:333-348; suspension ERP / CFM live in t.qrel[2] / t.qrel[3]
+    if ((parameter & 0xff00) == 0x100) limot_set(j->t.limot2, parameter & 0xff, value);
+    else if (parameter == dParamSuspensionERP) j->t.qrel[2] = value;
+    else if (parameter == dParamSuspensionCFM) j->t.qrel[3] = value;
+    else limot_set(j->t.limot1, parameter, value);
+}
 dJointID dJointCreateSlider(dWorldID w, dJointGroupID g) { return new_joint(w, g, dJointTypeSlider); }
 void dJointSetSliderAxis(dJointID j, Real x, Real y, Real z)
 {   // slider.cpp:249-260

@@ -159,6 +159,24 @@ static void host_set_fixed(const std::vector<HostBody> &hb, DJointT &j)
     j.anchor1[3] = 0;
     host_hinge_initial_rotation(hb, j);          // fixed.cpp:172-192 is the same formula as hinge.cpp:376-393
 }
+// dJointSetHinge2Axes hinge2.cpp:283-312: getAxisInfo -> s0, c0 (kept in qrel[1], qrel[0]) and makeV1andV2 :214-240 (v1, v2 kept in
+// qrel1, qrel2). Both bodies are required (dJOINT_TWOBODIES).
+static void host_hinge2_finish(const std::vector<HostBody> &hb, DJointT &j)
+{
+    if (j.b0 < 0 || j.b1 < 0) return;
+    Real ax1[3], ax2[3], ax[3], v[3];
+    mul0_331(ax1, hb[j.b0].R, j.axis1);
+    mul0_331(ax2, hb[j.b1].R, j.axis2);
+    cross3(ax, ax1, ax2);
+    j.qrel[1] = RSQRT(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
+    j.qrel[0] = dot3(ax1, ax2);
+    const Real k = dot3(ax1, ax2);
+    ax2[0] = ax2[0] + ax1[0] * (-k); ax2[1] = ax2[1] + ax1[1] * (-k); ax2[2] = ax2[2] + ax1[2] * (-k);
+    normalize3(ax2);
+    cross3(v, ax1, ax2);
+    mul1_331(j.qrel1, hb[j.b0].R, ax2); j.qrel1[3] = 0;
+    mul1_331(j.qrel2, hb[j.b0].R, v); j.qrel2[3] = 0;
+}
 // dJointSetSliderAxis slider.cpp:249-260: setAxes(axis1) + computeOffset (:406-425, centre of body 1 in body 2's frame, kept in
 // anchor1) + computeInitialRelativeRotation (:382-401)
 static void host_set_slider_axis(const std::vector<HostBody> &hb, DJointT &j, Real x, Real y, Real z)
@@ -506,7 +524,7 @@ OdebBatch *odeb_create(const OdebWorldParams *wp,
         const OdebJointDesc &d = joints[i];
         DJointT &j = T.jt[i];
         memset(&j, 0, sizeof(j));
-        if (d.type != ODEB_JOINT_BALL && d.type != ODEB_JOINT_HINGE && d.type != ODEB_JOINT_UNIVERSAL && d.type != ODEB_JOINT_FIXED && d.type != ODEB_JOINT_SLIDER) { set_err("joint %d: unsupported type %d", i, d.type); return 0; }
+        if (d.type != ODEB_JOINT_BALL && d.type != ODEB_JOINT_HINGE && d.type != ODEB_JOINT_UNIVERSAL && d.type != ODEB_JOINT_FIXED && d.type != ODEB_JOINT_SLIDER && d.type != ODEB_JOINT_HINGE2) { set_err("joint %d: unsupported type %d", i, d.type); return 0; }
         j.type = d.type; j.erp = erp; j.cfm = cfm;
         int b1 = d.body1, b2 = d.body2;
         if (b1 >= nbody || b2 >= nbody || (b1 < 0 && b2 < 0) || b1 == b2) { set_err("joint %d: bad bodies", i); return 0; }
@@ -517,7 +535,15 @@ OdebBatch *odeb_create(const OdebWorldParams *wp,
         host_set_anchors(hb, j, (Real)d.anchor[0], (Real)d.anchor[1], (Real)d.anchor[2]);
         host_limot(j.limot1, erp, cfm, d, 0);
         host_limot(j.limot2, erp, cfm, d, 1);
-        if (j.type == ODEB_JOINT_FIXED) host_set_fixed(hb, j);
+        if (j.type == ODEB_JOINT_HINGE2) {
+            if (j.b1 < 0 || j.reverse) { set_err("joint %d: a hinge2 joint needs two bodies", i); return 0; }
+            j.axis1[0] = 1; j.axis2[1] = 1;                       // hinge2.cpp:76-100
+            host_set_axes(hb, j, (Real)d.axis1[0], (Real)d.axis1[1], (Real)d.axis1[2], j.axis1, 0);
+            host_set_axes(hb, j, (Real)d.axis2[0], (Real)d.axis2[1], (Real)d.axis2[2], 0, j.axis2);
+            host_hinge2_finish(hb, j);
+            j.qrel[2] = d.susp_erp >= 0 ? (Real)d.susp_erp : erp;
+            j.qrel[3] = d.susp_cfm >= 0 ? (Real)d.susp_cfm : cfm;
+        } else if (j.type == ODEB_JOINT_FIXED) host_set_fixed(hb, j);
         else if (j.type == ODEB_JOINT_SLIDER) { j.axis1[0] = 1; host_set_slider_axis(hb, j, (Real)d.axis1[0], (Real)d.axis1[1], (Real)d.axis1[2]); }
         else if (j.type == ODEB_JOINT_HINGE) {
             j.axis1[0] = 1; j.axis2[0] = 1;

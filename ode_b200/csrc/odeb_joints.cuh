@@ -17,6 +17,7 @@ struct DLimot {     // dxJointLimitMotor, static part (joints/joint.h:291-320)
 struct DJointT {    // template (per-batch) description of a permanent joint, after dJointAttach's swap
     int type, b0, b1, reverse;
     Real anchor1[4], anchor2[4], axis1[4], axis2[4], qrel[4], qrel1[4], qrel2[4];
+    // fixed / slider: anchor1 = offset. hinge2: qrel = {c0, s0, susp_erp, susp_cfm}, qrel1 = v1, qrel2 = v2 (hinge2.cpp:76-100)
     Real erp, cfm;
     DLimot limot1, limot2;
 };
@@ -235,6 +236,20 @@ __device__ void odeb_joint_info1(const DJointT &j, const DBody &b0, const DBody 
     ls->limit1 = ls->limit2 = 0; ls->err1 = ls->err2 = 0;
     if (j.type == 1) { *m = 3; return; }
     if (j.type == 7) { *m = 6; return; }           // fixed.cpp:52-57
+    if (j.type == 6) {                             // hinge2.cpp:110-130 (needs both bodies)
+        int mm = 4;
+        if ((j.limot1.lostop >= -M_PI || j.limot1.histop <= M_PI) && j.limot1.lostop <= j.limot1.histop) {
+            Real p[3], q[3];                       // measureAngle1 hinge2.cpp:33-52
+            mul0_331(p, b1->R, j.axis2);
+            mul1_331(q, b0.R, p);
+            Real x = dot3(j.qrel1, q), y = dot3(j.qrel2, q);
+            odeb_limot_test(j.limot1, -RATAN2(y, x), &ls->limit1, &ls->err1);
+        }
+        if (ls->limit1 || j.limot1.fmax > 0) mm++;
+        if (j.limot2.fmax > 0) mm++;
+        *m = mm;
+        return;
+    }
     if (j.type == 3) {                             // slider.cpp:115-145
         int mm = (j.limot1.fmax > 0) ? 6 : 5;
         if ((j.limot1.lostop > -R_INF || j.limot1.histop < R_INF) && j.limot1.lostop <= j.limot1.histop) {
@@ -286,6 +301,45 @@ __device__ void odeb_set_fixed_orientation(const DBody &b0, const DBody *b1, Rea
 __device__ void odeb_joint_info2(const DJointT &j, const DLimitState &ls, const DBody &b0, const DBody *b1,
                                  Real fps, Real worldERP, Real *row, Real *tq, bool *has_tq, Real *fq, Real *tboth, bool *has_f)
 {
+    if (j.type == 6) {   // hinge2.cpp:155-209 with setBall2 joints/joint.cpp:165-213 (two-body form)
+        Real ax1[3], ax2[3], q[3];
+        mul0_331(ax1, b0.R, j.axis1);
+        mul0_331(ax2, b1->R, j.axis2);
+        cross3(q, ax1, ax2);
+        const Real sn = RSQRT(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]), cs = dot3(ax1, ax2);
+        normalize3(q);
+        {   // setBall2: rows along (ax1, q1, q2); row 0 is the suspension (its own ERP / CFM)
+            Real q1[3], q2[3], a1[3], a2[3];
+            plane_space(ax1, q1, q2);
+            Real *r0 = row, *r1 = row + ROWLEN, *r2 = row + 2 * ROWLEN;
+            for (int t = 0; t < 3; t++) { r0[C_J1L + t] = ax1[t]; r1[C_J1L + t] = q1[t]; r2[C_J1L + t] = q2[t]; }
+            mul0_331(a1, b0.R, j.anchor1);
+            cross3(r0 + C_J1A, a1, ax1); cross3(r1 + C_J1A, a1, q1); cross3(r2 + C_J1A, a1, q2);
+            a1[0] = a1[0] + b0.pos[0]; a1[1] = a1[1] + b0.pos[1]; a1[2] = a1[2] + b0.pos[2];
+            const Real k1 = fps * j.qrel[2], k = fps * worldERP;
+            for (int t = 0; t < 3; t++) { r0[C_J2L + t] = -ax1[t]; r1[C_J2L + t] = -q1[t]; r2[C_J2L + t] = -q2[t]; }
+            mul0_331(a2, b1->R, j.anchor2);
+            cross3(r0 + C_J2A, ax1, a2); cross3(r1 + C_J2A, q1, a2); cross3(r2 + C_J2A, q2, a2);
+            a2[0] = a2[0] + b1->pos[0]; a2[1] = a2[1] + b1->pos[1]; a2[2] = a2[2] + b1->pos[2];
+            Real d[3] = { a2[0] - a1[0], a2[1] - a1[1], a2[2] - a1[2] };
+            r0[C_RHS] = k1 * dot3(ax1, d);
+            r1[C_RHS] = k * dot3(q1, d);
+            r2[C_RHS] = k * dot3(q2, d);
+            r0[C_CFM] = j.qrel[3];
+        }
+        Real *r3 = row + 3 * ROWLEN;
+        r3[C_J1A] = q[0]; r3[C_J1A + 1] = q[1]; r3[C_J1A + 2] = q[2];
+        r3[C_J2A] = -q[0]; r3[C_J2A + 1] = -q[1]; r3[C_J2A + 2] = -q[2];
+        r3[C_RHS] = fps * worldERP * (j.qrel[0] * sn - j.qrel[1] * cs);
+        int r = 4;
+        Real t[3];
+        bool ht = false;
+        if (odeb_add_limot(j.limot1, ls.limit1, ls.err1, b0, b1, fps, row + r * ROWLEN, ax1, t, &ht)) r++;
+        if (ht) { tq[0] += t[0]; tq[1] += t[1]; tq[2] += t[2]; *has_tq = true; }
+        ht = false;
+        odeb_add_limot(j.limot2, 0, 0, b0, b1, fps, row + r * ROWLEN, ax2, t, &ht);
+        return;
+    }
     if (j.type == 3) {   // slider.cpp:148-246
         odeb_set_fixed_orientation(b0, b1, fps, worldERP, row, j.qrel);
         Real ax1[3], p[3], q[3], c[3] = { 0, 0, 0 };

@@ -159,6 +159,49 @@ def sliders(nworlds=1, seed0=41):
     return sc
 
 
+def buggy(nworlds=1, seed0=51, stops=False):
+    """demo_buggy.cpp:200-260: a box chassis on three sphere wheels held by hinge2 joints (axis 1 = steering / suspension (0,0,1),
+    axis 2 = wheel axle (0,1,0), suspension ERP 0.4 / CFM 0.8), driven by the axis-2 motor of the front wheel and steered by the
+    axis-1 motor; ground contacts as demo_buggy.cpp:96-108 (Slip1|Slip2|SoftERP|SoftCFM|Approx1, mu = inf).
+    stops=False: no stops on axis 1 (nothing on the path calls libm: bit-exact scenes);
+    stops=True: steering stops +-0.75 on the front wheel and the rear wheels locked with lo = hi = 0 as in the demo
+    (measureAngle1 -> atan2: tolerance scenes)."""
+    mode = B.CONTACT_SLIP1 | B.CONTACT_SLIP2 | B.CONTACT_SOFT_ERP | B.CONTACT_SOFT_CFM | B.CONTACT_APPROX1
+    sc = B.Scene(B.default_world_params(gravity=(0, 0, -0.5), max_contacts=8, surf_mode=mode, mu=B.INF, slip1=0.1, slip2=0.1,
+                                        soft_erp=0.5, soft_cfm=0.3, skip_connected=1), nworlds)
+    sc.add_geom(B.PLANE, (0, 0, 1, 0), category=1, collide=2)
+    L, W, H, R, Z = 0.7, 0.5, 0.2, 0.18, 0.5
+    m, I = B.box_mass(1.0, L, W, H)
+    I = I / m                                         # dMassAdjust(&m, CMASS = 1)
+    chassis = sc.add_body(1.0, I, (0, 0, Z))
+    sc.add_geom(B.BOX, (L, W, H), body=chassis, category=2, collide=1)
+    ms, Is = B.sphere_mass(1.0, R)
+    Is = Is * (0.2 / ms)                              # WMASS = 0.2
+    s = np.sqrt(0.5)
+    wheels = []
+    for k, (x, y) in enumerate(((0.5 * L, 0.0), (-0.5 * L, 0.5 * W), (-0.5 * L, -0.5 * W))):
+        b = sc.add_body(0.2, Is, (x, y, Z - 0.5 * H), (s, s, 0.0, 0.0))       # dQFromAxisAndAngle(q, 1,0,0, pi/2)
+        sc.add_geom(B.SPHERE, (R,), body=b, category=2, collide=1)
+        wheels.append(b)
+        lo, hi = (-INF_, -INF_), (INF_, INF_)
+        if stops:
+            lo, hi = ((-0.75, -INF_), (0.75, INF_)) if k == 0 else ((0.0, -INF_), (0.0, INF_))
+        vel, fmax = ((0.3, -1.5), (0.2, 0.1)) if k == 0 else ((0.0, 0.0), (0.0, 0.0))
+        sc.add_joint(B.JOINT_HINGE2, chassis, b, (x, y, Z - 0.5 * H), axis1=(0, 0, 1), axis2=(0, 1, 0), lo_stop=lo, hi_stop=hi,
+                     vel=vel, fmax=fmax, susp_erp=0.4, susp_cfm=0.8)
+    nb = sc.nbody
+    pos = np.tile(np.asarray(sc.body_pos)[None], (nworlds, 1, 1))
+    quat = np.tile(np.asarray(sc.body_quat)[None], (nworlds, 1, 1))
+    lvel = np.zeros((nworlds, nb, 3))
+    avel = np.zeros((nworlds, nb, 3))
+    for w in range(nworlds):
+        r = _rng(seed0 + w)
+        lvel[w] = 0.1 * (r.rand(nb, 3) - 0.5)
+    sc.state = dict(pos=pos, quat=quat, lvel=lvel, avel=avel)
+    sc.seeds = (seed0 + np.arange(nworlds)).astype(np.uint32)
+    return sc
+
+
 def free_boxes(nworlds=1, nboxes=64, seed0=5, grid=8, spacing=1.5):
     """nboxes separate unit boxes resting/falling on the plane: many one-body islands per world
     (the scattered 64-body world of SURVEY.md 7.2(4))."""

@@ -181,6 +181,61 @@ static bool add_limot_linear(World &W, Joint &j, Limot &l, Real fps, Real *row, 
     return true;
 }
 
+// dxJointHinge2::getInfo1 hinge2.cpp:110-130 with measureAngle1 :33-52. Storage: qrel = {c0, s0, susp_erp, susp_cfm}, qrel1 = v1, qrel2 = v2
+static void hinge2_info1(World &W, Joint &j)
+{
+    j.m = 4; j.nub = 4;
+    j.limot1.limit = 0;
+    if ((j.limot1.lostop >= -M_PI || j.limot1.histop <= M_PI) && j.limot1.lostop <= j.limot1.histop) {
+        Real p[3], q[3];
+        mul0_331(p, W.bodies[j.b1].R, j.axis2);
+        mul1_331(q, W.bodies[j.b0].R, p);
+        Real x = dot3(j.qrel1, q), y = dot3(j.qrel2, q);
+        limot_test(j.limot1, -RATAN2(y, x));
+    }
+    if (j.limot1.limit || j.limot1.fmax > 0) j.m++;
+    j.limot2.limit = 0;
+    if (j.limot2.fmax > 0) j.m++;
+}
+
+// dxJointHinge2::getInfo2 hinge2.cpp:155-209 with setBall2 joints/joint.cpp:165-213 (two-body form; hinge2 is dJOINT_TWOBODIES)
+static void hinge2_info2(World &W, Joint &j, Real fps, Real worldERP, Real *row)
+{
+    const Body &b0 = W.bodies[j.b0], &b1 = W.bodies[j.b1];
+    Real ax1[3], ax2[3], q[3];
+    mul0_331(ax1, b0.R, j.axis1);
+    mul0_331(ax2, b1.R, j.axis2);
+    cross3(q, ax1, ax2);
+    Real sn = RSQRT(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]), cs = dot3(ax1, ax2);
+    normalize3(q);
+    {
+        Real q1[3], q2[3], a1[3], a2[3];
+        plane_space(ax1, q1, q2);
+        Real *r0 = row, *r1 = row + ROWLEN, *r2 = row + 2 * ROWLEN;
+        for (int t = 0; t < 3; t++) { r0[C_J1L + t] = ax1[t]; r1[C_J1L + t] = q1[t]; r2[C_J1L + t] = q2[t]; }
+        mul0_331(a1, b0.R, j.anchor1);
+        cross3(r0 + C_J1A, a1, ax1); cross3(r1 + C_J1A, a1, q1); cross3(r2 + C_J1A, a1, q2);
+        a1[0] = a1[0] + b0.pos[0]; a1[1] = a1[1] + b0.pos[1]; a1[2] = a1[2] + b0.pos[2];
+        Real k1 = fps * j.qrel[2], k = fps * worldERP;
+        for (int t = 0; t < 3; t++) { r0[C_J2L + t] = -ax1[t]; r1[C_J2L + t] = -q1[t]; r2[C_J2L + t] = -q2[t]; }
+        mul0_331(a2, b1.R, j.anchor2);
+        cross3(r0 + C_J2A, ax1, a2); cross3(r1 + C_J2A, q1, a2); cross3(r2 + C_J2A, q2, a2);
+        a2[0] = a2[0] + b1.pos[0]; a2[1] = a2[1] + b1.pos[1]; a2[2] = a2[2] + b1.pos[2];
+        Real d[3] = { a2[0] - a1[0], a2[1] - a1[1], a2[2] - a1[2] };
+        r0[C_RHS] = k1 * dot3(ax1, d);
+        r1[C_RHS] = k * dot3(q1, d);
+        r2[C_RHS] = k * dot3(q2, d);
+        r0[C_CFM] = j.qrel[3];
+    }
+    Real *r3 = row + 3 * ROWLEN;
+    r3[C_J1A] = q[0]; r3[C_J1A + 1] = q[1]; r3[C_J1A + 2] = q[2];
+    r3[C_J2A] = -q[0]; r3[C_J2A + 1] = -q[1]; r3[C_J2A + 2] = -q[2];
+    r3[C_RHS] = fps * worldERP * (j.qrel[0] * sn - j.qrel[1] * cs);
+    int r = 4;
+    if (add_limot(W, j, j.limot1, fps, row + r * ROWLEN, ax1)) r++;
+    add_limot(W, j, j.limot2, fps, row + r * ROWLEN, ax2);
+}
+
 // dJointGetSliderPosition slider.cpp:46-82 (offset kept in anchor1)
 static Real slider_position(World &W, Joint &j)
 {
@@ -383,7 +438,6 @@ static void slider_info2(World &W, Joint &j, Real fps, Real worldERP, Real *row)
 // dJointSet{Ball,Hinge,Universal}Anchor/Axis at the template pose
 static void joint_setup(const Batch &B, World &W, Joint &j, const OdebJointDesc &d)
 {
-    (void)B;
     set_anchors(W, j, (Real)d.anchor[0], (Real)d.anchor[1], (Real)d.anchor[2]);
     if (j.type == ODEB_JOINT_FIXED) {
         // dJointSetFixed fixed.cpp:113-142
@@ -394,6 +448,28 @@ static void joint_setup(const Batch &B, World &W, Joint &j, const OdebJointDesc 
         } else { j.anchor1[0] = b0.pos[0]; j.anchor1[1] = b0.pos[1]; j.anchor1[2] = b0.pos[2]; }
         if (j.b1 >= 0) qmul1(j.qrel, b0.q, W.bodies[j.b1].q);
         else { const Real *q = b0.q; j.qrel[0] = q[0]; j.qrel[1] = -q[1]; j.qrel[2] = -q[2]; j.qrel[3] = -q[3]; }
+    } else if (j.type == ODEB_JOINT_HINGE2) {
+        // dJointSetHinge2Anchor + dJointSetHinge2Axes hinge2.cpp:268-312, makeV1andV2 :214-240
+        j.axis1[0] = 1; j.axis2[1] = 1;
+        set_axes(W, j, (Real)d.axis1[0], (Real)d.axis1[1], (Real)d.axis1[2], j.axis1, 0);
+        set_axes(W, j, (Real)d.axis2[0], (Real)d.axis2[1], (Real)d.axis2[2], 0, j.axis2);
+        const Body &b0 = W.bodies[j.b0], &b1 = W.bodies[j.b1];
+        Real ax1[3], ax2[3], ax[3], v[3];
+        mul0_331(ax1, b0.R, j.axis1);
+        mul0_331(ax2, b1.R, j.axis2);
+        cross3(ax, ax1, ax2);
+        j.qrel[1] = RSQRT(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
+        j.qrel[0] = dot3(ax1, ax2);
+        Real k = dot3(ax1, ax2);
+        ax2[0] = ax2[0] + ax1[0] * (-k); ax2[1] = ax2[1] + ax1[1] * (-k); ax2[2] = ax2[2] + ax1[2] * (-k);
+        normalize3(ax2);
+        cross3(v, ax1, ax2);
+        mul1_331(j.qrel1, b0.R, ax2);
+        mul1_331(j.qrel2, b0.R, v);
+        j.qrel[2] = d.susp_erp >= 0 ? (Real)d.susp_erp : B.erp;
+        j.qrel[3] = d.susp_cfm >= 0 ? (Real)d.susp_cfm : B.cfm;
+        limot_set(j.limot1, d, 0);
+        limot_set(j.limot2, d, 1);
     } else if (j.type == ODEB_JOINT_SLIDER) {
         // dJointSetSliderAxis slider.cpp:249-260: setAxes(axis1), computeOffset :406-425, computeInitialRelativeRotation :382-401
         j.axis1[0] = 1;

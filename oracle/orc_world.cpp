@@ -539,6 +539,7 @@ void joint_info1(const Batch &B, World &W, Joint &j)
     case ODEB_JOINT_BALL: j.m = 3; j.nub = 3; break;       // ball.cpp:49-54
     case ODEB_JOINT_FIXED: j.m = 6; j.nub = 6; break;      // fixed.cpp:52-57
     case ODEB_JOINT_SLIDER: slider_info1(W, j); break;
+    case ODEB_JOINT_HINGE2: hinge2_info1(W, j); break;
     case ODEB_JOINT_HINGE: hinge_info1(W, j); break;
     case ODEB_JOINT_UNIVERSAL: universal_info1(W, j); break;
     }
@@ -554,6 +555,7 @@ void joint_info2(const Batch &B, World &W, Joint &j, Real fps, Real worldERP, Re
         break;
     case ODEB_JOINT_FIXED: fixed_info2(W, j, fps, worldERP, row); break;
     case ODEB_JOINT_SLIDER: slider_info2(W, j, fps, worldERP, row); break;
+    case ODEB_JOINT_HINGE2: hinge2_info2(W, j, fps, worldERP, row); break;
     case ODEB_JOINT_HINGE: hinge_info2(W, j, fps, worldERP, row, findex); break;
     case ODEB_JOINT_UNIVERSAL: universal_info2(W, j, fps, worldERP, row, findex); break;
     }

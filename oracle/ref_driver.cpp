@@ -98,9 +98,9 @@ void apply_world_params(dWorldID w, const OdebWorldParams &p)
 
 void set_limot(dJointID j, int type, const OdebJointDesc &d)
 {
-    for (int a = 0; a < (type == ODEB_JOINT_UNIVERSAL ? 2 : 1); a++) {
+    for (int a = 0; a < ((type == ODEB_JOINT_UNIVERSAL || type == ODEB_JOINT_HINGE2) ? 2 : 1); a++) {
         int grp = a * dParamGroup;
-        void (*setp)(dJointID, int, dReal) = (type == ODEB_JOINT_HINGE) ? dJointSetHingeParam : (type == ODEB_JOINT_SLIDER) ? dJointSetSliderParam : dJointSetUniversalParam;
+        void (*setp)(dJointID, int, dReal) = (type == ODEB_JOINT_HINGE) ? dJointSetHingeParam : (type == ODEB_JOINT_SLIDER) ? dJointSetSliderParam : (type == ODEB_JOINT_HINGE2) ? dJointSetHinge2Param : dJointSetUniversalParam;
         // the reference documents setting lo, hi, lo again when lo > hi may be transiently true
         setp(j, dParamLoStop + grp, (dReal)d.lo_stop[a]);
         setp(j, dParamHiStop + grp, (dReal)d.hi_stop[a]);
@@ -178,6 +178,15 @@ void *ref_create(const OdebWorldParams *wp,
             if (d.type == ODEB_JOINT_BALL) {
                 j = dJointCreateBall(W.world, 0); dJointAttach(j, b1, b2);
                 dJointSetBallAnchor(j, (dReal)d.anchor[0], (dReal)d.anchor[1], (dReal)d.anchor[2]);
+            } else if (d.type == ODEB_JOINT_HINGE2) {
+                if (!b1 || !b2) return 0;
+                j = dJointCreateHinge2(W.world, 0); dJointAttach(j, b1, b2);
+                dJointSetHinge2Anchor(j, (dReal)d.anchor[0], (dReal)d.anchor[1], (dReal)d.anchor[2]);
+                dVector3 a1 = { (dReal)d.axis1[0], (dReal)d.axis1[1], (dReal)d.axis1[2] }, a2 = { (dReal)d.axis2[0], (dReal)d.axis2[1], (dReal)d.axis2[2] };
+                dJointSetHinge2Axes(j, a1, a2);
+                set_limot(j, d.type, d);
+                if (d.susp_erp >= 0) dJointSetHinge2Param(j, dParamSuspensionERP, (dReal)d.susp_erp);
+                if (d.susp_cfm >= 0) dJointSetHinge2Param(j, dParamSuspensionCFM, (dReal)d.susp_cfm);
             } else if (d.type == ODEB_JOINT_SLIDER) {
                 j = dJointCreateSlider(W.world, 0); dJointAttach(j, b1, b2);
                 dJointSetSliderAxis(j, (dReal)d.axis1[0], (dReal)d.axis1[1], (dReal)d.axis1[2]);

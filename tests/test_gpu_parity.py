@@ -368,3 +368,33 @@ def test_slider_joints_bit_exact(prec, solver, monkeypatch):
         bad = compare_step(a, b, sc.nworlds) + compare_feedback(a, b, sc.nworlds, True, 0)
         assert not bad, (solver, s, bad[:4])
     b.close()
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("solver", ("v4", "p4"))
+def test_hinge2_joints(prec, solver, monkeypatch):
+    """Hinge2 joints (hinge2.cpp:110-209) on a demo_buggy-style vehicle. Without stops: every observable and the joint feedback
+    identical to the oracle, every step. With the demo's steering stops (measureAngle1 -> atan2, CUDA libm vs glibc): integer
+    observables identical, state within the stated tolerance per teacher-forced step."""
+    from test_oracle import compare_feedback
+    monkeypatch.setenv("ODEB_SOLVER", solver)
+    sc = scenes.buggy(5, stops=False)
+    a, b = B.Batch(orc_lib(prec), sc), B.Batch(gpu_lib(prec), sc)
+    a.enable_feedback()
+    b.enable_feedback()
+    for s in range(150):
+        a.step(0.05)
+        b.step(0.05)
+        bad = compare_step(a, b, sc.nworlds) + compare_feedback(a, b, sc.nworlds, True, 0)
+        assert not bad, (solver, s, bad[:4])
+    b.close()
+    sc = scenes.buggy(3, stops=True)
+    a, b = B.Batch(orc_lib(prec), sc), B.Batch(gpu_lib(prec), sc)
+    for s in range(100):
+        st = a.get_state()
+        b.set_state(**st)                       # teacher-forced: the CUDA step starts from the oracle's state
+        a.step(0.05)
+        b.step(0.05)
+        bad = compare_step(a, b, sc.nworlds, exact_float=False, tol=TOL[prec], what=("pairs", "islands", "state"))
+        assert not bad, (solver, s, bad[:4])
+    b.close()

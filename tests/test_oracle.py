@@ -204,3 +204,25 @@ def test_slider_joints_vs_reference(prec):
         assert not bad, (s, bad[:4])
     pos = b.get_state()["pos"]
     assert np.isfinite(pos).all()
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_hinge2_joints_vs_reference(prec):
+    """dJointCreateHinge2 / SetHinge2Anchor / SetHinge2Axes / SetHinge2Param (joints/hinge2.cpp, setBall2 with suspension ERP/CFM,
+    both motors) on a demo_buggy-style vehicle: restatement against the compiled reference. Without stops nothing calls libm:
+    bit-identical; with the demo's steering stops measureAngle1 goes through atan2 on both sides (glibc): still bit-identical."""
+    ref = ref_lib(prec)
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    for stops in (False, True):
+        sc = scenes.buggy(3, stops=stops)
+        a, b = B.Batch(ref, sc), B.Batch(orc_lib(prec), sc)
+        a.enable_feedback()
+        b.enable_feedback()
+        for s in range(150):
+            a.step(0.05)
+            b.step(0.05)
+            bad = compare_step(a, b, sc.nworlds) + compare_feedback(a, b, sc.nworlds, True, 0)
+            assert not bad, (stops, s, bad[:4])
+        st = b.get_state()
+        assert np.isfinite(st["pos"]).all() and np.abs(st["pos"][:, 0, :2]).max() > 0.05      # the buggy drove somewhere
