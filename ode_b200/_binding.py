@@ -253,14 +253,15 @@ class Batch:
         arrs = [self._arr(pos, 3), self._arr(quat, 4), self._arr(lvel, 3), self._arr(avel, 3)]
         self.slib._fn("set_state")(self.h, *[_ptr(a) for a in arrs])
 
-    def get_state(self):
+    def get_state(self, out=None):
+        """Body state as host arrays [W, NB, 3|4]. `out`: a dict returned by an earlier call, filled in place (the
+        steady-state loop of an application that owns its observation buffers)."""
         r = self.slib.real
-        pos = np.empty((self.W, self.NB, 3), r)
-        quat = np.empty((self.W, self.NB, 4), r)
-        lvel = np.empty((self.W, self.NB, 3), r)
-        avel = np.empty((self.W, self.NB, 3), r)
-        self.slib._fn("get_state")(self.h, _ptr(pos), _ptr(quat), _ptr(lvel), _ptr(avel))
-        return dict(pos=pos, quat=quat, lvel=lvel, avel=avel)
+        if out is None:
+            out = dict(pos=np.empty((self.W, self.NB, 3), r), quat=np.empty((self.W, self.NB, 4), r),
+                       lvel=np.empty((self.W, self.NB, 3), r), avel=np.empty((self.W, self.NB, 3), r))
+        self.slib._fn("get_state")(self.h, _ptr(out["pos"]), _ptr(out["quat"]), _ptr(out["lvel"]), _ptr(out["avel"]))
+        return out
 
     def add_force(self, force=None, torque=None):
         self.slib._fn("add_force")(self.h, _ptr(self._arr(force, 3)), _ptr(self._arr(torque, 3)))
