@@ -158,6 +158,17 @@ def other_configs(slib, device):
         b.close()
     except Exception as e:  # noqa: BLE001
         out["ragdoll"] = {"error": str(e)[:200]}
+    try:   # north_star shape: batched 64-body worlds (piles of boxes and spheres, several islands per world)
+        nw = 4096
+        b = B.Batch(slib, scenes.pile(nworlds=nw, nbodies=64), device=device)
+        b.step(0.01, 150)
+        b.step(0.01, 5)
+        r = timed(b, 0.01, 10, nw * 64)
+        r["workload"] = "%d worlds x 64-body pile (boxes + spheres dropped on a plane, Approx1 friction), dt=0.01 (north_star: batched 64-body worlds)" % nw
+        out["pile64"] = r
+        b.close()
+    except Exception as e:  # noqa: BLE001
+        out["pile64"] = {"error": str(e)[:200]}
     try:   # configs[4]: one 100k-box wall, sweep-and-prune space, large-island path (ODEB_MODE_CANONICAL)
         sc = scenes.wall(500, 200)
         b = B.Batch(slib, sc, device=device)

@@ -209,7 +209,7 @@ int odeb_timed_steps(OdebBatch *, double h, int nsteps, size_t flush_bytes, doub
 uint64_t odeb_launch_count(const OdebBatch *);
 /* name of the SOR kernel the next step will launch (the library picks one of several bit-identical kernels per batch:
  * k_solve, k_solve5<P>, k_solve_bl; ODEB_SOLVER=v4|p2|p4|p8|bl in the environment forces one) */
-const char *odeb_solver_kernel(const OdebBatch *);
+const char *odeb_solver_kernel(OdebBatch *);
 /* device-side duration (ms) of the solver kernel launches accumulated since the last call; resets */
 double odeb_solver_ms(OdebBatch *, int *launches);
 void   odeb_enable_timing(OdebBatch *, int on);

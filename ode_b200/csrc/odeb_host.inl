@@ -28,7 +28,8 @@ struct OdebBatch {
     cudaGraphExec_t graph; double graph_h; bool use_graph; int graph_cfg;
     // solver selection: 0 = k_solve (one row at a time per world), 1..3 = k_solve5<2/4/8> (static P-processor schedule),
     // 4 = k_solve_bl (one lane per body). hint_m = largest island (rows) seen since the last sync, read back in odeb_sync.
-    int s5_sr[4]; size_t s5_smem[4]; int hint_m; int solver_force;
+    int s5_sr[4]; size_t s5_smem[4]; int hint_m; int solver_force;   // s5_sr / s5_smem: row budget and shared memory of k_solve5<2^k> for the next launch
+    int graph_sr;
     size_t isl_smem;                         // shared memory of k_islands_t<true> per block, 0 = scratch in global memory
     size_t solve_smem;
     int bl_G, bl_SR; size_t bl_smem;          // body-lane solver (odeb_solve_bl.cuh): lanes per world (0 = not used), row budget, bytes per warp
@@ -300,7 +301,7 @@ static OdebBatch *batch_build(const OdebWorldParams *wp, const HostTemplate &T, 
     OdebBatch *B = new OdebBatch();
     B->device = device; B->bytes = 0; B->launches = 0; B->timing = false; B->solver_ms = 0; B->solver_launches = 0;
     B->mode = ODEB_MODE_REPLAY; B->large_ready = false; memset(&B->L, 0, sizeof(B->L));
-    B->graph = 0; B->graph_h = -1; B->graph_cfg = -1; B->hint_m = 0; B->solver_force = -1; B->use_graph = getenv("ODEB_NO_GRAPH") == 0 && !classic; B->h_stage = 0; B->d_stage = 0; B->stream = 0; B->flush_buf = 0; B->flush_bytes = 0;
+    B->graph = 0; B->graph_h = -1; B->graph_cfg = -1; B->graph_sr = -1; B->hint_m = 0; B->solver_force = -1; B->use_graph = getenv("ODEB_NO_GRAPH") == 0 && !classic; B->h_stage = 0; B->d_stage = 0; B->stream = 0; B->flush_buf = 0; B->flush_bytes = 0;
     memset(&B->D, 0, sizeof(B->D));
     DevParams &P = B->P;
     memset(&P, 0, sizeof(P));
@@ -352,22 +353,8 @@ static OdebBatch *batch_build(const OdebWorldParams *wp, const HostTemplate &T, 
         }
     }
 
-    {   // k_solve5<P>: row capacity that fits when every warp of the batch is resident at once
-        cudaDeviceProp prop; int nsm = 148;
-        if (cudaGetDeviceProperties(&prop, device) == cudaSuccess && prop.multiProcessorCount > 0) nsm = prop.multiProcessorCount;
-        for (int k = 1; k <= 3; k++) {
-            const int Pk = 1 << k;
-            B->s5_sr[k] = 0; B->s5_smem[k] = 0;
-            if (P.NB > ODEB5_MAXBODIES) continue;
-            const long long warps = ((long long)nworlds + (16 / Pk) - 1) / (16 / Pk);
-            long long per_sm = (warps + nsm - 1) / nsm;
-            if (per_sm > 32) per_sm = 32;
-            const size_t budget = (size_t)(227 * 1024) / (size_t)per_sm - 1024;
-            int sr = P.MR < 1023 ? P.MR : 1023;
-            while (sr >= 16 && odeb5_smem(Pk, P.NB, sr) > budget) sr -= 4;
-            if (sr < 16) continue;
-            B->s5_sr[k] = sr; B->s5_smem[k] = odeb5_smem(Pk, P.NB, sr);
-        }
+    {   // k_solve5<P>: the row budget is chosen per launch from the largest island seen so far (choose_solver)
+        for (int k = 0; k <= 3; k++) { B->s5_sr[k] = 0; B->s5_smem[k] = 0; }
         if (const char *sel = getenv("ODEB_SOLVER")) {
             if (!strcmp(sel, "v4")) B->solver_force = 0;
             else if (!strcmp(sel, "p2")) B->solver_force = 1;
@@ -431,10 +418,9 @@ static OdebBatch *batch_build(const OdebWorldParams *wp, const HostTemplate &T, 
         cudaFuncSetAttribute(k_solve_bl<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_solve_bl<32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (getenv("ODEB_DEBUG")) {
-            int nb0 = 0, nb4 = 0;
+            int nb0 = 0;
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb0, k_solve, 32, B->solve_smem);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb4, k_solve5<4>, 32, B->s5_smem[2]);
-            fprintf(stderr, "[odeb] k_solve: SR=%d smem=%zu blocks/SM=%d | k_solve5<4>: SR=%d smem=%zu blocks/SM=%d\n", P.SR, B->solve_smem, nb0, B->s5_sr[2], B->s5_smem[2], nb4);
+            fprintf(stderr, "[odeb] k_solve: SR=%d smem=%zu blocks/SM=%d\n", P.SR, B->solve_smem, nb0);
         }
     }
     if (!ok) { odeb_destroy(B); return 0; }
@@ -673,24 +659,40 @@ static void launch_collide(OdebBatch *B, cudaStream_t s, bool narrow)
     if (narrow) { k_narrow<<<nblk(W * P.MP, 64), 64, 0, s>>>(P, D); B->launches++; }
 }
 
-// Which solver kernel the next step uses. k_solve5<P> needs every island to fit its shared-memory row budget; the largest
-// island of the previous call (hint_m) decides, so the first call after creation runs k_solve.
-static int choose_solver(const OdebBatch *B)
+// Row budget of k_solve5<2^k> for islands of up to `need` rows: 0 when it cannot be launched (bodies / rows beyond the packed
+// entry, or one warp's shared memory beyond an SM).
+static int solve5_budget(OdebBatch *B, int k, int need)
+{
+    B->s5_sr[k] = 0; B->s5_smem[k] = 0;
+    if (B->P.NB > ODEB5_MAXBODIES) return 0;
+    int sr = (need + 31) / 32 * 32;
+    if (sr > B->P.MR) sr = B->P.MR;
+    if (sr < need || sr > ODEB5_MAXROWS) return 0;
+    const size_t smem = odeb5_smem(1 << k, B->P.NB, sr);
+    if (smem > 226 * 1024) return 0;
+    B->s5_sr[k] = sr; B->s5_smem[k] = smem;
+    return sr;
+}
+
+// Which solver kernel the next step uses. The largest island of the previous call (hint_m) decides, so the first call after
+// creation runs k_solve.
+static int choose_solver(OdebBatch *B)
 {
     const int f = B->solver_force;
+    const int need = B->hint_m > 0 ? B->hint_m + B->hint_m / 8 + 8 : (B->P.MR < 512 ? B->P.MR : 512);
     if (f == 0) return 0;
     if (f == 4) return B->bl_G ? 4 : 0;
-    if (f >= 1 && f <= 3) return B->s5_sr[f] > 0 ? f : 0;
+    if (f >= 1 && f <= 3) return solve5_budget(B, f, need) > 0 ? f : 0;
     if (B->hint_m <= 0) return 0;
     // Measured on B200 (4096 x 16-box stacks, single; solver ms for W = 1024 / 2048 / 4096 worlds): k_solve 1.19 / 1.19 / 1.26,
     // k_solve5<4> 0.67 / 0.83 / 1.25, k_solve5<8> 0.78 / - / -, k_solve5<2> - / - / 1.39.  With more than ~3.5 warps per SM the
     // extra warps of the P-processor schedule contend for the SM's shared-memory pipe and the gain is gone, so P = 4 is used
-    // while the batch needs at most that many warps and every island fits its row budget.
+    // while the batch needs at most that many warps. It is also used whenever an island does not fit k_solve's own row budget
+    // (64-body piles: 45 ms per step through the serial fallback against 3 ms), in several waves if need be.
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, B->device);
     const long long warps4 = ((long long)B->P.W + 3) / 4;
-    const int need = B->hint_m + B->hint_m / 8 + 8;
-    if (warps4 * 2 <= 7LL * nsm && B->s5_sr[2] >= need) return 2;
+    if (warps4 * 2 <= 7LL * nsm || need > B->P.SR) { if (solve5_budget(B, 2, need) > 0) return 2; }
     return 0;
 }
 
@@ -742,7 +744,8 @@ int odeb_step_async(OdebBatch *B, double h, int nsteps)
     }
     const bool graph_ok = B->use_graph && !B->timing;
     const int cfg = choose_solver(B);
-    if (graph_ok && (B->graph == 0 || B->graph_h != h || B->graph_cfg != cfg)) {
+    const int cfg_sr = (cfg >= 1 && cfg <= 3) ? B->s5_sr[cfg] : 0;
+    if (graph_ok && (B->graph == 0 || B->graph_h != h || B->graph_cfg != cfg || B->graph_sr != cfg_sr)) {
         if (B->graph) { cudaGraphExecDestroy(B->graph); B->graph = 0; }
         cudaGraph_t g = 0;
         uint64_t l0 = B->launches;
@@ -752,7 +755,7 @@ int odeb_step_async(OdebBatch *B, double h, int nsteps)
         B->launches = l0;
         CK(cudaGraphInstantiate(&B->graph, g, 0));
         cudaGraphDestroy(g);
-        B->graph_h = h; B->graph_cfg = cfg;
+        B->graph_h = h; B->graph_cfg = cfg; B->graph_sr = cfg_sr;
     }
     for (int s = 0; s < nsteps; s++) {
         if (graph_ok) {
@@ -904,7 +907,7 @@ int odeb_restore(OdebBatch *B, const void *buf, size_t bytes)
 }
 
 uint64_t odeb_launch_count(const OdebBatch *B) { return B->launches; }
-const char *odeb_solver_kernel(const OdebBatch *B)
+const char *odeb_solver_kernel(OdebBatch *B)
 {
     static const char *names[5] = { "k_solve", "k_solve5<2>", "k_solve5<4>", "k_solve5<8>", "k_solve_bl" };
     if (B->mode == ODEB_MODE_CANONICAL) return "k_lw_sweep";

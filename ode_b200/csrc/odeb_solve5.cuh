@@ -17,7 +17,8 @@
 //     stages and an additional prefetch.global.L2 ODEB5_FAR slots ahead were measured and bring nothing for P = 4,
 //     profiles/r1_solver_variants.txt).  Idle slots carry the dummy body and have their copies and stores predicated off.
 // Lane layout: side = lane >> 4, column = lane & 15 = proc * WPW + world (WPW = 16 / P worlds per warp).
-// One order / meta entry: row (bits 0..9) | friction row (10..19) | body-1 slot (20..25) | body-2 slot (26..31).
+// One order / meta entry: row (bits 0..11) | row - friction-index row (12..14, 0 = none; the reference only ever points a
+// friction row at the normal row of its own contact, 1 or 2 rows back) | body-1 slot (15..22) | body-2 slot (23..30).
 #ifndef ODEB_SOLVE5_CUH
 #define ODEB_SOLVE5_CUH
 
@@ -28,11 +29,12 @@
 #define ODEB5_FAR 12                                       // L2 prefetch distance in slots
 #endif
 #define ODEB5_PAD (ODEB5_RING + ODEB5_FAR + 4)
-#define ODEB5_MAXBODIES 62
-#define E5_ROW(e) ((int)((e) & 0x3ffu))
-#define E5_FI(e) ((int)(((e) >> 10) & 0x3ffu))
-#define E5_B1(e) ((int)(((e) >> 20) & 63u))
-#define E5_B2(e) ((int)((e) >> 26))
+#define ODEB5_MAXBODIES 254                                // 8-bit body slots, the dummy slot NB included
+#define ODEB5_MAXROWS 4095                                 // 12-bit row index
+#define E5_ROW(e) ((int)((e) & 0xfffu))
+#define E5_FI(e) (E5_ROW(e) - (int)(((e) >> 12) & 7u))     // friction-index row = row - delta, delta 0 = none (fi == row)
+#define E5_B1(e) ((int)(((e) >> 15) & 0xffu))
+#define E5_B2(e) ((int)(((e) >> 23) & 0xffu))
 
 // shared memory per warp for a capacity of sr rows (= schedule slots) per island
 __host__ __device__ inline size_t odeb5_smem(int P, int NB, int sr)
@@ -148,7 +150,7 @@ __global__ void __launch_bounds__(32) k_solve5(const __grid_constant__ DevParams
     unsigned *meta = (unsigned *)p; p += (size_t)(SR5 + ODEB5_PAD) * 16 * sizeof(unsigned);     // meta[slot * 16 + col]
     unsigned *order = (unsigned *)p + wl; p += (size_t)SR5 * WPW * sizeof(unsigned);            // order[i * WPW]
     unsigned short *last = (unsigned short *)p + wl;                                            // last[body * WPW]
-    const unsigned IDLE = ((unsigned)NBd << 20) | ((unsigned)NBd << 26);
+    const unsigned IDLE = ((unsigned)NBd << 15) | ((unsigned)NBd << 23);
 
     unsigned seed = D.seed[w];
     unsigned st0 = 0, st1 = 0, st2 = 0, st3 = 0;
@@ -170,7 +172,21 @@ __global__ void __launch_bounds__(32) k_solve5(const __grid_constant__ DevParams
         int4 info = make_int4(0, 0, 0, 0);
         if (is < nis) { info = iinfo[is]; if (leader) st0++; }
         const int bstart = info.x, nb = info.y, rstart = info.z, m = info.w;
-        const bool big = m > SR5;
+        // islands beyond the row budget, or with a friction index the packed entry cannot hold, take the serial path
+        const int m_try = (m > 0 && m <= SR5) ? m : 0;
+        const int m_try_max = __reduce_max_sync(ODEB_FULL, m_try);
+        int nfree = 0;
+        unsigned badfi = 0;
+        for (int i0 = 0; i0 < m_try_max; i0 += 2 * P) {
+            const int i = i0 + wid;
+            int fi = -1;
+            if (i < m_try) fi = findex[rstart + i];
+            const bool fr = (i < m_try) && fi == -1;
+            const bool bad = (i < m_try) && fi != -1 && (unsigned)(i - (fi - rstart) - 1) > 6u;
+            nfree += __popc(__ballot_sync(ODEB_FULL, fr) & wmask);
+            badfi |= __ballot_sync(ODEB_FULL, bad) & wmask;
+        }
+        const bool big = m > SR5 || badfi != 0;
         if (big && leader) solve_island_serial(Pm, D, w, bstart, nb, rstart, m, seed, st1, st2, st3, sweeps, rowsweeps);
         __syncwarp();
         const int m_own = (m > 0 && !big) ? m : 0;
@@ -185,12 +201,6 @@ __global__ void __launch_bounds__(32) k_solve5(const __grid_constant__ DevParams
             if (wid < 2) CF5(Pm.NB, wid) = z4;
             for (int i = wid; i <= m_own; i += 2 * P) lam[i * WPW] = 0;
         }
-        int nfree = 0;
-        for (int i0 = 0; i0 < m_max; i0 += 2 * P) {
-            const int i = i0 + wid;
-            const bool fr = (i < m_own) && findex[rstart + i] == -1;
-            nfree += __popc(__ballot_sync(ODEB_FULL, fr) & wmask);
-        }
         {
             int head = 0, tail = nfree;
             for (int i0 = 0; i0 < m_max; i0 += 2 * P) {
@@ -200,7 +210,7 @@ __global__ void __launch_bounds__(32) k_solve5(const __grid_constant__ DevParams
                 if (in) { fi = findex[rstart + i]; rb = rbody[rstart + i]; }
                 const bool fr = in && fi == -1;
                 const unsigned bf = __ballot_sync(ODEB_FULL, fr) & wmask, bo = __ballot_sync(ODEB_FULL, in && !fr) & wmask;
-                const unsigned e = (unsigned)i | ((unsigned)(fi == -1 ? i : fi - rstart) << 10) | ((unsigned)rb.x << 20) | ((unsigned)rb.y << 26);
+                const unsigned e = (unsigned)i | ((unsigned)(fi == -1 ? 0 : i - (fi - rstart)) << 12) | ((unsigned)rb.x << 15) | ((unsigned)rb.y << 23);
                 if (fr) order[(head + __popc(bf & below)) * WPW] = e;
                 else if (in) order[(tail + __popc(bo & below)) * WPW] = e;
                 head += __popc(bf); tail += __popc(bo);

@@ -398,3 +398,32 @@ def test_hinge2_joints(prec, solver, monkeypatch):
         bad = compare_step(a, b, sc.nworlds, exact_float=False, tol=TOL[prec], what=("pairs", "islands", "state"))
         assert not bad, (solver, s, bad[:4])
     b.close()
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_solve5_many_bodies_and_rows(prec, monkeypatch):
+    """k_solve5's packed schedule entries (12-bit row, 8-bit body slots): a 70-box stack in ONE island (~850 rows, beyond k_solve's
+    own row budget -> the case the host switches kernels for) and 100 separate bodies per world, against the oracle, bit-exact."""
+    monkeypatch.setenv("ODEB_SOLVER", "p4")
+    for mk, h, n in ((lambda: scenes.box_stack(nworlds=3, nboxes=70, demo_world_options=False), 0.02, 40),
+                     (lambda: scenes.free_boxes(2, 100, grid=10), 0.01, 20)):
+        sc = mk()
+        a, b = B.Batch(orc_lib(prec), sc), B.Batch(gpu_lib(prec), sc)
+        rows = 0
+        for s in range(n):
+            a.step(h)
+            b.step(h)
+            bad = compare_step(a, b, sc.nworlds)
+            assert not bad, (sc.nbody, s, bad[:4])
+            rows = max(rows, int(b.get_totals()[2]) // sc.nworlds)
+        b.close()
+    monkeypatch.delenv("ODEB_SOLVER")
+    # automatic choice: islands beyond k_solve's budget make the host pick k_solve5<4> after the first call
+    sc = scenes.box_stack(nworlds=3, nboxes=70, demo_world_options=False)
+    a, b = B.Batch(orc_lib(prec), sc), B.Batch(gpu_lib(prec), sc)
+    for s in range(30):
+        a.step(0.02)
+        b.step(0.02)
+        bad = compare_step(a, b, sc.nworlds)
+        assert not bad, (s, bad[:4])
+    b.close()
