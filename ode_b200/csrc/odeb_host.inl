@@ -742,26 +742,41 @@ int odeb_step_async(OdebBatch *B, double h, int nsteps)
         for (int s = 0; s < nsteps; s++) if (!large_step(B)) return 0;
         return 1;
     }
-    const bool graph_ok = B->use_graph && !B->timing;
-    const int cfg = choose_solver(B);
-    const int cfg_sr = (cfg >= 1 && cfg <= 3) ? B->s5_sr[cfg] : 0;
-    if (graph_ok && (B->graph == 0 || B->graph_h != h || B->graph_cfg != cfg || B->graph_sr != cfg_sr)) {
-        if (B->graph) { cudaGraphExecDestroy(B->graph); B->graph = 0; }
-        cudaGraph_t g = 0;
-        uint64_t l0 = B->launches;
-        CK(cudaStreamBeginCapture(B->stream, cudaStreamCaptureModeThreadLocal));
-        launch_step(B, B->stream, false, cfg);
-        CK(cudaStreamEndCapture(B->stream, &g));
-        B->launches = l0;
-        CK(cudaGraphInstantiate(&B->graph, g, 0));
-        cudaGraphDestroy(g);
-        B->graph_h = h; B->graph_cfg = cfg; B->graph_sr = cfg_sr;
-    }
-    for (int s = 0; s < nsteps; s++) {
-        if (graph_ok) {
-            CK(cudaGraphLaunch(B->graph, B->stream));
-            B->launches += (B->P.NG > 0 ? 5 : 0) + (B->P.NJ > 0 ? 1 : 0) + 6 + (B->D.jcopy ? 1 : 0);
-        } else launch_step(B, B->stream, B->timing, cfg);
+    // The solver kernel (and k_solve5's row budget) follow the largest island seen: a fresh batch reads it back once after its
+    // first step, long calls re-read it every 64 steps, so that a many-step call does not stay on a kernel its islands outgrew.
+    int done = 0;
+    while (done < nsteps) {
+        const bool graph_ok = B->use_graph && !B->timing;
+        const int cfg = choose_solver(B);
+        const int cfg_sr = (cfg >= 1 && cfg <= 3) ? B->s5_sr[cfg] : 0;
+        if (graph_ok && (B->graph == 0 || B->graph_h != h || B->graph_cfg != cfg || B->graph_sr != cfg_sr)) {
+            if (B->graph) { cudaGraphExecDestroy(B->graph); B->graph = 0; }
+            cudaGraph_t g = 0;
+            uint64_t l0 = B->launches;
+            CK(cudaStreamBeginCapture(B->stream, cudaStreamCaptureModeThreadLocal));
+            launch_step(B, B->stream, false, cfg);
+            CK(cudaStreamEndCapture(B->stream, &g));
+            B->launches = l0;
+            CK(cudaGraphInstantiate(&B->graph, g, 0));
+            cudaGraphDestroy(g);
+            B->graph_h = h; B->graph_cfg = cfg; B->graph_sr = cfg_sr;
+        }
+        int chunk = nsteps - done;
+        const bool probe = B->solver_force < 0 && chunk > 1;          // nothing to adapt when a kernel is forced
+        if (probe) { const int lim = B->hint_m <= 0 ? 1 : 64; if (chunk > lim) chunk = lim; }
+        for (int s = 0; s < chunk; s++) {
+            if (graph_ok) {
+                CK(cudaGraphLaunch(B->graph, B->stream));
+                B->launches += (B->P.NG > 0 ? 5 : 0) + (B->P.NJ > 0 ? 1 : 0) + 6 + (B->D.jcopy ? 1 : 0);
+            } else launch_step(B, B->stream, B->timing, cfg);
+        }
+        done += chunk;
+        if (probe && done < nsteps) {
+            int m = 0;
+            CK(cudaMemcpyAsync(&m, B->D.overflow + 1, sizeof(int), cudaMemcpyDeviceToHost, B->stream));
+            CK(cudaStreamSynchronize(B->stream));
+            if (m > B->hint_m) B->hint_m = m;
+        }
     }
     CK(cudaGetLastError());
     return 1;
