@@ -49,8 +49,8 @@ enum {
     ODEB_CONTACT_MU2 = 0x001, ODEB_CONTACT_FDIR1 = 0x002, ODEB_CONTACT_BOUNCE = 0x004,
     ODEB_CONTACT_SOFT_ERP = 0x008, ODEB_CONTACT_SOFT_CFM = 0x010, ODEB_CONTACT_MOTION1 = 0x020,
     ODEB_CONTACT_MOTION2 = 0x040, ODEB_CONTACT_MOTIONN = 0x080, ODEB_CONTACT_SLIP1 = 0x100,
-    ODEB_CONTACT_SLIP2 = 0x200, ODEB_CONTACT_APPROX1_1 = 0x1000, ODEB_CONTACT_APPROX1_2 = 0x2000,
-    ODEB_CONTACT_APPROX1 = 0x7000
+    ODEB_CONTACT_SLIP2 = 0x200, ODEB_CONTACT_ROLLING = 0x400, ODEB_CONTACT_APPROX1_1 = 0x1000, ODEB_CONTACT_APPROX1_2 = 0x2000,
+    ODEB_CONTACT_APPROX1_N = 0x4000, ODEB_CONTACT_APPROX1 = 0x7000
 };
 
 /* body flag bits a scene may set (ode/src/objects.h:72-87 keeps these internal; meaning identical) */
@@ -89,6 +89,7 @@ typedef struct OdebWorldParams {
     int    surf_mode;           /* dSurfaceParameters.mode */
     double mu, mu2, bounce, bounce_vel, soft_erp, soft_cfm;
     double motion1, motion2, motionN, slip1, slip2;
+    double rho, rho2, rhoN;     /* rolling / spinning friction, used with ODEB_CONTACT_ROLLING (contact.h:64-66) */
 } OdebWorldParams;
 
 typedef struct OdebBodyDesc {

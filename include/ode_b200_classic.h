@@ -18,7 +18,7 @@
  * stages: without a CUDA device dWorldQuickStep returns 0 and dSpaceCollide reports through the error handler.
  *
  * Outside the subset (calls are not exported): dWorldStep, joints other than contact/ball/hinge/slider/universal/hinge2/fixed, geoms other
- * than sphere/box/capsule/plane, geom offsets, nested spaces, rolling friction, per-body
+ * than sphere/box/capsule/plane, geom offsets, nested spaces, per-body
  * auto-disable thresholds (the world's are used), SAP axis orders other than dSAP_AXES_XYZ.
  */
 #ifndef ODE_B200_CLASSIC_H

@@ -27,6 +27,7 @@ class OdebWorldParams(C.Structure):
         ("soft_erp", C.c_double), ("soft_cfm", C.c_double),
         ("motion1", C.c_double), ("motion2", C.c_double), ("motionN", C.c_double),
         ("slip1", C.c_double), ("slip2", C.c_double),
+        ("rho", C.c_double), ("rho2", C.c_double), ("rhoN", C.c_double),
     ]
 
 
@@ -58,7 +59,7 @@ JOINT_BALL, JOINT_HINGE, JOINT_SLIDER, JOINT_CONTACT, JOINT_UNIVERSAL, JOINT_HIN
 SPACE_HASH, SPACE_SAP = 0, 1
 CONTACT_MU2, CONTACT_BOUNCE, CONTACT_SOFT_ERP, CONTACT_SOFT_CFM = 0x001, 0x004, 0x008, 0x010
 CONTACT_MOTION1, CONTACT_MOTION2, CONTACT_MOTIONN = 0x020, 0x040, 0x080
-CONTACT_SLIP1, CONTACT_SLIP2, CONTACT_APPROX1 = 0x100, 0x200, 0x7000
+CONTACT_SLIP1, CONTACT_SLIP2, CONTACT_ROLLING, CONTACT_APPROX1 = 0x100, 0x200, 0x400, 0x7000
 BODY_NO_GRAVITY, BODY_NO_GYRO, BODY_DISABLED, BODY_FINITE_ROTATION = 1, 2, 4, 8
 INF = float("inf")
 

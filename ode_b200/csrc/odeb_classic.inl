@@ -1179,16 +1179,14 @@ static void surface_to_device(const dContact &ct, DSurface &S)
 {   // dxJointContact::getInfo1 contact.cpp:48-122 (row count, negative mu clamped to 0)
     const dSurfaceParameters &p = ct.surface;
     memset(&S, 0, sizeof(S));
-    S.mode = p.mode & ~dContactRolling;
+    S.mode = p.mode;
     S.mu = p.mu < 0 ? 0 : p.mu;
     S.mu2 = p.mu2 < 0 ? 0 : p.mu2;
     S.bounce = p.bounce; S.bounce_vel = p.bounce_vel; S.soft_erp = p.soft_erp; S.soft_cfm = p.soft_cfm;
     S.motion1 = p.motion1; S.motion2 = p.motion2; S.motionN = p.motionN; S.slip1 = p.slip1; S.slip2 = p.slip2;
     S.fdir1[0] = ct.fdir1[0]; S.fdir1[1] = ct.fdir1[1]; S.fdir1[2] = ct.fdir1[2];
-    int m = 1;
-    if (S.mode & dContactMu2) { if (S.mu > 0) m++; if (S.mu2 > 0) m++; }
-    else if (S.mu > 0) m += 2;
-    S.the_m = m;
+    S.the_m = odeb_contact_rows(S.mode, S.mu, S.mu2, p.rho, p.rho2, p.rhoN);
+    S.rho = p.rho < 0 ? 0 : p.rho; S.rho2 = p.rho2 < 0 ? 0 : p.rho2; S.rhoN = p.rhoN < 0 ? 0 : p.rhoN;
 }
 
 int dWorldQuickStep(dWorldID w, Real stepsize)

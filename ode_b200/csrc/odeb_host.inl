@@ -225,10 +225,9 @@ static void apply_world_params(DevParams &P, const OdebWorldParams *wp, bool cla
     S.bounce = (Real)wp->bounce; S.bounce_vel = (Real)wp->bounce_vel; S.soft_erp = (Real)wp->soft_erp; S.soft_cfm = (Real)wp->soft_cfm;
     S.motion1 = (Real)wp->motion1; S.motion2 = (Real)wp->motion2; S.motionN = (Real)wp->motionN; S.slip1 = (Real)wp->slip1; S.slip2 = (Real)wp->slip2;
     {   // getInfo1 row count of a contact joint (contact.cpp:48-122); uniform under one policy, per contact in classic mode
-        int m = 1;
-        if (S.mode & ODEB_CONTACT_MU2) { if (S.mu > 0) m++; if (S.mu2 > 0) m++; }
-        else if (S.mu > 0) m += 2;
-        S.the_m = m; P.m_contact = classic ? 3 : m;
+        const int m = odeb_contact_rows(S.mode, S.mu, S.mu2, (Real)wp->rho, (Real)wp->rho2, (Real)wp->rhoN);
+        S.rho = (Real)wp->rho < 0 ? 0 : (Real)wp->rho; S.rho2 = (Real)wp->rho2 < 0 ? 0 : (Real)wp->rho2; S.rhoN = (Real)wp->rhoN < 0 ? 0 : (Real)wp->rhoN;
+        S.the_m = m; P.m_contact = classic ? 6 : m;
     }
     for (int k = 0; k < 3; k++) P.gravity[k] = (Real)wp->gravity[k];
     P.erp = (Real)wp->erp;
@@ -295,7 +294,7 @@ static OdebBatch *batch_build(const OdebWorldParams *wp, const HostTemplate &T, 
     const int nbody = (int)T.bmass.size(), ngeom = (int)T.gtype.size(), njoint = (int)T.jt.size();
     const bool classic = caps && caps->classic;
     if (nworlds <= 0 || nbody <= 0) { set_err("bad sizes"); return 0; }
-    if (!classic && (wp->surf_mode & (ODEB_CONTACT_FDIR1 | 0x400))) { set_err("contact modes FDir1 / Rolling are outside the supported policy"); return 0; }
+    if (!classic && (wp->surf_mode & ODEB_CONTACT_FDIR1)) { set_err("contact mode FDir1 needs a per-contact direction: use the classic API"); return 0; }
     if (wp->max_contacts < 1 || wp->max_contacts > 8) { set_err("max_contacts must be in 1..8"); return 0; }
 
     OdebBatch *B = new OdebBatch();

@@ -443,10 +443,28 @@ __device__ void odeb_joint_info2(const DJointT &j, const DLimitState &ls, const 
 struct DSurface {
     int mode, the_m;
     Real mu, mu2, bounce, bounce_vel, soft_erp, soft_cfm, motion1, motion2, motionN, slip1, slip2;
+    Real rho, rho2, rhoN;   // rolling / spinning friction (dContactRolling), clamped to >= 0 like getInfo1 does
     Real fdir1[3];          // dContact.fdir1, used when mode has dContactFDir1 (classic per-object API only)
 };
 
-// dxJointContact::getInfo2 joints/contact.cpp:125-347 (no rolling friction)
+// dxJointContact::getInfo1 row count (contact.cpp:48-122). Note the reference's asymmetry: a rolling coefficient of exactly 0
+// still counts a row here, while getInfo2 (:299-343) fills rows only for rho > 0; the counted row then stays at its initial
+// values (J = 0, world CFM, lo/hi = -+inf).
+__host__ __device__ inline int odeb_contact_rows(int mode, Real mu, Real mu2, Real rho, Real rho2, Real rhoN)
+{
+    int m = 1;
+    if (mode & 0x001) {
+        if (mu > 0) m++;
+        if (mu2 > 0) m++;
+        if (mode & 0x400) { if (!(rho < 0)) m++; if (!(rho2 < 0)) m++; if (!(rhoN < 0)) m++; }
+    } else {
+        if (mu > 0) m += 2;
+        if ((mode & 0x400) && !(rho < 0)) m += 3;
+    }
+    return m;
+}
+
+// dxJointContact::getInfo2 joints/contact.cpp:125-347
 __device__ void odeb_contact_info2(const DSurface &s, const Real *cpos, const Real *cnormal, Real cdepth, int reverse,
                                    const DBody &b0, const DBody *b1, Real fps, Real worldERP, Real min_depth, Real maxvel,
                                    Real *row, int *findex)
@@ -512,6 +530,21 @@ __device__ void odeb_contact_info2(const DSurface &s, const Real *cpos, const Re
             q[C_LO] = -mu2; q[C_HI] = mu2;
             if (mode & 0x2000) findex[r] = 0;
             r++;
+        }
+        if (mode & 0x400) {   // rolling about t1, t2 and spinning about the normal (contact.cpp:299-343)
+            const Real *ax[3] = { t1, t2, normal };
+            const int approx_bits[3] = { 0x1000, 0x2000, 0x4000 };
+            const Real rho[3] = { s.rho, (mode & 0x001) ? s.rho2 : s.rho, (mode & 0x001) ? s.rhoN : s.rho };
+            for (int i = 0; i < 3; i++) {
+                if (rho[i] > 0) {
+                    Real *q = row + r * ROWLEN;
+                    q[C_J1A] = ax[i][0]; q[C_J1A + 1] = ax[i][1]; q[C_J1A + 2] = ax[i][2];
+                    if (b1) { q[C_J2A] = -ax[i][0]; q[C_J2A + 1] = -ax[i][1]; q[C_J2A + 2] = -ax[i][2]; }
+                    q[C_LO] = -rho[i]; q[C_HI] = rho[i];
+                    if (mode & approx_bits[i]) findex[r] = 0;
+                    r++;
+                }
+            }
         }
     }
 }

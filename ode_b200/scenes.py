@@ -202,6 +202,39 @@ def buggy(nworlds=1, seed0=51, stops=False):
     return sc
 
 
+def rolling(nworlds=1, seed0=61, axis_dep=False):
+    """Rolling / spinning friction (dContactRolling, contact.cpp:73-116, :299-343): spheres and a box sliding, rolling and spinning
+    on a plane and against each other. axis_dep=False: one rho for all three axes, Approx1 (limits proportional to the normal force);
+    axis_dep=True: dContactAxisDep (= Mu2) with rho, rho2 = 0 (the reference counts a row for it and leaves it empty) and rhoN."""
+    if axis_dep:
+        mode = B.CONTACT_ROLLING | B.CONTACT_MU2
+        wp = B.default_world_params(gravity=(0, 0, -9.81), max_contacts=4, surf_mode=mode, mu=0.8, mu2=0.4, rho=0.02, rho2=0.0, rhoN=0.1)
+    else:
+        mode = B.CONTACT_ROLLING | B.CONTACT_APPROX1
+        wp = B.default_world_params(gravity=(0, 0, -9.81), max_contacts=4, surf_mode=mode, mu=1.0, rho=0.05)
+    sc = B.Scene(wp, nworlds)
+    sc.add_geom(B.PLANE, (0, 0, 1, 0))
+    for k in range(5):
+        ms, Is = B.sphere_mass(1.0, 0.2)
+        b = sc.add_body(ms, Is, (0.45 * k, 0.05 * k, 0.2))
+        sc.add_geom(B.SPHERE, (0.2,), body=b)
+    m, I = B.box_mass(1.0, 0.4, 0.4, 0.2)
+    b = sc.add_body(m, I, (0.9, 1.0, 0.1))
+    sc.add_geom(B.BOX, (0.4, 0.4, 0.2), body=b)
+    nb = sc.nbody
+    pos = np.tile(np.asarray(sc.body_pos)[None], (nworlds, 1, 1))
+    quat = np.tile(np.array([1.0, 0, 0, 0])[None, None], (nworlds, nb, 1))
+    lvel = np.zeros((nworlds, nb, 3))
+    avel = np.zeros((nworlds, nb, 3))
+    for w in range(nworlds):
+        r = _rng(seed0 + w)
+        lvel[w, :, :2] = 1.5 * (r.rand(nb, 2) - 0.5)
+        avel[w] = 6.0 * (r.rand(nb, 3) - 0.5)
+    sc.state = dict(pos=pos, quat=quat, lvel=lvel, avel=avel)
+    sc.seeds = (seed0 + np.arange(nworlds)).astype(np.uint32)
+    return sc
+
+
 def free_boxes(nworlds=1, nboxes=64, seed0=5, grid=8, spacing=1.5):
     """nboxes separate unit boxes resting/falling on the plane: many one-body islands per world
     (the scattered 64-body world of SURVEY.md 7.2(4))."""

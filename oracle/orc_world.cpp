@@ -451,8 +451,16 @@ void contact_info1(const Batch &B, Joint &j)
         if (mu > 0) { if (mu == R_INF) nub++; m++; }
         Real mu2 = (Real)B.wp.mu2;
         if (mu2 > 0) { if (mu2 == R_INF) nub++; m++; }
+        if (B.wp.surf_mode & ODEB_CONTACT_ROLLING) {          // contact.cpp:73-98: rho == 0 still counts a row
+            const Real r[3] = { (Real)B.wp.rho, (Real)B.wp.rho2, (Real)B.wp.rhoN };
+            for (int i = 0; i < 3; i++) if (!(r[i] < 0)) { if (r[i] == R_INF) nub++; m++; }
+        }
     } else {
         if (mu > 0) { if (mu == R_INF) nub += 2; m += 2; }
+        if (B.wp.surf_mode & ODEB_CONTACT_ROLLING) {          // contact.cpp:108-116
+            const Real r = (Real)B.wp.rho;
+            if (!(r < 0)) { if (r == R_INF) nub += 3; m += 3; }
+        }
     }
     j.the_m = m; j.m = m; j.nub = nub;
 }
@@ -528,6 +536,24 @@ void contact_info2(const Batch &B, World &W, Joint &j, Real fps, Real worldERP, 
             q[LO] = -mu2; q[HI] = mu2;
             if (mode & ODEB_CONTACT_APPROX1_2) findex[r] = 0;
             r++;
+        }
+        if (mode & ODEB_CONTACT_ROLLING) {   // contact.cpp:299-343
+            const Real *ax[3] = { t1, t2, normal };
+            const int approx_bits[3] = { ODEB_CONTACT_APPROX1_1, ODEB_CONTACT_APPROX1_2, ODEB_CONTACT_APPROX1_N };
+            Real rho[3];
+            rho[0] = (Real)p.rho < 0 ? 0 : (Real)p.rho;
+            if (mode & ODEB_CONTACT_MU2) { rho[1] = (Real)p.rho2 < 0 ? 0 : (Real)p.rho2; rho[2] = (Real)p.rhoN < 0 ? 0 : (Real)p.rhoN; }
+            else { rho[1] = rho[0]; rho[2] = rho[0]; }
+            for (int i = 0; i < 3; i++) {
+                if (rho[i] > 0) {
+                    Real *q = row + r * ROW;
+                    q[J1A] = ax[i][0]; q[J1A + 1] = ax[i][1]; q[J1A + 2] = ax[i][2];
+                    if (j.b1 >= 0) { q[J2A] = -ax[i][0]; q[J2A + 1] = -ax[i][1]; q[J2A + 2] = -ax[i][2]; }
+                    q[LO] = -rho[i]; q[HI] = rho[i];
+                    if (mode & approx_bits[i]) findex[r] = 0;
+                    r++;
+                }
+            }
         }
     }
 }
@@ -881,7 +907,7 @@ extern "C" {
 void *orc_create(const OdebWorldParams *wp, int nbody, const OdebBodyDesc *bodies, const double *body_pos, const double *body_quat,
                  int ngeom, const OdebGeomDesc *geoms, int njoint, const OdebJointDesc *joints, int nworlds, int /*device*/)
 {
-    if (wp->surf_mode & (ODEB_CONTACT_FDIR1 | 0x400)) return 0;
+    if (wp->surf_mode & ODEB_CONTACT_FDIR1) return 0;
     Batch *B = new Batch;
     B->wp = *wp; B->nbody = nbody; B->ngeom = ngeom; B->njoint = njoint; B->canonical = 0; B->feedback = 0;
     for (int k = 0; k < 3; k++) B->gravity[k] = (Real)wp->gravity[k];

@@ -311,6 +311,7 @@ static void ref_collide_world(RefBatch *B, RefWorld &W)
             s.soft_erp = (dReal)p.soft_erp; s.soft_cfm = (dReal)p.soft_cfm;
             s.motion1 = (dReal)p.motion1; s.motion2 = (dReal)p.motion2; s.motionN = (dReal)p.motionN;
             s.slip1 = (dReal)p.slip1; s.slip2 = (dReal)p.slip2;
+            s.rho = (dReal)p.rho; s.rho2 = (dReal)p.rho2; s.rhoN = (dReal)p.rhoN;
             dJointID c = dJointCreateContact(W.world, W.group, &contact[i]);
             dJointAttach(c, b1, b2);
             W.cjoints.push_back(c);
@@ -398,6 +399,7 @@ static void near_cb_direct(void *data, dGeomID o1, dGeomID o2)
         s.soft_erp = (dReal)p.soft_erp; s.soft_cfm = (dReal)p.soft_cfm;
         s.motion1 = (dReal)p.motion1; s.motion2 = (dReal)p.motion2; s.motionN = (dReal)p.motionN;
         s.slip1 = (dReal)p.slip1; s.slip2 = (dReal)p.slip2;
+        s.rho = (dReal)p.rho; s.rho2 = (dReal)p.rho2; s.rhoN = (dReal)p.rhoN;
         dJointID cj = dJointCreateContact(W.world, W.group, &contact[i]);
         dJointAttach(cj, b1, b2);
     }

@@ -427,3 +427,22 @@ def test_solve5_many_bodies_and_rows(prec, monkeypatch):
         bad = compare_step(a, b, sc.nworlds)
         assert not bad, (s, bad[:4])
     b.close()
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("solver", ("v4", "p4"))
+def test_rolling_friction(prec, solver, monkeypatch):
+    """Rolling / spinning friction rows (contact.cpp:299-343, up to 6 rows per contact, friction index up to 5 rows back) on the GPU.
+    Sphere contacts are libm-free: bit-exact; the box in the scene goes through cullPoints (atan2), so the comparison is teacher-forced
+    with the stated tolerance and exact integer observables."""
+    monkeypatch.setenv("ODEB_SOLVER", solver)
+    for axis_dep in (False, True):
+        sc = scenes.rolling(5, axis_dep=axis_dep)
+        a, b = B.Batch(orc_lib(prec), sc), B.Batch(gpu_lib(prec), sc)
+        for s in range(120):
+            b.set_state(**a.get_state())
+            a.step(0.01)
+            b.step(0.01)
+            bad = compare_step(a, b, sc.nworlds, exact_float=False, tol=TOL[prec], what=("pairs", "contacts", "islands", "stats", "seeds", "state"))
+            assert not bad, (solver, axis_dep, s, bad[:4])
+        b.close()

@@ -226,3 +226,24 @@ def test_hinge2_joints_vs_reference(prec):
             assert not bad, (stops, s, bad[:4])
         st = b.get_state()
         assert np.isfinite(st["pos"]).all() and np.abs(st["pos"][:, 0, :2]).max() > 0.05      # the buggy drove somewhere
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_rolling_friction_vs_reference(prec):
+    """dContactRolling (rolling about t1 / t2, spinning about the normal; proportional limits with Approx1; the AxisDep form with a
+    zero coefficient, which the reference counts as a row and leaves empty): restatement against the compiled reference."""
+    ref = ref_lib(prec)
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    for axis_dep in (False, True):
+        sc = scenes.rolling(3, axis_dep=axis_dep)
+        a, b = B.Batch(ref, sc), B.Batch(orc_lib(prec), sc)
+        a.enable_feedback()
+        b.enable_feedback()
+        for s in range(150):
+            a.step(0.01)
+            b.step(0.01)
+            bad = compare_step(a, b, sc.nworlds, exact_float=(prec == "double" or True)) + compare_feedback(a, b, sc.nworlds, True, 0)
+            assert not bad, (axis_dep, s, bad[:4])
+        st = b.get_state()
+        assert np.abs(st["avel"]).max() < 6.0          # rolling / spinning friction slowed the bodies down
