@@ -56,7 +56,8 @@ enum {
 /* body flag bits a scene may set (ode/src/objects.h:72-87 keeps these internal; meaning identical) */
 enum {
     ODEB_BODY_NO_GRAVITY = 1, ODEB_BODY_NO_GYRO = 2, ODEB_BODY_DISABLED = 4,
-    ODEB_BODY_FINITE_ROTATION = 8
+    ODEB_BODY_FINITE_ROTATION = 8,
+    ODEB_BODY_KINEMATIC = 16    /* dBodySetKinematic (ode.cpp:837-842): inverse mass and inverse inertia are zero */
 };
 
 /* World-level parameters (dWorldSet*; defaults ode/src/objects.cpp:37-121) + the contact policy. */

@@ -218,6 +218,9 @@ const dReal *dBodyGetLinearVel(dBodyID);
 const dReal *dBodyGetAngularVel(dBodyID);
 void dBodySetMass(dBodyID, const dMass *mass);
 void dBodyGetMass(dBodyID, dMass *mass);
+void dBodySetKinematic(dBodyID);
+void dBodySetDynamic(dBodyID);
+int dBodyIsKinematic(dBodyID);
 void dBodyAddForce(dBodyID, dReal fx, dReal fy, dReal fz);
 void dBodyAddTorque(dBodyID, dReal fx, dReal fy, dReal fz);
 const dReal *dBodyGetForce(dBodyID);

@@ -60,7 +60,7 @@ SPACE_HASH, SPACE_SAP = 0, 1
 CONTACT_MU2, CONTACT_BOUNCE, CONTACT_SOFT_ERP, CONTACT_SOFT_CFM = 0x001, 0x004, 0x008, 0x010
 CONTACT_MOTION1, CONTACT_MOTION2, CONTACT_MOTIONN = 0x020, 0x040, 0x080
 CONTACT_SLIP1, CONTACT_SLIP2, CONTACT_ROLLING, CONTACT_APPROX1 = 0x100, 0x200, 0x400, 0x7000
-BODY_NO_GRAVITY, BODY_NO_GYRO, BODY_DISABLED, BODY_FINITE_ROTATION = 1, 2, 4, 8
+BODY_NO_GRAVITY, BODY_NO_GYRO, BODY_DISABLED, BODY_FINITE_ROTATION, BODY_KINEMATIC = 1, 2, 4, 8, 16
 INF = float("inf")
 
 

@@ -720,6 +720,13 @@ void dBodySetMass(dBodyID b, const dMass *mass)
     b->world->topo_dirty = true;
 }
 void dBodyGetMass(dBodyID b, dMass *mass) { *mass = b->mass; }
+void dBodySetKinematic(dBodyID b)
+{   // ode.cpp:837-842
+    memset(b->invI, 0, sizeof(b->invI)); b->invMass = 0;
+    b->world->topo_dirty = true;
+}
+void dBodySetDynamic(dBodyID b) { dBodySetMass(b, &b->mass); }      // ode.cpp:830-835
+int dBodyIsKinematic(dBodyID b) { return b->invMass == 0; }
 void dBodyAddForce(dBodyID b, Real fx, Real fy, Real fz) { b->facc[0] += fx; b->facc[1] += fy; b->facc[2] += fz; }
 void dBodyAddTorque(dBodyID b, Real fx, Real fy, Real fz) { b->tacc[0] += fx; b->tacc[1] += fy; b->tacc[2] += fz; }
 const odeb_real *dBodyGetForce(dBodyID b) { return b->facc; }

@@ -475,6 +475,7 @@ OdebBatch *odeb_create(const OdebWorldParams *wp,
         Ib[1] = (Real)I[1]; Ib[2] = (Real)I[2]; Ib[6] = (Real)I[5];
         Ib[4] = (Real)I[1]; Ib[8] = (Real)I[2]; Ib[9] = (Real)I[5];
         if (!host_invert_pd3(Ib, &T.binvI[12 * i])) { Real *v = &T.binvI[12 * i]; memset(v, 0, 12 * sizeof(Real)); v[0] = v[5] = v[10] = 1; }
+        if (bodies[i].flags & ODEB_BODY_KINEMATIC) { memset(&T.binvI[12 * i], 0, 12 * sizeof(Real)); T.binvmass[i] = 0; }     // dBodySetKinematic ode.cpp:837-842
         HostBody &h = hb[i];
         for (int k = 0; k < 3; k++) h.pos[k] = (Real)body_pos[3 * i + k];
         for (int k = 0; k < 4; k++) h.q[k] = (Real)body_quat[4 * i + k];

@@ -235,6 +235,33 @@ def rolling(nworlds=1, seed0=61, axis_dep=False):
     return sc
 
 
+def conveyor(nworlds=1, seed0=71):
+    """Kinematic bodies (dBodySetKinematic, ode.cpp:837-842): a platform that moves and turns at constant velocity whatever rests on
+    it, carrying three boxes by friction above a ground plane."""
+    sc = B.Scene(B.default_world_params(gravity=(0, 0, -9.81), max_contacts=4, surf_mode=B.CONTACT_APPROX1, mu=1.0), nworlds)
+    sc.add_geom(B.PLANE, (0, 0, 1, 0))
+    m, I = B.box_mass(1.0, 2.0, 1.0, 0.1)
+    plat = sc.add_body(m, I, (0, 0, 0.5), flags=B.BODY_KINEMATIC)
+    sc.add_geom(B.BOX, (2.0, 1.0, 0.1), body=plat)
+    mb, Ib = B.box_mass(2.0, 0.3, 0.3, 0.3)
+    for k in range(3):
+        b = sc.add_body(mb, Ib, (-0.6 + 0.6 * k, 0.1 * k, 0.5 + 0.05 + 0.15 + 0.002))
+        sc.add_geom(B.BOX, (0.3, 0.3, 0.3), body=b)
+    nb = sc.nbody
+    pos = np.tile(np.asarray(sc.body_pos)[None], (nworlds, 1, 1))
+    quat = np.tile(np.array([1.0, 0, 0, 0])[None, None], (nworlds, nb, 1))
+    lvel = np.zeros((nworlds, nb, 3))
+    avel = np.zeros((nworlds, nb, 3))
+    for w in range(nworlds):
+        r = _rng(seed0 + w)
+        lvel[w, 0] = (0.3 + 0.1 * r.rand(), 0.0, 0.0)
+        avel[w, 0] = (0.0, 0.0, 0.2)
+        lvel[w, 3] = (0.3, 0.0, 0.0)
+    sc.state = dict(pos=pos, quat=quat, lvel=lvel, avel=avel)
+    sc.seeds = (seed0 + np.arange(nworlds)).astype(np.uint32)
+    return sc
+
+
 def free_boxes(nworlds=1, nboxes=64, seed0=5, grid=8, spacing=1.5):
     """nboxes separate unit boxes resting/falling on the plane: many one-body islands per world
     (the scattered 64-body world of SURVEY.md 7.2(4))."""

@@ -946,6 +946,7 @@ void *orc_create(const OdebWorldParams *wp, int nbody, const OdebBodyDesc *bodie
             b.I[4] = (Real)I[1]; b.I[8] = (Real)I[2]; b.I[9] = (Real)I[5];
             if (!invert_pd3(b.I, b.invI)) memcpy(b.invI, g_identity, sizeof(g_identity));
             b.invMass = rrecip(b.mass);
+            if (bodies[i].flags & ODEB_BODY_KINEMATIC) { memset(b.invI, 0, sizeof(b.invI)); b.invMass = 0; }     // dBodySetKinematic ode.cpp:837-842
             b.pos[0] = (Real)body_pos[3 * i]; b.pos[1] = (Real)body_pos[3 * i + 1]; b.pos[2] = (Real)body_pos[3 * i + 2];
             Real q[4] = { (Real)body_quat[4 * i], (Real)body_quat[4 * i + 1], (Real)body_quat[4 * i + 2], (Real)body_quat[4 * i + 3] };
             body_set_quat(b, q);

@@ -153,6 +153,7 @@ void *ref_create(const OdebWorldParams *wp,
             if (fl & ODEB_BODY_NO_GYRO) dBodySetGyroscopicMode(b, 0);
             if (fl & ODEB_BODY_FINITE_ROTATION) dBodySetFiniteRotationMode(b, 1);
             if (fl & ODEB_BODY_DISABLED) dBodyDisable(b);
+            if (fl & ODEB_BODY_KINEMATIC) dBodySetKinematic(b);
             W.bodies.push_back(b);
         }
         for (int i = 0; i < ngeom; i++) {

@@ -446,3 +446,17 @@ def test_rolling_friction(prec, solver, monkeypatch):
             bad = compare_step(a, b, sc.nworlds, exact_float=False, tol=TOL[prec], what=("pairs", "contacts", "islands", "stats", "seeds", "state"))
             assert not bad, (solver, axis_dep, s, bad[:4])
         b.close()
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_kinematic_bodies(prec):
+    """Kinematic platform carrying boxes (box-box contacts go through cullPoints / atan2: teacher-forced, stated tolerance)."""
+    sc = scenes.conveyor(5)
+    a, b = B.Batch(orc_lib(prec), sc), B.Batch(gpu_lib(prec), sc)
+    for s in range(120):
+        b.set_state(**a.get_state())
+        a.step(0.01)
+        b.step(0.01)
+        bad = compare_step(a, b, sc.nworlds, exact_float=False, tol=TOL[prec], what=("pairs", "contacts", "islands", "stats", "seeds", "state"))
+        assert not bad, (s, bad[:4])
+    b.close()

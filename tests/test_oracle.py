@@ -247,3 +247,22 @@ def test_rolling_friction_vs_reference(prec):
             assert not bad, (axis_dep, s, bad[:4])
         st = b.get_state()
         assert np.abs(st["avel"]).max() < 6.0          # rolling / spinning friction slowed the bodies down
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_kinematic_bodies_vs_reference(prec):
+    """dBodySetKinematic: zero inverse mass / inertia, the body keeps its velocity under contact forces and gravity."""
+    ref = ref_lib(prec)
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    sc = scenes.conveyor(2)
+    a, b = B.Batch(ref, sc), B.Batch(orc_lib(prec), sc)
+    v0 = b.get_state()["lvel"][:, 0].copy()
+    for s in range(150):
+        a.step(0.01)
+        b.step(0.01)
+        bad = compare_step(a, b, sc.nworlds)
+        assert not bad, (s, bad[:4])
+    st = b.get_state()
+    assert np.array_equal(st["lvel"][:, 0], v0) and abs(st["pos"][0, 0, 2] - 0.5) < 1e-6      # the platform did not react
+    assert st["pos"][0, 1, 0] > -0.6 + 0.2                                                    # and carried its load along
