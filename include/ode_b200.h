@@ -41,8 +41,11 @@ typedef float odeb_real;
 enum { ODEB_SPHERE = 0, ODEB_BOX = 1, ODEB_CAPSULE = 2, ODEB_PLANE = 4 };
 /* joint types: numbering of the reference dJointType (include/ode/common.h:406-426) */
 enum { ODEB_JOINT_BALL = 1, ODEB_JOINT_HINGE = 2, ODEB_JOINT_SLIDER = 3, ODEB_JOINT_CONTACT = 4, ODEB_JOINT_UNIVERSAL = 5, ODEB_JOINT_HINGE2 = 6, ODEB_JOINT_FIXED = 7 };
-/* broadphase flavours: which reference space's callback stream is reproduced (as a set) */
-enum { ODEB_SPACE_HASH = 0, ODEB_SPACE_SAP = 1 };
+/* broadphase flavours: which reference space's callback stream is reproduced (as a set).
+ * HASH: dxHashSpace::collide collision_space.cpp:421-614 -- AABB-overlapping pairs that the cell walk brings together (a pair whose
+ *       shared cells are all reached through differently wrapped hash addresses is not reported, see DESIGN.md "hash space");
+ * SAP:  dxSAPSpace::collide collision_sapspace.cpp:428-496;  SIMPLE: dxSimpleSpace::collide collision_space.cpp:245-267, every AABB-overlapping pair. */
+enum { ODEB_SPACE_HASH = 0, ODEB_SPACE_SAP = 1, ODEB_SPACE_SIMPLE = 2 };
 
 /* contact surface mode bits: include/ode/contact.h:34-52 */
 enum {
@@ -91,6 +94,8 @@ typedef struct OdebWorldParams {
     double mu, mu2, bounce, bounce_vel, soft_erp, soft_cfm;
     double motion1, motion2, motionN, slip1, slip2;
     double rho, rho2, rhoN;     /* rolling / spinning friction, used with ODEB_CONTACT_ROLLING (contact.h:64-66) */
+    int    hash_levels_set;     /* 0: the hash space's default levels -3..10 (collision_space.cpp:387-388); 1: dHashSpaceSetLevels values below */
+    int    hash_minlevel, hash_maxlevel;
 } OdebWorldParams;
 
 typedef struct OdebBodyDesc {
@@ -105,6 +110,9 @@ typedef struct OdebGeomDesc {
     int    body;                /* body index in the world, -1 = static (dGeomSetBody not called) */
     double p[4];
     uint32_t category_bits, collide_bits; /* dGeomSetCategoryBits / dGeomSetCollideBits */
+    int    has_offset;          /* dGeomSetOffsetPosition / dGeomSetOffsetQuaternion (collision_kernel.cpp:455-466): pose of the geom */
+    double offset_pos[3];       /*   relative to its body; composite bodies. Ignored for geoms without a body.                      */
+    double offset_quat[4];
 } OdebGeomDesc;
 
 typedef struct OdebJointDesc {

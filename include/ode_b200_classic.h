@@ -18,7 +18,7 @@
  * stages: without a CUDA device dWorldQuickStep returns 0 and dSpaceCollide reports through the error handler.
  *
  * Outside the subset (calls are not exported): dWorldStep, joints other than contact/ball/hinge/slider/universal/hinge2/fixed, geoms other
- * than sphere/box/capsule/plane, geom offsets, nested spaces, per-body
+ * than sphere/box/capsule/plane, nested spaces, per-body
  * auto-disable thresholds (the world's are used), SAP axis orders other than dSAP_AXES_XYZ.
  */
 #ifndef ODE_B200_CLASSIC_H
@@ -292,6 +292,7 @@ dSpaceID dSimpleSpaceCreate(dSpaceID space);
 dSpaceID dHashSpaceCreate(dSpaceID space);
 dSpaceID dSweepAndPruneSpaceCreate(dSpaceID space, int axisorder);
 void dHashSpaceSetLevels(dSpaceID space, int minlevel, int maxlevel);
+void dHashSpaceGetLevels(dSpaceID space, int *minlevel, int *maxlevel);
 void dSpaceDestroy(dSpaceID);
 void dSpaceSetCleanup(dSpaceID space, int mode);
 int dSpaceGetCleanup(dSpaceID space);
@@ -315,6 +316,13 @@ void dGeomSetRotation(dGeomID, const dMatrix3 R);
 void dGeomSetQuaternion(dGeomID, const dQuaternion Q);
 const dReal *dGeomGetPosition(dGeomID);
 const dReal *dGeomGetRotation(dGeomID);
+void dGeomSetOffsetPosition(dGeomID, dReal x, dReal y, dReal z);      /* composite bodies: pose relative to the body */
+void dGeomSetOffsetRotation(dGeomID, const dMatrix3 R);
+void dGeomSetOffsetQuaternion(dGeomID, const dQuaternion q);
+void dGeomClearOffset(dGeomID);
+int dGeomIsOffset(dGeomID);
+const dReal *dGeomGetOffsetPosition(dGeomID);
+const dReal *dGeomGetOffsetRotation(dGeomID);
 void dGeomGetAABB(dGeomID, dReal aabb[6]);
 int dGeomGetClass(dGeomID);
 void dGeomSetCategoryBits(dGeomID, unsigned long bits);

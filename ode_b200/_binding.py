@@ -28,6 +28,7 @@ class OdebWorldParams(C.Structure):
         ("motion1", C.c_double), ("motion2", C.c_double), ("motionN", C.c_double),
         ("slip1", C.c_double), ("slip2", C.c_double),
         ("rho", C.c_double), ("rho2", C.c_double), ("rhoN", C.c_double),
+        ("hash_levels_set", C.c_int), ("hash_minlevel", C.c_int), ("hash_maxlevel", C.c_int),
     ]
 
 
@@ -37,7 +38,8 @@ class OdebBodyDesc(C.Structure):
 
 class OdebGeomDesc(C.Structure):
     _fields_ = [("type", C.c_int), ("body", C.c_int), ("p", C.c_double * 4),
-                ("category_bits", C.c_uint32), ("collide_bits", C.c_uint32)]
+                ("category_bits", C.c_uint32), ("collide_bits", C.c_uint32),
+                ("has_offset", C.c_int), ("offset_pos", C.c_double * 3), ("offset_quat", C.c_double * 4)]
 
 
 class OdebJointDesc(C.Structure):
@@ -56,7 +58,7 @@ class OdebStats(C.Structure):
 
 SPHERE, BOX, CAPSULE, PLANE = 0, 1, 2, 4
 JOINT_BALL, JOINT_HINGE, JOINT_SLIDER, JOINT_CONTACT, JOINT_UNIVERSAL, JOINT_HINGE2, JOINT_FIXED = 1, 2, 3, 4, 5, 6, 7
-SPACE_HASH, SPACE_SAP = 0, 1
+SPACE_HASH, SPACE_SAP, SPACE_SIMPLE = 0, 1, 2
 CONTACT_MU2, CONTACT_BOUNCE, CONTACT_SOFT_ERP, CONTACT_SOFT_CFM = 0x001, 0x004, 0x008, 0x010
 CONTACT_MOTION1, CONTACT_MOTION2, CONTACT_MOTIONN = 0x020, 0x040, 0x080
 CONTACT_SLIP1, CONTACT_SLIP2, CONTACT_ROLLING, CONTACT_APPROX1 = 0x100, 0x200, 0x400, 0x7000
@@ -110,9 +112,13 @@ class Scene:
         self.body_quat.append(tuple(float(x) for x in quat))
         return len(self.bodies) - 1
 
-    def add_geom(self, gtype, params, body=-1, category=0xFFFFFFFF, collide=0xFFFFFFFF):
+    def add_geom(self, gtype, params, body=-1, category=0xFFFFFFFF, collide=0xFFFFFFFF, offset_pos=None, offset_quat=None):
         g = OdebGeomDesc()
         g.type, g.body = gtype, body
+        if offset_pos is not None or offset_quat is not None:
+            g.has_offset = 1
+            g.offset_pos[:] = offset_pos if offset_pos is not None else (0, 0, 0)
+            g.offset_quat[:] = offset_quat if offset_quat is not None else (1, 0, 0, 0)
         pp = list(params) + [0.0] * (4 - len(params))
         g.p[:] = pp
         g.category_bits, g.collide_bits = category, collide

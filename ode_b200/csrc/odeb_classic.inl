@@ -52,12 +52,15 @@ struct dxGeom {
     int type; dxSpace *space; dxBody *body; void *userdata;
     Real p[4];                               // class parameters (radius | sides | radius,length | plane)
     Real pos[4], R[12];                      // own placement when no body is attached
+    int has_ofs; Real opos[4], oR[12];       // dGeomSetOffset*: pose relative to the body (collision_kernel.cpp:1000-1130)
+    Real fpos[4], fR[12];                    // final pose handed out by dGeomGetPosition / dGeomGetRotation for offset geoms
     unsigned long cat, col;
     int index;                               // position in space->geoms
 };
 
 struct dxSpace {
-    int type;                                // ODEB_SPACE_HASH (simple and hash spaces report the same pair set) | ODEB_SPACE_SAP
+    int type;                                // ODEB_SPACE_HASH | ODEB_SPACE_SAP | ODEB_SPACE_SIMPLE
+    int minlevel, maxlevel;                  // dxHashSpace::global_minlevel / global_maxlevel
     int cleanup;
     std::vector<dxGeom *> geoms;
     int lock_count;
@@ -164,7 +167,7 @@ static ClassicCtx *ctx_get(dxWorld *w, dxSpace *s, int need_contacts)
         body_to_host(b, T.hb[i]);
         T.bflags0[i] = b->flags;
     }
-    T.gtype.resize(ng); T.gbody.resize(ng); T.gparam.resize(4 * (size_t)ng); T.gcat.resize(ng); T.gcol.resize(ng); T.gspose.resize(4 * (size_t)ng);
+    T.gtype.resize(ng); T.gbody.resize(ng); T.gparam.resize(4 * (size_t)ng); T.gcat.resize(ng); T.gcol.resize(ng); T.gspose.resize(4 * (size_t)ng); T.gofs.assign(ng, 0);
     for (int i = 0; i < ng; i++) {
         dxGeom *g = s->geoms[i];
         g->index = i;
@@ -172,8 +175,11 @@ static ClassicCtx *ctx_get(dxWorld *w, dxSpace *s, int need_contacts)
         T.gtype[i] = g->type; T.gbody[i] = g->body ? g->body->index : -1;
         T.gcat[i] = (unsigned)g->cat; T.gcol[i] = (unsigned)g->col;
         for (int k = 0; k < 4; k++) T.gparam[4 * i + k] = g->p[k];
-        Real4 p = { g->pos[0], g->pos[1], g->pos[2], 0 }, r0 = { g->R[0], g->R[1], g->R[2], 0 }, r1 = { g->R[4], g->R[5], g->R[6], 0 }, r2 = { g->R[8], g->R[9], g->R[10], 0 };
+        const bool ofs = g->body && g->has_ofs;
+        const Real *gp = ofs ? g->opos : g->pos, *gR = ofs ? g->oR : g->R;
+        Real4 p = { gp[0], gp[1], gp[2], 0 }, r0 = { gR[0], gR[1], gR[2], 0 }, r1 = { gR[4], gR[5], gR[6], 0 }, r2 = { gR[8], gR[9], gR[10], 0 };
         T.gspose[4 * i] = p; T.gspose[4 * i + 1] = r0; T.gspose[4 * i + 2] = r1; T.gspose[4 * i + 3] = r2;
+        T.gofs[i] = ofs ? 1 : 0;
     }
     c = new ClassicCtx();
     c->B = 0; c->space = s; c->nb = nb; c->ng = ng; c->in_pass = false; c->cache_flags = -1; c->cache_maxc = 0;
@@ -240,13 +246,17 @@ static int ctx_upload_state(dxWorld *w, ClassicCtx *c)
     if (c->space && c->ng > 0) {
         std::vector<Real4> gs(4 * (size_t)c->ng);
         std::vector<unsigned> gc(c->ng), gl(c->ng);
+        std::vector<int> go(c->ng);
         for (int i = 0; i < c->ng; i++) {
             const dxGeom *g = c->space->geoms[i];
-            Real4 p = { g->pos[0], g->pos[1], g->pos[2], 0 }, r0 = { g->R[0], g->R[1], g->R[2], 0 }, r1 = { g->R[4], g->R[5], g->R[6], 0 }, r2 = { g->R[8], g->R[9], g->R[10], 0 };
+            const bool ofs = g->body && g->has_ofs;
+            const Real *gp = ofs ? g->opos : g->pos, *gR = ofs ? g->oR : g->R;
+            Real4 p = { gp[0], gp[1], gp[2], 0 }, r0 = { gR[0], gR[1], gR[2], 0 }, r1 = { gR[4], gR[5], gR[6], 0 }, r2 = { gR[8], gR[9], gR[10], 0 };
             gs[4 * i] = p; gs[4 * i + 1] = r0; gs[4 * i + 2] = r1; gs[4 * i + 3] = r2;
-            gc[i] = (unsigned)g->cat; gl[i] = (unsigned)g->col;
+            gc[i] = (unsigned)g->cat; gl[i] = (unsigned)g->col; go[i] = ofs ? 1 : 0;
         }
         CK(cudaMemcpy(D.gspose, gs.data(), gs.size() * sizeof(Real4), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(D.gofs, go.data(), go.size() * sizeof(int), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(D.gcat, gc.data(), gc.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(D.gcol, gl.data(), gl.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
     }
@@ -934,7 +944,7 @@ int dAreConnectedExcluding(dBodyID b1, dBodyID b2, int joint_type)
 static dxSpace *new_space(int type)
 {
     dxSpace *s = new dxSpace();
-    s->type = type; s->cleanup = 1; s->lock_count = 0;
+    s->type = type; s->cleanup = 1; s->lock_count = 0; s->minlevel = -3; s->maxlevel = 10;
     g_spaces.push_back(s);
     return s;
 }
@@ -943,7 +953,7 @@ static void space_changed(dxSpace *s)
     dxWorld *w = s ? space_world(s) : 0;
     if (w) w->topo_dirty = true;
 }
-dSpaceID dSimpleSpaceCreate(dSpaceID parent) { if (parent) classic_error("nested spaces are outside the supported subset"); return new_space(ODEB_SPACE_HASH); }
+dSpaceID dSimpleSpaceCreate(dSpaceID parent) { if (parent) classic_error("nested spaces are outside the supported subset"); return new_space(ODEB_SPACE_SIMPLE); }
 dSpaceID dHashSpaceCreate(dSpaceID parent) { if (parent) classic_error("nested spaces are outside the supported subset"); return new_space(ODEB_SPACE_HASH); }
 dSpaceID dSweepAndPruneSpaceCreate(dSpaceID parent, int axisorder)
 {
@@ -951,7 +961,8 @@ dSpaceID dSweepAndPruneSpaceCreate(dSpaceID parent, int axisorder)
     if (axisorder != dSAP_AXES_XYZ) classic_error("dSweepAndPruneSpaceCreate: only dSAP_AXES_XYZ is supported");
     return new_space(ODEB_SPACE_SAP);
 }
-void dHashSpaceSetLevels(dSpaceID, int, int) {}      // the reported pair set does not depend on the hash levels
+void dHashSpaceSetLevels(dSpaceID s, int minlevel, int maxlevel) { s->minlevel = minlevel; s->maxlevel = maxlevel; }   // dxHashSpace::setLevels collision_space.cpp:392-397
+void dHashSpaceGetLevels(dSpaceID s, int *minlevel, int *maxlevel) { if (minlevel) *minlevel = s->minlevel; if (maxlevel) *maxlevel = s->maxlevel; }
 void dSpaceSetCleanup(dSpaceID s, int mode) { s->cleanup = mode != 0; }
 int dSpaceGetCleanup(dSpaceID s) { return s->cleanup; }
 int dSpaceGetNumGeoms(dSpaceID s) { return (int)s->geoms.size(); }
@@ -994,6 +1005,8 @@ static dxGeom *new_geom(dxSpace *s, int type, Real p0, Real p1, Real p2, Real p3
     g->p[0] = p0; g->p[1] = p1; g->p[2] = p2; g->p[3] = p3;
     for (int k = 0; k < 4; k++) g->pos[k] = 0;
     set_identity_R(g->R);
+    g->has_ofs = 0; for (int k = 0; k < 4; k++) g->opos[k] = g->fpos[k] = 0;
+    set_identity_R(g->oR); set_identity_R(g->fR);
     g->cat = ~0UL; g->col = ~0UL; g->index = -1;
     if (s) dSpaceAdd(s, g);
     return g;
@@ -1024,8 +1037,30 @@ void dGeomSetPosition(dGeomID g, Real x, Real y, Real z)
 }
 void dGeomSetRotation(dGeomID g, const Real *R) { if (g->body) dBodySetRotation(g->body, R); else memcpy(g->R, R, 12 * sizeof(Real)); }
 void dGeomSetQuaternion(dGeomID g, const Real *q) { if (g->body) dBodySetQuaternion(g->body, q); else r_from_q(g->R, q); }
-const odeb_real *dGeomGetPosition(dGeomID g) { return g->body ? g->body->pos : g->pos; }
-const odeb_real *dGeomGetRotation(dGeomID g) { return g->body ? g->body->R : g->R; }
+static void geom_final_pose(dxGeom *g)
+{   // dxGeom::computePosr collision_kernel.cpp:455-466
+    mul0_331(g->fpos, g->body->R, g->opos);
+    g->fpos[0] += g->body->pos[0]; g->fpos[1] += g->body->pos[1]; g->fpos[2] += g->body->pos[2];
+    mul0_333(g->fR, g->body->R, g->oR);
+}
+const odeb_real *dGeomGetPosition(dGeomID g)
+{
+    if (g->body && g->has_ofs) { geom_final_pose(g); return g->fpos; }
+    return g->body ? g->body->pos : g->pos;
+}
+const odeb_real *dGeomGetRotation(dGeomID g)
+{
+    if (g->body && g->has_ofs) { geom_final_pose(g); return g->fR; }
+    return g->body ? g->body->R : g->R;
+}
+// geom offsets relative to the body (collision_kernel.cpp:1000-1130); a geom without a body cannot have one
+void dGeomSetOffsetPosition(dGeomID g, Real x, Real y, Real z) { if (!g->body) return; g->has_ofs = 1; g->opos[0] = x; g->opos[1] = y; g->opos[2] = z; }
+void dGeomSetOffsetRotation(dGeomID g, const Real *R) { if (!g->body) return; g->has_ofs = 1; memcpy(g->oR, R, 12 * sizeof(Real)); }
+void dGeomSetOffsetQuaternion(dGeomID g, const Real *q) { if (!g->body) return; g->has_ofs = 1; r_from_q(g->oR, q); }
+void dGeomClearOffset(dGeomID g) { g->has_ofs = 0; g->opos[0] = g->opos[1] = g->opos[2] = 0; set_identity_R(g->oR); }
+int dGeomIsOffset(dGeomID g) { return g->has_ofs; }
+const odeb_real *dGeomGetOffsetPosition(dGeomID g) { return g->opos; }
+const odeb_real *dGeomGetOffsetRotation(dGeomID g) { return g->oR; }
 int dGeomGetClass(dGeomID g) { return g->type; }
 void dGeomSetCategoryBits(dGeomID g, unsigned long bits) { g->cat = bits; }
 void dGeomSetCollideBits(dGeomID g, unsigned long bits) { g->col = bits; }
@@ -1101,7 +1136,7 @@ void dSpaceCollide(dSpaceID s, void *data, dNearCallback *callback)
         OdebBatch *B = c->B;
         OdebWorldParams wp = w->wp; wp.space_type = s->type; wp.max_contacts = 8;
         apply_world_params(B->P, &wp, true);
-        B->P.space_type = s->type;
+        B->P.space_type = s->type; B->P.hash_minlevel = s->minlevel; B->P.hash_maxlevel = s->maxlevel;
         launch_collide(B, B->stream, false);
         int np = 0, ov = 0;
         cudaStreamSynchronize(B->stream);

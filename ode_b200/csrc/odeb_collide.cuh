@@ -50,6 +50,45 @@ __device__ __forceinline__ void odeb_compute_aabb(const DGeom &g, Real *a)
     }
 }
 
+// dxHashSpace::collide collision_space.cpp:421-614 beyond the AABB test: does the cell walk bring two overlapping AABBs together?
+// level = frexp exponent of the largest extent (findLevel :329-349) clamped up to minlevel; cell bounds = floor(aabb / 2^level) (:448-462);
+// levels above maxlevel (infinite AABBs: MAXINT) sit in the big list and are tested against everything (:590-607).  The lower-level AABB
+// probes the higher level with bounds >>= 1 (:582).  The hash index of a cell column starts at (level*1000UL + x*100UL + y*10UL + zbegin) % sz
+// (:358-361, :499, :533; level/x/y through unsigned int, zbegin a plain int) and is incremented per z: a negative zbegin larger than the
+// base wraps the sum around 2^64, which shifts that column's slots by 2^64 % sz (sz is an odd prime), so the two sides only see each
+// other in columns they address with the same wrap state.
+__device__ __forceinline__ int odeb_hash_level(const Real *a, int minlevel)
+{
+    if (a[0] <= -R_INF || a[1] >= R_INF || a[2] <= -R_INF || a[3] >= R_INF || a[4] <= -R_INF || a[5] >= R_INF) return 0x7fffffff;
+    Real q = a[1] - a[0], q2 = a[3] - a[2];
+    if (q2 > q) q = q2;
+    q2 = a[5] - a[4];
+    if (q2 > q) q = q2;
+    int level;
+    frexp(q, &level);
+    return level < minlevel ? minlevel : level;
+}
+__device__ __forceinline__ bool odeb_hash_column_wraps(int level, int x, int y, int zbegin)
+{
+    unsigned long long base = (unsigned long long)(unsigned)level * 1000ULL + (unsigned long long)(unsigned)x * 100ULL + (unsigned long long)(unsigned)y * 10ULL;
+    return zbegin < 0 && base < (unsigned long long)(-(long long)zbegin);
+}
+__device__ __noinline__ bool odeb_hash_space_meets(const Real *a, const Real *b, int minlevel, int maxlevel)
+{
+    int la = odeb_hash_level(a, minlevel), lb = odeb_hash_level(b, minlevel);
+    if (la > maxlevel || lb > maxlevel) return true;
+    if (la > lb) { const Real *t = a; a = b; b = t; int tl = la; la = lb; lb = tl; }
+    int da[6], db[6];
+    const Real ra = ldexp((Real)1, -la), rb = ldexp((Real)1, -lb);
+    for (int i = 0; i < 6; i++) { da[i] = (int)floor(a[i] * ra) >> (lb - la); db[i] = (int)floor(b[i] * rb); }
+    if (da[4] >= 0 && db[4] >= 0) return true;                  // nothing wraps: overlapping AABBs always share a cell
+    const int x0 = max(da[0], db[0]), x1 = min(da[1], db[1]), y0 = max(da[2], db[2]), y1 = min(da[3], db[3]);
+    if (max(da[4], db[4]) > min(da[5], db[5])) return false;
+    for (int x = x0; x <= x1; x++) for (int y = y0; y <= y1; y++)
+        if (odeb_hash_column_wraps(lb, x, y, da[4]) == odeb_hash_column_wraps(lb, x, y, db[4])) return true;
+    return false;
+}
+
 // dCollideSpheres collision_util.cpp:38-67
 __device__ int odeb_collide_spheres(const Real *p1, Real r1, const Real *p2, Real r2, DContactGeom *c)
 {

@@ -277,7 +277,8 @@ struct HostTemplate {
     std::vector<HostBody> hb;                                // pose of every body
     std::vector<int> bflags0;                                // BF_* per body
     std::vector<int> gtype, gbody; std::vector<Real> gparam; std::vector<unsigned> gcat, gcol;
-    std::vector<Real4> gspose;                               // [NG*4]: position + 3 rotation rows of geoms without a body
+    std::vector<Real4> gspose;                               // [NG*4]: position + 3 rotation rows of geoms without a body / offset pose
+    std::vector<int> gofs;                                   // [NG]: geom has an offset relative to its body
     std::vector<DJointT> jt;
     std::vector<int> sofs, sj, so;                           // per-body joint adjacency in attach order (CSR)
 };
@@ -306,6 +307,7 @@ static OdebBatch *batch_build(const OdebWorldParams *wp, const HostTemplate &T, 
     memset(&P, 0, sizeof(P));
     P.W = nworlds; P.NB = nbody; P.NG = ngeom; P.NJ = njoint; P.classic = classic ? 1 : 0;
     P.maxc = wp->max_contacts; P.space_type = wp->space_type; P.skip_connected = wp->skip_connected;
+    P.hash_minlevel = wp->hash_levels_set ? wp->hash_minlevel : -3; P.hash_maxlevel = wp->hash_levels_set ? wp->hash_maxlevel : 10;   // dxHashSpace::dxHashSpace collision_space.cpp:383-389
     {
         long long all = (long long)ngeom * (ngeom - 1) / 2;
         long long mp = all < 16LL * ngeom ? all : 16LL * ngeom;
@@ -375,7 +377,7 @@ static OdebBatch *batch_build(const OdebWorldParams *wp, const HostTemplate &T, 
             && dev_alloc(B, &D.avg_buf, WB * 6 * NS) && dev_alloc(B, &D.avg_counter, WB) && dev_alloc(B, &D.avg_ready, WB);
     ok = ok && dev_alloc(B, &D.bmass, nbody) && dev_alloc(B, &D.binvmass, nbody) && dev_alloc(B, &D.bI, 12 * (size_t)nbody) && dev_alloc(B, &D.binvI, 12 * (size_t)nbody)
             && dev_alloc(B, &D.gtype, ngeom) && dev_alloc(B, &D.gbody, ngeom) && dev_alloc(B, &D.gparam, 4 * (size_t)ngeom)
-            && dev_alloc(B, &D.gcat, ngeom) && dev_alloc(B, &D.gcol, ngeom) && dev_alloc(B, &D.gspose, 4 * (size_t)ngeom) && dev_alloc(B, &D.joints, njoint)
+            && dev_alloc(B, &D.gcat, ngeom) && dev_alloc(B, &D.gcol, ngeom) && dev_alloc(B, &D.gspose, 4 * (size_t)ngeom) && dev_alloc(B, &D.gofs, ngeom) && dev_alloc(B, &D.joints, njoint)
             && dev_alloc(B, &D.sadj_ofs, nbody + 1) && dev_alloc(B, &D.sadj_joint, nadj) && dev_alloc(B, &D.sadj_other, nadj);
     ok = ok && dev_alloc(B, &D.aabb, WG * 6) && dev_alloc(B, &D.pair_cnt, WG) && dev_alloc(B, &D.pair_ofs, WG) && dev_alloc(B, &D.npairs, W)
             && dev_alloc(B, &D.pairs, W * P.MP) && dev_alloc(B, &D.pc_count, W * P.MP) && dev_alloc(B, &D.cgeom, W * (classic ? (size_t)P.MC : (size_t)P.MP * P.maxc) * 2)
@@ -426,7 +428,7 @@ static OdebBatch *batch_build(const OdebWorldParams *wp, const HostTemplate &T, 
 
     ok = upload(D.bmass, T.bmass) && upload(D.binvmass, T.binvmass) && upload(D.bI, T.bI) && upload(D.binvI, T.binvI)
       && upload(D.gtype, T.gtype) && upload(D.gbody, T.gbody) && upload(D.gparam, T.gparam) && upload(D.gcat, T.gcat) && upload(D.gcol, T.gcol)
-      && upload(D.gspose, T.gspose)
+      && upload(D.gspose, T.gspose) && upload(D.gofs, T.gofs)
       && upload(D.joints, T.jt) && upload(D.sadj_ofs, T.sofs) && upload(D.sadj_joint, T.sj) && upload(D.sadj_other, T.so);
     // initial per-world state = template pose
     {
@@ -493,7 +495,7 @@ OdebBatch *odeb_create(const OdebWorldParams *wp,
         T.bflags0[i] = fl;
     }
     T.gtype.resize(ngeom); T.gbody.resize(ngeom); T.gparam.resize(4 * (size_t)ngeom); T.gcat.resize(ngeom); T.gcol.resize(ngeom);
-    T.gspose.resize(4 * (size_t)ngeom);
+    T.gspose.resize(4 * (size_t)ngeom); T.gofs.assign(ngeom, 0);
     for (int i = 0; i < ngeom; i++) {
         T.gtype[i] = geoms[i].type; T.gbody[i] = geoms[i].body; T.gcat[i] = geoms[i].category_bits; T.gcol[i] = geoms[i].collide_bits;
         if (T.gbody[i] >= nbody) { set_err("geom %d: bad body index", i); return 0; }
@@ -503,6 +505,14 @@ OdebBatch *odeb_create(const OdebWorldParams *wp,
         if (T.gtype[i] == ODEB_PLANE) host_normalize_plane(p);
         Real4 z = { 0, 0, 0, 0 }, r0 = { 1, 0, 0, 0 }, r1 = { 0, 1, 0, 0 }, r2 = { 0, 0, 1, 0 };
         T.gspose[4 * i] = z; T.gspose[4 * i + 1] = r0; T.gspose[4 * i + 2] = r1; T.gspose[4 * i + 3] = r2;
+        if (geoms[i].has_offset && T.gbody[i] >= 0) {      // dGeomSetOffsetPosition / dGeomSetOffsetQuaternion (dRfromQ)
+            Real q[4] = { (Real)geoms[i].offset_quat[0], (Real)geoms[i].offset_quat[1], (Real)geoms[i].offset_quat[2], (Real)geoms[i].offset_quat[3] }, oR[12];
+            r_from_q(oR, q);
+            Real4 op = { (Real)geoms[i].offset_pos[0], (Real)geoms[i].offset_pos[1], (Real)geoms[i].offset_pos[2], 0 };
+            Real4 a = { oR[0], oR[1], oR[2], 0 }, b = { oR[4], oR[5], oR[6], 0 }, c = { oR[8], oR[9], oR[10], 0 };
+            T.gspose[4 * i] = op; T.gspose[4 * i + 1] = a; T.gspose[4 * i + 2] = b; T.gspose[4 * i + 3] = c;
+            T.gofs[i] = 1;
+        }
     }
     T.jt.resize(njoint);
     std::vector<std::vector<std::pair<int, int> > > adj(nbody);

@@ -47,6 +47,7 @@ enum { BF_FINITE_ROT = 1, BF_DISABLED = 4, BF_NO_GRAVITY = 8, BF_AUTO_DISABLE = 
 struct DevParams {
     int W, NB, NG, NJ, MP, MC, MR, NJT;   // worlds, bodies, geoms, permanent joints, pair / contact / row capacity, NJ+MC
     int maxc, space_type, skip_connected;
+    int hash_minlevel, hash_maxlevel;     // dxHashSpace levels (default -3..10, dHashSpaceSetLevels)
     int classic;                          // 1: contacts, their surfaces and the joint adjacency are supplied by the host every step (odeb_classic.inl)
     int m_contact;                        // rows per contact joint (contact.cpp:48-122, uniform under one policy)
     DSurface surf;
@@ -66,7 +67,8 @@ struct DevPtrs {
     // template (per batch)
     Real *bmass, *binvmass; Real *bI, *binvI;    // [NB], [NB*12]
     int *gtype, *gbody; Real *gparam; unsigned *gcat, *gcol;   // [NG], gparam [NG*4]
-    Real4 *gspose;                               // [NG*4] position + rotation rows of geoms that have no body
+    Real4 *gspose;                               // [NG*4] position + rotation rows of geoms that have no body; offset pose of body geoms with gofs
+    int *gofs;                                   // [NG] 1: the geom sits at gspose relative to its body (dGeomSetOffset*)
     DJointT *joints;                             // [NJ]
     int *sadj_ofs, *sadj_joint, *sadj_other;     // static adjacency in attach order
     // collision scratch
@@ -129,6 +131,15 @@ __device__ __forceinline__ void load_geom(const DevParams &P, const DevPtrs &D, 
         G.R[0] = r0.x; G.R[1] = r0.y; G.R[2] = r0.z; G.R[3] = 0;
         G.R[4] = r1.x; G.R[5] = r1.y; G.R[6] = r1.z; G.R[7] = 0;
         G.R[8] = r2.x; G.R[9] = r2.y; G.R[10] = r2.z; G.R[11] = 0;
+        if (D.gofs[g]) {   // dxGeom::computePosr collision_kernel.cpp:455-466: final = body pose * offset pose
+            const Real4 *sp = D.gspose + 4 * (size_t)g;
+            Real4 op = sp[0], o0 = sp[1], o1 = sp[2], o2 = sp[3];
+            Real ofs[3] = { op.x, op.y, op.z }, oR[12] = { o0.x, o0.y, o0.z, 0, o1.x, o1.y, o1.z, 0, o2.x, o2.y, o2.z, 0 }, fp[3], fR[12];
+            mul0_331(fp, G.R, ofs);
+            G.pos[0] = fp[0] + G.pos[0]; G.pos[1] = fp[1] + G.pos[1]; G.pos[2] = fp[2] + G.pos[2];
+            mul0_333(fR, G.R, oR);
+            for (int k = 0; k < 12; k++) G.R[k] = fR[k];
+        }
     } else {
         const Real4 *sp = D.gspose + 4 * (size_t)g;
         Real4 p = sp[0], r0 = sp[1], r1 = sp[2], r2 = sp[3];
@@ -170,7 +181,8 @@ __device__ __forceinline__ bool pair_hit(const DevParams &P, const DevPtrs &D, c
             return ax0 && !(ai[3] < aj[2] || aj[3] < ai[2]) && !(ai[5] < aj[4] || aj[5] < ai[4]);
         }
     }
-    return !(ai[0] > aj[1] || ai[1] < aj[0] || ai[2] > aj[3] || ai[3] < aj[2] || ai[4] > aj[5] || ai[5] < aj[4]);
+    if (ai[0] > aj[1] || ai[1] < aj[0] || ai[2] > aj[3] || ai[3] < aj[2] || ai[4] > aj[5] || ai[5] < aj[4]) return false;
+    return P.space_type != ODEB_SPACE_HASH || odeb_hash_space_meets(ai, aj, P.hash_minlevel, P.hash_maxlevel);
 }
 
 template <bool FILL>

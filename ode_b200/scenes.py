@@ -262,6 +262,68 @@ def conveyor(nworlds=1, seed0=71):
     return sc
 
 
+def composite(nworlds=1, seed0=81):
+    """Composite bodies through geom offsets (dGeomSetOffsetPosition / dGeomSetOffsetQuaternion, collision_kernel.cpp:455-466): dumbbells =
+    one body carrying two spheres at +-0.3 along its x axis and a capsule bar between them (offset rotation), tumbling onto a plane and
+    onto each other; the demo_boxstack 'x' objects are built the same way."""
+    sc = B.Scene(B.default_world_params(gravity=(0, 0, -9.81), max_contacts=4, surf_mode=B.CONTACT_APPROX1, mu=0.7), nworlds)
+    sc.add_geom(B.PLANE, (0, 0, 1, 0))
+    s = np.sqrt(0.5)
+    for k in range(4):
+        I = np.diag([0.02, 0.12, 0.12])
+        b = sc.add_body(1.5, I, (0.25 * k, 0.3 * k, 0.5 + 0.55 * k), (np.cos(0.2 * k), 0.0, np.sin(0.2 * k), 0.0))
+        sc.add_geom(B.SPHERE, (0.15,), body=b, offset_pos=(0.3, 0, 0))
+        sc.add_geom(B.SPHERE, (0.15,), body=b, offset_pos=(-0.3, 0, 0))
+        sc.add_geom(B.CAPSULE, (0.05, 0.5), body=b, offset_pos=(0, 0, 0), offset_quat=(s, 0.0, s, 0.0))      # capsule axis z -> body x
+    nb = sc.nbody
+    pos = np.tile(np.asarray(sc.body_pos)[None], (nworlds, 1, 1))
+    quat = np.tile(np.asarray(sc.body_quat)[None], (nworlds, 1, 1))
+    lvel = np.zeros((nworlds, nb, 3))
+    avel = np.zeros((nworlds, nb, 3))
+    for w in range(nworlds):
+        r = _rng(seed0 + w)
+        avel[w] = 2.0 * (r.rand(nb, 3) - 0.5)
+    sc.state = dict(pos=pos, quat=quat, lvel=lvel, avel=avel)
+    sc.seeds = (seed0 + np.arange(nworlds)).astype(np.uint32)
+    return sc
+
+
+def scatter(nworlds=1, n=40, seed0=300, space_type=B.SPACE_HASH, extent=1.0, levels=None, plane=True):
+    """Broadphase exerciser: n spheres / boxes / capsules of sizes 0.05 .. 1.5 (hash levels -3 .. 1) scattered in a cube of half-width
+    `extent` around the origin, no gravity, slow drift.  Around the origin the hash space's cell addresses with negative z wrap
+    (collision_space.cpp:499, :533), so its callback stream is a strict subset of the simple space's there; per world the positions
+    and orientations differ, the sizes are the template's."""
+    kw = dict(gravity=(0, 0, 0), max_contacts=2, surf_mode=B.CONTACT_APPROX1, mu=0.5, space_type=space_type)
+    if levels is not None:
+        kw.update(hash_levels_set=1, hash_minlevel=levels[0], hash_maxlevel=levels[1])
+    sc = B.Scene(B.default_world_params(**kw), nworlds)
+    if plane:
+        sc.add_geom(B.PLANE, (0, 0, 1, -extent))
+    r = _rng(seed0)
+    for i in range(n):
+        size = 0.05 * (30.0 ** r.rand())
+        b = sc.add_body(1.0, np.eye(3) * 0.1, (0, 0, 0))
+        kind = i % 3
+        if kind == 0:
+            sc.add_geom(B.SPHERE, (0.5 * size,), body=b)
+        elif kind == 1:
+            sc.add_geom(B.BOX, (size, size * (0.3 + 0.7 * r.rand()), size * (0.3 + 0.7 * r.rand())), body=b)
+        else:
+            sc.add_geom(B.CAPSULE, (0.15 * size, 0.7 * size), body=b)
+    pos = np.zeros((nworlds, n, 3))
+    quat = np.zeros((nworlds, n, 4))
+    lvel = np.zeros((nworlds, n, 3))
+    for w in range(nworlds):
+        rw = _rng(seed0 + 1 + w)
+        pos[w] = extent * (2 * rw.rand(n, 3) - 1)
+        q = rw.randn(n, 4)
+        quat[w] = q / np.linalg.norm(q, axis=1, keepdims=True)
+        lvel[w] = 0.5 * (rw.rand(n, 3) - 0.5)
+    sc.state = dict(pos=pos, quat=quat, lvel=lvel, avel=np.zeros_like(pos))
+    sc.seeds = (seed0 + np.arange(nworlds)).astype(np.uint32)
+    return sc
+
+
 def free_boxes(nworlds=1, nboxes=64, seed0=5, grid=8, spacing=1.5):
     """nboxes separate unit boxes resting/falling on the plane: many one-body islands per world
     (the scattered 64-body world of SURVEY.md 7.2(4))."""

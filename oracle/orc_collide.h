@@ -13,6 +13,8 @@ struct OrcGeom {
     const Real *pos; // -> body pos (4) or own storage
     const Real *R;   // -> body R (12)
     Real aabb[6];
+    int has_ofs;     // dGeomSetOffset*: opos / oR relative to the body, fpos / fR = final pose (computePosr collision_kernel.cpp:455-466)
+    Real opos[4], oR[12], fpos[4], fR[12];
 };
 
 struct OrcContactGeom { Real pos[3], normal[3], depth; };

@@ -211,6 +211,50 @@ inline bool pair_filter(const OrcGeom &g1, const OrcGeom &g2)
     return true;
 }
 
+// dxHashSpace::collide collision_space.cpp:421-614, the part that is not a plain AABB test: whether the cell walk brings two AABBs together.
+// Each AABB gets level = exponent of frexp(largest extent) (findLevel :329-349) clamped up to minlevel, and integer cell bounds
+// floor(aabb / 2^level) (:448-462); levels above maxlevel (planes: MAXINT) go to the big list, which is tested against everything
+// (:590-607).  An AABB is inserted in the cells of its own level and probes its own and every higher level with bounds >>= 1 (:521-582).
+// Per (x,y) column the hash index starts at (level*1000UL + x*100UL + y*10UL + zbegin) % sz with level/x/y converted through unsigned int
+// and zbegin an int added to an unsigned long (:358-361, :499, :533), and is then incremented per z.  For zbegin < 0 and a base smaller
+// than -zbegin the sum wraps around 2^64, and since sz (a prime >= 13) does not divide 2^64 the cells of that column land 2^64 % sz slots
+// away from where an AABB with a non-wrapping zbegin looks for them.  Two overlapping AABBs therefore meet iff some shared cell column
+// is addressed with the same wrap state from both sides.
+static int hash_level(const Real *a, int minlevel)
+{
+    if (a[0] <= -R_INF || a[1] >= R_INF || a[2] <= -R_INF || a[3] >= R_INF || a[4] <= -R_INF || a[5] >= R_INF) return 0x7fffffff;
+    Real q = a[1] - a[0], q2 = a[3] - a[2];
+    if (q2 > q) q = q2;
+    q2 = a[5] - a[4];
+    if (q2 > q) q = q2;
+    int level;
+    frexp(q, &level);
+    return level < minlevel ? minlevel : level;
+}
+static bool hash_column_wraps(int level, int x, int y, int zbegin)
+{
+    unsigned long base = (unsigned int)level * 1000UL + (unsigned int)x * 100UL + (unsigned int)y * 10UL;
+    return zbegin < 0 && base < (unsigned long)(-(long)zbegin);
+}
+bool hash_space_meets(const Real *a, const Real *b, int minlevel, int maxlevel)
+{
+    int la = hash_level(a, minlevel), lb = hash_level(b, minlevel);
+    if (la > maxlevel || lb > maxlevel) return true;
+    if (la > lb) { const Real *t = a; a = b; b = t; int tl = la; la = lb; lb = tl; }
+    int da[6], db[6];
+    const Real ra = (Real)1 / (Real)ldexp(1.0, la), rb = (Real)1 / (Real)ldexp(1.0, lb);
+    for (int i = 0; i < 6; i++) { da[i] = (int)floor(a[i] * ra); db[i] = (int)floor(b[i] * rb); }
+    for (int l = la; l < lb; l++) for (int i = 0; i < 6; i++) da[i] >>= 1;
+    if (da[4] >= 0 && db[4] >= 0) return true;                  // nothing wraps: overlapping AABBs always share a cell
+    const int x0 = da[0] > db[0] ? da[0] : db[0], x1 = da[1] < db[1] ? da[1] : db[1];
+    const int y0 = da[2] > db[2] ? da[2] : db[2], y1 = da[3] < db[3] ? da[3] : db[3];
+    const int z0 = da[4] > db[4] ? da[4] : db[4], z1 = da[5] < db[5] ? da[5] : db[5];
+    if (z0 > z1) return false;
+    for (int x = x0; x <= x1; x++) for (int y = y0; y <= y1; y++)
+        if (hash_column_wraps(lb, x, y, da[4]) == hash_column_wraps(lb, x, y, db[4])) return true;
+    return false;
+}
+
 void find_pairs(const Batch &B, World &W)
 {
     int ng = (int)W.geoms.size();
@@ -239,11 +283,15 @@ void find_pairs(const Batch &B, World &W)
             if (hit) { W.pairs.push_back(i); W.pairs.push_back(j); }
         }
     } else {
-        // dxHashSpace::collide collision_space.cpp:421-614 as a SET == all pairs passing collideAABBs
+        // dxSimpleSpace::collide collision_space.cpp:245-267 as a SET == all pairs passing collideAABBs;
+        // dxHashSpace::collide :421-614 == those of them that its cell walk brings together
+        const bool hash = (B.wp.space_type == ODEB_SPACE_HASH);
+        const int minl = B.wp.hash_levels_set ? B.wp.hash_minlevel : -3, maxl = B.wp.hash_levels_set ? B.wp.hash_maxlevel : 10;
         for (int i = 0; i < ng; i++) for (int j = i + 1; j < ng; j++) {
             const OrcGeom &g1 = W.geoms[i], &g2 = W.geoms[j];
             if (!pair_filter(g1, g2)) continue;
             if (!aabb_overlap(g1.aabb, g2.aabb)) continue;
+            if (hash && !hash_space_meets(g1.aabb, g2.aabb, minl, maxl)) continue;
             W.pairs.push_back(i); W.pairs.push_back(j);
         }
     }
@@ -269,6 +317,15 @@ void attach(World &W, int jid, Joint &j, int body1, int body2)
 
 void collide_world(const Batch &B, World &W)
 {
+    for (size_t i = 0; i < W.geoms.size(); i++) {       // recomputePosr of geoms with an offset
+        OrcGeom &g = W.geoms[i];
+        if (!g.has_ofs) continue;
+        const Body &b = W.bodies[g.body];
+        mul0_331(g.fpos, b.R, g.opos);
+        g.fpos[0] += b.pos[0]; g.fpos[1] += b.pos[1]; g.fpos[2] += b.pos[2];
+        mul0_333(g.fR, b.R, g.oR);
+        g.pos = g.fpos; g.R = g.fR;
+    }
     find_pairs(B, W);
     W.contacts.clear(); W.contact_g.clear();
     const OdebWorldParams &p = B.wp;
@@ -979,6 +1036,15 @@ void *orc_create(const OdebWorldParams *wp, int nbody, const OdebBodyDesc *bodie
             g.cat = geoms[i].category_bits; g.col = geoms[i].collide_bits;
             if (g.body >= 0) { g.pos = W.bodies[g.body].pos; g.R = W.bodies[g.body].R; }
             else { g.pos = g_zero4; g.R = g_identity; }
+            g.has_ofs = 0;
+            if (geoms[i].has_offset && g.body >= 0) {
+                g.has_ofs = 1;
+                Real q[4] = { (Real)geoms[i].offset_quat[0], (Real)geoms[i].offset_quat[1], (Real)geoms[i].offset_quat[2], (Real)geoms[i].offset_quat[3] };
+                memset(g.oR, 0, sizeof(g.oR)); memset(g.fR, 0, sizeof(g.fR));
+                r_from_q(g.oR, q);
+                g.opos[0] = (Real)geoms[i].offset_pos[0]; g.opos[1] = (Real)geoms[i].offset_pos[1]; g.opos[2] = (Real)geoms[i].offset_pos[2]; g.opos[3] = 0;
+                g.fpos[3] = 0;
+            }
         }
         W.pjoints.resize(njoint);
         for (int i = 0; i < njoint; i++) {

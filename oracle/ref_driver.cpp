@@ -131,7 +131,9 @@ void *ref_create(const OdebWorldParams *wp,
     for (int wi = 0; wi < nworlds; wi++) {
         RefWorld &W = B->worlds[wi];
         W.world = dWorldCreate();
-        W.space = (wp->space_type == ODEB_SPACE_SAP) ? dSweepAndPruneSpaceCreate(0, dSAP_AXES_XYZ) : dHashSpaceCreate(0);
+        W.space = (wp->space_type == ODEB_SPACE_SAP) ? dSweepAndPruneSpaceCreate(0, dSAP_AXES_XYZ)
+                : (wp->space_type == ODEB_SPACE_SIMPLE) ? dSimpleSpaceCreate(0) : dHashSpaceCreate(0);
+        if (wp->space_type == ODEB_SPACE_HASH && wp->hash_levels_set) dHashSpaceSetLevels(W.space, wp->hash_minlevel, wp->hash_maxlevel);
         W.group = dJointGroupCreate(0);
         W.seed = 0; W.island_count = 0;
         memset(&W.stats, 0, sizeof(W.stats));
@@ -167,6 +169,11 @@ void *ref_create(const OdebWorldParams *wp,
             default: return 0;
             }
             if (g.body >= 0) dGeomSetBody(id, W.bodies[g.body]);
+            if (g.body >= 0 && g.has_offset) {
+                dGeomSetOffsetPosition(id, (dReal)g.offset_pos[0], (dReal)g.offset_pos[1], (dReal)g.offset_pos[2]);
+                dQuaternion q = { (dReal)g.offset_quat[0], (dReal)g.offset_quat[1], (dReal)g.offset_quat[2], (dReal)g.offset_quat[3] };
+                dGeomSetOffsetQuaternion(id, q);
+            }
             dGeomSetCategoryBits(id, g.category_bits);
             dGeomSetCollideBits(id, g.collide_bits);
             dGeomSetData(id, (void *)(intptr_t)i);

@@ -460,3 +460,41 @@ def test_kinematic_bodies(prec):
         bad = compare_step(a, b, sc.nworlds, exact_float=False, tol=TOL[prec], what=("pairs", "contacts", "islands", "stats", "seeds", "state"))
         assert not bad, (s, bad[:4])
     b.close()
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_geom_offsets(prec):
+    """Composite bodies (geoms at offset poses on one body): spheres and capsules only, so nothing on the path calls libm: every
+    observable identical to the oracle, every step."""
+    sc = scenes.composite(5)
+    a, b = B.Batch(orc_lib(prec), sc), B.Batch(gpu_lib(prec), sc)
+    for s in range(200):
+        a.step(0.01)
+        b.step(0.01)
+        bad = compare_step(a, b, sc.nworlds)
+        assert not bad, (s, bad[:4])
+    b.close()
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("space,levels", [(B.SPACE_HASH, None), (B.SPACE_HASH, (-1, 0)), (B.SPACE_HASH, (0, 4)), (B.SPACE_SIMPLE, None), (B.SPACE_SAP, None)])
+def test_broadphase_spaces(prec, space, levels):
+    """Callback stream of each reference space as a set, around the origin where the hash space's wrapped cell addresses drop pairs
+    (oracle pinned to the compiled reference in test_oracle.py::test_broadphase_callback_stream_vs_reference): batch path and, for one
+    world, the large-world sort + sweep path.  Boxes are in the scene, so floats are compared to tolerance and the sets exactly."""
+    sc = scenes.scatter(24, space_type=space, levels=levels)
+    a, b = B.Batch(orc_lib(prec), sc), B.Batch(gpu_lib(prec), sc)
+    for s in range(12):
+        a.step(0.02)
+        b.step(0.02)
+        bad = compare_step(a, b, sc.nworlds, exact_float=False, tol=TOL[prec], what=("pairs", "contacts", "islands", "state"))
+        assert not bad, (s, bad[:4])
+    b.close()
+    sc = scenes.scatter(1, n=120, space_type=space, levels=levels, extent=1.5)
+    a, b = _canon_pair(prec, sc)
+    for s in range(6):
+        a.step(0.02)
+        b.step(0.02)
+        bad = compare_step(a, b, 1, exact_float=False, tol=TOL[prec], what=("pairs", "contacts", "islands", "state"))
+        assert not bad, (s, bad[:4])
+    b.close()

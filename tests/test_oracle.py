@@ -266,3 +266,56 @@ def test_kinematic_bodies_vs_reference(prec):
     st = b.get_state()
     assert np.array_equal(st["lvel"][:, 0], v0) and abs(st["pos"][0, 0, 2] - 0.5) < 1e-6      # the platform did not react
     assert st["pos"][0, 1, 0] > -0.6 + 0.2                                                    # and carried its load along
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_geom_offsets_vs_reference(prec):
+    """dGeomSetOffsetPosition / dGeomSetOffsetQuaternion: composite bodies (several geoms per body at offset poses), pair sets, contacts
+    and trajectories of the restatement against the compiled reference."""
+    ref = ref_lib(prec)
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    sc = scenes.composite(2)
+    a, b = B.Batch(ref, sc), B.Batch(orc_lib(prec), sc)
+    ncont = 0
+    for s in range(200):
+        a.step(0.01)
+        b.step(0.01)
+        bad = compare_step(a, b, sc.nworlds)
+        assert not bad, (s, bad[:4])
+        ncont += len(b.get_contacts(0)[1])
+    assert ncont > 200
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("space,levels", [(B.SPACE_HASH, None), (B.SPACE_HASH, (-1, 0)), (B.SPACE_HASH, (0, 4)), (B.SPACE_SIMPLE, None), (B.SPACE_SAP, None)])
+def test_broadphase_callback_stream_vs_reference(prec, space, levels):
+    """Pair sets of the three spaces around the origin, where the hash space's negative-z cell addresses wrap (collision_space.cpp:499,
+    :533) and it reports fewer pairs than the simple space: the restatement's set against the compiled reference's callback stream,
+    with default and dHashSpaceSetLevels levels (min level clamp, big-box list)."""
+    ref = ref_lib(prec)
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    sc = scenes.scatter(24, space_type=space, levels=levels)
+    a, b = B.Batch(ref, sc), B.Batch(orc_lib(prec), sc)
+    npairs = 0
+    for s in range(12):
+        a.step(0.02)
+        b.step(0.02)
+        bad = compare_step(a, b, sc.nworlds, what=("pairs", "contacts"))
+        assert not bad, (s, bad[:4])
+        npairs += sum(len(b.get_pairs(w)) for w in range(sc.nworlds))
+    assert npairs > 2000
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_hash_space_is_a_strict_subset_of_simple_space_here(prec):
+    """The scatter scene does exercise the wrap: the hash space's set is smaller than the simple space's on the same geoms."""
+    counts = {}
+    for space in (B.SPACE_HASH, B.SPACE_SIMPLE):
+        sc = scenes.scatter(24, space_type=space)
+        b = B.Batch(orc_lib(prec), sc)
+        b.step(0.02)
+        counts[space] = [set(map(tuple, b.get_pairs(w))) for w in range(sc.nworlds)]
+    assert all(h <= s for h, s in zip(counts[B.SPACE_HASH], counts[B.SPACE_SIMPLE]))
+    assert sum(len(s) - len(h) for h, s in zip(counts[B.SPACE_HASH], counts[B.SPACE_SIMPLE])) > 0
