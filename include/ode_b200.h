@@ -40,7 +40,7 @@ typedef float odeb_real;
 /* geom classes: numbering of the reference (include/ode/collision.h:881-902) */
 enum { ODEB_SPHERE = 0, ODEB_BOX = 1, ODEB_CAPSULE = 2, ODEB_PLANE = 4 };
 /* joint types: numbering of the reference dJointType (include/ode/common.h:406-426) */
-enum { ODEB_JOINT_BALL = 1, ODEB_JOINT_HINGE = 2, ODEB_JOINT_SLIDER = 3, ODEB_JOINT_CONTACT = 4, ODEB_JOINT_UNIVERSAL = 5, ODEB_JOINT_HINGE2 = 6, ODEB_JOINT_FIXED = 7 };
+enum { ODEB_JOINT_BALL = 1, ODEB_JOINT_HINGE = 2, ODEB_JOINT_SLIDER = 3, ODEB_JOINT_CONTACT = 4, ODEB_JOINT_UNIVERSAL = 5, ODEB_JOINT_HINGE2 = 6, ODEB_JOINT_FIXED = 7, ODEB_JOINT_AMOTOR = 9, ODEB_JOINT_LMOTOR = 10 };
 /* broadphase flavours: which reference space's callback stream is reproduced (as a set).
  * HASH: dxHashSpace::collide collision_space.cpp:421-614 -- AABB-overlapping pairs that the cell walk brings together (a pair whose
  *       shared cells are all reached through differently wrapped hash addresses is not reported, see DESIGN.md "hash space");
@@ -121,12 +121,19 @@ typedef struct OdebJointDesc {
     int    body1, body2;        /* dJointAttach(j, body1, body2); -1 = the static environment */
     double anchor[3];           /* dJointSet*Anchor, world frame at the template pose */
     double axis1[3], axis2[3];  /* dJointSetHingeAxis / dJointSetUniversalAxis1,2 */
-    double lo_stop[2], hi_stop[2]; /* dParamLoStop/HiStop (axis 1, axis 2); defaults -inf/+inf */
-    double vel[2], fmax[2];     /* dParamVel, dParamFMax; default 0 */
-    double fudge_factor[2], bounce[2], stop_erp[2], stop_cfm[2]; /* <0 = keep defaults */
+    double lo_stop[3], hi_stop[3]; /* dParamLoStop/HiStop (axis 1, axis 2, axis 3: the dParam*, dParam*2, dParam*3 groups); defaults -inf/+inf */
+    double vel[3], fmax[3];     /* dParamVel, dParamFMax; default 0 */
+    double fudge_factor[3], bounce[3], stop_erp[3], stop_cfm[3]; /* <0 = keep defaults */
     double susp_erp, susp_cfm;  /* ODEB_JOINT_HINGE2: dParamSuspensionERP / dParamSuspensionCFM, <0 = the world's ERP / CFM.
                                    Hinge2 = dJointSetHinge2Anchor(anchor) + dJointSetHinge2Axes(axis1, axis2), needs both bodies;
                                    stops / motor of axis 1 and the motor of axis 2 are the [0] / [1] entries above */
+    /* ODEB_JOINT_LMOTOR (lmotor.cpp) / ODEB_JOINT_AMOTOR (amotor.cpp): dJointSet{L,A}MotorNumAxes, dJointSetAMotorMode (0 = dAMotorUser,
+     * 1 = dAMotorEuler: 3 axes, axis 0 relative to body 1 and axis 2 relative to body 2), dJointSet{L,A}MotorAxis(anum, rel, x, y, z) with the
+     * axis given in the world frame at the template pose and rel = 0 global / 1 body1 / 2 body2, dJointSetAMotorAngle (user mode).
+     * Motor velocity / force and the stops of axis k are the [k] entries above (stops only act on AMotor axes). */
+    int    motor_num, motor_mode, motor_rel[3];
+    double motor_axis[3][3];
+    double motor_angle[3];
 } OdebJointDesc;
 
 /* per-world counters of dWorldQuickStepIterationCount_DynamicAdjustmentStatistics

@@ -17,7 +17,7 @@
  * getters return pointers into library storage (ode.cpp:413-484).  There is no CPU implementation of any of these
  * stages: without a CUDA device dWorldQuickStep returns 0 and dSpaceCollide reports through the error handler.
  *
- * Outside the subset (calls are not exported): dWorldStep, joints other than contact/ball/hinge/slider/universal/hinge2/fixed, geoms other
+ * Outside the subset (calls are not exported): dWorldStep, joints other than contact/ball/hinge/slider/universal/hinge2/fixed/amotor/lmotor, geoms other
  * than sphere/box/capsule/plane, nested spaces, per-body
  * auto-disable thresholds (the world's are used), SAP axis orders other than dSAP_AXES_XYZ.
  */
@@ -253,6 +253,24 @@ void dJointSetHinge2Axes(dJointID, const dReal *axis1, const dReal *axis2);
 void dJointSetHinge2Axis1(dJointID, dReal x, dReal y, dReal z);
 void dJointSetHinge2Axis2(dJointID, dReal x, dReal y, dReal z);
 void dJointSetHinge2Param(dJointID, int parameter, dReal value);
+enum { dAMotorUser = 0, dAMotorEuler = 1 };                      /* include/ode/common.h:500-503 */
+dJointID dJointCreateLMotor(dWorldID, dJointGroupID);           /* joints/lmotor.cpp */
+void dJointSetLMotorNumAxes(dJointID, int num);
+int dJointGetLMotorNumAxes(dJointID);
+void dJointSetLMotorAxis(dJointID, int anum, int rel, dReal x, dReal y, dReal z);
+void dJointGetLMotorAxis(dJointID, int anum, dVector3 result);
+void dJointSetLMotorParam(dJointID, int parameter, dReal value);
+dJointID dJointCreateAMotor(dWorldID, dJointGroupID);           /* joints/amotor.cpp */
+void dJointSetAMotorMode(dJointID, int mode);
+int dJointGetAMotorMode(dJointID);
+void dJointSetAMotorNumAxes(dJointID, int num);
+int dJointGetAMotorNumAxes(dJointID);
+void dJointSetAMotorAxis(dJointID, int anum, int rel, dReal x, dReal y, dReal z);
+void dJointGetAMotorAxis(dJointID, int anum, dVector3 result);
+int dJointGetAMotorAxisRel(dJointID, int anum);
+void dJointSetAMotorAngle(dJointID, int anum, dReal angle);
+dReal dJointGetAMotorAngle(dJointID, int anum);                 /* user mode: the angle that was set */
+void dJointSetAMotorParam(dJointID, int parameter, dReal value);
 dJointID dJointCreateSlider(dWorldID, dJointGroupID);           /* joints/slider.cpp */
 void dJointSetSliderAxis(dJointID, dReal x, dReal y, dReal z);
 void dJointGetSliderAxis(dJointID, dVector3 result);

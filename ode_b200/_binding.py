@@ -45,11 +45,13 @@ class OdebGeomDesc(C.Structure):
 class OdebJointDesc(C.Structure):
     _fields_ = [("type", C.c_int), ("body1", C.c_int), ("body2", C.c_int),
                 ("anchor", C.c_double * 3), ("axis1", C.c_double * 3), ("axis2", C.c_double * 3),
-                ("lo_stop", C.c_double * 2), ("hi_stop", C.c_double * 2),
-                ("vel", C.c_double * 2), ("fmax", C.c_double * 2),
-                ("fudge_factor", C.c_double * 2), ("bounce", C.c_double * 2),
-                ("stop_erp", C.c_double * 2), ("stop_cfm", C.c_double * 2),
-                ("susp_erp", C.c_double), ("susp_cfm", C.c_double)]
+                ("lo_stop", C.c_double * 3), ("hi_stop", C.c_double * 3),
+                ("vel", C.c_double * 3), ("fmax", C.c_double * 3),
+                ("fudge_factor", C.c_double * 3), ("bounce", C.c_double * 3),
+                ("stop_erp", C.c_double * 3), ("stop_cfm", C.c_double * 3),
+                ("susp_erp", C.c_double), ("susp_cfm", C.c_double),
+                ("motor_num", C.c_int), ("motor_mode", C.c_int), ("motor_rel", C.c_int * 3),
+                ("motor_axis", (C.c_double * 3) * 3), ("motor_angle", C.c_double * 3)]
 
 
 class OdebStats(C.Structure):
@@ -58,6 +60,8 @@ class OdebStats(C.Structure):
 
 SPHERE, BOX, CAPSULE, PLANE = 0, 1, 2, 4
 JOINT_BALL, JOINT_HINGE, JOINT_SLIDER, JOINT_CONTACT, JOINT_UNIVERSAL, JOINT_HINGE2, JOINT_FIXED = 1, 2, 3, 4, 5, 6, 7
+JOINT_AMOTOR, JOINT_LMOTOR = 9, 10
+AMOTOR_USER, AMOTOR_EULER = 0, 1
 SPACE_HASH, SPACE_SAP, SPACE_SIMPLE = 0, 1, 2
 CONTACT_MU2, CONTACT_BOUNCE, CONTACT_SOFT_ERP, CONTACT_SOFT_CFM = 0x001, 0x004, 0x008, 0x010
 CONTACT_MOTION1, CONTACT_MOTION2, CONTACT_MOTIONN = 0x020, 0x040, 0x080
@@ -125,23 +129,33 @@ class Scene:
         self.geoms.append(g)
         return len(self.geoms) - 1
 
-    def add_joint(self, jtype, body1, body2, anchor, axis1=(1, 0, 0), axis2=(0, 1, 0),
+    def add_joint(self, jtype, body1, body2, anchor=(0, 0, 0), axis1=(1, 0, 0), axis2=(0, 1, 0),
                   lo_stop=(-INF, -INF), hi_stop=(INF, INF), vel=(0, 0), fmax=(0, 0),
-                  fudge_factor=(-1, -1), bounce=(-1, -1), stop_erp=(-1, -1), stop_cfm=(-1, -1), susp_erp=-1.0, susp_cfm=-1.0):
+                  fudge_factor=(-1, -1), bounce=(-1, -1), stop_erp=(-1, -1), stop_cfm=(-1, -1), susp_erp=-1.0, susp_cfm=-1.0,
+                  motor_axes=(), motor_mode=0, motor_angle=(0, 0, 0)):
+        """motor_axes (LMotor / AMotor): up to three (rel, (x, y, z)) entries; the per-axis limit-motor tuples then take up to 3 values."""
+        def pad(v, fill):
+            v = tuple(v)
+            return v + (fill,) * (3 - len(v))
         j = OdebJointDesc()
         j.type, j.body1, j.body2 = jtype, body1, body2
         j.anchor[:] = anchor
         j.axis1[:] = axis1
         j.axis2[:] = axis2
-        j.lo_stop[:] = lo_stop
-        j.hi_stop[:] = hi_stop
-        j.vel[:] = vel
-        j.fmax[:] = fmax
-        j.fudge_factor[:] = fudge_factor
-        j.bounce[:] = bounce
-        j.stop_erp[:] = stop_erp
-        j.stop_cfm[:] = stop_cfm
+        j.lo_stop[:] = pad(lo_stop, -INF)
+        j.hi_stop[:] = pad(hi_stop, INF)
+        j.vel[:] = pad(vel, 0)
+        j.fmax[:] = pad(fmax, 0)
+        j.fudge_factor[:] = pad(fudge_factor, -1)
+        j.bounce[:] = pad(bounce, -1)
+        j.stop_erp[:] = pad(stop_erp, -1)
+        j.stop_cfm[:] = pad(stop_cfm, -1)
         j.susp_erp, j.susp_cfm = susp_erp, susp_cfm
+        j.motor_num, j.motor_mode = len(motor_axes), motor_mode
+        for k, (rel, ax) in enumerate(motor_axes):
+            j.motor_rel[k] = rel
+            j.motor_axis[k][:] = ax
+        j.motor_angle[:] = motor_angle
         self.joints.append(j)
         return len(self.joints) - 1
 

@@ -389,6 +389,7 @@ static void joint_set_relative_values(dxJoint *j)
 {   // dxJoint*::setRelativeValues (ball.cpp:179-185, hinge.cpp:359-369, universal.cpp:785-808): called by dJointAttach
     DJointT &t = j->t;
     if (j->type == dJointTypeContact || j->type == dJointTypeFixed) return;     // dxJointFixed keeps offset / qrel until dJointSetFixed
+    if (j->type == dJointTypeAMotor || j->type == dJointTypeLMotor) return;     // no setRelativeValues override (joints/joint.cpp:68-71)
     if (j->type == dJointTypeHinge2) {                                          // hinge2.cpp:517-536: anchor, both axes, v1/v2 from the new bodies
         Real anchor[3] = { 0, 0, 0 }, a1[3] = { 0, 0, 0 }, a2[3] = { 0, 0, 0 };
         if (!j->body[0] || !j->body[1]) return;
@@ -462,7 +463,7 @@ static dxJoint *new_joint(dxWorld *w, dxJointGroup *g, int type)
 #else
     j->t.cfm = w->wp.cfm >= 0 ? (Real)w->wp.cfm : R_(1e-5);
 #endif
-    limot_init(j->t.limot1, w); limot_init(j->t.limot2, w);
+    limot_init(j->t.limot1, w); limot_init(j->t.limot2, w); limot_init(j->t.limot3, w);
     if (type == dJointTypeHinge) { j->t.axis1[0] = 1; j->t.axis2[0] = 1; }
     if (type == dJointTypeSlider) j->t.axis1[0] = 1;
     if (type == dJointTypeHinge2) { j->t.axis1[0] = 1; j->t.axis2[1] = 1; j->t.qrel1[0] = 1; j->t.qrel2[1] = 1; j->t.qrel[2] = j->t.erp; j->t.qrel[3] = j->t.cfm; }   // hinge2.cpp:76-100
@@ -806,6 +807,58 @@ void dJointSetHinge2Param(dJointID j, int parameter, Real value)
     else if (parameter == dParamSuspensionCFM) j->t.qrel[3] = value;
     else limot_set(j->t.limot1, parameter, value);
 }
+// ---- linear / angular motors (joints/lmotor.cpp, joints/amotor.cpp)
+static DLimot &motor_limot(dxJoint *j, int anum) { return anum <= 0 ? j->t.limot1 : anum == 1 ? j->t.limot2 : j->t.limot3; }
+static void motor_set_axis(dxJoint *j, int anum, int rel, Real x, Real y, Real z)
+{
+    if (anum < 0) anum = 0;
+    if (anum > 2) anum = 2;
+    std::vector<HostBody> hb = joint_bodies(j, j->t);
+    j->t.reverse = j->reverse;
+    host_motor_set_axis(hb, j->t, anum, rel, x, y, z);
+    if (j->type == dJointTypeAMotor && j->t.mmode == dAMotorEuler) host_amotor_euler_references(hb, j->t);
+   
+}
+static void motor_get_axis(dxJoint *j, int anum, Real *result)
+{   // dJointGetLMotorAxis lmotor.cpp:196-205 returns the stored axis; dxJointAMotor::doGetUserAxis amotor.cpp:471-493 rotates it into the world frame
+    if (anum < 0) anum = 0;
+    if (anum > 2) anum = 2;
+    const Real *a = j->t.maxis[anum];
+    result[0] = a[0]; result[1] = a[1]; result[2] = a[2];
+    if (j->type == dJointTypeAMotor && j->t.mmode == dAMotorUser) {
+        if (j->t.mrel[anum] == 1 && j->body[0]) mul0_331(result, j->body[0]->R, a);
+        else if (j->t.mrel[anum] == 2 && j->body[1]) mul0_331(result, j->body[1]->R, a);
+    }
+}
+dJointID dJointCreateLMotor(dWorldID w, dJointGroupID g) { return new_joint(w, g, dJointTypeLMotor); }
+void dJointSetLMotorNumAxes(dJointID j, int num) { j->t.mnum = num < 0 ? 0 : num > 3 ? 3 : num; }
+int dJointGetLMotorNumAxes(dJointID j) { return j->t.mnum; }
+void dJointSetLMotorAxis(dJointID j, int anum, int rel, Real x, Real y, Real z) { motor_set_axis(j, anum, rel, x, y, z); }
+void dJointGetLMotorAxis(dJointID j, int anum, Real *result) { motor_get_axis(j, anum, result); }
+void dJointSetLMotorParam(dJointID j, int parameter, Real value) { limot_set(motor_limot(j, parameter >> 8), parameter & 0xff, value); }
+dJointID dJointCreateAMotor(dWorldID w, dJointGroupID g) { return new_joint(w, g, dJointTypeAMotor); }
+void dJointSetAMotorMode(dJointID j, int mode)
+{   // dxJointAMotor::setOperationMode amotor.cpp:354-363
+    j->t.mmode = mode;
+    if (mode == dAMotorEuler) {
+        j->t.mnum = 3;
+        if (j->body[0]) { std::vector<HostBody> hb = joint_bodies(j, j->t); j->t.reverse = j->reverse; host_amotor_euler_references(hb, j->t); }
+    }
+   
+}
+int dJointGetAMotorMode(dJointID j) { return j->t.mmode; }
+void dJointSetAMotorNumAxes(dJointID j, int num) { j->t.mnum = j->t.mmode == dAMotorEuler ? 3 : (num < 0 ? 0 : num > 3 ? 3 : num); }
+int dJointGetAMotorNumAxes(dJointID j) { return j->t.mnum; }
+void dJointSetAMotorAxis(dJointID j, int anum, int rel, Real x, Real y, Real z) { motor_set_axis(j, anum, rel, x, y, z); }
+void dJointGetAMotorAxis(dJointID j, int anum, Real *result) { motor_get_axis(j, anum, result); }
+int dJointGetAMotorAxisRel(dJointID j, int anum)
+{   // getAxisBodyRelativity amotor.cpp:380-390
+    int rel = j->t.mrel[anum < 0 ? 0 : anum > 2 ? 2 : anum];
+    return (rel != 0 && j->reverse) ? 3 - rel : rel;
+}
+void dJointSetAMotorAngle(dJointID j, int anum, Real angle) { if (j->t.mmode == dAMotorUser) { j->t.mangle[anum < 0 ? 0 : anum > 2 ? 2 : anum] = angle; } }
+Real dJointGetAMotorAngle(dJointID j, int anum) { return j->t.mangle[anum < 0 ? 0 : anum > 2 ? 2 : anum]; }     // user mode: the value that was set
+void dJointSetAMotorParam(dJointID j, int parameter, Real value) { limot_set(motor_limot(j, parameter >> 8), parameter & 0xff, value); }
 dJointID dJointCreateSlider(dWorldID w, dJointGroupID g) { return new_joint(w, g, dJointTypeSlider); }
 void dJointSetSliderAxis(dJointID j, Real x, Real y, Real z)
 {   // slider.cpp:249-260

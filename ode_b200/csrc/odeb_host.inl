@@ -141,6 +141,36 @@ static void host_limot(DLimot &l, Real erp, Real cfm, const OdebJointDesc &d, in
 }
 
 
+// dJointSetLMotorAxis lmotor.cpp:118-160 / dxJointAMotor::setAxisValue amotor.cpp:393-442 (x, y, z in the world frame)
+static void host_motor_set_axis(const std::vector<HostBody> &hb, DJointT &j, int anum, int rel, Real x, Real y, Real z)
+{
+    if (j.type == ODEB_JOINT_LMOTOR) { if (j.b1 < 0 && rel == 2) rel = 1; }
+    else if (rel != 0 && j.reverse) rel = 3 - rel;
+    j.mrel[anum] = rel;
+    Real r[3] = { x, y, z }, *a = j.maxis[anum];
+    if (rel == 1) mul1_331(a, hb[j.b0].R, r);
+    else if (rel == 2 && j.b1 >= 0) mul1_331(a, hb[j.b1].R, r);
+    else { a[0] = x; a[1] = y; a[2] = z; }
+    a[3] = 0;
+    normalize3(a);
+}
+// dxJointAMotor::setEulerReferenceVectors amotor.cpp:768-796
+static void host_amotor_euler_references(const std::vector<HostBody> &hb, DJointT &j)
+{
+    const int first = j.reverse ? 2 : 0, second = 2 - first;
+    if (j.b1 >= 0) {
+        Real r[3];
+        mul0_331(r, hb[j.b0].R, j.maxis[first]);
+        mul1_331(j.mref[1], hb[j.b1].R, r);
+        mul0_331(r, hb[j.b1].R, j.maxis[second]);
+        mul1_331(j.mref[0], hb[j.b0].R, r);
+    } else {
+        mul0_331(j.mref[1], hb[j.b0].R, j.maxis[first]);
+        mul1_331(j.mref[0], hb[j.b0].R, j.maxis[second]);
+    }
+    j.mref[0][3] = j.mref[1][3] = 0;
+}
+
 // hinge.cpp:376-393 computeInitialRelativeRotation
 static void host_hinge_initial_rotation(const std::vector<HostBody> &hb, DJointT &j)
 {
@@ -520,7 +550,7 @@ OdebBatch *odeb_create(const OdebWorldParams *wp,
         const OdebJointDesc &d = joints[i];
         DJointT &j = T.jt[i];
         memset(&j, 0, sizeof(j));
-        if (d.type != ODEB_JOINT_BALL && d.type != ODEB_JOINT_HINGE && d.type != ODEB_JOINT_UNIVERSAL && d.type != ODEB_JOINT_FIXED && d.type != ODEB_JOINT_SLIDER && d.type != ODEB_JOINT_HINGE2) { set_err("joint %d: unsupported type %d", i, d.type); return 0; }
+        if (d.type != ODEB_JOINT_BALL && d.type != ODEB_JOINT_HINGE && d.type != ODEB_JOINT_UNIVERSAL && d.type != ODEB_JOINT_FIXED && d.type != ODEB_JOINT_SLIDER && d.type != ODEB_JOINT_HINGE2 && d.type != ODEB_JOINT_AMOTOR && d.type != ODEB_JOINT_LMOTOR) { set_err("joint %d: unsupported type %d", i, d.type); return 0; }
         j.type = d.type; j.erp = erp; j.cfm = cfm;
         int b1 = d.body1, b2 = d.body2;
         if (b1 >= nbody || b2 >= nbody || (b1 < 0 && b2 < 0) || b1 == b2) { set_err("joint %d: bad bodies", i); return 0; }
@@ -531,7 +561,20 @@ OdebBatch *odeb_create(const OdebWorldParams *wp,
         host_set_anchors(hb, j, (Real)d.anchor[0], (Real)d.anchor[1], (Real)d.anchor[2]);
         host_limot(j.limot1, erp, cfm, d, 0);
         host_limot(j.limot2, erp, cfm, d, 1);
-        if (j.type == ODEB_JOINT_HINGE2) {
+        host_limot(j.limot3, erp, cfm, d, 2);
+        if (j.type == ODEB_JOINT_LMOTOR || j.type == ODEB_JOINT_AMOTOR) {
+            // dJointSet{L,A}MotorNumAxes, dJointSetAMotorMode (amotor.cpp:354-377: Euler mode has 3 axes, axis 1 derived), axes, user angles
+            const bool am = j.type == ODEB_JOINT_AMOTOR;
+            if (d.motor_num < 0 || d.motor_num > 3) { set_err("joint %d: motor_num must be 0..3", i); return 0; }
+            j.mmode = am ? d.motor_mode : 0;
+            j.mnum = (am && j.mmode == 1) ? 3 : d.motor_num;
+            for (int k = 0; k < d.motor_num; k++) {
+                if (am && j.mmode == 1 && k == 1) continue;
+                host_motor_set_axis(hb, j, k, d.motor_rel[k], (Real)d.motor_axis[k][0], (Real)d.motor_axis[k][1], (Real)d.motor_axis[k][2]);
+            }
+            if (am && j.mmode == 1) host_amotor_euler_references(hb, j);
+            for (int k = 0; k < 3; k++) j.mangle[k] = am ? (Real)d.motor_angle[k] : 0;
+        } else if (j.type == ODEB_JOINT_HINGE2) {
             if (j.b1 < 0 || j.reverse) { set_err("joint %d: a hinge2 joint needs two bodies", i); return 0; }
             j.axis1[0] = 1; j.axis2[1] = 1;                       // hinge2.cpp:76-100
             host_set_axes(hb, j, (Real)d.axis1[0], (Real)d.axis1[1], (Real)d.axis1[2], j.axis1, 0);

@@ -20,9 +20,14 @@ struct DJointT {    // template (per-batch) description of a permanent joint, af
     // fixed / slider: anchor1 = offset. hinge2: qrel = {c0, s0, susp_erp, susp_cfm}, qrel1 = v1, qrel2 = v2 (hinge2.cpp:76-100)
     Real erp, cfm;
     DLimot limot1, limot2;
+    // lmotor / amotor (lmotor.h:30-49, amotor.h:91-101): number of axes, mode (0 user, 1 Euler), what each axis is relative to (after the
+    // reverse swap of amotor.cpp:405-409), axes, Euler reference vectors, user-mode angles, third limit motor
+    int mnum, mmode, mrel[3];
+    Real maxis[3][4], mref[2][4], mangle[3];
+    DLimot limot3;
 };
 
-struct DLimitState { int limit1, limit2; Real err1, err2; };
+struct DLimitState { int limit1, limit2; Real err1, err2; int limit3; Real err3; };
 
 __host__ __device__ __forceinline__ void odeb_qmul3(Real *qa, const Real *qb, const Real *qc)
 {   // dQMultiply3 rotation.cpp:221-228
@@ -230,10 +235,62 @@ __device__ void odeb_universal_angles(const DJointT &j, const DBody &b0, const D
     *angle2 = -odeb_hinge_angle_from_relq(qrel, j.axis2);
 }
 
+// dxJointLMotor::computeGlobalAxes lmotor.cpp:51-76 / dxJointAMotor::doComputeGlobalUserAxes, doComputeGlobalEulerAxes amotor.cpp:662-713
+__device__ void odeb_motor_global_axes(const DJointT &j, const DBody &b0, const DBody *b1, Real ax[3][3])
+{
+    for (int i = 0; i < 3; i++) ax[i][0] = ax[i][1] = ax[i][2] = 0;
+    if (j.type == 9 && j.mmode == 1) {
+        const int first = j.reverse ? 2 : 0, second = 2 - first;     // BuildFirstBodyEulerAxis amotor.cpp:798-807
+        mul0_331(ax[first], b0.R, j.maxis[first]);
+        if (b1) mul0_331(ax[second], b1->R, j.maxis[second]);
+        else { ax[second][0] = j.maxis[second][0]; ax[second][1] = j.maxis[second][1]; ax[second][2] = j.maxis[second][2]; }
+        cross3(ax[1], ax[2], ax[0]);
+        normalize3(ax[1]);
+        return;
+    }
+    for (int i = 0; i < j.mnum; i++) {
+        if (j.mrel[i] == 1) mul0_331(ax[i], b0.R, j.maxis[i]);
+        else if (j.mrel[i] == 2 && b1) mul0_331(ax[i], b1->R, j.maxis[i]);
+        else if (j.mrel[i] == 2 && j.type == 10) { }                  // lmotor.cpp:61-66: left as it is
+        else { ax[i][0] = j.maxis[i][0]; ax[i][1] = j.maxis[i][1]; ax[i][2] = j.maxis[i][2]; }
+    }
+}
+
 // getInfo1 of hinge (hinge.cpp:54-74) and universal (universal.cpp:266-293): row count + limit state
 __device__ void odeb_joint_info1(const DJointT &j, const DBody &b0, const DBody *b1, int *m, DLimitState *ls)
 {
-    ls->limit1 = ls->limit2 = 0; ls->err1 = ls->err2 = 0;
+    ls->limit1 = ls->limit2 = ls->limit3 = 0; ls->err1 = ls->err2 = ls->err3 = 0;
+    if (j.type == 10) {                            // lmotor.cpp:84-97
+        int mm = 0;
+        if (j.mnum > 0 && j.limot1.fmax > 0) mm++;
+        if (j.mnum > 1 && j.limot2.fmax > 0) mm++;
+        if (j.mnum > 2 && j.limot3.fmax > 0) mm++;
+        *m = mm;
+        return;
+    }
+    if (j.type == 9) {                             // amotor.cpp:264-287, computeEulerAngles :716-758
+        Real ang[3] = { j.mangle[0], j.mangle[1], j.mangle[2] };
+        if (j.mmode == 1) {
+            Real ax[3][3], refs[2][3], q[3];
+            odeb_motor_global_axes(j, b0, b1, ax);
+            mul0_331(refs[0], b0.R, j.mref[0]);
+            if (b1) mul0_331(refs[1], b1->R, j.mref[1]);
+            else { refs[1][0] = j.mref[1][0]; refs[1][1] = j.mref[1][1]; refs[1][2] = j.mref[1][2]; }
+            const int fb = j.reverse ? 1 : 0, sb = 1 - fb;
+            cross3(q, ax[0], refs[fb]);
+            ang[0] = -RATAN2(dot3(ax[2], q), dot3(ax[2], refs[fb]));
+            cross3(q, ax[0], ax[1]);
+            ang[1] = -RATAN2(dot3(ax[2], ax[0]), dot3(ax[2], q));
+            cross3(q, ax[1], ax[2]);
+            ang[2] = -RATAN2(dot3(refs[sb], ax[1]), dot3(refs[sb], q));
+        }
+        int mm = 0;
+        if (j.mnum > 0 && (odeb_limot_test(j.limot1, ang[0], &ls->limit1, &ls->err1) || j.limot1.fmax > 0)) mm++;
+        if (j.mnum > 1 && (odeb_limot_test(j.limot2, ang[1], &ls->limit2, &ls->err2) || j.limot2.fmax > 0)) mm++;
+        if (j.mnum > 2 && (odeb_limot_test(j.limot3, ang[2], &ls->limit3, &ls->err3) || j.limot3.fmax > 0)) mm++;
+        *m = mm;
+        return;
+    }
     if (j.type == 1) { *m = 3; return; }
     if (j.type == 7) { *m = 6; return; }           // fixed.cpp:52-57
     if (j.type == 6) {                             // hinge2.cpp:110-130 (needs both bodies)
@@ -301,6 +358,36 @@ __device__ void odeb_set_fixed_orientation(const DBody &b0, const DBody *b1, Rea
 __device__ void odeb_joint_info2(const DJointT &j, const DLimitState &ls, const DBody &b0, const DBody *b1,
                                  Real fps, Real worldERP, Real *row, Real *tq, bool *has_tq, Real *fq, Real *tboth, bool *has_f)
 {
+    if (j.type == 10) {  // lmotor.cpp:99-116: one linear limit-motor row per powered axis (no stops: the limit state is never set)
+        Real ax[3][3];
+        odeb_motor_global_axes(j, b0, b1, ax);
+        int r = 0;
+        for (int i = 0; i < j.mnum; i++) {
+            const DLimot &l = i == 0 ? j.limot1 : i == 1 ? j.limot2 : j.limot3;
+            Real f[3], tb[3]; bool hf = false;
+            if (odeb_add_limot_linear(l, 0, 0, b0, b1, fps, row + r * ROWLEN, ax[i], f, tb, &hf)) r++;
+        }
+        return;
+    }
+    if (j.type == 9) {   // amotor.cpp:290-339: Euler mode constrains along ax1 x ax2, ax1, ax0 x ax1
+        Real ax[3][3], c01[3], c12[3];
+        odeb_motor_global_axes(j, b0, b1, ax);
+        const Real *axp[3] = { ax[0], ax[1], ax[2] };
+        if (j.mmode == 1) {
+            cross3(c01, ax[0], ax[1]); axp[2] = c01;
+            cross3(c12, ax[1], ax[2]); axp[0] = c12;
+        }
+        int r = 0;
+        for (int i = 0; i < j.mnum; i++) {
+            const DLimot &l = i == 0 ? j.limot1 : i == 1 ? j.limot2 : j.limot3;
+            const int lim = i == 0 ? ls.limit1 : i == 1 ? ls.limit2 : ls.limit3;
+            const Real err = i == 0 ? ls.err1 : i == 1 ? ls.err2 : ls.err3;
+            Real t[3]; bool ht = false;
+            if (odeb_add_limot(l, lim, err, b0, b1, fps, row + r * ROWLEN, axp[i], t, &ht)) r++;
+            if (ht) { tq[0] += t[0]; tq[1] += t[1]; tq[2] += t[2]; *has_tq = true; }
+        }
+        return;
+    }
     if (j.type == 6) {   // hinge2.cpp:155-209 with setBall2 joints/joint.cpp:165-213 (two-body form)
         Real ax1[3], ax2[3], q[3];
         mul0_331(ax1, b0.R, j.axis1);

@@ -288,6 +288,55 @@ def composite(nworlds=1, seed0=81):
     return sc
 
 
+def motors(nworlds=1, seed0=91, dynamic_iterations=True):
+    """Linear and angular motors (lmotor.cpp, amotor.cpp): a box driven along a global and a body-relative axis by an LMotor to the
+    world; a two-link arm (ball joints) whose elbow carries an Euler-mode AMotor with stops, bounce and a powered middle axis; a
+    ball-jointed pair with a user-mode AMotor (axes relative to body 1 / body 2 / global, one axis powered at its stop, one with
+    lo == hi); an Euler AMotor and an LMotor attached as (world, body), i.e. with dJOINT_REVERSE; a 3-axis LMotor between two free boxes."""
+    kw = dict(gravity=(0, 0, -9.81), max_contacts=4, surf_mode=B.CONTACT_APPROX1, mu=0.6, skip_connected=1)
+    if not dynamic_iterations:      # dWorldSetQuickStepDynamicIterationParameters(w, 0, 0, ...): always exactly num_iterations sweeps
+        kw.update(premature_exit_delta=0.0, max_extra_factor=0.0)
+    sc = B.Scene(B.default_world_params(**kw), nworlds)
+    sc.add_geom(B.PLANE, (0, 0, 1, 0))
+    m, I = B.box_mass(2.0, 0.4, 0.3, 0.2)
+
+    def box(pos):
+        b = sc.add_body(m, I, pos)
+        sc.add_geom(B.BOX, (0.4, 0.3, 0.2), body=b)
+        return b
+    b0 = box((0, 0, 0.1))
+    sc.add_joint(B.JOINT_LMOTOR, b0, -1, motor_axes=((0, (1, 0, 0)), (1, (0, 1, 0))), vel=(0.5, -0.2), fmax=(8.0, 3.0))
+    b1, b2 = box((2, 0, 1.0)), box((2.6, 0, 1.0))
+    sc.add_joint(B.JOINT_BALL, b1, -1, (1.7, 0, 1.0))
+    sc.add_joint(B.JOINT_BALL, b1, b2, (2.3, 0, 1.0))
+    sc.add_joint(B.JOINT_AMOTOR, b1, b2, motor_mode=B.AMOTOR_EULER, motor_axes=((1, (1, 0, 0)), (0, (0, 1, 0)), (2, (0, 0, 1))),
+                 lo_stop=(-0.3, -0.25, -0.4), hi_stop=(0.3, 0.25, 0.4), vel=(0, 0.5, 0), fmax=(0, 2.0, 0), bounce=(0.2, -1, 0.1))
+    b3, b4 = box((4, 0, 1.0)), box((4, 0.6, 1.0))
+    sc.add_joint(B.JOINT_BALL, b3, b4, (4, 0.3, 1.0))
+    sc.add_joint(B.JOINT_AMOTOR, b3, b4, motor_mode=B.AMOTOR_USER, motor_axes=((1, (1, 0, 0)), (2, (0, 1, 0)), (0, (0, 0, 1))),
+                 motor_angle=(0.5, 0.0, 0.0), lo_stop=(-0.2, -INF_, 0.0), hi_stop=(0.2, INF_, 0.0), vel=(0.3, -0.2, 0), fmax=(1.0, 1.0, 0),
+                 fudge_factor=(0.5, -1, -1))
+    b5 = box((6, 0, 1.5))
+    sc.add_joint(B.JOINT_AMOTOR, -1, b5, motor_mode=B.AMOTOR_EULER, motor_axes=((1, (1, 0, 0)), (0, (0, 1, 0)), (2, (0, 0, 1))),
+                 lo_stop=(-0.2, -0.2, -0.2), hi_stop=(0.2, 0.2, 0.2), stop_erp=(0.5, -1, -1), stop_cfm=(1e-3, -1, -1))
+    b6, b7 = box((8, 0, 0.8)), box((8, 0.5, 1.1))
+    sc.add_joint(B.JOINT_LMOTOR, b6, b7, motor_axes=((0, (0, 0, 1)), (1, (1, 0, 0)), (2, (0, 1, 0))), vel=(0.1, 0.3, -0.3), fmax=(5.0, 2.0, 2.0))
+    b8 = box((10, 0, 0.6))
+    sc.add_joint(B.JOINT_LMOTOR, -1, b8, motor_axes=((2, (1, 1, 0)),), vel=(0.4,), fmax=(6.0,))
+    nb = sc.nbody
+    pos = np.tile(np.asarray(sc.body_pos)[None], (nworlds, 1, 1))
+    quat = np.tile(np.asarray(sc.body_quat)[None], (nworlds, 1, 1))
+    lvel = np.zeros((nworlds, nb, 3))
+    avel = np.zeros((nworlds, nb, 3))
+    for w in range(nworlds):
+        r = _rng(seed0 + w)
+        avel[w] = 3.0 * (r.rand(nb, 3) - 0.5)
+        lvel[w] = 0.3 * (r.rand(nb, 3) - 0.5)
+    sc.state = dict(pos=pos, quat=quat, lvel=lvel, avel=avel)
+    sc.seeds = (seed0 + np.arange(nworlds)).astype(np.uint32)
+    return sc
+
+
 def scatter(nworlds=1, n=40, seed0=300, space_type=B.SPACE_HASH, extent=1.0, levels=None, plane=True):
     """Broadphase exerciser: n spheres / boxes / capsules of sizes 0.05 .. 1.5 (hash levels -3 .. 1) scattered in a cube of half-width
     `extent` around the origin, no gravity, slow drift.  Around the origin the hash space's cell addresses with negative z wrap

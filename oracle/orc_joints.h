@@ -435,9 +435,150 @@ static void slider_info2(World &W, Joint &j, Real fps, Real worldERP, Real *row)
     add_limot_linear(W, j, j.limot1, fps, row + 5 * ROWLEN, ax1);
 }
 
+// ---- linear motor (lmotor.cpp) and angular motor (amotor.cpp)
+static Limot &motor_limot(Joint &j, int i) { return i == 0 ? j.limot1 : i == 1 ? j.limot2 : j.limot3; }
+
+// dxJointLMotor::computeGlobalAxes lmotor.cpp:51-76
+static void lmotor_global_axes(World &W, Joint &j, Real ax[3][3])
+{
+    for (int i = 0; i < j.mnum; i++) {
+        if (j.mrel[i] == 1) mul0_331(ax[i], W.bodies[j.b0].R, j.maxis[i]);
+        else if (j.mrel[i] == 2) { if (j.b1 >= 0) mul0_331(ax[i], W.bodies[j.b1].R, j.maxis[i]); }
+        else { ax[i][0] = j.maxis[i][0]; ax[i][1] = j.maxis[i][1]; ax[i][2] = j.maxis[i][2]; }
+    }
+}
+// dxJointLMotor::getInfo1 lmotor.cpp:84-97
+static void lmotor_info1(World &W, Joint &j)
+{
+    j.m = 0; j.nub = 0;
+    for (int i = 0; i < j.mnum; i++) if (motor_limot(j, i).fmax > 0) j.m++;
+}
+// dxJointLMotor::getInfo2 lmotor.cpp:99-116
+static void lmotor_info2(World &W, Joint &j, Real fps, Real *row)
+{
+    Real ax[3][3] = { { 0 } };
+    lmotor_global_axes(W, j, ax);
+    int r = 0;
+    for (int i = 0; i < j.mnum; i++) if (add_limot_linear(W, j, motor_limot(j, i), fps, row + r * ROWLEN, ax[i])) r++;
+}
+// dJointSetLMotorAxis lmotor.cpp:118-160
+static void lmotor_set_axis(World &W, Joint &j, int anum, int rel, Real x, Real y, Real z)
+{
+    if (j.b1 < 0 && rel == 2) rel = 1;
+    j.mrel[anum] = rel;
+    Real r[3] = { x, y, z };
+    if (rel == 1) mul1_331(j.maxis[anum], W.bodies[j.b0].R, r);
+    else if (rel == 2) mul1_331(j.maxis[anum], W.bodies[j.b1].R, r);
+    else { j.maxis[anum][0] = x; j.maxis[anum][1] = y; j.maxis[anum][2] = z; }
+    normalize3(j.maxis[anum]);
+}
+
+// dxJointAMotor::doComputeGlobalUserAxes / doComputeGlobalEulerAxes amotor.cpp:662-713
+static void amotor_global_axes(World &W, Joint &j, Real ax[3][3])
+{
+    if (j.mmode == 0) {
+        for (int i = 0; i < j.mnum; i++) {
+            bool assigned = false;
+            if (j.mrel[i] == 1) { mul0_331(ax[i], W.bodies[j.b0].R, j.maxis[i]); assigned = true; }
+            else if (j.mrel[i] == 2 && j.b1 >= 0) { mul0_331(ax[i], W.bodies[j.b1].R, j.maxis[i]); assigned = true; }
+            if (!assigned) { ax[i][0] = j.maxis[i][0]; ax[i][1] = j.maxis[i][1]; ax[i][2] = j.maxis[i][2]; }
+        }
+    } else {
+        const int first = j.reverse ? 2 : 0, second = 2 - first;     // BuildFirstBodyEulerAxis :798-807
+        mul0_331(ax[first], W.bodies[j.b0].R, j.maxis[first]);
+        if (j.b1 >= 0) mul0_331(ax[second], W.bodies[j.b1].R, j.maxis[second]);
+        else { ax[second][0] = j.maxis[second][0]; ax[second][1] = j.maxis[second][1]; ax[second][2] = j.maxis[second][2]; }
+        cross3(ax[1], ax[2], ax[0]);
+        normalize3(ax[1]);
+    }
+}
+// dxJointAMotor::computeEulerAngles amotor.cpp:716-758
+static void amotor_euler_angles(World &W, Joint &j, Real ax[3][3])
+{
+    Real refs[2][3], q[3];
+    mul0_331(refs[0], W.bodies[j.b0].R, j.mref[0]);
+    if (j.b1 >= 0) mul0_331(refs[1], W.bodies[j.b1].R, j.mref[1]);
+    else { refs[1][0] = j.mref[1][0]; refs[1][1] = j.mref[1][1]; refs[1][2] = j.mref[1][2]; }
+    const int fb = j.reverse ? 1 : 0, sb = 1 - fb;
+    cross3(q, ax[0], refs[fb]);
+    j.mangle[0] = -RATAN2(dot3(ax[2], q), dot3(ax[2], refs[fb]));
+    cross3(q, ax[0], ax[1]);
+    j.mangle[1] = -RATAN2(dot3(ax[2], ax[0]), dot3(ax[2], q));
+    cross3(q, ax[1], ax[2]);
+    j.mangle[2] = -RATAN2(dot3(refs[sb], ax[1]), dot3(refs[sb], q));
+}
+// dxJointAMotor::getInfo1 amotor.cpp:264-287
+static void amotor_info1(World &W, Joint &j)
+{
+    j.m = 0; j.nub = 0;
+    if (j.mmode == 1) {
+        Real ax[3][3] = { { 0 } };
+        amotor_global_axes(W, j, ax);
+        amotor_euler_angles(W, j, ax);
+    }
+    for (int i = 0; i < j.mnum; i++) {
+        Limot &l = motor_limot(j, i);
+        if (limot_test(l, j.mangle[i]) || l.fmax > 0) j.m++;
+    }
+}
+// dxJointAMotor::getInfo2 amotor.cpp:290-339
+static void amotor_info2(World &W, Joint &j, Real fps, Real *row)
+{
+    Real ax[3][3] = { { 0 } }, c01[3], c12[3];
+    amotor_global_axes(W, j, ax);
+    const Real *axp[3] = { ax[0], ax[1], ax[2] };
+    if (j.mmode == 1) {
+        cross3(c01, ax[0], ax[1]); axp[2] = c01;
+        cross3(c12, ax[1], ax[2]); axp[0] = c12;
+    }
+    int r = 0;
+    for (int i = 0; i < j.mnum; i++) if (add_limot(W, j, motor_limot(j, i), fps, row + r * ROWLEN, axp[i])) r++;
+}
+// dxJointAMotor::setAxisValue amotor.cpp:393-442
+static void amotor_set_axis(World &W, Joint &j, int anum, int rel, Real x, Real y, Real z)
+{
+    if (rel != 0 && j.reverse) rel = 3 - rel;
+    j.mrel[anum] = rel;
+    Real r[3] = { x, y, z };
+    bool assigned = false;
+    if (rel == 1) { mul1_331(j.maxis[anum], W.bodies[j.b0].R, r); assigned = true; }
+    else if (rel == 2 && j.b1 >= 0) { mul1_331(j.maxis[anum], W.bodies[j.b1].R, r); assigned = true; }
+    if (!assigned) { j.maxis[anum][0] = x; j.maxis[anum][1] = y; j.maxis[anum][2] = z; }
+    normalize3(j.maxis[anum]);
+}
+// dxJointAMotor::setEulerReferenceVectors amotor.cpp:768-796
+static void amotor_set_euler_references(World &W, Joint &j)
+{
+    const int first = j.reverse ? 2 : 0, second = 2 - first;
+    if (j.b1 >= 0) {
+        Real r[3];
+        mul0_331(r, W.bodies[j.b0].R, j.maxis[first]);
+        mul1_331(j.mref[1], W.bodies[j.b1].R, r);
+        mul0_331(r, W.bodies[j.b1].R, j.maxis[second]);
+        mul1_331(j.mref[0], W.bodies[j.b0].R, r);
+    } else {
+        mul0_331(j.mref[1], W.bodies[j.b0].R, j.maxis[first]);
+        mul1_331(j.mref[0], W.bodies[j.b0].R, j.maxis[second]);
+    }
+}
+
 // dJointSet{Ball,Hinge,Universal}Anchor/Axis at the template pose
 static void joint_setup(const Batch &B, World &W, Joint &j, const OdebJointDesc &d)
 {
+    if (j.type == ODEB_JOINT_LMOTOR || j.type == ODEB_JOINT_AMOTOR) {
+        // dJointSet{L,A}MotorNumAxes, dJointSetAMotorMode (amotor.cpp:354-377: Euler mode forces 3 axes), dJointSet{L,A}MotorAxis, dJointSetAMotorAngle
+        const bool am = j.type == ODEB_JOINT_AMOTOR;
+        j.mmode = am ? d.motor_mode : 0;
+        j.mnum = (am && j.mmode == 1) ? 3 : d.motor_num;
+        for (int i = 0; i < d.motor_num; i++) {
+            if (am && j.mmode == 1 && i == 1) continue;                 // Euler mode: axis 1 is derived (ax[2] x ax[0])
+            if (am) amotor_set_axis(W, j, i, d.motor_rel[i], (Real)d.motor_axis[i][0], (Real)d.motor_axis[i][1], (Real)d.motor_axis[i][2]);
+            else lmotor_set_axis(W, j, i, d.motor_rel[i], (Real)d.motor_axis[i][0], (Real)d.motor_axis[i][1], (Real)d.motor_axis[i][2]);
+        }
+        if (am && j.mmode == 1) amotor_set_euler_references(W, j);
+        for (int i = 0; i < 3; i++) { j.mangle[i] = am ? (Real)d.motor_angle[i] : 0; limot_set(motor_limot(j, i), d, i); }
+        return;
+    }
     set_anchors(W, j, (Real)d.anchor[0], (Real)d.anchor[1], (Real)d.anchor[2]);
     if (j.type == ODEB_JOINT_FIXED) {
         // dJointSetFixed fixed.cpp:113-142

@@ -53,6 +53,10 @@ struct Joint {
     Real anchor1[4], anchor2[4], axis1[4], axis2[4], qrel[4], qrel1[4], qrel2[4];
     Real erp, cfm;
     Limot limot1, limot2;
+    // lmotor / amotor (lmotor.h:30-49, amotor.h:91-101): axes, what they are relative to, Euler reference vectors, angles, third limit motor
+    int mnum, mmode, mrel[3];
+    Real maxis[3][4], mref[2][4], mangle[3];
+    Limot limot3;
     int m, nub;
 };
 
@@ -625,6 +629,8 @@ void joint_info1(const Batch &B, World &W, Joint &j)
     case ODEB_JOINT_HINGE2: hinge2_info1(W, j); break;
     case ODEB_JOINT_HINGE: hinge_info1(W, j); break;
     case ODEB_JOINT_UNIVERSAL: universal_info1(W, j); break;
+    case ODEB_JOINT_LMOTOR: lmotor_info1(W, j); break;
+    case ODEB_JOINT_AMOTOR: amotor_info1(W, j); break;
     }
 }
 
@@ -641,6 +647,8 @@ void joint_info2(const Batch &B, World &W, Joint &j, Real fps, Real worldERP, Re
     case ODEB_JOINT_HINGE2: hinge2_info2(W, j, fps, worldERP, row); break;
     case ODEB_JOINT_HINGE: hinge_info2(W, j, fps, worldERP, row, findex); break;
     case ODEB_JOINT_UNIVERSAL: universal_info2(W, j, fps, worldERP, row, findex); break;
+    case ODEB_JOINT_LMOTOR: lmotor_info2(W, j, fps, row); break;
+    case ODEB_JOINT_AMOTOR: amotor_info2(W, j, fps, row); break;
     }
 }
 
@@ -1053,7 +1061,7 @@ void *orc_create(const OdebWorldParams *wp, int nbody, const OdebBodyDesc *bodie
             const OdebJointDesc &d = joints[i];
             j.type = d.type;
             j.erp = B->erp; j.cfm = B->cfm;
-            limot_init(*B, j.limot1); limot_init(*B, j.limot2);
+            limot_init(*B, j.limot1); limot_init(*B, j.limot2); limot_init(*B, j.limot3);
             attach(W, i, j, d.body1, d.body2);
             joint_setup(*B, W, j, d);
         }

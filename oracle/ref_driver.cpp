@@ -98,9 +98,9 @@ void apply_world_params(dWorldID w, const OdebWorldParams &p)
 
 void set_limot(dJointID j, int type, const OdebJointDesc &d)
 {
-    for (int a = 0; a < ((type == ODEB_JOINT_UNIVERSAL || type == ODEB_JOINT_HINGE2) ? 2 : 1); a++) {
+    for (int a = 0; a < ((type == ODEB_JOINT_AMOTOR || type == ODEB_JOINT_LMOTOR) ? 3 : (type == ODEB_JOINT_UNIVERSAL || type == ODEB_JOINT_HINGE2) ? 2 : 1); a++) {
         int grp = a * dParamGroup;
-        void (*setp)(dJointID, int, dReal) = (type == ODEB_JOINT_HINGE) ? dJointSetHingeParam : (type == ODEB_JOINT_SLIDER) ? dJointSetSliderParam : (type == ODEB_JOINT_HINGE2) ? dJointSetHinge2Param : dJointSetUniversalParam;
+        void (*setp)(dJointID, int, dReal) = (type == ODEB_JOINT_AMOTOR) ? dJointSetAMotorParam : (type == ODEB_JOINT_LMOTOR) ? dJointSetLMotorParam : (type == ODEB_JOINT_HINGE) ? dJointSetHingeParam : (type == ODEB_JOINT_SLIDER) ? dJointSetSliderParam : (type == ODEB_JOINT_HINGE2) ? dJointSetHinge2Param : dJointSetUniversalParam;
         // the reference documents setting lo, hi, lo again when lo > hi may be transiently true
         setp(j, dParamLoStop + grp, (dReal)d.lo_stop[a]);
         setp(j, dParamHiStop + grp, (dReal)d.hi_stop[a]);
@@ -198,6 +198,21 @@ void *ref_create(const OdebWorldParams *wp,
             } else if (d.type == ODEB_JOINT_SLIDER) {
                 j = dJointCreateSlider(W.world, 0); dJointAttach(j, b1, b2);
                 dJointSetSliderAxis(j, (dReal)d.axis1[0], (dReal)d.axis1[1], (dReal)d.axis1[2]);
+                set_limot(j, d.type, d);
+            } else if (d.type == ODEB_JOINT_LMOTOR) {
+                j = dJointCreateLMotor(W.world, 0); dJointAttach(j, b1, b2);
+                dJointSetLMotorNumAxes(j, d.motor_num);
+                for (int k = 0; k < d.motor_num; k++) dJointSetLMotorAxis(j, k, d.motor_rel[k], (dReal)d.motor_axis[k][0], (dReal)d.motor_axis[k][1], (dReal)d.motor_axis[k][2]);
+                set_limot(j, d.type, d);
+            } else if (d.type == ODEB_JOINT_AMOTOR) {
+                j = dJointCreateAMotor(W.world, 0); dJointAttach(j, b1, b2);
+                dJointSetAMotorMode(j, d.motor_mode);
+                dJointSetAMotorNumAxes(j, d.motor_num);
+                for (int k = 0; k < d.motor_num; k++) {
+                    if (d.motor_mode == dAMotorEuler && k == 1) continue;
+                    dJointSetAMotorAxis(j, k, d.motor_rel[k], (dReal)d.motor_axis[k][0], (dReal)d.motor_axis[k][1], (dReal)d.motor_axis[k][2]);
+                }
+                if (d.motor_mode == dAMotorUser) for (int k = 0; k < d.motor_num; k++) dJointSetAMotorAngle(j, k, (dReal)d.motor_angle[k]);
                 set_limot(j, d.type, d);
             } else if (d.type == ODEB_JOINT_FIXED) {
                 j = dJointCreateFixed(W.world, 0); dJointAttach(j, b1, b2);

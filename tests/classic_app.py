@@ -79,7 +79,14 @@ class Ode:
             "dJointSetBallAnchor": (None, [vp, r, r, r]), "dJointSetHingeAnchor": (None, [vp, r, r, r]), "dJointSetHingeAxis": (None, [vp, r, r, r]),
             "dJointSetHingeParam": (None, [vp, i, r]), "dJointSetUniversalAnchor": (None, [vp, r, r, r]),
             "dJointSetUniversalAxis1": (None, [vp, r, r, r]), "dJointSetUniversalAxis2": (None, [vp, r, r, r]),
-            "dJointSetUniversalParam": (None, [vp, i, r]), "dJointSetFeedback": (None, [vp, vp]), "dJointGetFeedback": (vp, [vp]), "dAreConnectedExcluding": (i, [vp, vp, i]), "dAreConnected": (i, [vp, vp]),
+            "dJointSetUniversalParam": (None, [vp, i, r]),
+            "dJointCreateLMotor": (vp, [vp, vp]), "dJointSetLMotorNumAxes": (None, [vp, i]), "dJointSetLMotorAxis": (None, [vp, i, i, r, r, r]),
+            "dJointSetLMotorParam": (None, [vp, i, r]), "dJointCreateAMotor": (vp, [vp, vp]), "dJointSetAMotorMode": (None, [vp, i]),
+            "dJointSetAMotorNumAxes": (None, [vp, i]), "dJointSetAMotorAxis": (None, [vp, i, i, r, r, r]), "dJointSetAMotorAngle": (None, [vp, i, r]),
+            "dJointSetAMotorParam": (None, [vp, i, r]), "dJointGetAMotorAxisRel": (i, [vp, i]), "dJointGetAMotorNumAxes": (i, [vp]),
+            "dGeomSetOffsetPosition": (None, [vp, r, r, r]), "dGeomSetOffsetQuaternion": (None, [vp, C.POINTER(r)]),
+            "dHashSpaceSetLevels": (None, [vp, i, i]),
+            "dJointSetFeedback": (None, [vp, vp]), "dJointGetFeedback": (vp, [vp]), "dAreConnectedExcluding": (i, [vp, vp, i]), "dAreConnected": (i, [vp, vp]),
         }
         for name, (res, args) in sig.items():
             f = getattr(L, name)
@@ -300,4 +307,66 @@ def scene_linkage(app):
             o.dJointAttach(j, a, b)
             o.dJointSetBallAnchor(j, x, 0.0, 1.0)
         app.perm_joints = getattr(app, "perm_joints", []) + [j]
+    return bs
+
+
+def scene_motors(app):
+    """a driven box (LMotor to the environment), a two-link arm whose elbow carries an Euler-mode AMotor with stops, a user-mode AMotor
+    whose velocity target the application changes while it runs, and a composite dumbbell (geom offsets) dropped beside them"""
+    o = app.o
+    dParamVel, dParamFMax, dParamVel2, dParamFMax2, dParamLoStop3, dParamHiStop3 = 2, 5, 0x102, 0x105, 0x200, 0x201
+    app.plane(0, 0, 1, 0)
+    bs = [app.box((0.0, 0.0, 0.1), (0.4, 0.3, 0.2), density=2.0)]
+    j = o.dJointCreateLMotor(app.world, None)
+    o.dJointAttach(j, bs[0], None)
+    o.dJointSetLMotorNumAxes(j, 2)
+    o.dJointSetLMotorAxis(j, 0, 0, 1.0, 0.0, 0.0)
+    o.dJointSetLMotorAxis(j, 1, 1, 0.0, 1.0, 0.0)
+    o.dJointSetLMotorParam(j, dParamVel, 0.5)
+    o.dJointSetLMotorParam(j, dParamFMax, 8.0)
+    o.dJointSetLMotorParam(j, dParamVel2, -0.2)
+    o.dJointSetLMotorParam(j, dParamFMax2, 3.0)
+    a, b = app.box((2.0, 0.0, 1.0), (0.4, 0.3, 0.2), density=2.0), app.box((2.6, 0.0, 1.0), (0.4, 0.3, 0.2), density=2.0)
+    bs += [a, b]
+    j = o.dJointCreateBall(app.world, None)
+    o.dJointAttach(j, a, None)
+    o.dJointSetBallAnchor(j, 1.7, 0.0, 1.0)
+    j = o.dJointCreateBall(app.world, None)
+    o.dJointAttach(j, a, b)
+    o.dJointSetBallAnchor(j, 2.3, 0.0, 1.0)
+    j = o.dJointCreateAMotor(app.world, None)
+    o.dJointAttach(j, a, b)
+    o.dJointSetAMotorMode(j, 1)
+    o.dJointSetAMotorAxis(j, 0, 1, 1.0, 0.0, 0.0)
+    o.dJointSetAMotorAxis(j, 2, 2, 0.0, 0.0, 1.0)
+    for grp in (0, 0x100, 0x200):
+        o.dJointSetAMotorParam(j, dParamLoStop + grp, -0.3)
+        o.dJointSetAMotorParam(j, dParamHiStop + grp, 0.3)
+    assert o.dJointGetAMotorNumAxes(j) == 3 and o.dJointGetAMotorAxisRel(j, 2) == 2
+    c, d = app.box((4.0, 0.0, 1.0), (0.4, 0.3, 0.2), density=2.0), app.box((4.0, 0.6, 1.0), (0.4, 0.3, 0.2), density=2.0)
+    bs += [c, d]
+    j = o.dJointCreateBall(app.world, None)
+    o.dJointAttach(j, c, d)
+    o.dJointSetBallAnchor(j, 4.0, 0.3, 1.0)
+    j = o.dJointCreateAMotor(app.world, None)
+    o.dJointAttach(j, c, d)
+    o.dJointSetAMotorNumAxes(j, 2)
+    o.dJointSetAMotorAxis(j, 0, 1, 1.0, 0.0, 0.0)
+    o.dJointSetAMotorAxis(j, 1, 2, 0.0, 1.0, 0.0)
+    o.dJointSetAMotorParam(j, dParamFMax, 1.0)
+    o.dJointSetAMotorParam(j, dParamFMax2, 1.0)
+    app.user_motor = j
+    # composite dumbbell: one body, two offset spheres and an offset capsule
+    e = app.body((6.0, 0.0, 0.8))
+    m = o.dMass()
+    o.dMassSetBoxTotal(C.byref(m), 1.5, 0.7, 0.2, 0.2)
+    o.dBodySetMass(e, C.byref(m))
+    for ox in (0.3, -0.3):
+        g = app._add_geom(o.dCreateSphere(app.space, 0.15), e)
+        o.dGeomSetOffsetPosition(g, ox, 0.0, 0.0)
+    g = app._add_geom(o.dCreateCapsule(app.space, 0.05, 0.5), e)
+    s = math.sqrt(0.5)
+    o.dGeomSetOffsetQuaternion(g, (o.real * 4)(s, 0.0, s, 0.0))
+    o.dBodySetAngularVel(e, 0.5, 1.0, -0.7)
+    bs.append(e)
     return bs

@@ -4,6 +4,7 @@ unmodified reference library and on the B200 library; observables must agree.
 CPU part: symbols, struct layouts, host-side functions (mass, rotations, dRand known answers, object bookkeeping) and the
 loud failure without a CUDA device.  GPU part (-m gpu): pair sets, contacts, trajectories, statistics, dRand seed."""
 import ctypes as C
+import math
 import os
 import re
 import subprocess
@@ -253,3 +254,25 @@ def test_classic_joint_feedback(prec):
     assert wrote > 0
     ra.close()
     ga.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec", ("single", "double"))
+def test_classic_motors_and_offsets(prec):
+    """dJointCreateLMotor / dJointCreateAMotor (Euler mode with stops; user mode with the velocity target changed by the application
+    between steps) and dGeomSetOffset* composite bodies through the classic API, reference vs B200 (atan2 on the path -> tolerance)"""
+    apps = _run_both(prec, A.scene_motors, 80, 0.01, space="hash", max_contacts=4, surface="approx1")
+    ra, ga = apps
+    tol = 5e-4 if prec == "single" else 1e-9
+    for s in range(80):
+        for a in apps:
+            a.o.dJointSetAMotorParam(a.user_motor, 2, 0.4 * math.sin(0.1 * s))       # dParamVel
+            a.o.dJointSetAMotorParam(a.user_motor, 0x102, -0.2)                       # dParamVel2
+        assert ra.step(0.01, seed=100 + s) == 1 and ga.step(0.01, seed=100 + s) == 1
+        assert ra.pair_set() == ga.pair_set(), "pair set differs at step %d" % s
+        assert [c[:2] for c in ra.contact_log] == [c[:2] for c in ga.contact_log]
+        d = float(np.abs(ra.state().astype(np.float64) - ga.state()).max())
+        assert d <= tol, "state differs by %.3g at step %d" % (d, s)
+    assert ra.ncontacts == ga.ncontacts and ra.ncontacts > 0
+    for a in apps:
+        a.close()

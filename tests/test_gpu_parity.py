@@ -498,3 +498,25 @@ def test_broadphase_spaces(prec, space, levels):
         bad = compare_step(a, b, 1, exact_float=False, tol=TOL[prec], what=("pairs", "contacts", "islands", "state"))
         assert not bad, (s, bad[:4])
     b.close()
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_motor_joints(prec):
+    """LMotor / AMotor rows (user + Euler mode, stops, powered at a stop, reversed attachment).  Euler angles go through atan2 (CUDA
+    libm vs glibc), so teacher-forced single steps from the oracle's state: sets exact, floats to 10x the usual per-step tolerance
+    (the motor-driven bodies of this scene spin at |w| ~ 10).  Dynamic iteration adjustment is switched off here (exactly 20 sweeps):
+    with it a 1-ulp difference in a limit error can move one island's exit decision by a sweep, i.e. by ~1e-3 in a velocity, which is
+    the reference's own sensitivity and says nothing about the motor rows; the other scenes cover the adjustment logic."""
+    sc = scenes.motors(4, dynamic_iterations=False)
+    a, b = B.Batch(orc_lib(prec), sc), B.Batch(gpu_lib(prec), sc)
+    tol = dict(contact=TOL[prec]["contact"], state=10 * TOL[prec]["state"])
+    for s in range(120):
+        st = a.get_state()
+        b.set_state(**st)
+        b.set_seeds(a.get_seeds())
+        a.set_state(**st)
+        a.step(0.01)
+        b.step(0.01)
+        bad = compare_step(a, b, sc.nworlds, exact_float=False, tol=tol, what=("pairs", "contacts", "islands", "stats", "seeds", "state"))
+        assert not bad, (s, bad[:4])
+    b.close()

@@ -319,3 +319,19 @@ def test_hash_space_is_a_strict_subset_of_simple_space_here(prec):
         counts[space] = [set(map(tuple, b.get_pairs(w))) for w in range(sc.nworlds)]
     assert all(h <= s for h, s in zip(counts[B.SPACE_HASH], counts[B.SPACE_SIMPLE]))
     assert sum(len(s) - len(h) for h, s in zip(counts[B.SPACE_HASH], counts[B.SPACE_SIMPLE])) > 0
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_motor_joints_vs_reference(prec):
+    """LMotor (lmotor.cpp) and AMotor (amotor.cpp, user and Euler mode, stops, bounce, powered at a stop, lo == hi, dJOINT_REVERSE):
+    the restatement against the compiled reference, every observable, 300 steps."""
+    ref = ref_lib(prec)
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    sc = scenes.motors(3)
+    a, b = B.Batch(ref, sc), B.Batch(orc_lib(prec), sc)
+    for s in range(300):
+        a.step(0.01)
+        b.step(0.01)
+        bad = compare_step(a, b, sc.nworlds)
+        assert not bad, (s, bad[:4])
