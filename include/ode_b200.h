@@ -38,7 +38,7 @@ typedef float odeb_real;
 #endif
 
 /* geom classes: numbering of the reference (include/ode/collision.h:881-902) */
-enum { ODEB_SPHERE = 0, ODEB_BOX = 1, ODEB_CAPSULE = 2, ODEB_PLANE = 4 };
+enum { ODEB_SPHERE = 0, ODEB_BOX = 1, ODEB_CAPSULE = 2, ODEB_CYLINDER = 3, ODEB_PLANE = 4, ODEB_RAY = 5 };
 /* joint types: numbering of the reference dJointType (include/ode/common.h:406-426) */
 enum { ODEB_JOINT_BALL = 1, ODEB_JOINT_HINGE = 2, ODEB_JOINT_SLIDER = 3, ODEB_JOINT_CONTACT = 4, ODEB_JOINT_UNIVERSAL = 5, ODEB_JOINT_HINGE2 = 6, ODEB_JOINT_FIXED = 7, ODEB_JOINT_AMOTOR = 9, ODEB_JOINT_LMOTOR = 10 };
 /* broadphase flavours: which reference space's callback stream is reproduced (as a set).
@@ -106,7 +106,12 @@ typedef struct OdebBodyDesc {
 
 typedef struct OdebGeomDesc {
     int    type;                /* ODEB_SPHERE: p[0]=radius; ODEB_BOX: p[0..2]=side lengths;
-                                   ODEB_CAPSULE: p[0]=radius, p[1]=length; ODEB_PLANE: p[0..3]=a,b,c,d */
+                                   ODEB_CAPSULE: p[0]=radius, p[1]=length; ODEB_PLANE: p[0..3]=a,b,c,d;
+                                   ODEB_CYLINDER: p[0]=radius, p[1]=length (collides with planes and spheres: collision_cylinder_plane.cpp,
+                                   collision_cylinder_sphere.cpp; a scene in which a cylinder can meet a box is rejected, capsules and other
+                                   cylinders pass through it as in the reference's default build, which has no collider for them);
+                                   ODEB_RAY: p[0]=length, along the geom's local z axis (ray.cpp).  Rays are sensors: their hits are
+                                   reported by odeb_get_ray_hits and never become contact joints */
     int    body;                /* body index in the world, -1 = static (dGeomSetBody not called) */
     double p[4];
     uint32_t category_bits, collide_bits; /* dGeomSetCategoryBits / dGeomSetCollideBits */
@@ -236,6 +241,9 @@ void   odeb_enable_timing(OdebBatch *, int on);
  * islands: label per body (-1 = not stepped), labels numbered in processing order. */
 int odeb_get_pairs(OdebBatch *, int world, int *pairs, int cap);
 int odeb_get_contacts(OdebBatch *, int world, odeb_real *geom7, int *g12, int cap);
+/* hits of the world's ray geoms (ODEB_RAY) in the last step's collide pass, in pair order: [pos3, normal3, depth = distance along the ray]
+ * + (g1, g2); what a near-callback that treats rays as sensors collects with dCollide (ray.cpp) */
+int odeb_get_ray_hits(OdebBatch *, int world, odeb_real *geom7, int *g12, int cap);
 int odeb_get_islands(OdebBatch *, int world, int *label_per_body);
 int odeb_get_stats(OdebBatch *, int world, OdebStats *out);
 /* totals over all worlds for the most recent step:

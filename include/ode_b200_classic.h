@@ -18,7 +18,7 @@
  * stages: without a CUDA device dWorldQuickStep returns 0 and dSpaceCollide reports through the error handler.
  *
  * Outside the subset (calls are not exported): dWorldStep, joints other than contact/ball/hinge/slider/universal/hinge2/fixed/amotor/lmotor, geoms other
- * than sphere/box/capsule/plane, nested spaces, per-body
+ * than sphere/box/capsule/cylinder/plane/ray (cylinder-box pairs excepted), nested spaces, per-body
  * auto-disable thresholds (the world's are used), SAP axis orders other than dSAP_AXES_XYZ.
  */
 #ifndef ODE_B200_CLASSIC_H
@@ -117,7 +117,7 @@ typedef struct dMass {
 typedef struct dJointFeedback { dVector3 f1, t1, f2, t2; } dJointFeedback;
 
 /* include/ode/collision.h:881-902, :743; include/ode/collision_space.h:49-64 */
-enum { dSphereClass = 0, dBoxClass, dCapsuleClass, dCylinderClass, dPlaneClass };
+enum { dSphereClass = 0, dBoxClass, dCapsuleClass, dCylinderClass, dPlaneClass, dRayClass };
 #define CONTACTS_UNIMPORTANT 0x80000000
 typedef void dNearCallback(void *data, dGeomID o1, dGeomID o2);
 #define dSAP_AXES_XYZ ((0) | (1 << 2) | (2 << 4))
@@ -151,6 +151,8 @@ void dMassSetSphere(dMass *, dReal density, dReal radius);
 void dMassSetSphereTotal(dMass *, dReal total_mass, dReal radius);
 void dMassSetCapsule(dMass *, dReal density, int direction, dReal radius, dReal length);
 void dMassSetCapsuleTotal(dMass *, dReal total_mass, int direction, dReal radius, dReal length);
+void dMassSetCylinder(dMass *, dReal density, int direction, dReal radius, dReal length);
+void dMassSetCylinderTotal(dMass *, dReal total_mass, int direction, dReal radius, dReal length);
 void dMassSetBox(dMass *, dReal density, dReal lx, dReal ly, dReal lz);
 void dMassSetBoxTotal(dMass *, dReal total_mass, dReal lx, dReal ly, dReal lz);
 void dMassAdjust(dMass *, dReal newmass);
@@ -350,6 +352,14 @@ unsigned long dGeomGetCollideBits(dGeomID);
 dReal dGeomSphereGetRadius(dGeomID);
 void dGeomBoxGetLengths(dGeomID, dVector3 result);
 void dGeomCapsuleGetParams(dGeomID, dReal *radius, dReal *length);
+dGeomID dCreateCylinder(dSpaceID, dReal radius, dReal length);   /* cylinder.cpp; colliders: plane, sphere, ray (cylinder-box: dCollide reports an error) */
+void dGeomCylinderSetParams(dGeomID, dReal radius, dReal length);
+void dGeomCylinderGetParams(dGeomID, dReal *radius, dReal *length);
+dGeomID dCreateRay(dSpaceID, dReal length);                      /* ray.cpp; colliders: sphere, box, capsule, plane, cylinder */
+void dGeomRaySetLength(dGeomID, dReal length);
+dReal dGeomRayGetLength(dGeomID);
+void dGeomRaySet(dGeomID, dReal px, dReal py, dReal pz, dReal dx, dReal dy, dReal dz);   /* rays without a body */
+void dGeomRayGet(dGeomID, dVector3 start, dVector3 dir);
 void dGeomPlaneGetParams(dGeomID, dVector4 result);
 
 #ifdef __cplusplus

@@ -59,6 +59,7 @@ class OdebStats(C.Structure):
 
 
 SPHERE, BOX, CAPSULE, PLANE = 0, 1, 2, 4
+CYLINDER, RAY = 3, 5
 JOINT_BALL, JOINT_HINGE, JOINT_SLIDER, JOINT_CONTACT, JOINT_UNIVERSAL, JOINT_HINGE2, JOINT_FIXED = 1, 2, 3, 4, 5, 6, 7
 JOINT_AMOTOR, JOINT_LMOTOR = 9, 10
 AMOTOR_USER, AMOTOR_EULER = 0, 1
@@ -178,6 +179,13 @@ def sphere_mass(density, r):
     return m, np.eye(3) * (0.4 * m * r * r)
 
 
+def cylinder_mass(density, r, length):
+    """dMassSetCylinder along z (ode/src/mass.cpp:173-198), direction = 3."""
+    m = np.pi * r * r * length * density
+    Ia = m * (0.25 * r * r + length * length / 12.0)
+    return m, np.diag([Ia, Ia, m * 0.5 * r * r])
+
+
 def capsule_mass(density, r, length):
     """dMassSetCapsule along z (ode/src/mass.cpp:138-166), direction = 3."""
     M1 = np.pi * r * r * length * density
@@ -211,6 +219,8 @@ class SceneLib:
         self._fn("step").argtypes = [C.c_void_p, C.c_double, C.c_int]
         self._fn("get_pairs").argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         self._fn("get_contacts").argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        if hasattr(self.lib, prefix + "get_ray_hits"):
+            self._fn("get_ray_hits").argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         self._fn("get_islands").argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         self._fn("get_stats").argtypes = [C.c_void_p, C.c_int, C.POINTER(OdebStats)]
 
@@ -379,6 +389,15 @@ class Batch:
         n = self.slib._fn("get_contacts")(self.h, world, _ptr(g), _ptr(ids), cap)
         if n > cap:
             return self.get_contacts(world, n)
+        return g[:n].copy(), ids[:n].copy()
+
+    def get_ray_hits(self, world, cap=1 << 12):
+        """hits of the world's ray geoms in the last step's collide pass: ([pos3, normal3, depth = distance along the ray], (g1, g2))"""
+        g = np.empty((cap, 7), self.slib.real)
+        ids = np.empty((cap, 2), np.int32)
+        n = self.slib._fn("get_ray_hits")(self.h, world, _ptr(g), _ptr(ids), cap)
+        if n > cap:
+            return self.get_ray_hits(world, n)
         return g[:n].copy(), ids[:n].copy()
 
     def get_islands(self, world):

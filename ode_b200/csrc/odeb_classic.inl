@@ -543,6 +543,19 @@ void dMassSetCapsule(dMass *m, Real density, int direction, Real radius, Real le
     m->I[0] = Ia; m->I[5] = Ia; m->I[10] = Ia;
     m->I[(direction - 1) * 5] = Ib;
 }
+void dMassSetCylinderTotal(dMass *m, Real total_mass, int direction, Real radius, Real length)
+{   // mass.cpp:180-198
+    dMassSetZero(m);
+    const Real r2 = radius * radius;
+    m->mass = total_mass;
+    const Real I = total_mass * (R_(0.25) * r2 + (R_(1.0) / R_(12.0)) * length * length);
+    m->I[0] = I; m->I[5] = I; m->I[10] = I;
+    m->I[(direction - 1) * 5] = total_mass * R_(0.5) * r2;
+}
+void dMassSetCylinder(dMass *m, Real density, int direction, Real radius, Real length)
+{   // mass.cpp:173-178
+    dMassSetCylinderTotal(m, (Real)(M_PI * radius * radius * length * density), direction, radius, length);
+}
 void dMassSetCapsuleTotal(dMass *m, Real total_mass, int direction, Real a, Real b)
 {
     dMassSetCapsule(m, 1.0, direction, a, b);
@@ -1067,6 +1080,28 @@ static dxGeom *new_geom(dxSpace *s, int type, Real p0, Real p1, Real p2, Real p3
 dGeomID dCreateSphere(dSpaceID s, Real radius) { return new_geom(s, ODEB_SPHERE, radius, 0, 0, 0); }
 dGeomID dCreateBox(dSpaceID s, Real lx, Real ly, Real lz) { return new_geom(s, ODEB_BOX, lx, ly, lz, 0); }
 dGeomID dCreateCapsule(dSpaceID s, Real radius, Real length) { return new_geom(s, ODEB_CAPSULE, radius, length, 0, 0); }
+dGeomID dCreateCylinder(dSpaceID s, Real radius, Real length) { return new_geom(s, ODEB_CYLINDER, radius, length, 0, 0); }   // cylinder.cpp:52-60
+void dGeomCylinderSetParams(dGeomID g, Real radius, Real length) { g->p[0] = radius; g->p[1] = length; }
+void dGeomCylinderGetParams(dGeomID g, Real *radius, Real *length) { *radius = g->p[0]; *length = g->p[1]; }
+// rays (ray.cpp:46-205): length in p[0], direction = the geom's local z axis
+dGeomID dCreateRay(dSpaceID s, Real length) { return new_geom(s, ODEB_RAY, length, 0, 0, 0); }
+void dGeomRaySetLength(dGeomID g, Real length) { g->p[0] = length; }
+odeb_real dGeomRayGetLength(dGeomID g) { return g->p[0]; }
+void dGeomRaySet(dGeomID g, Real px, Real py, Real pz, Real dx, Real dy, Real dz)
+{   // ray.cpp:113-135: position + third column of the rotation.  The reference writes through final_posr, i.e. into the body's own
+    // pose for a ray that sits on a body without an offset; that aliasing is not reproduced: such a ray follows its body.
+    if (g->body) { classic_error("dGeomRaySet: the ray is attached to a body and follows it (use dGeomSetOffset* to aim it)"); return; }
+    Real n[3] = { dx, dy, dz };
+    normalize3(n);
+    g->pos[0] = px; g->pos[1] = py; g->pos[2] = pz;
+    g->R[2] = n[0]; g->R[6] = n[1]; g->R[10] = n[2];
+}
+void dGeomRayGet(dGeomID g, Real *start, Real *dir)
+{
+    const Real *p = dGeomGetPosition(g), *R = dGeomGetRotation(g);
+    start[0] = p[0]; start[1] = p[1]; start[2] = p[2];
+    dir[0] = R[2]; dir[1] = R[6]; dir[2] = R[10];
+}
 dGeomID dCreatePlane(dSpaceID s, Real a, Real b, Real c, Real d)
 {
     dxGeom *g = new_geom(s, ODEB_PLANE, a, b, c, d);
@@ -1222,6 +1257,9 @@ int dCollide(dGeomID o1, dGeomID o2, int flags, dContactGeom *contact, int skip)
     if (maxc < 1 || !contact || skip < (int)sizeof(dContactGeom)) { classic_error("dCollide: bad arguments"); return 0; }
     if (o1 == o2) return 0;
     if (o1->body == o2->body && o1->body) return 0;
+    if ((o1->type == ODEB_CYLINDER && o2->type == ODEB_BOX) || (o1->type == ODEB_BOX && o2->type == ODEB_CYLINDER)) {
+        classic_error("dCollide: the cylinder-box collider (collision_cylinder_box.cpp) is outside the supported subset"); return 0;
+    }
     dxSpace *s = o1->space;
     if (!s || o2->space != s) { classic_error("dCollide: both geoms must be in the same space"); return 0; }
     dxWorld *w = space_world(s);

@@ -9,7 +9,7 @@
 
 
 struct DGeom {
-    int type;        // ODEB_SPHERE / BOX / CAPSULE / PLANE
+    int type;        // ODEB_SPHERE / BOX / CAPSULE / CYLINDER / PLANE / RAY
     int body;        // -1 = none
     Real p[4];       // radius | sides | radius,length | plane a,b,c,d (normalised)
     Real pos[3];
@@ -41,6 +41,19 @@ __device__ __forceinline__ void odeb_compute_aabb(const DGeom &g, Real *a)
         Real yr = RFABS(R[6] * lz) * R_(0.5) + radius;
         Real zr = RFABS(R[10] * lz) * R_(0.5) + radius;
         a[0] = pos[0] - xr; a[1] = pos[0] + xr; a[2] = pos[1] - yr; a[3] = pos[1] + yr; a[4] = pos[2] - zr; a[5] = pos[2] + zr;
+    } else if (g.type == 3) {     // dxCylinder::computeAABB cylinder.cpp:63-80
+        Real radius = g.p[0], lz = g.p[1];
+        Real m0 = (Real)(R_(1.0) - R[2] * R[2]), m1 = (Real)(R_(1.0) - R[6] * R[6]), m2 = (Real)(R_(1.0) - R[10] * R[10]);
+        Real xr = RFABS(R[2] * lz * R_(0.5)) + radius * RSQRT(m0 > R_(0.0) ? m0 : R_(0.0));
+        Real yr = RFABS(R[6] * lz * R_(0.5)) + radius * RSQRT(m1 > R_(0.0) ? m1 : R_(0.0));
+        Real zr = RFABS(R[10] * lz * R_(0.5)) + radius * RSQRT(m2 > R_(0.0) ? m2 : R_(0.0));
+        a[0] = pos[0] - xr; a[1] = pos[0] + xr; a[2] = pos[1] - yr; a[3] = pos[1] + yr; a[4] = pos[2] - zr; a[5] = pos[2] + zr;
+    } else if (g.type == 5) {     // dxRay::computeAABB ray.cpp:58-93
+        const Real len = g.p[0];
+        for (int k = 0; k < 3; k++) {
+            Real e = pos[k] + R[4 * k + 2] * len;
+            if (pos[k] < e) { a[2 * k] = pos[k]; a[2 * k + 1] = e; } else { a[2 * k] = e; a[2 * k + 1] = pos[k]; }
+        }
     } else {
         const Real *p = g.p;
         a[0] = -R_INF; a[1] = R_INF; a[2] = -R_INF; a[3] = R_INF; a[4] = -R_INF; a[5] = R_INF;
@@ -685,6 +698,8 @@ __device__ int odeb_capsule_plane(const DGeom &o1, const DGeom &o2, int flags, D
 }
 
 
+#include "odeb_ray_cyl.cuh"
+
 // dCollide collision_kernel.cpp:292-338 with the collider table of dInitColliders (:166-268):
 // direct entries (sphere,sphere) (sphere,box) (sphere,plane) (box,box) (box,plane) (capsule,sphere)
 // (capsule,box) (capsule,capsule) (capsule,plane); the transposed pairs call the same function with
@@ -701,6 +716,14 @@ __device__ int odeb_collide_direct(const DGeom &a, const DGeom &b, int flags, DC
     if (a.type == 2 && b.type == 1) return odeb_capsule_box(a, b, flags, c);
     if (a.type == 2 && b.type == 2) return odeb_capsule_capsule(a, b, flags, c);
     if (a.type == 2 && b.type == 4) return odeb_capsule_plane(a, b, flags, c);
+    if (a.type == 5 && b.type == 0) return odeb_ray_sphere(a, b, c);          // collision_kernel.cpp:191-195
+    if (a.type == 5 && b.type == 1) return odeb_ray_box(a, b, c);
+    if (a.type == 5 && b.type == 2) return odeb_ray_capsule(a, b, c);
+    if (a.type == 5 && b.type == 4) return odeb_ray_plane(a, b, c);
+    if (a.type == 5 && b.type == 3) return odeb_ray_cylinder(a, b, c);
+    if (a.type == 3 && b.type == 0) return odeb_cylinder_sphere(a, b, c);     // :212-213; cylinder-box (:210) is not built (scenes that could
+    if (a.type == 3 && b.type == 4) return odeb_cylinder_plane(a, b, flags, c); // pair them are rejected at creation); no cylinder-capsule /
+                                                                              // cylinder-cylinder collider exists without libccd
     *handled = 0;
     return 0;
 }

@@ -410,7 +410,8 @@ static OdebBatch *batch_build(const OdebWorldParams *wp, const HostTemplate &T, 
             && dev_alloc(B, &D.gcat, ngeom) && dev_alloc(B, &D.gcol, ngeom) && dev_alloc(B, &D.gspose, 4 * (size_t)ngeom) && dev_alloc(B, &D.gofs, ngeom) && dev_alloc(B, &D.joints, njoint)
             && dev_alloc(B, &D.sadj_ofs, nbody + 1) && dev_alloc(B, &D.sadj_joint, nadj) && dev_alloc(B, &D.sadj_other, nadj);
     ok = ok && dev_alloc(B, &D.aabb, WG * 6) && dev_alloc(B, &D.pair_cnt, WG) && dev_alloc(B, &D.pair_ofs, WG) && dev_alloc(B, &D.npairs, W)
-            && dev_alloc(B, &D.pairs, W * P.MP) && dev_alloc(B, &D.pc_count, W * P.MP) && dev_alloc(B, &D.cgeom, W * (classic ? (size_t)P.MC : (size_t)P.MP * P.maxc) * 2)
+            && dev_alloc(B, &D.pairs, W * P.MP) && dev_alloc(B, &D.pc_count, W * P.MP)
+            && (std::find(T.gtype.begin(), T.gtype.end(), (int)ODEB_RAY) == T.gtype.end() || classic || dev_alloc(B, &D.ray_count, W * P.MP)) && dev_alloc(B, &D.cgeom, W * (classic ? (size_t)P.MC : (size_t)P.MP * P.maxc) * 2)
             && dev_alloc(B, &D.ncontacts, W) && dev_alloc(B, &D.cinfo, W * P.MC) && dev_alloc(B, &D.jm, WJ) && dev_alloc(B, &D.jlimit, WJ);
     if (classic) ok = ok && dev_alloc(B, &D.csurf, (size_t)P.MC);
     ok = ok && dev_alloc(B, &D.c_ofs, W * (nbody + 1)) && dev_alloc(B, &D.c_cur, WB) && dev_alloc(B, &D.c_adj_c, W * 2 * P.MC) && dev_alloc(B, &D.c_adj_o, W * 2 * P.MC)
@@ -529,7 +530,7 @@ OdebBatch *odeb_create(const OdebWorldParams *wp,
     for (int i = 0; i < ngeom; i++) {
         T.gtype[i] = geoms[i].type; T.gbody[i] = geoms[i].body; T.gcat[i] = geoms[i].category_bits; T.gcol[i] = geoms[i].collide_bits;
         if (T.gbody[i] >= nbody) { set_err("geom %d: bad body index", i); return 0; }
-        if (T.gtype[i] != ODEB_SPHERE && T.gtype[i] != ODEB_BOX && T.gtype[i] != ODEB_CAPSULE && T.gtype[i] != ODEB_PLANE) { set_err("geom %d: unsupported class %d", i, T.gtype[i]); return 0; }
+        if (T.gtype[i] != ODEB_SPHERE && T.gtype[i] != ODEB_BOX && T.gtype[i] != ODEB_CAPSULE && T.gtype[i] != ODEB_PLANE && T.gtype[i] != ODEB_CYLINDER && T.gtype[i] != ODEB_RAY) { set_err("geom %d: unsupported class %d", i, T.gtype[i]); return 0; }
         Real *p = &T.gparam[4 * i];
         for (int k = 0; k < 4; k++) p[k] = (Real)geoms[i].p[k];
         if (T.gtype[i] == ODEB_PLANE) host_normalize_plane(p);
@@ -543,6 +544,14 @@ OdebBatch *odeb_create(const OdebWorldParams *wp,
             T.gspose[4 * i] = op; T.gspose[4 * i + 1] = a; T.gspose[4 * i + 2] = b; T.gspose[4 * i + 3] = c;
             T.gofs[i] = 1;
         }
+    }
+    // the cylinder-box collider (collision_cylinder_box.cpp) is not built: a scene in which the broadphase could hand that pair to dCollide
+    // would silently lose contacts the reference makes, so it is refused
+    for (int i = 0; i < ngeom; i++) for (int j = 0; j < ngeom; j++) {
+        if (T.gtype[i] != ODEB_CYLINDER || T.gtype[j] != ODEB_BOX) continue;
+        if (T.gbody[i] == T.gbody[j] && T.gbody[i] >= 0) continue;
+        if (T.gbody[i] < 0 && T.gbody[j] < 0) continue;
+        if ((T.gcat[i] & T.gcol[j]) || (T.gcat[j] & T.gcol[i])) { set_err("geoms %d (cylinder) and %d (box) may collide: the cylinder-box collider is not supported (separate them with category / collide bits)", i, j); return 0; }
     }
     T.jt.resize(njoint);
     std::vector<std::vector<std::pair<int, int> > > adj(nbody);
@@ -1024,6 +1033,31 @@ int odeb_get_contacts(OdebBatch *B, int world, odeb_real *geom7, int *g12, int c
         geom7[7 * i + 3] = b.x; geom7[7 * i + 4] = b.y; geom7[7 * i + 5] = b.z; geom7[7 * i + 6] = a.w;
         int2 p = pr[slot / P.maxc];
         g12[2 * i] = p.x; g12[2 * i + 1] = p.y;
+    }
+    return n;
+}
+
+int odeb_get_ray_hits(OdebBatch *B, int world, odeb_real *geom7, int *g12, int cap)
+{
+    CK(cudaSetDevice(B->device));
+    CK(cudaStreamSynchronize(B->stream));
+    const DevParams &P = B->P;
+    if (!B->D.ray_count) return 0;
+    int np = 0;
+    CK(cudaMemcpy(&np, B->D.npairs + world, sizeof(int), cudaMemcpyDeviceToHost));
+    if (np == 0) return 0;
+    std::vector<int2> pr(np); std::vector<int> rc(np);
+    CK(cudaMemcpy(pr.data(), B->D.pairs + (size_t)world * P.MP, np * sizeof(int2), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(rc.data(), B->D.ray_count + (size_t)world * P.MP, np * sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<Real4> cg((size_t)np * P.maxc * 2);
+    CK(cudaMemcpy(cg.data(), B->D.cgeom + (size_t)world * P.MP * P.maxc * 2, cg.size() * sizeof(Real4), cudaMemcpyDeviceToHost));
+    int n = 0;
+    for (int p = 0; p < np; p++) for (int k = 0; k < rc[p]; k++, n++) {
+        if (n >= cap) continue;
+        Real4 a = cg[2 * ((size_t)p * P.maxc + k)], b = cg[2 * ((size_t)p * P.maxc + k) + 1];
+        geom7[7 * n] = a.x; geom7[7 * n + 1] = a.y; geom7[7 * n + 2] = a.z;
+        geom7[7 * n + 3] = b.x; geom7[7 * n + 4] = b.y; geom7[7 * n + 5] = b.z; geom7[7 * n + 6] = a.w;
+        g12[2 * n] = pr[p].x; g12[2 * n + 1] = pr[p].y;
     }
     return n;
 }

@@ -30,6 +30,7 @@
 #include <cstdarg>
 #include <string>
 #include <vector>
+#include <algorithm>
 #include "../../include/ode_b200.h"
 #include "odeb_collide.cuh"
 #include "odeb_joints.cuh"
@@ -76,6 +77,7 @@ struct DevPtrs {
     int *pair_cnt, *pair_ofs, *npairs;           // [W*NG], [W*NG], [W]
     int2 *pairs;                                 // [W*MP]
     int *pc_count; Real4 *cgeom;                 // [W*MP], [W*MP*maxc*2] (pos,depth | normal,0)
+    int *ray_count;                              // [W*MP] hits of pairs with a ray geom: reported (odeb_get_ray_hits), never turned into joints
     int *ncontacts; int4 *cinfo;                 // [W], [W*MC] = (slot, b0, b1, reverse)
     DSurface *csurf;                             // [MC] per-contact surface parameters (classic mode)
     // joints dynamic
@@ -244,6 +246,11 @@ __global__ void k_narrow(const __grid_constant__ DevParams P, const __grid_const
             Real4 b = { c[i].normal[0], c[i].normal[1], c[i].normal[2], 0 };
             out[2 * i] = a; out[2 * i + 1] = b;
         }
+    }
+    if (D.ray_count) {      // sensor policy: a pair with a ray keeps its hits in the contact slots but contributes no contact joint
+        const bool ray = !skip && (D.gtype[pr.x] == ODEB_RAY || D.gtype[pr.y] == ODEB_RAY);
+        D.ray_count[t] = ray ? n : 0;
+        if (ray) n = 0;
     }
     D.pc_count[t] = n;
 }

@@ -902,6 +902,47 @@ class GeomCapsule(GeomObject):
 GeomCCylinder = GeomCapsule      # ode.pyx keeps the old name
 
 
+class GeomCylinder(GeomObject):
+    """ode.pyx:3994-4040"""
+
+    def __init__(self, space=None, radius=0.5, length=1.0):
+        r = _L().real
+        self._register(_L().f("dCreateCylinder", VP, VP, r, r)(_sid(space), radius, length), space)
+
+    def getParams(self):
+        r = _L().real
+        a, b = r(), r()
+        _L().f("dGeomCylinderGetParams", None, VP, VP, VP)(self.gid, C.byref(a), C.byref(b))
+        return (a.value, b.value)
+
+    def setParams(self, radius, length):
+        r = _L().real
+        _L().f("dGeomCylinderSetParams", None, VP, r, r)(self.gid, radius, length)
+
+
+class GeomRay(GeomObject):
+    """ode.pyx:4043-4122: a ray of length rlen along its local z axis; collide(ray, geom) returns at most one Contact whose depth is
+    the distance from the ray's start to the hit"""
+
+    def __init__(self, space=None, rlen=1.0):
+        self._register(_L().f("dCreateRay", VP, VP, _L().real)(_sid(space), rlen), space)
+
+    def setLength(self, rlen):
+        _L().f("dGeomRaySetLength", None, VP, _L().real)(self.gid, rlen)
+
+    def getLength(self):
+        return float(_L().f("dGeomRayGetLength", _L().real, VP)(self.gid))
+
+    def set(self, p, u):
+        r = _L().real
+        _L().f("dGeomRaySet", None, VP, r, r, r, r, r, r)(self.gid, p[0], p[1], p[2], u[0], u[1], u[2])
+
+    def get(self):
+        p, u = _L().vec3(), _L().vec3()
+        _L().f("dGeomRayGet", None, VP, VP, VP)(self.gid, p, u)
+        return (_v3(p), _v3(u))
+
+
 class SpaceBase(GeomObject):
     _create = None
 

@@ -6,9 +6,9 @@
 #include "orc_math.h"
 
 struct OrcGeom {
-    int type;        // ODEB_SPHERE / BOX / CAPSULE / PLANE
+    int type;        // ODEB_SPHERE / BOX / CAPSULE / CYLINDER / PLANE / RAY
     int body;        // -1 = none
-    Real p[4];       // radius | sides | radius,length | plane a,b,c,d (normalised)
+    Real p[4];       // radius | sides | radius,length | plane a,b,c,d (normalised) | ray length
     unsigned cat, col;
     const Real *pos; // -> body pos (4) or own storage
     const Real *R;   // -> body R (12)
@@ -43,6 +43,19 @@ static inline void orc_compute_aabb(OrcGeom &g)
         Real yr = RFABS(R[6] * lz) * R_(0.5) + radius;
         Real zr = RFABS(R[10] * lz) * R_(0.5) + radius;
         a[0] = pos[0] - xr; a[1] = pos[0] + xr; a[2] = pos[1] - yr; a[3] = pos[1] + yr; a[4] = pos[2] - zr; a[5] = pos[2] + zr;
+    } else if (g.type == 3) {     // dxCylinder::computeAABB cylinder.cpp:63-80
+        Real radius = g.p[0], lz = g.p[1];
+        Real m0 = (Real)(R_(1.0) - R[2] * R[2]), m1 = (Real)(R_(1.0) - R[6] * R[6]), m2 = (Real)(R_(1.0) - R[10] * R[10]);
+        Real xr = RFABS(R[2] * lz * R_(0.5)) + radius * RSQRT(m0 > R_(0.0) ? m0 : R_(0.0));
+        Real yr = RFABS(R[6] * lz * R_(0.5)) + radius * RSQRT(m1 > R_(0.0) ? m1 : R_(0.0));
+        Real zr = RFABS(R[10] * lz * R_(0.5)) + radius * RSQRT(m2 > R_(0.0) ? m2 : R_(0.0));
+        a[0] = pos[0] - xr; a[1] = pos[0] + xr; a[2] = pos[1] - yr; a[3] = pos[1] + yr; a[4] = pos[2] - zr; a[5] = pos[2] + zr;
+    } else if (g.type == 5) {     // dxRay::computeAABB ray.cpp:58-93
+        const Real len = g.p[0];
+        for (int k = 0; k < 3; k++) {
+            Real e = pos[k] + R[4 * k + 2] * len;
+            if (pos[k] < e) { a[2 * k] = pos[k]; a[2 * k + 1] = e; } else { a[2 * k] = e; a[2 * k + 1] = pos[k]; }
+        }
     } else {
         const Real *p = g.p;
         a[0] = -R_INF; a[1] = R_INF; a[2] = -R_INF; a[3] = R_INF; a[4] = -R_INF; a[5] = R_INF;
@@ -421,6 +434,7 @@ static inline int orc_box_plane(const OrcGeom &o1, const OrcGeom &o2, int flags,
 }
 
 #include "orc_capsule.h"
+#include "orc_ray_cyl.h"
 
 // dCollide collision_kernel.cpp:292-338 with the collider table of dInitColliders (:166-268):
 // direct entries (sphere,sphere) (sphere,box) (sphere,plane) (box,box) (box,plane) (capsule,sphere)
@@ -438,6 +452,13 @@ static inline int orc_collide_direct(const OrcGeom &a, const OrcGeom &b, int fla
     if (a.type == 2 && b.type == 1) return orc_capsule_box(a, b, flags, c);
     if (a.type == 2 && b.type == 2) return orc_capsule_capsule(a, b, flags, c);
     if (a.type == 2 && b.type == 4) return orc_capsule_plane(a, b, flags, c);
+    if (a.type == 5 && b.type == 0) return orc_ray_sphere(a, b, c);          // collision_kernel.cpp:191-194
+    if (a.type == 5 && b.type == 1) return orc_ray_box(a, b, c);
+    if (a.type == 5 && b.type == 2) return orc_ray_capsule(a, b, c);
+    if (a.type == 5 && b.type == 4) return orc_ray_plane(a, b, c);
+    if (a.type == 5 && b.type == 3) return orc_ray_cylinder(a, b, c);        // :195
+    if (a.type == 3 && b.type == 0) return orc_cylinder_sphere(a, b, c);     // :212-213 (cylinder-box :210 is not restated; cylinder-capsule
+    if (a.type == 3 && b.type == 4) return orc_cylinder_plane(a, b, flags, c); //  and cylinder-cylinder have no collider without libccd)
     *handled = 0;
     return 0;
 }

@@ -71,6 +71,7 @@ struct World {
     std::vector<int> pairs;
     std::vector<int> contact_g;
     std::vector<OrcContactGeom> last_cg;  // contact geoms of the last step (kept after dJointGroupEmpty)
+    std::vector<OrcContactGeom> ray_cg; std::vector<int> ray_g;   // ray hits of the last collide pass (sensor results: no joints)
     std::vector<int> island_label; int island_count;
     unsigned long long sweeps;
     unsigned step_seed; int cur_island; unsigned long long draws;   // canonical mode bookkeeping
@@ -331,7 +332,7 @@ void collide_world(const Batch &B, World &W)
         g.pos = g.fpos; g.R = g.fR;
     }
     find_pairs(B, W);
-    W.contacts.clear(); W.contact_g.clear();
+    W.contacts.clear(); W.contact_g.clear(); W.ray_cg.clear(); W.ray_g.clear();
     const OdebWorldParams &p = B.wp;
     OrcContactGeom cg[16];
     int npj = (int)W.pjoints.size();
@@ -342,6 +343,10 @@ void collide_world(const Batch &B, World &W)
         if (p.skip_connected && b1 >= 0 && b2 >= 0 && connected_excluding_contacts(W, b1, b2)) continue;
         if (b1 < 0 && b2 < 0) continue;
         int n = orc_collide(o1, o2, p.max_contacts, cg);
+        if (o1.type == ODEB_RAY || o2.type == ODEB_RAY) {      // sensor policy: the hit is recorded, no contact joint
+            for (int i = 0; i < n; i++) { W.ray_cg.push_back(cg[i]); W.ray_g.push_back(i1); W.ray_g.push_back(i2); }
+            continue;
+        }
         for (int i = 0; i < n; i++) {
             Joint j;
             memset(&j, 0, sizeof(j));
@@ -1165,6 +1170,18 @@ int orc_get_contacts(void *h, int world, Real *geom7, int *g12, int cap)
         for (int k = 0; k < 3; k++) { geom7[7 * i + k] = c.pos[k]; geom7[7 * i + 3 + k] = c.normal[k]; }
         geom7[7 * i + 6] = c.depth;
         g12[2 * i] = W.contact_g[2 * i]; g12[2 * i + 1] = W.contact_g[2 * i + 1];
+    }
+    return n;
+}
+int orc_get_ray_hits(void *h, int world, Real *geom7, int *g12, int cap)
+{
+    World &W = ((Batch *)h)->worlds[world];
+    int n = (int)W.ray_cg.size();
+    for (int i = 0; i < n && i < cap; i++) {
+        const OrcContactGeom &c = W.ray_cg[i];
+        for (int k = 0; k < 3; k++) { geom7[7 * i + k] = c.pos[k]; geom7[7 * i + 3 + k] = c.normal[k]; }
+        geom7[7 * i + 6] = c.depth;
+        g12[2 * i] = W.ray_g[2 * i]; g12[2 * i + 1] = W.ray_g[2 * i + 1];
     }
     return n;
 }

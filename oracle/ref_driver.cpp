@@ -43,6 +43,7 @@ struct RefWorld {
     dWorldQuickStepIterationCount_DynamicAdjustmentStatistics stats;
     // observables of the last step
     std::vector<int> pairs;              // 2 per pair
+    std::vector<dContactGeom> ray_hits; std::vector<int> ray_g;   // hits of ray geoms (no joints are made from them)
     std::vector<dContactGeom> contacts;
     std::vector<int> contact_g;          // 2 per contact
     std::vector<int> island_label;       // per body
@@ -166,6 +167,8 @@ void *ref_create(const OdebWorldParams *wp,
             case ODEB_BOX: id = dCreateBox(W.space, (dReal)g.p[0], (dReal)g.p[1], (dReal)g.p[2]); break;
             case ODEB_CAPSULE: id = dCreateCapsule(W.space, (dReal)g.p[0], (dReal)g.p[1]); break;
             case ODEB_PLANE: id = dCreatePlane(W.space, (dReal)g.p[0], (dReal)g.p[1], (dReal)g.p[2], (dReal)g.p[3]); break;
+            case ODEB_CYLINDER: id = dCreateCylinder(W.space, (dReal)g.p[0], (dReal)g.p[1]); break;
+            case ODEB_RAY: id = dCreateRay(W.space, (dReal)g.p[0]); break;
             default: return 0;
             }
             if (g.body >= 0) dGeomSetBody(id, W.bodies[g.body]);
@@ -316,8 +319,8 @@ static void ref_collide_world(RefBatch *B, RefWorld &W)
     CbCtx ctx; ctx.w = &W;
     dSpaceCollide(W.space, &ctx, &near_cb);
     std::sort(ctx.buf.begin(), ctx.buf.end());
-    W.pairs.clear(); W.contacts.clear(); W.contact_g.clear(); W.cjoints.clear();
-    dContact contact[8];
+    W.pairs.clear(); W.contacts.clear(); W.contact_g.clear(); W.cjoints.clear(); W.ray_hits.clear(); W.ray_g.clear();
+    dContact contact[9];
     for (size_t k = 0; k < ctx.buf.size(); k++) {
         int i1 = ctx.buf[k].first, i2 = ctx.buf[k].second;
         W.pairs.push_back(i1); W.pairs.push_back(i2);
@@ -326,6 +329,10 @@ static void ref_collide_world(RefBatch *B, RefWorld &W)
         if (p.skip_connected && b1 && b2 && dAreConnectedExcluding(b1, b2, dJointTypeContact)) continue;
         if (!b1 && !b2) continue;
         int n = dCollide(o1, o2, p.max_contacts, &contact[0].geom, sizeof(dContact));
+        if (dGeomGetClass(o1) == dRayClass || dGeomGetClass(o2) == dRayClass) {      // sensor policy: record the hit, no contact joint
+            for (int i = 0; i < n; i++) { W.ray_hits.push_back(contact[i].geom); W.ray_g.push_back(i1); W.ray_g.push_back(i2); }
+            continue;
+        }
         for (int i = 0; i < n; i++) {
             dSurfaceParameters &s = contact[i].surface;
             memset(&s, 0, sizeof(s));
@@ -453,6 +460,18 @@ int ref_get_pairs(void *h, int world, int *pairs, int cap)
     return n;
 }
 
+int ref_get_ray_hits(void *h, int world, dReal *geom7, int *g12, int cap)
+{
+    RefWorld &W = ((RefBatch *)h)->worlds[world];
+    int n = (int)W.ray_hits.size();
+    for (int i = 0; i < n && i < cap; i++) {
+        const dContactGeom &c = W.ray_hits[i];
+        for (int k = 0; k < 3; k++) { geom7[7 * i + k] = c.pos[k]; geom7[7 * i + 3 + k] = c.normal[k]; }
+        geom7[7 * i + 6] = c.depth;
+        g12[2 * i] = W.ray_g[2 * i]; g12[2 * i + 1] = W.ray_g[2 * i + 1];
+    }
+    return n;
+}
 int ref_get_contacts(void *h, int world, dReal *geom7, int *g12, int cap)
 {
     RefWorld &W = ((RefBatch *)h)->worlds[world];

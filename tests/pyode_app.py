@@ -56,8 +56,31 @@ def run(ode, nsteps=240, space_type=1):
     lm.setParam(ode.ParamVel, 0.6)
     lm.setParam(ode.ParamFMax, 30.0)
 
+    # a rolling wheel (cylinder on the plane) and a downward-looking range sensor (ray) riding on the cart
+    wheel = ode.Body(world)
+    M = ode.Mass()
+    M.setCylinder(600, 3, 0.25, 0.12)
+    wheel.setMass(M)
+    wheel.setPosition((0.0, 0.25, -1.5))
+    wheel.setAngularVel((0, 0, -4.0))
+    wg = ode.GeomCylinder(space, 0.25, 0.12)
+    wg.setBody(wheel)
+    wg.setCategoryBits(2)
+    wg.setCollideBits(1)                  # meets the floor only (floor category 1): keeps boxes away, the cylinder-box collider is not built
+    floor.setCategoryBits(1)
+    add(wheel, wg)
+    ray = ode.GeomRay(space, 2.0)
+    ray.setBody(cart)
+    ray.setOffsetRotation([1, 0, 0, 0, 0, -1, 0, 1, 0])          # local z -> world -y: looks down
+    ray.setCategoryBits(4)
+    ray.setCollideBits(1 | 8)
+    order[ray._id()] = len(order)
+    ranges = []
+
     def drop_object(k):
         body, geom = create_box(ode, world, space, 1000, 1.0, 0.2, 0.2)
+        geom.setCategoryBits(8)
+        geom.setCollideBits(1 | 4 | 8)
         body.setPosition((0.05 * sin(1.7 * k), 3.0, 0.05 * cos(2.3 * k)))
         theta = 2 * pi * ((0.618 * k) % 1.0)
         ct, st = cos(theta), sin(theta)
@@ -79,6 +102,10 @@ def run(ode, nsteps=240, space_type=1):
         for geom1, geom2 in sorted(pairs, key=lambda p: (order[p[0]._id()], order[p[1]._id()])):
             if ode.areConnected(geom1.getBody(), geom2.getBody()):
                 continue
+            if geom1 is ray or geom2 is ray:                     # sensor: note the range, make no joint
+                for c in ode.collide(geom1, geom2):
+                    ranges.append((step, order[geom1._id()], order[geom2._id()], c.getContactGeomParams()[2]))
+                continue
             for c in ode.collide(geom1, geom2):
                 c.setBounce(0.2)
                 c.setMu(5000)
@@ -88,5 +115,5 @@ def run(ode, nsteps=240, space_type=1):
         world.quickStep(dt)
         contactgroup.empty()
         log.append([b.getPosition() + b.getQuaternion() + b.getLinearVel() + b.getAngularVel() for b in bodies])
-    return dict(log=log, seed=ode.randGetSeed(), ncontacts=ncontacts, nbodies=len(bodies), npairs=len(pairs), space_len=len(space),
+    return dict(log=log, seed=ode.randGetSeed(), ranges=ranges, ncontacts=ncontacts, nbodies=len(bodies), npairs=len(pairs), space_len=len(space),
                 gravity=world.getGravity(), hinge_axis=hinge.getAxis(), mass=bodies[0].getMass().mass)

@@ -520,3 +520,51 @@ def test_motor_joints(prec):
         bad = compare_step(a, b, sc.nworlds, exact_float=False, tol=tol, what=("pairs", "contacts", "islands", "stats", "seeds", "state"))
         assert not bad, (s, bad[:4])
     b.close()
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_ray_and_cylinder_colliders(prec):
+    """Rays (sensor hits through odeb_get_ray_hits, no joints) and cylinders (plane / sphere colliders, AABB) on the GPU against the
+    oracle.  No libm transcendental on these colliders, but the scene also holds box-box pairs (cullPoints' atan2), so trajectories are
+    compared teacher-forced to the usual tolerance; pair sets, contact and hit lists (which geoms, how many) exactly, and the hit
+    geometry of the step (computed from identical poses) bit for bit."""
+    sc = scenes.sensors(8)
+    a, b = B.Batch(orc_lib(prec), sc), B.Batch(gpu_lib(prec), sc)
+    nhits = 0
+    for s in range(100):
+        st = a.get_state()
+        b.set_state(**st)
+        b.set_seeds(a.get_seeds())
+        a.set_state(**st)
+        a.step(0.01)
+        b.step(0.01)
+        bad = compare_step(a, b, sc.nworlds, exact_float=False, tol=TOL[prec], what=("pairs", "contacts", "islands", "stats", "seeds", "state"))
+        for w in range(sc.nworlds):
+            (ga, ia), (gb, ib) = a.get_ray_hits(w), b.get_ray_hits(w)
+            if not np.array_equal(ia, ib) or not np.array_equal(ga, gb):
+                bad.append("world %d: ray hits differ (%d vs %d)" % (w, len(ia), len(ib)))
+            nhits += len(ia)
+        assert not bad, (s, bad[:4])
+    assert nhits > 3000
+    b.close()
+    sc = scenes.sensors(1, n=60, extent=1.6)          # large-world path: same colliders behind the sort + sweep broadphase
+    a, b = _canon_pair(prec, sc)
+    for s in range(10):
+        a.step(0.01)
+        b.step(0.01)
+        bad = compare_step(a, b, 1, exact_float=False, tol=TOL[prec], what=("pairs", "contacts", "islands", "state"))
+        (ga, ia), (gb, ib) = a.get_ray_hits(0), b.get_ray_hits(0)
+        assert not bad and np.array_equal(ia, ib), (s, bad[:4])
+    b.close()
+
+
+def test_cylinder_box_scene_is_refused():
+    sc = B.Scene(B.default_world_params(), 1)
+    b0 = sc.add_body(1.0, np.eye(3), (0, 0, 1))
+    b1 = sc.add_body(1.0, np.eye(3), (0, 0, 2))
+    sc.add_geom(B.CYLINDER, (0.2, 0.5), body=b0)
+    sc.add_geom(B.BOX, (0.2, 0.5, 0.3), body=b1)
+    sc.state = dict(pos=np.array([[[0, 0, 1.0], [0, 0, 2.0]]]), quat=np.array([[[1.0, 0, 0, 0]] * 2]), lvel=np.zeros((1, 2, 3)), avel=np.zeros((1, 2, 3)))
+    sc.seeds = np.zeros(1, np.uint32)
+    with pytest.raises(RuntimeError):
+        B.Batch(gpu_lib("single"), sc)

@@ -17,7 +17,7 @@ def test_surface_matches_ode_pyx_names():
     """classes / functions / constants a script written for the reference's module expects"""
     for n in ("World", "Body", "Mass", "JointGroup", "Joint", "BallJoint", "HingeJoint", "SliderJoint", "UniversalJoint", "Hinge2Joint",
               "FixedJoint", "ContactJoint", "AMotor", "LMotor", "GeomObject", "SpaceBase", "SimpleSpace", "HashSpace", "Space", "GeomSphere",
-              "GeomBox", "GeomPlane", "GeomCapsule", "GeomCCylinder", "Contact", "collide", "areConnected", "InitODE", "CloseODE", "environment",
+              "GeomBox", "GeomPlane", "GeomCapsule", "GeomCCylinder", "GeomCylinder", "GeomRay", "Contact", "collide", "areConnected", "InitODE", "CloseODE", "environment",
               "ParamLoStop", "ParamHiStop2", "ParamFMax3", "ParamSuspensionERP", "paramVel", "ContactBounce", "ContactApprox1", "ContactSoftCFM",
               "AMotorUser", "AMotorEuler", "Infinity"):
         assert hasattr(ode, n), n
@@ -79,7 +79,8 @@ def test_script_runs_on_the_reference(prec):
         pytest.skip("oracle/_ref not built")
     ode.use(_ref(prec))
     out = pyode_app.run(ode, nsteps=120)
-    assert out["ncontacts"] > 100 and out["nbodies"] >= 6 and out["space_len"] == out["nbodies"] + 1
+    assert out["ncontacts"] > 100 and out["nbodies"] >= 6 and out["space_len"] == out["nbodies"] + 2
+    assert len(out["ranges"]) >= 100 and abs(out["ranges"][0][3] - 0.1) < 1e-3          # the cart's sensor sees the floor 0.1 below its centre
     assert np.isfinite(np.array(out["log"][-1])).all() and np.allclose(out["hinge_axis"], (0, 0, 1), atol=1e-6)
 
 
@@ -99,3 +100,5 @@ def test_script_reference_vs_b200(prec, space_type):
         d = float(np.abs(np.array(x) - np.array(y)).max())
         assert d <= tol, "state differs by %.3g at step %d" % (d, s)
     assert a["ncontacts"] == b["ncontacts"] and a["nbodies"] == b["nbodies"] and a["seed"] == b["seed"]
+    assert [r[:3] for r in a["ranges"]] == [r[:3] for r in b["ranges"]]
+    assert np.abs(np.array([r[3] for r in a["ranges"]]) - np.array([r[3] for r in b["ranges"]])).max() <= tol
