@@ -240,11 +240,12 @@ def gpu_arm(args):
     # ---- end-to-end through the C-ABI with host buffers: per step H2D of per-body forces (the "actions"),
     #      the step, D2H of the full body state (the "observations")
     real = slib.real
-    force = np.zeros((W, NBOX, 3), real)
+    force = batch.alloc_host((W, NBOX, 3))            # the application's action / observation arrays live in page-locked host memory
+    force[:] = 0
     force[:, -1, 0] = 0.01
     barrier()
     e2e_steps = max(3, min(args.steps, 20))
-    st = batch.get_state()                # the application's own observation buffers, reused every step
+    st = batch.get_state(out=batch.alloc_state())     # observation buffers, reused every step
     t0 = time.time()
     for s in range(e2e_steps):
         batch.add_force(force=force)
@@ -308,7 +309,7 @@ def gpu_arm(args):
                        "per_step": {"pairs": pairs / W, "contacts": contacts / W, "rows": rows / W, "islands": islands / W,
                                     "sweeps_per_island": sweeps / max(1, islands)}},
             "e2e": {"value": e2e_value, "unit": "body-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "odeb_add_force + odeb_step + odeb_get_state (host buffers)"},
+                    "steps": e2e_steps, "api": "odeb_add_force + odeb_step + odeb_get_state (page-locked host buffers from odeb_alloc_host)"},
             "gpu_launches": launches,
             "clocks": sampler.summary(),
             "roofline": roofline,

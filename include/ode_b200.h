@@ -162,6 +162,10 @@ const char *odeb_last_error(void);
  * Setting a quaternion normalises it and rebuilds R like dBodySetQuaternion (ode.cpp:330-343). */
 int odeb_set_state(OdebBatch *, const odeb_real *pos, const odeb_real *quat, const odeb_real *lvel, const odeb_real *avel);
 int odeb_get_state(OdebBatch *, odeb_real *pos, odeb_real *quat, odeb_real *lvel, odeb_real *avel);
+/* Page-locked host memory for the arrays handed to odeb_set/get_state and odeb_add_force: with it the transfers run straight between the
+ * device and the caller's arrays (pageable arrays work too, through an internal pinned staging buffer and one extra host copy). */
+void *odeb_alloc_host(size_t bytes);
+void odeb_free_host(void *);
 /* dBodyAddForce / dBodyAddTorque for every body: added to the accumulators consumed by the next step */
 int odeb_add_force(OdebBatch *, const odeb_real *force, const odeb_real *torque);
 /* per-world dRandSetSeed / dRandGetSeed (ode/src/misc.cpp:52-61) */

@@ -284,6 +284,27 @@ class Batch:
         arrs = [self._arr(pos, 3), self._arr(quat, 4), self._arr(lvel, 3), self._arr(avel, 3)]
         self.slib._fn("set_state")(self.h, *[_ptr(a) for a in arrs])
 
+    def alloc_host(self, shape):
+        """A numpy array of the library's real type in page-locked host memory (odeb_alloc_host): state / force arrays of this kind move
+        to and from the device without the staging copy.  Libraries without the entry point (oracle, reference driver) get np.empty."""
+        r = self.slib.real
+        if not hasattr(self.slib.lib, self.slib.prefix + "alloc_host"):
+            return np.empty(shape, r)
+        f = self.slib._fn("alloc_host")
+        f.restype, f.argtypes = C.c_void_p, [C.c_size_t]
+        n = int(np.prod(shape))
+        p = f(n * r.itemsize)
+        if not p:
+            raise RuntimeError("%salloc_host failed" % self.slib.prefix)
+        self._pinned = getattr(self, "_pinned", []) + [p]
+        ct = C.c_float if r == np.float32 else C.c_double
+        return np.ctypeslib.as_array((ct * n).from_address(p)).reshape(shape)
+
+    def alloc_state(self):
+        """observation buffers for get_state(out=...) in page-locked memory"""
+        return dict(pos=self.alloc_host((self.W, self.NB, 3)), quat=self.alloc_host((self.W, self.NB, 4)),
+                    lvel=self.alloc_host((self.W, self.NB, 3)), avel=self.alloc_host((self.W, self.NB, 3)))
+
     def get_state(self, out=None):
         """Body state as host arrays [W, NB, 3|4]. `out`: a dict returned by an earlier call, filled in place (the
         steady-state loop of an application that owns its observation buffers)."""

@@ -568,3 +568,25 @@ def test_cylinder_box_scene_is_refused():
     sc.seeds = np.zeros(1, np.uint32)
     with pytest.raises(RuntimeError):
         B.Batch(gpu_lib("single"), sc)
+
+
+def test_page_locked_host_arrays_take_the_direct_path():
+    """odeb_alloc_host arrays (transfers straight to / from the caller's memory) and pageable numpy arrays (staged) carry the same bytes"""
+    sc = scenes.box_stack(nworlds=5, nboxes=6)
+    a, b = B.Batch(gpu_lib("single"), sc), B.Batch(gpu_lib("single"), sc)
+    f_pin = a.alloc_host((sc.nworlds, sc.nbody, 3))
+    f_pin[:] = 0
+    f_pin[:, -1, 0] = 0.3
+    f_pag = np.array(f_pin)
+    st_pin = a.alloc_state()
+    for s in range(20):
+        a.add_force(force=f_pin, torque=f_pin)
+        b.add_force(force=f_pag, torque=f_pag)
+        a.step(0.02)
+        b.step(0.02)
+        sa, sb = a.get_state(out=st_pin), b.get_state()
+        for k in ("pos", "quat", "lvel", "avel"):
+            assert np.array_equal(sa[k], sb[k]), (s, k)
+    assert sa["pos"] is st_pin["pos"] and np.abs(sa["lvel"][:, -1, 0]).max() > 0
+    a.close()
+    b.close()
