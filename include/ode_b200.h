@@ -107,8 +107,8 @@ typedef struct OdebBodyDesc {
 typedef struct OdebGeomDesc {
     int    type;                /* ODEB_SPHERE: p[0]=radius; ODEB_BOX: p[0..2]=side lengths;
                                    ODEB_CAPSULE: p[0]=radius, p[1]=length; ODEB_PLANE: p[0..3]=a,b,c,d;
-                                   ODEB_CYLINDER: p[0]=radius, p[1]=length (collides with planes and spheres: collision_cylinder_plane.cpp,
-                                   collision_cylinder_sphere.cpp; a scene in which a cylinder can meet a box is rejected, capsules and other
+                                   ODEB_CYLINDER: p[0]=radius, p[1]=length (collides with planes, spheres and boxes:
+                                   collision_cylinder_plane.cpp, collision_cylinder_sphere.cpp, collision_cylinder_box.cpp; capsules and other
                                    cylinders pass through it as in the reference's default build, which has no collider for them);
                                    ODEB_RAY: p[0]=length, along the geom's local z axis (ray.cpp).  Rays are sensors: their hits are
                                    reported by odeb_get_ray_hits and never become contact joints */

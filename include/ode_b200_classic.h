@@ -18,7 +18,7 @@
  * stages: without a CUDA device dWorldQuickStep returns 0 and dSpaceCollide reports through the error handler.
  *
  * Outside the subset (calls are not exported): dWorldStep, joints other than contact/ball/hinge/slider/universal/hinge2/fixed/amotor/lmotor, geoms other
- * than sphere/box/capsule/cylinder/plane/ray (cylinder-box pairs excepted), nested spaces, per-body
+ * than sphere/box/capsule/cylinder/plane/ray, nested spaces, per-body
  * auto-disable thresholds (the world's are used), SAP axis orders other than dSAP_AXES_XYZ.
  */
 #ifndef ODE_B200_CLASSIC_H
@@ -352,7 +352,7 @@ unsigned long dGeomGetCollideBits(dGeomID);
 dReal dGeomSphereGetRadius(dGeomID);
 void dGeomBoxGetLengths(dGeomID, dVector3 result);
 void dGeomCapsuleGetParams(dGeomID, dReal *radius, dReal *length);
-dGeomID dCreateCylinder(dSpaceID, dReal radius, dReal length);   /* cylinder.cpp; colliders: plane, sphere, ray (cylinder-box: dCollide reports an error) */
+dGeomID dCreateCylinder(dSpaceID, dReal radius, dReal length);   /* cylinder.cpp; colliders: plane, sphere, box, ray */
 void dGeomCylinderSetParams(dGeomID, dReal radius, dReal length);
 void dGeomCylinderGetParams(dGeomID, dReal *radius, dReal *length);
 dGeomID dCreateRay(dSpaceID, dReal length);                      /* ray.cpp; colliders: sphere, box, capsule, plane, cylinder */

@@ -1257,9 +1257,6 @@ int dCollide(dGeomID o1, dGeomID o2, int flags, dContactGeom *contact, int skip)
     if (maxc < 1 || !contact || skip < (int)sizeof(dContactGeom)) { classic_error("dCollide: bad arguments"); return 0; }
     if (o1 == o2) return 0;
     if (o1->body == o2->body && o1->body) return 0;
-    if ((o1->type == ODEB_CYLINDER && o2->type == ODEB_BOX) || (o1->type == ODEB_BOX && o2->type == ODEB_CYLINDER)) {
-        classic_error("dCollide: the cylinder-box collider (collision_cylinder_box.cpp) is outside the supported subset"); return 0;
-    }
     dxSpace *s = o1->space;
     if (!s || o2->space != s) { classic_error("dCollide: both geoms must be in the same space"); return 0; }
     dxWorld *w = space_world(s);

@@ -721,9 +721,9 @@ __device__ int odeb_collide_direct(const DGeom &a, const DGeom &b, int flags, DC
     if (a.type == 5 && b.type == 2) return odeb_ray_capsule(a, b, c);
     if (a.type == 5 && b.type == 4) return odeb_ray_plane(a, b, c);
     if (a.type == 5 && b.type == 3) return odeb_ray_cylinder(a, b, c);
-    if (a.type == 3 && b.type == 0) return odeb_cylinder_sphere(a, b, c);     // :212-213; cylinder-box (:210) is not built (scenes that could
-    if (a.type == 3 && b.type == 4) return odeb_cylinder_plane(a, b, flags, c); // pair them are rejected at creation); no cylinder-capsule /
-                                                                              // cylinder-cylinder collider exists without libccd
+    if (a.type == 3 && b.type == 1) return odeb_cylinder_box(a, b, flags, c);   // :210
+    if (a.type == 3 && b.type == 0) return odeb_cylinder_sphere(a, b, c);     // :212-213; no cylinder-capsule / cylinder-cylinder collider
+    if (a.type == 3 && b.type == 4) return odeb_cylinder_plane(a, b, flags, c); // exists without libccd
     *handled = 0;
     return 0;
 }

@@ -545,14 +545,6 @@ OdebBatch *odeb_create(const OdebWorldParams *wp,
             T.gofs[i] = 1;
         }
     }
-    // the cylinder-box collider (collision_cylinder_box.cpp) is not built: a scene in which the broadphase could hand that pair to dCollide
-    // would silently lose contacts the reference makes, so it is refused
-    for (int i = 0; i < ngeom; i++) for (int j = 0; j < ngeom; j++) {
-        if (T.gtype[i] != ODEB_CYLINDER || T.gtype[j] != ODEB_BOX) continue;
-        if (T.gbody[i] == T.gbody[j] && T.gbody[i] >= 0) continue;
-        if (T.gbody[i] < 0 && T.gbody[j] < 0) continue;
-        if ((T.gcat[i] & T.gcol[j]) || (T.gcat[j] & T.gcol[i])) { set_err("geoms %d (cylinder) and %d (box) may collide: the cylinder-box collider is not supported (separate them with category / collide bits)", i, j); return 0; }
-    }
     T.jt.resize(njoint);
     std::vector<std::vector<std::pair<int, int> > > adj(nbody);
     for (int i = 0; i < njoint; i++) {

@@ -337,12 +337,12 @@ def motors(nworlds=1, seed0=91, dynamic_iterations=True):
     return sc
 
 
-def sensors(nworlds=1, n=24, seed0=500, extent=1.2, space_type=B.SPACE_SIMPLE):
+def sensors(nworlds=1, n=24, seed0=500, extent=1.2, space_type=B.SPACE_SIMPLE, cylinder_box=True):
     """Ray and cylinder colliders: n drifting bodies in zero gravity inside a cube of half-width `extent` above a ground plane, each
     carrying one of sphere / box / capsule / cylinder plus, on every second body, two ray geoms at offset poses (a forward "lidar" beam
     and a slanted one).  Rays report hits (odeb_get_ray_hits) and make no joints; cylinders collide with the plane and the spheres
-    (collision_cylinder_plane.cpp, collision_cylinder_sphere.cpp).  Boxes are kept away from cylinders by category bits (the
-    cylinder-box collider is the one piece not built); rays see everything."""
+    (collision_cylinder_plane.cpp, collision_cylinder_sphere.cpp) and the boxes (collision_cylinder_box.cpp; cylinder_box=False keeps
+    boxes and cylinders apart through category bits); rays see everything."""
     kw = dict(gravity=(0, 0, -2.0), max_contacts=4, surf_mode=B.CONTACT_APPROX1, mu=0.5, space_type=space_type)
     sc = B.Scene(B.default_world_params(**kw), nworlds)
     CAT_BOX, CAT_CYL, CAT_OTHER, CAT_RAY = 1, 2, 4, 8
@@ -356,11 +356,13 @@ def sensors(nworlds=1, n=24, seed0=500, extent=1.2, space_type=B.SPACE_SIMPLE):
         if kind == 0:
             sc.add_geom(B.SPHERE, (0.5 * size,), body=b, category=CAT_OTHER)
         elif kind == 1:
-            sc.add_geom(B.BOX, (size, 0.7 * size, 0.5 * size), body=b, category=CAT_BOX, collide=CAT_BOX | CAT_OTHER | CAT_RAY)
+            sc.add_geom(B.BOX, (size, 0.7 * size, 0.5 * size), body=b, category=CAT_BOX,
+                        collide=CAT_BOX | CAT_OTHER | CAT_RAY | (CAT_CYL if cylinder_box else 0))
         elif kind == 2:
             sc.add_geom(B.CAPSULE, (0.2 * size, 0.8 * size), body=b, category=CAT_OTHER)
         else:
-            sc.add_geom(B.CYLINDER, (0.4 * size, 0.6 * size), body=b, category=CAT_CYL, collide=CAT_CYL | CAT_OTHER | CAT_RAY)
+            sc.add_geom(B.CYLINDER, (0.4 * size, 0.6 * size), body=b, category=CAT_CYL,
+                        collide=CAT_CYL | CAT_OTHER | CAT_RAY | (CAT_BOX if cylinder_box else 0))
         if i % 2 == 0:
             sc.add_geom(B.RAY, (1.5,), body=b, category=CAT_RAY, offset_pos=(0, 0, 0.6 * size))
             sc.add_geom(B.RAY, (1.0,), body=b, category=CAT_RAY, offset_pos=(0.1, 0, 0), offset_quat=(s, 0.0, s, 0.0))
@@ -375,6 +377,38 @@ def sensors(nworlds=1, n=24, seed0=500, extent=1.2, space_type=B.SPACE_SIMPLE):
         quat[w] = q / np.linalg.norm(q, axis=1, keepdims=True)
         lvel[w] = 0.8 * (rw.rand(n, 3) - 0.5)
         avel[w] = 2.0 * (rw.rand(n, 3) - 0.5)
+    sc.state = dict(pos=pos, quat=quat, lvel=lvel, avel=avel)
+    sc.seeds = (seed0 + np.arange(nworlds)).astype(np.uint32)
+    return sc
+
+
+def cylinders_and_boxes(nworlds=1, n=30, seed0=700, extent=0.9):
+    """Cylinder-box collider exerciser (collision_cylinder_box.cpp): flat discs, long rods and ordinary cylinders tumbling among boxes of
+    mixed proportions in a small zero-gravity cube, so that face / edge / vertex / cap-edge separating axes and both clipping routines
+    (cylinder side line against the box, box face against the cap octagon) all come up."""
+    sc = B.Scene(B.default_world_params(gravity=(0, 0, 0), max_contacts=8, surf_mode=B.CONTACT_APPROX1, mu=0.3, space_type=B.SPACE_SIMPLE), nworlds)
+    r = _rng(seed0)
+    for i in range(n):
+        b = sc.add_body(1.0, np.eye(3) * 0.05, (0, 0, 0))
+        if i % 2 == 0:
+            shape = (i // 2) % 3
+            rad, length = ((0.35, 0.08), (0.08, 0.7), (0.2, 0.3))[shape]
+            sc.add_geom(B.CYLINDER, (rad * (0.8 + 0.4 * r.rand()), length * (0.8 + 0.4 * r.rand())), body=b)
+        else:
+            sc.add_geom(B.BOX, tuple(0.15 + 0.45 * r.rand(3)), body=b)
+    pos = np.zeros((nworlds, n, 3))
+    quat = np.zeros((nworlds, n, 4))
+    lvel = np.zeros((nworlds, n, 3))
+    avel = np.zeros((nworlds, n, 3))
+    for w in range(nworlds):
+        rw = _rng(seed0 + 1 + w)
+        pos[w] = extent * (2 * rw.rand(n, 3) - 1)
+        q = rw.randn(n, 4)
+        quat[w] = q / np.linalg.norm(q, axis=1, keepdims=True)
+        if w % 4 == 0:                      # axis-aligned poses too: parallel axes, zero cross products
+            quat[w, : n // 2] = (1, 0, 0, 0)
+        lvel[w] = 0.6 * (rw.rand(n, 3) - 0.5)
+        avel[w] = 1.5 * (rw.rand(n, 3) - 0.5)
     sc.state = dict(pos=pos, quat=quat, lvel=lvel, avel=avel)
     sc.seeds = (seed0 + np.arange(nworlds)).astype(np.uint32)
     return sc

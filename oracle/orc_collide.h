@@ -457,8 +457,9 @@ static inline int orc_collide_direct(const OrcGeom &a, const OrcGeom &b, int fla
     if (a.type == 5 && b.type == 2) return orc_ray_capsule(a, b, c);
     if (a.type == 5 && b.type == 4) return orc_ray_plane(a, b, c);
     if (a.type == 5 && b.type == 3) return orc_ray_cylinder(a, b, c);        // :195
-    if (a.type == 3 && b.type == 0) return orc_cylinder_sphere(a, b, c);     // :212-213 (cylinder-box :210 is not restated; cylinder-capsule
-    if (a.type == 3 && b.type == 4) return orc_cylinder_plane(a, b, flags, c); //  and cylinder-cylinder have no collider without libccd)
+    if (a.type == 3 && b.type == 1) return orc_cylinder_box(a, b, flags, c);   // :210
+    if (a.type == 3 && b.type == 0) return orc_cylinder_sphere(a, b, c);     // :212-213 (cylinder-capsule and cylinder-cylinder have no
+    if (a.type == 3 && b.type == 4) return orc_cylinder_plane(a, b, flags, c); //  collider without libccd)
     *handled = 0;
     return 0;
 }

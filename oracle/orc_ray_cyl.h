@@ -329,4 +329,261 @@ static inline int orc_cylinder_sphere(const OrcGeom &cy, const OrcGeom &sp, OrcC
         return 1;
     }
 }
+// ---- dCollideCylinderBox collision_cylinder_box.cpp:1026-1038 (Croteam's collider: 40 candidate separating axes, then either the
+// cylinder's side line clipped to the box or the nearest box face clipped to an octagon inscribed in the cylinder's cap)
+struct OrcCylBox {
+    Real cylR[12], cylPos[3], cylAxis[3], radius, size;
+    Real boxR[12], boxPos[3], half[3], vert[8][3];
+    Real diff[3], normal[3], bestDepth, bestrb, bestrc;
+    int bestAxis;
+};
+// the cap octagon's outward normals: -cos / -sin of pi/8 + k*pi/4 accumulated in dReal (collision_cylinder_box.cpp:183-197), as evaluated
+// by glibc (values generated with the reference's own expressions; the test against oracle/_ref pins them)
+#ifdef ODEB_DOUBLE
+#define ORC_CYLN { { -0x1.d906bcf328d46p-1, -0x1.87de2a6aea963p-2 }, { -0x1.87de2a6aea964p-2, -0x1.d906bcf328d46p-1 }, { 0x1.87de2a6aea962p-2, -0x1.d906bcf328d46p-1 }, \
+    { 0x1.d906bcf328d46p-1, -0x1.87de2a6aea965p-2 }, { 0x1.d906bcf328d47p-1, 0x1.87de2a6aea961p-2 }, { 0x1.87de2a6aea96dp-2, 0x1.d906bcf328d44p-1 }, \
+    { -0x1.87de2a6aea958p-2, 0x1.d906bcf328d48p-1 }, { -0x1.d906bcf328d44p-1, 0x1.87de2a6aea96ep-2 } }
+#else
+#define ORC_CYLN { { -0x1.d906bcp-1f, -0x1.87de2cp-2f }, { -0x1.87de2ap-2f, -0x1.d906bcp-1f }, { 0x1.87de3p-2f, -0x1.d906bcp-1f }, { 0x1.d906cp-1f, -0x1.87de2p-2f }, \
+    { 0x1.d906bap-1f, 0x1.87de3ap-2f }, { 0x1.87de16p-2f, 0x1.d906c2p-1f }, { -0x1.87de36p-2f, 0x1.d906bap-1f }, { -0x1.d906bep-1f, 0x1.87de2ap-2f } }
+#endif
+
+// _cldTestAxis :206-286
+static inline int orc_cb_test_axis(OrcCylBox &d, Real *n, int iAxis)
+{
+    Real fL = RSQRT(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    if (fL < R_(1e-5)) return 1;
+    normalize3(n);
+    Real fdot1 = dot3(d.cylAxis, n), frc;
+    if (fdot1 > R_(1.0)) frc = d.size * R_(0.5);
+    else if (fdot1 < R_(-1.0)) frc = d.size * R_(0.5);
+    else frc = RFABS(fdot1 * (d.size * R_(0.5))) + d.radius * RSQRT(R_(1.0) - (fdot1 * fdot1));
+    Real t[3];
+    t[0] = d.boxR[0]; t[1] = d.boxR[4]; t[2] = d.boxR[8];
+    Real frb = RFABS(dot3(t, n)) * d.half[0];
+    t[0] = d.boxR[1]; t[1] = d.boxR[5]; t[2] = d.boxR[9];
+    frb += RFABS(dot3(t, n)) * d.half[1];
+    t[0] = d.boxR[2]; t[1] = d.boxR[6]; t[2] = d.boxR[10];
+    frb += RFABS(dot3(t, n)) * d.half[2];
+    Real fd = dot3(d.diff, n);
+    Real fDepth = frc + frb;
+    if (RFABS(fd) > fDepth) return 0;
+    fDepth -= RFABS(fd);
+    if (fDepth < d.bestDepth) {
+        d.bestDepth = fDepth;
+        d.normal[0] = n[0]; d.normal[1] = n[1]; d.normal[2] = n[2];
+        d.bestAxis = iAxis; d.bestrb = frb; d.bestrc = frc;
+        if (fd > 0) { d.normal[0] = -d.normal[0]; d.normal[1] = -d.normal[1]; d.normal[2] = -d.normal[2]; }
+    }
+    return 1;
+}
+// _cldTestEdgeCircleAxis :289-333
+static inline int orc_cb_test_edge_circle(OrcCylBox &d, const Real *cc, const Real *v0, const Real *v1, int iAxis)
+{
+    Real e[3] = { v1[0] - v0[0], v1[1] - v0[1], v1[2] - v0[2] };
+    normalize3(e);
+    Real fdot2 = dot3(e, d.cylAxis);
+    if (RFABS(fdot2) < R_(1e-5)) return 1;
+    Real t1[3] = { cc[0] - v0[0], cc[1] - v0[1], cc[2] - v0[2] };
+    Real fdot1 = dot3(t1, d.cylAxis);
+    Real pnt[3] = { v0[0] + e[0] * (fdot1 / fdot2), v0[1] + e[1] * (fdot1 / fdot2), v0[2] + e[2] * (fdot1 / fdot2) };
+    Real tangent[3], axis[3];
+    t1[0] = cc[0] - pnt[0]; t1[1] = cc[1] - pnt[1]; t1[2] = cc[2] - pnt[2];
+    cross3(tangent, t1, d.cylAxis);
+    cross3(axis, tangent, e);
+    return orc_cb_test_axis(d, axis, iAxis);
+}
+// dClipEdgeToPlane collision_util.cpp:471-509
+static inline int orc_clip_edge_to_plane(Real *p0, Real *p1, const Real *pl)
+{
+    Real d0 = pl[0] * p0[0] + pl[1] * p0[1] + pl[2] * p0[2] + pl[3], d1 = pl[0] * p1[0] + pl[1] * p1[1] + pl[2] * p1[2] + pl[3];
+    if (d0 < 0 && d1 < 0) return 0;
+    else if (d0 > 0 && d1 > 0) return 1;
+    else if ((d0 > 0 && d1 < 0) || (d0 < 0 && d1 > 0)) {
+        Real ip[3];
+        ip[0] = p0[0] - (p0[0] - p1[0]) * d0 / (d0 - d1);
+        ip[1] = p0[1] - (p0[1] - p1[1]) * d0 / (d0 - d1);
+        ip[2] = p0[2] - (p0[2] - p1[2]) * d0 / (d0 - d1);
+        if (d0 < 0) { p0[0] = ip[0]; p0[1] = ip[1]; p0[2] = ip[2]; } else { p1[0] = ip[0]; p1[1] = ip[1]; p1[2] = ip[2]; }
+        return 1;
+    }
+    return 1;
+}
+// dClipPolyToPlane collision_util.cpp:512-557
+static inline void orc_clip_poly_to_plane(const Real (*in)[3], int ctIn, Real (*out)[3], int *ctOut, const Real *pl)
+{
+    int n = 0, i0 = ctIn - 1;
+    for (int i1 = 0; i1 < ctIn; i0 = i1, i1++) {
+        Real d0 = pl[0] * in[i0][0] + pl[1] * in[i0][1] + pl[2] * in[i0][2] + pl[3];
+        Real d1 = pl[0] * in[i1][0] + pl[1] * in[i1][1] + pl[2] * in[i1][2] + pl[3];
+        if (d0 >= 0) { out[n][0] = in[i0][0]; out[n][1] = in[i0][1]; out[n][2] = in[i0][2]; n++; }
+        if ((d0 > 0 && d1 < 0) || (d0 < 0 && d1 > 0)) {
+            out[n][0] = in[i0][0] - (in[i0][0] - in[i1][0]) * d0 / (d0 - d1);
+            out[n][1] = in[i0][1] - (in[i0][1] - in[i1][1]) * d0 / (d0 - d1);
+            out[n][2] = in[i0][2] - (in[i0][2] - in[i1][2]) * d0 / (d0 - d1);
+            n++;
+        }
+    }
+    *ctOut = n;
+}
+// dMatrix3Inv collision_util.h:199-235 (the adjugate is scaled by a double reciprocal of the dReal determinant)
+static inline void orc_matrix3_inv(const Real *ma, Real *dst)
+{
+    Real det = ma[0] * (ma[5] * ma[10] - ma[9] * ma[6]) - ma[1] * (ma[4] * ma[10] - ma[8] * ma[6]) + ma[2] * (ma[4] * ma[9] - ma[8] * ma[5]);
+    if (RFABS(det) < R_(0.0005)) { for (int k = 0; k < 12; k++) dst[k] = 0; dst[0] = dst[5] = dst[10] = 1; return; }
+    const double dr = (double)(R_(1.0) / det);
+    dst[0] = (Real)((ma[5] * ma[10] - ma[6] * ma[9]) * dr); dst[1] = (Real)((ma[9] * ma[2] - ma[1] * ma[10]) * dr); dst[2] = (Real)((ma[1] * ma[6] - ma[5] * ma[2]) * dr);
+    dst[4] = (Real)((ma[6] * ma[8] - ma[4] * ma[10]) * dr); dst[5] = (Real)((ma[0] * ma[10] - ma[8] * ma[2]) * dr); dst[6] = (Real)((ma[4] * ma[2] - ma[0] * ma[6]) * dr);
+    dst[8] = (Real)((ma[4] * ma[9] - ma[8] * ma[5]) * dr); dst[9] = (Real)((ma[8] * ma[1] - ma[0] * ma[9]) * dr); dst[10] = (Real)((ma[0] * ma[5] - ma[1] * ma[4]) * dr);
+    dst[3] = dst[7] = dst[11] = 0;
+}
+
+static inline int orc_cylinder_box(const OrcGeom &cy, const OrcGeom &bx, int flags, OrcContactGeom *c)
+{
+    const int maxc = flags & ORC_NUMC_MASK;
+    OrcCylBox d;
+    // _cldInitCylinderBox :100-203
+    for (int k = 0; k < 12; k++) { d.cylR[k] = cy.R[k]; d.boxR[k] = bx.R[k]; }
+    for (int k = 0; k < 3; k++) { d.cylPos[k] = cy.pos[k]; d.boxPos[k] = bx.pos[k]; d.half[k] = bx.p[k]; }
+    d.cylAxis[0] = d.cylR[2]; d.cylAxis[1] = d.cylR[6]; d.cylAxis[2] = d.cylR[10];
+    d.radius = cy.p[0]; d.size = cy.p[1];
+    d.half[0] *= R_(0.5); d.half[1] *= R_(0.5); d.half[2] *= R_(0.5);
+    {
+        const int sx[8] = { -1, 1, -1, 1, 1, 1, -1, -1 }, sy[8] = { 1, 1, -1, -1, 1, -1, -1, 1 }, sz[8] = { -1, -1, -1, -1, 1, 1, 1, 1 };
+        for (int i = 0; i < 8; i++) {
+            Real v[3] = { sx[i] < 0 ? -d.half[0] : d.half[0], sy[i] < 0 ? -d.half[1] : d.half[1], sz[i] < 0 ? -d.half[2] : d.half[2] }, t[3];
+            mul0_331(t, d.boxR, v);
+            d.vert[i][0] = t[0] + d.boxPos[0]; d.vert[i][1] = t[1] + d.boxPos[1]; d.vert[i][2] = t[2] + d.boxPos[2];
+        }
+    }
+    d.diff[0] = d.cylPos[0] - d.boxPos[0]; d.diff[1] = d.cylPos[1] - d.boxPos[1]; d.diff[2] = d.cylPos[2] - d.boxPos[2];
+    d.bestDepth = R_INF; d.normal[0] = d.normal[1] = d.normal[2] = 0; d.bestrb = 0; d.bestrc = 0; d.bestAxis = 0;
+    // _cldTestSeparatingAxes :336-573
+    {
+        Real ax[3], t1[3], t2[3], col[3];
+        const Real eps = R_(1e-6);
+        for (int k = 0; k < 3; k++) { ax[0] = d.boxR[k]; ax[1] = d.boxR[4 + k]; ax[2] = d.boxR[8 + k]; if (!orc_cb_test_axis(d, ax, 1 + k)) return 0; }
+        ax[0] = d.cylAxis[0]; ax[1] = d.cylAxis[1]; ax[2] = d.cylAxis[2];
+        if (!orc_cb_test_axis(d, ax, 4)) return 0;
+        for (int k = 0; k < 3; k++) {
+            col[0] = d.boxR[k]; col[1] = d.boxR[4 + k]; col[2] = d.boxR[8 + k];
+            cross3(ax, d.cylAxis, col);
+            if (ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2] > eps) if (!orc_cb_test_axis(d, ax, 5 + k)) return 0;
+        }
+        for (int i = 0; i < 8; i++) {
+            t1[0] = d.vert[i][0] - d.cylPos[0]; t1[1] = d.vert[i][1] - d.cylPos[1]; t1[2] = d.vert[i][2] - d.cylPos[2];
+            cross3(t2, d.cylAxis, t1);
+            cross3(ax, d.cylAxis, t2);
+            if (ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2] > eps) if (!orc_cb_test_axis(d, ax, 8 + i)) return 0;
+        }
+        const int e0[12] = { 1, 1, 2, 2, 4, 4, 0, 5, 5, 2, 4, 6 }, e1[12] = { 0, 3, 3, 0, 1, 7, 7, 3, 6, 6, 5, 7 };
+        Real cc[3];
+        for (int cap = 0; cap < 2; cap++) {
+            const Real hs = d.size * R_(0.5);
+            if (cap == 0) { cc[0] = d.cylPos[0] + d.cylAxis[0] * hs; cc[1] = d.cylPos[1] + d.cylAxis[1] * hs; cc[2] = d.cylPos[2] + d.cylAxis[2] * hs; }
+            else { cc[0] = d.cylPos[0] - d.cylAxis[0] * hs; cc[1] = d.cylPos[1] - d.cylAxis[1] * hs; cc[2] = d.cylPos[2] - d.cylAxis[2] * hs; }
+            for (int k = 0; k < 12; k++) if (!orc_cb_test_edge_circle(d, cc, d.vert[e0[k]], d.vert[e1[k]], 16 + 12 * cap + k)) return 0;
+        }
+    }
+    if (d.bestAxis == 0) return 0;
+    int nc = 0;
+    const Real fdot = dot3(d.normal, d.cylAxis);
+    if (RFABS(fdot) < R_(0.9)) {
+        // _cldClipCylinderToBox :576-717
+        Real vN[3], ep0[3], ep1[3], ct[3], pl[4], t[3];
+        const Real f1 = dot3(d.cylAxis, d.normal), hs = d.size * R_(0.5);
+        vN[0] = d.normal[0] - d.cylAxis[0] * f1; vN[1] = d.normal[1] - d.cylAxis[1] * f1; vN[2] = d.normal[2] - d.cylAxis[2] * f1;
+        normalize3(vN);
+        ct[0] = d.cylPos[0] + vN[0] * d.radius; ct[1] = d.cylPos[1] + vN[1] * d.radius; ct[2] = d.cylPos[2] + vN[2] * d.radius;
+        for (int k = 0; k < 3; k++) { ep0[k] = ct[k] + d.cylAxis[k] * hs; ep1[k] = ct[k] - d.cylAxis[k] * hs; }
+        for (int k = 0; k < 3; k++) { ep0[k] -= d.boxPos[k]; ep1[k] -= d.boxPos[k]; }
+        for (int k = 0; k < 6; k++) {
+            const int a = k % 3;
+            t[0] = d.boxR[a]; t[1] = d.boxR[4 + a]; t[2] = d.boxR[8 + a];
+            if (k >= 3) { t[0] = -t[0]; t[1] = -t[1]; t[2] = -t[2]; }
+            pl[0] = t[0]; pl[1] = t[1]; pl[2] = t[2]; pl[3] = d.half[a];
+            if (!orc_clip_edge_to_plane(ep0, ep1, pl)) return 0;
+        }
+        Real dep0 = d.bestrb + dot3(ep0, d.normal), dep1 = d.bestrb + dot3(ep1, d.normal);
+        if (dep0 < 0) dep0 = R_(0.0);
+        if (dep1 < 0) dep1 = R_(0.0);
+        for (int k = 0; k < 3; k++) { ep0[k] += d.boxPos[k]; ep1[k] += d.boxPos[k]; }
+        c[nc].depth = dep0;
+        for (int k = 0; k < 3; k++) { c[nc].normal[k] = -d.normal[k]; c[nc].pos[k] = ep0[k]; }
+        nc++;
+        if (nc != maxc) {
+            c[nc].depth = dep1;
+            for (int k = 0; k < 3; k++) { c[nc].normal[k] = -d.normal[k]; c[nc].pos[k] = ep1[k]; }
+            nc++;
+        }
+        return nc;
+    }
+    // _cldClipBoxToCylinder :720-982
+    {
+        Real ccp[3], cn[3] = { 0, 0, 0 };
+        const Real hs = d.size * R_(0.5);
+        if (dot3(d.cylAxis, d.normal) > R_(0.0)) { for (int k = 0; k < 3; k++) ccp[k] = d.cylPos[k] + d.cylAxis[k] * hs; cn[2] = R_(-1.0); }
+        else { for (int k = 0; k < 3; k++) ccp[k] = d.cylPos[k] - d.cylAxis[k] * hs; cn[2] = R_(1.0); }
+        Real vNr[3], inv[12], an[3];
+        orc_matrix3_inv(d.boxR, inv);
+        mul0_331(vNr, inv, d.normal);
+        an[0] = RFABS(vNr[0]); an[1] = RFABS(vNr[1]); an[2] = RFABS(vNr[2]);
+        int iB0, iB1, iB2;
+        if (an[1] > an[0]) {
+            if (an[0] > an[2]) { iB0 = 1; iB1 = 0; iB2 = 2; }
+            else if (an[1] > an[2]) { iB0 = 1; iB1 = 2; iB2 = 0; }
+            else { iB0 = 2; iB1 = 1; iB2 = 0; }
+        } else {
+            if (an[1] > an[2]) { iB0 = 0; iB1 = 1; iB2 = 2; }
+            else if (an[0] > an[2]) { iB0 = 0; iB1 = 2; iB2 = 1; }
+            else { iB0 = 2; iB1 = 0; iB2 = 1; }
+        }
+        Real ctr[3], t[3], a1[3], a2[3];
+        t[0] = d.boxR[iB0]; t[1] = d.boxR[4 + iB0]; t[2] = d.boxR[8 + iB0];
+        if (vNr[iB0] > 0) { for (int k = 0; k < 3; k++) ctr[k] = d.boxPos[k] - d.half[iB0] * t[k]; }
+        else { for (int k = 0; k < 3; k++) ctr[k] = d.boxPos[k] + d.half[iB0] * t[k]; }
+        Real pts[4][3], A1[16][3], A2[16][3];
+        for (int i = 0; i < 16; i++) for (int k = 0; k < 3; k++) { A1[i][k] = R_(0.0); A2[i][k] = R_(0.0); }
+        a1[0] = d.boxR[iB1]; a1[1] = d.boxR[4 + iB1]; a1[2] = d.boxR[8 + iB1];
+        a2[0] = d.boxR[iB2]; a2[1] = d.boxR[4 + iB2]; a2[2] = d.boxR[8 + iB2];
+        for (int k = 0; k < 3; k++) {
+            pts[0][k] = ctr[k] + d.half[iB1] * a1[k] - d.half[iB2] * a2[k];
+            pts[1][k] = ctr[k] - d.half[iB1] * a1[k] - d.half[iB2] * a2[k];
+            pts[2][k] = ctr[k] - d.half[iB1] * a1[k] + d.half[iB2] * a2[k];
+            pts[3][k] = ctr[k] + d.half[iB1] * a1[k] + d.half[iB2] * a2[k];
+        }
+        Real cinv[12];
+        orc_matrix3_inv(d.cylR, cinv);
+        for (int i = 0; i < 4; i++) {
+            t[0] = pts[i][0] - ccp[0]; t[1] = pts[i][1] - ccp[1]; t[2] = pts[i][2] - ccp[2];
+            mul0_331(pts[i], cinv, t);
+        }
+        int n1 = 0, n2 = 0;
+        Real pl[4] = { cn[0], cn[1], cn[2], R_(0.0) };
+        orc_clip_poly_to_plane(pts, 4, A1, &n1, pl);
+        const Real cyln[8][2] = ORC_CYLN;
+        int seg;
+        for (seg = 0; seg < 8; seg++) {
+            pl[0] = cyln[seg][0]; pl[1] = cyln[seg][1]; pl[2] = 0; pl[3] = d.radius;
+            if ((seg % 2) == 0) orc_clip_poly_to_plane(A1, n1, A2, &n2, pl);
+            else orc_clip_poly_to_plane(A2, n2, A1, &n1, pl);
+        }
+        const Real (*fin)[3] = (seg % 2) ? A2 : A1;
+        const int nf = (seg % 2) ? n2 : n1;
+        for (int i = 0; i < nf; i++) {
+            Real pt[3];
+            mul0_331(pt, d.cylR, fin[i]);
+            pt[0] += ccp[0]; pt[1] += ccp[1]; pt[2] += ccp[2];
+            t[0] = pt[0] - d.cylPos[0]; t[1] = pt[1] - d.cylPos[1]; t[2] = pt[2] - d.cylPos[2];
+            const Real depth = d.bestrc - dot3(t, d.normal);
+            if (depth > R_(0.0)) {
+                c[nc].depth = depth;
+                for (int k = 0; k < 3; k++) { c[nc].normal[k] = -d.normal[k]; c[nc].pos[k] = pt[k]; }
+                nc++;
+                if (nc == maxc) break;
+            }
+        }
+    }
+    return nc;
+}
 #endif

@@ -558,16 +558,31 @@ def test_ray_and_cylinder_colliders(prec):
     b.close()
 
 
-def test_cylinder_box_scene_is_refused():
-    sc = B.Scene(B.default_world_params(), 1)
-    b0 = sc.add_body(1.0, np.eye(3), (0, 0, 1))
-    b1 = sc.add_body(1.0, np.eye(3), (0, 0, 2))
-    sc.add_geom(B.CYLINDER, (0.2, 0.5), body=b0)
-    sc.add_geom(B.BOX, (0.2, 0.5, 0.3), body=b1)
-    sc.state = dict(pos=np.array([[[0, 0, 1.0], [0, 0, 2.0]]]), quat=np.array([[[1.0, 0, 0, 0]] * 2]), lvel=np.zeros((1, 2, 3)), avel=np.zeros((1, 2, 3)))
-    sc.seeds = np.zeros(1, np.uint32)
-    with pytest.raises(RuntimeError):
-        B.Batch(gpu_lib("single"), sc)
+@pytest.mark.parametrize("prec", PRECS)
+def test_cylinder_box_collider(prec):
+    """collision_cylinder_box.cpp on the GPU: discs, rods and cylinders among boxes (all 40 candidate axes, both clipping routines).  No
+    libm call at run time on this collider, but box-box pairs (cullPoints' atan2) share the scene: teacher-forced steps, sets exact,
+    contact geometry of the cylinder-box pairs bit for bit."""
+    sc = scenes.cylinders_and_boxes(16)
+    types = [g.type for g in sc.geoms]
+    a, b = B.Batch(orc_lib(prec), sc), B.Batch(gpu_lib(prec), sc)
+    ncb = 0
+    for s in range(50):
+        st = a.get_state()
+        b.set_state(**st)
+        b.set_seeds(a.get_seeds())
+        a.set_state(**st)
+        a.step(0.01)
+        b.step(0.01)
+        bad = compare_step(a, b, sc.nworlds, exact_float=False, tol=TOL[prec], what=("pairs", "contacts", "islands", "state"))
+        assert not bad, (s, bad[:4])
+        for w in range(sc.nworlds):
+            (ga, ia), (gb, ib) = a.get_contacts(w), b.get_contacts(w)
+            sel = np.array([{types[p[0]], types[p[1]]} == {1, 3} for p in ia], bool)
+            assert np.array_equal(ga[sel], gb[sel]), (s, w)
+            ncb += int(sel.sum())
+    assert ncb > 2000
+    b.close()
 
 
 def test_page_locked_host_arrays_take_the_direct_path():

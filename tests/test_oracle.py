@@ -366,3 +366,23 @@ def test_ray_and_cylinder_colliders_vs_reference(prec):
         assert not bad, (s, bad[:4])
         nhits += sum(len(b.get_ray_hits(w)[1]) for w in range(sc.nworlds))
     assert nhits > 5000
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_cylinder_box_collider_vs_reference(prec):
+    """dCollideCylinderBox (collision_cylinder_box.cpp): the restatement, incl. the cap octagon's constant normals and dMatrix3Inv's double
+    reciprocal, against the compiled reference on discs / rods / cylinders tumbling among boxes: every observable bit for bit."""
+    ref = ref_lib(prec)
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    sc = scenes.cylinders_and_boxes(16)
+    types = [g.type for g in sc.geoms]
+    a, b = B.Batch(ref, sc), B.Batch(orc_lib(prec), sc)
+    ncb = 0
+    for s in range(60):
+        a.step(0.01)
+        b.step(0.01)
+        bad = compare_step(a, b, sc.nworlds)
+        assert not bad, (s, bad[:4])
+        ncb += sum(1 for w in range(sc.nworlds) for p in b.get_contacts(w)[1] if {types[p[0]], types[p[1]]} == {1, 3})
+    assert ncb > 3000
