@@ -392,6 +392,7 @@ static OdebBatch *batch_build(const OdebWorldParams *wp, const HostTemplate &T, 
             else if (!strcmp(sel, "p4")) B->solver_force = 2;
             else if (!strcmp(sel, "p8")) B->solver_force = 3;
             else if (!strcmp(sel, "bl")) B->solver_force = 4;
+            else if (!strcmp(sel, "hy")) B->solver_force = 5;
         }
     }
 
@@ -421,7 +422,7 @@ static OdebBatch *batch_build(const OdebWorldParams *wp, const HostTemplate &T, 
             && dev_alloc(B, &D.island_info, WB) && dev_alloc(B, &D.nislands, W) && dev_alloc(B, &D.nordered, W) && dev_alloc(B, &D.njord, W) && dev_alloc(B, &D.mrows, W);
     ok = ok && dev_alloc(B, &D.rows, W * P.MR * 8) && dev_alloc(B, &D.rbody, W * P.MR) && dev_alloc(B, &D.findex, W * P.MR) && dev_alloc(B, &D.order, W * P.MR)
             && dev_alloc(B, &D.lambda, W * P.MR) && dev_alloc(B, &D.cforce, W * (nbody + 1) * 2) && dev_alloc(B, &D.invIw, WB * 12)
-            && dev_alloc(B, &D.stats, W * 4) && dev_alloc(B, &D.seed, W) && dev_alloc(B, &D.sweeps, 2 * W) && dev_alloc(B, &D.overflow, 2);
+            && dev_alloc(B, &D.stats, W * 4) && dev_alloc(B, &D.seed, W) && dev_alloc(B, &D.sweeps, 2 * W) && dev_alloc(B, &D.overflow, 2) && dev_alloc(B, &D.isl_done, WB);
     B->stage_elems = 4 * WB;                     // room for the tightly packed state of every body (13 reals) in one transfer
     ok = ok && dev_alloc(B, &B->d_stage, 4 * WB);
     if (ok && cudaMallocHost((void **)&B->h_stage, 4 * WB * sizeof(Real4)) != cudaSuccess) { set_err("cudaMallocHost failed"); ok = false; }
@@ -434,18 +435,22 @@ static OdebBatch *batch_build(const OdebWorldParams *wp, const HostTemplate &T, 
     if (ok) {   // opt every solver kernel into the full 227 KB of shared memory once (the attribute is per function, not per batch)
         const int mx = 227 * 1024;
         cudaError_t ce = cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_solve5<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_solve5<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_solve5<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_solve5_t<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_solve5_t<4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_solve5_t<8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_solve_hy, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_solve5_t<4, ODEB_HYBRID_SWEEPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
         if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_solve_bl<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
         if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_solve_bl<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
         if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_solve_bl<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
         if (ce != cudaSuccess) { set_err("cudaFuncSetAttribute(max dynamic shared memory) failed: %s", cudaGetErrorString(ce)); ok = false; }
         // the solvers live on shared memory and never reuse a global line through L1: ask for the largest carveout
         cudaFuncSetAttribute(k_solve, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(k_solve5<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(k_solve5<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(k_solve5<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_solve_hy, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_solve5_t<4, ODEB_HYBRID_SWEEPS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_solve5_t<2, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_solve5_t<4, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_solve5_t<8, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_solve_bl<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_solve_bl<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_solve_bl<32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -743,19 +748,46 @@ static int solve5_budget(OdebBatch *B, int k, int need)
     int sr = (need + 31) / 32 * 32;
     if (sr > B->P.MR) sr = B->P.MR;
     if (sr < need || sr > ODEB5_MAXROWS) return 0;
-    const size_t smem = odeb5_smem(1 << k, B->P.NB, sr);
+    size_t smem = odeb5_smem(1 << k, B->P.NB, sr);
     if (smem > 226 * 1024) return 0;
+    // Wave quantisation: every block holds 16 / P worlds and its shared memory decides how many blocks an SM holds.  4096 worlds x P = 4 are
+    // 1024 blocks = 6.9 per SM; with the generous row margin above a block took 32.5 KB, 6 fit, and the kernel ran two waves (1.77 ms
+    // instead of ~1.2).  When trimming the margin (never below the largest island seen, hint_m) brings the whole batch into one wave, do so;
+    // an island that outgrows the budget meanwhile takes the serial fallback for one step and raises the hint.
+    if (B->hint_m > 0) {
+        int nsm = 148;
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, B->device);
+        const long long blocks = ((long long)B->P.W + (16 >> k) - 1) / (16 >> k);
+        const long long per_sm = (blocks + nsm - 1) / nsm;
+        const size_t sm_bytes = 228 * 1024, reserve = 1024;
+        if (per_sm >= 1 && (smem + reserve) * (size_t)per_sm > sm_bytes) {
+            const int floor_sr = ((B->hint_m + 4) + 7) / 8 * 8;
+            for (int t = sr - 8; t >= floor_sr && t >= 8; t -= 8) {
+                const size_t b = odeb5_smem(1 << k, B->P.NB, t);
+                if ((b + reserve) * (size_t)per_sm <= sm_bytes) { sr = t; smem = b; break; }
+            }
+        }
+    }
     B->s5_sr[k] = sr; B->s5_smem[k] = smem;
     return sr;
 }
 
 // Which solver kernel the next step uses. The largest island of the previous call (hint_m) decides, so the first call after
 // creation runs k_solve.
+static bool hybrid_ok(OdebBatch *B, int need)
+{   // both halves must hold the islands (larger ones are completed by k_solve's own fallback), and the hand-over point has to lie
+    // before the first reorder and before the end of the regular iterations
+    // ... and the row stream should sit in L2 (126 MB): when it streams from HBM instead (65536 x 10-link chains: 350 MB) the one-row-at-a-time
+    // kernel alone is the faster one (4.25 against 4.79 ms per step)
+    const size_t stream_bytes = (size_t)B->P.W * (size_t)(B->hint_m > 0 ? B->hint_m : B->P.MR) * 32 * sizeof(Real);
+    return B->P.SR > 0 && (int)B->P.num_iter > ODEB_HYBRID_SWEEPS && stream_bytes <= ((size_t)128 << 20) && solve5_budget(B, 2, need) > 0;
+}
 static int choose_solver(OdebBatch *B)
 {
     const int f = B->solver_force;
     const int need = B->hint_m > 0 ? B->hint_m + B->hint_m / 8 + 8 : (B->P.MR < 512 ? B->P.MR : 512);
     if (f == 0) return 0;
+    if (f == 5) return (B->P.SR > 0 && (int)B->P.num_iter > ODEB_HYBRID_SWEEPS && solve5_budget(B, 2, need) > 0) ? 5 : 0;
     if (f == 4) return B->bl_G ? 4 : 0;
     if (f >= 1 && f <= 3) return solve5_budget(B, f, need) > 0 ? f : 0;
     if (B->hint_m <= 0) return 0;
@@ -768,6 +800,7 @@ static int choose_solver(OdebBatch *B)
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, B->device);
     const long long warps4 = ((long long)B->P.W + 3) / 4;
     if (warps4 * 2 <= 7LL * nsm || need > B->P.SR) { if (solve5_budget(B, 2, need) > 0) return 2; }
+    if (!getenv("ODEB_NO_HYBRID") && hybrid_ok(B, need)) return 5;     // large batches: see launch_dynamics, case 5
     return 0;
 }
 
@@ -785,15 +818,21 @@ static void launch_dynamics(OdebBatch *B, cudaStream_t s, bool timed, int cfg)
     cudaEvent_t e0 = 0, e1 = 0;
     if (timed) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s); }
     switch (cfg) {
-    case 1: k_solve5<2><<<nblk(W, 8), 32, B->s5_smem[1], s>>>(P, D, B->s5_sr[1]); break;
-    case 2: k_solve5<4><<<nblk(W, 4), 32, B->s5_smem[2], s>>>(P, D, B->s5_sr[2]); break;
-    case 3: k_solve5<8><<<nblk(W, 2), 32, B->s5_smem[3], s>>>(P, D, B->s5_sr[3]); break;
+    case 1: k_solve5_t<2, 0><<<nblk(W, 8), 32, B->s5_smem[1], s>>>(P, D, B->s5_sr[1]); break;
+    case 2: k_solve5_t<4, 0><<<nblk(W, 4), 32, B->s5_smem[2], s>>>(P, D, B->s5_sr[2]); break;
+    case 3: k_solve5_t<8, 0><<<nblk(W, 2), 32, B->s5_smem[3], s>>>(P, D, B->s5_sr[3]); break;
+    case 5:     // hybrid: the 8 sweeps in the initial order (long dependency chains: 136 schedule slots for 192 rows of a 16-box stack) one
+                // row at a time per world, the sweeps after the first dRand reorder (~52 slots) under the 4-processor schedule
+        k_solve_hy<<<nblk(W, ODEB_WPW), 32, B->solve_smem, s>>>(P, D, B->s5_sr[2]);
+        k_solve5_t<4, ODEB_HYBRID_SWEEPS><<<nblk(W, 4), 32, B->s5_smem[2], s>>>(P, D, B->s5_sr[2]);
+        B->launches++;
+        break;
     case 4:
         if (B->bl_G == 8) k_solve_bl<8><<<nblk(W, 4), 32, B->bl_smem, s>>>(P, D, B->bl_SR);
         else if (B->bl_G == 16) k_solve_bl<16><<<nblk(W, 2), 32, B->bl_smem, s>>>(P, D, B->bl_SR);
         else k_solve_bl<32><<<nblk(W, 1), 32, B->bl_smem, s>>>(P, D, B->bl_SR);
         break;
-    default: k_solve<<<nblk(W, ODEB_WPW), 32, B->solve_smem, s>>>(P, D);
+    default: k_solve<<<nblk(W, ODEB_WPW), 32, B->solve_smem, s>>>(P, D, 0);
     }
     if (timed) { cudaEventRecord(e1, s); B->pending.push_back(std::make_pair(e0, e1)); }
     if (D.jcopy) { k_feedback<<<nblk(W * P.NJT, 128), 128, 0, s>>>(P, D); B->launches++; }
@@ -823,7 +862,7 @@ int odeb_step_async(OdebBatch *B, double h, int nsteps)
     while (done < nsteps) {
         const bool graph_ok = B->use_graph && !B->timing;
         const int cfg = choose_solver(B);
-        const int cfg_sr = (cfg >= 1 && cfg <= 3) ? B->s5_sr[cfg] : 0;
+        const int cfg_sr = (cfg >= 1 && cfg <= 3) ? B->s5_sr[cfg] : (cfg == 5 ? B->s5_sr[2] : 0);
         if (graph_ok && (B->graph == 0 || B->graph_h != h || B->graph_cfg != cfg || B->graph_sr != cfg_sr)) {
             if (B->graph) { cudaGraphExecDestroy(B->graph); B->graph = 0; }
             cudaGraph_t g = 0;
@@ -842,7 +881,7 @@ int odeb_step_async(OdebBatch *B, double h, int nsteps)
         for (int s = 0; s < chunk; s++) {
             if (graph_ok) {
                 CK(cudaGraphLaunch(B->graph, B->stream));
-                B->launches += (B->P.NG > 0 ? 5 : 0) + (B->P.NJ > 0 ? 1 : 0) + 6 + (B->D.jcopy ? 1 : 0);
+                B->launches += (B->P.NG > 0 ? 5 : 0) + (B->P.NJ > 0 ? 1 : 0) + 6 + (cfg == 5 ? 1 : 0) + (B->D.jcopy ? 1 : 0);
             } else launch_step(B, B->stream, B->timing, cfg);
         }
         done += chunk;
@@ -999,7 +1038,7 @@ int odeb_restore(OdebBatch *B, const void *buf, size_t bytes)
 uint64_t odeb_launch_count(const OdebBatch *B) { return B->launches; }
 const char *odeb_solver_kernel(OdebBatch *B)
 {
-    static const char *names[5] = { "k_solve", "k_solve5<2>", "k_solve5<4>", "k_solve5<8>", "k_solve_bl" };
+    static const char *names[6] = { "k_solve", "k_solve5<2>", "k_solve5<4>", "k_solve5<8>", "k_solve_bl", "k_solve (8 sweeps) + k_solve5<4>" };
     if (B->mode == ODEB_MODE_CANONICAL) return "k_lw_sweep";
     return names[choose_solver(B)];
 }

@@ -102,6 +102,7 @@ struct DevPtrs {
     Real *invIw;                                 // [W*NB*12], indexed by order position
     unsigned *stats, *seed;                      // [W*4], [W]
     unsigned long long *sweeps;                  // [W*2] = (sweeps, row-sweeps) of the last step
+    int *isl_done;                               // [W*NB] hybrid solve: 1 = the island was completed by k_solve, 0 = k_solve5 continues it
     int *overflow;                               // [2] capacity overflow flag, largest island (rows) since the host last looked
 };
 

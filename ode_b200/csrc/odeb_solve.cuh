@@ -173,11 +173,13 @@ __device__ __forceinline__ void load_half(HalfRegs &h, const uint4 *slot)
 // Shared-memory solve of one island per world by the whole warp (lane pairs in lockstep). `m_own` is the island's
 // row count for this lane's world, 0 when the world has no island for this round (the pair then idles through
 // the row loop with stores predicated off).
+template <int HY>     // HY = number of sweeps after which a hybrid solve hands over to k_solve5 (0: plain kernel, compiled without any of it)
 __device__ __forceinline__ void solve_islands_warp(const DevParams &P, unsigned char *smem, int lane,
                                                    const Real4 *rows, const int *findex, const int2 *rbody, Real4 *cf_out, Real *lam_out,
                                                    int bstart, int nb, int rstart, int m_own, unsigned &seed,
                                                    unsigned &st1, unsigned &st2, unsigned &st3,
-                                                   unsigned long long &sweeps, unsigned long long &rowsweeps)
+                                                   unsigned long long &sweeps, unsigned long long &rowsweeps,
+                                                   const int pausable = 0, int *paused_out = 0)
 {
     constexpr int CH = ODEB_HALF_CHUNKS;
     const int wl = LANE_WL(lane), side = LANE_SIDE(lane);
@@ -211,6 +213,7 @@ __device__ __forceinline__ void solve_islands_warp(const DevParams &P, unsigned 
     Real exit_delta = P.premature_delta;
     CfShared cfs = { cf };
     int done = m_own > 0 ? 0 : 1;
+    int paused = 0;                 // hybrid solve (odeb_host.inl launch_dynamics): the island stops after `stop_after` sweeps and k_solve5 takes over
     unsigned iteration = 0, extra = 0;
     for (;;) {
         if (!done && iteration >= 8 && (iteration & 7) == 0) {
@@ -259,8 +262,10 @@ __device__ __forceinline__ void solve_islands_warp(const DevParams &P, unsigned 
         __syncwarp();
         d = __shfl_sync(ODEB_FULL, d, LANE_A(lane));
         done |= d;
+        if (HY) { if (pausable && !done && iteration == (unsigned)HY) { paused = 1; done = 1; } }   // before the first reorder: the seed is untouched
         if (__all_sync(ODEB_FULL, done)) break;
     }
+    if (HY) *paused_out = paused;
     if (m_own > 0) for (int k = side; k < 2 * nb; k += 2) cf_out[2 * bstart + k] = cf[(2 * bstart + k) * ODEB_WPW];
     if (lam_out && m_own > 0) for (int i = side; i < m_own; i += 2) lam_out[rstart + i] = lam[i * ODEB_WPW];   // joint feedback needs the final lambda
     __syncwarp();
@@ -295,8 +300,13 @@ __device__ __forceinline__ void row_update_global(const Real4 *r, int index, int
     }
 }
 
-__global__ void __launch_bounds__(32) k_solve(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D)
+// stop_after > 0: first half of the hybrid solve.  Islands of at most sr_b rows stop after `stop_after` sweeps (a multiple of 8 below
+// num_iterations, i.e. before any dRand draw and before the extra phase), leave their accumulators in cforce, lambda in D.lambda and
+// isl_done = 0; k_solve5 (resume) continues them.  Larger islands, and islands that finish early, are completed here (isl_done = 1).
+template <int HY>
+__global__ void __launch_bounds__(32) k_solve_t(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const int sr_b)
 {
+    constexpr int stop_after = HY;
     extern __shared__ __align__(32) unsigned char smem[];
     const int lane = threadIdx.x;
     const int side = LANE_SIDE(lane);
@@ -354,8 +364,11 @@ __global__ void __launch_bounds__(32) k_solve(const __grid_constant__ DevParams 
         __syncwarp();
         seed = __shfl_sync(ODEB_FULL, seed, LANE_A(lane));     // lane B replays the same dRand stream in the shared-memory path
         const int m_smem = (m > 0 && m <= P.SR) ? m : 0;
+        int paused = 0;
         if (__any_sync(ODEB_FULL, m_smem > 0))
-            solve_islands_warp(P, smem, lane, rows, findex, rbody, cf_out, D.jcopy ? D.lambda + (size_t)w * P.MR : 0, bstart, nb, rstart, m_smem, seed, st1, st2, st3, sweeps, rowsweeps);
+            solve_islands_warp<HY>(P, smem, lane, rows, findex, rbody, cf_out, (D.jcopy || stop_after) ? D.lambda + (size_t)w * P.MR : 0, bstart, nb, rstart, m_smem, seed, st1, st2, st3, sweeps, rowsweeps,
+                                   m_smem <= sr_b, &paused);
+        if (stop_after && side == 0 && is < nis && valid) D.isl_done[(size_t)w * P.NB + is] = paused ? 0 : 1;
         if (is < nis) st0++;
     }
     if (side == 0 && valid) {
@@ -365,4 +378,7 @@ __global__ void __launch_bounds__(32) k_solve(const __grid_constant__ DevParams 
         D.sweeps[2 * (size_t)w] = sweeps; D.sweeps[2 * (size_t)w + 1] = rowsweeps;
     }
 }
+#define ODEB_HYBRID_SWEEPS 8
+#define k_solve k_solve_t<0>
+#define k_solve_hy k_solve_t<ODEB_HYBRID_SWEEPS>
 #endif

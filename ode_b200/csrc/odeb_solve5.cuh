@@ -122,9 +122,13 @@ __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefe
         __syncwarp();                                                                                                    \
     }
 
-template <int P>
-__global__ void __launch_bounds__(32) k_solve5(const __grid_constant__ DevParams Pm, const __grid_constant__ DevPtrs D, const int SR5)
+// resume > 0: second half of the hybrid solve.  Islands k_solve paused after `resume` sweeps (D.isl_done == 0) are continued from their
+// accumulators (cforce) and lambda (D.lambda): ReorderPrep is rebuilt (it is deterministic), the reorder that the reference performs before
+// sweep resume + 1 is drawn here, and the sweeps go on under the P-processor schedule.  Islands with isl_done == 1 are left alone.
+template <int P, int RESUME>
+__global__ void __launch_bounds__(32) k_solve5_t(const __grid_constant__ DevParams Pm, const __grid_constant__ DevPtrs D, const int SR5)
 {
+    constexpr int resume = RESUME;
     extern __shared__ __align__(32) unsigned char smem[];
     constexpr int WPW = 16 / P;
     constexpr int CH = ODEB_HALF_CHUNKS;
@@ -170,7 +174,8 @@ __global__ void __launch_bounds__(32) k_solve5(const __grid_constant__ DevParams
 
     for (int is = 0; is < nis_max; is++) {
         int4 info = make_int4(0, 0, 0, 0);
-        if (is < nis) { info = iinfo[is]; if (leader) st0++; }
+        if (is < nis) { info = iinfo[is]; if (leader && !resume) st0++; }
+        if (resume && is < nis && D.isl_done[(size_t)w * Pm.NB + is]) info.w = 0;      // completed by k_solve
         const int bstart = info.x, nb = info.y, rstart = info.z, m = info.w;
         // islands beyond the row budget, or with a friction index the packed entry cannot hold, take the serial path
         const int m_try = (m > 0 && m <= SR5) ? m : 0;
@@ -197,9 +202,15 @@ __global__ void __launch_bounds__(32) k_solve5(const __grid_constant__ DevParams
         //      rows without a friction index first, quickstep.cpp:2329-2355)
         const Real4 z4 = { 0, 0, 0, 0 };
         if (m_own > 0) {
-            for (int k = wid; k < 2 * nb; k += 2 * P) CF5(bstart + (k >> 1), k & 1) = z4;
+            if (resume) {
+                const Real *lam_in = D.lambda + (size_t)w * Pm.MR + rstart;
+                for (int k = wid; k < 2 * nb; k += 2 * P) CF5(bstart + (k >> 1), k & 1) = cf_out[2 * bstart + k];
+                for (int i = wid; i <= m_own; i += 2 * P) lam[i * WPW] = i < m_own ? lam_in[i] : R_(0.0);
+            } else {
+                for (int k = wid; k < 2 * nb; k += 2 * P) CF5(bstart + (k >> 1), k & 1) = z4;
+                for (int i = wid; i <= m_own; i += 2 * P) lam[i * WPW] = 0;
+            }
             if (wid < 2) CF5(Pm.NB, wid) = z4;
-            for (int i = wid; i <= m_own; i += 2 * P) lam[i * WPW] = 0;
         }
         {
             int head = 0, tail = nfree;
@@ -222,9 +233,18 @@ __global__ void __launch_bounds__(32) k_solve5(const __grid_constant__ DevParams
         Real exit_delta = Pm.premature_delta;
         CfShared5<WPW> cfs = { cf };
         int done = m_own > 0 ? 0 : 1;
-        unsigned iteration = 0, extra = 0;
+        unsigned iteration = (unsigned)resume, extra = 0;
         int nslots = 0;
         bool resched = !done;
+        if (resume && !done && leader) {
+            // the reorder the reference performs at the top of iteration `resume` (a multiple of 8), quickstep.cpp:2578-2611
+            for (int idx = 1; idx < m_own; idx++) {
+                const int sw = odeb_rand_int(&seed, idx + 1);
+                const unsigned a = order[idx * WPW], b = order[sw * WPW];
+                order[idx * WPW] = b; order[sw * WPW] = a;
+            }
+        }
+        __syncwarp();
         for (;;) {
             if (__any_sync(ODEB_FULL, resched)) {
                 // ---- (re)build the schedule: clear the columns, then the leader list-schedules the order onto P processors
@@ -335,7 +355,8 @@ __global__ void __launch_bounds__(32) k_solve5(const __grid_constant__ DevParams
         D.seed[w] = seed;
         unsigned *st = D.stats + 4 * (size_t)w;
         st[0] += st0; st[1] += st1; st[2] += st2; st[3] += st3;
-        D.sweeps[2 * (size_t)w] = sweeps; D.sweeps[2 * (size_t)w + 1] = rowsweeps;
+        if (resume) { D.sweeps[2 * (size_t)w] += sweeps; D.sweeps[2 * (size_t)w + 1] += rowsweeps; }
+        else { D.sweeps[2 * (size_t)w] = sweeps; D.sweeps[2 * (size_t)w + 1] = rowsweeps; }
     }
 }
 #endif

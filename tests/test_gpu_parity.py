@@ -200,7 +200,7 @@ def test_canonical_mode_needs_single_world():
         b.set_solver_mode(1)
 
 
-SOLVERS = ("v4", "p2", "p4", "p8", "bl")
+SOLVERS = ("v4", "p2", "p4", "p8", "bl", "hy")
 
 
 @pytest.mark.parametrize("prec", PRECS)
@@ -229,7 +229,7 @@ def test_solver_kernels_bit_exact(prec, solver, monkeypatch):
 def test_solver_kernels_agree_at_bench_size(monkeypatch):
     """Full-size property check (BASELINE configs[1] shape, 512 worlds): the three kernels produce the same bits after 40 steps."""
     ref = None
-    for solver in ("v4", "p4", "bl"):
+    for solver in ("v4", "p4", "bl", "hy"):
         monkeypatch.setenv("ODEB_SOLVER", solver)
         b = B.Batch(gpu_lib("single"), scenes.box_stack(nworlds=512, demo_world_options=False))
         b.step(0.02, 40)
@@ -245,7 +245,7 @@ def test_solver_kernels_agree_at_bench_size(monkeypatch):
 
 
 @pytest.mark.parametrize("prec", PRECS)
-@pytest.mark.parametrize("solver", ("v4", "p4", "bl"))
+@pytest.mark.parametrize("solver", ("v4", "p4", "bl", "hy"))
 def test_joint_feedback_bit_exact(prec, solver, monkeypatch):
     """Joint feedback (dJointSetFeedback, quickstep.cpp:3108-3182) through the batch C-ABI: f1/t1/f2/t2 and the written /
     not-written state of every joint, CUDA path against the oracle, with every solver kernel (each writes lambda out)."""
