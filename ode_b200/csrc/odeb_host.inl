@@ -29,7 +29,7 @@ struct OdebBatch {
     // solver selection: 0 = k_solve (one row at a time per world), 1..3 = k_solve5<2/4/8> (static P-processor schedule),
     // 4 = k_solve_bl (one lane per body). hint_m = largest island (rows) seen since the last sync, read back in odeb_sync.
     int s5_sr[4]; size_t s5_smem[4]; int hint_m; int solver_force;   // s5_sr / s5_smem: row budget and shared memory of k_solve5<2^k> for the next launch
-    int graph_sr;
+    int graph_sr; int graph_nlaunch;          // kernels per replay of the captured step (counted while capturing)
     size_t isl_smem;                         // shared memory of k_islands_t<true> per block, 0 = scratch in global memory
     size_t solve_smem;
     int bl_G, bl_SR; size_t bl_smem;          // body-lane solver (odeb_solve_bl.cuh): lanes per world (0 = not used), row budget, bytes per warp
@@ -813,8 +813,11 @@ static void launch_dynamics(OdebBatch *B, cudaStream_t s, bool timed, int cfg)
     if (B->isl_smem) k_islands_t<true><<<nblk(W, 32), 32, B->isl_smem, s>>>(P, D);
     else k_islands_t<false><<<nblk(W, 32), 32, 0, s>>>(P, D);
     k_body_pre<<<nblk(W * P.NB, 128), 128, 0, s>>>(P, D);
-    k_rows<<<nblk(W * P.NJT, 64), 64, 0, s>>>(P, D);
-    k_rows_finish<<<nblk(W * P.MR, 128), 128, 0, s>>>(P, D);
+    if (P.NJ == 0 && !D.row_island && !getenv("ODEB_NO_FUSED_ROWS")) { k_rows_t<true><<<nblk(W * P.NJT, 64), 64, 0, s>>>(P, D); B->launches--; }
+    else {
+        k_rows_t<false><<<nblk(W * P.NJT, 64), 64, 0, s>>>(P, D);
+        k_rows_finish<<<nblk(W * P.MR, 128), 128, 0, s>>>(P, D);
+    }
     cudaEvent_t e0 = 0, e1 = 0;
     if (timed) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s); }
     switch (cfg) {
@@ -870,6 +873,7 @@ int odeb_step_async(OdebBatch *B, double h, int nsteps)
             CK(cudaStreamBeginCapture(B->stream, cudaStreamCaptureModeThreadLocal));
             launch_step(B, B->stream, false, cfg);
             CK(cudaStreamEndCapture(B->stream, &g));
+            B->graph_nlaunch = (int)(B->launches - l0);
             B->launches = l0;
             CK(cudaGraphInstantiate(&B->graph, g, 0));
             cudaGraphDestroy(g);
@@ -881,7 +885,7 @@ int odeb_step_async(OdebBatch *B, double h, int nsteps)
         for (int s = 0; s < chunk; s++) {
             if (graph_ok) {
                 CK(cudaGraphLaunch(B->graph, B->stream));
-                B->launches += (B->P.NG > 0 ? 5 : 0) + (B->P.NJ > 0 ? 1 : 0) + 6 + (cfg == 5 ? 1 : 0) + (B->D.jcopy ? 1 : 0);
+                B->launches += B->graph_nlaunch;
             } else launch_step(B, B->stream, B->timing, cfg);
         }
         done += chunk;

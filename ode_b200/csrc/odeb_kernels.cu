@@ -495,7 +495,74 @@ __global__ void k_body_pre(const __grid_constant__ DevParams P, const __grid_con
 
 __device__ __forceinline__ void atomic_add_real(Real *p, Real v) { atomicAdd(p, v); }
 
-__global__ void k_rows(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D)
+__device__ __forceinline__ Real modmax6(const Real *v)
+{   // dxCalculateModuloMaximum matrix.h:92-104
+    Real r = RFABS(v[0]);
+    for (int i = 1; i < 6; i++) { Real a = RFABS(v[i]); if (a > r) r = a; }
+    return r;
+}
+
+// rhs_tmp of one body (Stage2b quickstep.cpp:1644-1690), recomputed per row instead of staged
+__device__ __forceinline__ void body_rhs_tmp(const DevParams &P, const DevPtrs &D, int w, int pos, Real *out, Real *invI, Real *invMass)
+{
+    size_t go = (size_t)w * P.NB + pos;
+    int b = D.body_order[go];
+    size_t gb = (size_t)w * P.NB + b;
+    Real im = D.binvmass[b];
+    *invMass = im;
+    Real4 fa = D.facc[gb], ta = D.tacc[gb], lv = D.lvel[gb], av = D.avel[gb];
+    const Real *ii = D.invIw + 12 * go;
+    for (int i = 0; i < 12; i++) invI[i] = ii[i];
+    out[0] = -(fa.x * im + lv.x * P.hrecip);
+    out[1] = -(fa.y * im + lv.y * P.hrecip);
+    out[2] = -(fa.z * im + lv.z * P.hrecip);
+    Real tv[3] = { ta.x, ta.y, ta.z }, r[3];
+    mul0_331(r, invI, tv);
+    out[3] = -(av.x * P.hrecip) - r[0];
+    out[4] = -(av.y * P.hrecip) - r[1];
+    out[5] = -(av.z * P.hrecip) - r[2];
+}
+
+// Stage2c (rhs += J * rhs_tmp, quickstep.cpp:1023-1055), compute_invM_JT (:859-897) and Stage4LCP_AdComputation (:2251-2316) of one row, and
+// its final 8 x Real4 record (odeb_solve.cuh).  in/invI/im: body_rhs_tmp of the row's bodies.  Shared by k_rows_finish and the fused k_rows.
+__device__ __forceinline__ void finish_row(const DevParams &P, Real *q, const Real *in0, const Real *invI0, Real im0,
+                                           bool two, const Real *in1, const Real *invI1, Real im1, Real4 *Jp)
+{
+    Real imj[14];
+    Real sum = R_(0.0);
+    for (int k = 0; k < 6; k++) sum += q[C_J1L + k] * in0[k];
+    for (int k = 0; k < 3; k++) imj[k] = im0 * q[C_J1L + k];
+    mul0_331(imj + 3, invI0, q + C_J1A);
+    imj[6] = P.dyn_enabled ? modmax6(imj) : R_(0.0);
+    for (int k = 7; k < 14; k++) imj[k] = 0;
+    if (two) {
+        for (int k = 0; k < 6; k++) sum += q[C_J2L + k] * in1[k];
+        for (int k = 0; k < 3; k++) imj[7 + k] = im1 * q[C_J2L + k];
+        mul0_331(imj + 10, invI1, q + C_J2A);
+        imj[13] = P.dyn_enabled ? modmax6(imj + 7) : R_(0.0);
+    }
+    q[C_RHS] += sum;
+    Real s2 = R_(0.0);
+    for (int k = 0; k < 6; k++) s2 += imj[k] * q[C_J1L + k];
+    if (two) for (int k = 0; k < 6; k++) s2 += imj[7 + k] * q[C_J2L + k];
+    Real cfm_i = q[C_CFM];
+    Real Ad = P.sor_w / (s2 + cfm_i);
+    q[C_CFM] = cfm_i * Ad;
+    q[C_RHS] *= Ad;
+    for (int k = 0; k < 6; k++) q[C_J1L + k] *= Ad;
+    if (two) for (int k = 0; k < 6; k++) q[C_J2L + k] *= Ad;
+    Real4 a0 = { q[0], q[1], q[2], q[3] }, a1 = { q[4], q[5], q[6], q[7] };
+    Real4 a2 = { imj[0], imj[1], imj[2], imj[3] }, a3 = { imj[4], imj[5], imj[6], q[C_HI] };
+    Real4 b0 = { q[8], q[9], q[10], q[11] }, b1 = { q[12], q[13], q[C_LO], q[C_HI] };
+    Real4 b2 = { imj[7], imj[8], imj[9], imj[10] }, b3 = { imj[11], imj[12], imj[13], 0 };
+    Jp[0] = a0; Jp[1] = a1; Jp[2] = a2; Jp[3] = a3; Jp[4] = b0; Jp[5] = b1; Jp[6] = b2; Jp[7] = b3;
+}
+
+// FUSED (worlds without permanent joints: no limit motor can add body forces after a row was built, so the grid-wide ordering
+// Stage2a -> Stage2b of quickstep.cpp:1486-1690 is not needed): the thread finishes its rows itself (finish_row) and writes the final
+// records once, instead of k_rows_finish reading the half-built records back and rewriting them.
+template <bool FUSED>
+__global__ void k_rows_t(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D)
 {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (size_t)P.W * P.NJT) return;
@@ -544,11 +611,18 @@ __global__ void k_rows(const __grid_constant__ DevParams P, const __grid_constan
     int p0 = D.body_pos[(size_t)w * P.NB + b0i], p1 = b1i >= 0 ? D.body_pos[(size_t)w * P.NB + b1i] : -1;
     Real4 *rec = D.rows + ((size_t)w * P.MR + row0) * 8;
     int *fi = D.findex + (size_t)w * P.MR + row0;
+    Real in0[6], invI0[12], im0 = 0, in1[6], invI1[12], im1 = 0;
+    if (FUSED) {
+        body_rhs_tmp(P, D, w, p0, in0, invI0, &im0);
+        if (p1 != -1) body_rhs_tmp(P, D, w, p1, in1, invI1, &im1);
+    }
     for (int r = 0; r < m; r++) {
         Real *q = row + r * ROWLEN;
         q[C_RHS] *= P.hrecip; q[C_CFM] *= P.hrecip;
-        Real4 v0 = { q[0], q[1], q[2], q[3] }, v1 = { q[4], q[5], q[6], q[7] }, v2 = { q[8], q[9], q[10], q[11] }, v3 = { q[12], q[13], q[14], q[15] };
-        rec[8 * r] = v0; rec[8 * r + 1] = v1; rec[8 * r + 2] = v2; rec[8 * r + 3] = v3;
+        if (!FUSED) {
+            Real4 v0 = { q[0], q[1], q[2], q[3] }, v1 = { q[4], q[5], q[6], q[7] }, v2 = { q[8], q[9], q[10], q[11] }, v3 = { q[12], q[13], q[14], q[15] };
+            rec[8 * r] = v0; rec[8 * r + 1] = v1; rec[8 * r + 2] = v2; rec[8 * r + 3] = v3;
+        }
         if (D.jcopy) {   // Jcopy quickstep.cpp:1562-1583
             Real4 *jc = D.jcopy + ((size_t)w * P.MR + row0 + r) * 3;
             Real4 c0 = { q[C_J1L], q[C_J1L + 1], q[C_J1L + 2], q[C_J1A] }, c1 = { q[C_J1A + 1], q[C_J1A + 2], q[C_J2L], q[C_J2L + 1] },
@@ -560,8 +634,13 @@ __global__ void k_rows(const __grid_constant__ DevParams P, const __grid_constan
             D.row_island[row0 + r] = D.joint_island[t];
             D.row_group[row0 + r] = (jid >= P.NJ) ? row0 - (D.cinfo[(size_t)w * P.MC + (jid - P.NJ)].x % P.maxc) * m : row0;
         }
-        // body order positions travel in the last two slots of the record
-        *(int *)&rec[8 * r + 7].z = p0; *(int *)&rec[8 * r + 7].w = p1;
+        if (FUSED) {
+            finish_row(P, q, in0, invI0, im0, p1 != -1, in1, invI1, im1, rec + 8 * r);
+            D.rbody[(size_t)w * P.MR + row0 + r] = make_int2(p0, (p1 == -1) ? P.NB : p1);
+        } else {
+            // body order positions travel in the last two slots of the record
+            *(int *)&rec[8 * r + 7].z = p0; *(int *)&rec[8 * r + 7].w = p1;
+        }
     }
     if (has_f) {    // dBodyAddForce / dBodyAddTorque from a powered linear limit motor at its stop (joints/joint.cpp:688-704)
         Real *f0 = (Real *)&D.facc[(size_t)w * P.NB + b0i];
@@ -580,34 +659,6 @@ __global__ void k_rows(const __grid_constant__ DevParams P, const __grid_constan
     }
 }
 
-__device__ __forceinline__ Real modmax6(const Real *v)
-{   // dxCalculateModuloMaximum matrix.h:92-104
-    Real r = RFABS(v[0]);
-    for (int i = 1; i < 6; i++) { Real a = RFABS(v[i]); if (a > r) r = a; }
-    return r;
-}
-
-// rhs_tmp of one body (Stage2b quickstep.cpp:1644-1690), recomputed per row instead of staged
-__device__ __forceinline__ void body_rhs_tmp(const DevParams &P, const DevPtrs &D, int w, int pos, Real *out, Real *invI, Real *invMass)
-{
-    size_t go = (size_t)w * P.NB + pos;
-    int b = D.body_order[go];
-    size_t gb = (size_t)w * P.NB + b;
-    Real im = D.binvmass[b];
-    *invMass = im;
-    Real4 fa = D.facc[gb], ta = D.tacc[gb], lv = D.lvel[gb], av = D.avel[gb];
-    const Real *ii = D.invIw + 12 * go;
-    for (int i = 0; i < 12; i++) invI[i] = ii[i];
-    out[0] = -(fa.x * im + lv.x * P.hrecip);
-    out[1] = -(fa.y * im + lv.y * P.hrecip);
-    out[2] = -(fa.z * im + lv.z * P.hrecip);
-    Real tv[3] = { ta.x, ta.y, ta.z }, r[3];
-    mul0_331(r, invI, tv);
-    out[3] = -(av.x * P.hrecip) - r[0];
-    out[4] = -(av.y * P.hrecip) - r[1];
-    out[5] = -(av.z * P.hrecip) - r[2];
-}
-
 __global__ void k_rows_finish(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D)
 {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -620,41 +671,10 @@ __global__ void k_rows_finish(const __grid_constant__ DevParams P, const __grid_
       q[0] = v0.x; q[1] = v0.y; q[2] = v0.z; q[3] = v0.w; q[4] = v1.x; q[5] = v1.y; q[6] = v1.z; q[7] = v1.w;
       q[8] = v2.x; q[9] = v2.y; q[10] = v2.z; q[11] = v2.w; q[12] = v3.x; q[13] = v3.y; q[14] = v3.z; q[15] = v3.w; }
     int p0 = *(int *)&Mp[3].z, p1 = *(int *)&Mp[3].w;
-    Real in[6], invI[12], im;
-    Real imj[14];
-    // Stage2c multiplyAdd_J quickstep.cpp:1023-1055
-    Real sum = R_(0.0);
-    body_rhs_tmp(P, D, w, p0, in, invI, &im);
-    for (int k = 0; k < 6; k++) sum += q[C_J1L + k] * in[k];
-    // compute_invM_JT quickstep.cpp:859-897
-    for (int k = 0; k < 3; k++) imj[k] = im * q[C_J1L + k];
-    mul0_331(imj + 3, invI, q + C_J1A);
-    imj[6] = P.dyn_enabled ? modmax6(imj) : R_(0.0);
-    for (int k = 7; k < 14; k++) imj[k] = 0;
-    if (p1 != -1) {
-        body_rhs_tmp(P, D, w, p1, in, invI, &im);
-        for (int k = 0; k < 6; k++) sum += q[C_J2L + k] * in[k];
-        for (int k = 0; k < 3; k++) imj[7 + k] = im * q[C_J2L + k];
-        mul0_331(imj + 10, invI, q + C_J2A);
-        imj[13] = P.dyn_enabled ? modmax6(imj + 7) : R_(0.0);
-    }
-    q[C_RHS] += sum;
-    // Stage4LCP_AdComputation quickstep.cpp:2251-2316
-    Real s2 = R_(0.0);
-    for (int k = 0; k < 6; k++) s2 += imj[k] * q[C_J1L + k];
-    if (p1 != -1) for (int k = 0; k < 6; k++) s2 += imj[7 + k] * q[C_J2L + k];
-    Real cfm_i = q[C_CFM];
-    Real Ad = P.sor_w / (s2 + cfm_i);
-    q[C_CFM] = cfm_i * Ad;
-    q[C_RHS] *= Ad;
-    for (int k = 0; k < 6; k++) q[C_J1L + k] *= Ad;
-    if (p1 != -1) for (int k = 0; k < 6; k++) q[C_J2L + k] *= Ad;
-    // record = body-1 half | body-2 half (odeb_solve.cuh)
-    Real4 a0 = { q[0], q[1], q[2], q[3] }, a1 = { q[4], q[5], q[6], q[7] };
-    Real4 a2 = { imj[0], imj[1], imj[2], imj[3] }, a3 = { imj[4], imj[5], imj[6], q[C_HI] };
-    Real4 b0 = { q[8], q[9], q[10], q[11] }, b1 = { q[12], q[13], q[C_LO], q[C_HI] };
-    Real4 b2 = { imj[7], imj[8], imj[9], imj[10] }, b3 = { imj[11], imj[12], imj[13], 0 };
-    Jp[0] = a0; Jp[1] = a1; Jp[2] = a2; Jp[3] = a3; Jp[4] = b0; Jp[5] = b1; Jp[6] = b2; Jp[7] = b3;
+    Real in0[6], invI0[12], im0, in1[6], invI1[12], im1 = 0;
+    body_rhs_tmp(P, D, w, p0, in0, invI0, &im0);
+    if (p1 != -1) body_rhs_tmp(P, D, w, p1, in1, invI1, &im1);
+    finish_row(P, q, in0, invI0, im0, p1 != -1, in1, invI1, im1, Jp);
     D.rbody[t] = make_int2(p0, (p1 == -1) ? P.NB : p1);     // one-body rows address the dummy accumulator slot NB
 }
 

@@ -139,7 +139,7 @@ static int large_step(OdebBatch *B)
     // ---------------- QuickStep stages 0..3 (the batched path's kernels, W == 1)
     k_body_pre<<<nblk(NB, 128), 128, 0, s>>>(P, D);
     B->launches++;
-    if (hc[LWC_NJORD] > 0) { k_rows<<<nblk(hc[LWC_NJORD], 64), 64, 0, s>>>(P, D); B->launches++; }
+    if (hc[LWC_NJORD] > 0) { k_rows_t<false><<<nblk(hc[LWC_NJORD], 64), 64, 0, s>>>(P, D); B->launches++; }
     LCK(cudaMemsetAsync(D.cforce, 0, (size_t)(NB + 1) * 2 * sizeof(Real4), s));
     if (mrows > 0) {
         k_rows_finish<<<nblk(mrows, 128), 128, 0, s>>>(P, D);

@@ -439,7 +439,7 @@ __device__ void odeb_matrix3_inv(const Real *ma, Real *dst)
     dst[3] = dst[7] = dst[11] = 0;
 }
 
-__device__ int odeb_cylinder_box(const DGeom &cy, const DGeom &bx, int flags, DContactGeom *c)
+__device__ __noinline__ int odeb_cylinder_box(const DGeom &cy, const DGeom &bx, int flags, DContactGeom *c)
 {
     const int maxc = flags & ODEB_NUMC_MASK;
     DCylBox d;
