@@ -248,6 +248,11 @@ int odeb_get_contacts(OdebBatch *, int world, odeb_real *geom7, int *g12, int ca
 /* hits of the world's ray geoms (ODEB_RAY) in the last step's collide pass, in pair order: [pos3, normal3, depth = distance along the ray]
  * + (g1, g2); what a near-callback that treats rays as sensors collects with dCollide (ray.cpp) */
 int odeb_get_ray_hits(OdebBatch *, int world, odeb_real *geom7, int *g12, int cap);
+/* Range-sensor read-out for every world at once: range[world][ray] = distance to the nearest hit of the ray (ray geoms numbered in geom
+ * order, odeb_num_rays of them), +inf when it saw nothing; hit_geom[world][ray] = the geom it hit or -1 (either pointer may be NULL).
+ * Returns the number of rays per world. */
+int odeb_num_rays(OdebBatch *);
+int odeb_get_ray_ranges(OdebBatch *, odeb_real *range, int *hit_geom);
 int odeb_get_islands(OdebBatch *, int world, int *label_per_body);
 int odeb_get_stats(OdebBatch *, int world, OdebStats *out);
 /* totals over all worlds for the most recent step:

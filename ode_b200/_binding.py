@@ -421,6 +421,18 @@ class Batch:
             return self.get_ray_hits(world, n)
         return g[:n].copy(), ids[:n].copy()
 
+    def get_ray_ranges(self):
+        """(range[W, nray], hit_geom[W, nray]): nearest hit of every ray geom of every world in the last collide pass (inf / -1: none)"""
+        f = self.slib._fn("num_rays")
+        f.argtypes = [C.c_void_p]
+        nray = f(self.h)
+        rng = np.empty((self.W, nray), self.slib.real)
+        hit = np.empty((self.W, nray), np.int32)
+        g = self.slib._fn("get_ray_ranges")
+        g.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        g(self.h, _ptr(rng), _ptr(hit))
+        return rng, hit
+
     def get_islands(self, world):
         lab = np.empty(self.NB, np.int32)
         n = self.slib._fn("get_islands")(self.h, world, _ptr(lab))

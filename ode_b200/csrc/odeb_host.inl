@@ -412,7 +412,8 @@ static OdebBatch *batch_build(const OdebWorldParams *wp, const HostTemplate &T, 
             && dev_alloc(B, &D.sadj_ofs, nbody + 1) && dev_alloc(B, &D.sadj_joint, nadj) && dev_alloc(B, &D.sadj_other, nadj);
     ok = ok && dev_alloc(B, &D.aabb, WG * 6) && dev_alloc(B, &D.pair_cnt, WG) && dev_alloc(B, &D.pair_ofs, WG) && dev_alloc(B, &D.npairs, W)
             && dev_alloc(B, &D.pairs, W * P.MP) && dev_alloc(B, &D.pc_count, W * P.MP)
-            && (std::find(T.gtype.begin(), T.gtype.end(), (int)ODEB_RAY) == T.gtype.end() || classic || dev_alloc(B, &D.ray_count, W * P.MP)) && dev_alloc(B, &D.cgeom, W * (classic ? (size_t)P.MC : (size_t)P.MP * P.maxc) * 2)
+            && (std::find(T.gtype.begin(), T.gtype.end(), (int)ODEB_RAY) == T.gtype.end() || classic
+                || (dev_alloc(B, &D.ray_count, W * P.MP) && dev_alloc(B, &D.ray_geom, ngeom) && dev_alloc(B, &D.ray_range, WG) && dev_alloc(B, &D.ray_hit, WG))) && dev_alloc(B, &D.cgeom, W * (classic ? (size_t)P.MC : (size_t)P.MP * P.maxc) * 2)
             && dev_alloc(B, &D.ncontacts, W) && dev_alloc(B, &D.cinfo, W * P.MC) && dev_alloc(B, &D.jm, WJ) && dev_alloc(B, &D.jlimit, WJ);
     if (classic) ok = ok && dev_alloc(B, &D.csurf, (size_t)P.MC);
     ok = ok && dev_alloc(B, &D.c_ofs, W * (nbody + 1)) && dev_alloc(B, &D.c_cur, WB) && dev_alloc(B, &D.c_adj_c, W * 2 * P.MC) && dev_alloc(B, &D.c_adj_o, W * 2 * P.MC)
@@ -466,6 +467,12 @@ static OdebBatch *batch_build(const OdebWorldParams *wp, const HostTemplate &T, 
       && upload(D.gtype, T.gtype) && upload(D.gbody, T.gbody) && upload(D.gparam, T.gparam) && upload(D.gcat, T.gcat) && upload(D.gcol, T.gcol)
       && upload(D.gspose, T.gspose) && upload(D.gofs, T.gofs)
       && upload(D.joints, T.jt) && upload(D.sadj_ofs, T.sofs) && upload(D.sadj_joint, T.sj) && upload(D.sadj_other, T.so);
+    if (ok && D.ray_geom) {     // ray geoms in geom order (odeb_get_ray_ranges)
+        std::vector<int> rg;
+        for (int i = 0; i < ngeom; i++) if (T.gtype[i] == ODEB_RAY) rg.push_back(i);
+        D.nray = (int)rg.size();
+        ok = cudaMemcpy(D.ray_geom, rg.data(), rg.size() * sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess;
+    }
     // initial per-world state = template pose
     {
         std::vector<Real4> pos(WB), quat(WB), R(3 * WB);
@@ -1116,6 +1123,21 @@ int odeb_get_ray_hits(OdebBatch *B, int world, odeb_real *geom7, int *g12, int c
         g12[2 * n] = pr[p].x; g12[2 * n + 1] = pr[p].y;
     }
     return n;
+}
+
+int odeb_num_rays(OdebBatch *B) { return B->D.ray_count ? B->D.nray : 0; }
+int odeb_get_ray_ranges(OdebBatch *B, odeb_real *range, int *hit_geom)
+{
+    CK(cudaSetDevice(B->device));
+    DevPtrs &D = B->D;
+    if (!D.ray_count || D.nray == 0) return 0;
+    const size_t n = (size_t)B->P.W * D.nray;
+    k_ray_ranges<<<nblk(n, 128), 128, 0, B->stream>>>(B->P, D);
+    B->launches++;
+    if (range) CK(cudaMemcpyAsync(range, D.ray_range, n * sizeof(Real), cudaMemcpyDeviceToHost, B->stream));
+    if (hit_geom) CK(cudaMemcpyAsync(hit_geom, D.ray_hit, n * sizeof(int), cudaMemcpyDeviceToHost, B->stream));
+    CK(cudaStreamSynchronize(B->stream));
+    return D.nray;
 }
 
 int odeb_get_islands(OdebBatch *B, int world, int *label_per_body)

@@ -78,6 +78,8 @@ struct DevPtrs {
     int2 *pairs;                                 // [W*MP]
     int *pc_count; Real4 *cgeom;                 // [W*MP], [W*MP*maxc*2] (pos,depth | normal,0)
     int *ray_count;                              // [W*MP] hits of pairs with a ray geom: reported (odeb_get_ray_hits), never turned into joints
+    int *ray_geom; int nray;                     // [nray] geom index of every ray, in geom order
+    Real *ray_range; int *ray_hit;               // [W*nray] nearest hit of every ray in the last collide pass (k_ray_ranges)
     int *ncontacts; int4 *cinfo;                 // [W], [W*MC] = (slot, b0, b1, reverse)
     DSurface *csurf;                             // [MC] per-contact surface parameters (classic mode)
     // joints dynamic
@@ -821,6 +823,25 @@ __global__ void k_pack_state(size_t n, const Real4 *pos, const Real4 *quat, cons
     o = out + 3 * n + 4 * t;          o[0] = q.x; o[1] = q.y; o[2] = q.z; o[3] = q.w;
     o = out + 7 * n + 3 * t;          o[0] = l.x; o[1] = l.y; o[2] = l.z;
     o = out + 10 * n + 3 * t;         o[0] = a.x; o[1] = a.y; o[2] = a.z;
+}
+
+// Range-sensor read-out: nearest hit (smallest dContactGeom.depth = distance along the ray, ray.cpp) of every ray geom of every world in
+// the last collide pass, +inf / -1 when the ray saw nothing.  Thread per (world, ray); a world has a few dozen pairs at most.
+__global__ void k_ray_ranges(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D)
+{
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)P.W * D.nray) return;
+    const int w = (int)(t / D.nray), g = D.ray_geom[t % D.nray];
+    const int np = D.npairs[w];
+    const int2 *pr = D.pairs + (size_t)w * P.MP;
+    const int *rc = D.ray_count + (size_t)w * P.MP;
+    Real best = R_INF; int other = -1;
+    for (int p = 0; p < np; p++) {
+        if (rc[p] <= 0 || (pr[p].x != g && pr[p].y != g)) continue;
+        const Real d = D.cgeom[((size_t)w * P.MP + p) * P.maxc * 2].w;
+        if (d < best) { best = d; other = pr[p].x == g ? pr[p].y : pr[p].x; }
+    }
+    D.ray_range[t] = best; D.ray_hit[t] = other;
 }
 
 // dBodyAddForce / dBodyAddTorque for every body from tight [force 3n | torque 3n] arrays

@@ -546,6 +546,19 @@ def test_ray_and_cylinder_colliders(prec):
             nhits += len(ia)
         assert not bad, (s, bad[:4])
     assert nhits > 3000
+    # bulk read-out: nearest hit per ray and world, against the oracle's hit lists
+    rng, hit = b.get_ray_ranges()
+    rays = [i for i, g in enumerate(sc.geoms) if g.type == B.RAY]
+    assert rng.shape == (sc.nworlds, len(rays)) and np.isfinite(rng).sum() > 20
+    for w in range(sc.nworlds):
+        ga, ia = a.get_ray_hits(w)
+        for k, g in enumerate(rays):
+            sel = [j for j in range(len(ia)) if g in ia[j]]
+            if not sel:
+                assert np.isinf(rng[w, k]) and hit[w, k] == -1
+            else:
+                j = min(sel, key=lambda j: ga[j, 6])
+                assert rng[w, k] == ga[j, 6] and hit[w, k] == (ia[j][0] if ia[j][1] == g else ia[j][1])
     b.close()
     sc = scenes.sensors(1, n=60, extent=1.6)          # large-world path: same colliders behind the sort + sweep broadphase
     a, b = _canon_pair(prec, sc)
