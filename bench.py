@@ -249,7 +249,7 @@ def gpu_arm(args):
     t0 = time.time()
     for s in range(e2e_steps):
         batch.add_force(force=force)
-        batch.step(H)
+        batch.step_async(H)               # queued behind the force upload; get_state below is the blocking call of the step
         st = batch.get_state(out=st)
     torch.cuda.synchronize()
     e2e_t = time.time() - t0
@@ -309,7 +309,7 @@ def gpu_arm(args):
                        "per_step": {"pairs": pairs / W, "contacts": contacts / W, "rows": rows / W, "islands": islands / W,
                                     "sweeps_per_island": sweeps / max(1, islands)}},
             "e2e": {"value": e2e_value, "unit": "body-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "odeb_add_force + odeb_step + odeb_get_state (page-locked host buffers from odeb_alloc_host)"},
+                    "steps": e2e_steps, "api": "odeb_add_force + odeb_step_async + odeb_get_state (page-locked host buffers from odeb_alloc_host)"},
             "gpu_launches": launches,
             "clocks": sampler.summary(),
             "roofline": roofline,

@@ -388,6 +388,16 @@ class Batch:
                 msg = ": " + (fn() or b"").decode()
             raise RuntimeError("%sstep failed%s" % (self.slib.prefix, msg))
 
+    def step_async(self, h, nsteps=1):
+        """odeb_step_async: the steps are queued on the batch's stream; the next blocking call (get_state, sync, ...) waits for them.
+        Libraries without the entry point (oracle, reference driver) step synchronously."""
+        if not self.slib.has("step_async"):
+            return self.step(h, nsteps)
+        f = self.slib._fn("step_async")
+        f.restype, f.argtypes = C.c_int, [C.c_void_p, C.c_double, C.c_int]
+        if not f(self.h, float(h), int(nsteps)):
+            raise RuntimeError("%sstep_async failed" % self.slib.prefix)
+
     def get_totals(self):
         """[pairs, contacts, rows, islands, sweeps, row-sweeps] of the most recent step, summed over worlds"""
         out = (C.c_uint64 * 6)()
