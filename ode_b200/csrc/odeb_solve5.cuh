@@ -238,10 +238,12 @@ __global__ void __launch_bounds__(32) k_solve5_t(const __grid_constant__ DevPara
         bool resched = !done;
         if (resume && !done && leader) {
             // the reorder the reference performs at the top of iteration `resume` (a multiple of 8), quickstep.cpp:2578-2611
+            int sw = m_own > 1 ? odeb_rand_int(&seed, 2) : 0;        // the next draw is computed while this swap's loads are in flight
             for (int idx = 1; idx < m_own; idx++) {
-                const int sw = odeb_rand_int(&seed, idx + 1);
                 const unsigned a = order[idx * WPW], b = order[sw * WPW];
+                const int swn = idx + 1 < m_own ? odeb_rand_int(&seed, idx + 2) : 0;
                 order[idx * WPW] = b; order[sw * WPW] = a;
+                sw = swn;
             }
         }
         __syncwarp();
@@ -259,10 +261,16 @@ __global__ void __launch_bounds__(32) k_solve5_t(const __grid_constant__ DevPara
 #pragma unroll
                     for (int q = 0; q < P; q++) pf[q] = 0;
                     unsigned *mcol = meta + wl;
+                    // software-pipelined: the next row's entry and its bodies' last slots are loaded before this row's stores, then
+                    // patched if this row just moved them (the shared-memory round trip leaves the loop-carried chain)
+                    unsigned e = m_own > 0 ? order[0] : IDLE;
+                    int b1 = E5_B1(e), b2 = E5_B2(e);
+                    int l1 = last[b1 * WPW], l2 = last[b2 * WPW];
                     for (int i = 0; i < m_own; i++) {
-                        const unsigned e = order[i * WPW];
-                        const int b1 = E5_B1(e), b2 = E5_B2(e);
-                        const int l1 = last[b1 * WPW], l2 = last[b2 * WPW];
+                        unsigned en = IDLE;
+                        if (i + 1 < m_own) en = order[(i + 1) * WPW];
+                        const int b1n = E5_B1(en), b2n = E5_B2(en);
+                        int l1n = last[b1n * WPW], l2n = last[b2n * WPW];
                         const int r = l1 > l2 ? l1 : l2;
                         int best = -1, bestpf = -1, mn = 0, mnpf = pf[0];
 #pragma unroll
@@ -278,6 +286,9 @@ __global__ void __launch_bounds__(32) k_solve5_t(const __grid_constant__ DevPara
                         last[b1 * WPW] = (unsigned short)(slot + 1);
                         if (b2 != NBd) last[b2 * WPW] = (unsigned short)(slot + 1);
                         ns = ns > slot + 1 ? ns : slot + 1;
+                        if (b1n == b1 || b1n == b2) l1n = slot + 1;                     // b1n is a real body, so b1n == b2 implies b2 is one too
+                        if (b2n != NBd && (b2n == b1 || b2n == b2)) l2n = slot + 1;     // the dummy slot's entry stays 0
+                        e = en; b1 = b1n; b2 = b2n; l1 = l1n; l2 = l2n;
                     }
                 }
                 ns = __shfl_sync(ODEB_FULL, ns, wl);
@@ -333,10 +344,12 @@ __global__ void __launch_bounds__(32) k_solve5_t(const __grid_constant__ DevPara
                     shuffle = !d && iteration >= 8 && (iteration & 7) == 0;
                     if (shuffle) {
                         // ConstraintsShuffling quickstep.cpp:2578-2611 with dRandInt misc.cpp:78-139
+                        int sw = m_own > 1 ? odeb_rand_int(&seed, 2) : 0;
                         for (int idx = 1; idx < m_own; idx++) {
-                            const int sw = odeb_rand_int(&seed, idx + 1);
                             const unsigned a = order[idx * WPW], b = order[sw * WPW];
+                            const int swn = idx + 1 < m_own ? odeb_rand_int(&seed, idx + 2) : 0;
                             order[idx * WPW] = b; order[sw * WPW] = a;
+                            sw = swn;
                         }
                     }
                 }
