@@ -423,7 +423,7 @@ static OdebBatch *batch_build(const OdebWorldParams *wp, const HostTemplate &T, 
             && dev_alloc(B, &D.island_info, WB) && dev_alloc(B, &D.nislands, W) && dev_alloc(B, &D.nordered, W) && dev_alloc(B, &D.njord, W) && dev_alloc(B, &D.mrows, W);
     ok = ok && dev_alloc(B, &D.rows, W * P.MR * 8) && dev_alloc(B, &D.rbody, W * P.MR) && dev_alloc(B, &D.findex, W * P.MR) && dev_alloc(B, &D.order, W * P.MR)
             && dev_alloc(B, &D.lambda, W * P.MR) && dev_alloc(B, &D.cforce, W * (nbody + 1) * 2) && dev_alloc(B, &D.invIw, WB * 12)
-            && dev_alloc(B, &D.stats, W * 4) && dev_alloc(B, &D.seed, W) && dev_alloc(B, &D.sweeps, 2 * W) && dev_alloc(B, &D.overflow, 2) && dev_alloc(B, &D.isl_done, WB);
+            && dev_alloc(B, &D.stats, W * 4) && dev_alloc(B, &D.seed, W) && dev_alloc(B, &D.sweeps, 2 * W) && dev_alloc(B, &D.overflow, 2) && dev_alloc(B, &D.isl_done, WB) && dev_alloc(B, &D.maxpairs, 1);
     B->stage_elems = 4 * WB;                     // room for the tightly packed state of every body (13 reals) in one transfer
     ok = ok && dev_alloc(B, &B->d_stage, 4 * WB);
     if (ok && cudaMallocHost((void **)&B->h_stage, 4 * WB * sizeof(Real4)) != cudaSuccess) { set_err("cudaMallocHost failed"); ok = false; }
@@ -743,7 +743,7 @@ static void launch_collide(OdebBatch *B, cudaStream_t s, bool narrow)
     k_pair_scan<<<nblk(W, 64), 64, 0, s>>>(P, D);
     k_pair_pass<true><<<nblk(W * P.NG, 128), 128, 0, s>>>(P, D);
     B->launches += 4;
-    if (narrow) { k_narrow<<<nblk(W * P.MP, 64), 64, 0, s>>>(P, D); B->launches++; }
+    if (narrow) { k_narrow<<<nblk(W * P.MP, 64), 64, 0, s>>>(P, D, 1); B->launches++; }
 }
 
 // Row budget of k_solve5<2^k> for islands of up to `need` rows: 0 when it cannot be launched (bodies / rows beyond the packed

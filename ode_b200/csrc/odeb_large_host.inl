@@ -88,7 +88,7 @@ static int large_step(OdebBatch *B)
         k_bp_unpack<<<nblk(np > 0 ? np : 1, 256), 256, 0, s>>>(np, L.pair_key_s, D.pairs, D.npairs);
         B->launches++;
         if (np > 0) {
-            k_narrow<<<nblk(np, 64), 64, 0, s>>>(P, D);
+            k_narrow<<<nblk(np, 64), 64, 0, s>>>(P, D, 0);
             LCK(cub::DeviceScan::ExclusiveSum(L.tmp, L.tmp_bytes, D.pc_count, L.pc_base, np, s));
             k_lw_contact_fill<<<nblk(np, 128), 128, 0, s>>>(P, D, L, np);
             B->launches += 3;
