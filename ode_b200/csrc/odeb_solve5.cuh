@@ -16,7 +16,11 @@
 //     along the lane's own schedule column (4 stages: shared memory is what limits the number of resident warps; 8
 //     stages and an additional prefetch.global.L2 ODEB5_FAR slots ahead were measured and bring nothing for P = 4,
 //     profiles/r1_solver_variants.txt).  Idle slots carry the dummy body and have their copies and stores predicated off.
-// Lane layout: side = lane >> 4, column = lane & 15 = proc * WPW + world (WPW = 16 / P worlds per warp).
+// Lane layout: lane = proc * 2 WPW + side * WPW + world (WPW = 16 / P worlds per warp), schedule column = proc * WPW + world.  The two
+// lanes of a row (its body-1 / body-2 halves) are WPW lanes apart, i.e. in the same quarter-warp for P = 4: an LDS.128 / STS.128 phase then
+// holds, per world, the two bodies of ONE row (different bodies, neighbours in the island order for stacks and chains, hence different
+// CF5 colours) instead of the body-1 halves of two unrelated rows, which collided whenever their parities agreed (ODEB5_OLD_LANES: the
+// previous layout, side = lane >> 4).
 // One order / meta entry: row (bits 0..11) | row - friction-index row (12..14, 0 = none; the reference only ever points a
 // friction row at the normal row of its own contact, 1 or 2 rows back) | body-1 slot (15..22) | body-2 slot (23..30).
 #ifndef ODEB_SOLVE5_CUH
@@ -88,11 +92,11 @@ __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefe
         }                                                                                                                \
         ma = mp[((K) + ODEB5_RING) * 16];                               /* schedule entries for the next slot's copies */ \
         mf = mp[((K) + 1 + ODEB5_FAR) * 16];                                                                             \
-        const Real lo_b = shfl_xor1(ODEB_FULL, CUR.q1.z);               /* lane A receives lo from lane B */             \
+        const Real lo_b = __shfl_xor_sync(ODEB_FULL, CUR.q1.z, PARTNER5); /* lane A receives lo from lane B */           \
         const Real s = fa.x * CUR.q0.x + fa.y * CUR.q0.y + fa.z * CUR.q0.z + fa.w * CUR.q0.w + fb.x * CUR.q1.x + fb.y * CUR.q1.y; \
         const Real ta = (CUR.q1.z - old_lambda * CUR.q1.w) - s;         /* lane A: (rhs - lambda*cfm) - s1 */           \
         const Real mine = side ? s : ta;                                                                                 \
-        const Real other = shfl_xor1(ODEB_FULL, mine);                                                                   \
+        const Real other = __shfl_xor_sync(ODEB_FULL, mine, PARTNER5);                                                   \
         cp_async_wait<ODEB5_RING - 2>();                                                                                 \
         load_half(NXT, ring + (size_t)(((K) + 1) & (ODEB5_RING - 1)) * CH * 32);                                        \
         Real delta = side ? (other - mine) : (mine - other);            /* ((rhs - lambda*cfm) - s1) - s2 */             \
@@ -133,8 +137,15 @@ __global__ void __launch_bounds__(32) k_solve5_t(const __grid_constant__ DevPara
     constexpr int WPW = 16 / P;
     constexpr int CH = ODEB_HALF_CHUNKS;
     const int lane = threadIdx.x;
+#if defined(ODEB5_OLD_LANES)
+    constexpr int PARTNER5 = 16;
     const int side = lane >> 4, col = lane & 15;
     const int wl = col & (WPW - 1), proc = col / WPW;
+#else
+    constexpr int PARTNER5 = WPW;
+    const int wl = lane & (WPW - 1), side = (lane / WPW) & 1, proc = lane / (2 * WPW);
+    const int col = proc * WPW + wl;
+#endif
     const int wid = lane / WPW;                                   // index of the lane among its world's 2P lanes
     const unsigned wmask = ((WPW == 1) ? 0xffffffffu : (WPW == 2) ? 0x55555555u : (WPW == 4) ? 0x11111111u : 0x01010101u) << wl;
     const unsigned below = (1u << lane) - 1u;
