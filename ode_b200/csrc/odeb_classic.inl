@@ -1408,10 +1408,10 @@ int dWorldQuickStep(dWorldID w, Real stepsize)
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(B->stream));
     {
-        int ovh[2] = { 0, 0 };       // capacity overflow flag, largest island of this step (picks the solver kernel of the next one)
+        int ovh[4] = { 0, 0, 0, 0 };  // capacity overflow flag; largest island (rows, bodies) and island count of this step (pick the solver kernel of the next one)
         CK(cudaMemcpy(ovh, D.overflow, sizeof(ovh), cudaMemcpyDeviceToHost));
         const int ov = ovh[0];
-        if (ovh[1] > 0) { B->hint_m = ovh[1]; int z = 0; cudaMemcpy(D.overflow + 1, &z, sizeof(int), cudaMemcpyHostToDevice); }
+        if (ovh[1] > 0) { B->hint_m = ovh[1]; B->hint_nb = ovh[2]; B->hint_nis = ovh[3]; cudaMemset(D.overflow + 1, 0, 3 * sizeof(int)); }
         if (ov) { int z = 0; cudaMemcpy(D.overflow, &z, sizeof(int), cudaMemcpyHostToDevice); classic_error("dWorldQuickStep: device capacity overflow (%d)", ov); return 0; }
     }
     CK(cudaMemcpy(&seed, D.seed, sizeof(unsigned), cudaMemcpyDeviceToHost));

@@ -29,6 +29,8 @@ struct OdebBatch {
     // solver selection: 0 = k_solve (one row at a time per world), 1..3 = k_solve5<2/4/8> (static P-processor schedule),
     // 4 = k_solve_bl (one lane per body). hint_m = largest island (rows) seen since the last sync, read back in odeb_sync.
     int s5_sr[4]; size_t s5_smem[4]; int hint_m; int solver_force;   // s5_sr / s5_smem: row budget and shared memory of k_solve5<2^k> for the next launch
+    int s6_sr, s6_nbi; size_t s6_smem;        // k_solve6<P> (odeb_solve6.cuh): row / body budget per island and shared memory per warp for the next launch
+    int hint_nb, hint_nis;                    // largest island (bodies) and most islands with rows in one world seen so far
     int graph_sr; int graph_nlaunch;          // kernels per replay of the captured step (counted while capturing)
     size_t isl_smem;                         // shared memory of k_islands_t<true> per block, 0 = scratch in global memory
     size_t solve_smem;
@@ -331,7 +333,7 @@ static OdebBatch *batch_build(const OdebWorldParams *wp, const HostTemplate &T, 
     OdebBatch *B = new OdebBatch();
     B->device = device; B->bytes = 0; B->launches = 0; B->timing = false; B->solver_ms = 0; B->solver_launches = 0;
     B->mode = ODEB_MODE_REPLAY; B->large_ready = false; memset(&B->L, 0, sizeof(B->L));
-    B->graph = 0; B->graph_h = -1; B->graph_cfg = -1; B->graph_sr = -1; B->hint_m = 0; B->solver_force = -1; B->use_graph = getenv("ODEB_NO_GRAPH") == 0 && !classic; B->h_stage = 0; B->d_stage = 0; B->stream = 0; B->flush_buf = 0; B->flush_bytes = 0;
+    B->graph = 0; B->graph_h = -1; B->graph_cfg = -1; B->graph_sr = -1; B->hint_m = 0; B->hint_nb = 0; B->hint_nis = 0; B->s6_sr = 0; B->s6_nbi = 0; B->s6_smem = 0; B->solver_force = -1; B->use_graph = getenv("ODEB_NO_GRAPH") == 0 && !classic; B->h_stage = 0; B->d_stage = 0; B->stream = 0; B->flush_buf = 0; B->flush_bytes = 0;
     memset(&B->D, 0, sizeof(B->D));
     DevParams &P = B->P;
     memset(&P, 0, sizeof(P));
@@ -393,6 +395,10 @@ static OdebBatch *batch_build(const OdebWorldParams *wp, const HostTemplate &T, 
             else if (!strcmp(sel, "p8")) B->solver_force = 3;
             else if (!strcmp(sel, "bl")) B->solver_force = 4;
             else if (!strcmp(sel, "hy")) B->solver_force = 5;
+            else if (!strcmp(sel, "d1")) B->solver_force = 6;
+            else if (!strcmp(sel, "d2")) B->solver_force = 7;
+            else if (!strcmp(sel, "d4")) B->solver_force = 8;
+            else if (!strcmp(sel, "d8")) B->solver_force = 9;
         }
     }
 
@@ -421,9 +427,9 @@ static OdebBatch *batch_build(const OdebWorldParams *wp, const HostTemplate &T, 
             && dev_alloc(B, &D.body_order, WB) && dev_alloc(B, &D.body_pos, WB) && dev_alloc(B, &D.body_island, WB)
             && dev_alloc(B, &D.joint_order, W * P.NJT) && dev_alloc(B, &D.joint_row, W * P.NJT) && dev_alloc(B, &D.joint_island, W * P.NJT)
             && dev_alloc(B, &D.island_info, WB) && dev_alloc(B, &D.nislands, W) && dev_alloc(B, &D.nordered, W) && dev_alloc(B, &D.njord, W) && dev_alloc(B, &D.mrows, W);
-    ok = ok && dev_alloc(B, &D.rows, W * P.MR * 8) && dev_alloc(B, &D.rbody, W * P.MR) && dev_alloc(B, &D.findex, W * P.MR) && dev_alloc(B, &D.order, W * P.MR)
+    ok = ok && dev_alloc(B, &D.rows, W * P.MR * 8) && dev_alloc(B, &D.rbody, W * P.MR) && dev_alloc(B, &D.findex, W * P.MR) && dev_alloc(B, &D.order, W * P.MR) && dev_alloc(B, &D.order0, W * P.MR) && dev_alloc(B, &D.wkey, W) && dev_alloc(B, &D.wlist, W)
             && dev_alloc(B, &D.lambda, W * P.MR) && dev_alloc(B, &D.cforce, W * (nbody + 1) * 2) && dev_alloc(B, &D.invIw, WB * 12)
-            && dev_alloc(B, &D.stats, W * 4) && dev_alloc(B, &D.seed, W) && dev_alloc(B, &D.sweeps, 2 * W) && dev_alloc(B, &D.overflow, 2) && dev_alloc(B, &D.isl_done, WB) && dev_alloc(B, &D.maxpairs, 1);
+            && dev_alloc(B, &D.stats, W * 4) && dev_alloc(B, &D.seed, W) && dev_alloc(B, &D.sweeps, 2 * W) && dev_alloc(B, &D.overflow, 4) && dev_alloc(B, &D.isl_done, WB) && dev_alloc(B, &D.maxpairs, 1);
     B->stage_elems = 4 * WB;                     // room for the tightly packed state of every body (13 reals) in one transfer
     ok = ok && dev_alloc(B, &B->d_stage, 4 * WB);
     if (ok && cudaMallocHost((void **)&B->h_stage, 4 * WB * sizeof(Real4)) != cudaSuccess) { set_err("cudaMallocHost failed"); ok = false; }
@@ -441,6 +447,10 @@ static OdebBatch *batch_build(const OdebWorldParams *wp, const HostTemplate &T, 
         if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_solve5_t<8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
         if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_solve_hy, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
         if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_solve5_t<4, ODEB_HYBRID_SWEEPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_solve6_t<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_solve6_t<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_solve6_t<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_solve6_t<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
         if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_solve_bl<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
         if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_solve_bl<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
         if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_solve_bl<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
@@ -452,6 +462,10 @@ static OdebBatch *batch_build(const OdebWorldParams *wp, const HostTemplate &T, 
         cudaFuncSetAttribute(k_solve5_t<2, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_solve5_t<4, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_solve5_t<8, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_solve6_t<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_solve6_t<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_solve6_t<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_solve6_t<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_solve_bl<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_solve_bl<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_solve_bl<32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -779,6 +793,36 @@ static int solve5_budget(OdebBatch *B, int k, int need)
     return sr;
 }
 
+// Budget of k_solve6<2^k> (k = 0..2): rows and bodies per island with a margin over the largest island seen; 0 when it cannot be launched.
+static int solve6_budget(OdebBatch *B, int k)
+{
+    B->s6_sr = 0; B->s6_nbi = 0; B->s6_smem = 0;
+    const int hm = B->hint_m > 0 ? B->hint_m : (B->P.MR < 256 ? B->P.MR : 256);
+    const int hb = B->hint_nb > 0 ? B->hint_nb : (B->P.NB < 32 ? B->P.NB : 32);
+    // Margins over the largest island seen (an island that outgrows the budget before the hints are refreshed takes the serial path for a
+    // step): generous by default, trimmed when that lets one more warp live on an SM (shared memory decides how many worlds are resident,
+    // and the kernel is latency-bound: 64-body piles 4 -> 5 warps per SM).
+    int best_sr = 0, best_nbi = 0; size_t best_smem = 0; long long best_per_sm = -1;
+    for (int t = 0; t < 3; t++) {
+        const int mr = t == 0 ? hm / 8 + 8 : t == 1 ? hm / 16 + 8 : hm / 32 + 4;
+        const int mb = t == 0 ? hb / 4 + 2 : t == 1 ? hb / 8 + 2 : hb / 16 + 1;
+        int sr = (hm + mr + 7) / 8 * 8, nbi = hb + mb;
+        if (sr > B->P.MR) sr = (B->P.MR + 7) / 8 * 8;
+        if (nbi > B->P.NB) nbi = B->P.NB;
+        if (sr > ODEB5_MAXROWS) sr = ODEB5_MAXROWS / 8 * 8;
+        if (nbi > ODEB5_MAXBODIES - 1) nbi = ODEB5_MAXBODIES - 1;
+        if (sr < hm || nbi < hb) continue;
+        const size_t smem = odeb6_smem(1 << k, nbi, sr);
+        if (smem > 226 * 1024) continue;
+        long long per_sm = (long long)((228 * 1024) / (smem + 1024));
+        if (per_sm > 10) per_sm = 10;                                   // registers: ~200 per thread
+        if (per_sm > best_per_sm) { best_per_sm = per_sm; best_sr = sr; best_nbi = nbi; best_smem = smem; }
+    }
+    if (best_per_sm < 0) return 0;
+    B->s6_sr = best_sr; B->s6_nbi = best_nbi; B->s6_smem = best_smem;
+    return best_sr;
+}
+
 // Which solver kernel the next step uses. The largest island of the previous call (hint_m) decides, so the first call after
 // creation runs k_solve.
 static bool hybrid_ok(OdebBatch *B, int need)
@@ -797,7 +841,14 @@ static int choose_solver(OdebBatch *B)
     if (f == 5) return (B->P.SR > 0 && (int)B->P.num_iter > ODEB_HYBRID_SWEEPS && solve5_budget(B, 2, need) > 0) ? 5 : 0;
     if (f == 4) return B->bl_G ? 4 : 0;
     if (f >= 1 && f <= 3) return solve5_budget(B, f, need) > 0 ? f : 0;
+    if (f >= 6 && f <= 9) return solve6_budget(B, f - 6) > 0 ? f : 0;
     if (B->hint_m <= 0) return 0;
+    if (B->hint_nis >= 2 && !getenv("ODEB_NO_SOLVE6")) {
+        // worlds with several islands: independent walkers (odeb_solve6.cuh).  Measured on B200, 64-body piles, solver ms per step for
+        // P = 1 / 2 / 4 / 8 processors per world: 4096 worlds with one large island each 12.0 / 11.2 / 8.1 / 8.6 (k_solve5<4>: 9.3),
+        // 4096 settled piles (35 small islands per world) 6.6 / 6.9 / 6.4 / - (k_solve5<4>: 8.4), 16384 worlds - / 38.7 / 27.4 / 30.8.
+        if (solve6_budget(B, 2) > 0) return 8;
+    }
     // Measured on B200 (4096 x 16-box stacks, single; solver ms for W = 1024 / 2048 / 4096 worlds): k_solve 1.19 / 1.19 / 1.26,
     // k_solve5<4> 0.67 / 0.83 / 1.25, k_solve5<8> 0.78 / - / -, k_solve5<2> - / - / 1.39.  With more than ~3.5 warps per SM the
     // extra warps of the P-processor schedule contend for the SM's shared-memory pipe and the gain is gone, so P = 4 is used
@@ -833,8 +884,22 @@ static void launch_dynamics(OdebBatch *B, cudaStream_t s, bool timed, int cfg)
     case 3: k_solve5_t<8, 0><<<nblk(W, 2), 32, B->s5_smem[3], s>>>(P, D, B->s5_sr[3]); break;
     case 5:     // hybrid: the 8 sweeps in the initial order (long dependency chains: 136 schedule slots for 192 rows of a 16-box stack) one
                 // row at a time per world, the sweeps after the first dRand reorder (~52 slots) under the 4-processor schedule
-        k_solve_hy<<<nblk(W, ODEB_WPW), 32, B->solve_smem, s>>>(P, D, B->s5_sr[2]);
+        {   // ODEB_TEST_HY_ROWS (tests only): a smaller hand-over threshold, so that worlds mix islands that may and may not be paused
+            int srb = B->s5_sr[2];
+            if (const char *e = getenv("ODEB_TEST_HY_ROWS")) { const int v = atoi(e); if (v > 0 && v < srb) srb = v; }
+            k_solve_hy<<<nblk(W, ODEB_WPW), 32, B->solve_smem, s>>>(P, D, srb);
+        }
         k_solve5_t<4, ODEB_HYBRID_SWEEPS><<<nblk(W, 4), 32, B->s5_smem[2], s>>>(P, D, B->s5_sr[2]);
+        B->launches++;
+        break;
+    case 6: case 7: case 8: case 9:     // independent world walkers (odeb_solve6.cuh); the initial order of every island comes from k_reorder_prep
+        k_reorder_prep<<<nblk(W * 32, 128), 128, 0, s>>>(P, D);
+        k_world_sort<<<1, 1024, 0, s>>>(P, D);
+        B->launches++;
+        if (cfg == 6) k_solve6_t<1><<<nblk(W, 16), 32, B->s6_smem, s>>>(P, D, B->s6_sr, B->s6_nbi);
+        else if (cfg == 7) k_solve6_t<2><<<nblk(W, 8), 32, B->s6_smem, s>>>(P, D, B->s6_sr, B->s6_nbi);
+        else if (cfg == 8) k_solve6_t<4><<<nblk(W, 4), 32, B->s6_smem, s>>>(P, D, B->s6_sr, B->s6_nbi);
+        else k_solve6_t<8><<<nblk(W, 2), 32, B->s6_smem, s>>>(P, D, B->s6_sr, B->s6_nbi);
         B->launches++;
         break;
     case 4:
@@ -872,7 +937,7 @@ int odeb_step_async(OdebBatch *B, double h, int nsteps)
     while (done < nsteps) {
         const bool graph_ok = B->use_graph && !B->timing;
         const int cfg = choose_solver(B);
-        const int cfg_sr = (cfg >= 1 && cfg <= 3) ? B->s5_sr[cfg] : (cfg == 5 ? B->s5_sr[2] : 0);
+        const int cfg_sr = (cfg >= 1 && cfg <= 3) ? B->s5_sr[cfg] : (cfg == 5 ? B->s5_sr[2] : (cfg >= 6 ? B->s6_sr * 256 + B->s6_nbi : 0));
         if (graph_ok && (B->graph == 0 || B->graph_h != h || B->graph_cfg != cfg || B->graph_sr != cfg_sr)) {
             if (B->graph) { cudaGraphExecDestroy(B->graph); B->graph = 0; }
             cudaGraph_t g = 0;
@@ -897,10 +962,12 @@ int odeb_step_async(OdebBatch *B, double h, int nsteps)
         }
         done += chunk;
         if (probe && done < nsteps) {
-            int m = 0;
-            CK(cudaMemcpyAsync(&m, B->D.overflow + 1, sizeof(int), cudaMemcpyDeviceToHost, B->stream));
+            int m[3] = { 0, 0, 0 };
+            CK(cudaMemcpyAsync(m, B->D.overflow + 1, sizeof(m), cudaMemcpyDeviceToHost, B->stream));
             CK(cudaStreamSynchronize(B->stream));
-            if (m > B->hint_m) B->hint_m = m;
+            if (m[0] > B->hint_m) B->hint_m = m[0];
+            if (m[1] > B->hint_nb) B->hint_nb = m[1];
+            if (m[2] > B->hint_nis) B->hint_nis = m[2];
         }
     }
     CK(cudaGetLastError());
@@ -918,9 +985,9 @@ int odeb_sync(OdebBatch *B)
         cudaEventDestroy(B->pending[i].first); cudaEventDestroy(B->pending[i].second);
     }
     B->pending.clear();
-    int ovh[2] = { 0, 0 };
+    int ovh[4] = { 0, 0, 0, 0 };
     CK(cudaMemcpy(ovh, B->D.overflow, sizeof(ovh), cudaMemcpyDeviceToHost));
-    if (ovh[1] > 0) { B->hint_m = ovh[1]; CK(cudaMemset(B->D.overflow + 1, 0, sizeof(int))); }
+    if (ovh[1] > 0) { B->hint_m = ovh[1]; B->hint_nb = ovh[2]; B->hint_nis = ovh[3]; CK(cudaMemset(B->D.overflow + 1, 0, 3 * sizeof(int))); }
     const int ov = ovh[0];
     if (ov) {
         set_err("capacity overflow (%s): raise ODEB_MAX_PAIRS / ODEB_MAX_CONTACTS", ov == 1 ? "pairs" : ov == 2 ? "contacts" : "rows");
@@ -1049,7 +1116,7 @@ int odeb_restore(OdebBatch *B, const void *buf, size_t bytes)
 uint64_t odeb_launch_count(const OdebBatch *B) { return B->launches; }
 const char *odeb_solver_kernel(OdebBatch *B)
 {
-    static const char *names[6] = { "k_solve", "k_solve5<2>", "k_solve5<4>", "k_solve5<8>", "k_solve_bl", "k_solve (8 sweeps) + k_solve5<4>" };
+    static const char *names[10] = { "k_solve", "k_solve5<2>", "k_solve5<4>", "k_solve5<8>", "k_solve_bl", "k_solve (8 sweeps) + k_solve5<4>", "k_solve6<1>", "k_solve6<2>", "k_solve6<4>", "k_solve6<8>" };
     if (B->mode == ODEB_MODE_CANONICAL) return "k_lw_sweep";
     return names[choose_solver(B)];
 }
@@ -1175,3 +1242,13 @@ int odeb_get_totals(OdebBatch *B, uint64_t out[6])
 }
 
 } // extern "C"
+
+#if defined(ODEB6_PROF)
+// experiment builds only (tools/build_variant.sh): cycle accounting of k_solve6
+extern "C" int odeb_debug_prof(unsigned long long *out16, int reset)
+{
+    if (out16 && cudaMemcpyFromSymbol(out16, odeb6_prof, 16 * sizeof(unsigned long long)) != cudaSuccess) return 0;
+    if (reset) { unsigned long long z[16] = { 0 }; if (cudaMemcpyToSymbol(odeb6_prof, z, sizeof(z)) != cudaSuccess) return 0; }
+    return 1;
+}
+#endif

@@ -97,6 +97,8 @@ struct DevPtrs {
                                                  //   (layout in odeb_solve.cuh)
     int2 *rbody;                                 // [W*MR] accumulator slots (order positions) of the row's two bodies; one-body rows: (p0, NB)
     int *findex, *order; Real *lambda;           // [W*MR]
+    unsigned *wkey; int *wlist;                  // [W] work estimate of every world (k_reorder_prep) and the worlds sorted by it, heaviest first (k_solve6's block -> world map)
+    unsigned *order0;                            // [W*MR] ReorderPrep order of every island as packed schedule entries (k_reorder_prep, read by k_solve6)
     Real4 *jcopy;                                // [W*MR*3] J1l J1a J2l J2a of every row before any scaling (joint feedback on), else null
     Real4 *jfb;                                  // [W*NJT*4] per joint id: {f1, state} {t1, 0} {f2, 0} {t2, 0} (quickstep.cpp:3108-3182)
     int *row_island, *row_group;                 // [MR] island of every row, first row of the row's group (large-world path only, else null)
@@ -105,7 +107,8 @@ struct DevPtrs {
     unsigned *stats, *seed;                      // [W*4], [W]
     unsigned long long *sweeps;                  // [W*2] = (sweeps, row-sweeps) of the last step
     int *isl_done;                               // [W*NB] hybrid solve: 1 = the island was completed by k_solve, 0 = k_solve5 continues it
-    int *overflow;                               // [2] capacity overflow flag, largest island (rows) since the host last looked
+    int *overflow;                               // [4] capacity overflow flag; since the host last looked: largest island (rows), largest island
+                                                 //     with rows (bodies), most islands with rows in one world
     int *maxpairs;                               // [1] most pairs of any world in this collide pass (k_pair_scan): k_narrow packs its threads by it
 };
 
@@ -412,7 +415,7 @@ __global__ void __launch_bounds__(32) k_islands_t(const __grid_constant__ DevPar
     const int *jm = D.jm + (size_t)w * NJ;
     for (int b = 0; b < NB; b++) { btag[b * S] = 0; bisl[b] = -1; bpos[b] = -1; }
     for (int j = 0; j < NJ + nc; j++) jtag[j * S] = 0;
-    int nbo = 0, njo = 0, nis = 0, rows = 0;
+    int nbo = 0, njo = 0, nis = 0, rows = 0, nis_rows = 0, max_mi = 0, max_nbi = 0;
     for (int bb = NB - 1; bb >= 0; bb--) {
         if (btag[bb * S]) continue;
         if (bflags[bb] & BF_DISABLED) { btag[bb * S] = -1; continue; }
@@ -447,10 +450,12 @@ __global__ void __launch_bounds__(32) k_islands_t(const __grid_constant__ DevPar
         }
         if (rstart + mi > P.MR) { atomicExch(D.overflow, 3); mi = 0; }
         iinfo[nis] = make_int4(bstart, nbo - bstart, rstart, mi);
-        if (mi > 0) atomicMax(D.overflow + 1, mi);          // largest island of the call: the host picks the solver kernel from it
+        if (mi > 0) { nis_rows++; if (mi > max_mi) max_mi = mi; if (nbo - bstart > max_nbi) max_nbi = nbo - bstart; }
         rows += mi;
         nis++;
     }
+    // largest island / most islands of the call: the host picks the solver kernel and its shared-memory budget from them
+    if (max_mi > 0) { atomicMax(D.overflow + 1, max_mi); atomicMax(D.overflow + 2, max_nbi); atomicMax(D.overflow + 3, nis_rows); }
     D.nislands[w] = nis; D.nordered[w] = nbo; D.njord[w] = njo; D.mrows[w] = rows;
 }
 
@@ -729,6 +734,7 @@ __global__ void k_feedback(const __grid_constant__ DevParams P, const __grid_con
 #include "odeb_solve.cuh"
 #include "odeb_solve_bl.cuh"
 #include "odeb_solve5.cuh"
+#include "odeb_solve6.cuh"
 #include "odeb_large.cuh"
 
 // ------------------------------------------------------------------------------------------------

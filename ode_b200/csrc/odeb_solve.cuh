@@ -323,6 +323,11 @@ __global__ void __launch_bounds__(32) k_solve_t(const __grid_constant__ DevParam
     const int4 *iinfo = D.island_info + (size_t)w * P.NB;
     const int nis = valid ? D.nislands[w] : 0;
     const int nis_max = __reduce_max_sync(ODEB_FULL, nis);
+    // Hybrid solve: islands are handed over to k_solve5 only if EVERY island of the world can be (or finishes before the hand-over).  An
+    // island completed here draws its reorders from the world's seed at once; were an earlier island of the same world paused, it would
+    // draw later (in k_solve5) what the reference gives it first, and both islands would see different random orders.
+    bool world_pausable = stop_after != 0;
+    if (stop_after) for (int is = 0; is < nis; is++) if (iinfo[is].w > sr_b || iinfo[is].w > P.SR) world_pausable = false;
     for (int is = 0; is < nis_max; is++) {
         int4 info = make_int4(0, 0, 0, 0);
         if (is < nis) info = iinfo[is];
@@ -367,7 +372,7 @@ __global__ void __launch_bounds__(32) k_solve_t(const __grid_constant__ DevParam
         int paused = 0;
         if (__any_sync(ODEB_FULL, m_smem > 0))
             solve_islands_warp<HY>(P, smem, lane, rows, findex, rbody, cf_out, (D.jcopy || stop_after) ? D.lambda + (size_t)w * P.MR : 0, bstart, nb, rstart, m_smem, seed, st1, st2, st3, sweeps, rowsweeps,
-                                   m_smem <= sr_b, &paused);
+                                   world_pausable && m_smem <= sr_b, &paused);
         if (stop_after && side == 0 && is < nis && valid) D.isl_done[(size_t)w * P.NB + is] = paused ? 0 : 1;
         if (is < nis) st0++;
     }

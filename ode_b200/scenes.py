@@ -43,10 +43,12 @@ def box_stack(nworlds=1, nboxes=16, seed0=1000, jitter=1e-3, demo_world_options=
     return sc
 
 
-def pile(nworlds=1, nbodies=1000, seed=12345, spacing=1.1, space_type=B.SPACE_HASH, max_contacts=4):
+def pile(nworlds=1, nbodies=1000, seed=12345, spacing=1.1, space_type=B.SPACE_HASH, max_contacts=4, vary=0.0):
     """Config 1: alternating unit boxes / r=0.5 spheres on a cubic lattice dropped on the plane z=0.
 
     dContactApprox1, mu=0.5, <= 4 contacts per pair, g=(0,0,-9.81), defaults otherwise.
+    vary > 0: every world gets its own horizontal jitter of that size on top of the lattice (worlds then differ in island
+    structure and contact counts, not only in their dRand seed).
     """
     sc = B.Scene(B.default_world_params(gravity=(0, 0, -9.81), max_contacts=max_contacts,
                                         surf_mode=B.CONTACT_APPROX1, mu=0.5, space_type=space_type), nworlds)
@@ -70,6 +72,12 @@ def pile(nworlds=1, nbodies=1000, seed=12345, spacing=1.1, space_type=B.SPACE_HA
                     b = sc.add_body(ms, Is, pos)
                     sc.add_geom(B.SPHERE, (0.5,), body=b)
                 k += 1
+    if vary > 0:
+        pos = np.tile(np.asarray(sc.body_pos)[None], (nworlds, 1, 1))
+        for w in range(nworlds):
+            pos[w, :, :2] += vary * (_rng(seed + 7919 * (w + 1)).rand(sc.nbody, 2) - 0.5)
+        quat = np.tile(np.array([1.0, 0, 0, 0])[None, None], (nworlds, sc.nbody, 1))
+        sc.state = dict(pos=pos, quat=quat, lvel=np.zeros_like(pos), avel=np.zeros_like(pos))
     sc.seeds = (seed + np.arange(nworlds)).astype(np.uint32)
     return sc
 

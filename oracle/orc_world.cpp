@@ -74,6 +74,7 @@ struct World {
     std::vector<OrcContactGeom> ray_cg; std::vector<int> ray_g;   // ray hits of the last collide pass (sensor results: no joints)
     std::vector<int> island_label; int island_count;
     unsigned long long sweeps;
+    std::vector<int> isl_log;            // per island of the last step: bodies, rows, sweeps executed (test / profiling read-out)
     unsigned step_seed; int cur_island; unsigned long long draws;   // canonical mode bookkeeping
     // joint feedback of the last step (dJointSetFeedback, quickstep.cpp:3108-3182): per joint id 12 reals f1 t1 f2 t2 and a
     // state (0 = joint not stepped, 1 = body 1 only, 2 = both bodies)
@@ -715,6 +716,7 @@ void quickstep_island(const Batch &B, World &W, const int *bodies, int nb, const
     const Real hrecip = rrecip(h);
     std::vector<Real> J, iMJ, lambda, cforce(6 * nb, 0), fa(2 * nb, 0), rhs_tmp(6 * nb);
     std::vector<int> findex, jb, order, mindex(nj + 1), grp;
+    int isl_sweeps = 0;
     if (m > 0) {
         // Stage1 :1364-1472
         mindex[0] = 0;
@@ -866,7 +868,7 @@ void quickstep_island(const Batch &B, World &W, const int *bodies, int nb, const
                 }
             }
             ++iteration;
-            W.sweeps++;
+            W.sweeps++; isl_sweeps++;
             if (iteration - extra == num_iterations) {
                 if (extra != 0 || B.max_extra == 0) { if (extra != 0) W.stats[3]++; break; }
                 extra = B.max_extra;
@@ -913,6 +915,7 @@ void quickstep_island(const Batch &B, World &W, const int *bodies, int nb, const
         }
     }
     W.stats[0]++;     // Stage5 :3201-3203
+    W.isl_log.push_back(nb); W.isl_log.push_back((int)m); W.isl_log.push_back(isl_sweeps);
     // Stage6a :3299-3337
     for (int i = 0; i < nb; i++) {
         Body &b = W.bodies[bodies[i]];
@@ -946,6 +949,7 @@ void world_step(const Batch &B, World &W, Real h)
         for (int is = 0; is < W.island_count; is++) { for (int k = 0; k < isl.sizes[2 * is]; k++) W.island_label[isl.body[bo + k]] = is; bo += isl.sizes[2 * is]; }
     }
     size_t bo = 0, jo = 0;
+    W.isl_log.clear();
     if (B.canonical) {
         // canonical order of the large-world path: island membership and numbering as the reference finds them, but inside an
         // island bodies in descending creation index and joints in ascending id (permanent joints, then contacts in creation order)
@@ -1190,6 +1194,14 @@ int orc_get_islands(void *h, int world, int *label)
     Batch *B = (Batch *)h; World &W = B->worlds[world];
     for (int i = 0; i < B->nbody; i++) label[i] = i < (int)W.island_label.size() ? W.island_label[i] : -1;
     return W.island_count;
+}
+// per island of the world's last step, in solve order: bodies, rows, sweeps executed; returns the number of islands
+int orc_get_island_log(void *h, int world, int *out3, int cap)
+{
+    World &W = ((Batch *)h)->worlds[world];
+    const int n = (int)W.isl_log.size() / 3;
+    for (int i = 0; i < n && i < cap; i++) for (int k = 0; k < 3; k++) out3[3 * i + k] = W.isl_log[3 * i + k];
+    return n;
 }
 int orc_get_stats(void *h, int world, OdebStats *out)
 {

@@ -244,8 +244,58 @@ def test_solver_kernels_agree_at_bench_size(monkeypatch):
             assert np.array_equal(ref[1], seeds), solver
 
 
+WALKERS = ("d1", "d2", "d4", "d8")
+
+
 @pytest.mark.parametrize("prec", PRECS)
-@pytest.mark.parametrize("solver", ("v4", "p4", "bl", "hy"))
+@pytest.mark.parametrize("solver", WALKERS + ("auto",))
+def test_walker_solver_bit_exact(prec, solver, monkeypatch):
+    """k_solve6<P> (odeb_solve6.cuh: every world of a warp walks its own islands; shadow Fisher-Yates, window scheduler, world
+    sorting): 64-body piles whose worlds differ in island structure (the north-star shape, >= 8 worlds, several islands of 3..400
+    rows each), ragged small piles, many one-body islands, single-island stacks and chains, and a 70-box stack whose island
+    exceeds nothing but exercises the 12-bit rows.  Every observable incl. the dRand seed and the four iteration counters
+    identical to the oracle at every step."""
+    if solver == "auto":
+        monkeypatch.delenv("ODEB_SOLVER", raising=False)
+    else:
+        monkeypatch.setenv("ODEB_SOLVER", solver)
+    for mk, h, n in ((lambda: scenes.pile(nworlds=9, nbodies=64, vary=0.05), 0.01, 200),
+                     (lambda: scenes.pile(nworlds=21, nbodies=27, vary=0.1), 0.01, 120),
+                     (lambda: scenes.free_boxes(3, 100, grid=10), 0.01, 20),
+                     (lambda: scenes.box_stack(nworlds=7), 0.02, 60),
+                     (lambda: scenes.chain(3), 0.05, 60),
+                     (lambda: scenes.box_stack(nworlds=3, nboxes=70, demo_world_options=False), 0.02, 25)):
+        sc = mk()
+        a, b = B.Batch(orc_lib(prec), sc), B.Batch(gpu_lib(prec), sc)
+        for s in range(n):
+            a.step(h)
+            b.step(h)
+            bad = compare_step(a, b, sc.nworlds)
+            assert not bad, (solver, sc.nbody, s, bad[:4])
+        b.close()
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_hybrid_mixed_islands_keep_the_seed_order(prec, monkeypatch):
+    """Hybrid solve (k_solve 8 sweeps + k_solve5): a world whose islands are partly above the hand-over threshold must not pause
+    any island, or a later island would draw its reorders before an earlier, paused one.  ODEB_TEST_HY_ROWS
+    lowers the threshold so that the small piles mix islands on both sides of it."""
+    monkeypatch.setenv("ODEB_SOLVER", "hy")
+    monkeypatch.setenv("ODEB_TEST_HY_ROWS", "20")
+    for mk, h, n in ((lambda: scenes.pile(nworlds=21, nbodies=27, vary=0.1), 0.01, 120),
+                     (lambda: scenes.pile(nworlds=5, nbodies=64, vary=0.05), 0.01, 160)):
+        sc = mk()
+        a, b = B.Batch(orc_lib(prec), sc), B.Batch(gpu_lib(prec), sc)
+        for s in range(n):
+            a.step(h)
+            b.step(h)
+            bad = compare_step(a, b, sc.nworlds)
+            assert not bad, (sc.nbody, s, bad[:4])
+        b.close()
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("solver", ("v4", "p4", "bl", "hy", "d4", "d1"))
 def test_joint_feedback_bit_exact(prec, solver, monkeypatch):
     """Joint feedback (dJointSetFeedback, quickstep.cpp:3108-3182) through the batch C-ABI: f1/t1/f2/t2 and the written /
     not-written state of every joint, CUDA path against the oracle, with every solver kernel (each writes lambda out)."""
