@@ -123,20 +123,123 @@ def cpu_reference(steps, warm, worlds_per_proc=16, procs=None):
 
 # ---------------------------------------------------------------------------------------------- other BASELINE configs
 
-def other_configs(slib, device):
-    """Device-timed throughput of BASELINE configs[2..4] on this GPU (bounded: a few seconds each). Not the headline
-    line: reported beside it so the other scene families carry a measured number too."""
+CONFIG_SCENES = {
+    # name: (scene factory(nworlds, seed), dt, settle steps before timing)
+    "chain": (lambda nw, seed: scenes.chain(nw, seed0=seed), 0.05, 40),
+    "ragdoll": (lambda nw, seed: scenes.ragdoll(nw, seed0=seed), 0.01, 60),
+    "pile64": (lambda nw, seed: scenes.pile(nworlds=nw, nbodies=64, seed=seed), 0.01, 155),
+    "pile1000": (lambda nw, seed: scenes.pile(nbodies=1000, seed=seed), 0.01, 60),
+    "wall_100k": (lambda nw, seed: scenes.wall(500, 200), 0.05, 0),
+}
+
+
+def _ref_path():
+    ref = os.path.join(ROOT, "oracle", "_ref", "libode_ref_%s.so" % PREC)
+    if os.path.exists(ref):
+        return ref, "ref_", "reference"
+    return os.path.join(ROOT, "oracle", "liborc_%s.so" % PREC), "orc_", "port"
+
+
+def _cpu_scene_worker(args):
+    """one process: nworlds worlds of a named scene on the CPU checker library, optional threaded stepper (reference only)"""
+    path, prefix, name, nworlds, seed, steps, threads = args
+    real = np.float32 if PREC == "single" else np.float64
+    lib = B.SceneLib(path, prefix, real)
+    mk, h, settle = CONFIG_SCENES[name]
+    sc = mk(nworlds, seed)
+    b = B.Batch(lib, sc)
+    if prefix == "ref_":
+        fn = lib.lib.ref_step_plain
+        fn.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int]
+        if threads:
+            st = lib.lib.ref_set_threads
+            st.argtypes = [C.c_void_p, C.c_int]
+            st(b.h, threads)
+        step = lambda n: fn(b.h, h, n, 0, sc.nworlds)   # noqa: E731
+    else:
+        step = lambda n: b.step(h, n)                   # noqa: E731
+    if settle:
+        step(settle)
+    t = time.time()
+    step(steps)
+    dt = time.time() - t
+    if prefix == "ref_" and threads:
+        lib.lib.ref_set_threads(b.h, 0)
+    return dt, sc.nworlds * sc.nbody
+
+
+def cpu_config_baseline(name, nworlds, steps, procs=None, threads=0):
+    """The reference's CPU path on one of the other configs: `procs` independent processes (batched configs: one per host core,
+    each with its own worlds and its own dRand seed) or one process (single large worlds), bounded sample."""
+    import multiprocessing as mp
+    path, prefix, kind = _ref_path()
+    procs = procs or 1
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(procs) as pool:
+        res = pool.map(_cpu_scene_worker, [(path, prefix, name, nworlds, 1000 + 97 * i, steps, threads) for i in range(procs)])
+    slowest = max(r[0] for r in res)
+    bodies = sum(r[1] for r in res)
+    return {"value": bodies * steps / slowest, "unit": "body-steps/s", "ms_per_step": slowest / steps * 1e3, "cores": procs if not threads else threads,
+            "kind": kind, "threads_per_world": threads or 1,
+            "sample": "%d process(es) x %d world(s) x %d steps of '%s' after %d settle steps%s" % (
+                procs, nworlds, steps, name, CONFIG_SCENES[name][2], (", threaded stepper with a pool of %d (demo_crash.cpp:275-279)" % threads) if threads else "")}
+
+
+def solver_roofline(L, batch, h, nbodies, step_ms, extra_steps=3):
+    """Algorithmic bytes of the solver (per row per sweep 30 s + 16, per row once 46 s + 16, per body 26 s) over the
+    CUDA-event duration of the solver launches of a step, against the measured HBM peak."""
+    s = 4 if PREC == "single" else 8
+    L.odeb_enable_timing(batch.h, 1)
+    batch.step(h, extra_steps)
+    n = C.c_int(0)
+    sol_ms = L.odeb_solver_ms(batch.h, C.byref(n))
+    L.odeb_enable_timing(batch.h, 0)
+    tot = (C.c_uint64 * 6)()
+    L.odeb_get_totals(batch.h, tot)
+    pairs, contacts, rows, islands, sweeps, rowsweeps = [int(x) for x in tot]
+    alg_bytes = rowsweeps * (30 * s + 16) + rows * (46 * s + 16) + nbodies * 26 * s
+    sol_avg_ms = sol_ms / max(1, n.value)
+    if sol_avg_ms <= 0:
+        return None, (pairs, contacts, rows, islands, sweeps, rowsweeps)
+    achieved = alg_bytes / (sol_avg_ms * 1e-3) / 1e9
+    peak, which = peaks()
+    L.odeb_solver_kernel.restype = C.c_char_p
+    L.odeb_solver_kernel.argtypes = [C.c_void_p]
+    r = {"bound": "hbm", "kernel": (L.odeb_solver_kernel(batch.h) or b"k_solve").decode(), "achieved": round(achieved, 1), "peak": peak,
+         "peak_source": which, "unit": "GB/s", "frac": round(achieved / peak, 4), "algorithmic_bytes_per_launch": int(alg_bytes),
+         "launch_ms": round(sol_avg_ms, 4), "share_of_step": round(sol_avg_ms / step_ms, 3) if step_ms else None,
+         "row_sweeps_per_step": rowsweeps, "rows_per_step": rows}
+    return r, (pairs, contacts, rows, islands, sweeps, rowsweeps)
+
+
+def other_configs(slib, device, with_cpu=True, t_budget_end=None):
+    """Device-timed throughput of the other BASELINE configs on this GPU (bounded: a few seconds each), each with the roofline of
+    its solver launches and the reference's CPU number for the same scene beside it.  Not the headline line."""
     L = slib.lib
     out = {}
+    ncores = os.cpu_count() or 1
 
-    def timed(batch, h, steps, nbodies_total):
+    def timed(batch, h, steps, nbodies_total, roof=True):
         ms = C.c_double(0)
         if not L.odeb_timed_steps(batch.h, h, steps, FLUSH_BYTES, C.byref(ms)):
             raise RuntimeError("timed steps failed")
         tot = (C.c_uint64 * 6)()
         L.odeb_get_totals(batch.h, tot)
-        return {"ms_per_step": ms.value / steps, "body_steps_per_sec": nbodies_total * steps / (ms.value * 1e-3),
-                "rows_last_step": int(tot[2]), "steps": steps}
+        r = {"ms_per_step": ms.value / steps, "body_steps_per_sec": nbodies_total * steps / (ms.value * 1e-3),
+             "rows_last_step": int(tot[2]), "islands_last_step": int(tot[3]), "steps": steps}
+        if roof:
+            rf, _ = solver_roofline(L, batch, h, nbodies_total, ms.value / steps)
+            if rf:
+                r["roofline"] = rf
+        return r
+
+    def cpu(name, nworlds, steps, procs, **kw):
+        if not with_cpu:
+            return None
+        try:
+            return cpu_config_baseline(name, nworlds, steps, procs, **kw)
+        except Exception as e:  # noqa: BLE001
+            return {"error": str(e)[:200]}
 
     try:   # configs[2]: 65536 worlds of a 10-link ball-joint chain plus contacts (demo_chain2-style)
         nw = 65536
@@ -144,6 +247,7 @@ def other_configs(slib, device):
         b.step(0.05, 40)
         r = timed(b, 0.05, 20, nw * 10)
         r["workload"] = "%d worlds x 10-link chain, dt=0.05 (BASELINE configs[2], all on this GPU)" % nw
+        r["cpu_baseline"] = cpu("chain", 64, 100, ncores)
         out["chain"] = r
         b.close()
     except Exception as e:  # noqa: BLE001
@@ -154,30 +258,65 @@ def other_configs(slib, device):
         b.step(0.01, 60)
         r = timed(b, 0.01, 20, nw * 15)
         r["workload"] = "%d worlds x 15-capsule ragdoll (ball/hinge/universal joints with stops, friction contacts), dt=0.01 (BASELINE configs[3]: 16384 worlds / 8 GPUs)" % nw
+        r["cpu_baseline"] = cpu("ragdoll", 16, 100, ncores)
         out["ragdoll"] = r
         b.close()
     except Exception as e:  # noqa: BLE001
         out["ragdoll"] = {"error": str(e)[:200]}
-    try:   # north_star shape: batched 64-body worlds (piles of boxes and spheres, several islands per world)
-        nw = 4096
-        b = B.Batch(slib, scenes.pile(nworlds=nw, nbodies=64), device=device)
-        b.step(0.01, 150)
-        b.step(0.01, 5)
-        r = timed(b, 0.01, 10, nw * 64)
-        r["workload"] = "%d worlds x 64-body pile (boxes + spheres dropped on a plane, Approx1 friction), dt=0.01 (north_star: batched 64-body worlds)" % nw
-        out["pile64"] = r
+    for key, nw in (("pile64", 4096), ("pile64_16k", 16384)):
+        try:   # north_star shape: batched 64-body worlds (piles of boxes and spheres, several islands per world)
+            b = B.Batch(slib, scenes.pile(nworlds=nw, nbodies=64), device=device)
+            b.step(0.01, 150)
+            b.step(0.01, 5)
+            r = timed(b, 0.01, 10, nw * 64)
+            r["workload"] = "%d worlds x 64-body pile (boxes + spheres dropped on a plane, Approx1 friction), dt=0.01, steps 156-165 (north_star: batched 64-body worlds)" % nw
+            if key == "pile64":
+                r["cpu_baseline"] = cpu("pile64", 4, 20, ncores)
+            out[key] = r
+            b.close()
+        except Exception as e:  # noqa: BLE001
+            out[key] = {"error": str(e)[:200]}
+    try:   # configs[0]: the single 1000-body pile (the reference's own CPU-runnable case), large-world path on the GPU
+        sc = scenes.pile(nbodies=1000)
+        b = B.Batch(slib, sc, device=device)
+        b.set_solver_mode(1)
+        b.step(0.01, 60)
+        r = timed(b, 0.01, 20, sc.nbody, roof=False)
+        r["workload"] = "1 world x 1000 boxes + spheres on a plane, dHashSpace semantics, dt=0.01, steps 61-80 (BASELINE configs[0]); GPU: ODEB_MODE_CANONICAL"
+        r["cpu_baseline"] = cpu("pile1000", 1, 40, 1)
+        if with_cpu:   # the reference's threaded stepper, pool of k threads (timing only: it changes the sweep order)
+            sweep = {}
+            for k in sorted({2, 4, 8, ncores}):
+                if k <= ncores:
+                    c = cpu("pile1000", 1, 10, 1, threads=k)
+                    sweep[str(k)] = c.get("ms_per_step") if isinstance(c, dict) else None
+            r["cpu_threaded_stepper_ms_per_step"] = sweep
+        out["pile1000"] = r
         b.close()
     except Exception as e:  # noqa: BLE001
-        out["pile64"] = {"error": str(e)[:200]}
+        out["pile1000"] = {"error": str(e)[:200]}
     try:   # configs[4]: one 100k-box wall, sweep-and-prune space, large-island path (ODEB_MODE_CANONICAL)
         sc = scenes.wall(500, 200)
         b = B.Batch(slib, sc, device=device)
         b.set_solver_mode(1)
         b.step(0.05, 6)
-        r = timed(b, 0.05, 6, sc.nbody)
+        r = timed(b, 0.05, 6, sc.nbody, roof=False)
+        tot = (C.c_uint64 * 6)()
+        L.odeb_get_totals(b.h, tot)
+        s = 4 if PREC == "single" else 8
+        alg = int(tot[5]) * (30 * s + 16) + int(tot[2]) * (46 * s + 16) + sc.nbody * 26 * s
+        peak, which = peaks()
+        r["roofline"] = {"bound": "hbm", "kernel": "k_lw_sweep (whole step timed: the sweep is ~84 % of it)", "achieved": round(alg / (r["ms_per_step"] * 1e-3) / 1e9, 1), "peak": peak,
+                         "peak_source": which, "unit": "GB/s", "frac": round(alg / (r["ms_per_step"] * 1e-3) / 1e9 / peak, 4), "algorithmic_bytes_per_launch": alg,
+                         "limiter": "L2 round trips of the ticketed sweep (profiles/r1_lw_sweep_ncu_summary.txt), not DRAM"}
         r["workload"] = "1 world x %d bodies (500 x 200 brick wall + cannon ball), dSweepAndPruneSpace semantics, dt=0.05 (BASELINE configs[4])" % sc.nbody
-        out["wall_100k"] = r
         b.close()
+        # the reference needs ~45 s for ONE step of this world on one core: only when the time budget of the run allows it
+        if with_cpu and (t_budget_end is None or time.time() + 70 < t_budget_end):
+            r["cpu_baseline"] = cpu("wall_100k", 1, 1, 1)
+        else:
+            r["cpu_baseline"] = {"skipped": "time budget; measured once in this round: profiles/r2_cpu_baselines.txt"}
+        out["wall_100k"] = r
     except Exception as e:  # noqa: BLE001
         out["wall_100k"] = {"error": str(e)[:200]}
     return out

@@ -96,6 +96,10 @@ typedef struct OdebWorldParams {
     double rho, rho2, rhoN;     /* rolling / spinning friction, used with ODEB_CONTACT_ROLLING (contact.h:64-66) */
     int    hash_levels_set;     /* 0: the hash space's default levels -3..10 (collision_space.cpp:387-388); 1: dHashSpaceSetLevels values below */
     int    hash_minlevel, hash_maxlevel;
+    /* --- device capacities per world; 0 = automatic (pairs: min(all pairs, 16 per geom); contacts: pairs * max_contacts, capped at
+     *     2..4 per geom and max_contacts).  A step that needs more fails with "capacity overflow" (odeb_step / odeb_sync /
+     *     odeb_get_state return 0) and leaves the body state as the last complete step wrote it. */
+    int    max_pairs, max_contacts_per_world;
 } OdebWorldParams;
 
 typedef struct OdebBodyDesc {
@@ -162,6 +166,15 @@ const char *odeb_last_error(void);
  * Setting a quaternion normalises it and rebuilds R like dBodySetQuaternion (ode.cpp:330-343). */
 int odeb_set_state(OdebBatch *, const odeb_real *pos, const odeb_real *quat, const odeb_real *lvel, const odeb_real *avel);
 int odeb_get_state(OdebBatch *, odeb_real *pos, odeb_real *quat, odeb_real *lvel, odeb_real *avel);
+/* odeb_get_state is a blocking call: like odeb_sync it returns 0 ("capacity overflow ...") when a step queued by odeb_step_async
+ * truncated pairs / contacts / rows; no body is moved by such a step or by the steps queued behind it. */
+/* The packed body state on the DEVICE (pos [W*NB*3], quat [W*NB*4], lvel [W*NB*3], avel [W*NB*3], odeb_real) in a buffer owned by
+ * the batch, written on the batch's stream; valid until the next call.  For GPU-side consumers (NCCL gather of observations). */
+int odeb_pack_state_device(OdebBatch *, void **dev_ptr, size_t *bytes);
+/* device addresses of the per-world counters: stats [W*4] uint32 (dynamic-iteration counters), seeds [W] uint32 */
+int odeb_device_counters(OdebBatch *, void **stats, void **seeds);
+/* run the batch on the caller's CUDA stream (cudaStream_t) so that the caller's events order against the steps */
+int odeb_set_stream(OdebBatch *, void *stream);
 /* Page-locked host memory for the arrays handed to odeb_set/get_state and odeb_add_force: with it the transfers run straight between the
  * device and the caller's arrays (pageable arrays work too, through an internal pinned staging buffer and one extra host copy). */
 void *odeb_alloc_host(size_t bytes);
@@ -223,7 +236,10 @@ static inline ODEB_HD uint32_t odebi_canon_key(uint32_t seed, uint32_t island, u
 }
 
 /* nsteps x { dSpaceCollide + contact policy ; dWorldQuickStep(h) ; dJointGroupEmpty }.
- * Returns 1 on success, 0 on failure (like dWorldQuickStep), state untouched on allocation failure. */
+ * Returns 1 on success, 0 on failure (like dWorldQuickStep).  On a capacity overflow (more pairs / contacts / rows than the
+ * batch was created for) the failing step and every step queued behind it leave positions, orientations and velocities as
+ * the last complete step wrote them (dRand seeds, iteration counters and auto-disable history of those steps are undefined):
+ * raise OdebWorldParams.max_pairs / max_contacts_per_world, recreate, restore. */
 int odeb_step(OdebBatch *, double h, int nsteps);
 /* same, asynchronous on the batch's stream; pair with odeb_sync */
 int odeb_step_async(OdebBatch *, double h, int nsteps);

@@ -187,6 +187,10 @@ void dWorldSetContactMaxCorrectingVel(dWorldID, dReal vel);
 dReal dWorldGetContactMaxCorrectingVel(dWorldID);
 void dWorldSetContactSurfaceLayer(dWorldID, dReal depth);
 dReal dWorldGetContactSurfaceLayer(dWorldID);
+/* LIMITATION: auto-disable thresholds / steps / time, damping scales / thresholds and the maximum angular speed are WORLD-wide
+ * here and apply to every body at step time.  The reference copies the world's current defaults into each body at dBodyCreate
+ * (b->adis, b->dampingp), so there a later dWorldSet* call only affects bodies created afterwards; programs that change these
+ * defaults between body creations must set the per-body values explicitly (dBodySetAutoDisable*, dBodySet*Damping). */
 void dWorldSetAutoDisableFlag(dWorldID, int do_auto_disable);
 int dWorldGetAutoDisableFlag(dWorldID);
 void dWorldSetAutoDisableLinearThreshold(dWorldID, dReal linear_threshold);
@@ -320,6 +324,14 @@ void dSpaceAdd(dSpaceID, dGeomID);
 void dSpaceRemove(dSpaceID, dGeomID);
 int dSpaceGetNumGeoms(dSpaceID);
 dGeomID dSpaceGetGeom(dSpaceID, int i);
+/* CALLBACK ORDER: the reference hands pairs to the callback in the traversal order of its space (dGeomMoved re-inserts a moved
+ * geom at the head of the space's list, collision_space.cpp:205-209; dxHashSpace walks hash chains, :504-584; dxSAPSpace walks its
+ * sorted axis).  This library reports exactly the same SET of pairs (incl. the hash space's wrapped-address misses) but always in
+ * ascending (index of o1, index of o2) order, o1 created before o2.  Constraint order follows contact-creation order, so an
+ * application that creates its contacts directly in callback order sees a different (equally valid) SOR row order than on the
+ * reference; an application that buffers the pairs and creates contacts in a canonical order (tests/classic_app.py,
+ * oracle/ref_driver.cpp: sorted by geom index) gets identical contacts, islands and trajectories on both libraries.
+ * profiles/r2_callback_order.txt holds the reference-vs-reference yardstick (natural against sorted callback order). */
 void dSpaceCollide(dSpaceID space, void *data, dNearCallback *callback);
 int dCollide(dGeomID o1, dGeomID o2, int flags, dContactGeom *contact, int skip);
 dGeomID dCreateSphere(dSpaceID space, dReal radius);

@@ -29,6 +29,7 @@ class OdebWorldParams(C.Structure):
         ("slip1", C.c_double), ("slip2", C.c_double),
         ("rho", C.c_double), ("rho2", C.c_double), ("rhoN", C.c_double),
         ("hash_levels_set", C.c_int), ("hash_minlevel", C.c_int), ("hash_maxlevel", C.c_int),
+        ("max_pairs", C.c_int), ("max_contacts_per_world", C.c_int),
     ]
 
 
@@ -312,7 +313,15 @@ class Batch:
         if out is None:
             out = dict(pos=np.empty((self.W, self.NB, 3), r), quat=np.empty((self.W, self.NB, 4), r),
                        lvel=np.empty((self.W, self.NB, 3), r), avel=np.empty((self.W, self.NB, 3), r))
-        self.slib._fn("get_state")(self.h, _ptr(out["pos"]), _ptr(out["quat"]), _ptr(out["lvel"]), _ptr(out["avel"]))
+        f = self.slib._fn("get_state")
+        f.restype = C.c_int
+        if not f(self.h, _ptr(out["pos"]), _ptr(out["quat"]), _ptr(out["lvel"]), _ptr(out["avel"])):
+            msg = ""
+            if self.slib.has("last_error"):
+                fn = self.slib._fn("last_error")
+                fn.restype = C.c_char_p
+                msg = (fn() or b"").decode()
+            raise RuntimeError("%sget_state failed: %s" % (self.slib.prefix, msg))
         return out
 
     def add_force(self, force=None, torque=None):
@@ -397,6 +406,17 @@ class Batch:
         f.restype, f.argtypes = C.c_int, [C.c_void_p, C.c_double, C.c_int]
         if not f(self.h, float(h), int(nsteps)):
             raise RuntimeError("%sstep_async failed" % self.slib.prefix)
+
+    def sync(self):
+        """odeb_sync: waits for the queued steps; raises if one of them overflowed a device capacity"""
+        if not self.slib.has("sync"):
+            return
+        f = self.slib._fn("sync")
+        f.restype, f.argtypes = C.c_int, [C.c_void_p]
+        if not f(self.h):
+            fn = self.slib._fn("last_error")
+            fn.restype = C.c_char_p
+            raise RuntimeError("%ssync failed: %s" % (self.slib.prefix, (fn() or b"").decode()))
 
     def get_totals(self):
         """[pairs, contacts, rows, islands, sweeps, row-sweeps] of the most recent step, summed over worlds"""

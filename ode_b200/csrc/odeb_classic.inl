@@ -445,8 +445,9 @@ static void destroy_joint(dxJoint *j)
 {
     dxWorld *w = j->world;
     detach_joint(j);
-    std::vector<dxJoint *>::iterator it = std::find(w->joints.begin(), w->joints.end(), j);
-    if (it != w->joints.end()) w->joints.erase(it);
+    // searched from the back: a joint group is emptied newest first and a step's contact joints are the newest joints of the world, so
+    // dJointGroupEmpty is linear, not quadratic, in the number of contacts
+    for (size_t i = w->joints.size(); i > 0;) if (w->joints[--i] == j) { w->joints.erase(w->joints.begin() + (std::ptrdiff_t)i); break; }
     if (j->type != dJointTypeContact) w->topo_dirty = true;
     delete j;
 }

@@ -24,6 +24,9 @@ struct OdebBatch {
     // staging
     Real4 *d_stage; size_t stage_elems;
     Real4 *h_stage;
+    int *h_ov;                                // [4] page-locked copy of D.overflow (read back by every blocking getter)
+    Real4 *fb_jcopy, *fb_jfb;                 // joint-feedback buffers, kept across odeb_enable_feedback(0/1) toggles
+    bool own_stream;                          // the stream was created here (odeb_set_stream replaces it with the caller's)
     // cuda graph of one step
     cudaGraphExec_t graph; double graph_h; bool use_graph; int graph_cfg;
     // solver selection: 0 = k_solve (one row at a time per world), 1..3 = k_solve5<2/4/8> (static P-processor schedule),
@@ -40,6 +43,25 @@ struct OdebBatch {
     int mode; LargePtrs L; bool large_ready;
 };
 static int large_step(OdebBatch *B);
+
+// B->h_ov holds a fresh copy of D.overflow (the stream is idle): refresh the solver hints, report and clear a capacity overflow.
+// Device counters are reset on the batch's stream (a legacy-stream memset would not order against it).
+static int overflow_check(OdebBatch *B)
+{
+    const int *ovh = B->h_ov;
+    if (ovh[1] > 0) { B->hint_m = ovh[1]; B->hint_nb = ovh[2]; B->hint_nis = ovh[3]; CK(cudaMemsetAsync(B->D.overflow + 1, 0, 3 * sizeof(int), B->stream)); }
+    const int ov = ovh[0];
+    if (ov) {
+        set_err("capacity overflow (%s): raise OdebWorldParams.max_pairs / max_contacts_per_world (or ODEB_MAX_PAIRS / ODEB_MAX_CONTACTS); the body state is the one the last complete step left",
+                ov == 1 ? "pairs" : ov == 2 ? "contacts" : "rows");
+        CK(cudaMemsetAsync(B->D.overflow, 0, sizeof(int), B->stream));
+        CK(cudaStreamSynchronize(B->stream));
+        return 0;
+    }
+    return 1;
+}
+
+
 
 template <class T> static bool dev_alloc(OdebBatch *B, T **p, size_t n)
 {
@@ -296,8 +318,9 @@ void odeb_destroy(OdebBatch *B)
     if (B->graph) cudaGraphExecDestroy(B->graph);
     for (size_t i = 0; i < B->allocs.size(); i++) cudaFree(B->allocs[i]);
     if (B->h_stage) cudaFreeHost(B->h_stage);
+    if (B->h_ov) cudaFreeHost(B->h_ov);
     if (B->flush_buf) cudaFree(B->flush_buf);
-    if (B->stream) cudaStreamDestroy(B->stream);
+    if (B->stream && B->own_stream) cudaStreamDestroy(B->stream);
     delete B;
 }
 
@@ -333,7 +356,7 @@ static OdebBatch *batch_build(const OdebWorldParams *wp, const HostTemplate &T, 
     OdebBatch *B = new OdebBatch();
     B->device = device; B->bytes = 0; B->launches = 0; B->timing = false; B->solver_ms = 0; B->solver_launches = 0;
     B->mode = ODEB_MODE_REPLAY; B->large_ready = false; memset(&B->L, 0, sizeof(B->L));
-    B->graph = 0; B->graph_h = -1; B->graph_cfg = -1; B->graph_sr = -1; B->hint_m = 0; B->hint_nb = 0; B->hint_nis = 0; B->s6_sr = 0; B->s6_nbi = 0; B->s6_smem = 0; B->solver_force = -1; B->use_graph = getenv("ODEB_NO_GRAPH") == 0 && !classic; B->h_stage = 0; B->d_stage = 0; B->stream = 0; B->flush_buf = 0; B->flush_bytes = 0;
+    B->graph = 0; B->graph_h = -1; B->graph_cfg = -1; B->graph_sr = -1; B->hint_m = 0; B->hint_nb = 0; B->hint_nis = 0; B->s6_sr = 0; B->s6_nbi = 0; B->s6_smem = 0; B->solver_force = -1; B->use_graph = getenv("ODEB_NO_GRAPH") == 0 && !classic; B->h_stage = 0; B->h_ov = 0; B->fb_jcopy = 0; B->fb_jfb = 0; B->own_stream = true; B->d_stage = 0; B->stream = 0; B->flush_buf = 0; B->flush_bytes = 0;
     memset(&B->D, 0, sizeof(B->D));
     DevParams &P = B->P;
     memset(&P, 0, sizeof(P));
@@ -344,12 +367,14 @@ static OdebBatch *batch_build(const OdebWorldParams *wp, const HostTemplate &T, 
         long long all = (long long)ngeom * (ngeom - 1) / 2;
         long long mp = all < 16LL * ngeom ? all : 16LL * ngeom;
         if (const char *s = getenv("ODEB_MAX_PAIRS")) mp = atoll(s);
+        if (wp->max_pairs > 0) mp = wp->max_pairs;
         if (caps && caps->max_pairs > 0) mp = caps->max_pairs;
         P.MP = (int)(mp < 1 ? 1 : mp);
         long long mc = (long long)P.MP * P.maxc;
         long long cap = (nworlds == 1 ? 4LL : 2LL) * ngeom * P.maxc;   // a single (large) world may be a dense wall / pile
         if (mc > cap) mc = cap;
         if (const char *s = getenv("ODEB_MAX_CONTACTS")) mc = atoll(s);
+        if (wp->max_contacts_per_world > 0) mc = wp->max_contacts_per_world;
         if (caps && caps->max_contacts > 0) mc = caps->max_contacts;
         P.MC = (int)(mc < 1 ? 1 : mc);
     }
@@ -433,6 +458,7 @@ static OdebBatch *batch_build(const OdebWorldParams *wp, const HostTemplate &T, 
     B->stage_elems = 4 * WB;                     // room for the tightly packed state of every body (13 reals) in one transfer
     ok = ok && dev_alloc(B, &B->d_stage, 4 * WB);
     if (ok && cudaMallocHost((void **)&B->h_stage, 4 * WB * sizeof(Real4)) != cudaSuccess) { set_err("cudaMallocHost failed"); ok = false; }
+    if (ok && cudaMallocHost((void **)&B->h_ov, 4 * sizeof(int)) != cudaSuccess) { set_err("cudaMallocHost failed"); ok = false; }
     if (ok && cudaStreamCreateWithFlags(&B->stream, cudaStreamNonBlocking) != cudaSuccess) { set_err("cudaStreamCreate failed"); ok = false; }
     {   // island replay scratch in shared memory when 32 worlds fit (and the 16-bit indices hold)
         const size_t need = odeb_islands_smem(P.NB, P.MC, P.NJT);
@@ -693,8 +719,43 @@ int odeb_get_state(OdebBatch *B, odeb_real *pos, odeb_real *quat, odeb_real *lve
         staged[k] = !host_ptr_is_pinned(dst[k]);
         CK(cudaMemcpyAsync(staged[k] ? h + ofs[k] : dst[k], d + ofs[k], len[k] * sizeof(Real), cudaMemcpyDeviceToHost, B->stream));
     }
+    // this is the blocking call of the asynchronous loop (odeb_add_force, odeb_step_async, odeb_get_state): the capacity-overflow flag and
+    // the solver hints ride along, so a truncated step is reported here and not only by odeb_sync
+    CK(cudaMemcpyAsync(B->h_ov, B->D.overflow, 4 * sizeof(int), cudaMemcpyDeviceToHost, B->stream));
     CK(cudaStreamSynchronize(B->stream));
     for (int k = 0; k < 4; k++) if (dst[k] && staged[k]) memcpy(dst[k], h + ofs[k], len[k] * sizeof(Real));
+    return overflow_check(B);
+}
+
+/* The packed body state of the whole batch on the DEVICE: pos [W*NB*3], quat [W*NB*4], lvel [W*NB*3], avel [W*NB*3] (odeb_real, in
+ * that order) in a buffer owned by the batch, written by one kernel on the batch's stream; valid until the next call.  For consumers
+ * that live on the GPU (an NCCL gather of observations, a policy network): no host round trip.  *bytes = size of the buffer. */
+int odeb_pack_state_device(OdebBatch *B, void **dev_ptr, size_t *bytes)
+{
+    CK(cudaSetDevice(B->device));
+    const size_t n = (size_t)B->P.W * B->P.NB;
+    k_pack_state<<<nblk(n, 256), 256, 0, B->stream>>>(n, B->D.pos, B->D.quat, B->D.lvel, B->D.avel, (Real *)B->d_stage);
+    B->launches++;
+    if (dev_ptr) *dev_ptr = B->d_stage;
+    if (bytes) *bytes = 13 * n * sizeof(Real);
+    CK(cudaGetLastError());
+    return 1;
+}
+/* per-world counters of the last step on the device: stats [W*4] uint32 (the four dynamic-iteration counters), seeds [W] uint32 */
+int odeb_device_counters(OdebBatch *B, void **stats, void **seeds)
+{
+    if (stats) *stats = B->D.stats;
+    if (seeds) *seeds = B->D.seed;
+    return 1;
+}
+/* Run the batch on the caller's CUDA stream (a cudaStream_t, e.g. torch.cuda.Stream().cuda_stream) instead of its own, so that the
+ * caller's events / stream waits order its kernels against the steps.  The stream must outlive the batch or be replaced first. */
+int odeb_set_stream(OdebBatch *B, void *stream)
+{
+    CK(cudaSetDevice(B->device));
+    CK(cudaStreamSynchronize(B->stream));
+    if (B->own_stream && B->stream) cudaStreamDestroy(B->stream);
+    B->stream = (cudaStream_t)stream; B->own_stream = false;
     return 1;
 }
 
@@ -727,7 +788,10 @@ int odeb_add_force(OdebBatch *B, const odeb_real *force, const odeb_real *torque
 int odeb_set_seeds(OdebBatch *B, const uint32_t *seeds)
 {
     CK(cudaSetDevice(B->device));
-    CK(cudaMemcpy(B->D.seed, seeds, B->P.W * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    // on the batch's own stream, behind whatever odeb_step_async queued (a plain cudaMemcpy runs on the legacy stream, which does
+    // not order against this non-blocking stream: an in-flight solver could overwrite the new seeds or consume them mid-step)
+    CK(cudaMemcpyAsync(B->D.seed, seeds, B->P.W * sizeof(uint32_t), cudaMemcpyHostToDevice, B->stream));
+    CK(cudaStreamSynchronize(B->stream));
     return 1;
 }
 int odeb_get_seeds(OdebBatch *B, uint32_t *seeds)
@@ -985,16 +1049,9 @@ int odeb_sync(OdebBatch *B)
         cudaEventDestroy(B->pending[i].first); cudaEventDestroy(B->pending[i].second);
     }
     B->pending.clear();
-    int ovh[4] = { 0, 0, 0, 0 };
-    CK(cudaMemcpy(ovh, B->D.overflow, sizeof(ovh), cudaMemcpyDeviceToHost));
-    if (ovh[1] > 0) { B->hint_m = ovh[1]; B->hint_nb = ovh[2]; B->hint_nis = ovh[3]; CK(cudaMemset(B->D.overflow + 1, 0, 3 * sizeof(int))); }
-    const int ov = ovh[0];
-    if (ov) {
-        set_err("capacity overflow (%s): raise ODEB_MAX_PAIRS / ODEB_MAX_CONTACTS", ov == 1 ? "pairs" : ov == 2 ? "contacts" : "rows");
-        cudaMemset(B->D.overflow, 0, sizeof(int));
-        return 0;
-    }
-    return 1;
+    CK(cudaMemcpyAsync(B->h_ov, B->D.overflow, 4 * sizeof(int), cudaMemcpyDeviceToHost, B->stream));
+    CK(cudaStreamSynchronize(B->stream));
+    return overflow_check(B);
 }
 
 int odeb_step(OdebBatch *B, double h, int nsteps)
@@ -1037,8 +1094,11 @@ int odeb_enable_feedback(OdebBatch *B, int on)
     if (B->mode == ODEB_MODE_CANONICAL) { set_err("joint feedback is not available in ODEB_MODE_CANONICAL"); return 0; }
     if (on && !B->D.jcopy) {
         const size_t W = B->P.W;
-        if (!dev_alloc(B, &B->D.jcopy, W * B->P.MR * 3) || !dev_alloc(B, &B->D.jfb, W * B->P.NJT * 4)) return 0;
-    } else if (!on) { B->D.jcopy = 0; B->D.jfb = 0; }      // the buffers stay in the batch's allocation list until odeb_destroy
+        // allocated once per batch and kept: the classic dWorldQuickStep toggles feedback whenever "some joint has a dJointFeedback" changes
+        if (!B->fb_jcopy && (!dev_alloc(B, &B->fb_jcopy, W * B->P.MR * 3) || !dev_alloc(B, &B->fb_jfb, W * B->P.NJT * 4))) return 0;
+        CK(cudaDeviceSynchronize());                       // dev_alloc clears on the legacy stream
+        B->D.jcopy = B->fb_jcopy; B->D.jfb = B->fb_jfb;
+    } else if (!on) { B->D.jcopy = 0; B->D.jfb = 0; }
     if (B->graph) { cudaGraphExecDestroy(B->graph); B->graph = 0; }
     return 1;
 }

@@ -466,6 +466,9 @@ __global__ void k_body_pre(const __grid_constant__ DevParams P, const __grid_con
 {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (size_t)P.W * P.NB) return;
+    // a capacity overflow anywhere in this step (pairs, contacts or rows truncated): no body moves, in this step or in the ones queued
+    // behind it, until the host has seen the flag (odeb_sync / odeb_get_state) -- the state stays the one the last complete step left
+    if (D.overflow[0] != 0) return;
     int w = (int)(t / P.NB), k = (int)(t % P.NB);
     if (k >= D.nordered[w]) return;
     int b = D.body_order[t];
@@ -750,6 +753,9 @@ __global__ void k_integrate(const __grid_constant__ DevParams P, const __grid_co
 {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (size_t)P.W * P.NB) return;
+    // a capacity overflow anywhere in this step (pairs, contacts or rows truncated): no body moves, in this step or in the ones queued
+    // behind it, until the host has seen the flag (odeb_sync / odeb_get_state) -- the state stays the one the last complete step left
+    if (D.overflow[0] != 0) return;
     int w = (int)(t / P.NB), k = (int)(t % P.NB);
     if (k >= D.nordered[w]) return;
     int b = D.body_order[t];

@@ -435,6 +435,33 @@ static void near_cb_direct(void *data, dGeomID o1, dGeomID o2)
     }
 }
 
+/* The reference's threaded stepper, set up exactly like ode/demo/demo_crash.cpp:275-279 / :636-640: one
+ * multi-threaded implementation served by a pool of k threads, assigned to every world of the batch.  Timing baseline only: this
+ * mode changes the SOR sweep order (quickstep.cpp's multi-threaded LCP iteration), so it is never used as a parity reference.
+ * k <= 0 returns the worlds to the self-threaded default and frees the pool. */
+static dThreadingImplementationID g_threading = 0;
+static dThreadingThreadPoolID g_pool = 0;
+int ref_set_threads(void *h, int k)
+{
+    RefBatch *B = (RefBatch *)h;
+    if (g_threading) {
+        for (size_t w = 0; w < B->worlds.size(); w++) dWorldSetStepThreadingImplementation(B->worlds[w].world, NULL, NULL);
+        dThreadingImplementationShutdownProcessing(g_threading);
+        dThreadingFreeThreadPool(g_pool);
+        dThreadingFreeImplementation(g_threading);
+        g_threading = 0; g_pool = 0;
+    }
+    if (k <= 0) return 1;
+    g_threading = dThreadingAllocateMultiThreadedImplementation();
+    if (!g_threading) return 0;
+    g_pool = dThreadingAllocateThreadPool((unsigned)k, 0, dAllocateFlagBasicData, NULL);
+    if (!g_pool) return 0;
+    dThreadingThreadPoolServeMultiThreadedImplementation(g_pool, g_threading);
+    for (size_t w = 0; w < B->worlds.size(); w++)
+        dWorldSetStepThreadingImplementation(B->worlds[w].world, dThreadingImplementationGetFunctions(g_threading), g_threading);
+    return 1;
+}
+
 int ref_step_plain(void *h, double hstep, int nsteps, int world_begin, int world_end)
 {
     RefBatch *B = (RefBatch *)h;

@@ -159,11 +159,12 @@ def record_traj(batch, h, nsteps, every):
     return out
 
 
-def compare_traj(batch, gold, h, exact=True, tol=None, resync=False):
+def compare_traj(batch, gold, h, exact=True, tol=None, resync=False, meas=None):
     """Replays the recorded scene on `batch` and compares every checkpoint. Returns list of mismatches.
     resync=True re-uploads the recorded reference state (and dRand seeds) after each checkpoint, so that every
     segment between checkpoints starts from the reference's state (teacher forcing) and last-ulp libm
-    differences are not amplified over the whole run."""
+    differences are not amplified over the whole run.  meas: optional dict that receives the largest contact / state deviation
+    seen (tools/measure_tolerances.py: the stated tolerances are 4x these maxima)."""
     bad = []
     W = batch.W
     steps = list(gold["steps"])
@@ -190,6 +191,8 @@ def compare_traj(batch, gold, h, exact=True, tol=None, resync=False):
             bad.append("step %d: contact counts / geoms differ" % s)
         else:
             mc = np.concatenate([c[0] for c in ct])
+            if meas is not None and len(mc):
+                meas["contact"] = max(meas.get("contact", 0.0), float(np.abs(mc.astype(np.float64) - gc).max()))
             if exact and not np.array_equal(mc, gc):
                 bad.append("step %d: contact geometry differs by %.3g" % (s, np.abs(mc - gc).max()))
             elif not exact and len(mc) and np.abs(mc.astype(np.float64) - gc).max() > tol["contact"]:
@@ -202,6 +205,8 @@ def compare_traj(batch, gold, h, exact=True, tol=None, resync=False):
         if not np.array_equal(batch.get_seeds(), gold["seeds"][ci]):
             bad.append("step %d: dRand seeds differ" % s)
         for k in ("pos", "quat", "lvel", "avel"):
+            if meas is not None:
+                meas["state"] = max(meas.get("state", 0.0), float(np.abs(st[k].astype(np.float64) - gold[k][ci]).max()))
             if exact:
                 if not np.array_equal(st[k], gold[k][ci]):
                     bad.append("step %d: %s differs by %.3g" % (s, k, np.abs(st[k] - gold[k][ci]).max()))
