@@ -32,6 +32,8 @@ H = 0.02
 PREC = "single"
 METRIC = "body_steps_per_sec"
 FLUSH_BYTES = 256 << 20
+WORKLOAD = "%d worlds/GPU x %d-box stack on a plane (BASELINE configs[1]), dt=%g, 20 iters + default dynamic adjustment, auto-disable off" % (WORLDS_PER_GPU, NBOX, H)
+T_START = time.time()
 
 
 def make_scene(nworlds, seed0=1000):
@@ -233,13 +235,26 @@ def other_configs(slib, device, with_cpu=True, t_budget_end=None):
                 r["roofline"] = rf
         return r
 
+    deferred = []     # CPU legs run AFTER all GPU legs: the GPU drops to idle clocks while the host works, and a short GPU leg that
+                      # starts right after a CPU leg is timed during the clock ramp (ragdoll: 0.84 instead of 0.57 ms per step)
+
     def cpu(name, nworlds, steps, procs, **kw):
         if not with_cpu:
             return None
-        try:
-            return cpu_config_baseline(name, nworlds, steps, procs, **kw)
-        except Exception as e:  # noqa: BLE001
-            return {"error": str(e)[:200]}
+        slot = {"pending": True}
+        deferred.append((slot, name, nworlds, steps, procs, kw))
+        return slot
+
+    def run_deferred():
+        for slot, name, nworlds, steps, procs, kw in deferred:
+            slot.clear()
+            if name == "wall_100k" and t_budget_end is not None and time.time() + 70 > t_budget_end:
+                slot.update({"skipped": "time budget; measured once in this round: profiles/r2_cpu_baselines.txt"})
+                continue
+            try:
+                slot.update(cpu_config_baseline(name, nworlds, steps, procs, **kw))
+            except Exception as e:  # noqa: BLE001
+                slot.update({"error": str(e)[:200]})
 
     try:   # configs[2]: 65536 worlds of a 10-link ball-joint chain plus contacts (demo_chain2-style)
         nw = 65536
@@ -285,12 +300,7 @@ def other_configs(slib, device, with_cpu=True, t_budget_end=None):
         r["workload"] = "1 world x 1000 boxes + spheres on a plane, dHashSpace semantics, dt=0.01, steps 61-80 (BASELINE configs[0]); GPU: ODEB_MODE_CANONICAL"
         r["cpu_baseline"] = cpu("pile1000", 1, 40, 1)
         if with_cpu:   # the reference's threaded stepper, pool of k threads (timing only: it changes the sweep order)
-            sweep = {}
-            for k in sorted({2, 4, 8, ncores}):
-                if k <= ncores:
-                    c = cpu("pile1000", 1, 10, 1, threads=k)
-                    sweep[str(k)] = c.get("ms_per_step") if isinstance(c, dict) else None
-            r["cpu_threaded_stepper_ms_per_step"] = sweep
+            r["cpu_threaded_stepper"] = {str(k): cpu("pile1000", 1, 10, 1, threads=k) for k in sorted({2, 4, 8, ncores}) if k <= ncores}
         out["pile1000"] = r
         b.close()
     except Exception as e:  # noqa: BLE001
@@ -311,14 +321,12 @@ def other_configs(slib, device, with_cpu=True, t_budget_end=None):
                          "limiter": "L2 round trips of the ticketed sweep (profiles/r1_lw_sweep_ncu_summary.txt), not DRAM"}
         r["workload"] = "1 world x %d bodies (500 x 200 brick wall + cannon ball), dSweepAndPruneSpace semantics, dt=0.05 (BASELINE configs[4])" % sc.nbody
         b.close()
-        # the reference needs ~45 s for ONE step of this world on one core: only when the time budget of the run allows it
-        if with_cpu and (t_budget_end is None or time.time() + 70 < t_budget_end):
-            r["cpu_baseline"] = cpu("wall_100k", 1, 1, 1)
-        else:
-            r["cpu_baseline"] = {"skipped": "time budget; measured once in this round: profiles/r2_cpu_baselines.txt"}
+        # the reference needs 20-45 s for ONE step of this world on one core: only when the time budget of the run allows it
+        r["cpu_baseline"] = cpu("wall_100k", 1, 1, 1)
         out["wall_100k"] = r
     except Exception as e:  # noqa: BLE001
         out["wall_100k"] = {"error": str(e)[:200]}
+    run_deferred()
     return out
 
 
@@ -385,56 +393,87 @@ def gpu_arm(args):
     barrier()
     e2e_steps = max(3, min(args.steps, 20))
     st = batch.get_state(out=batch.alloc_state())     # observation buffers, reused every step
-    t0 = time.time()
-    for s in range(e2e_steps):
-        batch.add_force(force=force)
-        batch.step_async(H)               # queued behind the force upload; get_state below is the blocking call of the step
-        st = batch.get_state(out=st)
-    torch.cuda.synchronize()
-    e2e_t = time.time() - t0
-    tt = torch.tensor([e2e_t], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    e2e_value = ngpu * W * NBOX * e2e_steps / float(tt.item())
+
+    def e2e_loop(gather=None):
+        barrier()
+        t0 = time.time()
+        got = None
+        for s in range(e2e_steps):
+            batch.add_force(force=force)
+            batch.step_async(H)               # queued behind the force upload; get_state below is the blocking call of the step
+            if gather is not None:
+                got = gather.launch()         # pack + NCCL all_gather of stats and observations from device buffers, side stream
+            batch.get_state(out=st)
+        if gather is not None:
+            gather.wait()
+        torch.cuda.synchronize()
+        tt = torch.tensor([time.time() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return ngpu * W * NBOX * e2e_steps / float(tt.item()), got
+
+    e2e_value, _ = e2e_loop()
     h2d = int(force.nbytes)
     d2h = int(sum(v.nbytes for v in st.values()))
+    e2e_gather = None
+    if world > 1 and not args.no_gather:
+        # every rank receives the statistics and observations of ALL worlds each step (RL-style global observation),
+        # gathered by NCCL straight from the pack kernel's device buffer on a side stream, overlapping the next step
+        from ode_b200.shard import DeviceGather
+        g = DeviceGather(batch, dist)
+        e2e_loop(g)                                   # warm-up (NCCL communicator set-up)
+        v, got = e2e_loop(g)
+        e2e_gather = {"value": v, "unit": "body-steps/s", "gathered_bytes_per_step_per_rank": int(g.nbytes) * world,
+                      "what": "odeb_pack_state_device + the 4 iteration counters of every world, all_gather_into_tensor (NCCL) on a side stream, double-buffered"}
+
+    # ---- other BASELINE configs the way BASELINE states them for several GPUs: a fixed global batch split over the ranks
+    #      (world w -> rank floor(w N / W), strong scaling), timed with a barrier on both sides, max over ranks
+    strong = None
+    if world > 1 and not args.no_extras:
+        strong = {}
+        for key, mkscene, gw, hh, settle, nb in (("chain", lambda n, o: scenes.chain(n, seed0=7 + o), 65536, 0.05, 40, 10),
+                                                 ("ragdoll", lambda n, o: scenes.ragdoll(n, seed0=11 + o), 16384, 0.01, 60, 15)):
+            lo, hi = (rank * gw) // world, ((rank + 1) * gw) // world
+            bb = B.Batch(slib, mkscene(hi - lo, lo), device=local_rank)
+            bb.step(hh, settle)
+            barrier()
+            msx = C.c_double(0)
+            if not L.odeb_timed_steps(bb.h, hh, 20, FLUSH_BYTES, C.byref(msx)):
+                raise RuntimeError("timed steps failed")
+            barrier()
+            tx = torch.tensor([msx.value], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tx, op=dist.ReduceOp.MAX)
+            rf, _ = solver_roofline(L, bb, hh, (hi - lo) * nb, float(tx.item()) / 20)
+            strong[key] = {"global_worlds": gw, "worlds_per_rank": hi - lo, "ms_per_step": float(tx.item()) / 20,
+                           "body_steps_per_sec": gw * nb * 20 / (float(tx.item()) * 1e-3), "scaling": "strong",
+                           "roofline_rank0": rf,
+                           "workload": "BASELINE configs[%d]: %d worlds of the %s split over %d GPUs" % (2 if key == "chain" else 3, gw, key, world)}
+            bb.close()
 
     # ---- roofline of the dominant kernel (k_solve): algorithmic bytes / measured launch duration
     out = None
     if rank == 0:
-        s = 4 if PREC == "single" else 8
-        L.odeb_enable_timing(batch.h, 1)
-        batch.step(H, 5)
-        n = C.c_int(0)
-        sol_ms = L.odeb_solver_ms(batch.h, C.byref(n))
-        L.odeb_enable_timing(batch.h, 0)
-        tot = (C.c_uint64 * 6)()
-        L.odeb_get_totals(batch.h, tot)
-        pairs, contacts, rows, islands, sweeps, rowsweeps = [int(x) for x in tot]
-        # per row per sweep B_row = 30 s + 16; per row once (write J,iMJ; read for Ad; rewrite) 46 s + 16;
-        # per body (invI 12, cforce 6, rhs_tmp 6, fa 2) 26 s
-        alg_bytes = rowsweeps * (30 * s + 16) + rows * (46 * s + 16) + W * NBOX * 26 * s
-        sol_avg_ms = sol_ms / max(1, n.value)
-        achieved = alg_bytes / (sol_avg_ms * 1e-3) / 1e9
-        peak, which = peaks()
-        traffic = None
+        roofline, (pairs, contacts, rows, islands, sweeps, rowsweeps) = solver_roofline(L, batch, H, W * NBOX, total_ms / args.steps, extra_steps=5)
+        traffic, traffic_src = None, None
         pj = os.path.join(ROOT, "profiles", "solver_traffic.json")
         if os.path.exists(pj):
             try:
-                traffic = json.load(open(pj)).get("dram_bytes_per_launch")
+                tj = json.load(open(pj))
+                traffic = tj.get("dram_bytes_per_launch")
+                traffic_src = "static: ncu --set full capture of the same kernels on this workload (%s), not measured in this run" % tj.get("source", "profiles/solver_traffic.json")
             except Exception:
                 traffic = None
-        L.odeb_solver_kernel.restype = C.c_char_p
-        L.odeb_solver_kernel.argtypes = [C.c_void_p]
-        roofline = {"bound": "hbm", "kernel": (L.odeb_solver_kernel(batch.h) or b"k_solve").decode(), "achieved": round(achieved, 1), "peak": peak, "peak_source": which,
-                    "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
-                    "algorithmic_bytes_per_launch": int(alg_bytes), "launch_ms": round(sol_avg_ms, 4),
-                    "share_of_step": round(sol_avg_ms / (total_ms / args.steps), 3),
-                    "note": "rows are served from L2/shared memory, so algorithmic GB/s is not DRAM traffic; the kernel is bound by the serial row-update latency per world"}
+        roofline["traffic"] = traffic
+        roofline["traffic_source"] = traffic_src
+        if traffic:
+            roofline["dram_frac"] = round(traffic / (roofline["launch_ms"] * 1e-3) / 1e9 / roofline["peak"], 4)
+        roofline["limiter"] = ("lsu/latency: the row stream is served from L2 and shared memory, ncu shows the SM's LSU / shared-memory pipe and the "
+                               "per-world dependency chain as the limit, not DRAM (profiles/r2_*ncu*); `frac` is ALGORITHMIC bytes over the HBM peak, "
+                               "`dram_frac` the real DRAM traffic over the same peak")
         extras = None
         if ngpu == 1 and not args.no_extras:
             batch.close()
-            extras = other_configs(slib, local_rank)
+            extras = other_configs(slib, local_rank, with_cpu=not args.no_cpu, t_budget_end=T_START + args.budget)
         cpu = None
         if ngpu == 1 and not args.no_cpu:
             cpu = cpu_reference(args.cpu_steps, args.settle + args.warmup)
@@ -442,7 +481,7 @@ def gpu_arm(args):
             "metric": METRIC, "value": value, "unit": "body-steps/s", "n_gpus": ngpu, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if PREC == "single" else "f64", "data": "synthetic",
-            "config": {"workload": "%d worlds/GPU x %d-box stack on a plane (BASELINE configs[1]), dt=%g, 20 iters + default dynamic adjustment, auto-disable off" % (W, NBOX, H),
+            "config": {"workload": WORKLOAD,
                        "worlds_per_gpu": W, "bodies_per_world": NBOX, "precision": PREC, "settle_steps": args.settle,
                        "l2": "flushed before every timed step (256 MiB memset outside the event pairs)",
                        "per_step": {"pairs": pairs / W, "contacts": contacts / W, "rows": rows / W, "islands": islands / W,
@@ -453,10 +492,14 @@ def gpu_arm(args):
             "clocks": sampler.summary(),
             "roofline": roofline,
         }
+        if e2e_gather is not None:
+            out["e2e_with_gather"] = e2e_gather
         if cpu is not None:
             out["cpu_baseline"] = cpu
         if extras is not None:
             out["other_configs"] = extras
+        if strong is not None:
+            out["other_configs"] = strong
     batch.close()
     if world > 1:
         dist.barrier()
@@ -475,7 +518,7 @@ def reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": "body-steps/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if PREC == "single" else "f64", "data": "synthetic",
-        "config": {"workload": "%d-box stack worlds (BASELINE configs[1]) on the host CPU, %s" % (NBOX, cpu["sample"])},
+        "config": {"workload": WORKLOAD, "sampled_as": cpu["sample"]},
         "cpu_baseline": cpu,
         "e2e": {"value": cpu["value"], "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -492,6 +535,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the bounded runs of BASELINE configs[2..4]")
     ap.add_argument("--cpu-steps", type=int, default=1500)
+    ap.add_argument("--no-gather", action="store_true", help="N > 1: skip the e2e loop with the NCCL gather of stats + observations")
+    ap.add_argument("--budget", type=float, default=330.0, help="seconds after which optional slow legs (reference on the 100k wall) are skipped")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

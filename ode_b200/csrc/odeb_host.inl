@@ -36,6 +36,7 @@ struct OdebBatch {
     int hint_nb, hint_nis;                    // largest island (bodies) and most islands with rows in one world seen so far
     int graph_sr; int graph_nlaunch;          // kernels per replay of the captured step (counted while capturing)
     size_t isl_smem;                         // shared memory of k_islands_t<true> per block, 0 = scratch in global memory
+    int isl_one; size_t isl_one_smem;        // k_islands with one world per warp (4 per block) and its shared memory
     size_t solve_smem;
     int bl_G, bl_SR; size_t bl_smem;          // body-lane solver (odeb_solve_bl.cuh): lanes per world (0 = not used), row budget, bytes per warp
     void *flush_buf; size_t flush_bytes;
@@ -463,7 +464,18 @@ static OdebBatch *batch_build(const OdebWorldParams *wp, const HostTemplate &T, 
     {   // island replay scratch in shared memory when 32 worlds fit (and the 16-bit indices hold)
         const size_t need = odeb_islands_smem(P.NB, P.MC, P.NJT);
         B->isl_smem = (need <= 200 * 1024 && 2 * (size_t)P.MC < 65535 && (size_t)P.NB < 65535 && !getenv("ODEB_ISLANDS_GLOBAL")) ? need : 0;
-        if (ok && cudaFuncSetAttribute(k_islands_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) { set_err("cudaFuncSetAttribute(k_islands) failed"); ok = false; }
+        if (ok && cudaFuncSetAttribute(k_islands_t<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) { set_err("cudaFuncSetAttribute(k_islands) failed"); ok = false; }
+        // one world per warp (4 worlds per block) once a world is more than a handful of bodies: see k_islands_t
+        B->isl_one = 0; B->isl_one_smem = 0;
+        {
+            const size_t per_world = (need / 32 + 15) / 16 * 16;
+            const char *e = getenv("ODEB_ISLANDS_ONE");
+            const bool want = e ? atoi(e) != 0 : P.NB > 24;
+            if (want && B->isl_smem && 4 * per_world <= 200 * 1024) {
+                B->isl_one = 1; B->isl_one_smem = 4 * per_world;
+                if (ok && cudaFuncSetAttribute(k_islands_t<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) { set_err("cudaFuncSetAttribute(k_islands) failed"); ok = false; }
+            }
+        }
     }
     if (ok) {   // opt every solver kernel into the full 227 KB of shared memory once (the attribute is per function, not per batch)
         const int mx = 227 * 1024;
@@ -932,8 +944,9 @@ static void launch_dynamics(OdebBatch *B, cudaStream_t s, bool timed, int cfg)
     const size_t W = P.W;
     if (D.jfb) cudaMemsetAsync(D.jfb, 0, W * P.NJT * 4 * sizeof(Real4), s);      // state 0 = joint not stepped
     if (P.NJ > 0) { k_joint_info1<<<nblk(W * P.NJ, 128), 128, 0, s>>>(P, D); B->launches++; }
-    if (B->isl_smem) k_islands_t<true><<<nblk(W, 32), 32, B->isl_smem, s>>>(P, D);
-    else k_islands_t<false><<<nblk(W, 32), 32, 0, s>>>(P, D);
+    if (B->isl_one) k_islands_t<true, true><<<nblk(W * 32, 128), 128, B->isl_one_smem, s>>>(P, D);
+    else if (B->isl_smem) k_islands_t<true, false><<<nblk(W, 32), 32, B->isl_smem, s>>>(P, D);
+    else k_islands_t<false, false><<<nblk(W, 32), 32, 0, s>>>(P, D);
     k_body_pre<<<nblk(W * P.NB, 128), 128, 0, s>>>(P, D);
     if (P.NJ == 0 && !D.row_island && !getenv("ODEB_NO_FUSED_ROWS")) { k_rows_t<true><<<nblk(W * P.NJT, 64), 64, 0, s>>>(P, D); B->launches--; }
     else {

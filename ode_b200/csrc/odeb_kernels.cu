@@ -310,14 +310,19 @@ __host__ __device__ inline size_t odeb_islands_smem(int NB, int MC, int NJT)
 // SM = true: the scratch of the list replay (contact adjacency CSR, tags, DFS stack) lives in shared memory, interleaved
 // [element][thread] as 16-bit / 8-bit entries, instead of per-world global arrays: every step of the replay is a dependent
 // read-modify-write, and a world is one thread, so the kernel is bound by the latency of those accesses.
-template <bool SM>
-__global__ void __launch_bounds__(32) k_islands_t(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D)
+// ONE = true (worlds of more than a few bodies): one WORLD PER WARP, lane 0 runs the replay and its scratch is that warp's own slice of
+// shared memory (stride 1).  With a world per lane the 32 replays of a warp diverge at every branch (different contact lists, different
+// DFS orders) and execute one after the other: 4096 x 64-body piles took 488 us (0.93 M cycles per warp = 32 x the ~29 k cycles of one
+// world).  A warp per world has nothing to diverge from, and ~40 worlds are resident per SM (5 KB of scratch each) instead of 32.
+template <bool SM, bool ONE>
+__global__ void __launch_bounds__(ONE ? 128 : 32) k_islands_t(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D)
 {
     extern __shared__ __align__(16) unsigned char isl_smem[];
-    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    int w = ONE ? (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5) : (int)(blockIdx.x * blockDim.x + threadIdx.x);
     if (w >= P.W) return;
+    if (ONE && (threadIdx.x & 31) != 0) return;
     const int NB = P.NB, NJ = P.NJ, MC = P.MC;
-    constexpr int S = SM ? 32 : 1;                       // element stride of the scratch arrays
+    constexpr int S = (SM && !ONE) ? 32 : 1;             // element stride of the scratch arrays
     typedef typename IslIdx<SM>::type idx_t;             // unsigned short in shared memory, int in global memory
     const int NONE = SM ? 0xffff : -1;                   // "no second body" in adj_o
     // 1. number the contact joints in creation order (pair order, then dCollide's contact order)
@@ -345,7 +350,13 @@ __global__ void __launch_bounds__(32) k_islands_t(const __grid_constant__ DevPar
     // 2. per-body contact adjacency (CSR, ascending contact index; walked descending = newest first)
     idx_t *cofs, *ccur, *adj_c, *adj_o, *stack;
     signed char *btag, *jtag;
-    if (SM) {
+    if (SM && ONE) {
+        const size_t per_world = (odeb_islands_smem(NB, MC, P.NJT) / 32 + 15) / 16 * 16;
+        idx_t *q = (idx_t *)(isl_smem + (threadIdx.x >> 5) * per_world);
+        cofs = q; q += (size_t)(NB + 1); ccur = q; q += (size_t)NB; adj_c = q; q += (size_t)2 * MC;
+        adj_o = q; q += (size_t)2 * MC; stack = q; q += (size_t)NB;
+        btag = (signed char *)q; jtag = btag + (size_t)NB;
+    } else if (SM) {
         idx_t *q = (idx_t *)isl_smem + threadIdx.x;
         cofs = q; q += (size_t)(NB + 1) * 32; ccur = q; q += (size_t)NB * 32; adj_c = q; q += (size_t)2 * MC * 32;
         adj_o = q; q += (size_t)2 * MC * 32; stack = q; q += (size_t)NB * 32;

@@ -326,8 +326,10 @@ __global__ void __launch_bounds__(32) k_solve_t(const __grid_constant__ DevParam
     // Hybrid solve: islands are handed over to k_solve5 only if EVERY island of the world can be (or finishes before the hand-over).  An
     // island completed here draws its reorders from the world's seed at once; were an earlier island of the same world paused, it would
     // draw later (in k_solve5) what the reference gives it first, and both islands would see different random orders.
-    bool world_pausable = stop_after != 0;
-    if (stop_after) for (int is = 0; is < nis; is++) if (iinfo[is].w > sr_b || iinfo[is].w > P.SR) world_pausable = false;
+    // (decided from the world's total row count: sufficient, exact for single-island worlds, and one independent load instead of a scan
+    //  of the island table at the start of the kernel)
+    // (kept as a per-lane row threshold: the same test as a separate predicate costs 20 us per launch at 4096 worlds, measured)
+    const int srb_w = (stop_after != 0 && valid && D.mrows[w] <= (sr_b < P.SR ? sr_b : P.SR)) ? sr_b : -1;
     for (int is = 0; is < nis_max; is++) {
         int4 info = make_int4(0, 0, 0, 0);
         if (is < nis) info = iinfo[is];
@@ -372,7 +374,7 @@ __global__ void __launch_bounds__(32) k_solve_t(const __grid_constant__ DevParam
         int paused = 0;
         if (__any_sync(ODEB_FULL, m_smem > 0))
             solve_islands_warp<HY>(P, smem, lane, rows, findex, rbody, cf_out, (D.jcopy || stop_after) ? D.lambda + (size_t)w * P.MR : 0, bstart, nb, rstart, m_smem, seed, st1, st2, st3, sweeps, rowsweeps,
-                                   world_pausable && m_smem <= sr_b, &paused);
+                                   m_smem <= srb_w, &paused);
         if (stop_after && side == 0 && is < nis && valid) D.isl_done[(size_t)w * P.NB + is] = paused ? 0 : 1;
         if (is < nis) st0++;
     }

@@ -14,5 +14,15 @@ gpu = B.Batch(gpu_lib(prec), sc)
 if name == "wall":
     gpu.set_solver_mode(1)
 gpu.step(h, warm)
+# ncu --profile-from-start off: only the last `steps` steps are captured
+import ctypes
+rt = None
+for name_ in ("libcudart.so", "libcudart.so.12", "/usr/local/cuda/lib64/libcudart.so"):
+    try:
+        rt = ctypes.CDLL(name_); break
+    except OSError:
+        pass
+if rt: rt.cudaProfilerStart()
 gpu.step(h, steps)
+if rt: rt.cudaProfilerStop()
 print("done", gpu.get_totals())
