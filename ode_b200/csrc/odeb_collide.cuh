@@ -172,239 +172,13 @@ __device__ int odeb_sphere_plane(const DGeom &o1, const DGeom &o2, DContactGeom 
     return 0;
 }
 
-// dLineClosestApproach collision_util.cpp:70-92
-__device__ void odeb_line_closest_approach(const Real *pa, const Real *ua, const Real *pb, const Real *ub, Real *alpha, Real *beta)
-{
-    Real p[3] = { pb[0] - pa[0], pb[1] - pa[1], pb[2] - pa[2] };
-    Real uaub = dot3(ua, ub), q1 = dot3(ua, p), q2 = -dot3(ub, p);
-    Real d = 1 - uaub * uaub;
-    if (d <= R_(0.0001)) { *alpha = 0; *beta = 0; }
-    else { d = rrecip(d); *alpha = (q1 + uaub * q2) * d; *beta = (uaub * q1 + q2) * d; }
-}
-
-// intersectRectQuad box.cpp:212-263
-__device__ __noinline__ int odeb_intersect_rect_quad(const Real h[2], Real p[8], Real ret[16])
-{
-    int nq = 4, nr = 0;
-    Real buffer[16];
-    Real *q = p, *r = ret;
-    for (int dir = 0; dir <= 1; dir++) {
-        for (int sign = -1; sign <= 1; sign += 2) {
-            Real *pq = q, *pr = r;
-            nr = 0;
-            for (int i = nq; i > 0; i--) {
-                if (sign * pq[dir] < h[dir]) {
-                    pr[0] = pq[0]; pr[1] = pq[1]; pr += 2; nr++;
-                    if (nr & 8) { q = r; goto done; }
-                }
-                Real *nextq = (i > 1) ? pq + 2 : q;
-                if ((sign * pq[dir] < h[dir]) ^ (sign * nextq[dir] < h[dir])) {
-                    pr[1 - dir] = pq[1 - dir] + (nextq[1 - dir] - pq[1 - dir]) / (nextq[dir] - pq[dir]) * (sign * h[dir] - pq[dir]);
-                    pr[dir] = sign * h[dir];
-                    pr += 2; nr++;
-                    if (nr & 8) { q = r; goto done; }
-                }
-                pq += 2;
-            }
-            q = r;
-            r = (q == ret) ? buffer : ret;
-            nq = nr;
-        }
-    }
-done:
-    if (q != ret) for (int t = 0; t < nr * 2; t++) ret[t] = q[t];
-    return nr;
-}
-
-// cullPoints box.cpp:274-336 (note the double-precision M_PI expressions in the single build)
-__device__ __noinline__ void odeb_cull_points(int n, const Real p[], int m, int i0, int iret[])
-{
-    int i, j;
-    Real a, cx, cy, q;
-    if (n == 1) { cx = p[0]; cy = p[1]; }
-    else if (n == 2) { cx = R_(0.5) * (p[0] + p[2]); cy = R_(0.5) * (p[1] + p[3]); }
-    else {
-        a = 0; cx = 0; cy = 0;
-        for (i = 0; i < (n - 1); i++) {
-            q = p[i * 2] * p[i * 2 + 3] - p[i * 2 + 2] * p[i * 2 + 1];
-            a += q;
-            cx += q * (p[i * 2] + p[i * 2 + 2]);
-            cy += q * (p[i * 2 + 1] + p[i * 2 + 3]);
-        }
-        q = p[n * 2 - 2] * p[1] - p[0] * p[n * 2 - 1];
-        a = rrecip(R_(3.0) * (a + q));
-        cx = a * (cx + q * (p[n * 2 - 2] + p[0]));
-        cy = a * (cy + q * (p[n * 2 - 1] + p[1]));
-    }
-    Real A[8];
-    for (i = 0; i < n; i++) A[i] = RATAN2(p[i * 2 + 1] - cy, p[i * 2] - cx);
-    int avail[8];
-    for (i = 0; i < n; i++) avail[i] = 1;
-    avail[i0] = 0;
-    iret[0] = i0;
-    iret++;
-    for (j = 1; j < m; j++) {
-        a = (Real)((Real)j * (2 * M_PI / m) + A[i0]);
-        if (a > M_PI) a -= (Real)(2 * M_PI);
-        Real maxdiff = 1e9, diff;
-        *iret = i0;
-        for (i = 0; i < n; i++) {
-            if (avail[i]) {
-                diff = RFABS(A[i] - a);
-                if (diff > M_PI) diff = (Real)(2 * M_PI - diff);
-                if (diff < maxdiff) { maxdiff = diff; *iret = i; }
-            }
-        }
-        avail[*iret] = 0;
-        iret++;
-    }
-}
-
-// dBoxBox box.cpp:356-737. Returns contact count; normal/depth/code as the reference.
+// box-box: odeb_boxbox.cuh (separating-axis loop, edge / face manifold builders, rectangle clipper, contact spreading).  Kept out of
+// line: k_narrow and the capsule-box collider both call it, and inlining it twice costs k_narrow ~40 registers.
+#include "odeb_boxbox.cuh"
 __device__ __noinline__ int odeb_box_box(const Real *p1, const Real *R1, const Real *side1, const Real *p2, const Real *R2, const Real *side2,
-                              Real *normal, Real *depth, int *return_code, int flags, DContactGeom *contact)
+                                         Real *normal, Real *depth, int *return_code, int flags, DContactGeom *contact)
 {
-    const Real fudge = R_(1.05);
-    Real p[3], pp[3], normalC[3] = { 0, 0, 0 };
-    const Real *normalR = 0;
-    Real A[3], B[3], Rm[3][3], Q[3][3], s, s2, l, e1;
-    int i, j, invert_normal, code;
-    p[0] = p2[0] - p1[0]; p[1] = p2[1] - p1[1]; p[2] = p2[2] - p1[2];
-    mul1_331(pp, R1, p);
-    for (i = 0; i < 3; i++) { A[i] = side1[i] * R_(0.5); B[i] = side2[i] * R_(0.5); }
-    for (i = 0; i < 3; i++) for (j = 0; j < 3; j++) { Rm[i][j] = dot3s(R1 + i, 4, R2 + j, 4); Q[i][j] = RFABS(Rm[i][j]); }
-    s = -R_INF; invert_normal = 0; code = 0;
-    const bool unimportant = (flags & ODEB_CONTACTS_UNIMPORTANT) != 0;
-    do {
-#define ODEB_TST1(expr1, expr2, norm, cc) \
-        e1 = (expr1); s2 = RFABS(e1) - (expr2); if (s2 > 0) return 0; \
-        if (s2 > s) { s = s2; normalR = norm; invert_normal = (e1 < 0); code = (cc); if (unimportant) break; }
-        ODEB_TST1(pp[0], (A[0] + B[0] * Q[0][0] + B[1] * Q[0][1] + B[2] * Q[0][2]), R1 + 0, 1);
-        ODEB_TST1(pp[1], (A[1] + B[0] * Q[1][0] + B[1] * Q[1][1] + B[2] * Q[1][2]), R1 + 1, 2);
-        ODEB_TST1(pp[2], (A[2] + B[0] * Q[2][0] + B[1] * Q[2][1] + B[2] * Q[2][2]), R1 + 2, 3);
-        ODEB_TST1(dot3s(R2 + 0, 4, p, 1), (A[0] * Q[0][0] + A[1] * Q[1][0] + A[2] * Q[2][0] + B[0]), R2 + 0, 4);
-        ODEB_TST1(dot3s(R2 + 1, 4, p, 1), (A[0] * Q[0][1] + A[1] * Q[1][1] + A[2] * Q[2][1] + B[1]), R2 + 1, 5);
-        ODEB_TST1(dot3s(R2 + 2, 4, p, 1), (A[0] * Q[0][2] + A[1] * Q[1][2] + A[2] * Q[2][2] + B[2]), R2 + 2, 6);
-#undef ODEB_TST1
-#define ODEB_TST2(expr1, expr2, n1, n2, n3, cc) \
-        e1 = (expr1); s2 = RFABS(e1) - (expr2); if (s2 > 0) return 0; \
-        l = RSQRT((n1) * (n1) + (n2) * (n2) + (n3) * (n3)); \
-        if (l > 0) { s2 /= l; if (s2 * fudge > s) { s = s2; normalR = 0; \
-            normalC[0] = (n1) / l; normalC[1] = (n2) / l; normalC[2] = (n3) / l; \
-            invert_normal = (e1 < 0); code = (cc); if (unimportant) break; } }
-        ODEB_TST2(pp[2] * Rm[1][0] - pp[1] * Rm[2][0], (A[1] * Q[2][0] + A[2] * Q[1][0] + B[1] * Q[0][2] + B[2] * Q[0][1]), 0, -Rm[2][0], Rm[1][0], 7);
-        ODEB_TST2(pp[2] * Rm[1][1] - pp[1] * Rm[2][1], (A[1] * Q[2][1] + A[2] * Q[1][1] + B[0] * Q[0][2] + B[2] * Q[0][0]), 0, -Rm[2][1], Rm[1][1], 8);
-        ODEB_TST2(pp[2] * Rm[1][2] - pp[1] * Rm[2][2], (A[1] * Q[2][2] + A[2] * Q[1][2] + B[0] * Q[0][1] + B[1] * Q[0][0]), 0, -Rm[2][2], Rm[1][2], 9);
-        ODEB_TST2(pp[0] * Rm[2][0] - pp[2] * Rm[0][0], (A[0] * Q[2][0] + A[2] * Q[0][0] + B[1] * Q[1][2] + B[2] * Q[1][1]), Rm[2][0], 0, -Rm[0][0], 10);
-        ODEB_TST2(pp[0] * Rm[2][1] - pp[2] * Rm[0][1], (A[0] * Q[2][1] + A[2] * Q[0][1] + B[0] * Q[1][2] + B[2] * Q[1][0]), Rm[2][1], 0, -Rm[0][1], 11);
-        ODEB_TST2(pp[0] * Rm[2][2] - pp[2] * Rm[0][2], (A[0] * Q[2][2] + A[2] * Q[0][2] + B[0] * Q[1][1] + B[1] * Q[1][0]), Rm[2][2], 0, -Rm[0][2], 12);
-        ODEB_TST2(pp[1] * Rm[0][0] - pp[0] * Rm[1][0], (A[0] * Q[1][0] + A[1] * Q[0][0] + B[1] * Q[2][2] + B[2] * Q[2][1]), -Rm[1][0], Rm[0][0], 0, 13);
-        ODEB_TST2(pp[1] * Rm[0][1] - pp[0] * Rm[1][1], (A[0] * Q[1][1] + A[1] * Q[0][1] + B[0] * Q[2][2] + B[2] * Q[2][0]), -Rm[1][1], Rm[0][1], 0, 14);
-        ODEB_TST2(pp[1] * Rm[0][2] - pp[0] * Rm[1][2], (A[0] * Q[1][2] + A[1] * Q[0][2] + B[0] * Q[2][1] + B[1] * Q[2][0]), -Rm[1][2], Rm[0][2], 0, 15);
-#undef ODEB_TST2
-    } while (0);
-    if (!code) return 0;
-    if (normalR) { normal[0] = normalR[0]; normal[1] = normalR[4]; normal[2] = normalR[8]; }
-    else mul0_331(normal, R1, normalC);
-    if (invert_normal) { normal[0] = -normal[0]; normal[1] = -normal[1]; normal[2] = -normal[2]; }
-    *depth = -s;
-
-    if (code > 6) {
-        Real pa[3], pb[3], sign;
-        for (i = 0; i < 3; i++) pa[i] = p1[i];
-        for (j = 0; j < 3; j++) {
-            sign = (dot3s(normal, 1, R1 + j, 4) > 0) ? R_(1.0) : R_(-1.0);
-            for (i = 0; i < 3; i++) pa[i] += sign * A[j] * R1[i * 4 + j];
-        }
-        for (i = 0; i < 3; i++) pb[i] = p2[i];
-        for (j = 0; j < 3; j++) {
-            sign = (dot3s(normal, 1, R2 + j, 4) > 0) ? R_(-1.0) : R_(1.0);
-            for (i = 0; i < 3; i++) pb[i] += sign * B[j] * R2[i * 4 + j];
-        }
-        Real alpha, beta, ua[3], ub[3];
-        for (i = 0; i < 3; i++) ua[i] = R1[(code - 7) / 3 + i * 4];
-        for (i = 0; i < 3; i++) ub[i] = R2[(code - 7) % 3 + i * 4];
-        odeb_line_closest_approach(pa, ua, pb, ub, &alpha, &beta);
-        for (i = 0; i < 3; i++) pa[i] += ua[i] * alpha;
-        for (i = 0; i < 3; i++) pb[i] += ub[i] * beta;
-        for (i = 0; i < 3; i++) contact[0].pos[i] = R_(0.5) * (pa[i] + pb[i]);
-        contact[0].depth = *depth;
-        *return_code = code;
-        return 1;
-    }
-
-    const Real *Ra, *Rb, *pa, *pb, *Sa, *Sb;
-    if (code <= 3) { Ra = R1; Rb = R2; pa = p1; pb = p2; Sa = A; Sb = B; }
-    else { Ra = R2; Rb = R1; pa = p2; pb = p1; Sa = B; Sb = A; }
-    Real normal2[3], nr[3], anr[3];
-    if (code <= 3) { normal2[0] = normal[0]; normal2[1] = normal[1]; normal2[2] = normal[2]; }
-    else { normal2[0] = -normal[0]; normal2[1] = -normal[1]; normal2[2] = -normal[2]; }
-    mul1_331(nr, Rb, normal2);
-    anr[0] = RFABS(nr[0]); anr[1] = RFABS(nr[1]); anr[2] = RFABS(nr[2]);
-    int lanr, a1, a2;
-    if (anr[1] > anr[0]) {
-        if (anr[1] > anr[2]) { a1 = 0; lanr = 1; a2 = 2; } else { a1 = 0; a2 = 1; lanr = 2; }
-    } else {
-        if (anr[0] > anr[2]) { lanr = 0; a1 = 1; a2 = 2; } else { a1 = 0; a2 = 1; lanr = 2; }
-    }
-    Real center[3];
-    if (nr[lanr] < 0) { for (i = 0; i < 3; i++) center[i] = pb[i] - pa[i] + Sb[lanr] * Rb[i * 4 + lanr]; }
-    else { for (i = 0; i < 3; i++) center[i] = pb[i] - pa[i] - Sb[lanr] * Rb[i * 4 + lanr]; }
-    int codeN, code1, code2;
-    codeN = (code <= 3) ? code - 1 : code - 4;
-    if (codeN == 0) { code1 = 1; code2 = 2; } else if (codeN == 1) { code1 = 0; code2 = 2; } else { code1 = 0; code2 = 1; }
-    Real quad[8], c1, c2, m11, m12, m21, m22;
-    c1 = dot3s(center, 1, Ra + code1, 4);
-    c2 = dot3s(center, 1, Ra + code2, 4);
-    m11 = dot3s(Ra + code1, 4, Rb + a1, 4); m12 = dot3s(Ra + code1, 4, Rb + a2, 4);
-    m21 = dot3s(Ra + code2, 4, Rb + a1, 4); m22 = dot3s(Ra + code2, 4, Rb + a2, 4);
-    {
-        Real k1 = m11 * Sb[a1], k2 = m21 * Sb[a1], k3 = m12 * Sb[a2], k4 = m22 * Sb[a2];
-        quad[0] = c1 - k1 - k3; quad[1] = c2 - k2 - k4; quad[2] = c1 - k1 + k3; quad[3] = c2 - k2 + k4;
-        quad[4] = c1 + k1 + k3; quad[5] = c2 + k2 + k4; quad[6] = c1 + k1 - k3; quad[7] = c2 + k2 - k4;
-    }
-    Real rect[2] = { Sa[code1], Sa[code2] };
-    Real ret[16];
-    int n = odeb_intersect_rect_quad(rect, quad, ret);
-    if (n < 1) return 0;
-    Real point[3 * 8], dep[8];
-    Real det1 = rrecip(m11 * m22 - m12 * m21);
-    m11 *= det1; m12 *= det1; m21 *= det1; m22 *= det1;
-    int cnum = 0;
-    for (j = 0; j < n; j++) {
-        Real k1 = m22 * (ret[j * 2] - c1) - m12 * (ret[j * 2 + 1] - c2);
-        Real k2 = -m21 * (ret[j * 2] - c1) + m11 * (ret[j * 2 + 1] - c2);
-        for (i = 0; i < 3; i++) point[cnum * 3 + i] = center[i] + k1 * Rb[i * 4 + a1] + k2 * Rb[i * 4 + a2];
-        dep[cnum] = Sa[codeN] - dot3(normal2, point + cnum * 3);
-        if (dep[cnum] >= 0) {
-            ret[cnum * 2] = ret[j * 2]; ret[cnum * 2 + 1] = ret[j * 2 + 1];
-            cnum++;
-            if ((unsigned)(cnum | ODEB_CONTACTS_UNIMPORTANT) == ((unsigned)flags & (ODEB_NUMC_MASK | ODEB_CONTACTS_UNIMPORTANT))) break;
-        }
-    }
-    if (cnum < 1) return 0;
-    int maxc = flags & ODEB_NUMC_MASK;
-    if (maxc > cnum) maxc = cnum;
-    if (maxc < 1) maxc = 1;
-    if (cnum <= maxc) {
-        for (j = 0; j < cnum; j++) {
-            for (i = 0; i < 3; i++) contact[j].pos[i] = point[j * 3 + i] + pa[i];
-            contact[j].depth = dep[j];
-        }
-    } else {
-        int i1 = 0;
-        Real maxdepth = dep[0];
-        for (i = 1; i < cnum; i++) if (dep[i] > maxdepth) { maxdepth = dep[i]; i1 = i; }
-        int iret[8];
-        odeb_cull_points(cnum, ret, maxc, i1, iret);
-        for (j = 0; j < maxc; j++) {
-            for (i = 0; i < 3; i++) contact[j].pos[i] = point[iret[j] * 3 + i] + pa[i];
-            contact[j].depth = dep[iret[j]];
-        }
-        cnum = maxc;
-    }
-    *return_code = code;
-    return cnum;
+    return odeb_bb_collide(p1, R1, side1, p2, R2, side2, normal, depth, return_code, flags, contact);
 }
 
 // dCollideBoxBox box.cpp:741-767
@@ -584,9 +358,6 @@ __device__ int odeb_capsule_sphere(const DGeom &o1, const DGeom &o2, DContactGeo
     Real p[3] = { o1.pos[0] + alpha * R[2], o1.pos[1] + alpha * R[6], o1.pos[2] + alpha * R[10] };
     return odeb_collide_spheres(p, o1.p[0], o2.pos, o2.p[0], c);
 }
-
-__device__ __noinline__ int odeb_box_box(const Real *p1, const Real *R1, const Real *side1, const Real *p2, const Real *R2, const Real *side2,
-                              Real *normal, Real *depth, int *return_code, int flags, DContactGeom *contact);
 
 // dCollideCapsuleBox capsule.cpp:166-237
 __device__ int odeb_capsule_box(const DGeom &o1, const DGeom &o2, int flags, DContactGeom *contact)
