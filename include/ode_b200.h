@@ -192,13 +192,18 @@ int odeb_get_enabled(OdebBatch *, int *enabled /* [world][body] */);
  *     is inherently serial in this mode, so it is meant for batches of small worlds.
  *   ODEB_MODE_CANONICAL: the large-world path (single worlds of 10^3..10^5 bodies).  Pair set, contacts, island membership
  *     and island numbering are those of the reference; inside an island bodies are ordered by descending creation index and
- *     joints by ascending id (permanent joints, then contacts in creation order).  The row order of sweeps 0..7 keeps
- *     ReorderPrep's two classes (rows without a friction index first) but sorts each class by odeb_canon_key(seed, island, 0,
- *     row); the reorder at sweep 8k sorts all rows by odeb_canon_key(seed, island, k, row) instead of replaying Fisher-Yates,
- *     and the world's dRand seed is advanced by the draws the reference would have consumed.  Hashed orders keep the
- *     dependency graph of a sweep shallow; the sweeps themselves keep the sequential semantics of that order (a row runs
- *     after exactly the rows that precede it on its two bodies), so the result is bit-identical to the oracle run in the same
- *     mode (oracle: orc_set_solver_mode) and is one of the orders the reference's own random reordering could produce.
+ *     joints by ascending id (permanent joints, then contacts in creation order).  Rows are taken in GROUPS (the rows of the contacts
+ *     of one geom pair, or of one permanent joint: they act on the same two bodies).  For every phase of 8 sweeps (phase k starts at
+ *     sweep 8k, where the reference reorders) the groups of an island are coloured so that groups of one colour touch disjoint
+ *     bodies -- rounds of "every uncoloured group whose (odeb_canon_key(seed, island, k, first row), first row) exceeds that of all its
+ *     uncoloured neighbours takes the smallest colour none of its coloured neighbours holds" -- and the sweep order is colour
+ *     ascending, group ascending, rows of a group in row order (a contact's normal row right before its friction rows).  The
+ *     world's dRand seed is advanced by the draws the reference's Fisher-Yates reorders would have consumed.  Groups of one colour
+ *     are relaxed side by side on the GPU with exactly the result of the sequential sweep in that order, so the CUDA path is
+ *     bit-identical to the oracle run in the same mode (oracle: orc_set_solver_mode).  The order is this library's own (the
+ *     reference's is the attach order, then random permutations): trajectories differ from the reference the way two random
+ *     reorderings of the reference differ from each other (profiles/r2_callback_order.txt); everything a step decides before the
+ *     solver runs (pair set, contacts, islands) is the reference's.
  *     Requires nworlds == 1. */
 enum { ODEB_MODE_REPLAY = 0, ODEB_MODE_CANONICAL = 1 };
 int odeb_set_solver_mode(OdebBatch *, int mode);

@@ -54,7 +54,7 @@ static int overflow_check(OdebBatch *B)
     const int ov = ovh[0];
     if (ov) {
         set_err("capacity overflow (%s): raise OdebWorldParams.max_pairs / max_contacts_per_world (or ODEB_MAX_PAIRS / ODEB_MAX_CONTACTS); the body state is the one the last complete step left",
-                ov == 1 ? "pairs" : ov == 2 ? "contacts" : "rows");
+                ov == 1 ? "pairs" : ov == 2 ? "contacts" : ov == 3 ? "rows" : "row groups on one body (large-world colouring: more than 62)");
         CK(cudaMemsetAsync(B->D.overflow, 0, sizeof(int), B->stream));
         CK(cudaStreamSynchronize(B->stream));
         return 0;
@@ -453,8 +453,8 @@ static OdebBatch *batch_build(const OdebWorldParams *wp, const HostTemplate &T, 
             && dev_alloc(B, &D.body_order, WB) && dev_alloc(B, &D.body_pos, WB) && dev_alloc(B, &D.body_island, WB)
             && dev_alloc(B, &D.joint_order, W * P.NJT) && dev_alloc(B, &D.joint_row, W * P.NJT) && dev_alloc(B, &D.joint_island, W * P.NJT)
             && dev_alloc(B, &D.island_info, WB) && dev_alloc(B, &D.nislands, W) && dev_alloc(B, &D.nordered, W) && dev_alloc(B, &D.njord, W) && dev_alloc(B, &D.mrows, W);
-    ok = ok && dev_alloc(B, &D.rows, W * P.MR * 8) && dev_alloc(B, &D.rbody, W * P.MR) && dev_alloc(B, &D.findex, W * P.MR) && dev_alloc(B, &D.order, W * P.MR) && dev_alloc(B, &D.order0, W * P.MR) && dev_alloc(B, &D.wkey, W) && dev_alloc(B, &D.wlist, W)
-            && dev_alloc(B, &D.lambda, W * P.MR) && dev_alloc(B, &D.cforce, W * (nbody + 1) * 2) && dev_alloc(B, &D.invIw, WB * 12)
+    ok = ok && dev_alloc(B, &D.rows, W * P.MR * 8) && dev_alloc(B, &D.rbody, W * P.MR) && dev_alloc(B, &D.findex, W * P.MR + 8) && dev_alloc(B, &D.order, W * P.MR) && dev_alloc(B, &D.order0, W * P.MR) && dev_alloc(B, &D.wkey, W) && dev_alloc(B, &D.wlist, W)
+            && dev_alloc(B, &D.lambda, W * P.MR + 8) && dev_alloc(B, &D.cforce, W * (nbody + 1) * 2) && dev_alloc(B, &D.invIw, WB * 12)
             && dev_alloc(B, &D.stats, W * 4) && dev_alloc(B, &D.seed, W) && dev_alloc(B, &D.sweeps, 2 * W) && dev_alloc(B, &D.overflow, 4) && dev_alloc(B, &D.isl_done, WB) && dev_alloc(B, &D.maxpairs, 1);
     B->stage_elems = 4 * WB;                     // room for the tightly packed state of every body (13 reals) in one transfer
     ok = ok && dev_alloc(B, &B->d_stage, 4 * WB);

@@ -2,7 +2,7 @@
 //
 // The batched path gives each world to one warp lane pair; a single big world needs parallelism INSIDE the
 // world instead.  Every serial list walk of the reference is replaced by a sort / scan / union-find that yields
-// the same sets, and the order-sensitive SOR sweep keeps its sequential semantics through per-body tickets:
+// the same sets, and the order-sensitive SOR sweep keeps its sequential semantics through a colouring of the row groups:
 //
 //   broadphase   k_bp_keys + radix sort on (float)aabb.min[0] + k_bp_sweep / k_bp_big + radix sort of the pair keys
 //                -> the same pair set as k_pair_pass (collision_sapspace.cpp:521-582 BoxPruning is itself a sort + sweep;
@@ -12,11 +12,14 @@
 //   islands      lock-free union-find over all joints (util.cpp:724-860 finds the same components with a DFS);
 //                island number = rank of the component's highest enabled body, descending (world->firstbody order)
 //   order        bodies (island, descending index), joints (island, ascending id) by radix sort; row offsets by scan
-//   solve        per phase of 8 sweeps: row order = radix sort of (island, class|hash key); per body the rows that
-//                touch it are ranked by their position ("tickets"); k_lw_sweep walks the order with all SMs, a row
-//                runs when both of its bodies' counters have reached its tickets, i.e. after exactly the rows that
-//                precede it on those bodies in the sequential sweep (quickstep.cpp:2917-3033) -> bit-identical to the
-//                sequential sweep in that order, no level barriers
+//   solve        per phase of 8 sweeps the row GROUPS (rows of the contacts of one geom pair / of one joint: same two bodies) are
+//                coloured so that groups of one colour touch disjoint bodies (Jones-Plassmann rounds with first fit, priorities =
+//                odeb_canon_key(seed, island, phase, group): deterministic, the oracle runs the same rounds); the canonical sweep
+//                order is colour-major, and k_lwc_sweep relaxes all groups of a colour side by side, one thread per group with the
+//                two bodies' accumulators in registers: bit-identical to the sequential sweep in that order (quickstep.cpp:2917-3033),
+//                no tickets, no fences, no polling -- ~9 colours on a brick wall, i.e. ~9 short launches per sweep
+//                (round 1 walked a hash-sorted order with per-body tickets: 0.58 ms per sweep on the 100k-box wall, bound by the
+//                L2 round trips of the release / acquire hand-over along the dependency paths)
 //   control      k_lw_body_check + k_lw_island_ctl after every sweep (quickstep.cpp:1823-1856, :3253-3285), per island
 #ifndef ODEB_LARGE_CUH
 #define ODEB_LARGE_CUH
@@ -26,7 +29,7 @@ typedef unsigned long long u64;
 #define LW_NOKEY 0xFFFFFFFFFFFFFFFFull
 
 enum { LWC_NBIG = 0, LWC_NPAIRS = 1, LWC_NCONTACTS = 2, LWC_NORDERED = 3, LWC_NJORD = 4, LWC_MROWS = 5, LWC_NISLANDS = 6,
-       LWC_NACTIVE = 7, LWC_CURSOR = 8, LWC_COUNT = 16 };
+       LWC_NACTIVE = 7, LWC_NGROUPS = 8, LWC_UNCOLORED = 9, LWC_NCOLORS = 10, LWC_BIGGROUPS = 11, LWC_CHUNKS = 12, LWC_COUNT = 16 };
 
 struct LargePtrs {
     int *counters;                               // [LWC_COUNT]
@@ -42,11 +45,13 @@ struct LargePtrs {
     u64 *jkey, *jkey_s; int *jmv, *jmv_s, *jrow; // [NJT]
     // solver
     int *row_island;                             // [MR]
-    u64 *okey, *okey_s; int *oval, *ord, *rpos;  // [MR]
-    int *inc_ofs, *inc_cur, *inc, *inc_pos;      // [NB + 2], [NB + 1], [2 MR], [2 MR]
-    int2 *ticket;                                // [MR] at the head position of a run: the run's ticket on body 1, on body 2
-    int *row_group, *head_pos;                   // [MR] first row of the row's group; first position of the position's run
-    unsigned *cnt;                               // [NB + 1] runs executed on each body in the running sweep
+    int *row_group;                              // [MR] first row of the row's group
+    int *gsize, *heads;                          // [MR] rows of the group (at its first row); first rows of all groups, compacted
+    int *ginc_ofs, *ginc_cur, *ginc;             // [NB + 2], [NB + 2], [2 MR]: body (order position) -> groups acting on it
+    unsigned *gkey; int *gcolor, *gwin;          // [MR] at the group's first row: priority of the phase, colour (-1 none yet, -2 island finished), winner flag
+    int *clist, *ccount, *cofs;                  // [MR] groups by colour; [64] groups per colour; [65] first list position of every colour
+    int4 *cinfo;                                 // [MR] beside clist: (first row, rows, accumulator slot of body 1, of body 2) of the group
+    int *slot_row, *cstart;                      // [3 MR + 4096] row of every lane of every 32-row chunk (-1: empty); [65] first chunk of every colour
     void *tmp; size_t tmp_bytes;                 // cub scratch
 };
 
@@ -216,7 +221,7 @@ __global__ void k_lw_init_bodies(const __grid_constant__ DevParams P, const __gr
 {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b > P.NB) return;
-    L.isl_nb[b] = 0; L.isl_m[b] = 0; L.isl_done[b] = 0; L.isl_viol[b] = 0; L.cnt[b] = 0; L.inc_cur[b] = 0;
+    L.isl_nb[b] = 0; L.isl_m[b] = 0; L.isl_done[b] = 0; L.isl_viol[b] = 0; L.ginc_cur[b] = 0;
     if (b == P.NB) return;
     L.parent[b] = b; L.maxen[b] = -1;
 }
@@ -318,101 +323,114 @@ __global__ void k_lw_island_info(const __grid_constant__ DevParams P, const __gr
     if (m == 0) L.isl_done[is] = 1; else atomicAdd(&L.counters[LWC_NACTIVE], 1);
 }
 
-// ------------------------------------------------------------------------------------------------ solve: order + tickets
-__global__ void k_lw_inc_count(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L, int mrows)
-{
-    int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= mrows) return;
-    int2 rb = D.rbody[r];
-    atomicAdd(&L.inc_cur[rb.x], 1);
-    if (rb.y != P.NB) atomicAdd(&L.inc_cur[rb.y], 1);
-    D.lambda[r] = 0;
-}
-__global__ void k_lw_inc_fill(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L, int mrows)
-{
-    int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= mrows) return;
-    int2 rb = D.rbody[r];
-    L.inc[L.inc_ofs[rb.x] + atomicAdd(&L.inc_cur[rb.x], 1)] = 2 * r;
-    if (rb.y != P.NB) L.inc[L.inc_ofs[rb.y] + atomicAdd(&L.inc_cur[rb.y], 1)] = 2 * r + 1;
-}
+// ------------------------------------------------------------------------------------------------ solve: groups, colours, sweeps
 __global__ void k_lw_zero_cur(int n, int *v) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) v[i] = 0; }
 
-// Row order of one phase.  Rows are grouped: the rows of the contacts of one geom pair form a group (so do the rows of one
-// permanent joint); a group's key is odeb_canon_key(seed, island, phase, island-local index of the group's first row).
-// Phase 0 keeps ReorderPrep's two classes (rows without a friction index first, quickstep.cpp:2329-2355) and sorts each
-// class by group key; phase k >= 1 (the reorder at sweep 8k) sorts all rows by group key. Ties: ascending row index, so
-// the rows of a group stay adjacent and in joint order.
-__global__ void k_lw_order_keys(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L, int mrows, int phase)
+// once per step: size of every group, the compact list of groups (first rows), how many groups act on every body, lambda = 0
+__global__ void k_lwc_groups(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L, int mrows)
 {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= mrows) return;
-    const unsigned is = (unsigned)L.row_island[r];
-    const unsigned glocal = (unsigned)(L.row_group[r] - L.isl_rstart[is]);
-    u64 low = odebi_canon_key(D.seed[0], is, (unsigned)phase, glocal);
-    if (phase == 0 && D.findex[r] != -1) low |= 1ull << 32;
-    L.okey[r] = ((u64)is << 33) | low;
-    L.oval[r] = r;
+    D.lambda[r] = 0;
+    const int g = L.row_group[r];
+    atomicAdd(&L.gsize[g], 1);
+    if (g != r) return;
+    L.heads[atomicAdd(&L.counters[LWC_NGROUPS], 1)] = r;
+    const int2 rb = D.rbody[r];
+    atomicAdd(&L.ginc_cur[rb.x], 1);
+    if (rb.y != P.NB) atomicAdd(&L.ginc_cur[rb.y], 1);
 }
-// Runs: maximal stretches of consecutive positions inside one 32-position chunk that belong to one group (and, in phase 0,
-// one class). All rows of a run act on the same two bodies, so a run is the unit of scheduling: head_pos[p] = position
-// of the first row of p's run. Also the inverse permutation rpos.
-__global__ void k_lw_runs(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L, int mrows, int phase)
+__global__ void k_lwc_ginc_fill(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L)
 {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;          // blockDim is a multiple of 32: warps are chunk-aligned
-    const int lane = threadIdx.x & 31;
-    int key = -1;
-    if (p < mrows) {
-        const int r = L.ord[p];
-        L.rpos[r] = p;
-        key = 2 * L.row_group[r] + ((phase == 0 && D.findex[r] != -1) ? 1 : 0);
-    }
-    const int prev = __shfl_up_sync(0xffffffffu, key, 1);
-    const bool start = lane == 0 || key != prev;
-    const unsigned heads = __ballot_sync(0xffffffffu, start);
-    if (p < mrows) L.head_pos[p] = p - lane + (31 - __clz(heads & (0xffffffffu >> (31 - lane))));
-}
-// tickets: rank of every run among the runs acting on the same body, by position in the sweep order
-__global__ void k_lw_tickets(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L)
-{
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= L.counters[LWC_NORDERED]) return;
-    const int lo = L.inc_ofs[k], hi = L.inc_ofs[k + 1];
-    for (int e = lo; e < hi; e++) {
-        const int pe = L.rpos[L.inc[e] >> 1], hp = L.head_pos[pe];
-        L.inc_pos[e] = 2 * hp + (pe == hp ? 1 : 0);
-    }
-    for (int e = lo; e < hi; e++) {
-        const int ve = L.inc_pos[e];
-        if (!(ve & 1)) continue;
-        int rank = 0;
-        for (int f = lo; f < hi; f++) { const int vf = L.inc_pos[f]; rank += ((vf & 1) && vf < ve) ? 1 : 0; }
-        int *t = (int *)&L.ticket[ve >> 1];
-        t[L.inc[e] & 1] = rank;
-    }
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= L.counters[LWC_NGROUPS]) return;
+    const int g = L.heads[t];
+    const int2 rb = D.rbody[g];
+    L.ginc[L.ginc_ofs[rb.x] + atomicAdd(&L.ginc_cur[rb.x], 1)] = g;
+    if (rb.y != P.NB) L.ginc[L.ginc_ofs[rb.y] + atomicAdd(&L.ginc_cur[rb.y], 1)] = g;
 }
 
-// ------------------------------------------------------------------------------------------------ solve: sweep
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p)
+// Colouring of one phase (see oracle/orc_world.cpp canonical_order: the same rounds).  A group is "above" another one when its
+// (key, first row) is larger.  Round = k_lwc_mark (every uncoloured group that has no uncoloured neighbour above it wins; reads only
+// colours of earlier rounds) + k_lwc_assign (winners, never neighbours of each other, take the smallest colour none of their coloured
+// neighbours holds): the result does not depend on thread timing.
+__global__ void k_lwc_color_init(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L, int phase)
 {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < 64) L.ccount[t] = 0;
+    if (t >= L.counters[LWC_NGROUPS]) return;
+    const int g = L.heads[t];
+    const unsigned is = (unsigned)L.row_island[g];
+    if (L.isl_done[is]) { L.gcolor[g] = -2; return; }
+    L.gkey[g] = odebi_canon_key(D.seed[0], is, (unsigned)phase, (unsigned)(g - L.isl_rstart[is]));
+    L.gcolor[g] = -1;
+    atomicAdd(&L.counters[LWC_UNCOLORED], 1);
 }
-__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p)
+__global__ void k_lwc_mark(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L)
 {
-    unsigned v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= L.counters[LWC_NGROUPS]) return;
+    const int g = L.heads[t];
+    if (L.gcolor[g] != -1) { L.gwin[g] = 0; return; }
+    const unsigned kg = L.gkey[g];
+    const int2 rb = D.rbody[g];
+    bool top = true;
+    for (int side = 0; side < 2 && top; side++) {
+        const int b = side ? rb.y : rb.x;
+        if (b == P.NB) continue;
+        for (int e = L.ginc_ofs[b], e1 = L.ginc_ofs[b + 1]; e < e1; e++) {
+            const int h = L.ginc[e];
+            if (h == g || L.gcolor[h] != -1) continue;
+            const unsigned kh = L.gkey[h];
+            if (kh > kg || (kh == kg && h > g)) { top = false; break; }
+        }
+    }
+    L.gwin[g] = top ? 1 : 0;
 }
-__device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v)
+__global__ void k_lwc_assign(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L)
 {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= L.counters[LWC_NGROUPS]) return;
+    const int g = L.heads[t];
+    if (!L.gwin[g]) return;
+    const int2 rb = D.rbody[g];
+    unsigned long long used = 0;
+    for (int side = 0; side < 2; side++) {
+        const int b = side ? rb.y : rb.x;
+        if (b == P.NB) continue;
+        for (int e = L.ginc_ofs[b], e1 = L.ginc_ofs[b + 1]; e < e1; e++) {
+            const int c = L.gcolor[L.ginc[e]];                 // winners of this round are never neighbours: every neighbour's colour is final or -1
+            if (c >= 0 && c < 64) used |= 1ull << c;
+        }
+    }
+    int c = 0;
+    while (c < 63 && ((used >> c) & 1ull)) c++;
+    if (c >= 63) atomicExch(D.overflow, 4);                    // a body with more than 62 groups: beyond the colour mask
+    L.gcolor[g] = c;
+    atomicSub(&L.counters[LWC_UNCOLORED], 1);
+    atomicMax(&L.counters[LWC_NCOLORS], c + 1);
+    atomicAdd(&L.ccount[c], 1);
 }
-__device__ __forceinline__ void st_relaxed_u32(unsigned *p, unsigned v)
+// groups by colour: list offsets (one thread), then the lists (order inside a colour is irrelevant: disjoint bodies)
+__global__ void k_lwc_color_scan(const __grid_constant__ LargePtrs L)
 {
-    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    int o = 0;
+    for (int c = 0; c < 64; c++) { L.cofs[c] = o; o += L.ccount[c]; L.ccount[c] = 0; }
+    L.cofs[64] = o;
 }
+__global__ void k_lwc_color_fill(const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= L.counters[LWC_NGROUPS]) return;
+    const int g = L.heads[t];
+    const int c = L.gcolor[g];
+    if (c < 0) return;
+    const int pos = L.cofs[c] + atomicAdd(&L.ccount[c], 1);
+    L.clist[pos] = g;
+    const int2 rb = D.rbody[g];
+    L.cinfo[pos] = make_int4(g, L.gsize[g], rb.x, rb.y);
+}
+
 __device__ __forceinline__ Real4 ldcg4(const Real4 *p)
 {
 #if defined(ODEB_DOUBLE)
@@ -424,6 +442,13 @@ __device__ __forceinline__ Real4 ldcg4(const Real4 *p)
 #endif
     return r;
 }
+__device__ __forceinline__ Real4 shfl_up4(const Real4 &v)
+{
+    Real4 r;
+    r.x = __shfl_up_sync(0xffffffffu, v.x, 1); r.y = __shfl_up_sync(0xffffffffu, v.y, 1);
+    r.z = __shfl_up_sync(0xffffffffu, v.z, 1); r.w = __shfl_up_sync(0xffffffffu, v.w, 1);
+    return r;
+}
 __device__ __forceinline__ void stcg4(Real4 *p, const Real4 &v)
 {
 #if defined(ODEB_DOUBLE)
@@ -433,157 +458,409 @@ __device__ __forceinline__ void stcg4(Real4 *p, const Real4 &v)
 #endif
 }
 
-__device__ __forceinline__ Real4 shfl_up4(const Real4 &v)
+// Chunks: the groups of a colour are packed into chunks of 32 row slots (a group never straddles two chunks), so that a warp can give
+// every row of a chunk its own lane.  One warp packs 32 consecutive groups of the colour's list greedily and reserves its chunks with one
+// atomic on the global chunk cursor; the colours are packed one launch after the other, so the chunks of a colour are consecutive from
+// cstart[colour] (k_lwc_chunk_start).  Next-fit leaves every chunk but a warp's last more than half full: 3 MR slots always suffice.
+// Which group lands in which chunk depends on the list order (atomics), which is irrelevant: groups of a colour touch disjoint bodies.
+__global__ void k_lwc_chunk_start(const __grid_constant__ LargePtrs L, int colour) { L.cstart[colour] = L.counters[LWC_CHUNKS]; }
+__global__ void __launch_bounds__(256) k_lwc_chunks(const __grid_constant__ LargePtrs L, int colour)
 {
-    Real4 r;
-    r.x = __shfl_up_sync(0xffffffffu, v.x, 1); r.y = __shfl_up_sync(0xffffffffu, v.y, 1);
-    r.z = __shfl_up_sync(0xffffffffu, v.z, 1); r.w = __shfl_up_sync(0xffffffffu, v.w, 1);
-    return r;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    const int lo = L.cofs[colour], n = L.cofs[colour + 1] - lo;
+    if ((t & ~31) >= n) return;
+    const int g = t < n ? L.clist[lo + t] : -1;
+    const int sz = g >= 0 ? L.gsize[g] : 0;
+    if (sz > 32) atomicAdd(&L.counters[LWC_BIGGROUPS], 1);
+    int chunk = 0, fill = 0, my_chunk = 0, my_start = 0;
+    for (int k = 0; k < 32; k++) {                                 // every lane replays the same greedy packing
+        const int sk = __shfl_sync(0xffffffffu, sz, k);
+        if (sk == 0 || sk > 32) continue;
+        if (fill + sk > 32) { chunk++; fill = 0; }
+        if (k == lane) { my_chunk = chunk; my_start = fill; }
+        fill += sk;
+    }
+    const int used = chunk + (fill > 0 ? 1 : 0);
+    int base = 0;
+    if (lane == 0 && used > 0) base = atomicAdd(&L.counters[LWC_CHUNKS], used);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (g >= 0 && sz <= 32) {
+        int *slot = L.slot_row + ((size_t)(base + my_chunk) * 32 + my_start);
+        for (int i = 0; i < sz; i++) slot[i] = (g + i) | (i == 0 ? 0x40000000 : 0) | (i == sz - 1 ? (int)0x80000000u : 0);   // bit 30: first, bit 31: last row of its group
+    }
 }
 
-#ifndef ODEB_LW_BLOCKS
-#define ODEB_LW_BLOCKS 3             // resident blocks per SM (80 registers): 27.6 ms per step on the 100k-box wall, 2 -> 30.6, 4 (spills) -> 43.2
-#endif
-// One sweep over all rows of all unfinished islands, in the phase's order. Warps claim consecutive chunks of 32 positions
-// through one cursor, so every claimed position only ever waits for positions that are already claimed by a running warp
-// (or finished): the walk cannot deadlock whatever the grid size. Inside a chunk a lane owns one row (its record is in
-// registers before any waiting starts). The head lane of a run polls the two bodies' counters; when both have reached
-// the run's tickets it loads the bodies' accumulators, and the run then executes in lockstep, one row per step, the
-// accumulators travelling from lane to lane by shuffle; the tail lane writes them back and bumps the counters.
-// Arithmetic = Stage4LCP_IterationStep quickstep.cpp:2917-3033.
-__global__ void __launch_bounds__(256, ODEB_LW_BLOCKS) k_lw_sweep(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L, int mrows)
+// One colour of one sweep, lane per row: a warp takes one chunk, every lane loads its row's record (all rows of a colour are in flight
+// at once: the sweep streams the rows from HBM at bandwidth instead of one dependent row after the other per thread); the rows of a group
+// then execute in order, one per step, the two bodies' accumulators travelling from lane to lane by shuffle and a contact's normal-row
+// lambda forwarded to its friction rows; the last row of the group writes the accumulators back.
+__global__ void __launch_bounds__(128) k_lwc_sweep_rows(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L, int colour)
 {
-    if (L.counters[LWC_NACTIVE] == 0) return;
-    const int lane = threadIdx.x & 31;
-    const int nchunks = (mrows + 31) >> 5;
+    const int chunk = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    const int first = L.cstart[colour];
+    if (chunk >= L.cstart[colour + 1] - first) return;
+    const int slot = L.slot_row[(size_t)(first + chunk) * 32 + lane];
+    const bool any = slot != -1;
+    const int r = any ? (slot & 0x3fffffff) : 0;
+    const bool head = any && (slot & 0x40000000), tail = any && (slot < 0);
     Real4 *cf = D.cforce;
     Real *lam = D.lambda;
-#ifndef ODEB_LW_CLAIM
-#define ODEB_LW_CLAIM 1             // chunks claimed per cursor atomic. Must stay 1: a warp that holds chunks it is not yet working on makes
-                                   // every later position wait for it (measured: 4 -> 9.8 s per step instead of 38 ms)
+    // The 32 row records of the chunk (128 B each, scattered group by group) are fetched COALESCED: in each of 8 passes the warp reads
+    // 4 whole records (8 lanes x 16 B per record) and parks them in shared memory with a padded row stride, then every lane reads its own
+    // record from there (both sides free of bank conflicts: stride = 9 x 16 B).  A lane loading its own record directly touches 32
+    // different lines per instruction: measured 42-50 us per colour instead of ~10.
+    constexpr int RS = (int)sizeof(Real4) * 9;                                  // padded record stride in shared memory (bytes)
+    extern __shared__ __align__(16) unsigned char lwc_smem[];
+    unsigned char *wbuf = lwc_smem + (size_t)(threadIdx.x >> 5) * 32 * RS;
+    {
+        Real4 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int rs = 4 * k + (lane >> 3);
+            const int rr = __shfl_sync(0xffffffffu, r, rs);
+            v[k] = ldcg4(D.rows + (size_t)rr * 8 + (lane & 7));
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) *(Real4 *)(wbuf + (size_t)(4 * k + (lane >> 3)) * RS + (lane & 7) * sizeof(Real4)) = v[k];
+    }
+    __syncwarp();
+    const Real4 *rec = (const Real4 *)(wbuf + (size_t)lane * RS);
+    const Real4 a0 = rec[0], a1 = rec[1], a2 = rec[2], a3 = rec[3], b0 = rec[4], b1q = rec[5], b2q = rec[6], b3 = rec[7];
+    const int2 rb = any ? D.rbody[r] : make_int2(0, P.NB);
+    const int fi = any ? D.findex[r] : -1;
+    const Real old_lambda = any ? lam[r] : R_(0.0);
+    const int isl = any ? L.row_island[r] : 0;
+    const bool two = rb.y != P.NB;
+    Real4 f1a = { 0, 0, 0, 0 }, f1b = f1a, f2a = f1a, f2b = f1a;
+    if (head) {
+        f1a = ldcg4(&cf[2 * rb.x]); f1b = ldcg4(&cf[2 * rb.x + 1]);
+        if (two) { f2a = ldcg4(&cf[2 * rb.y]); f2b = ldcg4(&cf[2 * rb.y + 1]); }
+    }
+    const bool live = any && !L.isl_done[isl];
+    const unsigned heads = __ballot_sync(0xffffffffu, head);
+    const int headlane = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));       // first lane of this lane's run
+    // the friction-index row is an earlier row of the same group, i.e. an earlier lane of the same run: its new lambda is forwarded
+    const int fwd_src = (live && fi != -1) ? lane - (r - fi) : lane;
+    const bool fwd = live && fi != -1 && fwd_src >= headlane && fwd_src < lane;
+    Real my_lambda = 0;
+    bool have = live && head;
+    for (;;) {
+        const bool exec = have;
+        const Real lam_fw = __shfl_sync(0xffffffffu, my_lambda, fwd ? fwd_src : lane);
+        if (exec) {
+            Real delta = a1.z - old_lambda * a1.w;
+            delta -= f1a.x * a0.x + f1a.y * a0.y + f1a.z * a0.z + f1a.w * a0.w + f1b.x * a1.x + f1b.y * a1.y;
+            if (two) delta -= f2a.x * b0.x + f2a.y * b0.y + f2a.z * b0.z + f2a.w * b0.w + f2b.x * b1q.x + f2b.y * b1q.y;
+            Real hi_act, lo_act;
+            if (fi != -1) { hi_act = RFABS(b1q.w * (fwd ? lam_fw : lam[fi])); lo_act = -hi_act; }
+            else { hi_act = b1q.w; lo_act = b1q.z; }
+            Real new_lambda = old_lambda + delta;
+            if (new_lambda < lo_act) { delta = lo_act - old_lambda; new_lambda = lo_act; }
+            else if (new_lambda > hi_act) { delta = hi_act - old_lambda; new_lambda = hi_act; }
+            lam[r] = new_lambda;
+            my_lambda = new_lambda;
+            if (delta != 0) {
+                f1a.x += delta * a2.x; f1a.y += delta * a2.y; f1a.z += delta * a2.z; f1a.w += delta * a2.w;
+                f1b.x += delta * a3.x; f1b.y += delta * a3.y;
+                if (delta > 0) f1b.w += delta * a3.z; else f1b.z += delta * a3.z;
+                if (two) {
+                    if (delta > 0) f2b.w += delta * b3.z; else f2b.z += delta * b3.z;
+                    f2a.x += delta * b2q.x; f2a.y += delta * b2q.y; f2a.z += delta * b2q.z; f2a.w += delta * b2q.w;
+                    f2b.x += delta * b3.x; f2b.y += delta * b3.y;
+                }
+            }
+            if (tail) {
+                stcg4(&cf[2 * rb.x], f1a); stcg4(&cf[2 * rb.x + 1], f1b);
+                if (two) { stcg4(&cf[2 * rb.y], f2a); stcg4(&cf[2 * rb.y + 1], f2b); }
+            }
+        }
+        const unsigned pass = __ballot_sync(0xffffffffu, exec && !tail);
+        if (pass == 0) break;
+        const Real4 n1a = shfl_up4(f1a), n1b = shfl_up4(f1b), n2a = shfl_up4(f2a), n2b = shfl_up4(f2b);
+        have = lane > 0 && ((pass >> (lane - 1)) & 1u);
+        if (have) { f1a = n1a; f1b = n1b; f2a = n2a; f2b = n2b; }
+    }
+}
+
+// One colour of one sweep, thread per group with the records staged through shared memory.  ncu on the two simpler kernels says why:
+// a thread that walks its group's rows straight from HBM pays one memory latency per row (34 us per colour, 25 k threads in flight);
+// a lane per row fetches everything at once but then passes the accumulators from lane to lane, 12 steps of ~130 instructions with a
+// third of the lanes busy (issue-bound, 36 M warp instructions per colour, 36-50 us).  Here a warp takes 32 consecutive groups of the
+// colour, fetches ALL their records coalesced (8 lanes x 16 B per record, 4 records per instruction, every request in flight at once)
+// into shared memory with a padded record stride, and then every lane relaxes its own group from shared memory: full lanes, one
+// exposed memory latency per warp.  Groups whose records do not fit the warp's buffer (LWC_ROWS_PER_WARP) are relaxed straight from HBM.
+#if defined(ODEB_DOUBLE)
+#define LWC_ROWS_PER_WARP 160
+#else
+#define LWC_ROWS_PER_WARP 288
 #endif
-    for (int sub = ODEB_LW_CLAIM, base = 0;; sub++) {
-        if (sub == ODEB_LW_CLAIM) {
-            if (lane == 0) base = atomicAdd(&L.counters[LWC_CURSOR], ODEB_LW_CLAIM);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            sub = 0;
-        }
-        const int chunk = base + sub;
-        if (chunk >= nchunks) break;
-        const int p = chunk * 32 + lane;
-        bool pending = p < mrows;
-        int r = 0, fi = -1; int2 rb = make_int2(0, 0), tk = make_int2(0, 0);
-        bool head = false, tail = false;
-        int hl = lane;                           // lane of the head of this lane's run
-        Real old_lambda = 0;
-        Real4 a0, a1, a2, a3, b0, b1q, b2q, b3;
-        if (pending) {
-            r = L.ord[p];
-            if (L.isl_done[L.row_island[r]]) pending = false;
-        }
-        if (pending) {
-            const Real4 *rec = D.rows + (size_t)r * 8;
-            a0 = rec[0]; a1 = rec[1]; a2 = rec[2]; a3 = rec[3]; b0 = rec[4]; b1q = rec[5]; b2q = rec[6]; b3 = rec[7];
-            rb = D.rbody[r]; fi = D.findex[r];
-            hl = L.head_pos[p] - chunk * 32;                       // runs never cross a chunk (k_lw_runs)
-            head = hl == lane;
-            tail = (p + 1 >= mrows) || (L.head_pos[p + 1] == p + 1);
-            if (head) tk = L.ticket[p];
-            old_lambda = lam[r];            // each row is updated once per sweep: its own lambda cannot change under it
-        }
-        const bool two = rb.y != P.NB;
-        Real4 f1a = { 0, 0, 0, 0 }, f1b = f1a, f2a = f1a, f2b = f1a;
-        unsigned backoff = 0;
-        // lambda of the friction-index row (the contact's normal row). When that row sits earlier in the same run its new value
-        // is forwarded from the lane that computes it (fwd_src) instead of going through L2 once per friction row; otherwise
-        // the row ran in an earlier run on the same two bodies (or runs later in the sweep), so its value is final for this
-        // lane as soon as the run's tickets are up and is fetched together with the accumulators.
-        int fwd_src = lane; bool fwd = false;
-        {
-            const int src = lane - (r - fi);
-            const int r_src = __shfl_sync(0xffffffffu, r, (src >= 0 && src < 32) ? src : lane);
-            if (pending && fi != -1 && src >= hl && src < lane && r_src == fi) { fwd = true; fwd_src = src; }
-        }
-        Real lam_fi_val = 0, my_lambda = 0;
-        while (__any_sync(0xffffffffu, pending)) {
-            bool have = false;
-            if (pending && head) {
-                bool ok = ld_acquire_u32(&L.cnt[rb.x]) == (unsigned)tk.x;
-                if (ok && two) ok = ld_acquire_u32(&L.cnt[rb.y]) == (unsigned)tk.y;
-                if (ok) {
-                    f1a = ldcg4(&cf[2 * rb.x]); f1b = ldcg4(&cf[2 * rb.x + 1]);
-                    if (two) { f2a = ldcg4(&cf[2 * rb.y]); f2b = ldcg4(&cf[2 * rb.y + 1]); }
-                    have = true;
-                }
-            }
-#ifndef ODEB_LW_BACKOFF_MAX
-#define ODEB_LW_BACKOFF_MAX 128
-#endif
-            {
-                const unsigned started = __ballot_sync(0xffffffffu, have);
-                if (pending && fi != -1 && !fwd && ((started >> hl) & 1u)) lam_fi_val = __ldcg(&lam[fi]);
-            }
-            if (!__any_sync(0xffffffffu, have)) {
-                if (ODEB_LW_BACKOFF_MAX > 0) { backoff = backoff < ODEB_LW_BACKOFF_MAX ? backoff + 16 : ODEB_LW_BACKOFF_MAX; __nanosleep(backoff); }
-                continue;
-            }
-            backoff = 0;
-            for (;;) {
-                const bool exec = have;
-                const Real lam_fw = __shfl_sync(0xffffffffu, my_lambda, fwd_src);
-                if (exec) {
-                    Real delta = a1.z - old_lambda * a1.w;
-                    delta -= f1a.x * a0.x + f1a.y * a0.y + f1a.z * a0.z + f1a.w * a0.w + f1b.x * a1.x + f1b.y * a1.y;
-                    if (two) delta -= f2a.x * b0.x + f2a.y * b0.y + f2a.z * b0.z + f2a.w * b0.w + f2b.x * b1q.x + f2b.y * b1q.y;
-                    Real hi_act, lo_act;
-                    if (fi != -1) { hi_act = RFABS(b1q.w * (fwd ? lam_fw : lam_fi_val)); lo_act = -hi_act; }
-                    else { hi_act = b1q.w; lo_act = b1q.z; }
-                    Real new_lambda = old_lambda + delta;
-                    if (new_lambda < lo_act) { delta = lo_act - old_lambda; new_lambda = lo_act; }
-                    else if (new_lambda > hi_act) { delta = hi_act - old_lambda; new_lambda = hi_act; }
-                    __stcg(&lam[r], new_lambda);
-                    my_lambda = new_lambda;
-                    if (delta != 0) {
-                        f1a.x += delta * a2.x; f1a.y += delta * a2.y; f1a.z += delta * a2.z; f1a.w += delta * a2.w;
-                        f1b.x += delta * a3.x; f1b.y += delta * a3.y;
-                        if (delta > 0) f1b.w += delta * a3.z; else f1b.z += delta * a3.z;
-                        if (two) {
-                            if (delta > 0) f2b.w += delta * b3.z; else f2b.z += delta * b3.z;
-                            f2a.x += delta * b2q.x; f2a.y += delta * b2q.y; f2a.z += delta * b2q.z; f2a.w += delta * b2q.w;
-                            f2b.x += delta * b3.x; f2b.y += delta * b3.y;
-                        }
-                    }
-                    if (tail) {
-                        stcg4(&cf[2 * rb.x], f1a); stcg4(&cf[2 * rb.x + 1], f1b);
-                        if (two) { stcg4(&cf[2 * rb.y], f2a); stcg4(&cf[2 * rb.y + 1], f2b); }
-                    }
-                    pending = false;
-                }
-                __syncwarp();           // lambda written by an earlier row of the run is visible to the later rows (friction index)
-                const unsigned pass = __ballot_sync(0xffffffffu, exec && !tail);
-                // the run's tickets travel with the accumulators: the tail needs them for the release
-                const Real4 n1a = shfl_up4(f1a), n1b = shfl_up4(f1b), n2a = shfl_up4(f2a), n2b = shfl_up4(f2b);
-                const int ntx = __shfl_up_sync(0xffffffffu, tk.x, 1), nty = __shfl_up_sync(0xffffffffu, tk.y, 1);
-                if (exec && tail) {             // one fence for the run's stores, then both counters
-                    asm volatile("fence.acq_rel.gpu;" ::: "memory");        // (not __threadfence(): that is the sequentially consistent fence)
-                    st_relaxed_u32(&L.cnt[rb.x], (unsigned)tk.x + 1u);
-                    if (two) st_relaxed_u32(&L.cnt[rb.y], (unsigned)tk.y + 1u);
-                }
-                have = lane > 0 && ((pass >> (lane - 1)) & 1u);
-                if (have) { f1a = n1a; f1b = n1b; f2a = n2a; f2b = n2b; tk.x = ntx; tk.y = nty; }
-                if (pass == 0) break;
+#define LWC_WARPS 4
+__global__ void __launch_bounds__(32 * LWC_WARPS) k_lwc_sweep_staged(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L, int colour)
+{
+    constexpr int RS = (int)sizeof(Real4) * 9;                                  // padded record stride (bytes): conflict-free on both sides
+    extern __shared__ __align__(16) unsigned char lwc_smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    unsigned char *wbuf = lwc_smem + (size_t)wib * (LWC_ROWS_PER_WARP * RS + LWC_ROWS_PER_WARP * sizeof(int));
+    int *srow = (int *)(wbuf + (size_t)LWC_ROWS_PER_WARP * RS);
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lo = L.cofs[colour], n = L.cofs[colour + 1] - lo;
+    if ((t & ~31) >= n) return;
+    const int g = t < n ? L.clist[lo + t] : -1;
+    const int sz = g >= 0 ? L.gsize[g] : 0;
+    // slots of the warp's buffer: exclusive prefix of the group sizes; groups beyond the buffer stay in HBM
+    int ofs = sz;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, ofs, d); if (lane >= d) ofs += u; }
+    const int total = __shfl_sync(0xffffffffu, ofs, 31);
+    ofs -= sz;
+    const bool staged = g >= 0 && ofs + sz <= LWC_ROWS_PER_WARP;
+    const int nst = total < LWC_ROWS_PER_WARP ? total : LWC_ROWS_PER_WARP;
+    if (staged) for (int i = 0; i < sz; i++) srow[ofs + i] = g + i;
+    else if (g >= 0) for (int i = 0; ofs + i < LWC_ROWS_PER_WARP && i < sz; i++) srow[ofs + i] = g + i;      // a straddling group: harmless filler
+    __syncwarp();
+    for (int s0 = 0; s0 < nst; s0 += 16) {                        // 4 passes of 4 records per trip: 4 requests in flight per lane
+        Real4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const int s = s0 + 4 * k + (lane >> 3); if (s < nst) v[k] = ldcg4(D.rows + (size_t)srow[s] * 8 + (lane & 7)); }
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const int s = s0 + 4 * k + (lane >> 3); if (s < nst) *(Real4 *)(wbuf + (size_t)s * RS + (lane & 7) * sizeof(Real4)) = v[k]; }
+    }
+    if (g < 0) return;                                            // (no warp-level primitive below)
+    const bool skip = L.isl_done[L.row_island[g]] != 0;
+    const int2 rb = D.rbody[g];
+    const bool two = rb.y != P.NB;
+    Real4 *cf = D.cforce;
+    Real *lam = D.lambda;
+    Real4 f1a = ldcg4(&cf[2 * rb.x]), f1b = ldcg4(&cf[2 * rb.x + 1]);
+    Real4 f2a = { 0, 0, 0, 0 }, f2b = f2a;
+    if (two) { f2a = ldcg4(&cf[2 * rb.y]); f2b = ldcg4(&cf[2 * rb.y + 1]); }
+    __syncwarp();                                                 // the records are in shared memory
+    if (skip) return;
+    int free_row = -1; Real free_lambda = 0;                      // the latest row of the group without a friction index and its new lambda
+    for (int k = 0; k < sz; k++) {
+        const int r = g + k;
+        const Real4 *rec = staged ? (const Real4 *)(wbuf + (size_t)(ofs + k) * RS) : D.rows + (size_t)r * 8;
+        const Real4 a0 = rec[0], a1 = rec[1], a2 = rec[2], a3 = rec[3], b0 = rec[4], b1q = rec[5], b2q = rec[6], b3 = rec[7];
+        const Real old_lambda = lam[r];
+        const int fi = D.findex[r];
+        Real delta = a1.z - old_lambda * a1.w;
+        delta -= f1a.x * a0.x + f1a.y * a0.y + f1a.z * a0.z + f1a.w * a0.w + f1b.x * a1.x + f1b.y * a1.y;
+        if (two) delta -= f2a.x * b0.x + f2a.y * b0.y + f2a.z * b0.z + f2a.w * b0.w + f2b.x * b1q.x + f2b.y * b1q.y;
+        Real hi_act, lo_act;
+        if (fi != -1) { hi_act = RFABS(b1q.w * (fi == free_row ? free_lambda : lam[fi])); lo_act = -hi_act; }
+        else { hi_act = b1q.w; lo_act = b1q.z; }
+        Real new_lambda = old_lambda + delta;
+        if (new_lambda < lo_act) { delta = lo_act - old_lambda; new_lambda = lo_act; }
+        else if (new_lambda > hi_act) { delta = hi_act - old_lambda; new_lambda = hi_act; }
+        lam[r] = new_lambda;
+        if (fi == -1) { free_row = r; free_lambda = new_lambda; }
+        if (delta != 0) {
+            f1a.x += delta * a2.x; f1a.y += delta * a2.y; f1a.z += delta * a2.z; f1a.w += delta * a2.w;
+            f1b.x += delta * a3.x; f1b.y += delta * a3.y;
+            if (delta > 0) f1b.w += delta * a3.z; else f1b.z += delta * a3.z;
+            if (two) {
+                if (delta > 0) f2b.w += delta * b3.z; else f2b.z += delta * b3.z;
+                f2a.x += delta * b2q.x; f2a.y += delta * b2q.y; f2a.z += delta * b2q.z; f2a.w += delta * b2q.w;
+                f2b.x += delta * b3.x; f2b.y += delta * b3.y;
             }
         }
     }
+    stcg4(&cf[2 * rb.x], f1a); stcg4(&cf[2 * rb.x + 1], f1b);
+    if (two) { stcg4(&cf[2 * rb.y], f2a); stcg4(&cf[2 * rb.y + 1], f2b); }
+}
+
+// One colour of one sweep, thread per group, the records brought in by TMA bulk copies.  The records of a group are one contiguous
+// block of HBM (gsize x 32 reals), so every lane issues ONE cp.async.bulk for its whole group into the warp's shared-memory pool,
+// all of them complete on the warp's mbarrier (lane 0 armed it with the byte count), and after one wait every lane relaxes its own
+// group from shared memory.  All records of the colour are in flight at once and no register or LSU instruction is spent per 16 bytes:
+// what made the thread-per-group kernel slow was one DRAM latency per row (ncu: stall_long_sb 86 %, issue active 7 %), what made the
+// lane-per-row kernel slow was passing accumulators between lanes (issue-bound).  Group j of the warp starts at row offset ofs_j in
+// the pool, shifted by j x 16 bytes: the eight lanes of a shared-memory phase then read eight different bank groups (records are 8 or
+// 16 x 16 bytes).  Groups that do not fit the pool read their records from HBM.
+__device__ __forceinline__ void lwc_mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void lwc_mbar_expect_tx(unsigned bar, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void lwc_bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ bool lwc_mbar_try_wait(unsigned bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+#define LWC_TMA_WARPS 2
+#define LWC_AUX_ROWS 24                                     // rows per group whose lambda / findex ranges fit the per-lane slots
+#define LWC_AUX_BYTES ((LWC_AUX_ROWS + 8) * (int)sizeof(Real))
+__global__ void __launch_bounds__(32 * LWC_TMA_WARPS) k_lwc_sweep_tma(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L, int colour)
+{
+    constexpr int REC = (int)sizeof(Real4) * 8;                                 // bytes of a record
+    constexpr int POOL = LWC_ROWS_PER_WARP * REC + 32 * 16 + 32 * 2 * LWC_AUX_BYTES;   // pool of a warp: records + the per-group 16-byte shifts + lambda / findex ranges
+    extern __shared__ __align__(128) unsigned char lwc_smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    unsigned char *pool = lwc_smem + (size_t)wib * POOL;
+    unsigned char *aux = pool + LWC_ROWS_PER_WARP * REC + 32 * 16;
+    unsigned long long *bars = (unsigned long long *)(lwc_smem + (size_t)LWC_TMA_WARPS * POOL);
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(bars + wib);
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lo = L.cofs[colour], n = L.cofs[colour + 1] - lo;
+    if ((t & ~31) >= n) return;
+    if (lane == 0) lwc_mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    const int4 gi = t < n ? L.cinfo[lo + t] : make_int4(-1, 0, 0, P.NB);
+    const int g = gi.x, sz = gi.y;
+    int ofs = sz;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, ofs, d); if (lane >= d) ofs += u; }
+    ofs -= sz;
+    const bool staged = g >= 0 && ofs + sz <= LWC_ROWS_PER_WARP && sz <= LWC_AUX_ROWS;
+    // lambda and the friction indices of the group's rows come along as two more bulk copies (the 16-byte aligned ranges that hold them):
+    // a load of lambda inside the row loop would put one memory latency on every row
+    const int a0i = g & ~3, a1i = (g + sz + 3) & ~3;              // aligned element range [a0i, a1i) of both arrays
+    const unsigned abytes = staged ? (unsigned)(a1i - a0i) * 4u : 0u;
+    const unsigned bytes = staged ? (unsigned)sz * REC : 0u;
+    const unsigned lbytes = staged ? (unsigned)(a1i - a0i) * (unsigned)sizeof(Real) : 0u;
+    const unsigned total = __reduce_add_sync(0xffffffffu, bytes + lbytes + abytes);
+    unsigned char *mine = pool + (size_t)ofs * REC + lane * 16;
+    unsigned char *auxl = aux + (size_t)lane * (2 * LWC_AUX_BYTES);          // [lambda range | findex range] of this lane's group
+    if (lane == 0) lwc_mbar_expect_tx(bar, total);
+    __syncwarp();
+    if (staged) {
+        lwc_bulk_g2s((unsigned)__cvta_generic_to_shared(mine), D.rows + (size_t)g * 8, bytes, bar);
+        lwc_bulk_g2s((unsigned)__cvta_generic_to_shared(auxl), D.lambda + a0i, lbytes, bar);
+        lwc_bulk_g2s((unsigned)__cvta_generic_to_shared(auxl + LWC_AUX_BYTES), D.findex + a0i, abytes, bar);
+    }
+    // what does not come through the pool is requested meanwhile
+    bool skip = true;
+    const int2 rb = make_int2(gi.z, gi.w);
+    Real4 f1a = { 0, 0, 0, 0 }, f1b = f1a, f2a = f1a, f2b = f1a;
+    Real4 *cf = D.cforce;
+    Real *lam = D.lambda;
+    if (g >= 0) {
+        f1a = ldcg4(&cf[2 * rb.x]); f1b = ldcg4(&cf[2 * rb.x + 1]);
+        if (rb.y != P.NB) { f2a = ldcg4(&cf[2 * rb.y]); f2b = ldcg4(&cf[2 * rb.y + 1]); }
+        skip = L.isl_done[L.row_island[g]] != 0;
+    }
+    const bool two = rb.y != P.NB;
+    const Real *slam = (const Real *)auxl + (g - a0i);
+    const int *sfi = (const int *)(auxl + LWC_AUX_BYTES) + (g - a0i);
+    while (!lwc_mbar_try_wait(bar, 0)) { }
+    if (skip) return;
+    int free_row = -1; Real free_lambda = 0;                      // the latest row of the group without a friction index and its new lambda
+    for (int k = 0; k < sz; k++) {
+        const int r = g + k;
+        const Real4 *rec = staged ? (const Real4 *)(mine + (size_t)k * REC) : D.rows + (size_t)r * 8;
+        const Real4 a0 = rec[0], a1 = rec[1], a2 = rec[2], a3 = rec[3], b0 = rec[4], b1q = rec[5], b2q = rec[6], b3 = rec[7];
+        const Real old_lambda = staged ? slam[k] : lam[r];
+        const int fi = staged ? sfi[k] : D.findex[r];
+        Real delta = a1.z - old_lambda * a1.w;
+        delta -= f1a.x * a0.x + f1a.y * a0.y + f1a.z * a0.z + f1a.w * a0.w + f1b.x * a1.x + f1b.y * a1.y;
+        if (two) delta -= f2a.x * b0.x + f2a.y * b0.y + f2a.z * b0.z + f2a.w * b0.w + f2b.x * b1q.x + f2b.y * b1q.y;
+        Real hi_act, lo_act;
+        if (fi != -1) { hi_act = RFABS(b1q.w * (fi == free_row ? free_lambda : lam[fi])); lo_act = -hi_act; }
+        else { hi_act = b1q.w; lo_act = b1q.z; }
+        Real new_lambda = old_lambda + delta;
+        if (new_lambda < lo_act) { delta = lo_act - old_lambda; new_lambda = lo_act; }
+        else if (new_lambda > hi_act) { delta = hi_act - old_lambda; new_lambda = hi_act; }
+        lam[r] = new_lambda;
+        if (fi == -1) { free_row = r; free_lambda = new_lambda; }
+        if (delta != 0) {
+            f1a.x += delta * a2.x; f1a.y += delta * a2.y; f1a.z += delta * a2.z; f1a.w += delta * a2.w;
+            f1b.x += delta * a3.x; f1b.y += delta * a3.y;
+            if (delta > 0) f1b.w += delta * a3.z; else f1b.z += delta * a3.z;
+            if (two) {
+                if (delta > 0) f2b.w += delta * b3.z; else f2b.z += delta * b3.z;
+                f2a.x += delta * b2q.x; f2a.y += delta * b2q.y; f2a.z += delta * b2q.z; f2a.w += delta * b2q.w;
+                f2b.x += delta * b3.x; f2b.y += delta * b3.y;
+            }
+        }
+    }
+    stcg4(&cf[2 * rb.x], f1a); stcg4(&cf[2 * rb.x + 1], f1b);
+    if (two) { stcg4(&cf[2 * rb.y], f2a); stcg4(&cf[2 * rb.y + 1], f2b); }
+}
+
+// One colour of one sweep: a thread relaxes the rows of one group in row order, the two bodies' accumulators (and the most recent
+// normal-row lambda, which the contact's friction rows clamp against) in registers; the next row's record is requested while the current
+// one is computed.  No other group of the colour touches these bodies.  Arithmetic = Stage4LCP_IterationStep quickstep.cpp:2917-3033.
+#ifndef LWC_BLK
+#define LWC_BLK 2
+#endif
+__global__ void __launch_bounds__(128) k_lwc_sweep(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L, int colour)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lo = L.cofs[colour];
+    if (t >= L.cofs[colour + 1] - lo) return;
+    const int4 gi = L.cinfo[lo + t];                              // (first row, rows, accumulator slots of the two bodies): one load
+    const int g = gi.x, n = gi.y;
+    const int2 rb = make_int2(gi.z, gi.w);
+    const bool two = rb.y != P.NB;
+    Real4 *cf = D.cforce;
+    Real *lam = D.lambda;
+    // A launch holds only as many threads as the colour has groups (~45 k on the 100k-box wall: 10 warps per SM), so registers are free
+    // and latency is everything: the records are fetched LWC_BLK rows at a time (8 independent 16-byte loads per row in flight, together
+    // with their lambdas and friction indices) -- one exposed memory latency per LWC_BLK rows instead of one per row.
+    const Real4 *rec = D.rows + (size_t)g * 8;
+    Real4 q[LWC_BLK][8]; Real ol[LWC_BLK]; int fx[LWC_BLK];
+#pragma unroll
+    for (int j = 0; j < LWC_BLK; j++) if (j < n) {
+#pragma unroll
+        for (int c = 0; c < 8; c++) q[j][c] = ldcg4(rec + 8 * j + c);
+        ol[j] = lam[g + j]; fx[j] = D.findex[g + j];
+    }
+    Real4 f1a = ldcg4(&cf[2 * rb.x]), f1b = ldcg4(&cf[2 * rb.x + 1]);
+    Real4 f2a = { 0, 0, 0, 0 }, f2b = f2a;
+    if (two) { f2a = ldcg4(&cf[2 * rb.y]); f2b = ldcg4(&cf[2 * rb.y + 1]); }
+    if (L.isl_done[L.row_island[g]]) return;
+    int free_row = -1; Real free_lambda = 0;                   // the latest row of the group without a friction index and its new lambda
+    for (int k0 = 0; k0 < n; k0 += LWC_BLK) {
+#pragma unroll
+        for (int j = 0; j < LWC_BLK; j++) if (k0 + j < n) {
+            const int r = g + k0 + j;
+            const Real4 a0 = q[j][0], a1 = q[j][1], a2 = q[j][2], a3 = q[j][3], b0 = q[j][4], b1q = q[j][5], b2q = q[j][6], b3 = q[j][7];
+            const Real old_lambda = ol[j];
+            const int fi = fx[j];
+            Real delta = a1.z - old_lambda * a1.w;
+            delta -= f1a.x * a0.x + f1a.y * a0.y + f1a.z * a0.z + f1a.w * a0.w + f1b.x * a1.x + f1b.y * a1.y;
+            if (two) delta -= f2a.x * b0.x + f2a.y * b0.y + f2a.z * b0.z + f2a.w * b0.w + f2b.x * b1q.x + f2b.y * b1q.y;
+            Real hi_act, lo_act;
+            if (fi != -1) { hi_act = RFABS(b1q.w * (fi == free_row ? free_lambda : lam[fi])); lo_act = -hi_act; }
+            else { hi_act = b1q.w; lo_act = b1q.z; }
+            Real new_lambda = old_lambda + delta;
+            if (new_lambda < lo_act) { delta = lo_act - old_lambda; new_lambda = lo_act; }
+            else if (new_lambda > hi_act) { delta = hi_act - old_lambda; new_lambda = hi_act; }
+            lam[r] = new_lambda;
+            if (fi == -1) { free_row = r; free_lambda = new_lambda; }
+            if (delta != 0) {
+                f1a.x += delta * a2.x; f1a.y += delta * a2.y; f1a.z += delta * a2.z; f1a.w += delta * a2.w;
+                f1b.x += delta * a3.x; f1b.y += delta * a3.y;
+                if (delta > 0) f1b.w += delta * a3.z; else f1b.z += delta * a3.z;
+                if (two) {
+                    if (delta > 0) f2b.w += delta * b3.z; else f2b.z += delta * b3.z;
+                    f2a.x += delta * b2q.x; f2a.y += delta * b2q.y; f2a.z += delta * b2q.z; f2a.w += delta * b2q.w;
+                    f2b.x += delta * b3.x; f2b.y += delta * b3.y;
+                }
+            }
+        }
+        if (k0 + LWC_BLK < n) {
+            const Real4 *nr = rec + 8 * (size_t)(k0 + LWC_BLK);
+#pragma unroll
+            for (int j = 0; j < LWC_BLK; j++) if (k0 + LWC_BLK + j < n) {
+#pragma unroll
+                for (int c = 0; c < 8; c++) q[j][c] = ldcg4(nr + 8 * j + c);
+                ol[j] = lam[g + k0 + LWC_BLK + j]; fx[j] = D.findex[g + k0 + LWC_BLK + j];
+            }
+        }
+    }
+    stcg4(&cf[2 * rb.x], f1a); stcg4(&cf[2 * rb.x + 1], f1b);
+    if (two) { stcg4(&cf[2 * rb.y], f2a); stcg4(&cf[2 * rb.y + 1], f2b); }
 }
 
 // after a sweep: per-body convergence test + reset (CheckForMaximumToBeLessThanLimitAndResetMaxAdjustments quickstep.cpp:3253-3285)
 __global__ void k_lw_body_check(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L, Real exit_delta, int check)
 {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k == 0) L.counters[LWC_CURSOR] = 0;
     if (k >= L.counters[LWC_NORDERED]) return;
-    L.cnt[k] = 0;
     const int is = D.body_island[D.body_order[k]];
     if (L.isl_done[is] || !check) return;
     Real4 v = D.cforce[2 * k + 1];

@@ -12,7 +12,6 @@ static size_t large_cub_bytes(const DevParams &P)
     cub::DeviceRadixSort::SortKeys(0, b, (u64 *)0, (u64 *)0, P.MP); best = b > best ? b : best;
     cub::DeviceRadixSort::SortPairs(0, b, (u64 *)0, (u64 *)0, (int *)0, (int *)0, P.NB); best = b > best ? b : best;
     cub::DeviceRadixSort::SortPairs(0, b, (u64 *)0, (u64 *)0, (int *)0, (int *)0, P.NJT); best = b > best ? b : best;
-    cub::DeviceRadixSort::SortPairs(0, b, (u64 *)0, (u64 *)0, (int *)0, (int *)0, P.MR); best = b > best ? b : best;
     cub::DeviceScan::ExclusiveSum(0, b, (int *)0, (int *)0, P.MP); best = b > best ? b : best;
     cub::DeviceScan::ExclusiveSum(0, b, (int *)0, (int *)0, P.NJT); best = b > best ? b : best;
     cub::DeviceScan::InclusiveSum(0, b, (int *)0, (int *)0, P.NB + 2); best = b > best ? b : best;
@@ -33,9 +32,11 @@ static int large_prepare(OdebBatch *B)
            && dev_alloc(B, &L.isl_nb, NB + 2) && dev_alloc(B, &L.isl_m, NB + 2) && dev_alloc(B, &L.isl_bstart, NB + 2) && dev_alloc(B, &L.isl_rstart, NB + 2)
            && dev_alloc(B, &L.isl_done, NB + 2) && dev_alloc(B, &L.isl_viol, NB + 2)
            && dev_alloc(B, &L.jkey, NJT) && dev_alloc(B, &L.jkey_s, NJT) && dev_alloc(B, &L.jmv, NJT) && dev_alloc(B, &L.jmv_s, NJT) && dev_alloc(B, &L.jrow, NJT)
-           && dev_alloc(B, &L.row_island, MR) && dev_alloc(B, &L.okey, MR) && dev_alloc(B, &L.okey_s, MR) && dev_alloc(B, &L.oval, MR) && dev_alloc(B, &L.ord, MR)
-           && dev_alloc(B, &L.rpos, MR) && dev_alloc(B, &L.inc_ofs, NB + 2) && dev_alloc(B, &L.inc_cur, NB + 2) && dev_alloc(B, &L.inc, 2 * MR)
-           && dev_alloc(B, &L.inc_pos, 2 * MR) && dev_alloc(B, &L.ticket, MR) && dev_alloc(B, &L.row_group, MR) && dev_alloc(B, &L.head_pos, MR + 1) && dev_alloc(B, &L.cnt, NB + 2);
+           && dev_alloc(B, &L.row_island, MR) && dev_alloc(B, &L.row_group, MR) && dev_alloc(B, &L.gsize, MR) && dev_alloc(B, &L.heads, MR)
+           && dev_alloc(B, &L.ginc_ofs, NB + 2) && dev_alloc(B, &L.ginc_cur, NB + 2) && dev_alloc(B, &L.ginc, 2 * MR)
+           && dev_alloc(B, &L.gkey, MR) && dev_alloc(B, &L.gcolor, MR) && dev_alloc(B, &L.gwin, MR)
+           && dev_alloc(B, &L.clist, MR) && dev_alloc(B, &L.cinfo, MR) && dev_alloc(B, &L.ccount, 64) && dev_alloc(B, &L.cofs, 65)
+           && dev_alloc(B, &L.slot_row, 3 * MR + 4096) && dev_alloc(B, &L.cstart, 66);
     if (!ok) return 0;
     L.tmp_bytes = large_cub_bytes(P);
     { unsigned char *t = 0; if (!dev_alloc(B, &t, L.tmp_bytes)) return 0; L.tmp = t; }
@@ -143,20 +144,29 @@ static int large_step(OdebBatch *B)
     LCK(cudaMemsetAsync(D.cforce, 0, (size_t)(NB + 1) * 2 * sizeof(Real4), s));
     if (mrows > 0) {
         k_rows_finish<<<nblk(mrows, 128), 128, 0, s>>>(P, D);
-        // body -> incident rows (CSR), built once per step; re-ranked by position for every phase
-        k_lw_inc_count<<<nblk(mrows, 256), 256, 0, s>>>(P, D, L, mrows);
-        LCK(cub::DeviceScan::ExclusiveSum(L.tmp, L.tmp_bytes, L.inc_cur, L.inc_ofs, NB + 1, s));
-        k_lw_zero_cur<<<nblk(NB + 1, 256), 256, 0, s>>>(NB + 1, L.inc_cur);
-        k_lw_inc_fill<<<nblk(mrows, 256), 256, 0, s>>>(P, D, L, mrows);
-        B->launches += 5;
+        // groups (rows of one geom pair's contacts / of one joint), their compact list and the body -> groups incidence (CSR): once per step
+        LCK(cudaMemsetAsync(L.gsize, 0, (size_t)mrows * sizeof(int), s));
+        LCK(cudaMemsetAsync(L.counters + LWC_NGROUPS, 0, 3 * sizeof(int), s));
+        k_lwc_groups<<<nblk(mrows, 256), 256, 0, s>>>(P, D, L, mrows);
+        LCK(cub::DeviceScan::ExclusiveSum(L.tmp, L.tmp_bytes, L.ginc_cur, L.ginc_ofs, NB + 1, s));
+        k_lw_zero_cur<<<nblk(NB + 1, 256), 256, 0, s>>>(NB + 1, L.ginc_cur);
+        int ngroups = 0;
+        LCK(cudaMemcpyAsync(&ngroups, L.counters + LWC_NGROUPS, sizeof(int), cudaMemcpyDeviceToHost, s));
+        LCK(cudaStreamSynchronize(s));
+        k_lwc_ginc_fill<<<nblk(ngroups, 256), 256, 0, s>>>(P, D, L);
+        B->launches += 4;
         // ---------------- SOR sweeps
         cudaEvent_t e0 = 0, e1 = 0;
         if (B->timing) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s); }
-        const int key_bits = 33 + bits_for((unsigned)(T > 0 ? T : 1));
-        int sweep_blocks = (mrows + 255) / 256;
-        { int cap = 148 * 8; if (sweep_blocks > cap) sweep_blocks = cap; }
         Real exit_delta = P.premature_delta;
         unsigned iteration = 0, extra = 0;
+        int ncolors = 0, csize[65], cstart[66], biggroups = 0;
+        // ODEB_LW_SWEEP=1|2|3|4 (experiments): thread per group from HBM / lane per row / thread per group, records staged by cooperative loads / by TMA bulk copies (default)
+        const int lw_variant = getenv("ODEB_LW_SWEEP") ? atoi(getenv("ODEB_LW_SWEEP")) : 4;
+        const size_t lw_tma_smem = (size_t)LWC_TMA_WARPS * (LWC_ROWS_PER_WARP * 8 * sizeof(Real4) + 32 * 16 + 32 * 2 * LWC_AUX_BYTES) + LWC_TMA_WARPS * sizeof(unsigned long long);
+        cudaFuncSetAttribute(k_lwc_sweep_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lw_tma_smem);
+        const size_t lw_staged_smem = (size_t)LWC_WARPS * (LWC_ROWS_PER_WARP * 9 * sizeof(Real4) + LWC_ROWS_PER_WARP * sizeof(int));
+        cudaFuncSetAttribute(k_lwc_sweep_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lw_staged_smem);
         for (;;) {
             if ((iteration & 7) == 0) {
                 if (iteration > 0) {
@@ -164,14 +174,53 @@ static int large_step(OdebBatch *B)
                     LCK(cudaStreamSynchronize(s));
                     if (hc[LWC_NACTIVE] == 0) break;
                 }
+                // the phase's colouring: rounds in batches of 8, until no group of an unfinished island is left uncoloured
                 const int phase = (int)(iteration >> 3);
-                k_lw_order_keys<<<nblk(mrows, 256), 256, 0, s>>>(P, D, L, mrows, phase);
-                LCK(cub::DeviceRadixSort::SortPairs(L.tmp, L.tmp_bytes, L.okey, L.okey_s, L.oval, L.ord, mrows, 0, key_bits, s));
-                k_lw_runs<<<nblk(mrows, 256), 256, 0, s>>>(P, D, L, mrows, phase);
-                k_lw_tickets<<<nblk(nordered, 64), 64, 0, s>>>(P, D, L);
-                B->launches += 4;
+                LCK(cudaMemsetAsync(L.counters + LWC_UNCOLORED, 0, 2 * sizeof(int), s));
+                k_lwc_color_init<<<nblk(ngroups > 64 ? ngroups : 64, 256), 256, 0, s>>>(P, D, L, phase);
+                B->launches++;
+                for (int guard = 0; guard < 4096; guard++) {
+                    for (int k = 0; k < 8; k++) {
+                        k_lwc_mark<<<nblk(ngroups, 256), 256, 0, s>>>(P, D, L);
+                        k_lwc_assign<<<nblk(ngroups, 256), 256, 0, s>>>(P, D, L);
+                    }
+                    B->launches += 16;
+                    int left[2] = { 0, 0 };
+                    LCK(cudaMemcpyAsync(left, L.counters + LWC_UNCOLORED, sizeof(left), cudaMemcpyDeviceToHost, s));
+                    LCK(cudaStreamSynchronize(s));
+                    ncolors = left[1];
+                    if (left[0] <= 0) break;
+                }
+                k_lwc_color_scan<<<1, 1, 0, s>>>(L);
+                k_lwc_color_fill<<<nblk(ngroups, 256), 256, 0, s>>>(D, L);
+                LCK(cudaMemcpyAsync(csize, L.cofs, sizeof(csize), cudaMemcpyDeviceToHost, s));
+                LCK(cudaStreamSynchronize(s));
+                B->launches += 2;
+                // 32-row chunks of every colour (lane-per-row sweep, experiments only); groups of more than 32 rows keep the thread-per-group kernel
+                if (lw_variant == 2) {
+                LCK(cudaMemsetAsync(L.slot_row, 0xff, ((size_t)3 * mrows + 4096) * sizeof(int), s));
+                LCK(cudaMemsetAsync(L.counters + LWC_BIGGROUPS, 0, 2 * sizeof(int), s));
+                for (int c = 0; c < ncolors; c++) {
+                    k_lwc_chunk_start<<<1, 1, 0, s>>>(L, c);
+                    const int nc = csize[c + 1] - csize[c];
+                    if (nc > 0) k_lwc_chunks<<<nblk(nc, 256), 256, 0, s>>>(L, c);
+                }
+                k_lwc_chunk_start<<<1, 1, 0, s>>>(L, ncolors);
+                B->launches += 2 * ncolors + 1;
+                LCK(cudaMemcpyAsync(cstart, L.cstart, sizeof(cstart), cudaMemcpyDeviceToHost, s));
+                LCK(cudaMemcpyAsync(&biggroups, L.counters + LWC_BIGGROUPS, sizeof(int), cudaMemcpyDeviceToHost, s));
+                LCK(cudaStreamSynchronize(s));
+                }
             }
-            k_lw_sweep<<<sweep_blocks, 256, 0, s>>>(P, D, L, mrows);
+            for (int c = 0; c < ncolors; c++) {
+                const int nc = csize[c + 1] - csize[c];
+                if (nc <= 0) continue;
+                if (lw_variant == 1) k_lwc_sweep<<<nblk(nc, 128), 128, 0, s>>>(P, D, L, c);
+                else if (lw_variant == 2 && biggroups == 0) k_lwc_sweep_rows<<<nblk((cstart[c + 1] - cstart[c]) * 32, 128), 128, 4 * 32 * 9 * sizeof(Real4), s>>>(P, D, L, c);
+                else if (lw_variant == 3) k_lwc_sweep_staged<<<nblk(nc, 32 * LWC_WARPS), 32 * LWC_WARPS, lw_staged_smem, s>>>(P, D, L, c);
+                else k_lwc_sweep_tma<<<nblk(nc, 32 * LWC_TMA_WARPS), 32 * LWC_TMA_WARPS, lw_tma_smem, s>>>(P, D, L, c);
+                B->launches++;
+            }
             ++iteration;
             int terminate_all = 0, in_extra = 0;
             if (iteration - extra == P.num_iter) {          // quickstep.cpp:1832-1845
@@ -180,7 +229,7 @@ static int large_step(OdebBatch *B)
             }
             k_lw_body_check<<<nblk(nordered, 256), 256, 0, s>>>(P, D, L, exit_delta, (P.dyn_enabled && !terminate_all) ? 1 : 0);
             k_lw_island_ctl<<<nblk(T, 256), 256, 0, s>>>(P, D, L, iteration, terminate_all, in_extra, exit_delta);
-            B->launches += 3;
+            B->launches += 2;
             if (terminate_all) break;
         }
         if (B->timing) { cudaEventRecord(e1, s); B->pending.push_back(std::make_pair(e0, e1)); }

@@ -669,6 +669,64 @@ Real modulo_max6(const Real *v)
     return r;
 }
 
+// Canonical row order of one phase (8 sweeps) of the large-world path, ODEB_MODE_CANONICAL (include/ode_b200.h).
+// Groups that share a body conflict.  Colouring by rounds (Jones-Plassmann with first fit): in every round each still uncoloured
+// group whose (key, first row) is larger than that of all its still uncoloured neighbours takes the smallest colour none of its
+// already coloured neighbours holds; key = odeb_canon_key(seed, island, phase, first row of the group).  Winners of a round are never
+// neighbours, so the result does not depend on any evaluation order (the CUDA path runs the rounds as two kernels, mark and assign).
+// Sweep order = colour ascending, then group (first row) ascending, rows of a group in row order (a contact's normal row right before
+// its friction rows).  Groups of one colour touch disjoint bodies: the CUDA path relaxes them side by side with the same result.
+static void canonical_order(unsigned seed, unsigned island, unsigned phase, unsigned m, int nb, const std::vector<int> &grp,
+                            const std::vector<int> &jb, std::vector<int> &order)
+{
+    std::vector<int> heads;
+    for (unsigned r = 0; r < m; r++) if (grp[r] == (int)r) heads.push_back((int)r);
+    std::vector<std::vector<int> > on_body(nb);
+    for (size_t k = 0; k < heads.size(); k++) for (int side = 0; side < 2; side++) { const int b = jb[2 * heads[k] + side]; if (b >= 0) on_body[b].push_back(heads[k]); }
+    std::vector<unsigned> key(m, 0);
+    std::vector<int> colour(m, -1);
+    for (size_t k = 0; k < heads.size(); k++) key[heads[k]] = odebi_canon_key(seed, island, phase, (unsigned)heads[k]);
+    size_t left = heads.size();
+    while (left > 0) {
+        std::vector<int> winners;
+        for (size_t k = 0; k < heads.size(); k++) {
+            const int g = heads[k];
+            if (colour[g] >= 0) continue;
+            bool top = true;
+            for (int side = 0; side < 2 && top; side++) {
+                const int b = jb[2 * g + side];
+                if (b < 0) continue;
+                for (size_t t = 0; t < on_body[b].size(); t++) {
+                    const int h = on_body[b][t];
+                    if (h != g && colour[h] < 0 && (key[h] > key[g] || (key[h] == key[g] && h > g))) { top = false; break; }
+                }
+            }
+            if (top) winners.push_back(g);
+        }
+        std::vector<int> picked(winners.size());
+        for (size_t k = 0; k < winners.size(); k++) {
+            const int g = winners[k];
+            unsigned long long used = 0;                       // colours 0..63 held by coloured neighbours (a body carries far fewer groups)
+            for (int side = 0; side < 2; side++) {
+                const int b = jb[2 * g + side];
+                if (b < 0) continue;
+                for (size_t t = 0; t < on_body[b].size(); t++) { const int c = colour[on_body[b][t]]; if (c >= 0 && c < 64) used |= 1ull << c; }
+            }
+            int c = 0;
+            while (c < 63 && ((used >> c) & 1ull)) c++;
+            picked[k] = c;
+        }
+        for (size_t k = 0; k < winners.size(); k++) colour[winners[k]] = picked[k];
+        left -= winners.size();
+    }
+    for (unsigned r = 0; r < m; r++) order[r] = (int)r;
+    std::sort(order.begin(), order.begin() + m, [&](int a, int b) {
+        const int ca = colour[grp[a]], cb = colour[grp[b]];
+        if (ca != cb) return ca < cb;
+        return a < b;                                          // rows of a group are contiguous: (group, row) order = row order
+    });
+}
+
 void quickstep_island(const Batch &B, World &W, const int *bodies, int nb, const int *joints, int nj_all, Real h)
 {
     std::vector<Real> invI(12 * nb);
@@ -796,7 +854,8 @@ void quickstep_island(const Batch &B, World &W, const int *bodies, int nb, const
             for (unsigned i = 0; i < m; i++) { if (findex[i] == -1) order[head++] = i; else order[tail++] = i; }
             if (B.canonical) {
                 // canonical mode (include/ode_b200.h): row groups = the rows of the contacts of one geom pair / of one permanent
-                // joint; inside each of the two classes the rows are ordered by the phase-0 key of their group (ties by row index)
+                // joint (all rows of a group act on the same two bodies); the order of every phase of 8 sweeps is colour-major, see
+                // canonical_order below
                 grp.resize(m);
                 const int npj = (int)W.pjoints.size();
                 for (int k = 0; k < nj; k++) {
@@ -807,13 +866,7 @@ void quickstep_island(const Batch &B, World &W, const int *bodies, int nb, const
                     }
                     for (int r = mindex[k]; r < mindex[k + 1]; r++) grp[r] = first;
                 }
-                const unsigned nfree = m - valid_findices;
-                auto by_key = [&](int a, int b) {
-                    unsigned ka = odebi_canon_key(W.step_seed, (unsigned)W.cur_island, 0, (unsigned)grp[a]), kb = odebi_canon_key(W.step_seed, (unsigned)W.cur_island, 0, (unsigned)grp[b]);
-                    return ka != kb ? ka < kb : a < b;
-                };
-                std::sort(order.begin(), order.begin() + nfree, by_key);
-                std::sort(order.begin() + nfree, order.end(), by_key);
+                canonical_order(W.step_seed, (unsigned)W.cur_island, 0, m, nb, grp, jb, order);
             }
         }
         // iteration loop :1823-1856
@@ -823,12 +876,9 @@ void quickstep_island(const Batch &B, World &W, const int *bodies, int nb, const
             // IsSORConstraintsReorderRequiredForIteration :1080-1109 + ConstraintsShuffling :2578-2611
             if (iteration >= 8 && (iteration % 8) == 0) {
                 if (B.canonical) {
-                    // canonical mode: the permutation of phase k = rows sorted by the keyed hash of their group (ties by row index); the dRand
-                    // stream is advanced by the m-1 draws the reference's Fisher-Yates pass would have consumed (world_step)
-                    std::vector<std::pair<unsigned, unsigned> > kv(m);
-                    for (unsigned i = 0; i < m; i++) kv[i] = std::make_pair(odebi_canon_key(W.step_seed, (unsigned)W.cur_island, iteration / 8, (unsigned)grp[i]), i);
-                    std::stable_sort(kv.begin(), kv.end(), [](const std::pair<unsigned, unsigned> &a, const std::pair<unsigned, unsigned> &b) { return a.first < b.first; });
-                    for (unsigned i = 0; i < m; i++) order[i] = kv[i].second;
+                    // canonical mode: the colour-major order of phase k; the dRand stream is advanced by the m-1 draws the reference's
+                    // Fisher-Yates pass would have consumed (world_step)
+                    canonical_order(W.step_seed, (unsigned)W.cur_island, iteration / 8, m, nb, grp, jb, order);
                     W.draws += m - 1;
                 } else
                 for (unsigned idx = 1; idx < m; idx++) {
