@@ -193,13 +193,14 @@ int odeb_get_enabled(OdebBatch *, int *enabled /* [world][body] */);
  *   ODEB_MODE_CANONICAL: the large-world path (single worlds of 10^3..10^5 bodies).  Pair set, contacts, island membership
  *     and island numbering are those of the reference; inside an island bodies are ordered by descending creation index and
  *     joints by ascending id (permanent joints, then contacts in creation order).  Rows are taken in GROUPS (the rows of the contacts
- *     of one geom pair, or of one permanent joint: they act on the same two bodies).  For every phase of 8 sweeps (phase k starts at
- *     sweep 8k, where the reference reorders) the groups of an island are coloured so that groups of one colour touch disjoint
- *     bodies -- rounds of "every uncoloured group whose (odeb_canon_key(seed, island, k, first row), first row) exceeds that of all its
- *     uncoloured neighbours takes the smallest colour none of its coloured neighbours holds" -- and the sweep order is colour
- *     ascending, group ascending, rows of a group in row order (a contact's normal row right before its friction rows).  The
- *     world's dRand seed is advanced by the draws the reference's Fisher-Yates reorders would have consumed.  Groups of one colour
- *     are relaxed side by side on the GPU with exactly the result of the sequential sweep in that order, so the CUDA path is
+ *     of one geom pair, or of one permanent joint: they act on the same two bodies).  Once per step the groups of an island are
+ *     coloured so that groups of one colour touch disjoint bodies -- rounds of "every uncoloured group whose
+ *     (odeb_canon_key(seed, island, 0, first row), first row) exceeds that of all its uncoloured neighbours takes the smallest colour
+ *     none of its coloured neighbours holds".  In phase k (the 8 sweeps from sweep 8k on, where the reference reorders) the colours are
+ *     visited in ascending (odeb_canon_key(seed, ~0, k, colour), colour) order (odebi_canon_colour_ranks), the groups of a colour by
+ *     ascending first row, the rows of a group in row order (a contact's normal row right before its friction rows).  The world's
+ *     dRand seed is advanced by the draws the reference's Fisher-Yates reorders would have consumed.  Groups of one colour are
+ *     relaxed side by side on the GPU with exactly the result of the sequential sweep in that order, so the CUDA path is
  *     bit-identical to the oracle run in the same mode (oracle: orc_set_solver_mode).  The order is this library's own (the
  *     reference's is the attach order, then random permutations): trajectories differ from the reference the way two random
  *     reorderings of the reference differ from each other (profiles/r2_callback_order.txt); everything a step decides before the
@@ -238,6 +239,17 @@ static inline ODEB_HD uint32_t odebi_canon_key(uint32_t seed, uint32_t island, u
     uint32_t x = seed ^ (island * 0x9E3779B9u) ^ (phase * 0x85EBCA6Bu) ^ (row * 0xC2B2AE35u);
     x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
     return x;
+}
+/* rank[c] = position of colour c in the visiting order of phase `phase`: colours by ascending (odeb_canon_key(seed, ~0, phase, c), c). */
+static inline ODEB_HD void odebi_canon_colour_ranks(uint32_t seed, uint32_t phase, int rank[64])
+{
+    uint32_t key[64];
+    for (int c = 0; c < 64; c++) key[c] = odebi_canon_key(seed, 0xffffffffu, phase, (uint32_t)c);
+    for (int c = 0; c < 64; c++) {
+        int r = 0;
+        for (int d = 0; d < 64; d++) if (key[d] < key[c] || (key[d] == key[c] && d < c)) r++;
+        rank[c] = r;
+    }
 }
 
 /* nsteps x { dSpaceCollide + contact policy ; dWorldQuickStep(h) ; dJointGroupEmpty }.

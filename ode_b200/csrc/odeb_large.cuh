@@ -12,14 +12,18 @@
 //   islands      lock-free union-find over all joints (util.cpp:724-860 finds the same components with a DFS);
 //                island number = rank of the component's highest enabled body, descending (world->firstbody order)
 //   order        bodies (island, descending index), joints (island, ascending id) by radix sort; row offsets by scan
-//   solve        per phase of 8 sweeps the row GROUPS (rows of the contacts of one geom pair / of one joint: same two bodies) are
-//                coloured so that groups of one colour touch disjoint bodies (Jones-Plassmann rounds with first fit, priorities =
-//                odeb_canon_key(seed, island, phase, group): deterministic, the oracle runs the same rounds); the canonical sweep
-//                order is colour-major, and k_lwc_sweep relaxes all groups of a colour side by side, one thread per group with the
-//                two bodies' accumulators in registers: bit-identical to the sequential sweep in that order (quickstep.cpp:2917-3033),
-//                no tickets, no fences, no polling -- ~9 colours on a brick wall, i.e. ~9 short launches per sweep
+//   solve        once per step the row GROUPS (rows of the contacts of one geom pair / of one joint: same two bodies) are coloured so
+//                that groups of one colour touch disjoint bodies (Jones-Plassmann rounds with first fit, priorities =
+//                odeb_canon_key(seed, island, 0, group): deterministic, the oracle runs the same rounds); the canonical sweep order
+//                is colour-major (the colours in a per-phase order), and a launch relaxes all groups of a colour side by side, one
+//                lane per group with the two bodies' accumulators in registers: bit-identical to the sequential sweep in that order
+//                (quickstep.cpp:2917-3033), no tickets, no fences, no polling -- ~9 colours on a brick wall, i.e. ~9 short launches
+//                per sweep.  The records are re-laid once per step into TILES (32 groups of a colour, lane-interleaved, in sweep
+//                order), so a sweep is one coalesced stream over HBM (k_lwt_sweep: register double buffer; k_lwt_sweep_tma:
+//                cp.async.bulk + mbarrier ring).
 //                (round 1 walked a hash-sorted order with per-body tickets: 0.58 ms per sweep on the 100k-box wall, bound by the
-//                L2 round trips of the release / acquire hand-over along the dependency paths)
+//                L2 round trips of the release / acquire hand-over along the dependency paths; a thread per group reading its
+//                records where k_rows left them: 0.5 ms per sweep, bound by the number of outstanding scattered requests per SM)
 //   control      k_lw_body_check + k_lw_island_ctl after every sweep (quickstep.cpp:1823-1856, :3253-3285), per island
 #ifndef ODEB_LARGE_CUH
 #define ODEB_LARGE_CUH
@@ -29,7 +33,7 @@ typedef unsigned long long u64;
 #define LW_NOKEY 0xFFFFFFFFFFFFFFFFull
 
 enum { LWC_NBIG = 0, LWC_NPAIRS = 1, LWC_NCONTACTS = 2, LWC_NORDERED = 3, LWC_NJORD = 4, LWC_MROWS = 5, LWC_NISLANDS = 6,
-       LWC_NACTIVE = 7, LWC_NGROUPS = 8, LWC_UNCOLORED = 9, LWC_NCOLORS = 10, LWC_BIGGROUPS = 11, LWC_CHUNKS = 12, LWC_COUNT = 16 };
+       LWC_NACTIVE = 7, LWC_NGROUPS = 8, LWC_UNCOLORED = 9, LWC_NCOLORS = 10, LWC_NTILES = 11, LWC_SEED = 12, LWC_COUNT = 16 };
 
 struct LargePtrs {
     int *counters;                               // [LWC_COUNT]
@@ -49,9 +53,12 @@ struct LargePtrs {
     int *gsize, *heads;                          // [MR] rows of the group (at its first row); first rows of all groups, compacted
     int *ginc_ofs, *ginc_cur, *ginc;             // [NB + 2], [NB + 2], [2 MR]: body (order position) -> groups acting on it
     unsigned *gkey; int *gcolor, *gwin;          // [MR] at the group's first row: priority of the phase, colour (-1 none yet, -2 island finished), winner flag
-    int *clist, *ccount, *cofs;                  // [MR] groups by colour; [64] groups per colour; [65] first list position of every colour
-    int4 *cinfo;                                 // [MR] beside clist: (first row, rows, accumulator slot of body 1, of body 2) of the group
-    int *slot_row, *cstart;                      // [3 MR + 4096] row of every lane of every 32-row chunk (-1: empty); [65] first chunk of every colour
+    unsigned *skey, *skey_s;                     // [MR] sort keys of the groups: (colour, rows descending)
+    int *clist, *ccount, *cofs, *tstart;         // [MR] groups by (colour, rows descending); [64] groups per colour; [65] first list position / first tile of every colour
+    int *theight, *tbase, *tgroup;               // [MR/32 + 130] rows of a tile, its first tile row; [MR + 4160] first row of the group of every tile lane (-1: none)
+    int4 *tginfo;                                // [MR + 4160] beside tgroup: (rows, accumulator slot of body 1, of body 2, island)
+    Real4 *trec; Real *tlam;                     // [trcap * 8 * 32], [trcap * 32]: lane-interleaved records / lambdas of all tile rows
+    int trcap;                                   // tile rows the two buffers hold
     void *tmp; size_t tmp_bytes;                 // cub scratch
 };
 
@@ -354,15 +361,14 @@ __global__ void k_lwc_ginc_fill(const __grid_constant__ DevParams P, const __gri
 // (key, first row) is larger.  Round = k_lwc_mark (every uncoloured group that has no uncoloured neighbour above it wins; reads only
 // colours of earlier rounds) + k_lwc_assign (winners, never neighbours of each other, take the smallest colour none of their coloured
 // neighbours holds): the result does not depend on thread timing.
-__global__ void k_lwc_color_init(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L, int phase)
+__global__ void k_lwc_color_init(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L)
 {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < 64) L.ccount[t] = 0;
     if (t >= L.counters[LWC_NGROUPS]) return;
     const int g = L.heads[t];
     const unsigned is = (unsigned)L.row_island[g];
-    if (L.isl_done[is]) { L.gcolor[g] = -2; return; }
-    L.gkey[g] = odebi_canon_key(D.seed[0], is, (unsigned)phase, (unsigned)(g - L.isl_rstart[is]));
+    L.gkey[g] = odebi_canon_key(D.seed[0], is, 0u, (unsigned)(g - L.isl_rstart[is]));
     L.gcolor[g] = -1;
     atomicAdd(&L.counters[LWC_UNCOLORED], 1);
 }
@@ -411,26 +417,6 @@ __global__ void k_lwc_assign(const __grid_constant__ DevParams P, const __grid_c
     atomicMax(&L.counters[LWC_NCOLORS], c + 1);
     atomicAdd(&L.ccount[c], 1);
 }
-// groups by colour: list offsets (one thread), then the lists (order inside a colour is irrelevant: disjoint bodies)
-__global__ void k_lwc_color_scan(const __grid_constant__ LargePtrs L)
-{
-    int o = 0;
-    for (int c = 0; c < 64; c++) { L.cofs[c] = o; o += L.ccount[c]; L.ccount[c] = 0; }
-    L.cofs[64] = o;
-}
-__global__ void k_lwc_color_fill(const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L)
-{
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= L.counters[LWC_NGROUPS]) return;
-    const int g = L.heads[t];
-    const int c = L.gcolor[g];
-    if (c < 0) return;
-    const int pos = L.cofs[c] + atomicAdd(&L.ccount[c], 1);
-    L.clist[pos] = g;
-    const int2 rb = D.rbody[g];
-    L.cinfo[pos] = make_int4(g, L.gsize[g], rb.x, rb.y);
-}
-
 __device__ __forceinline__ Real4 ldcg4(const Real4 *p)
 {
 #if defined(ODEB_DOUBLE)
@@ -442,13 +428,6 @@ __device__ __forceinline__ Real4 ldcg4(const Real4 *p)
 #endif
     return r;
 }
-__device__ __forceinline__ Real4 shfl_up4(const Real4 &v)
-{
-    Real4 r;
-    r.x = __shfl_up_sync(0xffffffffu, v.x, 1); r.y = __shfl_up_sync(0xffffffffu, v.y, 1);
-    r.z = __shfl_up_sync(0xffffffffu, v.z, 1); r.w = __shfl_up_sync(0xffffffffu, v.w, 1);
-    return r;
-}
 __device__ __forceinline__ void stcg4(Real4 *p, const Real4 &v)
 {
 #if defined(ODEB_DOUBLE)
@@ -458,402 +437,248 @@ __device__ __forceinline__ void stcg4(Real4 *p, const Real4 &v)
 #endif
 }
 
-// Chunks: the groups of a colour are packed into chunks of 32 row slots (a group never straddles two chunks), so that a warp can give
-// every row of a chunk its own lane.  One warp packs 32 consecutive groups of the colour's list greedily and reserves its chunks with one
-// atomic on the global chunk cursor; the colours are packed one launch after the other, so the chunks of a colour are consecutive from
-// cstart[colour] (k_lwc_chunk_start).  Next-fit leaves every chunk but a warp's last more than half full: 3 MR slots always suffice.
-// Which group lands in which chunk depends on the list order (atomics), which is irrelevant: groups of a colour touch disjoint bodies.
-__global__ void k_lwc_chunk_start(const __grid_constant__ LargePtrs L, int colour) { L.cstart[colour] = L.counters[LWC_CHUNKS]; }
-__global__ void __launch_bounds__(256) k_lwc_chunks(const __grid_constant__ LargePtrs L, int colour)
+// ---- tiles.  The groups are sorted by (colour, rows descending) and cut into TILES of 32 groups of one colour; a tile is as high as its
+// largest group.  The records of a tile are stored lane-interleaved in a second buffer: quad q (16 bytes) of row k of the tile's group
+// `lane` sits at trec[((tbase + k) * 8 + q) * 32 + lane], its lambda at tlam[(tbase + k) * 32 + lane].  The whole tile is ONE contiguous
+// block of HBM in exactly the order the sweep walks it, every warp access is a full 512-byte line set, and the colouring is fixed for
+// the step, so the layout is built once per step (k_lwt_gather) and the 40 sweeps stream it.
+__global__ void k_lwt_sort_keys(const __grid_constant__ LargePtrs L)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
-    const int lo = L.cofs[colour], n = L.cofs[colour + 1] - lo;
-    if ((t & ~31) >= n) return;
-    const int g = t < n ? L.clist[lo + t] : -1;
-    const int sz = g >= 0 ? L.gsize[g] : 0;
-    if (sz > 32) atomicAdd(&L.counters[LWC_BIGGROUPS], 1);
-    int chunk = 0, fill = 0, my_chunk = 0, my_start = 0;
-    for (int k = 0; k < 32; k++) {                                 // every lane replays the same greedy packing
-        const int sk = __shfl_sync(0xffffffffu, sz, k);
-        if (sk == 0 || sk > 32) continue;
-        if (fill + sk > 32) { chunk++; fill = 0; }
-        if (k == lane) { my_chunk = chunk; my_start = fill; }
-        fill += sk;
-    }
-    const int used = chunk + (fill > 0 ? 1 : 0);
-    int base = 0;
-    if (lane == 0 && used > 0) base = atomicAdd(&L.counters[LWC_CHUNKS], used);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (g >= 0 && sz <= 32) {
-        int *slot = L.slot_row + ((size_t)(base + my_chunk) * 32 + my_start);
-        for (int i = 0; i < sz; i++) slot[i] = (g + i) | (i == 0 ? 0x40000000 : 0) | (i == sz - 1 ? (int)0x80000000u : 0);   // bit 30: first, bit 31: last row of its group
-    }
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= L.counters[LWC_NGROUPS]) return;
+    const int g = L.heads[t];
+    const int sz = L.gsize[g] < 4095 ? L.gsize[g] : 4095;
+    L.skey[t] = ((unsigned)L.gcolor[g] << 12) | (unsigned)(4095 - sz);
 }
-
-// One colour of one sweep, lane per row: a warp takes one chunk, every lane loads its row's record (all rows of a colour are in flight
-// at once: the sweep streams the rows from HBM at bandwidth instead of one dependent row after the other per thread); the rows of a group
-// then execute in order, one per step, the two bodies' accumulators travelling from lane to lane by shuffle and a contact's normal-row
-// lambda forwarded to its friction rows; the last row of the group writes the accumulators back.
-__global__ void __launch_bounds__(128) k_lwc_sweep_rows(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L, int colour)
+// list offsets and first tile of every colour (one thread)
+__global__ void k_lwt_color_scan(const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L)
 {
-    const int chunk = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-    const int first = L.cstart[colour];
-    if (chunk >= L.cstart[colour + 1] - first) return;
-    const int slot = L.slot_row[(size_t)(first + chunk) * 32 + lane];
-    const bool any = slot != -1;
-    const int r = any ? (slot & 0x3fffffff) : 0;
-    const bool head = any && (slot & 0x40000000), tail = any && (slot < 0);
-    Real4 *cf = D.cforce;
-    Real *lam = D.lambda;
-    // The 32 row records of the chunk (128 B each, scattered group by group) are fetched COALESCED: in each of 8 passes the warp reads
-    // 4 whole records (8 lanes x 16 B per record) and parks them in shared memory with a padded row stride, then every lane reads its own
-    // record from there (both sides free of bank conflicts: stride = 9 x 16 B).  A lane loading its own record directly touches 32
-    // different lines per instruction: measured 42-50 us per colour instead of ~10.
-    constexpr int RS = (int)sizeof(Real4) * 9;                                  // padded record stride in shared memory (bytes)
-    extern __shared__ __align__(16) unsigned char lwc_smem[];
-    unsigned char *wbuf = lwc_smem + (size_t)(threadIdx.x >> 5) * 32 * RS;
-    {
+    int o = 0, t = 0;
+    for (int c = 0; c < 64; c++) { L.cofs[c] = o; L.tstart[c] = t; o += L.ccount[c]; t += (L.ccount[c] + 31) >> 5; }
+    L.cofs[64] = o; L.tstart[64] = t;
+    L.counters[LWC_NTILES] = t;
+    L.counters[LWC_SEED] = (int)D.seed[0];
+}
+// one warp per tile: the groups of its lanes (rows, accumulator slots of the two bodies, island), the tile's height
+__global__ void __launch_bounds__(128) k_lwt_tiles(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L)
+{
+    const int tile = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (tile >= L.counters[LWC_NTILES]) return;
+    int c = 0;
+    while (c < 63 && tile >= L.tstart[c + 1]) c++;
+    const int pos = L.cofs[c] + ((tile - L.tstart[c]) << 5) + lane;
+    int4 gi = make_int4(0, 0, P.NB, 0);                            // (rows, body 1, body 2, island); rows == 0: empty lane
+    int g = -1;
+    if (pos < L.cofs[c + 1]) {
+        g = L.clist[pos];
+        const int2 rb = D.rbody[g];
+        gi = make_int4(L.gsize[g], rb.x, rb.y, L.row_island[g]);
+    }
+    L.tginfo[(size_t)tile * 32 + lane] = gi;
+    L.tgroup[(size_t)tile * 32 + lane] = g;
+    const int h = __reduce_max_sync(0xffffffffu, gi.x);
+    if (lane == 0) { L.theight[tile] = h; if (tile == 0) L.theight[L.counters[LWC_NTILES]] = 0; }
+}
+// one block per tile: the records into the interleaved layout (friction rows carry `row - findex` in the spare last word), lambda = 0
+__global__ void __launch_bounds__(128) k_lwt_gather(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L)
+{
+    const int tile = blockIdx.x, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int base = L.tbase[tile];
+    if (base + L.theight[tile] > L.trcap) { if (threadIdx.x == 0) atomicExch(D.overflow, 3); return; }
+    const int g = L.tgroup[(size_t)tile * 32 + lane];
+    const int sz = g >= 0 ? L.gsize[g] : 0;
+    for (int k = wib; k < sz; k += 4) {
+        const Real4 *src = D.rows + (size_t)(g + k) * 8;
         Real4 v[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const int rs = 4 * k + (lane >> 3);
-            const int rr = __shfl_sync(0xffffffffu, r, rs);
-            v[k] = ldcg4(D.rows + (size_t)rr * 8 + (lane & 7));
-        }
+        for (int q = 0; q < 8; q++) v[q] = ldcg4(src + q);
+        const int fi = D.findex[g + k];
+        *(int *)&v[7].w = fi == -1 ? 0 : g + k - fi;
+        Real4 *dst = L.trec + ((size_t)(base + k) * 8) * 32 + lane;
 #pragma unroll
-        for (int k = 0; k < 8; k++) *(Real4 *)(wbuf + (size_t)(4 * k + (lane >> 3)) * RS + (lane & 7) * sizeof(Real4)) = v[k];
-    }
-    __syncwarp();
-    const Real4 *rec = (const Real4 *)(wbuf + (size_t)lane * RS);
-    const Real4 a0 = rec[0], a1 = rec[1], a2 = rec[2], a3 = rec[3], b0 = rec[4], b1q = rec[5], b2q = rec[6], b3 = rec[7];
-    const int2 rb = any ? D.rbody[r] : make_int2(0, P.NB);
-    const int fi = any ? D.findex[r] : -1;
-    const Real old_lambda = any ? lam[r] : R_(0.0);
-    const int isl = any ? L.row_island[r] : 0;
-    const bool two = rb.y != P.NB;
-    Real4 f1a = { 0, 0, 0, 0 }, f1b = f1a, f2a = f1a, f2b = f1a;
-    if (head) {
-        f1a = ldcg4(&cf[2 * rb.x]); f1b = ldcg4(&cf[2 * rb.x + 1]);
-        if (two) { f2a = ldcg4(&cf[2 * rb.y]); f2b = ldcg4(&cf[2 * rb.y + 1]); }
-    }
-    const bool live = any && !L.isl_done[isl];
-    const unsigned heads = __ballot_sync(0xffffffffu, head);
-    const int headlane = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));       // first lane of this lane's run
-    // the friction-index row is an earlier row of the same group, i.e. an earlier lane of the same run: its new lambda is forwarded
-    const int fwd_src = (live && fi != -1) ? lane - (r - fi) : lane;
-    const bool fwd = live && fi != -1 && fwd_src >= headlane && fwd_src < lane;
-    Real my_lambda = 0;
-    bool have = live && head;
-    for (;;) {
-        const bool exec = have;
-        const Real lam_fw = __shfl_sync(0xffffffffu, my_lambda, fwd ? fwd_src : lane);
-        if (exec) {
-            Real delta = a1.z - old_lambda * a1.w;
-            delta -= f1a.x * a0.x + f1a.y * a0.y + f1a.z * a0.z + f1a.w * a0.w + f1b.x * a1.x + f1b.y * a1.y;
-            if (two) delta -= f2a.x * b0.x + f2a.y * b0.y + f2a.z * b0.z + f2a.w * b0.w + f2b.x * b1q.x + f2b.y * b1q.y;
-            Real hi_act, lo_act;
-            if (fi != -1) { hi_act = RFABS(b1q.w * (fwd ? lam_fw : lam[fi])); lo_act = -hi_act; }
-            else { hi_act = b1q.w; lo_act = b1q.z; }
-            Real new_lambda = old_lambda + delta;
-            if (new_lambda < lo_act) { delta = lo_act - old_lambda; new_lambda = lo_act; }
-            else if (new_lambda > hi_act) { delta = hi_act - old_lambda; new_lambda = hi_act; }
-            lam[r] = new_lambda;
-            my_lambda = new_lambda;
-            if (delta != 0) {
-                f1a.x += delta * a2.x; f1a.y += delta * a2.y; f1a.z += delta * a2.z; f1a.w += delta * a2.w;
-                f1b.x += delta * a3.x; f1b.y += delta * a3.y;
-                if (delta > 0) f1b.w += delta * a3.z; else f1b.z += delta * a3.z;
-                if (two) {
-                    if (delta > 0) f2b.w += delta * b3.z; else f2b.z += delta * b3.z;
-                    f2a.x += delta * b2q.x; f2a.y += delta * b2q.y; f2a.z += delta * b2q.z; f2a.w += delta * b2q.w;
-                    f2b.x += delta * b3.x; f2b.y += delta * b3.y;
-                }
-            }
-            if (tail) {
-                stcg4(&cf[2 * rb.x], f1a); stcg4(&cf[2 * rb.x + 1], f1b);
-                if (two) { stcg4(&cf[2 * rb.y], f2a); stcg4(&cf[2 * rb.y + 1], f2b); }
-            }
-        }
-        const unsigned pass = __ballot_sync(0xffffffffu, exec && !tail);
-        if (pass == 0) break;
-        const Real4 n1a = shfl_up4(f1a), n1b = shfl_up4(f1b), n2a = shfl_up4(f2a), n2b = shfl_up4(f2b);
-        have = lane > 0 && ((pass >> (lane - 1)) & 1u);
-        if (have) { f1a = n1a; f1b = n1b; f2a = n2a; f2b = n2b; }
+        for (int q = 0; q < 8; q++) dst[q * 32] = v[q];
+        L.tlam[(size_t)(base + k) * 32 + lane] = 0;
     }
 }
-
-// One colour of one sweep, thread per group with the records staged through shared memory.  ncu on the two simpler kernels says why:
-// a thread that walks its group's rows straight from HBM pays one memory latency per row (34 us per colour, 25 k threads in flight);
-// a lane per row fetches everything at once but then passes the accumulators from lane to lane, 12 steps of ~130 instructions with a
-// third of the lanes busy (issue-bound, 36 M warp instructions per colour, 36-50 us).  Here a warp takes 32 consecutive groups of the
-// colour, fetches ALL their records coalesced (8 lanes x 16 B per record, 4 records per instruction, every request in flight at once)
-// into shared memory with a padded record stride, and then every lane relaxes its own group from shared memory: full lanes, one
-// exposed memory latency per warp.  Groups whose records do not fit the warp's buffer (LWC_ROWS_PER_WARP) are relaxed straight from HBM.
-#if defined(ODEB_DOUBLE)
-#define LWC_ROWS_PER_WARP 160
-#else
-#define LWC_ROWS_PER_WARP 288
-#endif
-#define LWC_WARPS 4
-__global__ void __launch_bounds__(32 * LWC_WARPS) k_lwc_sweep_staged(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L, int colour)
+// feedback only: the final lambdas back in row order
+__global__ void __launch_bounds__(128) k_lwt_lambda_out(const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L)
 {
-    constexpr int RS = (int)sizeof(Real4) * 9;                                  // padded record stride (bytes): conflict-free on both sides
-    extern __shared__ __align__(16) unsigned char lwc_smem[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    unsigned char *wbuf = lwc_smem + (size_t)wib * (LWC_ROWS_PER_WARP * RS + LWC_ROWS_PER_WARP * sizeof(int));
-    int *srow = (int *)(wbuf + (size_t)LWC_ROWS_PER_WARP * RS);
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int lo = L.cofs[colour], n = L.cofs[colour + 1] - lo;
-    if ((t & ~31) >= n) return;
-    const int g = t < n ? L.clist[lo + t] : -1;
+    const int tile = blockIdx.x, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int base = L.tbase[tile];
+    const int g = L.tgroup[(size_t)tile * 32 + lane];
     const int sz = g >= 0 ? L.gsize[g] : 0;
-    // slots of the warp's buffer: exclusive prefix of the group sizes; groups beyond the buffer stay in HBM
-    int ofs = sz;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, ofs, d); if (lane >= d) ofs += u; }
-    const int total = __shfl_sync(0xffffffffu, ofs, 31);
-    ofs -= sz;
-    const bool staged = g >= 0 && ofs + sz <= LWC_ROWS_PER_WARP;
-    const int nst = total < LWC_ROWS_PER_WARP ? total : LWC_ROWS_PER_WARP;
-    if (staged) for (int i = 0; i < sz; i++) srow[ofs + i] = g + i;
-    else if (g >= 0) for (int i = 0; ofs + i < LWC_ROWS_PER_WARP && i < sz; i++) srow[ofs + i] = g + i;      // a straddling group: harmless filler
-    __syncwarp();
-    for (int s0 = 0; s0 < nst; s0 += 16) {                        // 4 passes of 4 records per trip: 4 requests in flight per lane
-        Real4 v[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) { const int s = s0 + 4 * k + (lane >> 3); if (s < nst) v[k] = ldcg4(D.rows + (size_t)srow[s] * 8 + (lane & 7)); }
-#pragma unroll
-        for (int k = 0; k < 4; k++) { const int s = s0 + 4 * k + (lane >> 3); if (s < nst) *(Real4 *)(wbuf + (size_t)s * RS + (lane & 7) * sizeof(Real4)) = v[k]; }
+    for (int k = wib; k < sz; k += 4) D.lambda[g + k] = L.tlam[(size_t)(base + k) * 32 + lane];
+}
+
+// The row update (Stage4LCP_IterationStep quickstep.cpp:2917-3033) of one row of a group whose two bodies' accumulators are in registers.
+// `fd` = row - findex (0: none); the row it points at is an earlier row of the same group (findex is joint-local), normally the latest
+// row without a friction index, whose new lambda is kept in a register.
+#define LWT_ROW(A0, A1, A2, A3, B0, B1, B2, B3, OLD, K)                                                                   \
+    {                                                                                                                    \
+        const int fd = *(const int *)&(B3).w;                                                                            \
+        Real delta = (A1).z - (OLD) * (A1).w;                                                                            \
+        delta -= f1a.x * (A0).x + f1a.y * (A0).y + f1a.z * (A0).z + f1a.w * (A0).w + f1b.x * (A1).x + f1b.y * (A1).y;    \
+        if (two) delta -= f2a.x * (B0).x + f2a.y * (B0).y + f2a.z * (B0).z + f2a.w * (B0).w + f2b.x * (B1).x + f2b.y * (B1).y; \
+        Real hi_act, lo_act;                                                                                             \
+        if (fd != 0) { hi_act = RFABS((B1).w * ((K) - fd == free_k ? free_lambda : lamp[(size_t)((K) - fd) * 32])); lo_act = -hi_act; } \
+        else { hi_act = (B1).w; lo_act = (B1).z; }                                                                       \
+        Real new_lambda = (OLD) + delta;                                                                                 \
+        if (new_lambda < lo_act) { delta = lo_act - (OLD); new_lambda = lo_act; }                                        \
+        else if (new_lambda > hi_act) { delta = hi_act - (OLD); new_lambda = hi_act; }                                   \
+        lamp[(size_t)(K) * 32] = new_lambda;                                                                             \
+        if (fd == 0) { free_k = (K); free_lambda = new_lambda; }                                                         \
+        if (delta != 0) {                                                                                                \
+            f1a.x += delta * (A2).x; f1a.y += delta * (A2).y; f1a.z += delta * (A2).z; f1a.w += delta * (A2).w;          \
+            f1b.x += delta * (A3).x; f1b.y += delta * (A3).y;                                                            \
+            if (delta > 0) f1b.w += delta * (A3).z; else f1b.z += delta * (A3).z;                                        \
+            if (two) {                                                                                                   \
+                if (delta > 0) f2b.w += delta * (B3).z; else f2b.z += delta * (B3).z;                                    \
+                f2a.x += delta * (B2).x; f2a.y += delta * (B2).y; f2a.z += delta * (B2).z; f2a.w += delta * (B2).w;      \
+                f2b.x += delta * (B3).x; f2b.y += delta * (B3).y;                                                        \
+            }                                                                                                            \
+        }                                                                                                                \
     }
-    if (g < 0) return;                                            // (no warp-level primitive below)
-    const bool skip = L.isl_done[L.row_island[g]] != 0;
-    const int2 rb = D.rbody[g];
-    const bool two = rb.y != P.NB;
+
+// One colour of one sweep, register variant: a warp per tile, a lane per group; the lane walks its group's rows with the two bodies'
+// accumulators in registers, its records arrive through fully coalesced loads (the 32 lanes read 512 consecutive bytes per instruction)
+// issued LWT_AHEAD rows ahead.  No other group of the colour touches these bodies: bit-identical to the sequential sweep.
+#if defined(ODEB_DOUBLE)
+#define LWT_AHEAD 1
+#else
+#define LWT_AHEAD 2
+#endif
+__global__ void __launch_bounds__(128) k_lwt_sweep(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L, int tile0, int ntiles)
+{
+    const int wt = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (wt >= ntiles) return;
+    const int tile = tile0 + wt;
+    const int4 gi = L.tginfo[(size_t)tile * 32 + lane];
+    const int sz = gi.x;
+    if (sz == 0) return;                                           // (no warp-level primitive below)
+    const int base = L.tbase[tile];
+    const Real4 *rec = L.trec + (size_t)base * 8 * 32 + lane;
+    Real *lamp = L.tlam + (size_t)base * 32 + lane;
+    constexpr int NBUF = LWT_AHEAD + 1;
+    Real4 q[NBUF][8]; Real ol[NBUF];
+#pragma unroll
+    for (int j = 0; j < LWT_AHEAD; j++) if (j < sz) {
+#pragma unroll
+        for (int c = 0; c < 8; c++) q[j][c] = ldcg4(rec + ((size_t)j * 8 + c) * 32);
+        ol[j] = __ldcg(lamp + (size_t)j * 32);
+    }
+    const bool two = gi.z != P.NB;
     Real4 *cf = D.cforce;
-    Real *lam = D.lambda;
-    Real4 f1a = ldcg4(&cf[2 * rb.x]), f1b = ldcg4(&cf[2 * rb.x + 1]);
+    Real4 f1a = ldcg4(&cf[2 * gi.y]), f1b = ldcg4(&cf[2 * gi.y + 1]);
     Real4 f2a = { 0, 0, 0, 0 }, f2b = f2a;
-    if (two) { f2a = ldcg4(&cf[2 * rb.y]); f2b = ldcg4(&cf[2 * rb.y + 1]); }
-    __syncwarp();                                                 // the records are in shared memory
-    if (skip) return;
-    int free_row = -1; Real free_lambda = 0;                      // the latest row of the group without a friction index and its new lambda
-    for (int k = 0; k < sz; k++) {
-        const int r = g + k;
-        const Real4 *rec = staged ? (const Real4 *)(wbuf + (size_t)(ofs + k) * RS) : D.rows + (size_t)r * 8;
-        const Real4 a0 = rec[0], a1 = rec[1], a2 = rec[2], a3 = rec[3], b0 = rec[4], b1q = rec[5], b2q = rec[6], b3 = rec[7];
-        const Real old_lambda = lam[r];
-        const int fi = D.findex[r];
-        Real delta = a1.z - old_lambda * a1.w;
-        delta -= f1a.x * a0.x + f1a.y * a0.y + f1a.z * a0.z + f1a.w * a0.w + f1b.x * a1.x + f1b.y * a1.y;
-        if (two) delta -= f2a.x * b0.x + f2a.y * b0.y + f2a.z * b0.z + f2a.w * b0.w + f2b.x * b1q.x + f2b.y * b1q.y;
-        Real hi_act, lo_act;
-        if (fi != -1) { hi_act = RFABS(b1q.w * (fi == free_row ? free_lambda : lam[fi])); lo_act = -hi_act; }
-        else { hi_act = b1q.w; lo_act = b1q.z; }
-        Real new_lambda = old_lambda + delta;
-        if (new_lambda < lo_act) { delta = lo_act - old_lambda; new_lambda = lo_act; }
-        else if (new_lambda > hi_act) { delta = hi_act - old_lambda; new_lambda = hi_act; }
-        lam[r] = new_lambda;
-        if (fi == -1) { free_row = r; free_lambda = new_lambda; }
-        if (delta != 0) {
-            f1a.x += delta * a2.x; f1a.y += delta * a2.y; f1a.z += delta * a2.z; f1a.w += delta * a2.w;
-            f1b.x += delta * a3.x; f1b.y += delta * a3.y;
-            if (delta > 0) f1b.w += delta * a3.z; else f1b.z += delta * a3.z;
-            if (two) {
-                if (delta > 0) f2b.w += delta * b3.z; else f2b.z += delta * b3.z;
-                f2a.x += delta * b2q.x; f2a.y += delta * b2q.y; f2a.z += delta * b2q.z; f2a.w += delta * b2q.w;
-                f2b.x += delta * b3.x; f2b.y += delta * b3.y;
+    if (two) { f2a = ldcg4(&cf[2 * gi.z]); f2b = ldcg4(&cf[2 * gi.z + 1]); }
+    if (L.isl_done[gi.w]) return;
+    int free_k = -1; Real free_lambda = 0;
+    for (int k0 = 0; k0 < sz; k0 += NBUF) {
+#pragma unroll
+        for (int j = 0; j < NBUF; j++) {
+            const int k = k0 + j;
+            if (k < sz) {
+                const int kn = k + LWT_AHEAD;                       // the row requested now lands in the buffer freed by row k - 1
+                if (kn < sz) {
+#pragma unroll
+                    for (int c = 0; c < 8; c++) q[(j + LWT_AHEAD) % NBUF][c] = ldcg4(rec + ((size_t)kn * 8 + c) * 32);
+                    ol[(j + LWT_AHEAD) % NBUF] = __ldcg(lamp + (size_t)kn * 32);
+                }
+                LWT_ROW(q[j][0], q[j][1], q[j][2], q[j][3], q[j][4], q[j][5], q[j][6], q[j][7], ol[j], k)
             }
         }
     }
-    stcg4(&cf[2 * rb.x], f1a); stcg4(&cf[2 * rb.x + 1], f1b);
-    if (two) { stcg4(&cf[2 * rb.y], f2a); stcg4(&cf[2 * rb.y + 1], f2b); }
+    stcg4(&cf[2 * gi.y], f1a); stcg4(&cf[2 * gi.y + 1], f1b);
+    if (two) { stcg4(&cf[2 * gi.z], f2a); stcg4(&cf[2 * gi.z + 1], f2b); }
 }
 
-// One colour of one sweep, thread per group, the records brought in by TMA bulk copies.  The records of a group are one contiguous
-// block of HBM (gsize x 32 reals), so every lane issues ONE cp.async.bulk for its whole group into the warp's shared-memory pool,
-// all of them complete on the warp's mbarrier (lane 0 armed it with the byte count), and after one wait every lane relaxes its own
-// group from shared memory.  All records of the colour are in flight at once and no register or LSU instruction is spent per 16 bytes:
-// what made the thread-per-group kernel slow was one DRAM latency per row (ncu: stall_long_sb 86 %, issue active 7 %), what made the
-// lane-per-row kernel slow was passing accumulators between lanes (issue-bound).  Group j of the warp starts at row offset ofs_j in
-// the pool, shifted by j x 16 bytes: the eight lanes of a shared-memory phase then read eight different bank groups (records are 8 or
-// 16 x 16 bytes).  Groups that do not fit the pool read their records from HBM.
-__device__ __forceinline__ void lwc_mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
-__device__ __forceinline__ void lwc_mbar_expect_tx(unsigned bar, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
-__device__ __forceinline__ void lwc_bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar)
+// One colour of one sweep, TMA variant: the same walk, but the tile rows (32 lanes x 8 quads = 4 KB single / 8 KB double, one contiguous
+// block) are brought into a per-warp ring of shared-memory stages by cp.async.bulk, one copy for the records and one for the 32 lambdas
+// of a tile row, issued by lane 0 LWT_STAGES - 1 rows ahead and completing on the stage's mbarrier: no register and no LSU instruction is
+// spent on the fetch, and the prefetch distance does not cost registers.  The lanes read their quads from the stage (conflict-free:
+// consecutive lanes, consecutive 16-byte words).
+__device__ __forceinline__ void lwt_mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void lwt_mbar_expect_tx(unsigned bar, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void lwt_bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-__device__ __forceinline__ bool lwc_mbar_try_wait(unsigned bar, unsigned parity)
+__device__ __forceinline__ void lwt_mbar_wait(unsigned bar, unsigned parity)
 {
-    unsigned ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
+    asm volatile("{\n\t.reg .pred p;\n\tLWT_WAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra LWT_DONE_%=;\n\tbra LWT_WAIT_%=;\n\tLWT_DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
-#define LWC_TMA_WARPS 2
-#define LWC_AUX_ROWS 24                                     // rows per group whose lambda / findex ranges fit the per-lane slots
-#define LWC_AUX_BYTES ((LWC_AUX_ROWS + 8) * (int)sizeof(Real))
-__global__ void __launch_bounds__(32 * LWC_TMA_WARPS) k_lwc_sweep_tma(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L, int colour)
-{
-    constexpr int REC = (int)sizeof(Real4) * 8;                                 // bytes of a record
-    constexpr int POOL = LWC_ROWS_PER_WARP * REC + 32 * 16 + 32 * 2 * LWC_AUX_BYTES;   // pool of a warp: records + the per-group 16-byte shifts + lambda / findex ranges
-    extern __shared__ __align__(128) unsigned char lwc_smem[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    unsigned char *pool = lwc_smem + (size_t)wib * POOL;
-    unsigned char *aux = pool + LWC_ROWS_PER_WARP * REC + 32 * 16;
-    unsigned long long *bars = (unsigned long long *)(lwc_smem + (size_t)LWC_TMA_WARPS * POOL);
-    const unsigned bar = (unsigned)__cvta_generic_to_shared(bars + wib);
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int lo = L.cofs[colour], n = L.cofs[colour + 1] - lo;
-    if ((t & ~31) >= n) return;
-    if (lane == 0) lwc_mbar_init(bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    __syncwarp();
-    const int4 gi = t < n ? L.cinfo[lo + t] : make_int4(-1, 0, 0, P.NB);
-    const int g = gi.x, sz = gi.y;
-    int ofs = sz;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, ofs, d); if (lane >= d) ofs += u; }
-    ofs -= sz;
-    const bool staged = g >= 0 && ofs + sz <= LWC_ROWS_PER_WARP && sz <= LWC_AUX_ROWS;
-    // lambda and the friction indices of the group's rows come along as two more bulk copies (the 16-byte aligned ranges that hold them):
-    // a load of lambda inside the row loop would put one memory latency on every row
-    const int a0i = g & ~3, a1i = (g + sz + 3) & ~3;              // aligned element range [a0i, a1i) of both arrays
-    const unsigned abytes = staged ? (unsigned)(a1i - a0i) * 4u : 0u;
-    const unsigned bytes = staged ? (unsigned)sz * REC : 0u;
-    const unsigned lbytes = staged ? (unsigned)(a1i - a0i) * (unsigned)sizeof(Real) : 0u;
-    const unsigned total = __reduce_add_sync(0xffffffffu, bytes + lbytes + abytes);
-    unsigned char *mine = pool + (size_t)ofs * REC + lane * 16;
-    unsigned char *auxl = aux + (size_t)lane * (2 * LWC_AUX_BYTES);          // [lambda range | findex range] of this lane's group
-    if (lane == 0) lwc_mbar_expect_tx(bar, total);
-    __syncwarp();
-    if (staged) {
-        lwc_bulk_g2s((unsigned)__cvta_generic_to_shared(mine), D.rows + (size_t)g * 8, bytes, bar);
-        lwc_bulk_g2s((unsigned)__cvta_generic_to_shared(auxl), D.lambda + a0i, lbytes, bar);
-        lwc_bulk_g2s((unsigned)__cvta_generic_to_shared(auxl + LWC_AUX_BYTES), D.findex + a0i, abytes, bar);
-    }
-    // what does not come through the pool is requested meanwhile
-    bool skip = true;
-    const int2 rb = make_int2(gi.z, gi.w);
-    Real4 f1a = { 0, 0, 0, 0 }, f1b = f1a, f2a = f1a, f2b = f1a;
-    Real4 *cf = D.cforce;
-    Real *lam = D.lambda;
-    if (g >= 0) {
-        f1a = ldcg4(&cf[2 * rb.x]); f1b = ldcg4(&cf[2 * rb.x + 1]);
-        if (rb.y != P.NB) { f2a = ldcg4(&cf[2 * rb.y]); f2b = ldcg4(&cf[2 * rb.y + 1]); }
-        skip = L.isl_done[L.row_island[g]] != 0;
-    }
-    const bool two = rb.y != P.NB;
-    const Real *slam = (const Real *)auxl + (g - a0i);
-    const int *sfi = (const int *)(auxl + LWC_AUX_BYTES) + (g - a0i);
-    while (!lwc_mbar_try_wait(bar, 0)) { }
-    if (skip) return;
-    int free_row = -1; Real free_lambda = 0;                      // the latest row of the group without a friction index and its new lambda
-    for (int k = 0; k < sz; k++) {
-        const int r = g + k;
-        const Real4 *rec = staged ? (const Real4 *)(mine + (size_t)k * REC) : D.rows + (size_t)r * 8;
-        const Real4 a0 = rec[0], a1 = rec[1], a2 = rec[2], a3 = rec[3], b0 = rec[4], b1q = rec[5], b2q = rec[6], b3 = rec[7];
-        const Real old_lambda = staged ? slam[k] : lam[r];
-        const int fi = staged ? sfi[k] : D.findex[r];
-        Real delta = a1.z - old_lambda * a1.w;
-        delta -= f1a.x * a0.x + f1a.y * a0.y + f1a.z * a0.z + f1a.w * a0.w + f1b.x * a1.x + f1b.y * a1.y;
-        if (two) delta -= f2a.x * b0.x + f2a.y * b0.y + f2a.z * b0.z + f2a.w * b0.w + f2b.x * b1q.x + f2b.y * b1q.y;
-        Real hi_act, lo_act;
-        if (fi != -1) { hi_act = RFABS(b1q.w * (fi == free_row ? free_lambda : lam[fi])); lo_act = -hi_act; }
-        else { hi_act = b1q.w; lo_act = b1q.z; }
-        Real new_lambda = old_lambda + delta;
-        if (new_lambda < lo_act) { delta = lo_act - old_lambda; new_lambda = lo_act; }
-        else if (new_lambda > hi_act) { delta = hi_act - old_lambda; new_lambda = hi_act; }
-        lam[r] = new_lambda;
-        if (fi == -1) { free_row = r; free_lambda = new_lambda; }
-        if (delta != 0) {
-            f1a.x += delta * a2.x; f1a.y += delta * a2.y; f1a.z += delta * a2.z; f1a.w += delta * a2.w;
-            f1b.x += delta * a3.x; f1b.y += delta * a3.y;
-            if (delta > 0) f1b.w += delta * a3.z; else f1b.z += delta * a3.z;
-            if (two) {
-                if (delta > 0) f2b.w += delta * b3.z; else f2b.z += delta * b3.z;
-                f2a.x += delta * b2q.x; f2a.y += delta * b2q.y; f2a.z += delta * b2q.z; f2a.w += delta * b2q.w;
-                f2b.x += delta * b3.x; f2b.y += delta * b3.y;
-            }
-        }
-    }
-    stcg4(&cf[2 * rb.x], f1a); stcg4(&cf[2 * rb.x + 1], f1b);
-    if (two) { stcg4(&cf[2 * rb.y], f2a); stcg4(&cf[2 * rb.y + 1], f2b); }
-}
-
-// One colour of one sweep: a thread relaxes the rows of one group in row order, the two bodies' accumulators (and the most recent
-// normal-row lambda, which the contact's friction rows clamp against) in registers; the next row's record is requested while the current
-// one is computed.  No other group of the colour touches these bodies.  Arithmetic = Stage4LCP_IterationStep quickstep.cpp:2917-3033.
-#ifndef LWC_BLK
-#define LWC_BLK 2
+#define LWT_STAGES 4
+#if defined(ODEB_DOUBLE)
+#define LWT_WARPS 2
+#else
+#define LWT_WARPS 4
 #endif
-__global__ void __launch_bounds__(128) k_lwc_sweep(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L, int colour)
+#define LWT_STAGE_BYTES (32 * 8 * (int)sizeof(Real4) + 32 * (int)sizeof(Real))
+__global__ void __launch_bounds__(32 * LWT_WARPS) k_lwt_sweep_tma(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L, int tile0, int ntiles)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int lo = L.cofs[colour];
-    if (t >= L.cofs[colour + 1] - lo) return;
-    const int4 gi = L.cinfo[lo + t];                              // (first row, rows, accumulator slots of the two bodies): one load
-    const int g = gi.x, n = gi.y;
-    const int2 rb = make_int2(gi.z, gi.w);
-    const bool two = rb.y != P.NB;
+    extern __shared__ __align__(128) unsigned char lwt_smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int wt = blockIdx.x * LWT_WARPS + wib;
+    if (wt >= ntiles) return;
+    const int tile = tile0 + wt;
+    unsigned char *ring = lwt_smem + (size_t)wib * LWT_STAGES * LWT_STAGE_BYTES;
+    unsigned long long *bars = (unsigned long long *)(lwt_smem + (size_t)LWT_WARPS * LWT_STAGES * LWT_STAGE_BYTES) + wib * LWT_STAGES;
+    const unsigned bar0 = (unsigned)__cvta_generic_to_shared(bars);
+    const unsigned ring0 = (unsigned)__cvta_generic_to_shared(ring);
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < LWT_STAGES; s++) lwt_mbar_init(bar0 + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const int height = L.theight[tile];
+    const int base = L.tbase[tile];
+    const Real4 *rec = L.trec + (size_t)base * 8 * 32;
+    Real *lam0 = L.tlam + (size_t)base * 32;
+    constexpr unsigned RB = 32 * 8 * (unsigned)sizeof(Real4), LB = 32 * (unsigned)sizeof(Real);
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < LWT_STAGES - 1; s++) if (s < height) {
+            lwt_mbar_expect_tx(bar0 + 8 * s, RB + LB);
+            lwt_bulk_g2s(ring0 + s * LWT_STAGE_BYTES, rec + (size_t)s * 8 * 32, RB, bar0 + 8 * s);
+            lwt_bulk_g2s(ring0 + s * LWT_STAGE_BYTES + RB, lam0 + (size_t)s * 32, LB, bar0 + 8 * s);
+        }
+    }
+    const int4 gi = L.tginfo[(size_t)tile * 32 + lane];
+    const int sz = gi.x;
+    const bool two = gi.z != P.NB;
     Real4 *cf = D.cforce;
-    Real *lam = D.lambda;
-    // A launch holds only as many threads as the colour has groups (~45 k on the 100k-box wall: 10 warps per SM), so registers are free
-    // and latency is everything: the records are fetched LWC_BLK rows at a time (8 independent 16-byte loads per row in flight, together
-    // with their lambdas and friction indices) -- one exposed memory latency per LWC_BLK rows instead of one per row.
-    const Real4 *rec = D.rows + (size_t)g * 8;
-    Real4 q[LWC_BLK][8]; Real ol[LWC_BLK]; int fx[LWC_BLK];
-#pragma unroll
-    for (int j = 0; j < LWC_BLK; j++) if (j < n) {
-#pragma unroll
-        for (int c = 0; c < 8; c++) q[j][c] = ldcg4(rec + 8 * j + c);
-        ol[j] = lam[g + j]; fx[j] = D.findex[g + j];
+    Real4 f1a = { 0, 0, 0, 0 }, f1b = f1a, f2a = f1a, f2b = f1a;
+    bool run = false;
+    if (sz > 0) {
+        f1a = ldcg4(&cf[2 * gi.y]); f1b = ldcg4(&cf[2 * gi.y + 1]);
+        if (two) { f2a = ldcg4(&cf[2 * gi.z]); f2b = ldcg4(&cf[2 * gi.z + 1]); }
+        run = L.isl_done[gi.w] == 0;
     }
-    Real4 f1a = ldcg4(&cf[2 * rb.x]), f1b = ldcg4(&cf[2 * rb.x + 1]);
-    Real4 f2a = { 0, 0, 0, 0 }, f2b = f2a;
-    if (two) { f2a = ldcg4(&cf[2 * rb.y]); f2b = ldcg4(&cf[2 * rb.y + 1]); }
-    if (L.isl_done[L.row_island[g]]) return;
-    int free_row = -1; Real free_lambda = 0;                   // the latest row of the group without a friction index and its new lambda
-    for (int k0 = 0; k0 < n; k0 += LWC_BLK) {
-#pragma unroll
-        for (int j = 0; j < LWC_BLK; j++) if (k0 + j < n) {
-            const int r = g + k0 + j;
-            const Real4 a0 = q[j][0], a1 = q[j][1], a2 = q[j][2], a3 = q[j][3], b0 = q[j][4], b1q = q[j][5], b2q = q[j][6], b3 = q[j][7];
-            const Real old_lambda = ol[j];
-            const int fi = fx[j];
-            Real delta = a1.z - old_lambda * a1.w;
-            delta -= f1a.x * a0.x + f1a.y * a0.y + f1a.z * a0.z + f1a.w * a0.w + f1b.x * a1.x + f1b.y * a1.y;
-            if (two) delta -= f2a.x * b0.x + f2a.y * b0.y + f2a.z * b0.z + f2a.w * b0.w + f2b.x * b1q.x + f2b.y * b1q.y;
-            Real hi_act, lo_act;
-            if (fi != -1) { hi_act = RFABS(b1q.w * (fi == free_row ? free_lambda : lam[fi])); lo_act = -hi_act; }
-            else { hi_act = b1q.w; lo_act = b1q.z; }
-            Real new_lambda = old_lambda + delta;
-            if (new_lambda < lo_act) { delta = lo_act - old_lambda; new_lambda = lo_act; }
-            else if (new_lambda > hi_act) { delta = hi_act - old_lambda; new_lambda = hi_act; }
-            lam[r] = new_lambda;
-            if (fi == -1) { free_row = r; free_lambda = new_lambda; }
-            if (delta != 0) {
-                f1a.x += delta * a2.x; f1a.y += delta * a2.y; f1a.z += delta * a2.z; f1a.w += delta * a2.w;
-                f1b.x += delta * a3.x; f1b.y += delta * a3.y;
-                if (delta > 0) f1b.w += delta * a3.z; else f1b.z += delta * a3.z;
-                if (two) {
-                    if (delta > 0) f2b.w += delta * b3.z; else f2b.z += delta * b3.z;
-                    f2a.x += delta * b2q.x; f2a.y += delta * b2q.y; f2a.z += delta * b2q.z; f2a.w += delta * b2q.w;
-                    f2b.x += delta * b3.x; f2b.y += delta * b3.y;
-                }
-            }
+    Real *lamp = lam0 + lane;
+    int free_k = -1; Real free_lambda = 0;
+    for (int k = 0; k < height; k++) {
+        const int s = k % LWT_STAGES;
+        lwt_mbar_wait(bar0 + 8 * s, (unsigned)((k / LWT_STAGES) & 1));
+        if (run && k < sz) {
+            const Real4 *st = (const Real4 *)(ring + (size_t)s * LWT_STAGE_BYTES) + lane;
+            const Real4 a0 = st[0], a1 = st[32], a2 = st[64], a3 = st[96], b0 = st[128], b1q = st[160], b2q = st[192], b3 = st[224];
+            const Real old_lambda = ((const Real *)(ring + (size_t)s * LWT_STAGE_BYTES + RB))[lane];
+            LWT_ROW(a0, a1, a2, a3, b0, b1q, b2q, b3, old_lambda, k)
         }
-        if (k0 + LWC_BLK < n) {
-            const Real4 *nr = rec + 8 * (size_t)(k0 + LWC_BLK);
-#pragma unroll
-            for (int j = 0; j < LWC_BLK; j++) if (k0 + LWC_BLK + j < n) {
-#pragma unroll
-                for (int c = 0; c < 8; c++) q[j][c] = ldcg4(nr + 8 * j + c);
-                ol[j] = lam[g + k0 + LWC_BLK + j]; fx[j] = D.findex[g + k0 + LWC_BLK + j];
-            }
+        __syncwarp();                                              // every lane is done with the stage of row k - 1 ... and with this one's reads
+        const int kn = k + LWT_STAGES - 1;                         // refill the stage row k - 1 used
+        if (lane == 0 && kn < height) {
+            const int sn = kn % LWT_STAGES;
+            lwt_mbar_expect_tx(bar0 + 8 * sn, RB + LB);
+            lwt_bulk_g2s(ring0 + sn * LWT_STAGE_BYTES, rec + (size_t)kn * 8 * 32, RB, bar0 + 8 * sn);
+            lwt_bulk_g2s(ring0 + sn * LWT_STAGE_BYTES + RB, lam0 + (size_t)kn * 32, LB, bar0 + 8 * sn);
         }
     }
-    stcg4(&cf[2 * rb.x], f1a); stcg4(&cf[2 * rb.x + 1], f1b);
-    if (two) { stcg4(&cf[2 * rb.y], f2a); stcg4(&cf[2 * rb.y + 1], f2b); }
+    if (run) {
+        stcg4(&cf[2 * gi.y], f1a); stcg4(&cf[2 * gi.y + 1], f1b);
+        if (two) { stcg4(&cf[2 * gi.z], f2a); stcg4(&cf[2 * gi.z + 1], f2b); }
+    }
 }
 
 // after a sweep: per-body convergence test + reset (CheckForMaximumToBeLessThanLimitAndResetMaxAdjustments quickstep.cpp:3253-3285)

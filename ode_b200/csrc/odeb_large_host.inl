@@ -12,6 +12,7 @@ static size_t large_cub_bytes(const DevParams &P)
     cub::DeviceRadixSort::SortKeys(0, b, (u64 *)0, (u64 *)0, P.MP); best = b > best ? b : best;
     cub::DeviceRadixSort::SortPairs(0, b, (u64 *)0, (u64 *)0, (int *)0, (int *)0, P.NB); best = b > best ? b : best;
     cub::DeviceRadixSort::SortPairs(0, b, (u64 *)0, (u64 *)0, (int *)0, (int *)0, P.NJT); best = b > best ? b : best;
+    cub::DeviceRadixSort::SortPairs(0, b, (unsigned *)0, (unsigned *)0, (int *)0, (int *)0, P.MR); best = b > best ? b : best;
     cub::DeviceScan::ExclusiveSum(0, b, (int *)0, (int *)0, P.MP); best = b > best ? b : best;
     cub::DeviceScan::ExclusiveSum(0, b, (int *)0, (int *)0, P.NJT); best = b > best ? b : best;
     cub::DeviceScan::InclusiveSum(0, b, (int *)0, (int *)0, P.NB + 2); best = b > best ? b : best;
@@ -35,8 +36,12 @@ static int large_prepare(OdebBatch *B)
            && dev_alloc(B, &L.row_island, MR) && dev_alloc(B, &L.row_group, MR) && dev_alloc(B, &L.gsize, MR) && dev_alloc(B, &L.heads, MR)
            && dev_alloc(B, &L.ginc_ofs, NB + 2) && dev_alloc(B, &L.ginc_cur, NB + 2) && dev_alloc(B, &L.ginc, 2 * MR)
            && dev_alloc(B, &L.gkey, MR) && dev_alloc(B, &L.gcolor, MR) && dev_alloc(B, &L.gwin, MR)
-           && dev_alloc(B, &L.clist, MR) && dev_alloc(B, &L.cinfo, MR) && dev_alloc(B, &L.ccount, 64) && dev_alloc(B, &L.cofs, 65)
-           && dev_alloc(B, &L.slot_row, 3 * MR + 4096) && dev_alloc(B, &L.cstart, 66);
+           && dev_alloc(B, &L.clist, MR) && dev_alloc(B, &L.ccount, 64) && dev_alloc(B, &L.cofs, 65) && dev_alloc(B, &L.tstart, 65)
+           && dev_alloc(B, &L.skey, MR) && dev_alloc(B, &L.skey_s, MR)
+           && dev_alloc(B, &L.theight, MR / 32 + 130) && dev_alloc(B, &L.tbase, MR / 32 + 130) && dev_alloc(B, &L.tgroup, MR + 4160) && dev_alloc(B, &L.tginfo, MR + 4160);
+    // tile rows: every row once, plus the padding of tiles whose groups differ in size (sorted by size: a few tile heights per colour)
+    L.trcap = (int)((MR + MR / 4 + 32768 + 31) / 32);
+    ok = ok && dev_alloc(B, &L.trec, (size_t)L.trcap * 8 * 32) && dev_alloc(B, &L.tlam, (size_t)L.trcap * 32);
     if (!ok) return 0;
     L.tmp_bytes = large_cub_bytes(P);
     { unsigned char *t = 0; if (!dev_alloc(B, &t, L.tmp_bytes)) return 0; L.tmp = t; }
@@ -160,13 +165,40 @@ static int large_step(OdebBatch *B)
         if (B->timing) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s); }
         Real exit_delta = P.premature_delta;
         unsigned iteration = 0, extra = 0;
-        int ncolors = 0, csize[65], cstart[66], biggroups = 0;
-        // ODEB_LW_SWEEP=1|2|3|4 (experiments): thread per group from HBM / lane per row / thread per group, records staged by cooperative loads / by TMA bulk copies (default)
-        const int lw_variant = getenv("ODEB_LW_SWEEP") ? atoi(getenv("ODEB_LW_SWEEP")) : 4;
-        const size_t lw_tma_smem = (size_t)LWC_TMA_WARPS * (LWC_ROWS_PER_WARP * 8 * sizeof(Real4) + 32 * 16 + 32 * 2 * LWC_AUX_BYTES) + LWC_TMA_WARPS * sizeof(unsigned long long);
-        cudaFuncSetAttribute(k_lwc_sweep_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lw_tma_smem);
-        const size_t lw_staged_smem = (size_t)LWC_WARPS * (LWC_ROWS_PER_WARP * 9 * sizeof(Real4) + LWC_ROWS_PER_WARP * sizeof(int));
-        cudaFuncSetAttribute(k_lwc_sweep_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lw_staged_smem);
+        // the step's colouring: rounds in batches of 8, until no group is left uncoloured
+        LCK(cudaMemsetAsync(L.counters + LWC_UNCOLORED, 0, 2 * sizeof(int), s));
+        k_lwc_color_init<<<nblk(ngroups > 64 ? ngroups : 64, 256), 256, 0, s>>>(P, D, L);
+        B->launches++;
+        for (int guard = 0; guard < 4096; guard++) {
+            for (int k = 0; k < 8; k++) {
+                k_lwc_mark<<<nblk(ngroups, 256), 256, 0, s>>>(P, D, L);
+                k_lwc_assign<<<nblk(ngroups, 256), 256, 0, s>>>(P, D, L);
+            }
+            B->launches += 16;
+            int left = 0;
+            LCK(cudaMemcpyAsync(&left, L.counters + LWC_UNCOLORED, sizeof(left), cudaMemcpyDeviceToHost, s));
+            LCK(cudaStreamSynchronize(s));
+            if (left <= 0) break;
+        }
+        // tiles: groups by (colour, rows descending), 32 per tile; records and lambdas into the lane-interleaved layout
+        int tstart[65];
+        k_lwt_sort_keys<<<nblk(ngroups, 256), 256, 0, s>>>(L);
+        LCK(cub::DeviceRadixSort::SortPairs(L.tmp, L.tmp_bytes, L.skey, L.skey_s, L.heads, L.clist, ngroups, 0, 18, s));
+        k_lwt_color_scan<<<1, 1, 0, s>>>(D, L);
+        LCK(cudaMemcpyAsync(tstart, L.tstart, sizeof(tstart), cudaMemcpyDeviceToHost, s));
+        LCK(cudaMemcpyAsync(hc, L.counters, sizeof(hc), cudaMemcpyDeviceToHost, s));
+        LCK(cudaStreamSynchronize(s));
+        const int ntiles = tstart[64], ncolors = hc[LWC_NCOLORS];
+        const unsigned step_seed = (unsigned)hc[LWC_SEED];
+        k_lwt_tiles<<<nblk(ntiles * 32, 128), 128, 0, s>>>(P, D, L);
+        LCK(cub::DeviceScan::ExclusiveSum(L.tmp, L.tmp_bytes, L.theight, L.tbase, ntiles + 1, s));
+        k_lwt_gather<<<ntiles, 128, 0, s>>>(P, D, L);
+        B->launches += 6;
+        // ODEB_LW_SWEEP=1|2 (experiments): register double buffer / TMA ring (default)
+        const int lw_variant = B->lw_variant;
+        const size_t lw_tma_smem = (size_t)LWT_WARPS * LWT_STAGES * LWT_STAGE_BYTES + (size_t)LWT_WARPS * LWT_STAGES * sizeof(unsigned long long);
+        if (lw_variant != 1) cudaFuncSetAttribute(k_lwt_sweep_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lw_tma_smem);
+        int corder[64];
         for (;;) {
             if ((iteration & 7) == 0) {
                 if (iteration > 0) {
@@ -174,51 +206,18 @@ static int large_step(OdebBatch *B)
                     LCK(cudaStreamSynchronize(s));
                     if (hc[LWC_NACTIVE] == 0) break;
                 }
-                // the phase's colouring: rounds in batches of 8, until no group of an unfinished island is left uncoloured
-                const int phase = (int)(iteration >> 3);
-                LCK(cudaMemsetAsync(L.counters + LWC_UNCOLORED, 0, 2 * sizeof(int), s));
-                k_lwc_color_init<<<nblk(ngroups > 64 ? ngroups : 64, 256), 256, 0, s>>>(P, D, L, phase);
-                B->launches++;
-                for (int guard = 0; guard < 4096; guard++) {
-                    for (int k = 0; k < 8; k++) {
-                        k_lwc_mark<<<nblk(ngroups, 256), 256, 0, s>>>(P, D, L);
-                        k_lwc_assign<<<nblk(ngroups, 256), 256, 0, s>>>(P, D, L);
-                    }
-                    B->launches += 16;
-                    int left[2] = { 0, 0 };
-                    LCK(cudaMemcpyAsync(left, L.counters + LWC_UNCOLORED, sizeof(left), cudaMemcpyDeviceToHost, s));
-                    LCK(cudaStreamSynchronize(s));
-                    ncolors = left[1];
-                    if (left[0] <= 0) break;
-                }
-                k_lwc_color_scan<<<1, 1, 0, s>>>(L);
-                k_lwc_color_fill<<<nblk(ngroups, 256), 256, 0, s>>>(D, L);
-                LCK(cudaMemcpyAsync(csize, L.cofs, sizeof(csize), cudaMemcpyDeviceToHost, s));
-                LCK(cudaStreamSynchronize(s));
-                B->launches += 2;
-                // 32-row chunks of every colour (lane-per-row sweep, experiments only); groups of more than 32 rows keep the thread-per-group kernel
-                if (lw_variant == 2) {
-                LCK(cudaMemsetAsync(L.slot_row, 0xff, ((size_t)3 * mrows + 4096) * sizeof(int), s));
-                LCK(cudaMemsetAsync(L.counters + LWC_BIGGROUPS, 0, 2 * sizeof(int), s));
-                for (int c = 0; c < ncolors; c++) {
-                    k_lwc_chunk_start<<<1, 1, 0, s>>>(L, c);
-                    const int nc = csize[c + 1] - csize[c];
-                    if (nc > 0) k_lwc_chunks<<<nblk(nc, 256), 256, 0, s>>>(L, c);
-                }
-                k_lwc_chunk_start<<<1, 1, 0, s>>>(L, ncolors);
-                B->launches += 2 * ncolors + 1;
-                LCK(cudaMemcpyAsync(cstart, L.cstart, sizeof(cstart), cudaMemcpyDeviceToHost, s));
-                LCK(cudaMemcpyAsync(&biggroups, L.counters + LWC_BIGGROUPS, sizeof(int), cudaMemcpyDeviceToHost, s));
-                LCK(cudaStreamSynchronize(s));
-                }
+                // the phase's order of the colours (include/ode_b200.h: odebi_canon_colour_ranks)
+                int rank[64];
+                odebi_canon_colour_ranks(step_seed, iteration >> 3, rank);
+                for (int c = 0; c < 64; c++) corder[rank[c]] = c;
             }
-            for (int c = 0; c < ncolors; c++) {
-                const int nc = csize[c + 1] - csize[c];
-                if (nc <= 0) continue;
-                if (lw_variant == 1) k_lwc_sweep<<<nblk(nc, 128), 128, 0, s>>>(P, D, L, c);
-                else if (lw_variant == 2 && biggroups == 0) k_lwc_sweep_rows<<<nblk((cstart[c + 1] - cstart[c]) * 32, 128), 128, 4 * 32 * 9 * sizeof(Real4), s>>>(P, D, L, c);
-                else if (lw_variant == 3) k_lwc_sweep_staged<<<nblk(nc, 32 * LWC_WARPS), 32 * LWC_WARPS, lw_staged_smem, s>>>(P, D, L, c);
-                else k_lwc_sweep_tma<<<nblk(nc, 32 * LWC_TMA_WARPS), 32 * LWC_TMA_WARPS, lw_tma_smem, s>>>(P, D, L, c);
+            for (int k = 0; k < 64; k++) {
+                const int c = corder[k];
+                if (c >= ncolors) continue;
+                const int nt = tstart[c + 1] - tstart[c];
+                if (nt <= 0) continue;
+                if (lw_variant == 1) k_lwt_sweep<<<nblk(nt * 32, 128), 128, 0, s>>>(P, D, L, tstart[c], nt);
+                else k_lwt_sweep_tma<<<nblk(nt, LWT_WARPS), 32 * LWT_WARPS, lw_tma_smem, s>>>(P, D, L, tstart[c], nt);
                 B->launches++;
             }
             ++iteration;
@@ -233,6 +232,7 @@ static int large_step(OdebBatch *B)
             if (terminate_all) break;
         }
         if (B->timing) { cudaEventRecord(e1, s); B->pending.push_back(std::make_pair(e0, e1)); }
+        if (D.jcopy) { k_lwt_lambda_out<<<ntiles, 128, 0, s>>>(D, L); B->launches++; }
     }
     k_lw_finish<<<1, 1, 0, s>>>(P, D, L);
     k_integrate<<<nblk(NB, 128), 128, 0, s>>>(P, D);

@@ -669,23 +669,21 @@ Real modulo_max6(const Real *v)
     return r;
 }
 
-// Canonical row order of one phase (8 sweeps) of the large-world path, ODEB_MODE_CANONICAL (include/ode_b200.h).
-// Groups that share a body conflict.  Colouring by rounds (Jones-Plassmann with first fit): in every round each still uncoloured
-// group whose (key, first row) is larger than that of all its still uncoloured neighbours takes the smallest colour none of its
-// already coloured neighbours holds; key = odeb_canon_key(seed, island, phase, first row of the group).  Winners of a round are never
-// neighbours, so the result does not depend on any evaluation order (the CUDA path runs the rounds as two kernels, mark and assign).
-// Sweep order = colour ascending, then group (first row) ascending, rows of a group in row order (a contact's normal row right before
-// its friction rows).  Groups of one colour touch disjoint bodies: the CUDA path relaxes them side by side with the same result.
-static void canonical_order(unsigned seed, unsigned island, unsigned phase, unsigned m, int nb, const std::vector<int> &grp,
-                            const std::vector<int> &jb, std::vector<int> &order)
+// Canonical row order of the large-world path, ODEB_MODE_CANONICAL (include/ode_b200.h).
+// Groups that share a body conflict.  ONCE per step and island the groups are coloured by rounds (Jones-Plassmann with first fit): in
+// every round each still uncoloured group whose (key, first row) is larger than that of all its still uncoloured neighbours takes the
+// smallest colour none of its already coloured neighbours holds; key = odeb_canon_key(seed, island, 0, first row of the group).  Winners
+// of a round are never neighbours, so the result does not depend on any evaluation order (the CUDA path runs the rounds as two kernels,
+// mark and assign).  Groups of one colour touch disjoint bodies: the CUDA path relaxes them side by side with the same result.
+static void canonical_colours(unsigned seed, unsigned island, unsigned m, int nb, const std::vector<int> &grp, const std::vector<int> &jb, std::vector<int> &colour)
 {
     std::vector<int> heads;
     for (unsigned r = 0; r < m; r++) if (grp[r] == (int)r) heads.push_back((int)r);
     std::vector<std::vector<int> > on_body(nb);
     for (size_t k = 0; k < heads.size(); k++) for (int side = 0; side < 2; side++) { const int b = jb[2 * heads[k] + side]; if (b >= 0) on_body[b].push_back(heads[k]); }
     std::vector<unsigned> key(m, 0);
-    std::vector<int> colour(m, -1);
-    for (size_t k = 0; k < heads.size(); k++) key[heads[k]] = odebi_canon_key(seed, island, phase, (unsigned)heads[k]);
+    colour.assign(m, -1);
+    for (size_t k = 0; k < heads.size(); k++) key[heads[k]] = odebi_canon_key(seed, island, 0, (unsigned)heads[k]);
     size_t left = heads.size();
     while (left > 0) {
         std::vector<int> winners;
@@ -719,9 +717,17 @@ static void canonical_order(unsigned seed, unsigned island, unsigned phase, unsi
         for (size_t k = 0; k < winners.size(); k++) colour[winners[k]] = picked[k];
         left -= winners.size();
     }
+}
+// Sweep order of phase k (the 8 sweeps from sweep 8k on): the colours are visited in ascending (odeb_canon_key(seed, ~0, k, colour), colour)
+// -- one permutation of the 64 colour numbers per phase, the same for every island --, the groups of a colour by ascending first row, the
+// rows of a group in row order (a contact's normal row right before its friction rows).
+static void canonical_order(unsigned seed, unsigned phase, unsigned m, const std::vector<int> &grp, const std::vector<int> &colour, std::vector<int> &order)
+{
+    int rank[64];
+    odebi_canon_colour_ranks(seed, phase, rank);
     for (unsigned r = 0; r < m; r++) order[r] = (int)r;
     std::sort(order.begin(), order.begin() + m, [&](int a, int b) {
-        const int ca = colour[grp[a]], cb = colour[grp[b]];
+        const int ca = rank[colour[grp[a]]], cb = rank[colour[grp[b]]];
         if (ca != cb) return ca < cb;
         return a < b;                                          // rows of a group are contiguous: (group, row) order = row order
     });
@@ -773,7 +779,7 @@ void quickstep_island(const Batch &B, World &W, const int *bodies, int nb, const
     int nj = (int)jl.size();
     const Real hrecip = rrecip(h);
     std::vector<Real> J, iMJ, lambda, cforce(6 * nb, 0), fa(2 * nb, 0), rhs_tmp(6 * nb);
-    std::vector<int> findex, jb, order, mindex(nj + 1), grp;
+    std::vector<int> findex, jb, order, mindex(nj + 1), grp, gcolour;
     int isl_sweeps = 0;
     if (m > 0) {
         // Stage1 :1364-1472
@@ -866,7 +872,8 @@ void quickstep_island(const Batch &B, World &W, const int *bodies, int nb, const
                     }
                     for (int r = mindex[k]; r < mindex[k + 1]; r++) grp[r] = first;
                 }
-                canonical_order(W.step_seed, (unsigned)W.cur_island, 0, m, nb, grp, jb, order);
+                canonical_colours(W.step_seed, (unsigned)W.cur_island, m, nb, grp, jb, gcolour);
+                canonical_order(W.step_seed, 0, m, grp, gcolour, order);
             }
         }
         // iteration loop :1823-1856
@@ -876,9 +883,9 @@ void quickstep_island(const Batch &B, World &W, const int *bodies, int nb, const
             // IsSORConstraintsReorderRequiredForIteration :1080-1109 + ConstraintsShuffling :2578-2611
             if (iteration >= 8 && (iteration % 8) == 0) {
                 if (B.canonical) {
-                    // canonical mode: the colour-major order of phase k; the dRand stream is advanced by the m-1 draws the reference's
+                    // canonical mode: the colour-major order of phase k (same colouring, the colours visited in the phase's own order); the dRand stream is advanced by the m-1 draws the reference's
                     // Fisher-Yates pass would have consumed (world_step)
-                    canonical_order(W.step_seed, (unsigned)W.cur_island, iteration / 8, m, nb, grp, jb, order);
+                    canonical_order(W.step_seed, iteration / 8, m, grp, gcolour, order);
                     W.draws += m - 1;
                 } else
                 for (unsigned idx = 1; idx < m; idx++) {

@@ -1,8 +1,8 @@
 #!/bin/bash
+# canonical-mode parity tests + timing of the two large-world sweep kernels (ODEB_LW_SWEEP=1 registers, 2 TMA ring) + launch list of the wall
 cd /root/repo; mkdir -p gpurun_out
 {
-for v in 1; do export ODEB_LW_SWEEP=$v; timeout 1500 python -m pytest tests -m gpu -x -q -k "canonical" 2>&1 | tail -2; done
-export ODEB_LW_SWEEP=1
+for v in 1 2; do export ODEB_LW_SWEEP=$v; echo "== ODEB_LW_SWEEP=$v"; timeout 1500 python -m pytest tests -m gpu -x -q -k "canonical" 2>&1 | tail -3
 python - <<'PY'
 import sys, time, ctypes as C
 sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
@@ -16,7 +16,9 @@ for name, mk, h in (("wall 500x200", lambda: scenes.wall(500, 200), 0.05), ("pil
     ms = C.c_double(0); L.odeb_timed_steps(b.h, h, 6, 0, C.byref(ms))
     print(name, "ms/step %.3f" % (ms.value / 6), b.get_totals(), flush=True)
 PY
+done
+export ODEB_LW_SWEEP=${LW_PROFILE_VARIANT:-2}
 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/r2_launches_wall.csv python tools/profile_scene.py wall 1 8 1 > /dev/null 2>&1
 python tools/launch_summary.py gpurun_out/r2_launches_wall.csv 24
-} > gpurun_out/lw_a.log 2>&1
-tail -45 gpurun_out/lw_a.log
+} > gpurun_out/lw_b.log 2>&1
+tail -60 gpurun_out/lw_b.log
