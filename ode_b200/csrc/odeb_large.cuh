@@ -33,7 +33,7 @@ typedef unsigned long long u64;
 #define LW_NOKEY 0xFFFFFFFFFFFFFFFFull
 
 enum { LWC_NBIG = 0, LWC_NPAIRS = 1, LWC_NCONTACTS = 2, LWC_NORDERED = 3, LWC_NJORD = 4, LWC_MROWS = 5, LWC_NISLANDS = 6,
-       LWC_NACTIVE = 7, LWC_NGROUPS = 8, LWC_UNCOLORED = 9, LWC_NCOLORS = 10, LWC_NTILES = 11, LWC_SEED = 12, LWC_COUNT = 16 };
+       LWC_NACTIVE = 7, LWC_NGROUPS = 8, LWC_UNCOLORED = 9, LWC_NCOLORS = 10, LWC_NTILES = 11, LWC_SEED = 12, LWC_GBAR = 13, LWC_ITER = 14, LWC_EXTRA = 15, LWC_TERM = 16, LWC_COUNT = 20 };
 
 struct LargePtrs {
     int *counters;                               // [LWC_COUNT]
@@ -679,6 +679,185 @@ __global__ void __launch_bounds__(32 * LWT_WARPS) k_lwt_sweep_tma(const __grid_c
         stcg4(&cf[2 * gi.y], f1a); stcg4(&cf[2 * gi.y + 1], f1b);
         if (two) { stcg4(&cf[2 * gi.z], f2a); stcg4(&cf[2 * gi.z + 1], f2b); }
     }
+}
+
+// A whole PHASE (up to 8 sweeps: every colour in the phase's order, the per-body convergence test and the per-island iteration control
+// after each sweep) as one persistent cooperative launch.  ncu on the launch-per-colour version: a colour costs ~9 us however few tiles
+// it has (launch, tile lookup, first DRAM round trip, 12 dependent rows) and only ~8 us more for 46 MB of records -- latency, not
+// bandwidth.  Here a warp owns the same tiles in every sweep, the colours are separated by a grid barrier (one atomic + one spin per
+// block), and the records of a warp's NEXT tile are requested (tile lookup + the first bulk copies of its ring) BEFORE the warp enters the
+// barrier: records and lambdas of a tile only change when that tile itself runs, so the only loads left behind a barrier are the two
+// bodies' accumulators (L2 hits).  Everything another block may have written is read with ld.cg (L1 is not coherent across the barrier).
+struct LwPhase {
+    int norder;                                  // colours that have tiles, in the phase's visiting order
+    int corder[64];
+    int tstart[65];                              // first tile of every colour
+    int nordered, nislands;
+    unsigned iteration, extra;
+};
+__device__ __forceinline__ void lwt_grid_sync(unsigned *bar, unsigned &target)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        __threadfence();
+        atomicAdd(bar, 1u);
+        unsigned v;
+        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory"); } while ((int)(v - target) < 0);
+    }
+    __syncthreads();
+}
+__global__ void __launch_bounds__(32 * LWT_WARPS) k_lwt_phase(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L, const __grid_constant__ LwPhase ph)
+{
+    extern __shared__ __align__(128) unsigned char lwt_smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int gw = blockIdx.x * LWT_WARPS + wib, TW = gridDim.x * LWT_WARPS;
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, GT = gridDim.x * blockDim.x;
+    unsigned char *ring = lwt_smem + (size_t)wib * LWT_STAGES * LWT_STAGE_BYTES;
+    unsigned long long *bars = (unsigned long long *)(lwt_smem + (size_t)LWT_WARPS * LWT_STAGES * LWT_STAGE_BYTES) + wib * LWT_STAGES;
+    const unsigned bar0 = (unsigned)__cvta_generic_to_shared(bars);
+    const unsigned ring0 = (unsigned)__cvta_generic_to_shared(ring);
+    constexpr unsigned RB = 32 * 8 * (unsigned)sizeof(Real4), LB = 32 * (unsigned)sizeof(Real);
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < LWT_STAGES; s++) lwt_mbar_init(bar0 + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    unsigned *gbar = (unsigned *)&L.counters[LWC_GBAR];
+    unsigned gtarget = 0;
+    unsigned ri = 0, rc = 0;                                       // tile rows requested / consumed by this warp so far (ring position and mbarrier parity)
+    // the warp's pending item (sweep, position in the colour order, tile) and the state of the tile that was begun for it
+    int it_sw = 0, it_ci = ph.norder, it_tile = 0;
+    for (int ci = 0; ci < ph.norder; ci++) { const int c = ph.corder[ci]; if (ph.tstart[c] + gw < ph.tstart[c + 1]) { it_ci = ci; it_tile = ph.tstart[c] + gw; break; } }
+    const int first_ci = it_ci, first_tile = it_tile;
+    const bool any_items = first_ci < ph.norder;
+    int height = 0, issued = 0; int4 gi = make_int4(0, 0, P.NB, 0);
+    const Real4 *rec = 0; Real *lam0 = 0;
+    auto tile_begin = [&](int tile) {
+        height = L.theight[tile];
+        const int base = L.tbase[tile];
+        rec = L.trec + (size_t)base * 8 * 32;
+        lam0 = L.tlam + (size_t)base * 32;
+        gi = L.tginfo[(size_t)tile * 32 + lane];
+        issued = height < LWT_STAGES - 1 ? height : LWT_STAGES - 1;
+        if (lane == 0) {
+            for (int k = 0; k < issued; k++) {
+                const unsigned s = (ri + k) % LWT_STAGES;
+                lwt_mbar_expect_tx(bar0 + 8 * s, RB + LB);
+                lwt_bulk_g2s(ring0 + s * LWT_STAGE_BYTES, rec + (size_t)k * 8 * 32, RB, bar0 + 8 * s);
+                lwt_bulk_g2s(ring0 + s * LWT_STAGE_BYTES + RB, lam0 + (size_t)k * 32, LB, bar0 + 8 * s);
+            }
+        }
+        ri += issued;
+    };
+    if (any_items) tile_begin(it_tile);
+    unsigned iteration = ph.iteration, extra = ph.extra;
+    Real exit_delta = extra ? P.extra_delta : P.premature_delta;
+    int terminated = 0;
+    Real4 *cf = D.cforce;
+    for (int sw = 0; sw < 8; sw++) {
+        for (int ci = 0; ci < ph.norder; ci++) {
+            while (any_items && it_sw == sw && it_ci == ci) {
+                // ---- run the begun tile
+                const int sz = gi.x;
+                const bool two = gi.z != P.NB;
+                Real4 f1a = { 0, 0, 0, 0 }, f1b = f1a, f2a = f1a, f2b = f1a;
+                bool run = false;
+                if (sz > 0) {
+                    f1a = ldcg4(&cf[2 * gi.y]); f1b = ldcg4(&cf[2 * gi.y + 1]);
+                    if (two) { f2a = ldcg4(&cf[2 * gi.z]); f2b = ldcg4(&cf[2 * gi.z + 1]); }
+                    run = __ldcg(&L.isl_done[gi.w]) == 0;
+                }
+                Real *lamp = lam0 + lane;
+                int free_k = -1; Real free_lambda = 0;
+                for (int k = 0; k < height; k++) {
+                    const unsigned s = rc % LWT_STAGES;
+                    lwt_mbar_wait(bar0 + 8 * s, (rc / LWT_STAGES) & 1u);
+                    if (run && k < sz) {
+                        const Real4 *st = (const Real4 *)(ring + (size_t)s * LWT_STAGE_BYTES) + lane;
+                        const Real4 a0 = st[0], a1 = st[32], a2 = st[64], a3 = st[96], b0 = st[128], b1q = st[160], b2q = st[192], b3 = st[224];
+                        const Real old_lambda = ((const Real *)(ring + (size_t)s * LWT_STAGE_BYTES + RB))[lane];
+                        LWT_ROW(a0, a1, a2, a3, b0, b1q, b2q, b3, old_lambda, k)
+                    }
+                    rc++;
+                    __syncwarp();
+                    if (issued < height) {
+                        if (lane == 0) {
+                            const unsigned sn = ri % LWT_STAGES;
+                            lwt_mbar_expect_tx(bar0 + 8 * sn, RB + LB);
+                            lwt_bulk_g2s(ring0 + sn * LWT_STAGE_BYTES, rec + (size_t)issued * 8 * 32, RB, bar0 + 8 * sn);
+                            lwt_bulk_g2s(ring0 + sn * LWT_STAGE_BYTES + RB, lam0 + (size_t)issued * 32, LB, bar0 + 8 * sn);
+                        }
+                        ri++; issued++;
+                    }
+                }
+                if (run) {
+                    stcg4(&cf[2 * gi.y], f1a); stcg4(&cf[2 * gi.y + 1], f1b);
+                    if (two) { stcg4(&cf[2 * gi.z], f2a); stcg4(&cf[2 * gi.z + 1], f2b); }
+                }
+                // ---- the warp's next item; its tile is begun right away (before the barrier).  The lambdas this tile just wrote are read
+                // again by the bulk copies of its next visit (async proxy), possibly at once (a warp with a single tile)
+                asm volatile("fence.proxy.async.global;" ::: "memory");
+                __syncwarp();
+                {
+                    const int c = ph.corder[it_ci];
+                    it_tile += TW;
+                    if (it_tile >= ph.tstart[c + 1]) {
+                        int cj = it_ci + 1;
+                        for (; cj < ph.norder; cj++) { const int c2 = ph.corder[cj]; if (ph.tstart[c2] + gw < ph.tstart[c2 + 1]) { it_tile = ph.tstart[c2] + gw; break; } }
+                        if (cj < ph.norder) it_ci = cj;
+                        else { it_sw++; it_ci = first_ci; it_tile = first_tile; }
+                    }
+                    if (it_sw < 8) tile_begin(it_tile);
+                }
+            }
+            lwt_grid_sync(gbar, gtarget);
+        }
+        // ---- end of the sweep: iteration control quickstep.cpp:1832-1855, :3253-3285 (k_lw_body_check + k_lw_island_ctl)
+        ++iteration;
+        int terminate_all = 0, in_extra = 0;
+        if (iteration - extra == P.num_iter) {
+            if (extra != 0 || P.max_extra == 0) { terminate_all = 1; in_extra = extra != 0; }
+            else { extra = P.max_extra; exit_delta = P.extra_delta; }
+        }
+        if (P.dyn_enabled && !terminate_all) {
+            for (int k = gtid; k < ph.nordered; k += GT) {
+                const int is = D.body_island[D.body_order[k]];
+                if (__ldcg(&L.isl_done[is])) continue;
+                Real4 v = ldcg4(&cf[2 * k + 1]);
+                if (!(v.w < exit_delta) || !(-v.z < exit_delta)) __stcg(&L.isl_viol[is], 1);
+                v.z = 0; v.w = 0;
+                stcg4(&cf[2 * k + 1], v);
+            }
+            lwt_grid_sync(gbar, gtarget);
+        }
+        for (int is = gtid; is < ph.nislands; is += GT) {
+            if (__ldcg(&L.isl_done[is])) continue;
+            const int m = L.isl_m[is];
+            atomicAdd(&L.draws[1], 1ull); atomicAdd(&L.draws[2], (u64)m);
+            unsigned *st = D.stats;
+            bool done = false;
+            if (terminate_all) { if (in_extra) atomicAdd(&st[3], 1u); done = true; }
+            else if (P.dyn_enabled) {
+                const bool hit = (exit_delta == 0) || __ldcg(&L.isl_viol[is]);
+                __stcg(&L.isl_viol[is], 0);
+                if (!hit) {
+                    if (iteration < P.num_iter) atomicAdd(&st[1], 1u);
+                    else if (iteration > P.num_iter) atomicAdd(&st[2], 1u);
+                    done = true;
+                }
+            }
+            if (done) { __stcg(&L.isl_done[is], 1); atomicSub(&L.counters[LWC_NACTIVE], 1); }
+            else if (iteration >= 8 && (iteration & 7) == 0) atomicAdd(&L.draws[0], (u64)(m - 1));
+        }
+        lwt_grid_sync(gbar, gtarget);
+        if (terminate_all) { terminated = 1; break; }
+        if (__ldcg(&L.counters[LWC_NACTIVE]) == 0) break;
+    }
+    // bulk copies of a tile that was begun for a sweep that does not take place must land before the block retires
+    while (rc < ri) { lwt_mbar_wait(bar0 + 8 * (rc % LWT_STAGES), (rc / LWT_STAGES) & 1u); rc++; }
+    if (gtid == 0) { L.counters[LWC_ITER] = (int)iteration; L.counters[LWC_EXTRA] = (int)extra; L.counters[LWC_TERM] = terminated; }
 }
 
 // after a sweep: per-body convergence test + reset (CheckForMaximumToBeLessThanLimitAndResetMaxAdjustments quickstep.cpp:3253-3285)

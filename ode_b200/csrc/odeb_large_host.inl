@@ -194,11 +194,46 @@ static int large_step(OdebBatch *B)
         LCK(cub::DeviceScan::ExclusiveSum(L.tmp, L.tmp_bytes, L.theight, L.tbase, ntiles + 1, s));
         k_lwt_gather<<<ntiles, 128, 0, s>>>(P, D, L);
         B->launches += 6;
-        // ODEB_LW_SWEEP=1|2 (experiments): register double buffer / TMA ring (default)
+        // ODEB_LW_SWEEP=1|2 (experiments): a launch per colour, register double buffer / TMA ring; 3 (default): persistent phases
         const int lw_variant = B->lw_variant;
         const size_t lw_tma_smem = (size_t)LWT_WARPS * LWT_STAGES * LWT_STAGE_BYTES + (size_t)LWT_WARPS * LWT_STAGES * sizeof(unsigned long long);
-        if (lw_variant != 1) cudaFuncSetAttribute(k_lwt_sweep_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lw_tma_smem);
+        if (lw_variant == 2) cudaFuncSetAttribute(k_lwt_sweep_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lw_tma_smem);
         int corder[64];
+        if (lw_variant == 3) {
+            // persistent phases: one cooperative launch per 8 sweeps
+            if (B->lw_grid == 0) {
+                cudaFuncSetAttribute(k_lwt_phase, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lw_tma_smem);
+                int occ = 0, sms = 0;
+                LCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_lwt_phase, 32 * LWT_WARPS, lw_tma_smem));
+                LCK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, B->device));
+                B->lw_grid = occ * sms;
+                if (B->lw_grid <= 0) { set_err("k_lwt_phase does not fit an SM"); return 0; }
+            }
+            int maxnt = 1;
+            for (int c = 0; c < ncolors && c < 64; c++) if (tstart[c + 1] - tstart[c] > maxnt) maxnt = tstart[c + 1] - tstart[c];
+            int grid = (maxnt + LWT_WARPS - 1) / LWT_WARPS;
+            { const int by_bodies = (nordered + 32 * LWT_WARPS - 1) / (32 * LWT_WARPS); if (by_bodies > grid) grid = by_bodies; }
+            if (grid > B->lw_grid) grid = B->lw_grid;
+            LwPhase ph;
+            for (int c = 0; c < 65; c++) ph.tstart[c] = tstart[c];
+            ph.nordered = nordered; ph.nislands = T;
+            for (;;) {
+                int rank[64];
+                odebi_canon_colour_ranks(step_seed, iteration >> 3, rank);
+                for (int c = 0; c < 64; c++) corder[rank[c]] = c;
+                ph.norder = 0;
+                for (int k = 0; k < 64; k++) { const int c = corder[k]; if (c < ncolors && tstart[c + 1] > tstart[c]) ph.corder[ph.norder++] = c; }
+                ph.iteration = iteration; ph.extra = extra;
+                LCK(cudaMemsetAsync(L.counters + LWC_GBAR, 0, sizeof(int), s));
+                void *args[4] = { (void *)&P, (void *)&D, (void *)&L, (void *)&ph };
+                LCK(cudaLaunchCooperativeKernel((const void *)k_lwt_phase, dim3(grid), dim3(32 * LWT_WARPS), args, lw_tma_smem, s));
+                B->launches++;
+                LCK(cudaMemcpyAsync(hc, L.counters, sizeof(hc), cudaMemcpyDeviceToHost, s));
+                LCK(cudaStreamSynchronize(s));
+                iteration = (unsigned)hc[LWC_ITER]; extra = (unsigned)hc[LWC_EXTRA];
+                if (hc[LWC_TERM] || hc[LWC_NACTIVE] == 0) break;
+            }
+        } else
         for (;;) {
             if ((iteration & 7) == 0) {
                 if (iteration > 0) {

@@ -181,7 +181,7 @@ def test_capacity_overflow_in_the_async_loop():
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# large-world path (ODEB_MODE_CANONICAL): sort/scan/union-find pipeline + ticketed sweeps against the oracle run in the
+# large-world path (ODEB_MODE_CANONICAL): sort/scan/union-find pipeline + coloured tile sweeps against the oracle run in the
 # same mode. Integer observables identical; floats bit-identical for scenes without libm calls.
 def _canon_pair(prec, sc):
     a, b = B.Batch(orc_lib(prec), sc), B.Batch(gpu_lib(prec), sc)
