@@ -40,6 +40,7 @@ struct LargePtrs {
     u64 *draws;                                  // [4]: dRand draws the reference's reorders would have consumed, sweeps, row-sweeps
     // broadphase
     unsigned *bp_key, *bp_key_s; int *bp_idx, *bp_idx_s, *bp_big;   // [NG]
+    Real4 *bp_yz;                                // [NG] (min, max) on axes 1 and 2 in sorted order
     u64 *pair_key, *pair_key_s;                  // [MP]
     int *pc_base;                                // [MP]
     // islands
@@ -51,7 +52,7 @@ struct LargePtrs {
     int *row_island;                             // [MR]
     int *row_group;                              // [MR] first row of the row's group
     int *gsize, *heads;                          // [MR] rows of the group (at its first row); first rows of all groups, compacted
-    int *ginc_ofs, *ginc_cur, *ginc;             // [NB + 2], [NB + 2], [2 MR]: body (order position) -> groups acting on it
+    int *ginc_ofs, *ginc_cur; int2 *ginc;        // [NB + 2], [NB + 2], [2 MR]: body (order position) -> (group, its priority) of the groups acting on it
     unsigned *gkey; int *gcolor, *gwin;          // [MR] at the group's first row: priority of the phase, colour (-1 none yet, -2 island finished), winner flag
     unsigned *skey, *skey_s;                     // [MR] sort keys of the groups: (colour, rows descending)
     int *clist, *ccount, *cofs, *tstart;         // [MR] groups by (colour, rows descending); [64] groups per colour; [65] first list position / first tile of every colour
@@ -88,24 +89,55 @@ __device__ __forceinline__ void lw_emit_pair(const DevParams &P, const LargePtrs
     if (k < P.MP) L.pair_key[k] = ((u64)(unsigned)lo << 32) | (unsigned)hi;
 }
 
-// sweep along axis 0 in float-sorted order: every pair whose axis-0 intervals overlap is visited from its earlier member
+// sweep along axis 0 in float-sorted order: every pair whose axis-0 intervals overlap is visited from its earlier member.  A thread keeps
+// the pairs it finds (a box of a wall meets ~4 later neighbours) and the warp reserves room for all of them with ONE atomic at the end:
+// one atomicAdd per pair on the single pair counter serialised the kernel (0.68 ms for 393 k pairs).
+#define LW_PAIRBUF 8
+// the y / z extents in sorted order: the sweep reads its candidates' boxes as one sequential, L1-friendly stream and rejects most of them
+// (a wall: ~600 candidates with overlapping axis-0 intervals per box, ~4 hits) before touching anything that is indexed by geom
+__global__ void k_bp_gather(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L)
+{
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= P.NG) return;
+    const Real *a = D.aabb + 6 * (size_t)L.bp_idx_s[q];
+    const Real4 v = { a[2], a[3], a[4], a[5] };
+    L.bp_yz[q] = v;
+}
 __global__ void k_bp_sweep(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L)
 {
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= P.NG) return;
-    if (L.bp_key_s[p] == 0xFFFFFFFFu) return;
-    const int i = L.bp_idx_s[p];
-    Real ai[6];
-    for (int k = 0; k < 6; k++) ai[k] = D.aabb[6 * (size_t)i + k];
-    const unsigned kmax = lw_float_key(ai[1]);
-    for (int q = p + 1; q < P.NG; q++) {
-        if (L.bp_key_s[q] > kmax) break;
-        const int j = L.bp_idx_s[q];
-        Real aj[6];
-        for (int k = 0; k < 6; k++) aj[k] = D.aabb[6 * (size_t)j + k];
-        if (i < j) { if (pair_hit(P, D, ai, aj, i, j)) lw_emit_pair(P, L, i, j); }
-        else if (pair_hit(P, D, aj, ai, j, i)) lw_emit_pair(P, L, j, i);
+    const int p = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    u64 buf[LW_PAIRBUF]; int nbuf = 0;
+    if (p < P.NG && L.bp_key_s[p] != 0xFFFFFFFFu) {
+        const int i = L.bp_idx_s[p];
+        Real ai[6];
+        for (int k = 0; k < 6; k++) ai[k] = D.aabb[6 * (size_t)i + k];
+        const unsigned kmax = lw_float_key(ai[1]);
+        for (int q = p + 1; q < P.NG; q++) {
+            if (L.bp_key_s[q] > kmax) break;
+            const Real4 yz = L.bp_yz[q];
+            if (ai[3] < yz.x || yz.y < ai[2] || ai[5] < yz.z || yz.w < ai[4]) continue;    // no overlap on axis 1 or 2: no pair in any space flavour
+            const int j = L.bp_idx_s[q];
+            Real aj[6];
+            for (int k = 0; k < 6; k++) aj[k] = D.aabb[6 * (size_t)j + k];
+            const bool hit = i < j ? pair_hit(P, D, ai, aj, i, j) : pair_hit(P, D, aj, ai, j, i);
+            if (hit) {
+                if (nbuf == LW_PAIRBUF) {                            // a crowded neighbourhood: this thread's buffer goes out on its own
+                    const int base = atomicAdd(&L.counters[LWC_NPAIRS], nbuf);
+                    for (int k = 0; k < nbuf; k++) if (base + k < P.MP) L.pair_key[base + k] = buf[k];
+                    nbuf = 0;
+                }
+                buf[nbuf++] = i < j ? (((u64)(unsigned)i << 32) | (unsigned)j) : (((u64)(unsigned)j << 32) | (unsigned)i);
+            }
+        }
     }
+    int ofs = nbuf;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, ofs, d); if (lane >= d) ofs += u; }
+    const int total = __shfl_sync(0xffffffffu, ofs, 31);
+    int base = 0;
+    if (lane == 31 && total > 0) base = atomicAdd(&L.counters[LWC_NPAIRS], total);
+    base = __shfl_sync(0xffffffffu, base, 31) + ofs - nbuf;
+    for (int k = 0; k < nbuf; k++) if (base + k < P.MP) L.pair_key[base + k] = buf[k];
 }
 
 // geoms of unbounded axis-0 extent (planes) against everything
@@ -238,7 +270,10 @@ __global__ void k_lw_union(const __grid_constant__ DevParams P, const __grid_con
     if (j >= P.NJ + L.counters[LWC_NCONTACTS]) return;
     int b0, b1;
     if (j < P.NJ) { b0 = D.joints[j].b0; b1 = D.joints[j].b1; }
-    else { int4 v = D.cinfo[j - P.NJ]; b0 = v.y; b1 = v.z; }
+    else {
+        int4 v = D.cinfo[j - P.NJ]; b0 = v.y; b1 = v.z;
+        if (v.x % P.maxc != 0) return;                            // the first contact of the geom pair has made this union already
+    }
     if (b1 >= 0) uf_union(L.parent, b0, b1);
 }
 __global__ void k_lw_roots(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L)
@@ -269,8 +304,9 @@ __global__ void k_lw_label(const __grid_constant__ DevParams P, const __grid_con
     if (h >= 0) {
         is = T - L.head_scan[h];
         D.bflags[b] &= ~BF_DISABLED;                          // bodies reached by the traversal are re-enabled (util.cpp:786-790)
-        atomicAdd(&L.isl_nb[is], 1);
-        atomicAdd(&L.counters[LWC_NORDERED], 1);
+        // one atomic per island and warp (a wall is ONE island: 10^5 atomics on one address otherwise)
+        const unsigned peers = __match_any_sync(__activemask(), is);
+        if ((threadIdx.x & 31) == __ffs(peers) - 1) { atomicAdd(&L.isl_nb[is], __popc(peers)); atomicAdd(&L.counters[LWC_NORDERED], __popc(peers)); }
         key = ((u64)(unsigned)is << 32) | (0xFFFFFFFFu - (unsigned)b);
     }
     D.body_island[b] = is;
@@ -298,9 +334,14 @@ __global__ void k_lw_joint_keys(const __grid_constant__ DevParams P, const __gri
         const int is = D.body_island[b0];
         if (is >= 0 && m > 0) {
             key = ((u64)(unsigned)is << 32) | (unsigned)j;
-            atomicAdd(&L.isl_m[is], m);
-            atomicAdd(&L.counters[LWC_NJORD], 1);
-            atomicAdd(&L.counters[LWC_MROWS], m);
+            // one atomic per (island, rows per joint) and warp: a wall is one island, a million contact joints would queue on one address
+            const unsigned peers = __match_any_sync(__activemask(), ((u64)(unsigned)is << 8) | (unsigned)m);
+            if ((threadIdx.x & 31) == __ffs(peers) - 1) {
+                const int n = __popc(peers);
+                atomicAdd(&L.isl_m[is], m * n);
+                atomicAdd(&L.counters[LWC_NJORD], n);
+                atomicAdd(&L.counters[LWC_MROWS], m * n);
+            }
         } else m = 0;
     }
     L.jkey[j] = key; L.jmv[j] = m;
@@ -353,14 +394,17 @@ __global__ void k_lwc_ginc_fill(const __grid_constant__ DevParams P, const __gri
     if (t >= L.counters[LWC_NGROUPS]) return;
     const int g = L.heads[t];
     const int2 rb = D.rbody[g];
-    L.ginc[L.ginc_ofs[rb.x] + atomicAdd(&L.ginc_cur[rb.x], 1)] = g;
-    if (rb.y != P.NB) L.ginc[L.ginc_ofs[rb.y] + atomicAdd(&L.ginc_cur[rb.y], 1)] = g;
+    // (group, its priority): the colouring rounds compare priorities without a second dependent load
+    const unsigned is = (unsigned)L.row_island[g];
+    const int2 e = make_int2(g, (int)odebi_canon_key(D.seed[0], is, 0u, (unsigned)(g - L.isl_rstart[is])));
+    L.ginc[L.ginc_ofs[rb.x] + atomicAdd(&L.ginc_cur[rb.x], 1)] = e;
+    if (rb.y != P.NB) L.ginc[L.ginc_ofs[rb.y] + atomicAdd(&L.ginc_cur[rb.y], 1)] = e;
 }
 
 // Colouring of one phase (see oracle/orc_world.cpp canonical_order: the same rounds).  A group is "above" another one when its
-// (key, first row) is larger.  Round = k_lwc_mark (every uncoloured group that has no uncoloured neighbour above it wins; reads only
-// colours of earlier rounds) + k_lwc_assign (winners, never neighbours of each other, take the smallest colour none of their coloured
-// neighbours holds): the result does not depend on thread timing.
+// (key, first row) is larger.  Round = mark (every uncoloured group that has no uncoloured neighbour above it wins; reads only
+// colours of earlier rounds) + assign (winners, never neighbours of each other, take the smallest colour none of their coloured
+// neighbours holds): the result does not depend on thread timing (k_lwc_color_rounds).
 __global__ void k_lwc_color_init(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L)
 {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -372,51 +416,83 @@ __global__ void k_lwc_color_init(const __grid_constant__ DevParams P, const __gr
     L.gcolor[g] = -1;
     atomicAdd(&L.counters[LWC_UNCOLORED], 1);
 }
-__global__ void k_lwc_mark(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L)
+// all rounds of the colouring in ONE cooperative launch (grid barrier between mark and assign): a round is two passes over the groups that
+// still matter, and as separate launches the ~30 rounds of a wall cost 64 launches of ~14 us each plus a host round trip every 8 rounds
+__device__ __forceinline__ void lwc_grid_sync(unsigned *bar, unsigned &target)
 {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= L.counters[LWC_NGROUPS]) return;
-    const int g = L.heads[t];
-    if (L.gcolor[g] != -1) { L.gwin[g] = 0; return; }
-    const unsigned kg = L.gkey[g];
-    const int2 rb = D.rbody[g];
-    bool top = true;
-    for (int side = 0; side < 2 && top; side++) {
-        const int b = side ? rb.y : rb.x;
-        if (b == P.NB) continue;
-        for (int e = L.ginc_ofs[b], e1 = L.ginc_ofs[b + 1]; e < e1; e++) {
-            const int h = L.ginc[e];
-            if (h == g || L.gcolor[h] != -1) continue;
-            const unsigned kh = L.gkey[h];
-            if (kh > kg || (kh == kg && h > g)) { top = false; break; }
-        }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        __threadfence();
+        atomicAdd(bar, 1u);
+        unsigned v;
+        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory"); } while ((int)(v - target) < 0);
     }
-    L.gwin[g] = top ? 1 : 0;
+    __syncthreads();
 }
-__global__ void k_lwc_assign(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L)
+__global__ void __launch_bounds__(1024) k_lwc_color_rounds(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L)
 {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= L.counters[LWC_NGROUPS]) return;
-    const int g = L.heads[t];
-    if (!L.gwin[g]) return;
-    const int2 rb = D.rbody[g];
-    unsigned long long used = 0;
-    for (int side = 0; side < 2; side++) {
-        const int b = side ? rb.y : rb.x;
-        if (b == P.NB) continue;
-        for (int e = L.ginc_ofs[b], e1 = L.ginc_ofs[b + 1]; e < e1; e++) {
-            const int c = L.gcolor[L.ginc[e]];                 // winners of this round are never neighbours: every neighbour's colour is final or -1
-            if (c >= 0 && c < 64) used |= 1ull << c;
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, GT = gridDim.x * blockDim.x;
+    const int ng = L.counters[LWC_NGROUPS];
+    unsigned *gbar = (unsigned *)&L.counters[LWC_GBAR];
+    unsigned target = 0;
+    for (int round = 0; round < (1 << 20); round++) {
+        // mark: every uncoloured group without an uncoloured neighbour above it wins (reads only colours of earlier rounds).  The neighbours
+        // of a side are examined four at a time: their colours are independent loads (one exposed L2 latency per four neighbours)
+        for (int t = gtid; t < ng; t += GT) {
+            const int g = L.heads[t];
+            if (__ldcg(&L.gcolor[g]) != -1) continue;
+            const unsigned kg = L.gkey[g];
+            const int2 rb = D.rbody[g];
+            bool top = true;
+            for (int side = 0; side < 2 && top; side++) {
+                const int b = side ? rb.y : rb.x;
+                if (b == P.NB) continue;
+                const int e1 = L.ginc_ofs[b + 1];
+                for (int e = L.ginc_ofs[b]; e < e1 && top; e += 4) {
+                    int2 h[4]; int c[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) h[k] = e + k < e1 ? L.ginc[e + k] : make_int2(g, 0);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) c[k] = h[k].x != g ? __ldcg(&L.gcolor[h[k].x]) : 0;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) if (h[k].x != g && c[k] == -1 && ((unsigned)h[k].y > kg || ((unsigned)h[k].y == kg && h[k].x > g))) top = false;
+                }
+            }
+            __stcg(&L.gwin[g], top ? 1 : 0);
         }
+        lwc_grid_sync(gbar, target);
+        // assign: the winners (never neighbours of each other) take the smallest colour none of their coloured neighbours holds
+        for (int t = gtid; t < ng; t += GT) {
+            const int g = L.heads[t];
+            if (__ldcg(&L.gcolor[g]) != -1 || !__ldcg(&L.gwin[g])) continue;
+            const int2 rb = D.rbody[g];
+            unsigned long long used = 0;
+            for (int side = 0; side < 2; side++) {
+                const int b = side ? rb.y : rb.x;
+                if (b == P.NB) continue;
+                const int e1 = L.ginc_ofs[b + 1];
+                for (int e = L.ginc_ofs[b]; e < e1; e += 4) {
+                    int c[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) c[k] = e + k < e1 ? __ldcg(&L.gcolor[L.ginc[e + k].x]) : -1;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) if (c[k] >= 0 && c[k] < 64) used |= 1ull << c[k];
+                }
+            }
+            int c = 0;
+            while (c < 63 && ((used >> c) & 1ull)) c++;
+            if (c >= 63) atomicExch(D.overflow, 4);
+            __stcg(&L.gcolor[g], c);
+            atomicSub(&L.counters[LWC_UNCOLORED], 1);
+            atomicMax(&L.counters[LWC_NCOLORS], c + 1);
+            atomicAdd(&L.ccount[c], 1);
+        }
+        lwc_grid_sync(gbar, target);
+        if (__ldcg(&L.counters[LWC_UNCOLORED]) <= 0) break;
     }
-    int c = 0;
-    while (c < 63 && ((used >> c) & 1ull)) c++;
-    if (c >= 63) atomicExch(D.overflow, 4);                    // a body with more than 62 groups: beyond the colour mask
-    L.gcolor[g] = c;
-    atomicSub(&L.counters[LWC_UNCOLORED], 1);
-    atomicMax(&L.counters[LWC_NCOLORS], c + 1);
-    atomicAdd(&L.ccount[c], 1);
 }
+
 __device__ __forceinline__ Real4 ldcg4(const Real4 *p)
 {
 #if defined(ODEB_DOUBLE)
@@ -695,18 +771,6 @@ struct LwPhase {
     int nordered, nislands;
     unsigned iteration, extra;
 };
-__device__ __forceinline__ void lwt_grid_sync(unsigned *bar, unsigned &target)
-{
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        target += gridDim.x;
-        __threadfence();
-        atomicAdd(bar, 1u);
-        unsigned v;
-        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory"); } while ((int)(v - target) < 0);
-    }
-    __syncthreads();
-}
 __global__ void __launch_bounds__(32 * LWT_WARPS) k_lwt_phase(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L, const __grid_constant__ LwPhase ph)
 {
     extern __shared__ __align__(128) unsigned char lwt_smem[];
@@ -812,7 +876,7 @@ __global__ void __launch_bounds__(32 * LWT_WARPS) k_lwt_phase(const __grid_const
                     if (it_sw < 8) tile_begin(it_tile);
                 }
             }
-            lwt_grid_sync(gbar, gtarget);
+            lwc_grid_sync(gbar, gtarget);
         }
         // ---- end of the sweep: iteration control quickstep.cpp:1832-1855, :3253-3285 (k_lw_body_check + k_lw_island_ctl)
         ++iteration;
@@ -830,7 +894,7 @@ __global__ void __launch_bounds__(32 * LWT_WARPS) k_lwt_phase(const __grid_const
                 v.z = 0; v.w = 0;
                 stcg4(&cf[2 * k + 1], v);
             }
-            lwt_grid_sync(gbar, gtarget);
+            lwc_grid_sync(gbar, gtarget);
         }
         for (int is = gtid; is < ph.nislands; is += GT) {
             if (__ldcg(&L.isl_done[is])) continue;
@@ -851,7 +915,7 @@ __global__ void __launch_bounds__(32 * LWT_WARPS) k_lwt_phase(const __grid_const
             if (done) { __stcg(&L.isl_done[is], 1); atomicSub(&L.counters[LWC_NACTIVE], 1); }
             else if (iteration >= 8 && (iteration & 7) == 0) atomicAdd(&L.draws[0], (u64)(m - 1));
         }
-        lwt_grid_sync(gbar, gtarget);
+        lwc_grid_sync(gbar, gtarget);
         if (terminate_all) { terminated = 1; break; }
         if (__ldcg(&L.counters[LWC_NACTIVE]) == 0) break;
     }

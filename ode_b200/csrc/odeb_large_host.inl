@@ -26,7 +26,7 @@ static int large_prepare(OdebBatch *B)
     LargePtrs &L = B->L;
     const size_t NB = P.NB, NG = P.NG > 0 ? P.NG : 1, MP = P.MP, MR = P.MR, NJT = P.NJT;
     bool ok = dev_alloc(B, &L.counters, LWC_COUNT) && dev_alloc(B, &L.draws, 4)
-           && dev_alloc(B, &L.bp_key, NG) && dev_alloc(B, &L.bp_key_s, NG) && dev_alloc(B, &L.bp_idx, NG) && dev_alloc(B, &L.bp_idx_s, NG) && dev_alloc(B, &L.bp_big, NG)
+           && dev_alloc(B, &L.bp_key, NG) && dev_alloc(B, &L.bp_key_s, NG) && dev_alloc(B, &L.bp_idx, NG) && dev_alloc(B, &L.bp_idx_s, NG) && dev_alloc(B, &L.bp_big, NG) && dev_alloc(B, &L.bp_yz, NG)
            && dev_alloc(B, &L.pair_key, MP) && dev_alloc(B, &L.pair_key_s, MP) && dev_alloc(B, &L.pc_base, MP)
            && dev_alloc(B, &L.parent, NB) && dev_alloc(B, &L.maxen, NB) && dev_alloc(B, &L.head_scan, NB) && dev_alloc(B, &L.deg, NB)
            && dev_alloc(B, &L.bkey, NB) && dev_alloc(B, &L.bkey_s, NB) && dev_alloc(B, &L.bval, NB)
@@ -80,9 +80,10 @@ static int large_step(OdebBatch *B)
         k_aabb<<<nblk(NG, 128), 128, 0, s>>>(P, D);
         k_bp_keys<<<nblk(NG, 128), 128, 0, s>>>(P, D, L);
         LCK(cub::DeviceRadixSort::SortPairs(L.tmp, L.tmp_bytes, L.bp_key, L.bp_key_s, L.bp_idx, L.bp_idx_s, NG, 0, 32, s));
+        k_bp_gather<<<nblk(NG, 256), 256, 0, s>>>(P, D, L);
         k_bp_sweep<<<nblk(NG, 64), 64, 0, s>>>(P, D, L);
         k_bp_big<<<nblk(NG, 128), 128, 0, s>>>(P, D, L);
-        B->launches += 5;
+        B->launches += 6;
         LCK(cudaMemcpyAsync(hc, L.counters, sizeof(hc), cudaMemcpyDeviceToHost, s));
         LCK(cudaStreamSynchronize(s));
         np = hc[LWC_NPAIRS];
@@ -123,7 +124,7 @@ static int large_step(OdebBatch *B)
     LCK(cub::DeviceScan::InclusiveSum(L.tmp, L.tmp_bytes, L.deg, L.head_scan, NB, s));
     k_lw_label<<<nblk(NB, 256), 256, 0, s>>>(P, D, L);
     k_lw_iota<<<nblk(NB, 256), 256, 0, s>>>(NB, L.bval);
-    LCK(cub::DeviceRadixSort::SortPairs(L.tmp, L.tmp_bytes, L.bkey, L.bkey_s, L.bval, D.body_order, NB, 0, 64, s));
+    LCK(cub::DeviceRadixSort::SortPairs(L.tmp, L.tmp_bytes, L.bkey, L.bkey_s, L.bval, D.body_order, NB, 0, 32 + bits_for((unsigned)NB), s));   // island numbers are below NB; unordered bodies carry all-ones keys: last either way
     k_lw_body_pos<<<nblk(NB, 256), 256, 0, s>>>(P, D, L);
     k_lw_joint_keys<<<nblk(P.NJT, 256), 256, 0, s>>>(P, D, L);
     B->launches += 8;
@@ -135,7 +136,7 @@ static int large_step(OdebBatch *B)
     LCK(cub::DeviceScan::ExclusiveSum(L.tmp, L.tmp_bytes, L.isl_m, L.isl_rstart, NB + 1, s));
     B->launches += 2;
     if (nj > 0) {
-        LCK(cub::DeviceRadixSort::SortPairs(L.tmp, L.tmp_bytes, L.jkey, L.jkey_s, L.jmv, L.jmv_s, nj, 0, 64, s));
+        LCK(cub::DeviceRadixSort::SortPairs(L.tmp, L.tmp_bytes, L.jkey, L.jkey_s, L.jmv, L.jmv_s, nj, 0, 32 + bits_for((unsigned)(T > 0 ? T : 1)), s));   // unordered joints carry all-ones keys: last either way
         LCK(cub::DeviceScan::ExclusiveSum(L.tmp, L.tmp_bytes, L.jmv_s, L.jrow, nj, s));
         B->launches += 2;
     }
@@ -169,16 +170,20 @@ static int large_step(OdebBatch *B)
         LCK(cudaMemsetAsync(L.counters + LWC_UNCOLORED, 0, 2 * sizeof(int), s));
         k_lwc_color_init<<<nblk(ngroups > 64 ? ngroups : 64, 256), 256, 0, s>>>(P, D, L);
         B->launches++;
-        for (int guard = 0; guard < 4096; guard++) {
-            for (int k = 0; k < 8; k++) {
-                k_lwc_mark<<<nblk(ngroups, 256), 256, 0, s>>>(P, D, L);
-                k_lwc_assign<<<nblk(ngroups, 256), 256, 0, s>>>(P, D, L);
+        {
+            if (B->lwc_grid == 0) {
+                int occ = 0, sms = 0;
+                LCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_lwc_color_rounds, 1024, 0));
+                LCK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, B->device));
+                B->lwc_grid = occ * sms;
+                if (B->lwc_grid <= 0) { set_err("k_lwc_color_rounds does not fit an SM"); return 0; }
             }
-            B->launches += 16;
-            int left = 0;
-            LCK(cudaMemcpyAsync(&left, L.counters + LWC_UNCOLORED, sizeof(left), cudaMemcpyDeviceToHost, s));
-            LCK(cudaStreamSynchronize(s));
-            if (left <= 0) break;
+            int grid = nblk(ngroups, 1024);                    // few, large blocks: the grid barrier costs one atomic per block
+            if (grid > B->lwc_grid) grid = B->lwc_grid;
+            LCK(cudaMemsetAsync(L.counters + LWC_GBAR, 0, sizeof(int), s));
+            void *args[3] = { (void *)&P, (void *)&D, (void *)&L };
+            LCK(cudaLaunchCooperativeKernel((const void *)k_lwc_color_rounds, dim3(grid), dim3(1024), args, 0, s));
+            B->launches++;
         }
         // tiles: groups by (colour, rows descending), 32 per tile; records and lambdas into the lane-interleaved layout
         int tstart[65];
