@@ -58,7 +58,8 @@ struct LargePtrs {
     int *clist, *ccount, *cofs, *tstart;         // [MR] groups by (colour, rows descending); [64] groups per colour; [65] first list position / first tile of every colour
     int *theight, *tbase, *tgroup;               // [MR/32 + 130] rows of a tile, its first tile row; [MR + 4160] first row of the group of every tile lane (-1: none)
     int4 *tginfo;                                // [MR + 4160] beside tgroup: (rows, accumulator slot of body 1, of body 2, island)
-    Real4 *trec; Real *tlam;                     // [trcap * 8 * 32], [trcap * 32]: lane-interleaved records / lambdas of all tile rows
+    unsigned char *trec;                         // [trcap * LWT_ROW_BYTES]: per tile row the lane-interleaved compact records (LWT_QUADS x 32 quads), then the 32 lambdas
+    Real *pinvm;                                 // [NB + 1] inverse mass by body order position
     int trcap;                                   // tile rows the two buffers hold
     void *tmp; size_t tmp_bytes;                 // cub scratch
 };
@@ -380,11 +381,15 @@ __global__ void k_lwc_groups(const __grid_constant__ DevParams P, const __grid_c
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= mrows) return;
     D.lambda[r] = 0;
+    // the body order positions travel in the last two words of the half-built record (k_rows_t<false>)
+    const Real4 last = D.rows[(size_t)r * 8 + 7];
+    const int p0 = *(const int *)&last.z, p1 = *(const int *)&last.w;
+    const int2 rb = make_int2(p0, p1 == -1 ? P.NB : p1);         // one-body rows address the dummy accumulator slot NB
+    D.rbody[r] = rb;
     const int g = L.row_group[r];
     atomicAdd(&L.gsize[g], 1);
     if (g != r) return;
     L.heads[atomicAdd(&L.counters[LWC_NGROUPS], 1)] = r;
-    const int2 rb = D.rbody[r];
     atomicAdd(&L.ginc_cur[rb.x], 1);
     if (rb.y != P.NB) atomicAdd(&L.ginc_cur[rb.y], 1);
 }
@@ -425,8 +430,9 @@ __device__ __forceinline__ void lwc_grid_sync(unsigned *bar, unsigned &target)
         target += gridDim.x;
         __threadfence();
         atomicAdd(bar, 1u);
-        unsigned v;
-        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory"); } while ((int)(v - target) < 0);
+        unsigned v;                                               // relaxed polls (an acquire load invalidates the SM's L1 on every poll), one fence at the end
+        do { asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory"); } while ((int)(v - target) < 0);
+        __threadfence();
     }
     __syncthreads();
 }
@@ -515,9 +521,17 @@ __device__ __forceinline__ void stcg4(Real4 *p, const Real4 &v)
 
 // ---- tiles.  The groups are sorted by (colour, rows descending) and cut into TILES of 32 groups of one colour; a tile is as high as its
 // largest group.  The records of a tile are stored lane-interleaved in a second buffer: quad q (16 bytes) of row k of the tile's group
-// `lane` sits at trec[((tbase + k) * 8 + q) * 32 + lane], its lambda at tlam[(tbase + k) * 32 + lane].  The whole tile is ONE contiguous
-// block of HBM in exactly the order the sweep walks it, every warp access is a full 512-byte line set, and the colouring is fixed for
-// the step, so the layout is built once per step (k_lwt_gather) and the 40 sweeps stream it.
+// `lane` sits at quad (q * 32 + lane) of tile row tbase + k, its lambda behind the row's LWT_QUADS x 32 quads.  The whole tile is ONE
+// contiguous block of HBM in exactly the order the sweep walks it, every warp access is a full line set, and the colouring is fixed for
+// the step, so the layout is built once per step (k_lwt_finish) and the 40 sweeps stream it.
+// The tile record is COMPACT, 20 reals instead of the 32 of the batched kernels' record: the sweeps of a big world are bound by HBM
+// bandwidth, and 12 of the 32 reals (iMJ = invM * J^T) are cheap to recompute from the unscaled J and the two bodies' inverse mass /
+// inertia, which a lane loads once per group (L2 hits).  Every recomputed value comes out of the same expression on the same inputs as
+// in finish_row (compute_invM_JT quickstep.cpp:859-897, Ad scaling :2251-2316), so the bits are the same.
+//   c0 = J1l.xyz J1a.x | c1 = J1a.yz, rhs * Ad, cfm * Ad | c2 = J2l.xyz J2a.x | c3 = J2a.yz, lo, hi | c4 = Ad, row - findex, modmax 1, modmax 2
+#define LWT_QUADS 5
+#define LWT_ROW_BYTES (32 * LWT_QUADS * (int)sizeof(Real4) + 32 * (int)sizeof(Real))
+#define LWT_LAM_OFS (32 * LWT_QUADS * (int)sizeof(Real4))
 __global__ void k_lwt_sort_keys(const __grid_constant__ LargePtrs L)
 {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -555,25 +569,53 @@ __global__ void __launch_bounds__(128) k_lwt_tiles(const __grid_constant__ DevPa
     const int h = __reduce_max_sync(0xffffffffu, gi.x);
     if (lane == 0) { L.theight[tile] = h; if (tile == 0) L.theight[L.counters[LWC_NTILES]] = 0; }
 }
-// one block per tile: the records into the interleaved layout (friction rows carry `row - findex` in the spare last word), lambda = 0
-__global__ void __launch_bounds__(128) k_lwt_gather(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L)
+// one block per tile: Stage2c + compute_invM_JT + Ad (finish_row's arithmetic) of the half-built records k_rows_t<false> left, written as
+// compact tile records; lambda = 0; the bodies' inverse masses by order position for the sweeps
+__global__ void __launch_bounds__(128) k_lwt_finish(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L)
 {
     const int tile = blockIdx.x, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int base = L.tbase[tile];
     if (base + L.theight[tile] > L.trcap) { if (threadIdx.x == 0) atomicExch(D.overflow, 3); return; }
     const int g = L.tgroup[(size_t)tile * 32 + lane];
-    const int sz = g >= 0 ? L.gsize[g] : 0;
+    if (g < 0) return;
+    const int4 gi = L.tginfo[(size_t)tile * 32 + lane];
+    const int sz = gi.x;
+    const bool two = gi.z != P.NB;
+    Real in0[6], invI0[12], im0, in1[6], invI1[12], im1 = 0;
+    body_rhs_tmp(P, D, 0, gi.y, in0, invI0, &im0);
+    if (two) body_rhs_tmp(P, D, 0, gi.z, in1, invI1, &im1);
+    if (wib == 0) { L.pinvm[gi.y] = im0; if (two) L.pinvm[gi.z] = im1; }
     for (int k = wib; k < sz; k += 4) {
         const Real4 *src = D.rows + (size_t)(g + k) * 8;
-        Real4 v[8];
-#pragma unroll
-        for (int q = 0; q < 8; q++) v[q] = ldcg4(src + q);
+        const Real4 v0 = ldcg4(src), v1 = ldcg4(src + 1), v2 = ldcg4(src + 2), v3 = ldcg4(src + 3);
+        const Real q[16] = { v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w };
+        Real imj[14];
+        Real sum = R_(0.0);
+        for (int c = 0; c < 6; c++) sum += q[C_J1L + c] * in0[c];
+        for (int c = 0; c < 3; c++) imj[c] = im0 * q[C_J1L + c];
+        mul0_331(imj + 3, invI0, q + C_J1A);
+        imj[6] = P.dyn_enabled ? modmax6(imj) : R_(0.0);
+        for (int c = 7; c < 14; c++) imj[c] = 0;
+        if (two) {
+            for (int c = 0; c < 6; c++) sum += q[C_J2L + c] * in1[c];
+            for (int c = 0; c < 3; c++) imj[7 + c] = im1 * q[C_J2L + c];
+            mul0_331(imj + 10, invI1, q + C_J2A);
+            imj[13] = P.dyn_enabled ? modmax6(imj + 7) : R_(0.0);
+        }
+        const Real rhs = q[C_RHS] + sum;
+        Real s2 = R_(0.0);
+        for (int c = 0; c < 6; c++) s2 += imj[c] * q[C_J1L + c];
+        if (two) for (int c = 0; c < 6; c++) s2 += imj[7 + c] * q[C_J2L + c];
+        const Real cfm_i = q[C_CFM];
+        const Real Ad = P.sor_w / (s2 + cfm_i);
         const int fi = D.findex[g + k];
-        *(int *)&v[7].w = fi == -1 ? 0 : g + k - fi;
-        Real4 *dst = L.trec + ((size_t)(base + k) * 8) * 32 + lane;
-#pragma unroll
-        for (int q = 0; q < 8; q++) dst[q * 32] = v[q];
-        L.tlam[(size_t)(base + k) * 32 + lane] = 0;
+        Real4 c1 = v1, c4 = { Ad, 0, imj[6], imj[13] };
+        c1.z = rhs * Ad; c1.w = cfm_i * Ad;
+        *(int *)&c4.y = fi == -1 ? 0 : g + k - fi;
+        unsigned char *trow = L.trec + (size_t)(base + k) * LWT_ROW_BYTES;
+        Real4 *dst = (Real4 *)trow + lane;
+        dst[0] = v0; dst[32] = c1; dst[64] = v2; dst[96] = v3; dst[128] = c4;
+        ((Real *)(trow + LWT_LAM_OFS))[lane] = 0;
     }
 }
 // feedback only: the final lambdas back in row order
@@ -583,96 +625,49 @@ __global__ void __launch_bounds__(128) k_lwt_lambda_out(const __grid_constant__ 
     const int base = L.tbase[tile];
     const int g = L.tgroup[(size_t)tile * 32 + lane];
     const int sz = g >= 0 ? L.gsize[g] : 0;
-    for (int k = wib; k < sz; k += 4) D.lambda[g + k] = L.tlam[(size_t)(base + k) * 32 + lane];
+    for (int k = wib; k < sz; k += 4) D.lambda[g + k] = ((const Real *)(L.trec + (size_t)(base + k) * LWT_ROW_BYTES + LWT_LAM_OFS))[lane];
 }
 
-// The row update (Stage4LCP_IterationStep quickstep.cpp:2917-3033) of one row of a group whose two bodies' accumulators are in registers.
-// `fd` = row - findex (0: none); the row it points at is an earlier row of the same group (findex is joint-local), normally the latest
-// row without a friction index, whose new lambda is kept in a register.
-#define LWT_ROW(A0, A1, A2, A3, B0, B1, B2, B3, OLD, K)                                                                   \
+// The row update (Stage4LCP_IterationStep quickstep.cpp:2917-3033) of one row of a group whose two bodies' accumulators, inverse masses
+// and inverse inertias are in registers, from the compact tile record C0..C4.  `fd` = row - findex (0: none); the row it points at is an
+// earlier row of the same group (findex is joint-local), normally the latest row without a friction index, whose new lambda is kept in a
+// register.
+#define LWT_ROW(C0, C1, C2, C3, C4, OLD, K)                                                                              \
     {                                                                                                                    \
-        const int fd = *(const int *)&(B3).w;                                                                            \
-        Real delta = (A1).z - (OLD) * (A1).w;                                                                            \
-        delta -= f1a.x * (A0).x + f1a.y * (A0).y + f1a.z * (A0).z + f1a.w * (A0).w + f1b.x * (A1).x + f1b.y * (A1).y;    \
-        if (two) delta -= f2a.x * (B0).x + f2a.y * (B0).y + f2a.z * (B0).z + f2a.w * (B0).w + f2b.x * (B1).x + f2b.y * (B1).y; \
+        const Real Ad = (C4).x;                                                                                          \
+        const int fd = *(const int *)&(C4).y;                                                                            \
+        const Real ja1[3] = { (C0).w, (C1).x, (C1).y };                                                                  \
+        Real ma1[3];                                                                                                     \
+        mul0_331(ma1, invI0, ja1);                                                                                       \
+        Real delta = (C1).z - (OLD) * (C1).w;                                                                            \
+        delta -= f1a.x * ((C0).x * Ad) + f1a.y * ((C0).y * Ad) + f1a.z * ((C0).z * Ad) + f1a.w * ((C0).w * Ad) + f1b.x * ((C1).x * Ad) + f1b.y * ((C1).y * Ad); \
+        Real ma2[3] = { 0, 0, 0 };                                                                                       \
+        if (two) {                                                                                                       \
+            const Real ja2[3] = { (C2).w, (C3).x, (C3).y };                                                              \
+            mul0_331(ma2, invI1, ja2);                                                                                   \
+            delta -= f2a.x * ((C2).x * Ad) + f2a.y * ((C2).y * Ad) + f2a.z * ((C2).z * Ad) + f2a.w * ((C2).w * Ad) + f2b.x * ((C3).x * Ad) + f2b.y * ((C3).y * Ad); \
+        }                                                                                                                \
         Real hi_act, lo_act;                                                                                             \
-        if (fd != 0) { hi_act = RFABS((B1).w * ((K) - fd == free_k ? free_lambda : lamp[(size_t)((K) - fd) * 32])); lo_act = -hi_act; } \
-        else { hi_act = (B1).w; lo_act = (B1).z; }                                                                       \
+        if (fd != 0) { hi_act = RFABS((C3).w * ((K) - fd == free_k ? free_lambda : __ldcg((const Real *)(lamp + (size_t)((K) - fd) * LWT_ROW_BYTES)))); lo_act = -hi_act; } \
+        else { hi_act = (C3).w; lo_act = (C3).z; }                                                                       \
         Real new_lambda = (OLD) + delta;                                                                                 \
         if (new_lambda < lo_act) { delta = lo_act - (OLD); new_lambda = lo_act; }                                        \
         else if (new_lambda > hi_act) { delta = hi_act - (OLD); new_lambda = hi_act; }                                   \
-        lamp[(size_t)(K) * 32] = new_lambda;                                                                             \
+        *(Real *)(lamp + (size_t)(K) * LWT_ROW_BYTES) = new_lambda;                                                      \
         if (fd == 0) { free_k = (K); free_lambda = new_lambda; }                                                         \
         if (delta != 0) {                                                                                                \
-            f1a.x += delta * (A2).x; f1a.y += delta * (A2).y; f1a.z += delta * (A2).z; f1a.w += delta * (A2).w;          \
-            f1b.x += delta * (A3).x; f1b.y += delta * (A3).y;                                                            \
-            if (delta > 0) f1b.w += delta * (A3).z; else f1b.z += delta * (A3).z;                                        \
+            f1a.x += delta * (im0 * (C0).x); f1a.y += delta * (im0 * (C0).y); f1a.z += delta * (im0 * (C0).z); f1a.w += delta * ma1[0]; \
+            f1b.x += delta * ma1[1]; f1b.y += delta * ma1[2];                                                            \
+            if (delta > 0) f1b.w += delta * (C4).z; else f1b.z += delta * (C4).z;                                        \
             if (two) {                                                                                                   \
-                if (delta > 0) f2b.w += delta * (B3).z; else f2b.z += delta * (B3).z;                                    \
-                f2a.x += delta * (B2).x; f2a.y += delta * (B2).y; f2a.z += delta * (B2).z; f2a.w += delta * (B2).w;      \
-                f2b.x += delta * (B3).x; f2b.y += delta * (B3).y;                                                        \
+                if (delta > 0) f2b.w += delta * (C4).w; else f2b.z += delta * (C4).w;                                    \
+                f2a.x += delta * (im1 * (C2).x); f2a.y += delta * (im1 * (C2).y); f2a.z += delta * (im1 * (C2).z); f2a.w += delta * ma2[0]; \
+                f2b.x += delta * ma2[1]; f2b.y += delta * ma2[2];                                                        \
             }                                                                                                            \
         }                                                                                                                \
     }
 
-// One colour of one sweep, register variant: a warp per tile, a lane per group; the lane walks its group's rows with the two bodies'
-// accumulators in registers, its records arrive through fully coalesced loads (the 32 lanes read 512 consecutive bytes per instruction)
-// issued LWT_AHEAD rows ahead.  No other group of the colour touches these bodies: bit-identical to the sequential sweep.
-#if defined(ODEB_DOUBLE)
-#define LWT_AHEAD 1
-#else
-#define LWT_AHEAD 2
-#endif
-__global__ void __launch_bounds__(128) k_lwt_sweep(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L, int tile0, int ntiles)
-{
-    const int wt = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-    if (wt >= ntiles) return;
-    const int tile = tile0 + wt;
-    const int4 gi = L.tginfo[(size_t)tile * 32 + lane];
-    const int sz = gi.x;
-    if (sz == 0) return;                                           // (no warp-level primitive below)
-    const int base = L.tbase[tile];
-    const Real4 *rec = L.trec + (size_t)base * 8 * 32 + lane;
-    Real *lamp = L.tlam + (size_t)base * 32 + lane;
-    constexpr int NBUF = LWT_AHEAD + 1;
-    Real4 q[NBUF][8]; Real ol[NBUF];
-#pragma unroll
-    for (int j = 0; j < LWT_AHEAD; j++) if (j < sz) {
-#pragma unroll
-        for (int c = 0; c < 8; c++) q[j][c] = ldcg4(rec + ((size_t)j * 8 + c) * 32);
-        ol[j] = __ldcg(lamp + (size_t)j * 32);
-    }
-    const bool two = gi.z != P.NB;
-    Real4 *cf = D.cforce;
-    Real4 f1a = ldcg4(&cf[2 * gi.y]), f1b = ldcg4(&cf[2 * gi.y + 1]);
-    Real4 f2a = { 0, 0, 0, 0 }, f2b = f2a;
-    if (two) { f2a = ldcg4(&cf[2 * gi.z]); f2b = ldcg4(&cf[2 * gi.z + 1]); }
-    if (L.isl_done[gi.w]) return;
-    int free_k = -1; Real free_lambda = 0;
-    for (int k0 = 0; k0 < sz; k0 += NBUF) {
-#pragma unroll
-        for (int j = 0; j < NBUF; j++) {
-            const int k = k0 + j;
-            if (k < sz) {
-                const int kn = k + LWT_AHEAD;                       // the row requested now lands in the buffer freed by row k - 1
-                if (kn < sz) {
-#pragma unroll
-                    for (int c = 0; c < 8; c++) q[(j + LWT_AHEAD) % NBUF][c] = ldcg4(rec + ((size_t)kn * 8 + c) * 32);
-                    ol[(j + LWT_AHEAD) % NBUF] = __ldcg(lamp + (size_t)kn * 32);
-                }
-                LWT_ROW(q[j][0], q[j][1], q[j][2], q[j][3], q[j][4], q[j][5], q[j][6], q[j][7], ol[j], k)
-            }
-        }
-    }
-    stcg4(&cf[2 * gi.y], f1a); stcg4(&cf[2 * gi.y + 1], f1b);
-    if (two) { stcg4(&cf[2 * gi.z], f2a); stcg4(&cf[2 * gi.z + 1], f2b); }
-}
-
-// One colour of one sweep, TMA variant: the same walk, but the tile rows (32 lanes x 8 quads = 4 KB single / 8 KB double, one contiguous
-// block) are brought into a per-warp ring of shared-memory stages by cp.async.bulk, one copy for the records and one for the 32 lambdas
-// of a tile row, issued by lane 0 LWT_STAGES - 1 rows ahead and completing on the stage's mbarrier: no register and no LSU instruction is
-// spent on the fetch, and the prefetch distance does not cost registers.  The lanes read their quads from the stage (conflict-free:
-// consecutive lanes, consecutive 16-byte words).
+// cp.async.bulk + mbarrier plumbing of the sweep kernel's per-warp ring
 __device__ __forceinline__ void lwt_mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
 __device__ __forceinline__ void lwt_mbar_expect_tx(unsigned bar, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
 __device__ __forceinline__ void lwt_bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar)
@@ -683,80 +678,13 @@ __device__ __forceinline__ void lwt_mbar_wait(unsigned bar, unsigned parity)
 {
     asm volatile("{\n\t.reg .pred p;\n\tLWT_WAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra LWT_DONE_%=;\n\tbra LWT_WAIT_%=;\n\tLWT_DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
-#define LWT_STAGES 4
+#define LWT_STAGES 6
 #if defined(ODEB_DOUBLE)
 #define LWT_WARPS 2
 #else
 #define LWT_WARPS 4
 #endif
-#define LWT_STAGE_BYTES (32 * 8 * (int)sizeof(Real4) + 32 * (int)sizeof(Real))
-__global__ void __launch_bounds__(32 * LWT_WARPS) k_lwt_sweep_tma(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L, int tile0, int ntiles)
-{
-    extern __shared__ __align__(128) unsigned char lwt_smem[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int wt = blockIdx.x * LWT_WARPS + wib;
-    if (wt >= ntiles) return;
-    const int tile = tile0 + wt;
-    unsigned char *ring = lwt_smem + (size_t)wib * LWT_STAGES * LWT_STAGE_BYTES;
-    unsigned long long *bars = (unsigned long long *)(lwt_smem + (size_t)LWT_WARPS * LWT_STAGES * LWT_STAGE_BYTES) + wib * LWT_STAGES;
-    const unsigned bar0 = (unsigned)__cvta_generic_to_shared(bars);
-    const unsigned ring0 = (unsigned)__cvta_generic_to_shared(ring);
-    if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < LWT_STAGES; s++) lwt_mbar_init(bar0 + 8 * s, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-    const int height = L.theight[tile];
-    const int base = L.tbase[tile];
-    const Real4 *rec = L.trec + (size_t)base * 8 * 32;
-    Real *lam0 = L.tlam + (size_t)base * 32;
-    constexpr unsigned RB = 32 * 8 * (unsigned)sizeof(Real4), LB = 32 * (unsigned)sizeof(Real);
-    if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < LWT_STAGES - 1; s++) if (s < height) {
-            lwt_mbar_expect_tx(bar0 + 8 * s, RB + LB);
-            lwt_bulk_g2s(ring0 + s * LWT_STAGE_BYTES, rec + (size_t)s * 8 * 32, RB, bar0 + 8 * s);
-            lwt_bulk_g2s(ring0 + s * LWT_STAGE_BYTES + RB, lam0 + (size_t)s * 32, LB, bar0 + 8 * s);
-        }
-    }
-    const int4 gi = L.tginfo[(size_t)tile * 32 + lane];
-    const int sz = gi.x;
-    const bool two = gi.z != P.NB;
-    Real4 *cf = D.cforce;
-    Real4 f1a = { 0, 0, 0, 0 }, f1b = f1a, f2a = f1a, f2b = f1a;
-    bool run = false;
-    if (sz > 0) {
-        f1a = ldcg4(&cf[2 * gi.y]); f1b = ldcg4(&cf[2 * gi.y + 1]);
-        if (two) { f2a = ldcg4(&cf[2 * gi.z]); f2b = ldcg4(&cf[2 * gi.z + 1]); }
-        run = L.isl_done[gi.w] == 0;
-    }
-    Real *lamp = lam0 + lane;
-    int free_k = -1; Real free_lambda = 0;
-    for (int k = 0; k < height; k++) {
-        const int s = k % LWT_STAGES;
-        lwt_mbar_wait(bar0 + 8 * s, (unsigned)((k / LWT_STAGES) & 1));
-        if (run && k < sz) {
-            const Real4 *st = (const Real4 *)(ring + (size_t)s * LWT_STAGE_BYTES) + lane;
-            const Real4 a0 = st[0], a1 = st[32], a2 = st[64], a3 = st[96], b0 = st[128], b1q = st[160], b2q = st[192], b3 = st[224];
-            const Real old_lambda = ((const Real *)(ring + (size_t)s * LWT_STAGE_BYTES + RB))[lane];
-            LWT_ROW(a0, a1, a2, a3, b0, b1q, b2q, b3, old_lambda, k)
-        }
-        __syncwarp();                                              // every lane is done with the stage of row k - 1 ... and with this one's reads
-        const int kn = k + LWT_STAGES - 1;                         // refill the stage row k - 1 used
-        if (lane == 0 && kn < height) {
-            const int sn = kn % LWT_STAGES;
-            lwt_mbar_expect_tx(bar0 + 8 * sn, RB + LB);
-            lwt_bulk_g2s(ring0 + sn * LWT_STAGE_BYTES, rec + (size_t)kn * 8 * 32, RB, bar0 + 8 * sn);
-            lwt_bulk_g2s(ring0 + sn * LWT_STAGE_BYTES + RB, lam0 + (size_t)kn * 32, LB, bar0 + 8 * sn);
-        }
-    }
-    if (run) {
-        stcg4(&cf[2 * gi.y], f1a); stcg4(&cf[2 * gi.y + 1], f1b);
-        if (two) { stcg4(&cf[2 * gi.z], f2a); stcg4(&cf[2 * gi.z + 1], f2b); }
-    }
-}
-
+#define LWT_STAGE_BYTES LWT_ROW_BYTES
 // A whole PHASE (up to 8 sweeps: every colour in the phase's order, the per-body convergence test and the per-island iteration control
 // after each sweep) as one persistent cooperative launch.  ncu on the launch-per-colour version: a colour costs ~9 us however few tiles
 // it has (launch, tile lookup, first DRAM round trip, 12 dependent rows) and only ~8 us more for 46 MB of records -- latency, not
@@ -781,7 +709,7 @@ __global__ void __launch_bounds__(32 * LWT_WARPS) k_lwt_phase(const __grid_const
     unsigned long long *bars = (unsigned long long *)(lwt_smem + (size_t)LWT_WARPS * LWT_STAGES * LWT_STAGE_BYTES) + wib * LWT_STAGES;
     const unsigned bar0 = (unsigned)__cvta_generic_to_shared(bars);
     const unsigned ring0 = (unsigned)__cvta_generic_to_shared(ring);
-    constexpr unsigned RB = 32 * 8 * (unsigned)sizeof(Real4), LB = 32 * (unsigned)sizeof(Real);
+    constexpr unsigned RB = 32 * LWT_QUADS * (unsigned)sizeof(Real4), LB = 32 * (unsigned)sizeof(Real);
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < LWT_STAGES; s++) lwt_mbar_init(bar0 + 8 * s, 1);
@@ -797,20 +725,34 @@ __global__ void __launch_bounds__(32 * LWT_WARPS) k_lwt_phase(const __grid_const
     const int first_ci = it_ci, first_tile = it_tile;
     const bool any_items = first_ci < ph.norder;
     int height = 0, issued = 0; int4 gi = make_int4(0, 0, P.NB, 0);
-    const Real4 *rec = 0; Real *lam0 = 0;
+    unsigned char *rec = 0;
+    Real invI0[12], invI1[12], im0 = 0, im1 = 0;
+#pragma unroll
+    for (int c = 0; c < 12; c++) { invI0[c] = 0; invI1[c] = 0; }
     auto tile_begin = [&](int tile) {
         height = L.theight[tile];
         const int base = L.tbase[tile];
-        rec = L.trec + (size_t)base * 8 * 32;
-        lam0 = L.tlam + (size_t)base * 32;
+        rec = L.trec + (size_t)base * LWT_ROW_BYTES;
         gi = L.tginfo[(size_t)tile * 32 + lane];
+        // the two bodies' inverse inertia (world frame, k_body_pre) and inverse mass: constant during the solve
+        if (gi.x > 0) {
+            const Real4 *ii = (const Real4 *)(D.invIw + 12 * (size_t)gi.y);
+            const Real4 r0 = ii[0], r1 = ii[1], r2 = ii[2];
+            invI0[0] = r0.x; invI0[1] = r0.y; invI0[2] = r0.z; invI0[4] = r1.x; invI0[5] = r1.y; invI0[6] = r1.z; invI0[8] = r2.x; invI0[9] = r2.y; invI0[10] = r2.z;
+            im0 = L.pinvm[gi.y];
+            if (gi.z != P.NB) {
+                const Real4 *jj = (const Real4 *)(D.invIw + 12 * (size_t)gi.z);
+                const Real4 t0 = jj[0], t1 = jj[1], t2 = jj[2];
+                invI1[0] = t0.x; invI1[1] = t0.y; invI1[2] = t0.z; invI1[4] = t1.x; invI1[5] = t1.y; invI1[6] = t1.z; invI1[8] = t2.x; invI1[9] = t2.y; invI1[10] = t2.z;
+                im1 = L.pinvm[gi.z];
+            }
+        }
         issued = height < LWT_STAGES - 1 ? height : LWT_STAGES - 1;
         if (lane == 0) {
             for (int k = 0; k < issued; k++) {
                 const unsigned s = (ri + k) % LWT_STAGES;
                 lwt_mbar_expect_tx(bar0 + 8 * s, RB + LB);
-                lwt_bulk_g2s(ring0 + s * LWT_STAGE_BYTES, rec + (size_t)k * 8 * 32, RB, bar0 + 8 * s);
-                lwt_bulk_g2s(ring0 + s * LWT_STAGE_BYTES + RB, lam0 + (size_t)k * 32, LB, bar0 + 8 * s);
+                lwt_bulk_g2s(ring0 + s * LWT_STAGE_BYTES, rec + (size_t)k * LWT_ROW_BYTES, RB + LB, bar0 + 8 * s);
             }
         }
         ri += issued;
@@ -833,16 +775,16 @@ __global__ void __launch_bounds__(32 * LWT_WARPS) k_lwt_phase(const __grid_const
                     if (two) { f2a = ldcg4(&cf[2 * gi.z]); f2b = ldcg4(&cf[2 * gi.z + 1]); }
                     run = __ldcg(&L.isl_done[gi.w]) == 0;
                 }
-                Real *lamp = lam0 + lane;
+                unsigned char *lamp = rec + LWT_LAM_OFS + lane * sizeof(Real);
                 int free_k = -1; Real free_lambda = 0;
                 for (int k = 0; k < height; k++) {
                     const unsigned s = rc % LWT_STAGES;
                     lwt_mbar_wait(bar0 + 8 * s, (rc / LWT_STAGES) & 1u);
                     if (run && k < sz) {
                         const Real4 *st = (const Real4 *)(ring + (size_t)s * LWT_STAGE_BYTES) + lane;
-                        const Real4 a0 = st[0], a1 = st[32], a2 = st[64], a3 = st[96], b0 = st[128], b1q = st[160], b2q = st[192], b3 = st[224];
+                        const Real4 c0 = st[0], c1 = st[32], c2 = st[64], c3 = st[96], c4 = st[128];
                         const Real old_lambda = ((const Real *)(ring + (size_t)s * LWT_STAGE_BYTES + RB))[lane];
-                        LWT_ROW(a0, a1, a2, a3, b0, b1q, b2q, b3, old_lambda, k)
+                        LWT_ROW(c0, c1, c2, c3, c4, old_lambda, k)
                     }
                     rc++;
                     __syncwarp();
@@ -850,8 +792,7 @@ __global__ void __launch_bounds__(32 * LWT_WARPS) k_lwt_phase(const __grid_const
                         if (lane == 0) {
                             const unsigned sn = ri % LWT_STAGES;
                             lwt_mbar_expect_tx(bar0 + 8 * sn, RB + LB);
-                            lwt_bulk_g2s(ring0 + sn * LWT_STAGE_BYTES, rec + (size_t)issued * 8 * 32, RB, bar0 + 8 * sn);
-                            lwt_bulk_g2s(ring0 + sn * LWT_STAGE_BYTES + RB, lam0 + (size_t)issued * 32, LB, bar0 + 8 * sn);
+                            lwt_bulk_g2s(ring0 + sn * LWT_STAGE_BYTES, rec + (size_t)issued * LWT_ROW_BYTES, RB + LB, bar0 + 8 * sn);
                         }
                         ri++; issued++;
                     }

@@ -41,7 +41,7 @@ static int large_prepare(OdebBatch *B)
            && dev_alloc(B, &L.theight, MR / 32 + 130) && dev_alloc(B, &L.tbase, MR / 32 + 130) && dev_alloc(B, &L.tgroup, MR + 4160) && dev_alloc(B, &L.tginfo, MR + 4160);
     // tile rows: every row once, plus the padding of tiles whose groups differ in size (sorted by size: a few tile heights per colour)
     L.trcap = (int)((MR + MR / 4 + 32768 + 31) / 32);
-    ok = ok && dev_alloc(B, &L.trec, (size_t)L.trcap * 8 * 32) && dev_alloc(B, &L.tlam, (size_t)L.trcap * 32);
+    ok = ok && dev_alloc(B, &L.trec, (size_t)L.trcap * LWT_ROW_BYTES) && dev_alloc(B, &L.pinvm, NB + 1);
     if (!ok) return 0;
     L.tmp_bytes = large_cub_bytes(P);
     { unsigned char *t = 0; if (!dev_alloc(B, &t, L.tmp_bytes)) return 0; L.tmp = t; }
@@ -149,7 +149,6 @@ static int large_step(OdebBatch *B)
     if (hc[LWC_NJORD] > 0) { k_rows_t<false><<<nblk(hc[LWC_NJORD], 64), 64, 0, s>>>(P, D); B->launches++; }
     LCK(cudaMemsetAsync(D.cforce, 0, (size_t)(NB + 1) * 2 * sizeof(Real4), s));
     if (mrows > 0) {
-        k_rows_finish<<<nblk(mrows, 128), 128, 0, s>>>(P, D);
         // groups (rows of one geom pair's contacts / of one joint), their compact list and the body -> groups incidence (CSR): once per step
         LCK(cudaMemsetAsync(L.gsize, 0, (size_t)mrows * sizeof(int), s));
         LCK(cudaMemsetAsync(L.counters + LWC_NGROUPS, 0, 3 * sizeof(int), s));
@@ -164,7 +163,6 @@ static int large_step(OdebBatch *B)
         // ---------------- SOR sweeps
         cudaEvent_t e0 = 0, e1 = 0;
         if (B->timing) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s); }
-        Real exit_delta = P.premature_delta;
         unsigned iteration = 0, extra = 0;
         // the step's colouring: rounds in batches of 8, until no group is left uncoloured
         LCK(cudaMemsetAsync(L.counters + LWC_UNCOLORED, 0, 2 * sizeof(int), s));
@@ -197,14 +195,11 @@ static int large_step(OdebBatch *B)
         const unsigned step_seed = (unsigned)hc[LWC_SEED];
         k_lwt_tiles<<<nblk(ntiles * 32, 128), 128, 0, s>>>(P, D, L);
         LCK(cub::DeviceScan::ExclusiveSum(L.tmp, L.tmp_bytes, L.theight, L.tbase, ntiles + 1, s));
-        k_lwt_gather<<<ntiles, 128, 0, s>>>(P, D, L);
+        k_lwt_finish<<<ntiles, 128, 0, s>>>(P, D, L);
         B->launches += 6;
-        // ODEB_LW_SWEEP=1|2 (experiments): a launch per colour, register double buffer / TMA ring; 3 (default): persistent phases
-        const int lw_variant = B->lw_variant;
         const size_t lw_tma_smem = (size_t)LWT_WARPS * LWT_STAGES * LWT_STAGE_BYTES + (size_t)LWT_WARPS * LWT_STAGES * sizeof(unsigned long long);
-        if (lw_variant == 2) cudaFuncSetAttribute(k_lwt_sweep_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lw_tma_smem);
         int corder[64];
-        if (lw_variant == 3) {
+        {
             // persistent phases: one cooperative launch per 8 sweeps
             if (B->lw_grid == 0) {
                 cudaFuncSetAttribute(k_lwt_phase, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lw_tma_smem);
@@ -238,38 +233,6 @@ static int large_step(OdebBatch *B)
                 iteration = (unsigned)hc[LWC_ITER]; extra = (unsigned)hc[LWC_EXTRA];
                 if (hc[LWC_TERM] || hc[LWC_NACTIVE] == 0) break;
             }
-        } else
-        for (;;) {
-            if ((iteration & 7) == 0) {
-                if (iteration > 0) {
-                    LCK(cudaMemcpyAsync(hc, L.counters, sizeof(hc), cudaMemcpyDeviceToHost, s));
-                    LCK(cudaStreamSynchronize(s));
-                    if (hc[LWC_NACTIVE] == 0) break;
-                }
-                // the phase's order of the colours (include/ode_b200.h: odebi_canon_colour_ranks)
-                int rank[64];
-                odebi_canon_colour_ranks(step_seed, iteration >> 3, rank);
-                for (int c = 0; c < 64; c++) corder[rank[c]] = c;
-            }
-            for (int k = 0; k < 64; k++) {
-                const int c = corder[k];
-                if (c >= ncolors) continue;
-                const int nt = tstart[c + 1] - tstart[c];
-                if (nt <= 0) continue;
-                if (lw_variant == 1) k_lwt_sweep<<<nblk(nt * 32, 128), 128, 0, s>>>(P, D, L, tstart[c], nt);
-                else k_lwt_sweep_tma<<<nblk(nt, LWT_WARPS), 32 * LWT_WARPS, lw_tma_smem, s>>>(P, D, L, tstart[c], nt);
-                B->launches++;
-            }
-            ++iteration;
-            int terminate_all = 0, in_extra = 0;
-            if (iteration - extra == P.num_iter) {          // quickstep.cpp:1832-1845
-                if (extra != 0 || P.max_extra == 0) { terminate_all = 1; in_extra = extra != 0; }
-                else { extra = P.max_extra; exit_delta = P.extra_delta; }
-            }
-            k_lw_body_check<<<nblk(nordered, 256), 256, 0, s>>>(P, D, L, exit_delta, (P.dyn_enabled && !terminate_all) ? 1 : 0);
-            k_lw_island_ctl<<<nblk(T, 256), 256, 0, s>>>(P, D, L, iteration, terminate_all, in_extra, exit_delta);
-            B->launches += 2;
-            if (terminate_all) break;
         }
         if (B->timing) { cudaEventRecord(e1, s); B->pending.push_back(std::make_pair(e0, e1)); }
         if (D.jcopy) { k_lwt_lambda_out<<<ntiles, 128, 0, s>>>(D, L); B->launches++; }
