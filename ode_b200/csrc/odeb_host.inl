@@ -31,7 +31,8 @@ struct OdebBatch {
     cudaGraphExec_t graph; double graph_h; bool use_graph; int graph_cfg;
     // solver selection: 0 = k_solve (one row at a time per world), 1..3 = k_solve5<2/4/8> (static P-processor schedule),
     // 4 = k_solve_bl (one lane per body). hint_m = largest island (rows) seen since the last sync, read back in odeb_sync.
-    int s5_sr[4]; size_t s5_smem[4]; int hint_m; int solver_force; int lw_variant, lw_grid, lwc_grid;   // s5_sr / s5_smem: row budget and shared memory of k_solve5<2^k> for the next launch
+    int s5_sr[4]; size_t s5_smem[4]; int hint_m; int solver_force; int lw_variant, lw_grid, lwc_grid;
+    bool env_no_solve6, env_no_hybrid, env_no_fused_rows; int env_hy_rows;   // experiment / test switches, read once at creation (ODEB_NO_SOLVE6, ODEB_NO_HYBRID, ODEB_NO_FUSED_ROWS, ODEB_TEST_HY_ROWS)   // s5_sr / s5_smem: row budget and shared memory of k_solve5<2^k> for the next launch
     int s6_sr, s6_nbi; size_t s6_smem;        // k_solve6<P> (odeb_solve6.cuh): row / body budget per island and shared memory per warp for the next launch
     int hint_nb, hint_nis;                    // largest island (bodies) and most islands with rows in one world seen so far
     int graph_sr; int graph_nlaunch;          // kernels per replay of the captured step (counted while capturing)
@@ -357,7 +358,7 @@ static OdebBatch *batch_build(const OdebWorldParams *wp, const HostTemplate &T, 
     OdebBatch *B = new OdebBatch();
     B->device = device; B->bytes = 0; B->launches = 0; B->timing = false; B->solver_ms = 0; B->solver_launches = 0;
     B->mode = ODEB_MODE_REPLAY; B->large_ready = false; memset(&B->L, 0, sizeof(B->L));
-    B->graph = 0; B->graph_h = -1; B->graph_cfg = -1; B->graph_sr = -1; B->hint_m = 0; B->hint_nb = 0; B->hint_nis = 0; B->s6_sr = 0; B->s6_nbi = 0; B->s6_smem = 0; B->solver_force = -1; B->lw_variant = getenv("ODEB_LW_SWEEP") ? atoi(getenv("ODEB_LW_SWEEP")) : 3; B->lw_grid = 0; B->lwc_grid = 0; B->use_graph = getenv("ODEB_NO_GRAPH") == 0 && !classic; B->h_stage = 0; B->h_ov = 0; B->fb_jcopy = 0; B->fb_jfb = 0; B->own_stream = true; B->d_stage = 0; B->stream = 0; B->flush_buf = 0; B->flush_bytes = 0;
+    B->graph = 0; B->graph_h = -1; B->graph_cfg = -1; B->graph_sr = -1; B->hint_m = 0; B->hint_nb = 0; B->hint_nis = 0; B->s6_sr = 0; B->s6_nbi = 0; B->s6_smem = 0; B->solver_force = -1; B->lw_variant = getenv("ODEB_LW_SWEEP") ? atoi(getenv("ODEB_LW_SWEEP")) : 3; B->lw_grid = 0; B->lwc_grid = 0; B->env_no_solve6 = getenv("ODEB_NO_SOLVE6") != 0; B->env_no_hybrid = getenv("ODEB_NO_HYBRID") != 0; B->env_no_fused_rows = getenv("ODEB_NO_FUSED_ROWS") != 0; B->env_hy_rows = getenv("ODEB_TEST_HY_ROWS") ? atoi(getenv("ODEB_TEST_HY_ROWS")) : 0; B->use_graph = getenv("ODEB_NO_GRAPH") == 0 && !classic; B->h_stage = 0; B->h_ov = 0; B->fb_jcopy = 0; B->fb_jfb = 0; B->own_stream = true; B->d_stage = 0; B->stream = 0; B->flush_buf = 0; B->flush_bytes = 0;
     memset(&B->D, 0, sizeof(B->D));
     DevParams &P = B->P;
     memset(&P, 0, sizeof(P));
@@ -823,8 +824,18 @@ int odeb_get_enabled(OdebBatch *B, int *enabled)
     return 1;
 }
 
+// Host-side NVTX ranges carrying the reference's own stage names (quickstep.cpp:569-575, :648-658, :784-800; util.cpp dxProcessIslands;
+// collision_space.cpp dSpaceCollide): a timeline of this library reads like a TIMING build of the reference.
+struct OdebRange {
+    bool open;
+    explicit OdebRange(const char *name) : open(true) { nvtxRangePushA(name); }
+    void end() { if (open) { nvtxRangePop(); open = false; } }
+    ~OdebRange() { end(); }
+};
+
 static void launch_collide(OdebBatch *B, cudaStream_t s, bool narrow)
 {
+    OdebRange nv_("dSpaceCollide + nearCallback (dCollide, dJointCreateContact)");
     const DevParams &P = B->P; const DevPtrs &D = B->D;
     const size_t W = P.W;
     if (P.NG <= 0) return;
@@ -919,7 +930,7 @@ static int choose_solver(OdebBatch *B)
     if (f >= 1 && f <= 3) return solve5_budget(B, f, need) > 0 ? f : 0;
     if (f >= 6 && f <= 9) return solve6_budget(B, f - 6) > 0 ? f : 0;
     if (B->hint_m <= 0) return 0;
-    if (B->hint_nis >= 2 && !getenv("ODEB_NO_SOLVE6")) {
+    if (B->hint_nis >= 2 && !B->env_no_solve6) {
         // worlds with several islands: independent walkers (odeb_solve6.cuh).  Measured on B200, 64-body piles, solver ms per step for
         // P = 1 / 2 / 4 / 8 processors per world: 4096 worlds with one large island each 12.0 / 11.2 / 8.1 / 8.6 (k_solve5<4>: 9.3),
         // 4096 settled piles (35 small islands per world) 6.6 / 6.9 / 6.4 / - (k_solve5<4>: 8.4), 16384 worlds - / 38.7 / 27.4 / 30.8.
@@ -934,7 +945,7 @@ static int choose_solver(OdebBatch *B)
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, B->device);
     const long long warps4 = ((long long)B->P.W + 3) / 4;
     if (warps4 * 2 <= 7LL * nsm || need > B->P.SR) { if (solve5_budget(B, 2, need) > 0) return 2; }
-    if (!getenv("ODEB_NO_HYBRID") && hybrid_ok(B, need)) return 5;     // large batches: see launch_dynamics, case 5
+    if (!B->env_no_hybrid && hybrid_ok(B, need)) return 5;     // large batches: see launch_dynamics, case 5
     return 0;
 }
 
@@ -943,16 +954,23 @@ static void launch_dynamics(OdebBatch *B, cudaStream_t s, bool timed, int cfg)
     const DevParams &P = B->P; const DevPtrs &D = B->D;
     const size_t W = P.W;
     if (D.jfb) cudaMemsetAsync(D.jfb, 0, W * P.NJT * 4 * sizeof(Real4), s);      // state 0 = joint not stepped
+    nvtxRangePushA("dxProcessIslands (auto-disable, island build) + dxQuickStepIsland_Stage0_Joints (getInfo1) + Stage1");
     if (P.NJ > 0) { k_joint_info1<<<nblk(W * P.NJ, 128), 128, 0, s>>>(P, D); B->launches++; }
     if (B->isl_one) k_islands_t<true, true><<<nblk(W * 32, 128), 128, B->isl_one_smem, s>>>(P, D);
     else if (B->isl_smem) k_islands_t<true, false><<<nblk(W, 32), 32, B->isl_smem, s>>>(P, D);
     else k_islands_t<false, false><<<nblk(W, 32), 32, 0, s>>>(P, D);
+    nvtxRangePop();
+    nvtxRangePushA("dxQuickStepIsland_Stage0_Bodies");
     k_body_pre<<<nblk(W * P.NB, 128), 128, 0, s>>>(P, D);
-    if (P.NJ == 0 && !D.row_island && !getenv("ODEB_NO_FUSED_ROWS")) { k_rows_t<true><<<nblk(W * P.NJT, 64), 64, 0, s>>>(P, D); B->launches--; }
+    nvtxRangePop();
+    nvtxRangePushA("dxQuickStepIsland_Stage2a/2b/2c (getInfo2, rhs) + Stage4LCP_iMJ + Stage4LCP_AdComputation");
+    if (P.NJ == 0 && !D.row_island && !B->env_no_fused_rows) { k_rows_t<true><<<nblk(W * P.NJT, 64), 64, 0, s>>>(P, D); B->launches--; }
     else {
         k_rows_t<false><<<nblk(W * P.NJT, 64), 64, 0, s>>>(P, D);
         k_rows_finish<<<nblk(W * P.MR, 128), 128, 0, s>>>(P, D);
     }
+    nvtxRangePop();
+    nvtxRangePushA("dxQuickStepIsland_Stage4LCP_ReorderPrep + Stage4LCP_Iteration (SOR sweeps)");
     cudaEvent_t e0 = 0, e1 = 0;
     if (timed) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s); }
     switch (cfg) {
@@ -963,7 +981,7 @@ static void launch_dynamics(OdebBatch *B, cudaStream_t s, bool timed, int cfg)
                 // row at a time per world, the sweeps after the first dRand reorder (~52 slots) under the 4-processor schedule
         {   // ODEB_TEST_HY_ROWS (tests only): a smaller hand-over threshold, so that worlds mix islands that may and may not be paused
             int srb = B->s5_sr[2];
-            if (const char *e = getenv("ODEB_TEST_HY_ROWS")) { const int v = atoi(e); if (v > 0 && v < srb) srb = v; }
+            if (B->env_hy_rows > 0 && B->env_hy_rows < srb) srb = B->env_hy_rows;
             k_solve_hy<<<nblk(W, ODEB_WPW), 32, B->solve_smem, s>>>(P, D, srb);
         }
         k_solve5_t<4, ODEB_HYBRID_SWEEPS><<<nblk(W, 4), 32, B->s5_smem[2], s>>>(P, D, B->s5_sr[2]);
@@ -987,6 +1005,8 @@ static void launch_dynamics(OdebBatch *B, cudaStream_t s, bool timed, int cfg)
     default: k_solve<<<nblk(W, ODEB_WPW), 32, B->solve_smem, s>>>(P, D, 0);
     }
     if (timed) { cudaEventRecord(e1, s); B->pending.push_back(std::make_pair(e0, e1)); }
+    nvtxRangePop();
+    OdebRange nv_("dxQuickStepIsland_Stage4b (feedback) + Stage6a/6b (velocity update, dxStepBody)");
     if (D.jcopy) { k_feedback<<<nblk(W * P.NJT, 128), 128, 0, s>>>(P, D); B->launches++; }
     k_integrate<<<nblk(W * P.NB, 128), 128, 0, s>>>(P, D);
     B->launches += 6;
@@ -1190,7 +1210,7 @@ uint64_t odeb_launch_count(const OdebBatch *B) { return B->launches; }
 const char *odeb_solver_kernel(OdebBatch *B)
 {
     static const char *names[10] = { "k_solve", "k_solve5<2>", "k_solve5<4>", "k_solve5<8>", "k_solve_bl", "k_solve (8 sweeps) + k_solve5<4>", "k_solve6<1>", "k_solve6<2>", "k_solve6<4>", "k_solve6<8>" };
-    if (B->mode == ODEB_MODE_CANONICAL) return "k_lw_sweep";
+    if (B->mode == ODEB_MODE_CANONICAL) return "k_lwt_phase";
     return names[choose_solver(B)];
 }
 void odeb_enable_timing(OdebBatch *B, int on) { B->timing = on != 0; }

@@ -31,6 +31,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <nvtx3/nvToolsExt.h>                 // header-only; a no-op unless a tool (nsys, ncu --nvtx) injects itself
 #include "../../include/ode_b200.h"
 #include "odeb_collide.cuh"
 #include "odeb_joints.cuh"

@@ -75,6 +75,7 @@ static int large_step(OdebBatch *B)
     LCK(cudaMemsetAsync(L.counters, 0, LWC_COUNT * sizeof(int), s));
     LCK(cudaMemsetAsync(L.draws, 0, 4 * sizeof(u64), s));
     // ---------------- collision
+    OdebRange nv_collide("dSpaceCollide (dxSAPSpace / dxHashSpace) + nearCallback (dCollide, dJointCreateContact)");
     int np = 0;
     if (NG > 0) {
         k_aabb<<<nblk(NG, 128), 128, 0, s>>>(P, D);
@@ -104,7 +105,9 @@ static int large_step(OdebBatch *B)
         LCK(cudaMemsetAsync(D.npairs, 0, sizeof(int), s));
         LCK(cudaMemsetAsync(D.ncontacts, 0, sizeof(int), s));
     }
+    nv_collide.end();
     // ---------------- joints, auto-disable, islands
+    OdebRange nv_islands("dxProcessIslands (auto-disable, island build) + dxQuickStepIsland_Stage0_Joints + Stage1");
     if (P.NJ > 0) { k_joint_info1<<<nblk(P.NJ, 128), 128, 0, s>>>(P, D); B->launches++; }
     LCK(cudaMemcpyAsync(hc, L.counters, sizeof(hc), cudaMemcpyDeviceToHost, s));
     LCK(cudaStreamSynchronize(s));
@@ -143,7 +146,9 @@ static int large_step(OdebBatch *B)
     k_lw_joint_final<<<nblk(nj > 0 ? nj : 1, 256), 256, 0, s>>>(P, D, L, nj);
     k_lw_island_info<<<nblk(T > 0 ? T : 1, 256), 256, 0, s>>>(P, D, L);
     B->launches += 2;
+    nv_islands.end();
     // ---------------- QuickStep stages 0..3 (the batched path's kernels, W == 1)
+    OdebRange nv_("dxQuickStepIsland stages 0-6 (large world: colouring, tiles, Stage4LCP_Iteration phases, dxStepBody)");
     k_body_pre<<<nblk(NB, 128), 128, 0, s>>>(P, D);
     B->launches++;
     if (hc[LWC_NJORD] > 0) { k_rows_t<false><<<nblk(hc[LWC_NJORD], 64), 64, 0, s>>>(P, D); B->launches++; }
@@ -162,7 +167,6 @@ static int large_step(OdebBatch *B)
         B->launches += 4;
         // ---------------- SOR sweeps
         cudaEvent_t e0 = 0, e1 = 0;
-        if (B->timing) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s); }
         unsigned iteration = 0, extra = 0;
         // the step's colouring: rounds in batches of 8, until no group is left uncoloured
         LCK(cudaMemsetAsync(L.counters + LWC_UNCOLORED, 0, 2 * sizeof(int), s));
@@ -199,6 +203,7 @@ static int large_step(OdebBatch *B)
         B->launches += 6;
         const size_t lw_tma_smem = (size_t)LWT_WARPS * LWT_STAGES * LWT_STAGE_BYTES + (size_t)LWT_WARPS * LWT_STAGES * sizeof(unsigned long long);
         int corder[64];
+        if (B->timing) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s); }   // the sweeps proper (what odeb_solver_ms reports)
         {
             // persistent phases: one cooperative launch per 8 sweeps
             if (B->lw_grid == 0) {
