@@ -179,7 +179,9 @@ int odeb_set_stream(OdebBatch *, void *stream);
  * device and the caller's arrays (pageable arrays work too, through an internal pinned staging buffer and one extra host copy). */
 void *odeb_alloc_host(size_t bytes);
 void odeb_free_host(void *);
-/* dBodyAddForce / dBodyAddTorque for every body: added to the accumulators consumed by the next step */
+/* dBodyAddForce / dBodyAddTorque for every body: added to the accumulators consumed by the next step.  Arrays from odeb_alloc_host are
+ * read asynchronously, in stream order: do not overwrite them before the next blocking call (odeb_get_state, odeb_sync, odeb_step);
+ * pageable arrays are copied before the call returns. */
 int odeb_add_force(OdebBatch *, const odeb_real *force, const odeb_real *torque);
 /* per-world dRandSetSeed / dRandGetSeed (ode/src/misc.cpp:52-61) */
 int odeb_set_seeds(OdebBatch *, const uint32_t *seeds);

@@ -794,7 +794,9 @@ int odeb_add_force(OdebBatch *B, const odeb_real *force, const odeb_real *torque
     }
     k_add_ft<<<nblk(n, 256), 256, 0, B->stream>>>(n, force ? B->D.facc : 0, torque ? B->D.tacc : 0, d);
     B->launches++;
-    CK(cudaStreamSynchronize(B->stream));            // the caller may reuse its arrays and ours right away
+    // pageable arrays went through the staging buffer: wait, so that the caller may reuse its arrays (and we ours) right away.  Page-locked
+    // arrays are read by the DMA engine in stream order: no host wait (include/ode_b200.h: leave them alone until the next blocking call)
+    if (synced) CK(cudaStreamSynchronize(B->stream));
     return 1;
 }
 
@@ -1124,7 +1126,6 @@ int odeb_enable_feedback(OdebBatch *B, int on)
 {
     CK(cudaSetDevice(B->device));
     CK(cudaStreamSynchronize(B->stream));
-    if (B->mode == ODEB_MODE_CANONICAL) { set_err("joint feedback is not available in ODEB_MODE_CANONICAL"); return 0; }
     if (on && !B->D.jcopy) {
         const size_t W = B->P.W;
         // allocated once per batch and kept: the classic dWorldQuickStep toggles feedback whenever "some joint has a dJointFeedback" changes

@@ -74,6 +74,7 @@ static int large_step(OdebBatch *B)
     int hc[LWC_COUNT];
     LCK(cudaMemsetAsync(L.counters, 0, LWC_COUNT * sizeof(int), s));
     LCK(cudaMemsetAsync(L.draws, 0, 4 * sizeof(u64), s));
+    if (D.jfb) LCK(cudaMemsetAsync(D.jfb, 0, (size_t)P.NJT * 4 * sizeof(Real4), s));      // state 0 = joint not stepped
     // ---------------- collision
     OdebRange nv_collide("dSpaceCollide (dxSAPSpace / dxHashSpace) + nearCallback (dCollide, dJointCreateContact)");
     int np = 0;
@@ -243,6 +244,7 @@ static int large_step(OdebBatch *B)
         if (D.jcopy) { k_lwt_lambda_out<<<ntiles, 128, 0, s>>>(D, L); B->launches++; }
     }
     k_lw_finish<<<1, 1, 0, s>>>(P, D, L);
+    if (D.jcopy && mrows > 0) { k_feedback<<<nblk(P.NJT, 128), 128, 0, s>>>(P, D); B->launches++; }   // Stage 4b: the lambdas are back in row order (k_lwt_lambda_out)
     k_integrate<<<nblk(NB, 128), 128, 0, s>>>(P, D);
     B->launches += 2;
     LCK(cudaGetLastError());

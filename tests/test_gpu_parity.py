@@ -208,6 +208,23 @@ def test_canonical_mode_bit_exact(prec):
 
 
 @pytest.mark.parametrize("prec", PRECS)
+def test_canonical_mode_joint_feedback(prec):
+    """Joint feedback on the large-world path: the lambdas live in the tile layout during the sweeps and go back to row order for
+    Stage 4b (k_lwt_lambda_out); permanent joints + contacts, every step identical to the oracle in the same mode."""
+    from test_oracle import compare_feedback
+    for mk, h, n in ((lambda: scenes.chain(1), 0.05, 40), (lambda: scenes.wall(6, 4, max_contacts=8), 0.05, 20)):
+        sc = mk()
+        a, b = _canon_pair(prec, sc)
+        a.enable_feedback()
+        b.enable_feedback()
+        for s in range(n):
+            a.step(h)
+            b.step(h)
+            bad = compare_step(a, b, 1) + compare_feedback(a, b, 1, True, 0)
+            assert not bad, (s, bad)
+
+
+@pytest.mark.parametrize("prec", PRECS)
 def test_canonical_mode_teacher_forced(prec):
     """Scenes with cullPoints/atan2 (<= 4 contacts per box pair) and hinge angles: teacher-forced single steps."""
     for mk, h, targets in ((lambda: scenes.pile(nbodies=1000), 0.01, (0, 40, 80)),
