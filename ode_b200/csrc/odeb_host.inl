@@ -32,6 +32,7 @@ struct OdebBatch {
     // solver selection: 0 = k_solve (one row at a time per world), 1..3 = k_solve5<2/4/8> (static P-processor schedule),
     // 4 = k_solve_bl (one lane per body). hint_m = largest island (rows) seen since the last sync, read back in odeb_sync.
     int s5_sr[4]; size_t s5_smem[4]; int hint_m; int solver_force; int lw_variant, lw_grid, lwc_grid;
+    bool rows_std3;                               // every joint is a contact of exactly three rows (normal + two friction directions): k_rows_t<true, true>
     bool env_no_solve6, env_no_hybrid, env_no_fused_rows; int env_hy_rows;   // experiment / test switches, read once at creation (ODEB_NO_SOLVE6, ODEB_NO_HYBRID, ODEB_NO_FUSED_ROWS, ODEB_TEST_HY_ROWS)   // s5_sr / s5_smem: row budget and shared memory of k_solve5<2^k> for the next launch
     int s6_sr, s6_nbi; size_t s6_smem;        // k_solve6<P> (odeb_solve6.cuh): row / body budget per island and shared memory per warp for the next launch
     int hint_nb, hint_nis;                    // largest island (bodies) and most islands with rows in one world seen so far
@@ -383,6 +384,8 @@ static OdebBatch *batch_build(const OdebWorldParams *wp, const HostTemplate &T, 
     apply_world_params(P, wp, classic);
     P.NJT = P.NJ + P.MC;
     P.MR = P.MC * P.m_contact + P.NJ * 6;
+    B->rows_std3 = !classic && P.NJ == 0 && P.surf.the_m == 3 && !(P.surf.mode & 0x400) && P.surf.mu > 0 && ((P.surf.mode & 0x001) ? P.surf.mu2 : P.surf.mu) > 0
+                   && getenv("ODEB_NO_STD3_ROWS") == 0;
     {   // shared-memory budget of k_solve (16 worlds per warp): ring + per-body accumulators + lambda/metadata for SR rows
         int sr = P.MR < 512 ? P.MR : 512;
         if (const char *s = getenv("ODEB_SOLVER_ROWS")) sr = atoi(s);
@@ -966,7 +969,10 @@ static void launch_dynamics(OdebBatch *B, cudaStream_t s, bool timed, int cfg)
     k_body_pre<<<nblk(W * P.NB, 128), 128, 0, s>>>(P, D);
     nvtxRangePop();
     nvtxRangePushA("dxQuickStepIsland_Stage2a/2b/2c (getInfo2, rhs) + Stage4LCP_iMJ + Stage4LCP_AdComputation");
-    if (P.NJ == 0 && !D.row_island && !B->env_no_fused_rows) { k_rows_t<true><<<nblk(W * P.NJT, 64), 64, 0, s>>>(P, D); B->launches--; }
+    if (P.NJ == 0 && !D.row_island && !B->env_no_fused_rows) {
+        if (B->rows_std3) k_rows_t<true, true><<<nblk(W * P.NJT, 64), 64, 0, s>>>(P, D); else k_rows_t<true><<<nblk(W * P.NJT, 64), 64, 0, s>>>(P, D);
+        B->launches--;
+    }
     else {
         k_rows_t<false><<<nblk(W * P.NJT, 64), 64, 0, s>>>(P, D);
         k_rows_finish<<<nblk(W * P.MR, 128), 128, 0, s>>>(P, D);

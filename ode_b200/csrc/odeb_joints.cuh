@@ -552,7 +552,10 @@ __host__ __device__ inline int odeb_contact_rows(int mode, Real mu, Real mu2, Re
 }
 
 // dxJointContact::getInfo2 joints/contact.cpp:125-347
-__device__ void odeb_contact_info2(const DSurface &s, const Real *cpos, const Real *cnormal, Real cdepth, int reverse,
+// STD3: the caller has checked that the contact has exactly its normal row and both friction rows (mu > 0, mu2 > 0, no rolling friction):
+// the row positions are compile-time constants then, and a caller that unrolls its own row loops keeps all three rows in registers
+template <bool STD3>
+__device__ __forceinline__ void odeb_contact_info2(const DSurface &s, const Real *cpos, const Real *cnormal, Real cdepth, int reverse,
                                    const DBody &b0, const DBody *b1, Real fps, Real worldERP, Real min_depth, Real maxvel,
                                    Real *row, int *findex)
 {
@@ -590,12 +593,12 @@ __device__ void odeb_contact_info2(const DSurface &s, const Real *cpos, const Re
     row[C_RHS] = c;
     if (mode & 0x010) row[C_CFM] = s.soft_cfm;
     row[C_LO] = 0; row[C_HI] = R_INF;
-    if (s.the_m > 1) {
+    if (STD3 || s.the_m > 1) {
         Real t1[3], t2[3];
         if (mode & 0x002) { t1[0] = s.fdir1[0]; t1[1] = s.fdir1[1]; t1[2] = s.fdir1[2]; cross3(t2, normal, t1); }   // contact.cpp:221-224
         else plane_space(normal, t1, t2);
         int r = 1;
-        if (s.mu > 0) {
+        if (STD3 || s.mu > 0) {
             Real *q = row + r * ROWLEN;
             q[C_J1L] = t1[0]; q[C_J1L + 1] = t1[1]; q[C_J1L + 2] = t1[2];
             cross3(q + C_J1A, c1, t1);
@@ -607,7 +610,7 @@ __device__ void odeb_contact_info2(const DSurface &s, const Real *cpos, const Re
             r++;
         }
         const Real mu2 = (mode & 0x001) ? s.mu2 : s.mu;
-        if (mu2 > 0) {
+        if (STD3 || mu2 > 0) {
             Real *q = row + r * ROWLEN;
             q[C_J1L] = t2[0]; q[C_J1L + 1] = t2[1]; q[C_J1L + 2] = t2[2];
             cross3(q + C_J1A, c1, t2);
@@ -618,7 +621,7 @@ __device__ void odeb_contact_info2(const DSurface &s, const Real *cpos, const Re
             if (mode & 0x2000) findex[r] = 0;
             r++;
         }
-        if (mode & 0x400) {   // rolling about t1, t2 and spinning about the normal (contact.cpp:299-343)
+        if (!STD3 && (mode & 0x400)) {   // rolling about t1, t2 and spinning about the normal (contact.cpp:299-343)
             const Real *ax[3] = { t1, t2, normal };
             const int approx_bits[3] = { 0x1000, 0x2000, 0x4000 };
             const Real rho[3] = { s.rho, (mode & 0x001) ? s.rho2 : s.rho, (mode & 0x001) ? s.rhoN : s.rho };

@@ -598,7 +598,9 @@ __device__ __forceinline__ void finish_row(const DevParams &P, Real *q, const Re
 // FUSED (worlds without permanent joints: no limit motor can add body forces after a row was built, so the grid-wide ordering
 // Stage2a -> Stage2b of quickstep.cpp:1486-1690 is not needed): the thread finishes its rows itself (finish_row) and writes the final
 // records once, instead of k_rows_finish reading the half-built records back and rewriting them.
-template <bool FUSED>
+// STD3 (with FUSED): every joint is a contact with exactly three rows (normal + two friction directions, DevParams::rows_std3): the row
+// loops unroll and the rows live in registers instead of a 640-byte local array.
+template <bool FUSED, bool STD3 = false>
 __global__ void k_rows_t(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D)
 {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -616,12 +618,14 @@ __global__ void k_rows_t(const __grid_constant__ DevParams P, const __grid_const
     DBody b0, b1;
     Real tq[3] = { 0, 0, 0 }, fq[3] = { 0, 0, 0 }, tboth[3] = { 0, 0, 0 };
     bool has_tq = false, has_f = false;
-    if (jid >= P.NJ) {
+    if (STD3 || jid >= P.NJ) {
         int4 ci = D.cinfo[(size_t)w * P.MC + (jid - P.NJ)];
-        const DSurface &surf = P.classic ? D.csurf[jid - P.NJ] : P.surf;
-        m = surf.the_m; b0i = ci.y; b1i = ci.z;
-        for (int r = 0; r < m; r++) {
+        const DSurface &surf = (!STD3 && P.classic) ? D.csurf[jid - P.NJ] : P.surf;
+        m = STD3 ? 3 : surf.the_m; b0i = ci.y; b1i = ci.z;
+#pragma unroll
+        for (int r = 0; r < (STD3 ? 3 : m); r++) {
             Real *q = row + r * ROWLEN;
+#pragma unroll
             for (int c = 0; c < ROWLEN; c++) q[c] = 0;
             q[C_CFM] = P.cfm; q[C_LO] = -R_INF; q[C_HI] = R_INF;
             findex[r] = -1;
@@ -631,7 +635,7 @@ __global__ void k_rows_t(const __grid_constant__ DevParams P, const __grid_const
         const Real4 *cg = D.cgeom + ((size_t)w * (P.classic ? (size_t)P.MC : (size_t)P.MP * P.maxc) + ci.x) * 2;
         Real4 a = cg[0], n4 = cg[1];
         Real cpos[3] = { a.x, a.y, a.z }, cn[3] = { n4.x, n4.y, n4.z };
-        odeb_contact_info2(surf, cpos, cn, a.w, ci.w, b0, b1i >= 0 ? &b1 : 0, P.hrecip, P.erp, P.min_depth, P.max_vel, row, findex);
+        odeb_contact_info2<STD3>(surf, cpos, cn, a.w, ci.w, b0, b1i >= 0 ? &b1 : 0, P.hrecip, P.erp, P.min_depth, P.max_vel, row, findex);
     } else {
         const DJointT &jt = D.joints[jid];
         m = D.jm[(size_t)w * P.NJ + jid]; b0i = jt.b0; b1i = jt.b1;
@@ -653,7 +657,8 @@ __global__ void k_rows_t(const __grid_constant__ DevParams P, const __grid_const
         body_rhs_tmp(P, D, w, p0, in0, invI0, &im0);
         if (p1 != -1) body_rhs_tmp(P, D, w, p1, in1, invI1, &im1);
     }
-    for (int r = 0; r < m; r++) {
+#pragma unroll
+    for (int r = 0; r < (STD3 ? 3 : m); r++) {
         Real *q = row + r * ROWLEN;
         q[C_RHS] *= P.hrecip; q[C_CFM] *= P.hrecip;
         if (!FUSED) {
