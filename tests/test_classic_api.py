@@ -335,3 +335,52 @@ def test_golden_colliders_through_classic_dcollide(prec):
             inexact += 1
     assert inexact <= 6, inexact
     assert int((gold["n"] > 1).sum()) > 30
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# prototypes: every function include/ode_b200_classic.h declares has the signature the reference's own headers give it
+_TYPEWORDS = {"void", "int", "unsigned", "char", "float", "double", "long", "short", "const", "signed", "struct"}
+
+
+def _norm_param(p):
+    p = re.sub(r"\[[^\]]*\]", "*", p.strip())            # an array parameter is a pointer
+    toks = re.findall(r"[A-Za-z_]\w*|\*", p)
+    words = [t for t in toks if t != "*"]
+    if len(words) >= 2 and words[-1] not in _TYPEWORDS and toks[-1] != "*":
+        toks = toks[:-1]                                   # the trailing identifier is the parameter's name
+    return " ".join(toks).replace(" *", "*").replace("* ", "*")
+
+
+def _prototypes(text):
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", " ", text)
+    text = re.sub(r"^[ \t]*#.*$", " ", text, flags=re.M)
+    text = re.sub(r"\bODE_API\b|\bODE_API_DEPRECATED\b|\bextern\b", " ", text)
+    out = {}
+    for m in re.finditer(r"([A-Za-z_][\w\s\*]*?)\b(d[A-Z]\w*)\s*\(([^;{}()]*)\)\s*;", text):
+        ret, name, params = m.group(1), m.group(2), m.group(3)
+        if "typedef" in ret or "return" in ret:
+            continue
+        ret = " ".join(re.findall(r"[A-Za-z_]\w*|\*", ret)).replace(" *", "*")
+        ps = [_norm_param(x) for x in params.split(",")]
+        out[name] = (ret, tuple([] if ps == ["void"] else ps))
+    return out
+
+
+def test_prototypes_match_the_reference_headers():
+    """Return type and parameter types of every declared function against /root/reference/include/ode/*.h (parameter names and
+    whitespace aside): a drop-in has to agree with the reference on more than the symbol names.  Only where the reference tree is
+    mounted (this container)."""
+    import glob
+    hdrs = glob.glob("/root/reference/include/ode/*.h")
+    if not hdrs:
+        pytest.skip("reference headers not present")
+    ours = _prototypes(open(os.path.join(ROOT, "include", "ode_b200_classic.h")).read())
+    ref = {}
+    for f in hdrs:
+        ref.update(_prototypes(open(f).read()))
+    assert len(ours) >= 200
+    missing = [n for n in ours if n not in ref]
+    assert not missing, missing
+    bad = [(n, ours[n], ref[n]) for n in sorted(ours) if ours[n] != ref[n]]
+    assert not bad, bad
