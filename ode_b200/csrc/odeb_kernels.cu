@@ -680,8 +680,9 @@ __global__ void k_rows_t(const __grid_constant__ DevParams P, const __grid_const
             finish_row(P, q, in0, invI0, im0, p1 != -1, in1, invI1, im1, rec + 8 * r);
             D.rbody[(size_t)w * P.MR + row0 + r] = make_int2(p0, (p1 == -1) ? P.NB : p1);
         } else {
-            // body order positions travel in the last two slots of the record
+            // body order positions travel in the last two slots of the record (k_rows_finish) and in rbody (large-world path: k_lwc_groups)
             *(int *)&rec[8 * r + 7].z = p0; *(int *)&rec[8 * r + 7].w = p1;
+            D.rbody[(size_t)w * P.MR + row0 + r] = make_int2(p0, (p1 == -1) ? P.NB : p1);
         }
     }
     if (has_f) {    // dBodyAddForce / dBodyAddTorque from a powered linear limit motor at its stop (joints/joint.cpp:688-704)

@@ -381,11 +381,7 @@ __global__ void k_lwc_groups(const __grid_constant__ DevParams P, const __grid_c
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= mrows) return;
     D.lambda[r] = 0;
-    // the body order positions travel in the last two words of the half-built record (k_rows_t<false>)
-    const Real4 last = D.rows[(size_t)r * 8 + 7];
-    const int p0 = *(const int *)&last.z, p1 = *(const int *)&last.w;
-    const int2 rb = make_int2(p0, p1 == -1 ? P.NB : p1);         // one-body rows address the dummy accumulator slot NB
-    D.rbody[r] = rb;
+    const int2 rb = D.rbody[r];                                   // accumulator slots of the row's two bodies (k_rows_t<false>)
     const int g = L.row_group[r];
     atomicAdd(&L.gsize[g], 1);
     if (g != r) return;

@@ -152,7 +152,10 @@ static int large_step(OdebBatch *B)
     OdebRange nv_("dxQuickStepIsland stages 0-6 (large world: colouring, tiles, Stage4LCP_Iteration phases, dxStepBody)");
     k_body_pre<<<nblk(NB, 128), 128, 0, s>>>(P, D);
     B->launches++;
-    if (hc[LWC_NJORD] > 0) { k_rows_t<false><<<nblk(hc[LWC_NJORD], 64), 64, 0, s>>>(P, D); B->launches++; }
+    if (hc[LWC_NJORD] > 0) {
+        if (B->rows_std3) k_rows_t<false, true><<<nblk(hc[LWC_NJORD], 64), 64, 0, s>>>(P, D); else k_rows_t<false><<<nblk(hc[LWC_NJORD], 64), 64, 0, s>>>(P, D);
+        B->launches++;
+    }
     LCK(cudaMemsetAsync(D.cforce, 0, (size_t)(NB + 1) * 2 * sizeof(Real4), s));
     if (mrows > 0) {
         // groups (rows of one geom pair's contacts / of one joint), their compact list and the body -> groups incidence (CSR): once per step
