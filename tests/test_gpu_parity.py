@@ -207,6 +207,34 @@ def test_canonical_mode_bit_exact(prec):
             assert not bad, (s, bad)
 
 
+def test_canonical_mode_full_size_wall():
+    """BASELINE configs[4] at its full size (500 x 200 bricks + cannon ball = 100 001 bodies, ~3.05 M rows, sweep-and-prune space): two
+    steps of the CUDA large-world path against the oracle in the same mode (single precision; the oracle needs ~20 s per step on one
+    core).  Step 0 (bricks at rest, axis-aligned): every observable bit for bit.  Step 1 starts from that identical state, but the bricks
+    have moved by then and a box-box pair with more than 4 candidate points goes through cullPoints' atan2 (CUDA libm vs glibc, DESIGN.md
+    section 1): pair set, per-pair contact counts, islands and seeds exact; measured on B200, 5 of the 1 137 774 contacts (3 pairs of
+    bricks touching edge-on with depths of ~1e-7, where two candidate points are a rounding error apart in angle) keep a different corner,
+    and the body state agrees to 1.2e-4 (tolerance 4x that)."""
+    sc = scenes.wall(500, 200)
+    a, b = _canon_pair("single", sc)
+    a.step(0.05)
+    b.step(0.05)
+    bad = compare_step(a, b, 1)
+    assert not bad, (0, bad)
+    assert b.get_totals()[2] > 3000000
+    a.step(0.05)
+    b.step(0.05)
+    bad = compare_step(a, b, 1, what=("pairs", "islands", "seeds"))
+    assert not bad, (1, bad)
+    (ga, ia), (gb, ib) = a.get_contacts(0), b.get_contacts(0)
+    assert np.array_equal(ia, ib)
+    differ = int((np.abs(ga.astype(np.float64) - gb).reshape(len(ga), -1).max(axis=1) > 0).sum())
+    assert differ <= len(ga) // 20000, differ
+    sa, sb = a.get_state(), b.get_state()
+    for k in ("pos", "quat", "lvel", "avel"):
+        assert np.abs(sa[k].astype(np.float64) - sb[k]).max() <= 5e-4, k
+
+
 @pytest.mark.parametrize("prec", PRECS)
 def test_canonical_mode_joint_feedback(prec):
     """Joint feedback on the large-world path: the lambdas live in the tile layout during the sweeps and go back to row order for
