@@ -236,6 +236,10 @@ int odeb_restore(OdebBatch *, const void *buf, size_t bytes);
  * `seed` = the world's dRand seed at the start of the step. Exported as odeb_canon_key; the inline body is shared with
  * the kernels and with oracle/. */
 uint32_t odeb_canon_key(uint32_t seed, uint32_t island, uint32_t phase, uint32_t row);
+/* Test hook: out[i] = the library's single-precision atan2 of (y[i], x[i]) -- the fdlibm algorithm the reference's host libm (glibc <= 2.40)
+ * uses, restated operation by operation (odeb_math.cuh) -- evaluated on the host (on_device = 0) or by a kernel on the current device
+ * (on_device = 1).  Tests compare it bit for bit with the host's atan2f.  Returns 1 on success. */
+int odeb_test_atan2f(const float *y, const float *x, float *out, int n, int on_device);
 static inline ODEB_HD uint32_t odebi_canon_key(uint32_t seed, uint32_t island, uint32_t phase, uint32_t row)
 {
     uint32_t x = seed ^ (island * 0x9E3779B9u) ^ (phase * 0x85EBCA6Bu) ^ (row * 0xC2B2AE35u);

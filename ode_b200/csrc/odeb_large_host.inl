@@ -64,6 +64,26 @@ extern "C" int odeb_set_solver_mode(OdebBatch *B, int mode)
 
 extern "C" uint32_t odeb_canon_key(uint32_t seed, uint32_t island, uint32_t phase, uint32_t row) { return odebi_canon_key(seed, island, phase, row); }
 
+__global__ void k_test_atan2f(const float *y, const float *x, float *out, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = odeb_atan2f_fdlibm(y[i], x[i]);
+}
+extern "C" int odeb_test_atan2f(const float *y, const float *x, float *out, int n, int on_device)
+{
+    if (n <= 0) return 1;
+    if (!on_device) { for (int i = 0; i < n; i++) out[i] = odeb_atan2f_fdlibm(y[i], x[i]); return 1; }
+    float *d = 0;
+    CK(cudaMalloc(&d, (size_t)3 * n * sizeof(float)));
+    cudaError_t e = cudaMemcpy(d, y, (size_t)n * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d + n, x, (size_t)n * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) { k_test_atan2f<<<(n + 255) / 256, 256>>>(d, d + n, d + 2 * (size_t)n, n); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaMemcpy(out, d + 2 * (size_t)n, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) { set_err("odeb_test_atan2f: %s", cudaGetErrorString(e)); return 0; }
+    return 1;
+}
+
 static int bits_for(unsigned v) { int b = 1; while ((v >> b) != 0 && b < 32) b++; return b; }
 
 static int large_step(OdebBatch *B)
