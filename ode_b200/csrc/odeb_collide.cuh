@@ -1,8 +1,8 @@
 // odeb_collide.cuh -- device-side AABBs and primitive colliders (sphere / box / capsule / plane) of the
 // B200 step path: one thread evaluates one geom pair. Operation order follows the reference functions
 // cited at each routine (ode/src/box.cpp, sphere.cpp, capsule.cpp, plane.cpp, collision_util.cpp,
-// collision_kernel.cpp) so contacts are bit-identical under -fmad=false except where CUDA libm
-// (atan2 in the contact culling) differs from glibc in the last ulp.
+// collision_kernel.cpp) so contacts are bit-identical under -fmad=false; the one libm call on the path, atan2 in the
+// contact culling, is the host libm's algorithm in single precision (odeb_math.cuh) and CUDA's libm (last-ulp differences) in double.
 #ifndef ODEB_COLLIDE_CUH
 #define ODEB_COLLIDE_CUH
 #include "odeb_math.cuh"

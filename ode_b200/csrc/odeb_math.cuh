@@ -1,6 +1,7 @@
 // odeb_math.cuh -- device-side small-vector math of the B200 step path.
 // Operation order follows the reference (citations per function) so that a build with -fmad=false is
-// bit-identical to the reference's x86-64 build for +,-,*,/,sqrt; sin/cos/atan2 are CUDA libm (<= 2 ulp).
+// bit-identical to the reference's x86-64 build for +,-,*,/,sqrt and single-precision atan2 (fdlibm's algorithm, below); sin/cos and the
+// double-precision atan2 are CUDA libm (<= 2 ulp).
 // dVector3 = 4 reals, dMatrix3 = 3 rows x 4 (include/ode/common.h:270-275), quaternion (w,x,y,z).
 #ifndef ODEB_MATH_CUH
 #define ODEB_MATH_CUH

@@ -212,18 +212,19 @@ def test_classic_boxstack_bit_exact(prec):
 @pytest.mark.parametrize("prec,space", (("single", "sap"), ("double", "hash"), ("single", "simple")))
 def test_classic_mixed_pile(prec, space):
     """boxes, spheres and capsules with friction (Approx1): all primitive pair types, per-contact surfaces.
-    Contact culling uses atan2 (box.cpp:305) -> CUDA libm vs glibc: stated tolerance on the state."""
+    Contact culling uses atan2 (box.cpp:305): bit-identical in single precision (the library's atan2f is the host libm's algorithm),
+    CUDA libm vs glibc in double: stated tolerance on the state."""
     apps = _run_both(prec, lambda a: A.scene_mixed_pile(a, 12), 80, 0.01, space=space, max_contacts=4, surface="approx1")
-    _compare(apps, 80, 0.01, exact=False, tol=2e-4 if prec == "single" else 1e-9)
+    _compare(apps, 80, 0.01, exact=prec == "single", tol=1e-9)
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("prec", ("single", "double"))
 def test_classic_linkage_joints(prec):
     """ball / hinge / universal joints with stops created through the classic setters + ground contacts (hinge angles use
-    atan2 -> tolerance as in tests/test_gpu_parity.py)"""
+    atan2: bit-identical in single precision, tolerance as in tests/test_gpu_parity.py in double)"""
     apps = _run_both(prec, A.scene_linkage, 100, 0.01, space="hash", max_contacts=4, surface="chain")
-    _compare(apps, 100, 0.01, exact=False, tol=5e-4 if prec == "single" else 1e-9)
+    _compare(apps, 100, 0.01, exact=prec == "single", tol=1e-9)
 
 
 @pytest.mark.gpu
@@ -239,7 +240,7 @@ def test_classic_joint_feedback(prec):
         a.contact_feedback = True
     apps = _run_both(prec, build, 60, 0.01, space="hash", max_contacts=4, surface="approx1")
     ra, ga = apps
-    tol = 5e-3 if prec == "single" else 1e-8        # hinge / universal angles go through atan2 (CUDA libm vs glibc)
+    tol = 0.0 if prec == "single" else 1e-8         # hinge / universal angles go through atan2: the host libm's algorithm in single (exact), CUDA libm in double
     wrote = 0
     for s in range(60):
         assert ra.step(0.01, seed=100 + s) == 1 and ga.step(0.01, seed=100 + s) == 1
@@ -263,7 +264,7 @@ def test_classic_motors_and_offsets(prec):
     between steps) and dGeomSetOffset* composite bodies through the classic API, reference vs B200 (atan2 on the path -> tolerance)"""
     apps = _run_both(prec, A.scene_motors, 80, 0.01, space="hash", max_contacts=4, surface="approx1")
     ra, ga = apps
-    tol = 5e-4 if prec == "single" else 1e-9
+    tol = 0.0 if prec == "single" else 1e-9          # single: atan2 is the host libm's algorithm, bit-identical
     for s in range(80):
         for a in apps:
             a.o.dJointSetAMotorParam(a.user_motor, 2, 0.4 * math.sin(0.1 * s))       # dParamVel
@@ -321,7 +322,7 @@ def test_golden_colliders_through_classic_dcollide(prec):
     geoms = [(make(c["t1"], c["p1"], c["pos1"], c["R1"]), make(c["t2"], c["p2"], c["pos2"], c["R2"])) for c in cases]
     CG = o.dContactGeom
     buf = (CG * 8)()
-    tol = 2e-5 if prec == "single" else 1e-12
+    tol = 0.0 if prec == "single" else 1e-12
     inexact = 0
     for i, (c, (g1, g2)) in enumerate(zip(cases, geoms)):
         n = o.dCollide(g1, g2, c["flags"], C.byref(buf), C.sizeof(CG))
@@ -333,7 +334,7 @@ def test_golden_colliders_through_classic_dcollide(prec):
             # same contact set, possibly another pick among the culled points: every point must be one the reference could produce
             assert np.abs(np.sort(got[:, 6]) - np.sort(want[:, 6])).max() <= tol or np.abs(got - want).max() <= tol, "case %d" % i
             inexact += 1
-    assert inexact <= 6, inexact
+    assert inexact <= (0 if prec == "single" else 6), inexact
     assert int((gold["n"] > 1).sum()) > 30
 
 
