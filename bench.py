@@ -256,6 +256,24 @@ def other_configs(slib, device, with_cpu=True, t_budget_end=None):
             except Exception as e:  # noqa: BLE001
                 slot.update({"error": str(e)[:200]})
 
+    try:   # the headline workload in DOUBLE precision (north_star: results match the reference built as dSINGLE and as dDOUBLE; the line's dtype is f32)
+        from ode_b200 import load
+        dl = load("double")
+        Ld = dl.lib
+        Ld.odeb_timed_steps.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_size_t, C.POINTER(C.c_double)]
+        Ld.odeb_solver_kernel.restype = C.c_char_p
+        Ld.odeb_solver_kernel.argtypes = [C.c_void_p]
+        b = B.Batch(dl, make_scene(WORLDS_PER_GPU, seed0=1000), device=device)
+        b.step(H, 155)
+        msd = C.c_double(0)
+        if not Ld.odeb_timed_steps(b.h, H, 20, FLUSH_BYTES, C.byref(msd)):
+            raise RuntimeError("odeb_timed_steps (double) failed")
+        out["stack_double"] = {"ms_per_step": msd.value / 20, "body_steps_per_sec": WORLDS_PER_GPU * NBOX * 20 / (msd.value * 1e-3), "steps": 20, "dtype": "f64",
+                               "kernel": (Ld.odeb_solver_kernel(b.h) or b"k_solve").decode(),
+                               "workload": "%d worlds x %d-box stack (the headline workload) in double precision, all on this GPU" % (WORLDS_PER_GPU, NBOX)}
+        b.close()
+    except Exception as e:  # noqa: BLE001
+        out["stack_double"] = {"error": str(e)[:200]}
     try:   # configs[2]: 65536 worlds of a 10-link ball-joint chain plus contacts (demo_chain2-style)
         nw = 65536
         b = B.Batch(slib, scenes.chain(nw), device=device)
