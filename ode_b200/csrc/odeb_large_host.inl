@@ -206,6 +206,7 @@ static int large_step(OdebBatch *B)
             }
             int grid = nblk(ngroups, 1024);                    // few, large blocks: the grid barrier costs one atomic per block
             if (grid > B->lwc_grid) grid = B->lwc_grid;
+            if (B->lw_maxgrid > 0 && grid > B->lw_maxgrid) grid = B->lw_maxgrid;
             LCK(cudaMemsetAsync(L.counters + LWC_GBAR, 0, sizeof(int), s));
             void *args[3] = { (void *)&P, (void *)&D, (void *)&L };
             LCK(cudaLaunchCooperativeKernel((const void *)k_lwc_color_rounds, dim3(grid), dim3(1024), args, 0, s));
@@ -243,6 +244,7 @@ static int large_step(OdebBatch *B)
             int grid = (maxnt + LWT_WARPS - 1) / LWT_WARPS;
             { const int by_bodies = (nordered + 32 * LWT_WARPS - 1) / (32 * LWT_WARPS); if (by_bodies > grid) grid = by_bodies; }
             if (grid > B->lw_grid) grid = B->lw_grid;
+            if (B->lw_maxgrid > 0 && grid > B->lw_maxgrid) grid = B->lw_maxgrid;
             LwPhase ph;
             for (int c = 0; c < 65; c++) ph.tstart[c] = tstart[c];
             ph.nordered = nordered; ph.nislands = T;

@@ -211,6 +211,25 @@ def test_canonical_mode_bit_exact(prec):
             assert not bad, (s, bad)
 
 
+@pytest.mark.parametrize("maxgrid", (1, 3))
+def test_canonical_mode_more_tiles_than_warps(maxgrid, monkeypatch):
+    """The persistent sweep kernel gives every warp the tiles t, t + (all warps), ... of a colour; up to 100k boxes a B200 has more warps
+    than the largest colour has tiles, so that loop (and the grid-stride loops of the colouring rounds, the body check and the island
+    control) only runs once.  ODEB_LW_MAXGRID caps the cooperative grids at 1 / 3 blocks: several tiles per warp and colour, same bits."""
+    monkeypatch.setenv("ODEB_LW_MAXGRID", str(maxgrid))
+    for prec in PRECS:
+        for mk, h, n in ((lambda: scenes.wall(24, 12, max_contacts=8), 0.05, 14), (lambda: scenes.free_boxes(1, 400, grid=20), 0.01, 12),
+                         (lambda: scenes.pile(nbodies=343), 0.01, 25)):
+            sc = mk()
+            a, b = _canon_pair(prec, sc)
+            for s in range(n):
+                a.step(h)
+                b.step(h)
+                bad = compare_step(a, b, 1, exact_float=prec == "single" or sc.nbody != 343, tol=TOL[prec])
+                assert not bad, (prec, sc.nbody, s, bad)
+            b.close()
+
+
 def test_canonical_mode_full_size_wall():
     """BASELINE configs[4] at its full size (500 x 200 bricks + cannon ball = 100 001 bodies, ~3.05 M rows, 1.14 M contacts, sweep-and-prune
     space): three steps of the CUDA large-world path against the oracle in the same mode, every observable bit for bit (single precision;
