@@ -207,7 +207,8 @@ int odeb_get_enabled(OdebBatch *, int *enabled /* [world][body] */);
  *     reference's is the attach order, then random permutations): trajectories differ from the reference the way two random
  *     reorderings of the reference differ from each other (profiles/r2_callback_order.txt); everything a step decides before the
  *     solver runs (pair set, contacts, islands) is the reference's.
- *     Requires nworlds == 1. */
+ *     Requires nworlds == 1.  At most 62 row groups (contact pairs / permanent joints) may act on one body (the static environment has no body
+ *     and does not count); a step that meets more fails like a capacity overflow, with the state of the last complete step kept. */
 enum { ODEB_MODE_REPLAY = 0, ODEB_MODE_CANONICAL = 1 };
 int odeb_set_solver_mode(OdebBatch *, int mode);
 

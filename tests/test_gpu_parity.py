@@ -230,6 +230,34 @@ def test_canonical_mode_more_tiles_than_warps(maxgrid, monkeypatch):
             b.close()
 
 
+def test_canonical_mode_reports_too_many_groups_on_one_body():
+    """The colouring of the large-world path holds at most 62 row groups (contact pairs / joints) on one BODY (the static plane has no body and
+    does not count): a platform carrying 81 boxes is refused loudly, and the state stays the one of the last complete step."""
+    sc = B.Scene(B.default_world_params(gravity=(0, 0, -9.81), max_contacts=4, surf_mode=B.CONTACT_APPROX1, mu=0.5), 1)
+    sc.add_geom(B.PLANE, (0, 0, 1, 0))
+    m, I = B.box_mass(1.0, 20, 20, 0.5)
+    p = sc.add_body(m, I, (0, 0, 0.25))
+    sc.add_geom(B.BOX, (20, 20, 0.5), body=p)
+    m, I = B.box_mass(1.0, 1, 1, 1)
+    for i in range(81):
+        bb = sc.add_body(m, I, ((i % 9) * 2.0 - 8.0, (i // 9) * 2.0 - 8.0, 1.0))
+        sc.add_geom(B.BOX, (1, 1, 1), body=bb)
+    n = 82
+    pos = np.asarray(sc.body_pos, dtype=np.float64)[None]
+    quat = np.tile(np.array([1.0, 0, 0, 0])[None, None], (1, n, 1))
+    sc.state = dict(pos=pos, quat=quat, lvel=np.zeros_like(pos), avel=np.zeros_like(pos))
+    sc.seeds = np.array([7], dtype=np.uint32)
+    b = B.Batch(gpu_lib("single"), sc)
+    b.set_solver_mode(1)
+    before = b.get_state()
+    with pytest.raises(RuntimeError, match="row groups on one body"):
+        b.step(0.01, 2)
+        b.get_state()
+    after = b.get_state()
+    assert np.array_equal(before["pos"], after["pos"])
+    b.close()
+
+
 def test_canonical_mode_full_size_wall():
     """BASELINE configs[4] at its full size (500 x 200 bricks + cannon ball = 100 001 bodies, ~3.05 M rows, 1.14 M contacts, sweep-and-prune
     space): three steps of the CUDA large-world path against the oracle in the same mode, every observable bit for bit (single precision;
