@@ -207,7 +207,7 @@ int odeb_get_enabled(OdebBatch *, int *enabled /* [world][body] */);
  *     reference's is the attach order, then random permutations): trajectories differ from the reference the way two random
  *     reorderings of the reference differ from each other (profiles/r2_callback_order.txt); everything a step decides before the
  *     solver runs (pair set, contacts, islands) is the reference's.
- *     Requires nworlds == 1.  At most 62 row groups (contact pairs / permanent joints) may act on one body (the static environment has no body
+ *     Requires nworlds == 1.  At most ODEB_CANON_COLOURS - 2 = 254 row groups (contact pairs / permanent joints) may act on one body (the static environment has no body
  *     and does not count); a step that meets more fails like a capacity overflow, with the state of the last complete step kept. */
 enum { ODEB_MODE_REPLAY = 0, ODEB_MODE_CANONICAL = 1 };
 int odeb_set_solver_mode(OdebBatch *, int mode);
@@ -247,14 +247,16 @@ static inline ODEB_HD uint32_t odebi_canon_key(uint32_t seed, uint32_t island, u
     x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
     return x;
 }
-/* rank[c] = position of colour c in the visiting order of phase `phase`: colours by ascending (odeb_canon_key(seed, ~0, phase, c), c). */
-static inline ODEB_HD void odebi_canon_colour_ranks(uint32_t seed, uint32_t phase, int rank[64])
+/* rank[c] = position of colour c in the visiting order of phase `phase`: colours by ascending (odeb_canon_key(seed, ~0, phase, c), c).
+ * ODEB_CANON_COLOURS = the most colours a colouring may use: one more than the most row groups that can meet on one body. */
+#define ODEB_CANON_COLOURS 256
+static inline ODEB_HD void odebi_canon_colour_ranks(uint32_t seed, uint32_t phase, int rank[ODEB_CANON_COLOURS])
 {
-    uint32_t key[64];
-    for (int c = 0; c < 64; c++) key[c] = odebi_canon_key(seed, 0xffffffffu, phase, (uint32_t)c);
-    for (int c = 0; c < 64; c++) {
+    uint32_t key[ODEB_CANON_COLOURS];
+    for (int c = 0; c < ODEB_CANON_COLOURS; c++) key[c] = odebi_canon_key(seed, 0xffffffffu, phase, (uint32_t)c);
+    for (int c = 0; c < ODEB_CANON_COLOURS; c++) {
         int r = 0;
-        for (int d = 0; d < 64; d++) if (key[d] < key[c] || (key[d] == key[c] && d < c)) r++;
+        for (int d = 0; d < ODEB_CANON_COLOURS; d++) if (key[d] < key[c] || (key[d] == key[c] && d < c)) r++;
         rank[c] = r;
     }
 }

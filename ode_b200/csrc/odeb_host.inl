@@ -56,7 +56,7 @@ static int overflow_check(OdebBatch *B)
     const int ov = ovh[0];
     if (ov) {
         set_err("capacity overflow (%s): raise OdebWorldParams.max_pairs / max_contacts_per_world (or ODEB_MAX_PAIRS / ODEB_MAX_CONTACTS); the body state is the one the last complete step left",
-                ov == 1 ? "pairs" : ov == 2 ? "contacts" : ov == 3 ? "rows" : "row groups on one body (large-world colouring: more than 62)");
+                ov == 1 ? "pairs" : ov == 2 ? "contacts" : ov == 3 ? "rows" : "row groups on one body (large-world colouring: more than 254)");
         CK(cudaMemsetAsync(B->D.overflow, 0, sizeof(int), B->stream));
         CK(cudaStreamSynchronize(B->stream));
         return 0;

@@ -55,9 +55,9 @@ struct LargePtrs {
     int *ginc_ofs, *ginc_cur; int2 *ginc;        // [NB + 2], [NB + 2], [2 MR]: body (order position) -> (group, its priority) of the groups acting on it
     unsigned *gkey; int *gcolor, *gwin;          // [MR] at the group's first row: priority of the phase, colour (-1 none yet, -2 island finished), winner flag
     unsigned *skey, *skey_s;                     // [MR] sort keys of the groups: (colour, rows descending)
-    int *clist, *ccount, *cofs, *tstart;         // [MR] groups by (colour, rows descending); [64] groups per colour; [65] first list position / first tile of every colour
-    int *theight, *tbase, *tgroup;               // [MR/32 + 130] rows of a tile, its first tile row; [MR + 4160] first row of the group of every tile lane (-1: none)
-    int4 *tginfo;                                // [MR + 4160] beside tgroup: (rows, accumulator slot of body 1, of body 2, island)
+    int *clist, *ccount, *cofs, *tstart;         // [MR] groups by (colour, rows descending); [ODEB_CANON_COLOURS] groups per colour; [ODEB_CANON_COLOURS + 1] first list position / first tile of every colour
+    int *theight, *tbase, *tgroup;               // [MR/32 + colours + 4] rows of a tile, its first tile row; [MR + 32 colours + 64] first row of the group of every tile lane (-1: none)
+    int4 *tginfo;                                // beside tgroup: (rows, accumulator slot of body 1, of body 2, island)
     unsigned char *trec;                         // [trcap * LWT_ROW_BYTES]: per tile row the lane-interleaved compact records (LWT_QUADS x 32 quads), then the 32 lambdas
     Real *pinvm;                                 // [NB + 1] inverse mass by body order position
     int trcap;                                   // tile rows the two buffers hold
@@ -409,7 +409,7 @@ __global__ void k_lwc_ginc_fill(const __grid_constant__ DevParams P, const __gri
 __global__ void k_lwc_color_init(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L)
 {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < 64) L.ccount[t] = 0;
+    if (t < ODEB_CANON_COLOURS) L.ccount[t] = 0;
     if (t >= L.counters[LWC_NGROUPS]) return;
     const int g = L.heads[t];
     const unsigned is = (unsigned)L.row_island[g];
@@ -469,7 +469,9 @@ __global__ void __launch_bounds__(1024) k_lwc_color_rounds(const __grid_constant
             const int g = L.heads[t];
             if (__ldcg(&L.gcolor[g]) != -1 || !__ldcg(&L.gwin[g])) continue;
             const int2 rb = D.rbody[g];
-            unsigned long long used = 0;
+            u64 used[ODEB_CANON_COLOURS / 64];
+#pragma unroll
+            for (int k = 0; k < ODEB_CANON_COLOURS / 64; k++) used[k] = 0;
             for (int side = 0; side < 2; side++) {
                 const int b = side ? rb.y : rb.x;
                 if (b == P.NB) continue;
@@ -479,12 +481,16 @@ __global__ void __launch_bounds__(1024) k_lwc_color_rounds(const __grid_constant
 #pragma unroll
                     for (int k = 0; k < 4; k++) c[k] = e + k < e1 ? __ldcg(&L.gcolor[L.ginc[e + k].x]) : -1;
 #pragma unroll
-                    for (int k = 0; k < 4; k++) if (c[k] >= 0 && c[k] < 64) used |= 1ull << c[k];
+                    for (int k = 0; k < 4; k++) if (c[k] >= 0 && c[k] < ODEB_CANON_COLOURS) {
+#pragma unroll
+                        for (int q = 0; q < ODEB_CANON_COLOURS / 64; q++) if ((c[k] >> 6) == q) used[q] |= 1ull << (c[k] & 63);
+                    }
                 }
             }
-            int c = 0;
-            while (c < 63 && ((used >> c) & 1ull)) c++;
-            if (c >= 63) atomicExch(D.overflow, 4);
+            int c = ODEB_CANON_COLOURS - 1;                        // the smallest colour no coloured neighbour holds
+#pragma unroll
+            for (int q = ODEB_CANON_COLOURS / 64 - 1; q >= 0; q--) if (~used[q] != 0ull) { const int f = 64 * q + __ffsll((long long)~used[q]) - 1; if (f < c) c = f; }
+            if (c >= ODEB_CANON_COLOURS - 1) atomicExch(D.overflow, 4);   // a body with more than ODEB_CANON_COLOURS - 2 groups
             __stcg(&L.gcolor[g], c);
             atomicSub(&L.counters[LWC_UNCOLORED], 1);
             atomicMax(&L.counters[LWC_NCOLORS], c + 1);
@@ -534,14 +540,14 @@ __global__ void k_lwt_sort_keys(const __grid_constant__ LargePtrs L)
     if (t >= L.counters[LWC_NGROUPS]) return;
     const int g = L.heads[t];
     const int sz = L.gsize[g] < 4095 ? L.gsize[g] : 4095;
-    L.skey[t] = ((unsigned)L.gcolor[g] << 12) | (unsigned)(4095 - sz);
+    L.skey[t] = ((unsigned)L.gcolor[g] << 12) | (unsigned)(4095 - sz);      // 8 + 12 bits
 }
 // list offsets and first tile of every colour (one thread)
 __global__ void k_lwt_color_scan(const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L)
 {
     int o = 0, t = 0;
-    for (int c = 0; c < 64; c++) { L.cofs[c] = o; L.tstart[c] = t; o += L.ccount[c]; t += (L.ccount[c] + 31) >> 5; }
-    L.cofs[64] = o; L.tstart[64] = t;
+    for (int c = 0; c < ODEB_CANON_COLOURS; c++) { L.cofs[c] = o; L.tstart[c] = t; o += L.ccount[c]; t += (L.ccount[c] + 31) >> 5; }
+    L.cofs[ODEB_CANON_COLOURS] = o; L.tstart[ODEB_CANON_COLOURS] = t;
     L.counters[LWC_NTILES] = t;
     L.counters[LWC_SEED] = (int)D.seed[0];
 }
@@ -551,7 +557,12 @@ __global__ void __launch_bounds__(128) k_lwt_tiles(const __grid_constant__ DevPa
     const int tile = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (tile >= L.counters[LWC_NTILES]) return;
     int c = 0;
-    while (c < 63 && tile >= L.tstart[c + 1]) c++;
+    {   // the colour whose tile range holds this tile (tstart is ascending)
+        int lo = 0, hi = ODEB_CANON_COLOURS - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (tile >= L.tstart[mid]) lo = mid; else hi = mid - 1; }
+        c = lo;
+        while (c < ODEB_CANON_COLOURS - 1 && L.tstart[c + 1] <= tile) c++;   // skip empty colours that start at the same tile
+    }
     const int pos = L.cofs[c] + ((tile - L.tstart[c]) << 5) + lane;
     int4 gi = make_int4(0, 0, P.NB, 0);                            // (rows, body 1, body 2, island); rows == 0: empty lane
     int g = -1;
@@ -690,8 +701,8 @@ __device__ __forceinline__ void lwt_mbar_wait(unsigned bar, unsigned parity)
 // bodies' accumulators (L2 hits).  Everything another block may have written is read with ld.cg (L1 is not coherent across the barrier).
 struct LwPhase {
     int norder;                                  // colours that have tiles, in the phase's visiting order
-    int corder[64];
-    int tstart[65];                              // first tile of every colour
+    int corder[ODEB_CANON_COLOURS];
+    int tstart[ODEB_CANON_COLOURS + 1];          // first tile of every colour
     int nordered, nislands;
     unsigned iteration, extra;
 };

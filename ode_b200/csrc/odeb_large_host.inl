@@ -36,11 +36,12 @@ static int large_prepare(OdebBatch *B)
            && dev_alloc(B, &L.row_island, MR) && dev_alloc(B, &L.row_group, MR) && dev_alloc(B, &L.gsize, MR) && dev_alloc(B, &L.heads, MR)
            && dev_alloc(B, &L.ginc_ofs, NB + 2) && dev_alloc(B, &L.ginc_cur, NB + 2) && dev_alloc(B, &L.ginc, 2 * MR)
            && dev_alloc(B, &L.gkey, MR) && dev_alloc(B, &L.gcolor, MR) && dev_alloc(B, &L.gwin, MR)
-           && dev_alloc(B, &L.clist, MR) && dev_alloc(B, &L.ccount, 64) && dev_alloc(B, &L.cofs, 65) && dev_alloc(B, &L.tstart, 65)
+           && dev_alloc(B, &L.clist, MR) && dev_alloc(B, &L.ccount, ODEB_CANON_COLOURS) && dev_alloc(B, &L.cofs, ODEB_CANON_COLOURS + 1) && dev_alloc(B, &L.tstart, ODEB_CANON_COLOURS + 1)
            && dev_alloc(B, &L.skey, MR) && dev_alloc(B, &L.skey_s, MR)
-           && dev_alloc(B, &L.theight, MR / 32 + 130) && dev_alloc(B, &L.tbase, MR / 32 + 130) && dev_alloc(B, &L.tgroup, MR + 4160) && dev_alloc(B, &L.tginfo, MR + 4160);
+           && dev_alloc(B, &L.theight, MR / 32 + ODEB_CANON_COLOURS + 4) && dev_alloc(B, &L.tbase, MR / 32 + ODEB_CANON_COLOURS + 4)
+           && dev_alloc(B, &L.tgroup, MR + 32 * ODEB_CANON_COLOURS + 64) && dev_alloc(B, &L.tginfo, MR + 32 * ODEB_CANON_COLOURS + 64);   // every colour ends with a partial tile
     // tile rows: every row once, plus the padding of tiles whose groups differ in size (sorted by size: a few tile heights per colour)
-    L.trcap = (int)((MR + MR / 4 + 32768 + 31) / 32);
+    L.trcap = (int)((MR + MR / 4 + 32 * ODEB_CANON_COLOURS * 16 + 31) / 32);
     ok = ok && dev_alloc(B, &L.trec, (size_t)L.trcap * LWT_ROW_BYTES) && dev_alloc(B, &L.pinvm, NB + 1);
     if (!ok) return 0;
     L.tmp_bytes = large_cub_bytes(P);
@@ -194,7 +195,7 @@ static int large_step(OdebBatch *B)
         unsigned iteration = 0, extra = 0;
         // the step's colouring: rounds in batches of 8, until no group is left uncoloured
         LCK(cudaMemsetAsync(L.counters + LWC_UNCOLORED, 0, 2 * sizeof(int), s));
-        k_lwc_color_init<<<nblk(ngroups > 64 ? ngroups : 64, 256), 256, 0, s>>>(P, D, L);
+        k_lwc_color_init<<<nblk(ngroups > ODEB_CANON_COLOURS ? ngroups : ODEB_CANON_COLOURS, 256), 256, 0, s>>>(P, D, L);
         B->launches++;
         {
             if (B->lwc_grid == 0) {
@@ -213,21 +214,23 @@ static int large_step(OdebBatch *B)
             B->launches++;
         }
         // tiles: groups by (colour, rows descending), 32 per tile; records and lambdas into the lane-interleaved layout
-        int tstart[65];
+        int tstart[ODEB_CANON_COLOURS + 1];
         k_lwt_sort_keys<<<nblk(ngroups, 256), 256, 0, s>>>(L);
-        LCK(cub::DeviceRadixSort::SortPairs(L.tmp, L.tmp_bytes, L.skey, L.skey_s, L.heads, L.clist, ngroups, 0, 18, s));
+        LCK(cub::DeviceRadixSort::SortPairs(L.tmp, L.tmp_bytes, L.skey, L.skey_s, L.heads, L.clist, ngroups, 0, 20, s));
         k_lwt_color_scan<<<1, 1, 0, s>>>(D, L);
         LCK(cudaMemcpyAsync(tstart, L.tstart, sizeof(tstart), cudaMemcpyDeviceToHost, s));
         LCK(cudaMemcpyAsync(hc, L.counters, sizeof(hc), cudaMemcpyDeviceToHost, s));
+        LCK(cudaMemcpyAsync(B->h_ov, D.overflow, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
         LCK(cudaStreamSynchronize(s));
-        const int ntiles = tstart[64], ncolors = hc[LWC_NCOLORS];
+        if (B->h_ov[0] == 4) return overflow_check(B);          // a colouring that ran out of colours is not a colouring: stop before any sweep
+        const int ntiles = tstart[ODEB_CANON_COLOURS], ncolors = hc[LWC_NCOLORS];
         const unsigned step_seed = (unsigned)hc[LWC_SEED];
         k_lwt_tiles<<<nblk(ntiles * 32, 128), 128, 0, s>>>(P, D, L);
         LCK(cub::DeviceScan::ExclusiveSum(L.tmp, L.tmp_bytes, L.theight, L.tbase, ntiles + 1, s));
         k_lwt_finish<<<ntiles, 128, 0, s>>>(P, D, L);
         B->launches += 6;
         const size_t lw_tma_smem = (size_t)LWT_WARPS * LWT_STAGES * LWT_STAGE_BYTES + (size_t)LWT_WARPS * LWT_STAGES * sizeof(unsigned long long);
-        int corder[64];
+        int corder[ODEB_CANON_COLOURS];
         if (B->timing) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s); }   // the sweeps proper (what odeb_solver_ms reports)
         {
             // persistent phases: one cooperative launch per 8 sweeps
@@ -240,20 +243,20 @@ static int large_step(OdebBatch *B)
                 if (B->lw_grid <= 0) { set_err("k_lwt_phase does not fit an SM"); return 0; }
             }
             int maxnt = 1;
-            for (int c = 0; c < ncolors && c < 64; c++) if (tstart[c + 1] - tstart[c] > maxnt) maxnt = tstart[c + 1] - tstart[c];
+            for (int c = 0; c < ncolors && c < ODEB_CANON_COLOURS; c++) if (tstart[c + 1] - tstart[c] > maxnt) maxnt = tstart[c + 1] - tstart[c];
             int grid = (maxnt + LWT_WARPS - 1) / LWT_WARPS;
             { const int by_bodies = (nordered + 32 * LWT_WARPS - 1) / (32 * LWT_WARPS); if (by_bodies > grid) grid = by_bodies; }
             if (grid > B->lw_grid) grid = B->lw_grid;
             if (B->lw_maxgrid > 0 && grid > B->lw_maxgrid) grid = B->lw_maxgrid;
             LwPhase ph;
-            for (int c = 0; c < 65; c++) ph.tstart[c] = tstart[c];
+            for (int c = 0; c <= ODEB_CANON_COLOURS; c++) ph.tstart[c] = tstart[c];
             ph.nordered = nordered; ph.nislands = T;
             for (;;) {
-                int rank[64];
+                int rank[ODEB_CANON_COLOURS];
                 odebi_canon_colour_ranks(step_seed, iteration >> 3, rank);
-                for (int c = 0; c < 64; c++) corder[rank[c]] = c;
+                for (int c = 0; c < ODEB_CANON_COLOURS; c++) corder[rank[c]] = c;
                 ph.norder = 0;
-                for (int k = 0; k < 64; k++) { const int c = corder[k]; if (c < ncolors && tstart[c + 1] > tstart[c]) ph.corder[ph.norder++] = c; }
+                for (int k = 0; k < ODEB_CANON_COLOURS; k++) { const int c = corder[k]; if (c < ncolors && tstart[c + 1] > tstart[c]) ph.corder[ph.norder++] = c; }
                 ph.iteration = iteration; ph.extra = extra;
                 LCK(cudaMemsetAsync(L.counters + LWC_GBAR, 0, sizeof(int), s));
                 void *args[4] = { (void *)&P, (void *)&D, (void *)&L, (void *)&ph };

@@ -704,14 +704,14 @@ static void canonical_colours(unsigned seed, unsigned island, unsigned m, int nb
         std::vector<int> picked(winners.size());
         for (size_t k = 0; k < winners.size(); k++) {
             const int g = winners[k];
-            unsigned long long used = 0;                       // colours 0..63 held by coloured neighbours (a body carries far fewer groups)
+            bool used[ODEB_CANON_COLOURS] = { false };         // colours held by coloured neighbours
             for (int side = 0; side < 2; side++) {
                 const int b = jb[2 * g + side];
                 if (b < 0) continue;
-                for (size_t t = 0; t < on_body[b].size(); t++) { const int c = colour[on_body[b][t]]; if (c >= 0 && c < 64) used |= 1ull << c; }
+                for (size_t t = 0; t < on_body[b].size(); t++) { const int c = colour[on_body[b][t]]; if (c >= 0 && c < ODEB_CANON_COLOURS) used[c] = true; }
             }
             int c = 0;
-            while (c < 63 && ((used >> c) & 1ull)) c++;
+            while (c < ODEB_CANON_COLOURS - 1 && used[c]) c++;
             picked[k] = c;
         }
         for (size_t k = 0; k < winners.size(); k++) colour[winners[k]] = picked[k];
@@ -719,11 +719,11 @@ static void canonical_colours(unsigned seed, unsigned island, unsigned m, int nb
     }
 }
 // Sweep order of phase k (the 8 sweeps from sweep 8k on): the colours are visited in ascending (odeb_canon_key(seed, ~0, k, colour), colour)
-// -- one permutation of the 64 colour numbers per phase, the same for every island --, the groups of a colour by ascending first row, the
+// -- one permutation of the colour numbers per phase, the same for every island --, the groups of a colour by ascending first row, the
 // rows of a group in row order (a contact's normal row right before its friction rows).
 static void canonical_order(unsigned seed, unsigned phase, unsigned m, const std::vector<int> &grp, const std::vector<int> &colour, std::vector<int> &order)
 {
-    int rank[64];
+    int rank[ODEB_CANON_COLOURS];
     odebi_canon_colour_ranks(seed, phase, rank);
     for (unsigned r = 0; r < m; r++) order[r] = (int)r;
     std::sort(order.begin(), order.begin() + m, [&](int a, int b) {

@@ -230,23 +230,39 @@ def test_canonical_mode_more_tiles_than_warps(maxgrid, monkeypatch):
             b.close()
 
 
-def test_canonical_mode_reports_too_many_groups_on_one_body():
-    """The colouring of the large-world path holds at most 62 row groups (contact pairs / joints) on one BODY (the static plane has no body and
-    does not count): a platform carrying 81 boxes is refused loudly, and the state stays the one of the last complete step."""
+def _platform_scene(nside):
+    """a dynamic platform on the plane carrying nside x nside unit boxes: nside^2 + 1 row groups act on the platform's body"""
     sc = B.Scene(B.default_world_params(gravity=(0, 0, -9.81), max_contacts=4, surf_mode=B.CONTACT_APPROX1, mu=0.5), 1)
     sc.add_geom(B.PLANE, (0, 0, 1, 0))
-    m, I = B.box_mass(1.0, 20, 20, 0.5)
+    side = 2.0 * nside + 2.0
+    m, I = B.box_mass(1.0, side, side, 0.5)
     p = sc.add_body(m, I, (0, 0, 0.25))
-    sc.add_geom(B.BOX, (20, 20, 0.5), body=p)
+    sc.add_geom(B.BOX, (side, side, 0.5), body=p)
     m, I = B.box_mass(1.0, 1, 1, 1)
-    for i in range(81):
-        bb = sc.add_body(m, I, ((i % 9) * 2.0 - 8.0, (i // 9) * 2.0 - 8.0, 1.0))
+    for i in range(nside * nside):
+        bb = sc.add_body(m, I, ((i % nside) * 2.0 - (nside - 1.0), (i // nside) * 2.0 - (nside - 1.0), 1.0))
         sc.add_geom(B.BOX, (1, 1, 1), body=bb)
-    n = 82
+    n = nside * nside + 1
     pos = np.asarray(sc.body_pos, dtype=np.float64)[None]
     quat = np.tile(np.array([1.0, 0, 0, 0])[None, None], (1, n, 1))
     sc.state = dict(pos=pos, quat=quat, lvel=np.zeros_like(pos), avel=np.zeros_like(pos))
     sc.seeds = np.array([7], dtype=np.uint32)
+    return sc
+
+
+def test_canonical_mode_many_groups_on_one_body():
+    """A body that carries many contact pairs needs as many colours (every group on it conflicts with every other one): 82 groups on the
+    platform of a 9 x 9 load -> more than 82 colours, bit-identical to the oracle; beyond ODEB_CANON_COLOURS - 2 = 254 groups on one body
+    the step is refused loudly and the state stays the one of the last complete step."""
+    sc = _platform_scene(9)
+    a, b = _canon_pair("single", sc)
+    for s in range(12):
+        a.step(0.01)
+        b.step(0.01)
+        bad = compare_step(a, b, 1)
+        assert not bad, (s, bad)
+    b.close()
+    sc = _platform_scene(16)
     b = B.Batch(gpu_lib("single"), sc)
     b.set_solver_mode(1)
     before = b.get_state()
