@@ -31,7 +31,7 @@ struct OdebBatch {
     cudaGraphExec_t graph; double graph_h; bool use_graph; int graph_cfg;
     // solver selection: 0 = k_solve (one row at a time per world), 1..3 = k_solve5<2/4/8> (static P-processor schedule),
     // 4 = k_solve_bl (one lane per body). hint_m = largest island (rows) seen since the last sync, read back in odeb_sync.
-    int s5_sr[4]; size_t s5_smem[4]; int hint_m; int solver_force; int lw_variant, lw_grid, lwc_grid, lw_maxgrid;   // lw_maxgrid: ODEB_LW_MAXGRID (tests: fewer blocks than tiles, so that warps walk several tiles per colour)
+    int s5_sr[4]; size_t s5_smem[4]; int hint_m; int solver_force; int lw_grid, lwc_grid, lw_maxgrid;   // lw_maxgrid: ODEB_LW_MAXGRID (tests: fewer blocks than tiles, so that warps walk several tiles per colour)
     bool rows_std3;                               // every joint is a contact of exactly three rows (normal + two friction directions): k_rows_t<true, true>
     bool env_no_solve6, env_no_hybrid, env_no_fused_rows; int env_hy_rows;   // experiment / test switches, read once at creation (ODEB_NO_SOLVE6, ODEB_NO_HYBRID, ODEB_NO_FUSED_ROWS, ODEB_TEST_HY_ROWS)   // s5_sr / s5_smem: row budget and shared memory of k_solve5<2^k> for the next launch
     int s6_sr, s6_nbi; size_t s6_smem;        // k_solve6<P> (odeb_solve6.cuh): row / body budget per island and shared memory per warp for the next launch
@@ -359,7 +359,7 @@ static OdebBatch *batch_build(const OdebWorldParams *wp, const HostTemplate &T, 
     OdebBatch *B = new OdebBatch();
     B->device = device; B->bytes = 0; B->launches = 0; B->timing = false; B->solver_ms = 0; B->solver_launches = 0;
     B->mode = ODEB_MODE_REPLAY; B->large_ready = false; memset(&B->L, 0, sizeof(B->L));
-    B->graph = 0; B->graph_h = -1; B->graph_cfg = -1; B->graph_sr = -1; B->hint_m = 0; B->hint_nb = 0; B->hint_nis = 0; B->s6_sr = 0; B->s6_nbi = 0; B->s6_smem = 0; B->solver_force = -1; B->lw_variant = getenv("ODEB_LW_SWEEP") ? atoi(getenv("ODEB_LW_SWEEP")) : 3; B->lw_grid = 0; B->lwc_grid = 0; B->lw_maxgrid = getenv("ODEB_LW_MAXGRID") ? atoi(getenv("ODEB_LW_MAXGRID")) : 0; B->env_no_solve6 = getenv("ODEB_NO_SOLVE6") != 0; B->env_no_hybrid = getenv("ODEB_NO_HYBRID") != 0; B->env_no_fused_rows = getenv("ODEB_NO_FUSED_ROWS") != 0; B->env_hy_rows = getenv("ODEB_TEST_HY_ROWS") ? atoi(getenv("ODEB_TEST_HY_ROWS")) : 0; B->use_graph = getenv("ODEB_NO_GRAPH") == 0 && !classic; B->h_stage = 0; B->h_ov = 0; B->fb_jcopy = 0; B->fb_jfb = 0; B->own_stream = true; B->d_stage = 0; B->stream = 0; B->flush_buf = 0; B->flush_bytes = 0;
+    B->graph = 0; B->graph_h = -1; B->graph_cfg = -1; B->graph_sr = -1; B->hint_m = 0; B->hint_nb = 0; B->hint_nis = 0; B->s6_sr = 0; B->s6_nbi = 0; B->s6_smem = 0; B->solver_force = -1; B->lw_grid = 0; B->lwc_grid = 0; B->lw_maxgrid = getenv("ODEB_LW_MAXGRID") ? atoi(getenv("ODEB_LW_MAXGRID")) : 0; B->env_no_solve6 = getenv("ODEB_NO_SOLVE6") != 0; B->env_no_hybrid = getenv("ODEB_NO_HYBRID") != 0; B->env_no_fused_rows = getenv("ODEB_NO_FUSED_ROWS") != 0; B->env_hy_rows = getenv("ODEB_TEST_HY_ROWS") ? atoi(getenv("ODEB_TEST_HY_ROWS")) : 0; B->use_graph = getenv("ODEB_NO_GRAPH") == 0 && !classic; B->h_stage = 0; B->h_ov = 0; B->fb_jcopy = 0; B->fb_jfb = 0; B->own_stream = true; B->d_stage = 0; B->stream = 0; B->flush_buf = 0; B->flush_bytes = 0;
     memset(&B->D, 0, sizeof(B->D));
     DevParams &P = B->P;
     memset(&P, 0, sizeof(P));
