@@ -686,10 +686,12 @@ __device__ __forceinline__ void lwt_mbar_wait(unsigned bar, unsigned parity)
     asm volatile("{\n\t.reg .pred p;\n\tLWT_WAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra LWT_DONE_%=;\n\tbra LWT_WAIT_%=;\n\tLWT_DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
 #define LWT_STAGES 6
+#ifndef LWT_WARPS
 #if defined(ODEB_DOUBLE)
 #define LWT_WARPS 2
 #else
 #define LWT_WARPS 4
+#endif
 #endif
 #define LWT_STAGE_BYTES LWT_ROW_BYTES
 // A whole PHASE (up to 8 sweeps: every colour in the phase's order, the per-body convergence test and the per-island iteration control

@@ -1,6 +1,6 @@
 #!/bin/bash
 cd /root/repo
-for v in "" lwfull ""; do
+for v in "" ""; do
 python - "$v" <<'PY'
 import sys, os, ctypes as C
 if sys.argv[1]: os.environ["ODEB_LIB_DIR"] = "/root/repo/ode_b200/variants/" + sys.argv[1]
