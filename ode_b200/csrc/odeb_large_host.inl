@@ -252,11 +252,16 @@ static int large_step(OdebBatch *B)
             for (int c = 0; c <= ODEB_CANON_COLOURS; c++) ph.tstart[c] = tstart[c];
             ph.nordered = nordered; ph.nislands = T;
             for (;;) {
-                int rank[ODEB_CANON_COLOURS];
-                odebi_canon_colour_ranks(step_seed, iteration >> 3, rank);
-                for (int c = 0; c < ODEB_CANON_COLOURS; c++) corder[rank[c]] = c;
-                ph.norder = 0;
-                for (int k = 0; k < ODEB_CANON_COLOURS; k++) { const int c = corder[k]; if (c < ncolors && tstart[c + 1] > tstart[c]) ph.corder[ph.norder++] = c; }
+                // the phase's visiting order (odebi_canon_colour_ranks, restricted to the colours in use: the same relative order)
+                {
+                    std::pair<uint32_t, int> ck[ODEB_CANON_COLOURS];
+                    const int nc = ncolors < ODEB_CANON_COLOURS ? ncolors : ODEB_CANON_COLOURS;
+                    for (int c = 0; c < nc; c++) ck[c] = std::make_pair(odebi_canon_key(step_seed, 0xffffffffu, iteration >> 3, (uint32_t)c), c);
+                    std::sort(ck, ck + nc);
+                    for (int k = 0; k < nc; k++) corder[k] = ck[k].second;
+                    ph.norder = 0;
+                    for (int k = 0; k < nc; k++) { const int c = corder[k]; if (tstart[c + 1] > tstart[c]) ph.corder[ph.norder++] = c; }
+                }
                 ph.iteration = iteration; ph.extra = extra;
                 LCK(cudaMemsetAsync(L.counters + LWC_GBAR, 0, sizeof(int), s));
                 void *args[4] = { (void *)&P, (void *)&D, (void *)&L, (void *)&ph };
