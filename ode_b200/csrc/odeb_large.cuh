@@ -33,7 +33,7 @@ typedef unsigned long long u64;
 #define LW_NOKEY 0xFFFFFFFFFFFFFFFFull
 
 enum { LWC_NBIG = 0, LWC_NPAIRS = 1, LWC_NCONTACTS = 2, LWC_NORDERED = 3, LWC_NJORD = 4, LWC_MROWS = 5, LWC_NISLANDS = 6,
-       LWC_NACTIVE = 7, LWC_NGROUPS = 8, LWC_UNCOLORED = 9, LWC_NCOLORS = 10, LWC_NTILES = 11, LWC_SEED = 12, LWC_GBAR = 13, LWC_ITER = 14, LWC_EXTRA = 15, LWC_TERM = 16, LWC_COUNT = 20 };
+       LWC_NACTIVE = 7, LWC_NGROUPS = 8, LWC_UNCOLORED = 9, LWC_NCOLORS = 10, LWC_NTILES = 11, LWC_SEED = 12, LWC_GBAR = 13, LWC_ITER = 14, LWC_EXTRA = 15, LWC_TERM = 16, LWC_PBAR = 20 /* one barrier counter per phase launch, 12 of them */, LWC_COUNT = 32 };
 
 struct LargePtrs {
     int *counters;                               // [LWC_COUNT]
@@ -706,7 +706,7 @@ struct LwPhase {
     int corder[ODEB_CANON_COLOURS];
     int tstart[ODEB_CANON_COLOURS + 1];          // first tile of every colour
     int nordered, nislands;
-    unsigned iteration, extra;
+    int phase;                                   // 0, 1, ...: this launch runs the sweeps 8 phase .. 8 phase + 7 (if the solve gets that far)
 };
 __global__ void __launch_bounds__(32 * LWT_WARPS) k_lwt_phase(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L, const __grid_constant__ LwPhase ph)
 {
@@ -725,7 +725,10 @@ __global__ void __launch_bounds__(32 * LWT_WARPS) k_lwt_phase(const __grid_const
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    unsigned *gbar = (unsigned *)&L.counters[LWC_GBAR];
+    // All phases of a step are queued back to back (no host round trip in between); a phase whose predecessors ended the solve returns at
+    // once.  Iteration state travels in the counters (written by the previous launch: kernel boundary).
+    if (L.counters[LWC_TERM] || L.counters[LWC_NACTIVE] == 0 || L.counters[LWC_ITER] != 8 * ph.phase) return;
+    unsigned *gbar = (unsigned *)&L.counters[LWC_PBAR + ph.phase];
     unsigned gtarget = 0;
     unsigned ri = 0, rc = 0;                                       // tile rows requested / consumed by this warp so far (ring position and mbarrier parity)
     // the warp's pending item (sweep, position in the colour order, tile) and the state of the tile that was begun for it
@@ -767,7 +770,7 @@ __global__ void __launch_bounds__(32 * LWT_WARPS) k_lwt_phase(const __grid_const
         ri += issued;
     };
     if (any_items) tile_begin(it_tile);
-    unsigned iteration = ph.iteration, extra = ph.extra;
+    unsigned iteration = (unsigned)L.counters[LWC_ITER], extra = (unsigned)L.counters[LWC_EXTRA];
     Real exit_delta = extra ? P.extra_delta : P.premature_delta;
     int terminated = 0;
     Real4 *cf = D.cforce;

@@ -192,7 +192,7 @@ static int large_step(OdebBatch *B)
         B->launches += 4;
         // ---------------- SOR sweeps
         cudaEvent_t e0 = 0, e1 = 0;
-        unsigned iteration = 0, extra = 0;
+        
         // the step's colouring: rounds in batches of 8, until no group is left uncoloured
         LCK(cudaMemsetAsync(L.counters + LWC_UNCOLORED, 0, 2 * sizeof(int), s));
         k_lwc_color_init<<<nblk(ngroups > ODEB_CANON_COLOURS ? ngroups : ODEB_CANON_COLOURS, 256), 256, 0, s>>>(P, D, L);
@@ -251,27 +251,24 @@ static int large_step(OdebBatch *B)
             LwPhase ph;
             for (int c = 0; c <= ODEB_CANON_COLOURS; c++) ph.tstart[c] = tstart[c];
             ph.nordered = nordered; ph.nislands = T;
-            for (;;) {
+            // every phase the solve can need, queued back to back; a launch whose predecessors finished the solve returns at once
+            const int nphases = (int)((P.num_iter + P.max_extra + 7) / 8);
+            if (nphases > 12) { set_err("ODEB_MODE_CANONICAL: more than 96 sweeps per step are not supported"); return 0; }
+            for (int phase = 0; phase < nphases; phase++) {
                 // the phase's visiting order (odebi_canon_colour_ranks, restricted to the colours in use: the same relative order)
-                {
-                    std::pair<uint32_t, int> ck[ODEB_CANON_COLOURS];
-                    const int nc = ncolors < ODEB_CANON_COLOURS ? ncolors : ODEB_CANON_COLOURS;
-                    for (int c = 0; c < nc; c++) ck[c] = std::make_pair(odebi_canon_key(step_seed, 0xffffffffu, iteration >> 3, (uint32_t)c), c);
-                    std::sort(ck, ck + nc);
-                    for (int k = 0; k < nc; k++) corder[k] = ck[k].second;
-                    ph.norder = 0;
-                    for (int k = 0; k < nc; k++) { const int c = corder[k]; if (tstart[c + 1] > tstart[c]) ph.corder[ph.norder++] = c; }
-                }
-                ph.iteration = iteration; ph.extra = extra;
-                LCK(cudaMemsetAsync(L.counters + LWC_GBAR, 0, sizeof(int), s));
+                std::pair<uint32_t, int> ck[ODEB_CANON_COLOURS];
+                const int nc = ncolors < ODEB_CANON_COLOURS ? ncolors : ODEB_CANON_COLOURS;
+                for (int c = 0; c < nc; c++) ck[c] = std::make_pair(odebi_canon_key(step_seed, 0xffffffffu, (uint32_t)phase, (uint32_t)c), c);
+                std::sort(ck, ck + nc);
+                for (int k = 0; k < nc; k++) corder[k] = ck[k].second;
+                ph.norder = 0;
+                for (int k = 0; k < nc; k++) { const int c = corder[k]; if (tstart[c + 1] > tstart[c]) ph.corder[ph.norder++] = c; }
+                ph.phase = phase;
                 void *args[4] = { (void *)&P, (void *)&D, (void *)&L, (void *)&ph };
                 LCK(cudaLaunchCooperativeKernel((const void *)k_lwt_phase, dim3(grid), dim3(32 * LWT_WARPS), args, lw_tma_smem, s));
                 B->launches++;
-                LCK(cudaMemcpyAsync(hc, L.counters, sizeof(hc), cudaMemcpyDeviceToHost, s));
-                LCK(cudaStreamSynchronize(s));
-                iteration = (unsigned)hc[LWC_ITER]; extra = (unsigned)hc[LWC_EXTRA];
-                if (hc[LWC_TERM] || hc[LWC_NACTIVE] == 0) break;
             }
+
         }
         if (B->timing) { cudaEventRecord(e1, s); B->pending.push_back(std::make_pair(e0, e1)); }
         if (D.jcopy) { k_lwt_lambda_out<<<ntiles, 128, 0, s>>>(D, L); B->launches++; }
