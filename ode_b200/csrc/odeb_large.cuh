@@ -694,6 +694,14 @@ __device__ __forceinline__ void lwt_mbar_wait(unsigned bar, unsigned parity)
 #endif
 #endif
 #define LWT_STAGE_BYTES LWT_ROW_BYTES
+// small worlds: ONE block of LWT_SMALL_WARPS warps holds every tile of a colour, the colours are separated by __syncthreads (~0.1 us) instead of
+// the grid barrier (~2 us of L2 round trips): a 1000-body pile spends most of its step in those barriers otherwise
+#if defined(ODEB_DOUBLE)
+#define LWT_SMALL_WARPS 8
+#else
+#define LWT_SMALL_WARPS 16
+#endif
+#define LWT_SMALL_STAGES 4
 // A whole PHASE (up to 8 sweeps: every colour in the phase's order, the per-body convergence test and the per-island iteration control
 // after each sweep) as one persistent cooperative launch.  ncu on the launch-per-colour version: a colour costs ~9 us however few tiles
 // it has (launch, tile lookup, first DRAM round trip, 12 dependent rows) and only ~8 us more for 46 MB of records -- latency, not
@@ -708,20 +716,26 @@ struct LwPhase {
     int nordered, nislands;
     int phase;                                   // 0, 1, ...: this launch runs the sweeps 8 phase .. 8 phase + 7 (if the solve gets that far)
 };
-__global__ void __launch_bounds__(32 * LWT_WARPS) k_lwt_phase(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L, const __grid_constant__ LwPhase ph)
+// a single-block launch (small worlds: every colour fits the block's warps) synchronises with the block barrier alone
+__device__ __forceinline__ void lwt_sync(unsigned *bar, unsigned &target)
+{
+    if (gridDim.x == 1) __syncthreads(); else lwc_grid_sync(bar, target);
+}
+template <int WARPS, int STAGES>
+__global__ void __launch_bounds__(32 * WARPS) k_lwt_phase_t(const __grid_constant__ DevParams P, const __grid_constant__ DevPtrs D, const __grid_constant__ LargePtrs L, const __grid_constant__ LwPhase ph)
 {
     extern __shared__ __align__(128) unsigned char lwt_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int gw = blockIdx.x * LWT_WARPS + wib, TW = gridDim.x * LWT_WARPS;
+    const int gw = blockIdx.x * WARPS + wib, TW = gridDim.x * WARPS;
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, GT = gridDim.x * blockDim.x;
-    unsigned char *ring = lwt_smem + (size_t)wib * LWT_STAGES * LWT_STAGE_BYTES;
-    unsigned long long *bars = (unsigned long long *)(lwt_smem + (size_t)LWT_WARPS * LWT_STAGES * LWT_STAGE_BYTES) + wib * LWT_STAGES;
+    unsigned char *ring = lwt_smem + (size_t)wib * STAGES * LWT_STAGE_BYTES;
+    unsigned long long *bars = (unsigned long long *)(lwt_smem + (size_t)WARPS * STAGES * LWT_STAGE_BYTES) + wib * STAGES;
     const unsigned bar0 = (unsigned)__cvta_generic_to_shared(bars);
     const unsigned ring0 = (unsigned)__cvta_generic_to_shared(ring);
     constexpr unsigned RB = 32 * LWT_QUADS * (unsigned)sizeof(Real4), LB = 32 * (unsigned)sizeof(Real);
     if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < LWT_STAGES; s++) lwt_mbar_init(bar0 + 8 * s, 1);
+        for (int s = 0; s < STAGES; s++) lwt_mbar_init(bar0 + 8 * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -759,10 +773,10 @@ __global__ void __launch_bounds__(32 * LWT_WARPS) k_lwt_phase(const __grid_const
                 im1 = L.pinvm[gi.z];
             }
         }
-        issued = height < LWT_STAGES - 1 ? height : LWT_STAGES - 1;
+        issued = height < STAGES - 1 ? height : STAGES - 1;
         if (lane == 0) {
             for (int k = 0; k < issued; k++) {
-                const unsigned s = (ri + k) % LWT_STAGES;
+                const unsigned s = (ri + k) % STAGES;
                 lwt_mbar_expect_tx(bar0 + 8 * s, RB + LB);
                 lwt_bulk_g2s(ring0 + s * LWT_STAGE_BYTES, rec + (size_t)k * LWT_ROW_BYTES, RB + LB, bar0 + 8 * s);
             }
@@ -790,8 +804,8 @@ __global__ void __launch_bounds__(32 * LWT_WARPS) k_lwt_phase(const __grid_const
                 unsigned char *lamp = rec + LWT_LAM_OFS + lane * sizeof(Real);
                 int free_k = -1; Real free_lambda = 0;
                 for (int k = 0; k < height; k++) {
-                    const unsigned s = rc % LWT_STAGES;
-                    lwt_mbar_wait(bar0 + 8 * s, (rc / LWT_STAGES) & 1u);
+                    const unsigned s = rc % STAGES;
+                    lwt_mbar_wait(bar0 + 8 * s, (rc / STAGES) & 1u);
                     if (run && k < sz) {
                         const Real4 *st = (const Real4 *)(ring + (size_t)s * LWT_STAGE_BYTES) + lane;
                         const Real4 c0 = st[0], c1 = st[32], c2 = st[64], c3 = st[96], c4 = st[128];
@@ -802,7 +816,7 @@ __global__ void __launch_bounds__(32 * LWT_WARPS) k_lwt_phase(const __grid_const
                     __syncwarp();
                     if (issued < height) {
                         if (lane == 0) {
-                            const unsigned sn = ri % LWT_STAGES;
+                            const unsigned sn = ri % STAGES;
                             lwt_mbar_expect_tx(bar0 + 8 * sn, RB + LB);
                             lwt_bulk_g2s(ring0 + sn * LWT_STAGE_BYTES, rec + (size_t)issued * LWT_ROW_BYTES, RB + LB, bar0 + 8 * sn);
                         }
@@ -829,7 +843,7 @@ __global__ void __launch_bounds__(32 * LWT_WARPS) k_lwt_phase(const __grid_const
                     if (it_sw < 8) tile_begin(it_tile);
                 }
             }
-            lwc_grid_sync(gbar, gtarget);
+            lwt_sync(gbar, gtarget);
         }
         // ---- end of the sweep: iteration control quickstep.cpp:1832-1855, :3253-3285 (k_lw_body_check + k_lw_island_ctl)
         ++iteration;
@@ -847,7 +861,7 @@ __global__ void __launch_bounds__(32 * LWT_WARPS) k_lwt_phase(const __grid_const
                 v.z = 0; v.w = 0;
                 stcg4(&cf[2 * k + 1], v);
             }
-            lwc_grid_sync(gbar, gtarget);
+            lwt_sync(gbar, gtarget);
         }
         for (int is = gtid; is < ph.nislands; is += GT) {
             if (__ldcg(&L.isl_done[is])) continue;
@@ -868,12 +882,12 @@ __global__ void __launch_bounds__(32 * LWT_WARPS) k_lwt_phase(const __grid_const
             if (done) { __stcg(&L.isl_done[is], 1); atomicSub(&L.counters[LWC_NACTIVE], 1); }
             else if (iteration >= 8 && (iteration & 7) == 0) atomicAdd(&L.draws[0], (u64)(m - 1));
         }
-        lwc_grid_sync(gbar, gtarget);
+        lwt_sync(gbar, gtarget);
         if (terminate_all) { terminated = 1; break; }
         if (__ldcg(&L.counters[LWC_NACTIVE]) == 0) break;
     }
     // bulk copies of a tile that was begun for a sweep that does not take place must land before the block retires
-    while (rc < ri) { lwt_mbar_wait(bar0 + 8 * (rc % LWT_STAGES), (rc / LWT_STAGES) & 1u); rc++; }
+    while (rc < ri) { lwt_mbar_wait(bar0 + 8 * (rc % STAGES), (rc / STAGES) & 1u); rc++; }
     if (gtid == 0) { L.counters[LWC_ITER] = (int)iteration; L.counters[LWC_EXTRA] = (int)extra; L.counters[LWC_TERM] = terminated; }
 }
 

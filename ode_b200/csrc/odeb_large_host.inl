@@ -230,14 +230,16 @@ static int large_step(OdebBatch *B)
         k_lwt_finish<<<ntiles, 128, 0, s>>>(P, D, L);
         B->launches += 6;
         const size_t lw_tma_smem = (size_t)LWT_WARPS * LWT_STAGES * LWT_STAGE_BYTES + (size_t)LWT_WARPS * LWT_STAGES * sizeof(unsigned long long);
+        const size_t lw_small_smem = (size_t)LWT_SMALL_WARPS * LWT_SMALL_STAGES * LWT_STAGE_BYTES + (size_t)LWT_SMALL_WARPS * LWT_SMALL_STAGES * sizeof(unsigned long long);
         int corder[ODEB_CANON_COLOURS];
         if (B->timing) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s); }   // the sweeps proper (what odeb_solver_ms reports)
         {
             // persistent phases: one cooperative launch per 8 sweeps
             if (B->lw_grid == 0) {
-                cudaFuncSetAttribute(k_lwt_phase, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lw_tma_smem);
+                cudaFuncSetAttribute(k_lwt_phase_t<LWT_WARPS, LWT_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lw_tma_smem);
+                cudaFuncSetAttribute(k_lwt_phase_t<LWT_SMALL_WARPS, LWT_SMALL_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lw_small_smem);
                 int occ = 0, sms = 0;
-                LCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_lwt_phase, 32 * LWT_WARPS, lw_tma_smem));
+                LCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_lwt_phase_t<LWT_WARPS, LWT_STAGES>, 32 * LWT_WARPS, lw_tma_smem));
                 LCK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, B->device));
                 B->lw_grid = occ * sms;
                 if (B->lw_grid <= 0) { set_err("k_lwt_phase does not fit an SM"); return 0; }
@@ -248,6 +250,8 @@ static int large_step(OdebBatch *B)
             { const int by_bodies = (nordered + 32 * LWT_WARPS - 1) / (32 * LWT_WARPS); if (by_bodies > grid) grid = by_bodies; }
             if (grid > B->lw_grid) grid = B->lw_grid;
             if (B->lw_maxgrid > 0 && grid > B->lw_maxgrid) grid = B->lw_maxgrid;
+            // small worlds: one block whose warps hold every tile of the largest colour (block barrier instead of the grid barrier)
+            const bool small = maxnt <= LWT_SMALL_WARPS && nordered <= 64 * 32 * LWT_SMALL_WARPS && B->lw_maxgrid == 0;
             LwPhase ph;
             for (int c = 0; c <= ODEB_CANON_COLOURS; c++) ph.tstart[c] = tstart[c];
             ph.nordered = nordered; ph.nislands = T;
@@ -265,7 +269,8 @@ static int large_step(OdebBatch *B)
                 for (int k = 0; k < nc; k++) { const int c = corder[k]; if (tstart[c + 1] > tstart[c]) ph.corder[ph.norder++] = c; }
                 ph.phase = phase;
                 void *args[4] = { (void *)&P, (void *)&D, (void *)&L, (void *)&ph };
-                LCK(cudaLaunchCooperativeKernel((const void *)k_lwt_phase, dim3(grid), dim3(32 * LWT_WARPS), args, lw_tma_smem, s));
+                if (small) LCK(cudaLaunchCooperativeKernel((const void *)k_lwt_phase_t<LWT_SMALL_WARPS, LWT_SMALL_STAGES>, dim3(1), dim3(32 * LWT_SMALL_WARPS), args, lw_small_smem, s));
+                else LCK(cudaLaunchCooperativeKernel((const void *)k_lwt_phase_t<LWT_WARPS, LWT_STAGES>, dim3(grid), dim3(32 * LWT_WARPS), args, lw_tma_smem, s));
                 B->launches++;
             }
 
