@@ -380,6 +380,33 @@ def _sample_worlds(full_scene, worlds, small_scene):
     return small_scene
 
 
+def test_full_size_pile64_batch_sampled_worlds():
+    """The north-star shape at the bench's size: 4096 worlds of a 64-body pile (boxes + spheres, ~13 islands per world, walker solver
+    k_solve6).  After 120 free-running steps (the piles have landed and are settling: several islands per world, reorders, early exits) 48
+    worlds sampled across the batch carry exactly the state, dRand seed and iteration counters the oracle computes for those worlds alone
+    (single precision: bit for bit)."""
+    W = 4096
+    sc = scenes.pile(nworlds=W, nbodies=64, vary=0.05)
+    worlds = np.unique(np.concatenate([np.arange(0, W, W // 40), [1, 2, 3, 5, 2047, 2048, 4094, 4095]]))[:48]
+    b = B.Batch(gpu_lib("single"), sc)
+    b.step(0.01, 120)
+    st, seeds = b.get_state(), b.get_seeds()
+    a = B.Batch(orc_lib("single"), _sample_worlds(sc, worlds, scenes.pile(nworlds=len(worlds), nbodies=64, vary=0.05)))
+    a.step(0.01, 120)
+    so = a.get_state()
+    for k in ("pos", "quat", "lvel", "avel"):
+        assert np.array_equal(st[k][worlds], so[k]), k
+    assert np.array_equal(seeds[worlds], a.get_seeds())
+    for j, w in enumerate(worlds):
+        assert np.array_equal(b.get_pairs(int(w)), a.get_pairs(j))
+        assert np.array_equal(b.get_contacts(int(w))[1], a.get_contacts(j)[1])
+        na, la = a.get_islands(j)
+        nb_, lb = b.get_islands(int(w))
+        assert na == nb_ and np.array_equal(la, lb)
+        assert np.array_equal(b.get_stats(int(w)), a.get_stats(j))
+    b.close()
+
+
 @pytest.mark.parametrize("prec", PRECS)
 def test_full_size_chain_batch_sampled_worlds(prec):
     """BASELINE configs[2] at its full size (65536 worlds of the 10-link chain on one GPU): 64 worlds sampled across the batch
