@@ -33,7 +33,9 @@
 #define ODEB_SOLVE6_CUH
 
 #define ODEB6_RING 4
-#define ODEB6_FYSTEPS 2
+#ifndef ODEB6_FYSTEPS
+#define ODEB6_FYSTEPS 1                    // shadow Fisher-Yates steps per trip: each costs ~2.5 % of the kernel on 64-body piles (1: 8.22, 2: 8.37, 4: 8.84 ms per step); the rest is caught up at the reorder
+#endif
 #define ODEB6_TAIL 16                      // entries behind a schedule: round-up to the ring, wrap-around copies, idle words
 #define ODEB6_DUMMY 255u                   // body-2 slot of one-body rows in k_reorder_prep's entries
 
