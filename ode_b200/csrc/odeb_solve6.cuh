@@ -158,14 +158,14 @@ __device__ unsigned long long odeb6_prof[16];
 #define ODEB6_SLOT(CUR, NXT, EK, EC, K)                                                                                  \
     {                                                                                                                    \
         const unsigned MT = EK;                                                                                          \
-        const int index = E5_ROW(MT), fi = E5_FI(MT), b1 = E5_B1(MT);                                                    \
-        const bool live = b1 != NBd;                                                                                     \
-        const int bs = side ? E5_B2(MT) : b1;                                                                            \
+        const int index = E5_ROW(MT), fi = E5_FI(MT);                                                                    \
+        const bool live = E5_LIVE(MT);                                                                                   \
+        const int bs = (int)((MT >> bsh) & 0xffu);                      /* this lane's body: bits 15.. (side 0) or 23.. (side 1) */ \
         const Real old_lambda = lam[index * WPW];                                                                        \
         const Real lam_fi = lam[fi * WPW];                                                                               \
         Real4 fa = CF5(bs, 0), fb = CF5(bs, 1);                                                                          \
         {                                                                                                                \
-            if (E5_B1(EC) != NBd) {                                                                                      \
+            if (E5_LIVE(EC)) {                                                                                           \
                 const char *src = rec_base + (size_t)E5_ROW(EC) * (sizeof(Real) * 32);                                   \
                 const unsigned dst = ring_addr + (unsigned)((((K) + ODEB6_RING - 1) & (ODEB6_RING - 1)) * CH * 32 * 16); \
                 _Pragma("unroll") for (int c = 0; c < CH; c++) cp_async16(dst + c * 32 * 16, src + c * 16);             \
@@ -263,7 +263,8 @@ __global__ void __launch_bounds__(32, 1) k_solve6_t(const __grid_constant__ DevP
     unsigned *sord = (unsigned *)p + wl;                          // P > 1: rows in schedule order
     unsigned short *sinfo = (unsigned short *)(p + (size_t)SR6 * WPW * sizeof(unsigned)) + wl;   // P > 1: slot s = (first entry << 4) | rows
     const unsigned below = (1u << lane) - 1u;
-    const unsigned IDLE = ((unsigned)NBd << 15) | ((unsigned)NBd << 23);
+    const unsigned IDLE = ((unsigned)NBd << 15) | ((unsigned)NBd << 23) | E5_IDLE_BIT;
+    const int bsh = side ? 23 : 15;
     const int IDLE_AT = SR6 + 8;                                  // [IDLE_AT, IDLE_AT + 8): idle for good (finished worlds park here)
 
     unsigned seed = D.seed[w];
@@ -504,7 +505,7 @@ __global__ void __launch_bounds__(32, 1) k_solve6_t(const __grid_constant__ DevP
                     const unsigned pe[3] = { e0, e1, e2 };
 #pragma unroll
                     for (int k = 0; k < ODEB6_RING - 1; k++) {
-                        if (E5_B1(pe[k]) != NBd) {
+                        if (E5_LIVE(pe[k])) {
                             const char *src = rec_base + (size_t)E5_ROW(pe[k]) * (sizeof(Real) * 32);
                             const unsigned dst = ring_addr + (unsigned)(k * CH * 32 * 16);
 #pragma unroll
