@@ -163,7 +163,10 @@ __device__ unsigned long long odeb6_prof[16];
         const int bs = (int)((MT >> bsh) & 0xffu);                      /* this lane's body: bits 15.. (side 0) or 23.. (side 1) */ \
         const Real old_lambda = lam[index * WPW];                                                                        \
         const Real lam_fi = lam[fi * WPW];                                                                               \
-        Real4 fa = CF5(bs, 0), fb = CF5(bs, 1);                                                                          \
+        /* CF5(bs, 0) / CF5(bs, 1) by byte offset: vector 1 is vector 0's slot with one bit flipped */                     \
+        const unsigned cfo = ((unsigned)bs * (2u * WPW) + (((unsigned)bs & 1u) * WPW)) * (unsigned)sizeof(Real4);       \
+        Real4 *const cfa = (Real4 *)((char *)cf + cfo), *const cfb = (Real4 *)((char *)cf + (cfo ^ (WPW * (unsigned)sizeof(Real4)))); \
+        Real4 fa = *cfa, fb = *cfb;                                                                                      \
         {                                                                                                                \
             if (E5_LIVE(EC)) {                                                                                           \
                 const char *src = rec_base + (size_t)E5_ROW(EC) * (sizeof(Real) * 32);                                   \
@@ -205,7 +208,7 @@ __device__ unsigned long long odeb6_prof[16];
         }                                                                                                                \
         if (live) {                                                                                                      \
             if (side == 0) lam[index * WPW] = new_lambda;                                                                \
-            CF5(bs, 0) = fa; CF5(bs, 1) = fb;                                                                            \
+            *cfa = fa; *cfb = fb;                                                                                       \
         }                                                                                                                \
         __syncwarp();                                                                                                    \
     }
