@@ -39,8 +39,6 @@
 #define E5_FI(e) (E5_ROW(e) - (int)(((e) >> 12) & 7u))     // friction-index row = row - delta, delta 0 = none (fi == row)
 #define E5_B1(e) ((int)(((e) >> 15) & 0xffu))
 #define E5_B2(e) ((int)(((e) >> 23) & 0xffu))
-#define E5_IDLE_BIT 0x80000000u                           // set in idle entries only (real entries end at bit 30): liveness is a sign test
-#define E5_LIVE(e) ((int)(e) >= 0)
 
 // shared memory per warp for a capacity of sr rows (= schedule slots) per island
 __host__ __device__ inline size_t odeb5_smem(int P, int NB, int sr)
@@ -76,21 +74,21 @@ __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefe
 // ma: entry RING-1 slots ahead (its cp.async is issued here), mf: entry FAR slots ahead (L2 prefetch).
 #define ODEB5_ROW(CUR, NXT, MT, MTN, K)                                                                                  \
     {                                                                                                                    \
-        const int index = E5_ROW(MT), fi = E5_FI(MT);                                                                    \
-        const bool live = E5_LIVE(MT);                                                                                   \
-        const int bs = (int)((MT >> bsh) & 0xffu);                      /* this lane's body: bits 15.. (side 0) or 23.. (side 1) */ \
+        const int index = E5_ROW(MT), fi = E5_FI(MT), b1 = E5_B1(MT);                                                    \
+        const bool live = b1 != NBd;                                                                                     \
+        const int bs = side ? E5_B2(MT) : b1;                                                                            \
         const Real old_lambda = lam[index * WPW];                                                                        \
         const Real lam_fi = lam[fi * WPW];                                                                               \
         Real4 fa = CF5(bs, 0), fb = CF5(bs, 1);                                                                          \
         MTN = mp[((K) + 1) * 16];                                                                                        \
         {                                                                                                                \
-            if (E5_LIVE(ma)) {                                                                                           \
+            if (E5_B1(ma) != NBd) {                                                                                      \
                 const char *src = rec_base + (size_t)E5_ROW(ma) * (sizeof(Real) * 32);                                   \
                 const unsigned dst = ring_addr + (unsigned)((((K) + ODEB5_RING - 1) & (ODEB5_RING - 1)) * CH * 32 * 16); \
                 _Pragma("unroll") for (int c = 0; c < CH; c++) cp_async16(dst + c * 32 * 16, src + c * 16);             \
             }                                                                                                            \
             cp_async_commit();                                                                                           \
-            if (E5_LIVE(mf)) prefetch_l2(rec_base + (size_t)E5_ROW(mf) * (sizeof(Real) * 32));                      \
+            if (E5_B1(mf) != NBd) prefetch_l2(rec_base + (size_t)E5_ROW(mf) * (sizeof(Real) * 32));                      \
         }                                                                                                                \
         ma = mp[((K) + ODEB5_RING) * 16];                               /* schedule entries for the next slot's copies */ \
         mf = mp[((K) + 1 + ODEB5_FAR) * 16];                                                                             \
@@ -167,8 +165,7 @@ __global__ void __launch_bounds__(32) k_solve5_t(const __grid_constant__ DevPara
     unsigned *meta = (unsigned *)p; p += (size_t)(SR5 + ODEB5_PAD) * 16 * sizeof(unsigned);     // meta[slot * 16 + col]
     unsigned *order = (unsigned *)p + wl; p += (size_t)SR5 * WPW * sizeof(unsigned);            // order[i * WPW]
     unsigned short *last = (unsigned short *)p + wl;                                            // last[body * WPW]
-    const unsigned IDLE = ((unsigned)NBd << 15) | ((unsigned)NBd << 23) | E5_IDLE_BIT;
-    const int bsh = side ? 23 : 15;
+    const unsigned IDLE = ((unsigned)NBd << 15) | ((unsigned)NBd << 23);
 
     unsigned seed = D.seed[w];
     unsigned st0 = 0, st1 = 0, st2 = 0, st3 = 0;
@@ -318,7 +315,7 @@ __global__ void __launch_bounds__(32) k_solve5_t(const __grid_constant__ DevPara
 #pragma unroll
             for (int k = 0; k < ODEB5_RING - 1; k++) {
                 const unsigned mk = mp[k * 16];
-                if (E5_LIVE(mk)) {
+                if (E5_B1(mk) != NBd) {
                     const char *src = rec_base + (size_t)E5_ROW(mk) * (sizeof(Real) * 32);
                     const unsigned dst = ring_addr + (unsigned)(k * CH * 32 * 16);
 #pragma unroll
@@ -328,7 +325,7 @@ __global__ void __launch_bounds__(32) k_solve5_t(const __grid_constant__ DevPara
             }
             for (int k = ODEB5_RING - 1; k < ODEB5_FAR; k++) {
                 const unsigned mk = mp[k * 16];
-                if (E5_LIVE(mk)) prefetch_l2(rec_base + (size_t)E5_ROW(mk) * (sizeof(Real) * 32));
+                if (E5_B1(mk) != NBd) prefetch_l2(rec_base + (size_t)E5_ROW(mk) * (sizeof(Real) * 32));
             }
             cp_async_wait<ODEB5_RING - 2>();
             HalfRegs r0, r1;

@@ -32,6 +32,10 @@
 #ifndef ODEB_SOLVE6_CUH
 #define ODEB_SOLVE6_CUH
 
+#ifndef E5_LIVE                             // idle schedule entries carry a sign bit (real entries end at bit 30): liveness is a sign test
+#define E5_IDLE_BIT 0x80000000u
+#define E5_LIVE(e) ((int)(e) >= 0)
+#endif
 #define ODEB6_RING 4
 #ifndef ODEB6_FYSTEPS
 #define ODEB6_FYSTEPS 1                    // shadow Fisher-Yates steps per trip: each costs ~2.5 % of the kernel on 64-body piles (1: 8.22, 2: 8.37, 4: 8.84 ms per step); the rest is caught up at the reorder
