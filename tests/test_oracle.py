@@ -386,3 +386,67 @@ def test_cylinder_box_collider_vs_reference(prec):
         assert not bad, (s, bad[:4])
         ncb += sum(1 for w in range(sc.nworlds) for p in b.get_contacts(w)[1] if {types[p[0]], types[p[1]]} == {1, 3})
     assert ncb > 3000
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# canonical mode of the oracle (ODEB_MODE_CANONICAL, include/ode_b200.h): the large-world path's CPU restatement
+@pytest.mark.parametrize("prec", PRECS)
+def test_canonical_mode_of_the_oracle_vs_compiled_reference(prec):
+    """The canonical order only changes the order in which rows are relaxed.  Teacher-forced from the compiled reference's state: pair set,
+    per-pair contact counts, contact geometry and island partition of a step are the reference's, bit for bit; the body state agrees with
+    the reference to the accuracy of a converged SOR solve (order effects only); two runs of the mode are identical."""
+    ref = ref_lib(prec)
+    if ref is None:
+        pytest.skip("oracle/_ref not built here")
+    for mk, h, targets in ((lambda: scenes.wall(10, 6), 0.05, (0, 8, 20)), (lambda: scenes.pile(nbodies=64), 0.01, (0, 40, 80)),
+                           (lambda: scenes.chain(1), 0.05, (0, 30))):
+        sc = mk()
+        a = B.Batch(ref, sc)
+        b, c = B.Batch(orc_lib(prec), sc), B.Batch(orc_lib(prec), sc)
+        b.set_solver_mode(1)
+        c.set_solver_mode(1)
+        done = 0
+        for target in targets:
+            a.step(h, target - done)
+            done = target
+            st = a.get_state()
+            for x in (a, b, c):
+                x.set_state(**st)
+            b.set_seeds(a.get_seeds())
+            c.set_seeds(a.get_seeds())
+            a.step(h)
+            b.step(h)
+            c.step(h)
+            done += 1
+            bad = compare_step(a, b, 1, what=("pairs", "contacts", "islands"))
+            assert not bad, (sc.nbody, target, bad)
+            bad = compare_step(b, c, 1)
+            assert not bad, (sc.nbody, target, bad)
+            sa, sb = a.get_state(), b.get_state()
+            for k in ("pos", "lvel"):
+                assert np.abs(sa[k].astype(np.float64) - sb[k]).max() < 0.05, (sc.nbody, target, k)
+
+
+def test_canonical_colour_order_helpers():
+    """odeb_canon_key through the C-ABI of the product library == the header's inline function the oracle uses (spot values), and the
+    per-phase colour ranks are a permutation that changes with the phase."""
+    lib = C.CDLL(os.path.join(ROOT, "ode_b200", "libode_b200_single.so"))
+    lib.odeb_canon_key.restype = C.c_uint32
+    lib.odeb_canon_key.argtypes = [C.c_uint32] * 4
+
+    def key(seed, island, phase, row):
+        x = (seed ^ (island * 0x9E3779B9) ^ (phase * 0x85EBCA6B) ^ (row * 0xC2B2AE35)) & 0xffffffff
+        x ^= x >> 16
+        x = (x * 0x85EBCA6B) & 0xffffffff
+        x ^= x >> 13
+        x = (x * 0xC2B2AE35) & 0xffffffff
+        x ^= x >> 16
+        return x
+    for args in ((1, 0, 0, 0), (12345, 3, 2, 77), (0xdeadbeef, 0xffffffff, 4, 255)):
+        assert lib.odeb_canon_key(*args) == key(*args)
+    orders = []
+    for phase in range(5):
+        ks = sorted((key(7, 0xffffffff, phase, c), c) for c in range(10))
+        orders.append(tuple(c for _, c in ks))
+        assert sorted(orders[-1]) == list(range(10))
+    assert len(set(orders)) > 1
