@@ -331,6 +331,11 @@ def other_configs(slib, device, with_cpu=True, t_budget_end=None):
         r = timed(b, 0.05, 6, sc.nbody)
         if "roofline" in r:
             r["roofline"]["bound"] = "latency (grid barrier between colours + the 12-row chain of a contact group), then hbm"
+            # static: dram__bytes_read + write of one k_lwt_phase launch (ncu --set full on this workload, profiles/r2_ncu_summary.txt) x the launches of a step
+            r["roofline"]["traffic"] = 5 * (2208631000 + 101905000)
+            r["roofline"]["traffic_source"] = "static: ncu --set full capture of one phase launch on this workload (profiles/r2_ncu_summary.txt) x 5 phases; not measured in this run"
+            if r["roofline"].get("launch_ms"):
+                r["roofline"]["dram_frac"] = round(r["roofline"]["traffic"] / (r["roofline"]["launch_ms"] * 1e-3) / 1e9 / r["roofline"]["peak"], 4)
             r["roofline"]["limiter"] = ("one persistent launch per 8 sweeps, ~10 colours per sweep separated by grid barriers: ncu (profiles/r2_ncu_summary.txt) "
                                         "shows 43 % of the warp samples at the barrier and DRAM at ~40 % of peak; real DRAM traffic per row-sweep is the compact "
                                         "84-byte tile record, the algorithmic figure counts SURVEY's 136 bytes")
