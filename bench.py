@@ -337,7 +337,7 @@ def other_configs(slib, device, with_cpu=True, t_budget_end=None):
             if r["roofline"].get("launch_ms"):
                 r["roofline"]["dram_frac"] = round(r["roofline"]["traffic"] / (r["roofline"]["launch_ms"] * 1e-3) / 1e9 / r["roofline"]["peak"], 4)
             r["roofline"]["limiter"] = ("one persistent launch per 8 sweeps, ~10 colours per sweep separated by grid barriers: ncu (profiles/r2_ncu_summary.txt) "
-                                        "shows 43 % of the warp samples at the barrier and DRAM at ~40 % of peak; real DRAM traffic per row-sweep is the compact "
+                                        "shows 48 % of the warp samples at the barrier and DRAM at ~30 % of peak; real DRAM traffic per row-sweep is the compact "
                                         "84-byte tile record, the algorithmic figure counts SURVEY's 136 bytes")
         r["workload"] = "1 world x %d bodies (500 x 200 brick wall + cannon ball), dSweepAndPruneSpace semantics, dt=0.05 (BASELINE configs[4])" % sc.nbody
         b.close()
