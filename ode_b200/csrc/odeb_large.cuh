@@ -744,7 +744,8 @@ __global__ void __launch_bounds__(32 * WARPS) k_lwt_phase_t(const __grid_constan
     if (L.counters[LWC_TERM] || L.counters[LWC_NACTIVE] == 0 || L.counters[LWC_ITER] != 8 * ph.phase) return;
     unsigned *gbar = (unsigned *)&L.counters[LWC_PBAR + ph.phase];
     unsigned gtarget = 0;
-    unsigned ri = 0, rc = 0;                                       // tile rows requested / consumed by this warp so far (ring position and mbarrier parity)
+    unsigned ri = 0, rc = 0;                                       // tile rows requested / consumed by this warp so far
+    unsigned is = 0, cs = 0, cpar = 0;                             // ring stage of the next request / of the next row consumed, and that stage's mbarrier parity
     // the warp's pending item (sweep, position in the colour order, tile) and the state of the tile that was begun for it
     int it_sw = 0, it_ci = ph.norder, it_tile = 0;
     for (int ci = 0; ci < ph.norder; ci++) { const int c = ph.corder[ci]; if (ph.tstart[c] + gw < ph.tstart[c + 1]) { it_ci = ci; it_tile = ph.tstart[c] + gw; break; } }
@@ -775,13 +776,15 @@ __global__ void __launch_bounds__(32 * WARPS) k_lwt_phase_t(const __grid_constan
         }
         issued = height < STAGES - 1 ? height : STAGES - 1;
         if (lane == 0) {
+            unsigned s = is;
             for (int k = 0; k < issued; k++) {
-                const unsigned s = (ri + k) % STAGES;
                 lwt_mbar_expect_tx(bar0 + 8 * s, RB + LB);
                 lwt_bulk_g2s(ring0 + s * LWT_STAGE_BYTES, rec + (size_t)k * LWT_ROW_BYTES, RB + LB, bar0 + 8 * s);
+                s = s + 1 == STAGES ? 0 : s + 1;
             }
         }
         ri += issued;
+        is = (is + issued) % STAGES;
     };
     if (any_items) tile_begin(it_tile);
     unsigned iteration = (unsigned)L.counters[LWC_ITER], extra = (unsigned)L.counters[LWC_EXTRA];
@@ -804,8 +807,8 @@ __global__ void __launch_bounds__(32 * WARPS) k_lwt_phase_t(const __grid_constan
                 unsigned char *lamp = rec + LWT_LAM_OFS + lane * sizeof(Real);
                 int free_k = -1; Real free_lambda = 0;
                 for (int k = 0; k < height; k++) {
-                    const unsigned s = rc % STAGES;
-                    lwt_mbar_wait(bar0 + 8 * s, (rc / STAGES) & 1u);
+                    const unsigned s = cs;
+                    lwt_mbar_wait(bar0 + 8 * s, cpar);
                     if (run && k < sz) {
                         const Real4 *st = (const Real4 *)(ring + (size_t)s * LWT_STAGE_BYTES) + lane;
                         const Real4 c0 = st[0], c1 = st[32], c2 = st[64], c3 = st[96], c4 = st[128];
@@ -813,14 +816,16 @@ __global__ void __launch_bounds__(32 * WARPS) k_lwt_phase_t(const __grid_constan
                         LWT_ROW(c0, c1, c2, c3, c4, old_lambda, k)
                     }
                     rc++;
+                    if (++cs == STAGES) { cs = 0; cpar ^= 1u; }
                     __syncwarp();
                     if (issued < height) {
                         if (lane == 0) {
-                            const unsigned sn = ri % STAGES;
+                            const unsigned sn = is;
                             lwt_mbar_expect_tx(bar0 + 8 * sn, RB + LB);
                             lwt_bulk_g2s(ring0 + sn * LWT_STAGE_BYTES, rec + (size_t)issued * LWT_ROW_BYTES, RB + LB, bar0 + 8 * sn);
                         }
                         ri++; issued++;
+                        is = is + 1 == STAGES ? 0 : is + 1;
                     }
                 }
                 if (run) {
@@ -887,7 +892,7 @@ __global__ void __launch_bounds__(32 * WARPS) k_lwt_phase_t(const __grid_constan
         if (__ldcg(&L.counters[LWC_NACTIVE]) == 0) break;
     }
     // bulk copies of a tile that was begun for a sweep that does not take place must land before the block retires
-    while (rc < ri) { lwt_mbar_wait(bar0 + 8 * (rc % STAGES), (rc / STAGES) & 1u); rc++; }
+    while (rc < ri) { lwt_mbar_wait(bar0 + 8 * cs, cpar); rc++; if (++cs == STAGES) { cs = 0; cpar ^= 1u; } }
     if (gtid == 0) { L.counters[LWC_ITER] = (int)iteration; L.counters[LWC_EXTRA] = (int)extra; L.counters[LWC_TERM] = terminated; }
 }
 
